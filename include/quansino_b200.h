@@ -1,0 +1,170 @@
+/* quansino_b200 -- C ABI of the B200-native batched Monte Carlo hot path.
+ *
+ * This header is the drop-in boundary for ONE path of quansino (v0.1.3): the inner body of
+ * `MonteCarlo.step` (src/quansino/mc/core.py:353-384) -- select move -> propose -> energy -> criteria ->
+ * save / revert -- executed for MANY independent replicas and a whole run of attempts per call, on one
+ * B200 (sm_100a).  quansino is pure Python and has no FFI of its own; the entry points below are what a
+ * binding for this path would call (see INTEGRATION.md for the ctypes stub), and the Python package
+ * `quansino_b200` mirrors the reference's Move / Operation / Criteria / Context / driver classes on top of
+ * exactly these calls.
+ *
+ * Conventions
+ *  - plain C, no exceptions across the boundary: every function returns 0 on success or a negative
+ *    QMC_ERR_* code; `qmc_last_error()` returns a thread-local message.
+ *  - every pointer inside `qmc_batch_t`, `qmc_move_t.labels` and `qmc_trace_t` is a DEVICE pointer owned
+ *    by the caller (the Python side allocates them as torch CUDA tensors); `stream` is a `cudaStream_t`
+ *    passed as `void *` (NULL = legacy default stream).  The `*_host` entry points take HOST pointers
+ *    and do their own transfers.
+ *  - units are ASE's: eV, Angstrom, amu, Kelvin; time in ASE units (fs * 0.0982269...).
+ *  - replicas are independent; replica r of this batch is GLOBAL replica `replica_offset + r` for the
+ *    random stream, so results do not depend on how replicas are sharded over GPUs.
+ *  - cells must be orthorhombic (diagonal); each periodic edge must be >= the neighbour cutoff.
+ *
+ * Random stream (shared with the oracle, DESIGN.md "Random stream"): Philox4x32-10,
+ * key = seed, counter = (attempt_lo, attempt_hi, global_replica, block); block 0 = (u_select, u_label),
+ * 1 = (op0, op1), 2 = (op2, u_accept), 3 = (u_coin, u_swap), 16 + p = Box-Muller pair p of the momenta.
+ */
+#ifndef QUANSINO_B200_H
+#define QUANSINO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QMC_ABI_VERSION 1
+#define QMC_MAX_MOVES 4
+
+enum qmc_error {
+    QMC_OK = 0,
+    QMC_ERR_INVALID = -1,     /* bad argument (ValueError on the Python side) */
+    QMC_ERR_UNSUPPORTED = -2, /* feature the GPU path refuses (NotImplementedError), never a silent fallback */
+    QMC_ERR_CUDA = -3,        /* CUDA runtime error; message in qmc_last_error() */
+    QMC_ERR_NO_DEVICE = -4    /* no CUDA device: there is NO CPU fallback */
+};
+
+/* per-replica status bits written by the kernels into qmc_batch_t.status */
+enum qmc_status {
+    QMC_STATUS_EXP_OVERFLOW = 1, /* criteria exponent > 709.78: the reference raises OverflowError (mc/criteria.py:108) */
+    QMC_STATUS_CAPACITY = 2,     /* insertion beyond n_max */
+    QMC_STATUS_CELL_TOO_SMALL = 4, /* a periodic edge shrank below the neighbour cutoff */
+    QMC_STATUS_LIST_OVERFLOW = 8
+};
+
+/* replaces ase.calculators.emt.EMT / ase.calculators.lj.LennardJones behind
+ * `atoms.get_potential_energy()` (call sites: src/quansino/mc/criteria.py:104-106,131-135,161-163,240-242)
+ * and `atoms.get_forces()` (src/quansino/integrators/displacement.py:63,77) */
+enum qmc_potential_kind { QMC_POT_EMT = 0, QMC_POT_LJ = 1 };
+typedef struct qmc_potential {
+    int32_t kind;
+    int32_t _pad;
+    /* EMT, single species, as EMT.initialize derives them (eV, Angstrom) */
+    double E0, s0, V0, eta2, kappa, lambda, beta, rc, rc_list, acut, gamma1, gamma2;
+    /* Lennard-Jones: sigma, epsilon, cutoff rc, shift e0 = 4 eps ((sigma/rc)^12 - (sigma/rc)^6) */
+    double sigma, epsilon, lj_rc, lj_e0;
+} qmc_potential_t;
+
+/* replaces one MoveStorage (src/quansino/utils/moves.py:19-60) with its Move and Operation:
+ * DisplacementMove + Ball/Box/Sphere (moves/displacement.py:143-171, operations/displacement.py:67-153),
+ * CellMove + IsotropicDeformation (moves/cell.py:57-94, operations/cell.py:153-169),
+ * ExchangeMove + Translation (moves/exchange.py:134-176, operations/displacement.py:170-175),
+ * HamiltonianDisplacementMove + Verlet (moves/displacement.py:307-345, integrators/displacement.py:52-81) */
+enum qmc_move_type { QMC_MOVE_DISPLACEMENT = 0, QMC_MOVE_CELL = 1, QMC_MOVE_EXCHANGE = 2, QMC_MOVE_HMC = 3 };
+enum qmc_op { QMC_OP_BALL = 0, QMC_OP_BOX = 1, QMC_OP_SPHERE = 2, QMC_OP_TRANSLATION = 3, QMC_OP_ISOTROPIC = 4, QMC_OP_VERLET = 5 };
+#define QMC_LABEL_NONE INT32_MIN
+typedef struct qmc_move {
+    int32_t type;          /* qmc_move_type */
+    int32_t op;            /* qmc_op */
+    double step;           /* Ball/Box/Sphere step_size, IsotropicDeformation max_value */
+    double probability;    /* MoveStorage.probability (normalised by the library like mc/core.py:344-347) */
+    double bias_insert;    /* ExchangeMove.bias_towards_insert */
+    double dt;             /* Verlet dt in ASE time units */
+    int32_t n_steps;       /* Verlet max_steps */
+    int32_t default_label; /* DisplacementMove.default_label; QMC_LABEL_NONE = None */
+    int32_t *labels;       /* device [n_replicas][n_max]; NULL = arange(n_atoms) and no exchange moves */
+} qmc_move_t;
+
+/* replaces Atoms + Context for R replicas (src/quansino/mc/contexts.py:20-385): the device-resident state */
+typedef struct qmc_batch {
+    int32_t n_replicas;     /* replicas held by THIS device */
+    int32_t n_max;          /* per-replica atom capacity (row stride of the per-atom arrays) */
+    int32_t replica_offset; /* global id of local replica 0 */
+    int32_t pbc[3];
+    double *pos;            /* [R][3][n_max]  x-row, y-row, z-row per replica */
+    double *cell;           /* [R][9] row-major, diagonal */
+    int32_t *n_atoms;       /* [R] */
+    double *energy;         /* [R] last_potential_energy */
+    double *temperature;    /* [R] Kelvin (per replica so that parallel tempering only permutes this array) */
+    double *sigma1;         /* [R][n_max] EMT cache: sigma_1 per atom (unnormalised) */
+    double *eatom;          /* [R][n_max] EMT cache: embedding energy per atom, E_c + E_AS(sigma) - E0 */
+    double *momenta;        /* [R][3][n_max] or NULL */
+    double *kinetic;        /* [R] last_kinetic_energy or NULL */
+    int32_t *n_exchange;    /* [R] number_of_exchange_particles or NULL */
+    int64_t *counters;      /* [R][QMC_MAX_MOVES][3] attempted, accepted, failed -- accumulated */
+    int32_t *status;        /* [R] qmc_status bits, OR-ed */
+    int64_t *pair_evals;    /* [R] pair evaluations performed by the sweeps, accumulated, or NULL */
+    double mass;            /* amu, single species */
+    double pressure;        /* eV / A^3 */
+    double chemical_potential;
+    double accessible_volume;
+    double exchange_mass;   /* amu */
+    double exchange_pos[3];
+} qmc_batch_t;
+
+/* optional per-attempt trace, device [R][n_attempts] each, any pointer may be NULL */
+typedef struct qmc_trace {
+    int8_t *move;      /* selected move index */
+    int8_t *accepted;  /* 1 / 0 / -1 (move failed, the reference's None) */
+    double *energy;    /* last_potential_energy after the attempt */
+    double *delta;     /* energy difference seen by the criteria */
+    int32_t *moved;    /* atom index moved / inserted / deleted, -1 otherwise */
+} qmc_trace_t;
+
+int qmc_abi_version(void);
+const char *qmc_last_error(void);
+/* number of CUDA devices, or QMC_ERR_NO_DEVICE */
+int qmc_device_count(void);
+
+/* bytes of dynamic shared memory one replica (one warp) of the sweep kernel needs for `n_max` atoms */
+int64_t qmc_sweep_smem_per_replica(const qmc_potential_t *pot, int32_t n_max);
+
+/* validate_simulation (src/quansino/mc/canonical.py:114-122, mc/core.py:221-229): full energy of every
+ * replica; fills energy[], sigma1[], eatom[].  `pair_count` (device [R] int64 or NULL) receives the number
+ * of (atom, neighbour image) pairs evaluated. */
+int qmc_energy_full(const qmc_potential_t *pot, const qmc_batch_t *batch, int64_t *pair_count, void *stream);
+
+/* full energy AND forces (device [R][3][n_max]) -- `atoms.get_forces()` */
+int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double *forces, void *stream);
+
+/* n_attempts cycles of MonteCarlo.step (src/quansino/mc/core.py:353-384) for every replica: move types
+ * displacement / cell / exchange; state committed in place. */
+int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move_t *moves, int32_t n_moves,
+              uint64_t seed, uint64_t attempt_base, int32_t n_attempts, const qmc_trace_t *trace, void *stream);
+
+/* n_attempts Hamiltonian attempts (src/quansino/moves/displacement.py:307-345 + mc/criteria.py:117-140) */
+int qmc_hmc(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move_t *move, uint64_t seed,
+            uint64_t attempt_base, int32_t n_attempts, const qmc_trace_t *trace, void *workspace,
+            int64_t workspace_bytes, void *stream);
+int64_t qmc_hmc_workspace_bytes(const qmc_batch_t *batch);
+
+/* parallel tempering between temperature-adjacent replicas (no counterpart in the reference):
+ * `energies_all` / `temperatures_all` are device [R_global] arrays every rank holds after the all-gather;
+ * the kernel evaluates the swap decisions of round `round` (even / odd pairs) from the shared stream and
+ * permutes the TEMPERATURES; `accepted` (device [R_global] int8 or NULL) marks swapped lower partners. */
+int qmc_pt_swap(double *temperatures_all, const double *energies_all, int32_t n_global, uint64_t seed,
+                uint64_t round, int8_t *accepted, void *stream);
+
+/* measured-FP64-peak microbenchmark used by bench.py for the roofline denominator: runs a register-resident
+ * DFMA loop and returns achieved FLOP/s in *flops (2 flop per DFMA). */
+int qmc_fp64_peak(double *flops, void *stream);
+
+/* host-buffer convenience: upload `batch_host` (same struct, HOST pointers), prime, run, download. */
+int qmc_sweep_host(const qmc_potential_t *pot, const qmc_batch_t *batch_host, const qmc_move_t *moves_host,
+                   int32_t n_moves, uint64_t seed, uint64_t attempt_base, int32_t n_attempts,
+                   const qmc_trace_t *trace_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,631 @@
+/* CPU oracle for the batched Monte Carlo hot path -- TEST INFRASTRUCTURE, never linked into the product.
+ * See qmc_oracle.h and oracle/__init__.py.  Every function cites the reference (quansino v0.1.3,
+ * paths relative to /root/reference) or the ASE 3.26.0 file whose published algorithm it restates.
+ *
+ * Deliberately simple: brute-force image enumeration, full-system recompute on every attempt -- exactly
+ * what `atoms.get_potential_energy()` does for the reference after any change of the atoms.
+ */
+#include "qmc_oracle.h"
+
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define KB 8.617330337217213e-05 /* ase.units.kB (CODATA 2014): _k / _e */
+#define H_PLANCK 6.626070040e-34
+#define E_CHARGE 1.6021766208e-19
+#define N_AVOGADRO 6.022140857e23
+#define TWO_PI 6.283185307179586 /* 2 * np.pi */
+
+/* ------------------------------------------------------------------------------------------------
+ * Philox4x32-10 (Salmon, Moraes, Dror, Shaw, SC'11) and the slot layout of oracle/philox.py
+ * ---------------------------------------------------------------------------------------------- */
+void qo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void qo_uniform_pair(uint64_t seed, uint64_t attempt, uint32_t replica, uint32_t block, double out[2]) {
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t ctr[4] = {(uint32_t)attempt, (uint32_t)(attempt >> 32), replica, block};
+    uint32_t w[4];
+    qo_philox4x32_10(ctr, key, w);
+    out[0] = ((double)(w[0] >> 5) * 67108864.0 + (double)(w[1] >> 6)) / 9007199254740992.0;
+    out[1] = ((double)(w[2] >> 5) * 67108864.0 + (double)(w[3] >> 6)) / 9007199254740992.0;
+}
+
+double qo_normal(uint64_t seed, uint64_t attempt, uint32_t replica, uint32_t m) {
+    double u[2];
+    qo_uniform_pair(seed, attempt, replica, 16u + m / 2u, u);
+    double r = sqrt(-2.0 * log(1.0 - u[0]));
+    double t = TWO_PI * u[1];
+    return (m % 2u == 0u) ? r * cos(t) : r * sin(t);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Geometry helpers
+ * ---------------------------------------------------------------------------------------------- */
+static double det3(const double c[9]) {
+    return c[0] * (c[4] * c[8] - c[5] * c[7]) - c[1] * (c[3] * c[8] - c[5] * c[6]) + c[2] * (c[3] * c[7] - c[4] * c[6]);
+}
+
+/* |det(cell)|: Atoms.get_volume / Cell.volume.  For the orthorhombic cells of the configs this is the plain
+ * product (a*b)*c; numpy's det goes through exp(sum(log|u_kk|)) and may differ in the last ulps. */
+static double volume(const double c[9]) {
+    if (c[1] == 0 && c[2] == 0 && c[3] == 0 && c[5] == 0 && c[6] == 0 && c[7] == 0) return fabs((c[0] * c[4]) * c[8]);
+    return fabs(det3(c));
+}
+
+static void inv3(const double c[9], double inv[9]) {
+    double d = det3(c);
+    inv[0] = (c[4] * c[8] - c[5] * c[7]) / d;
+    inv[1] = (c[2] * c[7] - c[1] * c[8]) / d;
+    inv[2] = (c[1] * c[5] - c[2] * c[4]) / d;
+    inv[3] = (c[5] * c[6] - c[3] * c[8]) / d;
+    inv[4] = (c[0] * c[8] - c[2] * c[6]) / d;
+    inv[5] = (c[2] * c[3] - c[0] * c[5]) / d;
+    inv[6] = (c[3] * c[7] - c[4] * c[6]) / d;
+    inv[7] = (c[1] * c[6] - c[0] * c[7]) / d;
+    inv[8] = (c[0] * c[4] - c[1] * c[3]) / d;
+}
+
+typedef struct {
+    int nmax[3];
+    int n_off;
+    int *off;       /* [n_off][3] */
+    double *shift;  /* [n_off][3] = off @ cell */
+    int *wrap;      /* [n][3] integer cell shift of each atom (0 along non-periodic axes) */
+} images_t;
+
+/* ase/neighborlist.py (PrimitiveNeighborList.build): the number of image repeats along axis k follows from the
+ * cell height along k; atoms are wrapped only to find the offsets, never moved. */
+static int images_build(images_t *im, int n, const double *pos, const double cell[9], const int32_t pbc[3], double cutoff) {
+    memset(im, 0, sizeof(*im));
+    int any = pbc[0] || pbc[1] || pbc[2];
+    im->wrap = (int *)calloc((size_t)(n > 0 ? n : 1) * 3, sizeof(int));
+    if (!im->wrap) return -1;
+    if (any) {
+        double vol = fabs(det3(cell));
+        if (!(vol > 0)) return -1;
+        for (int k = 0; k < 3; ++k) {
+            if (!pbc[k]) continue;
+            const double *a = cell + 3 * ((k + 1) % 3), *b = cell + 3 * ((k + 2) % 3);
+            double cx = a[1] * b[2] - a[2] * b[1], cy = a[2] * b[0] - a[0] * b[2], cz = a[0] * b[1] - a[1] * b[0];
+            double height = vol / sqrt(cx * cx + cy * cy + cz * cz);
+            im->nmax[k] = (int)ceil(cutoff / height);
+        }
+        double inv[9];
+        inv3(cell, inv);
+        for (int i = 0; i < n; ++i) {
+            for (int k = 0; k < 3; ++k) {
+                if (!pbc[k]) continue;
+                /* fractional coordinate k = pos . inv[:, k] */
+                double f = pos[3 * i] * inv[k] + pos[3 * i + 1] * inv[3 + k] + pos[3 * i + 2] * inv[6 + k];
+                im->wrap[3 * i + k] = (int)floor(f);
+            }
+        }
+    }
+    im->n_off = (2 * im->nmax[0] + 1) * (2 * im->nmax[1] + 1) * (2 * im->nmax[2] + 1);
+    im->off = (int *)malloc(sizeof(int) * 3 * (size_t)im->n_off);
+    im->shift = (double *)malloc(sizeof(double) * 3 * (size_t)im->n_off);
+    if (!im->off || !im->shift) return -1;
+    int q = 0;
+    for (int a = -im->nmax[0]; a <= im->nmax[0]; ++a)
+        for (int b = -im->nmax[1]; b <= im->nmax[1]; ++b)
+            for (int c = -im->nmax[2]; c <= im->nmax[2]; ++c) {
+                im->off[3 * q] = a; im->off[3 * q + 1] = b; im->off[3 * q + 2] = c;
+                for (int x = 0; x < 3; ++x)
+                    im->shift[3 * q + x] = ((double)a * cell[x] + (double)b * cell[3 + x]) + (double)c * cell[6 + x];
+                ++q;
+            }
+    return 0;
+}
+
+static void images_free(images_t *im) {
+    free(im->off); free(im->shift); free(im->wrap);
+    memset(im, 0, sizeof(*im));
+}
+
+/* distance vector of image q of atom j seen from atom i: positions[j] + T @ cell - positions[i] with the
+ * integer offset T = off[q] + wrap[i] - wrap[j]  (ASE: positions[neighbors] + offsets @ cell - positions[a1]) */
+static inline void image_vector(const images_t *im, const double *pos, const double cell[9], int i, int j, int q, double d[3]) {
+    const int *wi = im->wrap + 3 * i, *wj = im->wrap + 3 * j;
+    int t0 = wi[0] - wj[0], t1 = wi[1] - wj[1], t2 = wi[2] - wj[2];
+    if ((t0 | t1 | t2) == 0) {
+        for (int x = 0; x < 3; ++x) d[x] = (pos[3 * j + x] + im->shift[3 * q + x]) - pos[3 * i + x];
+    } else {
+        double a = (double)(im->off[3 * q] + t0), b = (double)(im->off[3 * q + 1] + t1), c = (double)(im->off[3 * q + 2] + t2);
+        for (int x = 0; x < 3; ++x) {
+            double s = (a * cell[x] + b * cell[3 + x]) + c * cell[6 + x];
+            d[x] = (pos[3 * j + x] + s) - pos[3 * i + x];
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * ASE EMT, single species  (ase/calculators/emt.py: calculate, _get_neighbors, _calc_theta, _calc_dsigma1,
+ * _calc_dsigma2, _calc_e_c_a2, _calc_efs_a1, _calc_fs_c_a2; energies -= E0 at the end)
+ * ---------------------------------------------------------------------------------------------- */
+static int64_t emt_eval(const qo_potential_t *p, int n, const double *pos, const double cell[9], const int32_t pbc[3],
+                        double *energy, double *forces, double *sigma1_out) {
+    images_t im;
+    if (images_build(&im, n, pos, cell, pbc, p->rc_list) != 0) { images_free(&im); return -1; }
+    double *sig = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    double *deds = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    double *en = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
+    const double beta = p->beta;
+    const double inv12gamma1 = 1.0 / (12.0 * p->gamma1);
+    const double neghalfv0overgamma2 = -0.5 * p->V0 / p->gamma2;
+    int64_t npairs = 0;
+    /* pass 1: sigma1 and the pair part of E_AS */
+    for (int i = 0; i < n; ++i) {
+        double s1 = 0.0, s2 = 0.0;
+        int cnt = 0;
+        for (int j = 0; j < n; ++j)
+            for (int q = 0; q < im.n_off; ++q) {
+                if (j == i && im.off[3 * q] == 0 && im.off[3 * q + 1] == 0 && im.off[3 * q + 2] == 0) continue;
+                double d[3];
+                image_vector(&im, pos, cell, i, j, q, d);
+                double r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                if (!(r < p->rc_list)) continue; /* mask = r < self.rc_list */
+                double w = 1.0 / (1.0 + exp(p->acut * (r - p->rc)));
+                s1 += exp(-p->eta2 * (r - beta * p->s0)) * w;
+                s2 += exp(-p->kappa * (r / beta - p->s0)) * w;
+                ++cnt;
+            }
+        npairs += cnt;
+        sig[i] = s1;
+        if (cnt == 0) {
+            en[i] = -p->E0; /* no neighbours: energies[a] stays 0, then -= E0 */
+            deds[i] = 0.0;
+            continue;
+        }
+        double ds = -1.0 * log(s1 * inv12gamma1) / (beta * p->eta2);
+        double lmdsds = p->lambda * ds;
+        double expneglmdds = exp(-1.0 * lmdsds);
+        double e = p->E0 * (1.0 + lmdsds) * expneglmdds;
+        double de = -1.0 * p->E0 * p->lambda * lmdsds * expneglmdds;
+        double sixv0 = 6.0 * p->V0 * exp(-1.0 * p->kappa * ds);
+        e += sixv0;
+        de += -1.0 * p->kappa * sixv0;
+        de /= -1.0 * beta * p->eta2 * s1;
+        deds[i] = de;
+        double es_sum = neghalfv0overgamma2 * s2;
+        e += 0.5 * (es_sum + es_sum);
+        en[i] = e - p->E0;
+    }
+    double etot = 0.0;
+    for (int i = 0; i < n; ++i) etot += en[i];
+    if (energy) *energy = etot;
+    if (sigma1_out) memcpy(sigma1_out, sig, sizeof(double) * (size_t)n);
+    if (forces) {
+        for (int i = 0; i < n; ++i) {
+            double f[3] = {0, 0, 0};
+            for (int j = 0; j < n; ++j)
+                for (int q = 0; q < im.n_off; ++q) {
+                    if (j == i && im.off[3 * q] == 0 && im.off[3 * q + 1] == 0 && im.off[3 * q + 2] == 0) continue;
+                    double d[3];
+                    image_vector(&im, pos, cell, i, j, q, d);
+                    double r = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+                    if (!(r < p->rc_list)) continue;
+                    double w = 1.0 / (1.0 + exp(p->acut * (r - p->rc)));
+                    double dwdroverw = p->acut * (w - 1.0);
+                    double ds1 = exp(-p->eta2 * (r - beta * p->s0)) * w;
+                    double ds2 = exp(-p->kappa * (r / beta - p->s0)) * w;
+                    double invr = 1.0 / r;
+                    double es = neghalfv0overgamma2 * ds2;
+                    double dedr_pair = es * (dwdroverw - p->kappa / beta);
+                    double dds1dr = ds1 * (dwdroverw - p->eta2);
+                    double g = ((dedr_pair + dedr_pair) + (deds[i] * dds1dr + deds[j] * dds1dr)) * invr;
+                    f[0] += g * d[0]; f[1] += g * d[1]; f[2] += g * d[2];
+                }
+            forces[3 * i] = f[0]; forces[3 * i + 1] = f[1]; forces[3 * i + 2] = f[2];
+        }
+    }
+    free(sig); free(deds); free(en);
+    images_free(&im);
+    return npairs;
+}
+
+/* ASE LennardJones.calculate, smooth=False (ase/calculators/lj.py) */
+static int64_t lj_eval(const qo_potential_t *p, int n, const double *pos, const double cell[9], const int32_t pbc[3],
+                       double *energy, double *forces) {
+    images_t im;
+    if (images_build(&im, n, pos, cell, pbc, p->lj_rc) != 0) { images_free(&im); return -1; }
+    const double rc2 = p->lj_rc * p->lj_rc, s2 = p->sigma * p->sigma;
+    int64_t npairs = 0;
+    double etot = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double e = 0.0, f[3] = {0, 0, 0};
+        for (int j = 0; j < n; ++j)
+            for (int q = 0; q < im.n_off; ++q) {
+                if (j == i && im.off[3 * q] == 0 && im.off[3 * q + 1] == 0 && im.off[3 * q + 2] == 0) continue;
+                double d[3];
+                image_vector(&im, pos, cell, i, j, q, d);
+                double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+                if (r2 > rc2) continue; /* c6[r2 > rc**2] = 0 */
+                double c6 = (s2 / r2) * (s2 / r2) * (s2 / r2);
+                double c12 = c6 * c6;
+                e += 4 * p->epsilon * (c12 - c6) - p->lj_e0;
+                if (forces) {
+                    double g = -24 * p->epsilon * (2 * c12 - c6) / r2;
+                    f[0] += g * d[0]; f[1] += g * d[1]; f[2] += g * d[2];
+                }
+                ++npairs;
+            }
+        etot += 0.5 * e;
+        if (forces) { forces[3 * i] = f[0]; forces[3 * i + 1] = f[1]; forces[3 * i + 2] = f[2]; }
+    }
+    if (energy) *energy = etot;
+    images_free(&im);
+    return npairs;
+}
+
+int64_t qo_energy(const qo_potential_t *pot, int32_t n, const double *pos, const double *cell, const int32_t *pbc,
+                  double *energy, double *forces, double *sigma1) {
+    if (pot->kind == QO_POT_EMT) return emt_eval(pot, n, pos, cell, pbc, energy, forces, sigma1);
+    if (pot->kind == QO_POT_LJ) return lj_eval(pot, n, pos, cell, pbc, energy, forces);
+    return -1;
+}
+
+/* neighbour images of atom i inside the list cutoff; marks distinct neighbour atoms in seen[] */
+static int count_neighbours(const qo_potential_t *pot, int n, const double *pos, const double cell[9], const int32_t pbc[3],
+                            int i, char *seen) {
+    double cutoff = pot->kind == QO_POT_EMT ? pot->rc_list : pot->lj_rc;
+    images_t im;
+    if (images_build(&im, n, pos, cell, pbc, cutoff) != 0) { images_free(&im); return 0; }
+    int cnt = 0;
+    for (int j = 0; j < n; ++j)
+        for (int q = 0; q < im.n_off; ++q) {
+            if (j == i && im.off[3 * q] == 0 && im.off[3 * q + 1] == 0 && im.off[3 * q + 2] == 0) continue;
+            double d[3];
+            image_vector(&im, pos, cell, i, j, q, d);
+            double r2 = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+            int in = pot->kind == QO_POT_EMT ? (sqrt(r2) < cutoff) : !(r2 > cutoff * cutoff);
+            if (in) { ++cnt; if (seen) seen[j] = 1; }
+        }
+    images_free(&im);
+    return cnt;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Criteria (src/quansino/mc/criteria.py)
+ * ---------------------------------------------------------------------------------------------- */
+double qo_debroglie_wavelength(double mass_amu, double temperature) {
+    /* mc/criteria.py:260-266, evaluated left to right like the Python expression */
+    double denom = 2 * 3.141592653589793 * mass_amu * KB * temperature / N_AVOGADRO * 1e-3 * E_CHARGE;
+    return sqrt(H_PLANCK * H_PLANCK / denom) * 1e10;
+}
+
+/* returns criteria * prefactor of GrandCanonicalCriteria.evaluate (mc/criteria.py:243-278); sets *overflow */
+static double gc_probability(double delta_e, int particle_delta, int n_ex, double acc_volume, double mass, double temperature,
+                             double mu, int *overflow) {
+    double vol = pow(acc_volume, (double)particle_delta);
+    double factorial_term = 1.0;
+    if (particle_delta > 0) {
+        for (int i = n_ex + 1; i < n_ex + particle_delta + 1; ++i) factorial_term /= (double)i;
+    } else if (particle_delta < 0) {
+        for (int i = n_ex + particle_delta + 1; i < n_ex + 1; ++i) factorial_term *= (double)i;
+    }
+    double debroglie = pow(qo_debroglie_wavelength(mass, temperature), (double)(-3 * particle_delta));
+    double prefactor = vol * factorial_term * debroglie;
+    double exponential = ((double)particle_delta * mu - delta_e) / (temperature * KB);
+    if (exponential > 709.782712893384) { if (overflow) *overflow = 1; return INFINITY; }
+    return exp(exponential) * prefactor;
+}
+
+double qo_gc_acceptance(double delta_e, int32_t particle_delta, int32_t n_exchange, double accessible_volume, double mass_amu,
+                        double temperature, double mu) {
+    int ov = 0;
+    return gc_probability(delta_e, particle_delta, n_exchange, accessible_volume, mass_amu, temperature, mu, &ov);
+}
+
+int qo_pt_swap_accept(double e_k, double e_k1, double t_k, double t_k1, double u) {
+    /* replica exchange between temperatures t_k and t_k1: u < exp((1/kT_k - 1/kT_k1) (E_k - E_k1)) */
+    double x = (1.0 / (t_k * KB) - 1.0 / (t_k1 * KB)) * (e_k - e_k1);
+    if (x >= 0) return 1;
+    return u < exp(x);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Label bookkeeping (src/quansino/moves/displacement.py:173-184, 226-253)
+ * ---------------------------------------------------------------------------------------------- */
+static int cmp_int(const void *a, const void *b) {
+    int x = *(const int *)a, y = *(const int *)b;
+    return (x > y) - (x < y);
+}
+
+/* sorted unique non-negative labels; returns count */
+static int unique_labels(const int32_t *labels, int n, int *uniq) {
+    int m = 0;
+    for (int i = 0; i < n; ++i)
+        if (labels[i] >= 0) uniq[m++] = labels[i];
+    qsort(uniq, (size_t)m, sizeof(int), cmp_int);
+    int k = 0;
+    for (int i = 0; i < m; ++i)
+        if (k == 0 || uniq[k - 1] != uniq[i]) uniq[k++] = uniq[i];
+    return k;
+}
+
+/* the single atom carrying `label`; -2 if the group has != 1 member (molecules: SURVEY 8f, unsupported) */
+static int atom_of_label(const int32_t *labels, int n, int label) {
+    int found = -1, cnt = 0;
+    for (int i = 0; i < n; ++i)
+        if (labels[i] == label) { found = i; ++cnt; }
+    return cnt == 1 ? found : -2;
+}
+
+/* on_atoms_changed(added, removed) for one move, one added atom at the end and/or one removed index */
+static void labels_on_atoms_changed(qo_move_t *mv, int n_before, int added, int removed_index, int *scratch) {
+    int n = n_before;
+    if (added) {
+        int k = unique_labels(mv->labels, n, scratch);
+        /* `self.default_label or (...)`: None and 0 are both falsy */
+        int label = (mv->default_label != INT32_MIN && mv->default_label != 0) ? mv->default_label : (k ? scratch[k - 1] + 1 : 0);
+        mv->labels[n++] = label;
+    }
+    if (removed_index >= 0) {
+        for (int i = removed_index; i + 1 < n; ++i) mv->labels[i] = mv->labels[i + 1];
+        --n;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * One attempt of each move type.  All work on a TRIAL copy; commit on accept => revert is bit-exact.
+ * ---------------------------------------------------------------------------------------------- */
+static double kinetic_energy(int n, const double *mom, double mass) {
+    /* Atoms.get_kinetic_energy: 0.5 * vdot(p, p / m) */
+    double s = 0.0;
+    for (int i = 0; i < 3 * n; ++i) s += mom[i] * (mom[i] / mass);
+    return 0.5 * s;
+}
+
+/* Atoms.set_cell(new, scale_atoms=True): M = solve(old, new); positions = positions @ M.  For the diagonal
+ * cells of the configs M is diagonal with M_kk = new_kk / old_kk. */
+static void scale_positions(int n, double *pos, const double old_cell[9], const double new_cell[9]) {
+    double inv[9], M[9];
+    int diag = old_cell[1] == 0 && old_cell[2] == 0 && old_cell[3] == 0 && old_cell[5] == 0 && old_cell[6] == 0 && old_cell[7] == 0;
+    if (diag) {
+        memset(M, 0, sizeof(M));
+        M[0] = new_cell[0] / old_cell[0]; M[4] = new_cell[4] / old_cell[4]; M[8] = new_cell[8] / old_cell[8];
+        M[1] = new_cell[1] / old_cell[0]; M[2] = new_cell[2] / old_cell[0];
+        M[3] = new_cell[3] / old_cell[4]; M[5] = new_cell[5] / old_cell[4];
+        M[6] = new_cell[6] / old_cell[8]; M[7] = new_cell[7] / old_cell[8];
+    } else {
+        inv3(old_cell, inv);
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) M[3 * r + c] = (inv[3 * r] * new_cell[c] + inv[3 * r + 1] * new_cell[3 + c]) + inv[3 * r + 2] * new_cell[6 + c];
+    }
+    for (int i = 0; i < n; ++i) {
+        double x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+        for (int c = 0; c < 3; ++c) pos[3 * i + c] = (x * M[c] + y * M[3 + c]) + z * M[6 + c];
+    }
+}
+
+int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32_t n_moves, uint64_t seed, uint32_t replica,
+              uint64_t attempt_base, int32_t n_attempts, qo_trace_t *trace, int64_t counters[4]) {
+    const int nmax = st->n_max;
+    int rc = 0;
+    double *trial = (double *)malloc(sizeof(double) * 3 * (size_t)nmax);
+    double *mom = (double *)malloc(sizeof(double) * 3 * (size_t)nmax);
+    double *frc = (double *)malloc(sizeof(double) * 3 * (size_t)nmax);
+    int *uniq = (int *)malloc(sizeof(int) * (size_t)(nmax + 1));
+    char *seen = (char *)malloc((size_t)(nmax + 1));
+    double cdf[16];
+    int64_t cnt[4] = {0, 0, 0, 0};
+    if (!trial || !mom || !frc || !uniq || !seen || n_moves > 16 || n_moves < 1) { rc = -1; goto done; }
+
+    /* validate_simulation (mc/canonical.py:114-122): prime last_potential_energy only if NaN */
+    if (isnan(st->last_energy)) {
+        int64_t np_ = qo_energy(pot, st->n_atoms, st->pos, st->cell, st->pbc, &st->last_energy, NULL, NULL);
+        if (np_ < 0) { rc = -1; goto done; }
+        cnt[0] += np_; cnt[3] += 1;
+    }
+
+    /* yield_moves (mc/core.py:340-349): probabilities normalised, numpy choice(p=) = searchsorted(cdf, u, 'right') */
+    {
+        double tot = 0.0, acc = 0.0;
+        for (int m = 0; m < n_moves; ++m) tot += moves[m].probability;
+        for (int m = 0; m < n_moves; ++m) { acc += moves[m].probability / tot; cdf[m] = acc; }
+        double last = cdf[n_moves - 1];
+        for (int m = 0; m < n_moves; ++m) cdf[m] /= last;
+    }
+
+    for (int k = 0; k < n_attempts; ++k) {
+        const uint64_t attempt = attempt_base + (uint64_t)k;
+        double b0[2], b1[2], b2[2], b3[2];
+        qo_uniform_pair(seed, attempt, replica, 0, b0);
+        qo_uniform_pair(seed, attempt, replica, 1, b1);
+        qo_uniform_pair(seed, attempt, replica, 2, b2);
+        qo_uniform_pair(seed, attempt, replica, 3, b3);
+        const double u_select = b0[0], u_label = b0[1], u_accept = b2[1], u_coin = b3[0];
+        const double opd[3] = {b1[0], b1[1], b2[0]};
+        int m = 0;
+        while (m < n_moves - 1 && cdf[m] <= u_select) ++m;
+        qo_move_t *mv = &moves[m];
+        const int n = st->n_atoms;
+        const double kT = st->temperature * KB;
+        int accepted = -1, moved = -1;
+        double delta = NAN;
+
+        if (mv->type == QO_MOVE_DISPLACEMENT) {
+            int nu = unique_labels(mv->labels, n, uniq);
+            if (nu > 0) {
+                int label = uniq[(int)(u_label * (double)nu)];
+                int a = atom_of_label(mv->labels, n, label);
+                if (a < 0) { rc = -2; goto done; }
+                double t[3];
+                if (mv->op == QO_OP_BALL) { /* operations/displacement.py:146-153 */
+                    double r = 0.0 + (mv->step - 0.0) * opd[0];
+                    double phi = 0.0 + (TWO_PI - 0.0) * opd[1];
+                    double c = -1.0 + (1.0 - -1.0) * opd[2];
+                    double s = sqrt(1 - c * c);
+                    t[0] = r * s * cos(phi); t[1] = r * s * sin(phi); t[2] = r * c;
+                } else if (mv->op == QO_OP_SPHERE) { /* :103-110 */
+                    double phi = 0.0 + (TWO_PI - 0.0) * opd[0];
+                    double c = -1.0 + (1.0 - -1.0) * opd[1];
+                    double s = sqrt(1 - c * c);
+                    t[0] = mv->step * (s * cos(phi)); t[1] = mv->step * (s * sin(phi)); t[2] = mv->step * c;
+                } else if (mv->op == QO_OP_BOX) { /* :67-68 */
+                    for (int x = 0; x < 3; ++x) t[x] = -mv->step + (mv->step - -mv->step) * opd[x];
+                } else { rc = -1; goto done; }
+                memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
+                for (int x = 0; x < 3; ++x) trial[3 * a + x] = st->pos[3 * a + x] + t[x];
+                moved = a;
+                double e_new;
+                int64_t np_ = qo_energy(pot, n, trial, st->cell, st->pbc, &e_new, NULL, NULL);
+                cnt[0] += np_; cnt[3] += 1;
+                memset(seen, 0, (size_t)n);
+                seen[a] = 1;
+                cnt[1] += count_neighbours(pot, n, st->pos, st->cell, st->pbc, a, seen);
+                cnt[1] += count_neighbours(pot, n, trial, st->cell, st->pbc, a, seen);
+                for (int i = 0; i < n; ++i) cnt[2] += seen[i];
+                delta = e_new - st->last_energy;
+                double x = -delta / kT; /* mc/criteria.py:104-110 */
+                if (x > 709.782712893384) { rc = -4; goto done; }
+                accepted = u_accept < exp(x);
+                if (accepted) {
+                    memcpy(st->pos, trial, sizeof(double) * 3 * (size_t)n);
+                    st->last_energy = e_new;
+                }
+            }
+        } else if (mv->type == QO_MOVE_CELL) {
+            /* operations/cell.py:167-169, moves/cell.py:73-84, mc/criteria.py:160-172 */
+            double s = exp(-mv->step + (mv->step - -mv->step) * opd[0]);
+            double new_cell[9];
+            for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) new_cell[3 * r + c] = s * st->cell[3 * r + c]; /* (s I) @ cell */
+            memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
+            scale_positions(n, trial, st->cell, new_cell);
+            double e_new;
+            int64_t np_ = qo_energy(pot, n, trial, new_cell, st->pbc, &e_new, NULL, NULL);
+            cnt[0] += np_; cnt[3] += 1; cnt[1] += np_; cnt[2] += n;
+            delta = e_new - st->last_energy;
+            double v_new = volume(new_cell), v_old = volume(st->cell);
+            double x = -(delta + st->pressure * (v_new - v_old)) / kT + (double)(n + 1) * log(v_new / v_old);
+            if (x > 709.782712893384) { rc = -4; goto done; }
+            accepted = u_accept < exp(x);
+            if (accepted) {
+                memcpy(st->pos, trial, sizeof(double) * 3 * (size_t)n);
+                memcpy(st->cell, new_cell, sizeof(new_cell));
+                st->last_energy = e_new;
+            }
+        } else if (mv->type == QO_MOVE_EXCHANGE) {
+            /* moves/exchange.py:134-176 */
+            int is_addition = u_coin < mv->bias_insert;
+            int n_new = n, particle_delta = 0, removed = -1;
+            if (is_addition) {
+                if (n + 1 > nmax) { rc = -3; goto done; }
+                memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
+                /* Translation (operations/displacement.py:173-175): uniform(0,1,(1,3)) @ cell - mean(pos[moving]) */
+                for (int x = 0; x < 3; ++x) {
+                    double fc = (opd[0] * st->cell[x] + opd[1] * st->cell[3 + x]) + opd[2] * st->cell[6 + x];
+                    trial[3 * n + x] = st->exchange_pos[x] + (fc - st->exchange_pos[x]);
+                }
+                n_new = n + 1; particle_delta = 1; moved = n;
+                memset(seen, 0, (size_t)n_new);
+                seen[n] = 1;
+                cnt[1] += count_neighbours(pot, n_new, trial, st->cell, st->pbc, n, seen);
+                for (int i = 0; i < n_new; ++i) cnt[2] += seen[i];
+            } else {
+                int nu = unique_labels(mv->labels, n, uniq);
+                if (nu > 0) {
+                    int label = uniq[(int)(u_label * (double)nu)];
+                    int a = atom_of_label(mv->labels, n, label);
+                    if (a < 0) { rc = -2; goto done; }
+                    memset(seen, 0, (size_t)n);
+                    cnt[1] += count_neighbours(pot, n, st->pos, st->cell, st->pbc, a, seen);
+                    for (int i = 0; i < n; ++i) cnt[2] += seen[i];
+                    for (int i = 0, o = 0; i < n; ++i)
+                        if (i != a) { memcpy(trial + 3 * o, st->pos + 3 * i, sizeof(double) * 3); ++o; }
+                    n_new = n - 1; particle_delta = -1; removed = a; moved = a;
+                }
+            }
+            if (particle_delta != 0) {
+                double e_new;
+                int64_t np_ = qo_energy(pot, n_new, trial, st->cell, st->pbc, &e_new, NULL, NULL);
+                cnt[0] += np_; cnt[3] += 1;
+                delta = e_new - st->last_energy;
+                int ov = 0;
+                double prob = gc_probability(delta, particle_delta, st->n_exchange, st->accessible_volume, st->exchange_mass,
+                                             st->temperature, st->chemical_potential, &ov);
+                if (ov) { rc = -4; goto done; }
+                accepted = u_accept < prob;
+                if (accepted) {
+                    /* GrandCanonical.save_state (mc/gcmc.py:207-214): every move re-labels, then N_ex += delta */
+                    for (int q = 0; q < n_moves; ++q)
+                        if (moves[q].labels) labels_on_atoms_changed(&moves[q], n, particle_delta > 0, removed, uniq);
+                    memcpy(st->pos, trial, sizeof(double) * 3 * (size_t)n_new);
+                    if (st->momenta) {
+                        if (particle_delta > 0) memset(st->momenta + 3 * n, 0, sizeof(double) * 3);
+                        else memmove(st->momenta + 3 * removed, st->momenta + 3 * (removed + 1), sizeof(double) * 3 * (size_t)(n - removed - 1));
+                    }
+                    st->n_atoms = n_new;
+                    st->n_exchange += particle_delta;
+                    st->last_energy = e_new;
+                }
+            }
+        } else if (mv->type == QO_MOVE_HMC) {
+            /* moves/displacement.py:307-345, utils/dynamics.py:27-43, integrators/displacement.py:52-81,
+             * mc/criteria.py:117-140, mc/contexts.py:186-198 */
+            if (!st->momenta) { rc = -1; goto done; }
+            const double mass = st->mass, dt = mv->dt;
+            const double pscale = sqrt(mass * kT);
+            for (int i = 0; i < 3 * n; ++i) mom[i] = qo_normal(seed, attempt, replica, (uint32_t)i) * pscale;
+            for (int i = 0; i < 3 * n; ++i) mom[i] = mom[i] * 1.0; /* set_momenta(get_momenta() * scale), scale = 1.0 */
+            st->last_kinetic = kinetic_energy(n, mom, mass);
+            memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
+            double e_pot;
+            int64_t np_ = qo_energy(pot, n, trial, st->cell, st->pbc, &e_pot, frc, NULL);
+            cnt[0] += np_; cnt[3] += 1; cnt[1] += np_; cnt[2] += n;
+            for (int s = 0; s < mv->n_steps; ++s) {
+                for (int i = 0; i < 3 * n; ++i) {
+                    double new_mom = mom[i] + 0.5 * frc[i] * dt;
+                    double x_old = trial[i];
+                    double x_new = x_old + new_mom / mass * dt;
+                    trial[i] = x_new;
+                    mom[i] = (x_new - x_old) * mass / dt; /* apply_constraints=True re-derivation (:74-75) */
+                }
+                np_ = qo_energy(pot, n, trial, st->cell, st->pbc, &e_pot, frc, NULL);
+                cnt[0] += np_; cnt[3] += 1; cnt[1] += np_; cnt[2] += n;
+                for (int i = 0; i < 3 * n; ++i) mom[i] = mom[i] + 0.5 * frc[i] * dt;
+            }
+            double e_kin = kinetic_energy(n, mom, mass);
+            delta = (e_pot + e_kin) - st->last_energy - st->last_kinetic;
+            double x = -delta / kT;
+            if (x > 709.782712893384) { rc = -4; goto done; }
+            accepted = u_accept < exp(x);
+            if (accepted) {
+                memcpy(st->pos, trial, sizeof(double) * 3 * (size_t)n);
+                memcpy(st->momenta, mom, sizeof(double) * 3 * (size_t)n);
+                st->last_energy = e_pot;
+                st->last_kinetic = e_kin;
+            }
+        } else { rc = -1; goto done; }
+
+        if (trace) {
+            if (trace->move) trace->move[k] = (int8_t)m;
+            if (trace->accepted) trace->accepted[k] = (int8_t)accepted;
+            if (trace->energy) trace->energy[k] = st->last_energy;
+            if (trace->delta) trace->delta[k] = delta;
+            if (trace->n_atoms) trace->n_atoms[k] = st->n_atoms;
+            if (trace->moved) trace->moved[k] = moved;
+        }
+    }
+done:
+    if (counters) for (int i = 0; i < 4; ++i) counters[i] += cnt[i];
+    free(trial); free(mom); free(frc); free(uniq); free(seen);
+    return rc;
+}

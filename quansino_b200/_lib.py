@@ -1,0 +1,144 @@
+"""ctypes binding of ``libquansino_b200.so`` (the C ABI declared in ``include/quansino_b200.h``).
+
+There is no CPU fallback: if the library is missing, or a compute entry point finds no CUDA device, an
+exception is raised.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libquansino_b200.so"
+
+QMC_MAX_MOVES = 4
+LABEL_NONE = -(2**31)
+
+POT_EMT, POT_LJ = 0, 1
+MOVE_DISPLACEMENT, MOVE_CELL, MOVE_EXCHANGE, MOVE_HMC = 0, 1, 2, 3
+OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET = 0, 1, 2, 3, 4, 5
+
+ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
+STATUS_EXP_OVERFLOW, STATUS_CAPACITY, STATUS_CELL_TOO_SMALL, STATUS_LIST_OVERFLOW = 1, 2, 4, 8
+
+EXPORTS = (
+    "qmc_abi_version", "qmc_last_error", "qmc_device_count", "qmc_sweep_smem_per_replica", "qmc_energy_full",
+    "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_hmc_workspace_bytes", "qmc_pt_swap", "qmc_fp64_peak",
+    "qmc_sweep_host",
+)  # fmt: skip
+
+
+class Potential(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32)] + [
+        (name, C.c_double)
+        for name in (
+            "E0", "s0", "V0", "eta2", "kappa", "lmbda", "beta", "rc", "rc_list", "acut", "gamma1", "gamma2",
+            "sigma", "epsilon", "lj_rc", "lj_e0",
+        )
+    ]  # fmt: skip
+
+
+class Move(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32),
+        ("op", C.c_int32),
+        ("step", C.c_double),
+        ("probability", C.c_double),
+        ("bias_insert", C.c_double),
+        ("dt", C.c_double),
+        ("n_steps", C.c_int32),
+        ("default_label", C.c_int32),
+        ("labels", C.c_void_p),
+    ]
+
+
+class Batch(C.Structure):
+    _fields_ = [
+        ("n_replicas", C.c_int32),
+        ("n_max", C.c_int32),
+        ("replica_offset", C.c_int32),
+        ("pbc", C.c_int32 * 3),
+        ("pos", C.c_void_p),
+        ("cell", C.c_void_p),
+        ("n_atoms", C.c_void_p),
+        ("energy", C.c_void_p),
+        ("temperature", C.c_void_p),
+        ("sigma1", C.c_void_p),
+        ("eatom", C.c_void_p),
+        ("momenta", C.c_void_p),
+        ("kinetic", C.c_void_p),
+        ("n_exchange", C.c_void_p),
+        ("counters", C.c_void_p),
+        ("status", C.c_void_p),
+        ("pair_evals", C.c_void_p),
+        ("mass", C.c_double),
+        ("pressure", C.c_double),
+        ("chemical_potential", C.c_double),
+        ("accessible_volume", C.c_double),
+        ("exchange_mass", C.c_double),
+        ("exchange_pos", C.c_double * 3),
+    ]
+
+
+class Trace(C.Structure):
+    _fields_ = [
+        ("move", C.c_void_p),
+        ("accepted", C.c_void_p),
+        ("energy", C.c_void_p),
+        ("delta", C.c_void_p),
+        ("moved", C.c_void_p),
+    ]
+
+
+class NoDeviceError(RuntimeError):
+    """Raised when a compute entry point is called without a CUDA device (there is no CPU fallback)."""
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the C-ABI library built by ``python -m quansino_b200.build``; fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m quansino_b200.build` "
+            "(quansino_b200 has no CPU fallback and will not run without its CUDA library)"
+        )
+    L = C.CDLL(str(LIB_PATH))
+    vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
+    L.qmc_abi_version.restype = C.c_int
+    L.qmc_last_error.restype = C.c_char_p
+    L.qmc_device_count.restype = C.c_int
+    L.qmc_sweep_smem_per_replica.argtypes = [C.POINTER(Potential), i32]
+    L.qmc_sweep_smem_per_replica.restype = i64
+    L.qmc_energy_full.argtypes = [C.POINTER(Potential), C.POINTER(Batch), vp, vp]
+    L.qmc_forces_full.argtypes = [C.POINTER(Potential), C.POINTER(Batch), vp, vp]
+    L.qmc_sweep.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), i32, u64, u64, i32, C.POINTER(Trace), vp]
+    L.qmc_hmc.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), u64, u64, i32, C.POINTER(Trace), vp, i64, vp]
+    L.qmc_hmc_workspace_bytes.argtypes = [C.POINTER(Batch)]
+    L.qmc_hmc_workspace_bytes.restype = i64
+    L.qmc_pt_swap.argtypes = [vp, vp, i32, u64, u64, vp, vp]
+    L.qmc_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
+    L.qmc_sweep_host.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), i32, u64, u64, i32, C.POINTER(Trace)]
+    for name in ("qmc_energy_full", "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_pt_swap", "qmc_fp64_peak", "qmc_sweep_host"):
+        getattr(L, name).restype = C.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    """Map a C status code onto the exception type the reference would raise."""
+    if rc >= 0:
+        return
+    msg = load().qmc_last_error().decode(errors="replace")
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == ERR_NO_DEVICE:
+        raise NoDeviceError(msg + " (quansino_b200 has no CPU fallback)")
+    raise RuntimeError(msg)

@@ -1,0 +1,502 @@
+// The Monte Carlo sweep kernel: n_attempts cycles of `MonteCarlo.step` (src/quansino/mc/core.py:353-384) for
+// every replica of the batch, one warp per replica, replica state resident in shared memory.
+//
+// Per attempt, for one replica (reference file:line in brackets):
+//   draws      Philox blocks 0..3 of (attempt, global replica)                  [mc/core.py:344-349 and below]
+//   select     searchsorted(cdf, u_select, 'right') over the move table         [mc/core.py:344-349]
+//   propose    DisplacementMove + Ball / Box / Sphere                           [moves/displacement.py:143-171,
+//                                                                                 operations/displacement.py:67-153]
+//              CellMove + IsotropicDeformation                                  [moves/cell.py:57-94, operations/cell.py:153-169]
+//              ExchangeMove + Translation                                       [moves/exchange.py:134-176]
+//   energy     LOCAL delta of the moved / inserted / deleted atom (the reference recomputes the whole system
+//              through ASE: mc/criteria.py:104-106); full recompute only for cell moves
+//   criteria   Canonical / Isobaric / GrandCanonical                            [mc/criteria.py:89-110,146-172,226-278]
+//   commit     in place on accept; nothing to undo on reject                    [mc/contexts.py:144-156,350-368]
+#pragma once
+
+#include "replica_warp.cuh"
+
+namespace qmc {
+
+struct MoveDev {
+    int type, op;
+    double step, bias;
+    int default_label;
+    int *labels;  // device [R][n_max] or nullptr (= arange, no exchange)
+};
+
+struct SweepArgs {
+    PotDev pot;
+    qmc_batch_t b;
+    MoveDev mv[QMC_MAX_MOVES];
+    double cdf[QMC_MAX_MOVES];
+    int n_moves;
+    int need_coin;  // any exchange move present
+    unsigned long long seed, attempt_base;
+    int n_attempts;
+    qmc_trace_t tr;
+    long long smem_per_warp;
+};
+
+// --- label bookkeeping (moves/displacement.py:173-184, 226-253); labels live in global memory -------------------
+__device__ inline int count_labelled(const int *lab, int n) {
+    int c = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane_id();
+        c += __popc(__ballot_sync(FULL, j < n && lab[j] >= 0));
+    }
+    return c;
+}
+
+// index of the idx-th atom (in index order) with a non-negative label; labels are strictly increasing with the atom
+// index among the non-negative ones (validated on the host), so this IS unique_labels[idx]'s atom.
+__device__ inline int select_labelled(const int *lab, int n, int idx) {
+    int run = 0, found = -1;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane_id();
+        const unsigned b = __ballot_sync(FULL, j < n && lab[j] >= 0);
+        const int c = __popc(b);
+        if (found < 0 && idx < run + c) found = base + (int)__fns(b, 0, idx - run + 1);
+        run += c;
+    }
+    return found;
+}
+
+__device__ inline int max_label(const int *lab, int n) {
+    int m = -1;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane_id();
+        const int v = (j < n) ? lab[j] : -1;
+        m = max(m, __reduce_max_sync(FULL, v));
+    }
+    return m;
+}
+
+// on_atoms_changed for one move: append one label and / or remove index `removed`
+__device__ inline void labels_changed(int *lab, int n, bool added, int removed, int default_label) {
+    const int lane = lane_id();
+    if (added) {
+        const int mx = max_label(lab, n);
+        // `self.default_label or (max(unique_labels) + 1 if len(unique_labels) else 0)`: None and 0 are falsy
+        const int label = (default_label != QMC_LABEL_NONE && default_label != 0) ? default_label : (mx >= 0 ? mx + 1 : 0);
+        if (lane == 0) lab[n] = label;
+        n += 1;
+        __syncwarp();
+    }
+    if (removed >= 0) {
+        for (int base = removed; base < n - 1; base += 32) {
+            const int j = base + lane;
+            int t = 0;
+            if (j < n - 1) t = lab[j + 1];
+            __syncwarp();
+            if (j < n - 1) lab[j] = t;
+            __syncwarp();
+        }
+    }
+}
+
+__device__ inline void shift_down(double *arr, int removed, int n) {
+    const int lane = lane_id();
+    for (int base = removed; base < n - 1; base += 32) {
+        const int j = base + lane;
+        double t = 0.0;
+        if (j < n - 1) t = arr[j + 1];
+        __syncwarp();
+        if (j < n - 1) arr[j] = t;
+        __syncwarp();
+    }
+}
+
+// --- local energy delta -----------------------------------------------------------------------------------------
+struct Trial {
+    double dE;       // energy difference of the whole system
+    double sig_i;    // sigma_1 of the moved atom at its new position (EMT)
+    double eat_i;    // its embedding energy there
+    int n2;          // atoms whose sigma_1 changed (entries of l2; trial sigma in dsig[j], trial energy in lr[e])
+    int pairs;       // pair evaluations done (warp total)
+};
+
+template <int POT>
+__device__ __forceinline__ Trial local_delta(const PotDev &pot, Replica &R, int n_scan, int i, bool has_old, bool has_new,
+                                             const double po[3], const double pn[3]) {
+    const int lane = lane_id();
+    Trial T;
+    DeltaAcc acc = {0.0, 0.0, 0};
+    T.n2 = scan_and_accumulate<POT, 0>(pot, R, n_scan, has_old ? i : -1, has_old, has_new, po, pn, acc);
+    const double vs = warp_sum(acc.v);
+    T.pairs = acc.pairs;
+    T.sig_i = 0.0;
+    T.eat_i = 0.0;
+    if (POT == QMC_POT_LJ) {
+        T.dE = vs;  // E = 1/2 sum_i sum_j e_ij: the moved atom's row and column change together
+        return T;
+    }
+    if (has_new) T.sig_i = warp_sum(acc.snew);
+    double part = 0.0, e_i_lane = 0.0;
+    const int total = T.n2 + (has_new ? 1 : 0);
+    for (int e = lane; e < total; e += 32) {
+        const bool nb = e < T.n2;
+        const int j = nb ? R.l2[e] : 0;
+        const double sn = nb ? (R.sig[j] + R.dsig[j]) : T.sig_i;
+        const double eold = nb ? R.eat[j] : (has_old ? R.eat[i] : 0.0);
+        const double en = emt_embed(pot, sn);
+        part += en - eold;
+        if (nb) {
+            R.dsig[j] = sn;
+            R.lr[e] = en;
+        } else {
+            e_i_lane = en;
+        }
+    }
+    if (has_new) T.eat_i = __shfl_sync(FULL, e_i_lane, T.n2 & 31);
+    if (!has_new && lane == 0) part -= R.eat[i];  // deletion: the atom's own embedding energy disappears
+    // pair part: rows (i, j) and (j, i) change together: 2 * 0.5 * (es + eo) = 2 * neghalfv0overgamma2 * dsigma2
+    T.dE = warp_sum(part) + 2.0 * pot.neghalfv0overgamma2 * vs;
+    __syncwarp();
+    return T;
+}
+
+template <int POT>
+__device__ __forceinline__ void finish_trial(Replica &R, const Trial &T, bool accept) {
+    if (POT != QMC_POT_EMT) return;
+    for (int e = lane_id(); e < T.n2; e += 32) {
+        const int j = R.l2[e];
+        if (accept) {
+            R.sig[j] = R.dsig[j];
+            R.eat[j] = R.lr[e];
+        }
+        R.dsig[j] = 0.0;
+    }
+    __syncwarp();
+}
+
+// GrandCanonicalCriteria.evaluate (mc/criteria.py:243-278): criteria * prefactor
+__device__ inline double gc_probability(double dE, int delta, int n_ex, double acc_volume, double mass, double temperature,
+                                        double mu, bool &overflow) {
+    const double vol = delta > 0 ? acc_volume : 1.0 / acc_volume;
+    const double factorial_term = delta > 0 ? 1.0 / (double)(n_ex + 1) : (double)n_ex;
+    const double denom = 2 * 3.141592653589793 * mass * KB * temperature / 6.022140857e23 * 1e-3 * 1.6021766208e-19;
+    const double lam = sqrt(6.626070040e-34 * 6.626070040e-34 / denom) * 1e10;
+    const double debroglie = pow(lam, (double)(-3 * delta));
+    const double prefactor = vol * factorial_term * debroglie;
+    const double exponential = ((double)delta * mu - dE) / (temperature * KB);
+    overflow = exponential > EXP_OVERFLOW;
+    return exp(exponential) * prefactor;
+}
+
+template <int POT, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_constant__ SweepArgs a) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int r = blockIdx.x * WARPS + warp;
+    if (r >= a.b.n_replicas) return;  // whole warp exits; no block-wide barrier is used below
+    const PotDev &pot = a.pot;
+    const int nmax = a.b.n_max;
+    Replica R;
+    replica_carve(R, smem + (size_t)warp * a.smem_per_warp, POT, nmax);
+
+    // ---- load the replica ----
+    R.n = a.b.n_atoms[r];
+    double *gx = a.b.pos + (size_t)r * 3 * nmax, *gy = gx + nmax, *gz = gy + nmax;
+    double *gs = POT == QMC_POT_EMT ? a.b.sigma1 + (size_t)r * nmax : nullptr;
+    double *ge = POT == QMC_POT_EMT ? a.b.eatom + (size_t)r * nmax : nullptr;
+    for (int j = lane; j < nmax; j += 32) {
+        const bool in = j < R.n;
+        R.x[j] = in ? gx[j] : 0.0;
+        R.y[j] = in ? gy[j] : 0.0;
+        R.z[j] = in ? gz[j] : 0.0;
+        if (POT == QMC_POT_EMT) {
+            R.sig[j] = in ? gs[j] : 0.0;
+            R.eat[j] = in ? ge[j] : 0.0;
+            R.dsig[j] = 0.0;
+        }
+    }
+    double cell[3] = {a.b.cell[(size_t)r * 9 + 0], a.b.cell[(size_t)r * 9 + 4], a.b.cell[(size_t)r * 9 + 8]};
+    int status = 0;
+    if (!replica_set_cell(R, cell, a.b.pbc, pot.cut)) status |= QMC_STATUS_CELL_TOO_SMALL;
+    double E = a.b.energy[r];
+    const double temperature = a.b.temperature[r];
+    const double kT = temperature * KB;
+    int n_ex = a.b.n_exchange ? a.b.n_exchange[r] : 0;
+    const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
+    const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+    long long n_pairs = 0;
+    __syncwarp();
+
+    for (int k = 0; k < a.n_attempts; ++k) {
+        const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
+        double u_select, u_label, o0, o1, o2, u_accept, u_coin = 0.0, u_spare;
+        uniform_pair(key, attempt, grep, 0, u_select, u_label);
+        uniform_pair(key, attempt, grep, 1, o0, o1);
+        uniform_pair(key, attempt, grep, 2, o2, u_accept);
+        if (a.need_coin) uniform_pair(key, attempt, grep, 3, u_coin, u_spare);
+
+        int m = 0;
+        while (m < a.n_moves - 1 && a.cdf[m] <= u_select) ++m;
+        const MoveDev &mv = a.mv[m];
+        const int *lab = mv.labels ? mv.labels + (size_t)r * nmax : nullptr;
+
+        int accepted = -1, moved = -1;
+        double delta = __longlong_as_double(0x7ff8000000000000LL);  // NaN
+
+        if (mv.type == QMC_MOVE_DISPLACEMENT) {
+            const int nu = lab ? count_labelled(lab, R.n) : R.n;
+            if (nu > 0) {
+                const int idx = (int)(u_label * (double)nu);
+                const int i = lab ? select_labelled(lab, R.n, idx) : idx;
+                double t[3];
+                if (mv.op == QMC_OP_BALL) {
+                    const double rr = mv.step * o0, phi = TWO_PI * o1, c = -1.0 + 2.0 * o2;
+                    const double s = sqrt(__dsub_rn(1.0, __dmul_rn(c, c)));
+                    double sp, cp;
+                    sincos(phi, &sp, &cp);
+                    t[0] = __dmul_rn(__dmul_rn(rr, s), cp);
+                    t[1] = __dmul_rn(__dmul_rn(rr, s), sp);
+                    t[2] = __dmul_rn(rr, c);
+                } else if (mv.op == QMC_OP_SPHERE) {
+                    const double phi = TWO_PI * o0, c = -1.0 + 2.0 * o1;
+                    const double s = sqrt(__dsub_rn(1.0, __dmul_rn(c, c)));
+                    double sp, cp;
+                    sincos(phi, &sp, &cp);
+                    t[0] = __dmul_rn(mv.step, __dmul_rn(s, cp));
+                    t[1] = __dmul_rn(mv.step, __dmul_rn(s, sp));
+                    t[2] = __dmul_rn(mv.step, c);
+                } else {  // QMC_OP_BOX
+                    const double w = mv.step - -mv.step;
+                    t[0] = __dadd_rn(-mv.step, __dmul_rn(w, o0));
+                    t[1] = __dadd_rn(-mv.step, __dmul_rn(w, o1));
+                    t[2] = __dadd_rn(-mv.step, __dmul_rn(w, o2));
+                }
+                const double po[3] = {R.x[i], R.y[i], R.z[i]};
+                const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
+                const Trial T = local_delta<POT>(pot, R, R.n, i, true, true, po, pn);
+                n_pairs += T.pairs;
+                delta = T.dE;
+                const double x = -delta / kT;
+                if (x > EXP_OVERFLOW) status |= QMC_STATUS_EXP_OVERFLOW;
+                const bool acc = u_accept < exp(x);
+                finish_trial<POT>(R, T, acc);
+                if (acc) {
+                    if (lane == 0) {
+                        R.x[i] = pn[0];
+                        R.y[i] = pn[1];
+                        R.z[i] = pn[2];
+                        if (POT == QMC_POT_EMT) {
+                            R.sig[i] = T.sig_i;
+                            R.eat[i] = T.eat_i;
+                        }
+                    }
+                    E += delta;
+                }
+                __syncwarp();
+                accepted = acc ? 1 : 0;
+                moved = i;
+            }
+        } else if (mv.type == QMC_MOVE_CELL) {
+            // snapshot the last accepted state in global memory, deform in place, recompute everything
+            for (int j = lane; j < R.n; j += 32) {
+                gx[j] = R.x[j];
+                gy[j] = R.y[j];
+                gz[j] = R.z[j];
+                if (POT == QMC_POT_EMT) {
+                    gs[j] = R.sig[j];
+                    ge[j] = R.eat[j];
+                }
+            }
+            const double s = exp(__dadd_rn(-mv.step, __dmul_rn(mv.step - -mv.step, o0)));
+            double ncell[3], scale[3];
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                ncell[d] = s * cell[d];         // (s I) @ cell
+                scale[d] = ncell[d] / cell[d];  // solve(old_cell, new_cell), diagonal
+            }
+            for (int j = lane; j < R.n; j += 32) {
+                R.x[j] = R.x[j] * scale[0];
+                R.y[j] = R.y[j] * scale[1];
+                R.z[j] = R.z[j] * scale[2];
+            }
+            __syncwarp();
+            const bool cell_ok = replica_set_cell(R, ncell, a.b.pbc, pot.cut);
+            if (!cell_ok) status |= QMC_STATUS_CELL_TOO_SMALL;
+            long long fp = 0;
+            const double e_new = cell_ok ? replica_full_energy<POT>(pot, R, fp) : E;
+            n_pairs += fp;
+            delta = e_new - E;
+            const double v_new = fabs((ncell[0] * ncell[1]) * ncell[2]), v_old = fabs((cell[0] * cell[1]) * cell[2]);
+            const double x = -(delta + a.b.pressure * (v_new - v_old)) / kT + (double)(R.n + 1) * log(v_new / v_old);
+            if (x > EXP_OVERFLOW) status |= QMC_STATUS_EXP_OVERFLOW;
+            const bool acc = cell_ok && (u_accept < exp(x));
+            if (acc) {
+                E = e_new;
+                cell[0] = ncell[0];
+                cell[1] = ncell[1];
+                cell[2] = ncell[2];
+            } else {
+                for (int j = lane; j < R.n; j += 32) {
+                    R.x[j] = gx[j];
+                    R.y[j] = gy[j];
+                    R.z[j] = gz[j];
+                    if (POT == QMC_POT_EMT) {
+                        R.sig[j] = gs[j];
+                        R.eat[j] = ge[j];
+                    }
+                }
+                replica_set_cell(R, cell, a.b.pbc, pot.cut);
+            }
+            __syncwarp();
+            accepted = acc ? 1 : 0;
+        } else if (mv.type == QMC_MOVE_EXCHANGE) {
+            const bool is_add = u_coin < mv.bias;
+            int pd = 0, i = -1;
+            Trial T;
+            double pn[3] = {0, 0, 0}, po[3] = {0, 0, 0};
+            if (is_add) {
+                if (R.n + 1 > nmax) {
+                    status |= QMC_STATUS_CAPACITY;
+                } else {
+                    // Translation: uniform(0,1,(1,3)) @ cell - mean(positions[moving]); diagonal cell
+                    const double f[3] = {o0, o1, o2};
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const double fc = __dmul_rn(f[d], cell[d]);
+                        pn[d] = __dadd_rn(a.b.exchange_pos[d], __dsub_rn(fc, a.b.exchange_pos[d]));
+                    }
+                    i = R.n;
+                    T = local_delta<POT>(pot, R, R.n, i, false, true, po, pn);
+                    pd = 1;
+                }
+            } else {
+                const int nu = lab ? count_labelled(lab, R.n) : R.n;
+                if (nu > 0) {
+                    const int idx = (int)(u_label * (double)nu);
+                    i = lab ? select_labelled(lab, R.n, idx) : idx;
+                    po[0] = R.x[i];
+                    po[1] = R.y[i];
+                    po[2] = R.z[i];
+                    T = local_delta<POT>(pot, R, R.n, i, true, false, po, pn);
+                    pd = -1;
+                }
+            }
+            if (pd != 0) {
+                n_pairs += T.pairs;
+                delta = T.dE;
+                bool ov;
+                const double prob = gc_probability(delta, pd, n_ex, a.b.accessible_volume, a.b.exchange_mass, temperature,
+                                                   a.b.chemical_potential, ov);
+                if (ov) status |= QMC_STATUS_EXP_OVERFLOW;
+                const bool acc = u_accept < prob;
+                finish_trial<POT>(R, T, acc);
+                if (acc) {
+                    // GrandCanonical.save_state (mc/gcmc.py:207-214): every registered move re-labels
+                    for (int q = 0; q < a.n_moves; ++q)
+                        if (a.mv[q].labels)
+                            labels_changed(a.mv[q].labels + (size_t)r * nmax, R.n, pd > 0, pd < 0 ? i : -1, a.mv[q].default_label);
+                    if (pd > 0) {
+                        if (lane == 0) {
+                            R.x[i] = pn[0];
+                            R.y[i] = pn[1];
+                            R.z[i] = pn[2];
+                            if (POT == QMC_POT_EMT) {
+                                R.sig[i] = T.sig_i;
+                                R.eat[i] = T.eat_i;
+                            }
+                        }
+                        R.n += 1;
+                    } else {
+                        shift_down(R.x, i, R.n);
+                        shift_down(R.y, i, R.n);
+                        shift_down(R.z, i, R.n);
+                        if (POT == QMC_POT_EMT) {
+                            shift_down(R.sig, i, R.n);
+                            shift_down(R.eat, i, R.n);
+                        }
+                        R.n -= 1;
+                    }
+                    n_ex += pd;
+                    E += delta;
+                }
+                __syncwarp();
+                accepted = acc ? 1 : 0;
+                moved = i;
+            }
+        }
+
+        if (lane == 0) {
+            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(a.b.counters) + ((size_t)r * QMC_MAX_MOVES + m) * 3;
+            atomicAdd(cnt + 0, 1ull);
+            if (accepted == 1) atomicAdd(cnt + 1, 1ull);
+            if (accepted < 0) atomicAdd(cnt + 2, 1ull);
+            const size_t ti = (size_t)r * a.n_attempts + k;
+            if (a.tr.move) a.tr.move[ti] = (int8_t)m;
+            if (a.tr.accepted) a.tr.accepted[ti] = (int8_t)accepted;
+            if (a.tr.energy) a.tr.energy[ti] = E;
+            if (a.tr.delta) a.tr.delta[ti] = delta;
+            if (a.tr.moved) a.tr.moved[ti] = moved;
+        }
+    }
+
+    // ---- store the replica ----
+    __syncwarp();
+    for (int j = lane; j < R.n; j += 32) {
+        gx[j] = R.x[j];
+        gy[j] = R.y[j];
+        gz[j] = R.z[j];
+        if (POT == QMC_POT_EMT) {
+            gs[j] = R.sig[j];
+            ge[j] = R.eat[j];
+        }
+    }
+    if (lane == 0) {
+        a.b.n_atoms[r] = R.n;
+        a.b.energy[r] = E;
+        a.b.cell[(size_t)r * 9 + 0] = cell[0];
+        a.b.cell[(size_t)r * 9 + 4] = cell[1];
+        a.b.cell[(size_t)r * 9 + 8] = cell[2];
+        if (a.b.n_exchange) a.b.n_exchange[r] = n_ex;
+        if (status) atomicOr(a.b.status + r, status);
+    }
+    if (a.b.pair_evals) {
+        for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(FULL, n_pairs, o);
+        if (lane == 0) a.b.pair_evals[r] += n_pairs;
+    }
+}
+
+// validate_simulation: full energy of every replica, caches primed
+template <int POT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) energy_kernel(const __grid_constant__ SweepArgs a, long long *pair_count) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int r = blockIdx.x * WARPS + warp;
+    if (r >= a.b.n_replicas) return;
+    const int nmax = a.b.n_max;
+    Replica R;
+    replica_carve(R, smem + (size_t)warp * a.smem_per_warp, POT, nmax);
+    R.n = a.b.n_atoms[r];
+    const double *gx = a.b.pos + (size_t)r * 3 * nmax, *gy = gx + nmax, *gz = gy + nmax;
+    for (int j = lane; j < nmax; j += 32) {
+        const bool in = j < R.n;
+        R.x[j] = in ? gx[j] : 0.0;
+        R.y[j] = in ? gy[j] : 0.0;
+        R.z[j] = in ? gz[j] : 0.0;
+        if (POT == QMC_POT_EMT) R.dsig[j] = 0.0;
+    }
+    const double cell[3] = {a.b.cell[(size_t)r * 9 + 0], a.b.cell[(size_t)r * 9 + 4], a.b.cell[(size_t)r * 9 + 8]};
+    const bool ok = replica_set_cell(R, cell, a.b.pbc, a.pot.cut);
+    __syncwarp();
+    long long pairs = 0;
+    const double E = ok ? replica_full_energy<POT>(a.pot, R, pairs) : __longlong_as_double(0x7ff8000000000000LL);
+    if (POT == QMC_POT_EMT) {
+        for (int j = lane; j < R.n; j += 32) {
+            a.b.sigma1[(size_t)r * nmax + j] = R.sig[j];
+            a.b.eatom[(size_t)r * nmax + j] = R.eat[j];
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(FULL, pairs, o);
+    if (lane == 0) {
+        a.b.energy[r] = E;
+        if (pair_count) pair_count[r] = pairs;
+        if (!ok) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
+    }
+}
+
+}  // namespace qmc

@@ -1,0 +1,19 @@
+"""Mirror of ``quansino.mc`` for the GPU path."""
+
+from quansino_b200.mc.canonical import Canonical, HamiltonianCanonical
+from quansino_b200.mc.contexts import (
+    Context, DeformationContext, DisplacementContext, ExchangeContext, HamiltonianDisplacementContext, MultiContexts,
+)
+from quansino_b200.mc.core import MonteCarlo
+from quansino_b200.mc.criteria import (
+    BaseCriteria, CanonicalCriteria, GrandCanonicalCriteria, HamiltonianCanonicalCriteria, IsobaricCriteria,
+)
+from quansino_b200.mc.gcmc import GrandCanonical
+from quansino_b200.mc.isobaric import Isobaric
+
+__all__ = [
+    "BaseCriteria", "Canonical", "CanonicalCriteria", "Context", "DeformationContext", "DisplacementContext",
+    "ExchangeContext", "GrandCanonical", "GrandCanonicalCriteria", "HamiltonianCanonical",
+    "HamiltonianCanonicalCriteria", "HamiltonianDisplacementContext", "Isobaric", "IsobaricCriteria", "MonteCarlo",
+    "MultiContexts",
+]  # fmt: skip

@@ -1,0 +1,174 @@
+"""Contexts (``src/quansino/mc/contexts.py:20-436``): per-ensemble simulation state.
+
+In the reference a Context owns ``atoms``, ``rng`` and the ``last_*`` snapshots used to revert a rejected move.  On
+the GPU path the state of all replicas lives in a ``ReplicaBatch`` on the device, moves are committed in place
+on acceptance and a rejected trial is simply never written, so ``save_state`` / ``revert_state`` have nothing left to
+do on the host.  The attributes below are views of the device state (host copies on access)."""
+
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+
+from quansino_b200.batch import BatchedAtoms, ReplicaBatch
+
+
+class Context:
+    def __init__(self, atoms: BatchedAtoms, batch: ReplicaBatch, seed: int) -> None:
+        self.atoms = atoms
+        self.batch = batch
+        self.seed = seed  # the Philox key: the counter-based stream replaces the reference's `rng`
+        self.last_results: dict[str, Any] = {}
+
+    def save_state(self) -> None:
+        """Accepted moves are committed in place by the kernels."""
+
+    def revert_state(self) -> None:
+        """Rejected trials are never written by the kernels; nothing to undo."""
+
+    def to_dict(self) -> dict[str, Any]:
+        return {"last_results": self.last_results}
+
+
+class DisplacementContext(Context):
+    @property
+    def temperature(self) -> np.ndarray:
+        return self.batch.temperature.cpu().numpy()
+
+    @temperature.setter
+    def temperature(self, value) -> None:
+        self.batch.set_temperature(value)
+
+    @property
+    def last_positions(self) -> np.ndarray:
+        return self.batch.positions()
+
+    @property
+    def last_potential_energy(self) -> np.ndarray:
+        return self.batch.energy.cpu().numpy()
+
+    def to_dict(self) -> dict[str, Any]:
+        return {
+            **super().to_dict(),
+            "temperature": self.temperature,
+            "last_positions": self.last_positions,
+            "last_potential_energy": self.last_potential_energy,
+        }
+
+
+class HamiltonianDisplacementContext(DisplacementContext):
+    @property
+    def last_momenta(self) -> np.ndarray:
+        return np.ascontiguousarray(self.batch.momenta.cpu().numpy().transpose(0, 2, 1))
+
+    @property
+    def last_kinetic_energy(self) -> np.ndarray:
+        return self.batch.kinetic.cpu().numpy()
+
+    def to_dict(self) -> dict[str, Any]:
+        return {**super().to_dict(), "last_momenta": self.last_momenta, "last_kinetic_energy": self.last_kinetic_energy}
+
+
+class DeformationContext(DisplacementContext):
+    @property
+    def pressure(self) -> float:
+        return self.batch.pressure
+
+    @pressure.setter
+    def pressure(self, value: float) -> None:
+        self.batch.pressure = float(value)
+
+    @property
+    def last_cell(self) -> np.ndarray:
+        return self.batch.cell.cpu().numpy().reshape(-1, 3, 3)
+
+    def to_dict(self) -> dict[str, Any]:
+        return {**super().to_dict(), "pressure": self.pressure, "last_cell": self.last_cell}
+
+
+class ExchangeContext(DisplacementContext):
+    def __init__(self, atoms: BatchedAtoms, batch: ReplicaBatch, seed: int) -> None:
+        super().__init__(atoms, batch, seed)
+        self._exchange_atoms = None
+
+    @property
+    def chemical_potential(self) -> float:
+        return self.batch.chemical_potential
+
+    @chemical_potential.setter
+    def chemical_potential(self, value: float) -> None:
+        self.batch.chemical_potential = float(value)
+
+    @property
+    def number_of_exchange_particles(self) -> np.ndarray:
+        return self.batch.n_exchange.cpu().numpy()
+
+    @number_of_exchange_particles.setter
+    def number_of_exchange_particles(self, value) -> None:
+        import torch
+
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.int32), (self.batch.R,)))
+        self.batch.n_exchange.copy_(torch.from_numpy(v))
+
+    @property
+    def accessible_volume(self) -> float:
+        return self.batch.accessible_volume
+
+    @accessible_volume.setter
+    def accessible_volume(self, value: float) -> None:
+        self.batch.accessible_volume = float(value)
+
+    @property
+    def exchange_atoms(self):
+        return self._exchange_atoms
+
+    @exchange_atoms.setter
+    def exchange_atoms(self, value) -> None:
+        """One exchange atom: an ASE-like ``Atoms`` of length 1, or ``(symbol, position)``."""
+        from quansino_b200.calculators import ATOMIC_MASSES
+
+        if value is None:
+            self._exchange_atoms = None
+            return
+        if isinstance(value, (tuple, list)) and isinstance(value[0], str):
+            symbol, pos = value[0], np.asarray(value[1] if len(value) > 1 else (0.0, 0.0, 0.0), dtype=float)
+            mass = ATOMIC_MASSES[symbol]
+        else:
+            symbols = list(value.get_chemical_symbols())
+            if len(symbols) != 1:
+                raise NotImplementedError("molecular exchange (more than one atom per insertion) is SURVEY.md section 8f")
+            symbol, pos, mass = symbols[0], np.asarray(value.positions[0], dtype=float), float(np.sum(value.get_masses()))
+        if symbol != self.batch.symbol:
+            raise NotImplementedError("single-species systems only on the GPU path: the exchange atom must match the batch species")
+        self._exchange_atoms = value
+        self.batch.exchange_mass = float(mass)
+        self.batch.exchange_pos = tuple(float(x) for x in pos)
+
+    def to_dict(self) -> dict[str, Any]:
+        return {
+            **super().to_dict(),
+            "chemical_potential": self.chemical_potential,
+            "number_of_exchange_particles": self.number_of_exchange_particles,
+            "accessible_volume": self.accessible_volume,
+            "exchange_atoms": self._exchange_atoms,
+        }
+
+
+class MultiContexts:
+    """``mc/contexts.py:393-436`` keeps a list of contexts; the batched contexts above already hold every replica."""
+
+    def __init__(self, contexts: list[Context]) -> None:
+        self.contexts = contexts
+        self.active_context = None
+
+    def save_state(self) -> None:
+        for c in self.contexts:
+            c.save_state()
+
+    def revert_state(self) -> None:
+        for c in self.contexts:
+            c.revert_state()
+
+    def to_dict(self) -> dict[str, Any]:
+        return {"contexts": [c.to_dict() for c in self.contexts]}

@@ -1,0 +1,316 @@
+"""The Monte Carlo driver (``src/quansino/mc/driver.py:27-176`` and ``src/quansino/mc/core.py:36-411``) over a batch
+of replicas.
+
+The host keeps quansino's loop -- ``run -> irun -> step``, move registration, observers, ``step_count`` -- while the
+body of ``MonteCarlo.step`` (``mc/core.py:353-384``: select -> propose -> energy -> criteria -> save / revert, once per
+cycle) is ONE kernel launch that performs ``max_cycles`` attempts for every replica.
+
+Deviations from the reference, all explicit:
+
+* ``step()`` still is a generator, but it yields the names of the moves available in this step once per launch, not
+  one name per cycle (the per-cycle selection happens on the device, independently per replica);
+* ``seed`` keys a counter-based Philox stream (DESIGN.md "Random stream") instead of PCG64;
+* forced moves (``minimum_count > 0``), user-defined Python hooks and everything listed in SURVEY.md section 8f raise
+  ``NotImplementedError`` -- nothing falls back to the CPU.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Any, Callable, ClassVar
+from warnings import warn
+
+import numpy as np
+import torch
+
+from quansino_b200 import _lib
+from quansino_b200.batch import BatchedAtoms, ReplicaBatch
+from quansino_b200.mc.contexts import Context
+from quansino_b200.mc.criteria import BaseCriteria
+from quansino_b200.moves.core import BaseMove
+from quansino_b200.utils.moves import MoveStorage
+
+
+class MonteCarlo:
+    """Batched counterpart of ``quansino.mc.core.MonteCarlo``.
+
+    Parameters
+    ----------
+    atoms
+        ``BatchedAtoms``, or one ASE-like ``Atoms`` together with ``replicas``, or a list of ``Atoms``.
+    max_cycles
+        Attempts per step and replica.
+    seed
+        Key of the random stream.
+    replicas, calc, device, replica_offset
+        Batch construction: number of copies of a single ``Atoms``, the potential description
+        (``quansino_b200.calculators``), the CUDA device, and the global id of the first local replica (sharding).
+    steps_per_launch
+        ``run`` fuses up to this many steps into one kernel launch when no observer needs the state in between.
+    resync_interval
+        Every this many steps the caches are re-primed with a full energy evaluation (bounds the drift of the
+        incrementally updated sigma_1 / energy); 0 disables.
+    trace
+        Keep the per-attempt trace of the last launch in ``last_trace`` (parity tests).
+    """
+
+    default_criteria: ClassVar[dict[type, type]] = {BaseMove: BaseCriteria}
+    default_context: ClassVar[type] = Context
+    needs_momenta: ClassVar[bool] = False
+
+    def __init__(
+        self,
+        atoms,
+        max_cycles: int = 1,
+        seed: int | None = None,
+        replicas: int | None = None,
+        calc=None,
+        device: str | torch.device = "cuda",
+        replica_offset: int = 0,
+        steps_per_launch: int = 1,
+        resync_interval: int = 100,
+        trace: bool = False,
+        logging_interval: int = 1,
+    ) -> None:
+        self.moves: dict[str, MoveStorage] = {}
+        self.max_cycles = max_cycles
+        self.acceptance_rate: np.ndarray | float = 0.0
+        self.move_history: list[tuple[str, Any]] = []
+        self._seed = int(seed) if seed else int.from_bytes(os.urandom(8), "little")
+        self.logging_interval = logging_interval
+        self.step_count = 0
+        self.max_steps = 0
+        self.attempt_counter = 0
+        self.steps_per_launch = max(1, int(steps_per_launch))
+        self.resync_interval = int(resync_interval)
+        self.trace = bool(trace)
+        self.last_trace: dict[str, np.ndarray] | None = None
+        self.observers: dict[str, tuple[Callable[[], Any], int]] = {}
+
+        if not isinstance(atoms, BatchedAtoms):
+            atoms = BatchedAtoms.from_ase(atoms, replicas=replicas if not isinstance(atoms, (list, tuple)) else None, calc=calc)
+        self.atoms = atoms
+        self.batch = ReplicaBatch(
+            atoms, calc=calc, device=device, replica_offset=replica_offset, with_momenta=self.needs_momenta
+        )
+        self.context = self.default_context(atoms, self.batch, self._seed)
+        self._lowered: tuple | None = None
+        self._primed = False
+        self._counters_before: torch.Tensor | None = None
+        self._cycles_last_launch = 0
+
+    # -- move registration (mc/core.py:133-184) -------------------------------------------------------
+    def add_move(self, move, criteria=None, name: str = "default", interval: int = 1, probability: float = 1.0, minimum_count: int = 0) -> None:
+        forced_moves_count = sum(self.moves[n].minimum_count for n in self.moves)
+        if forced_moves_count + minimum_count > self.max_cycles:
+            raise ValueError("The number of forced moves exceeds the number of cycles.")
+        if criteria is None:
+            for move_type in self.default_criteria:
+                if isinstance(move, move_type):
+                    criteria = self.default_criteria[move_type]()
+                    break
+        if criteria is None:
+            raise ValueError(f"No criteria provided, and no default criteria found for move type {type(move)}.")
+        if minimum_count:
+            raise NotImplementedError("forced moves (minimum_count > 0) are not available on the GPU path")
+        self.moves[name] = MoveStorage(move=move, criteria=criteria, interval=interval, probability=probability, minimum_count=minimum_count)
+        self._lowered = None
+
+    # -- lowering -----------------------------------------------------------------------------------
+    _criteria_for: ClassVar[dict[int, tuple[str, ...]]] = {
+        _lib.MOVE_DISPLACEMENT: ("CanonicalCriteria",),
+        _lib.MOVE_CELL: ("IsobaricCriteria",),
+        _lib.MOVE_EXCHANGE: ("GrandCanonicalCriteria",),
+        _lib.MOVE_HMC: ("HamiltonianCanonicalCriteria",),
+    }
+
+    def _lower(self, names: list[str]):
+        """POD move table for the given (available) move names; label tables are created once per move."""
+        key = tuple(names)
+        if self._lowered is not None and self._lowered[0] == key:
+            for i, n in enumerate(names):  # probabilities may be changed between steps (mc/core.py:344-347)
+                self._lowered[1][i].probability = float(self.moves[n].probability)
+            return self._lowered[1], self._lowered[2]
+        if len(names) > _lib.QMC_MAX_MOVES:
+            raise NotImplementedError(f"at most {_lib.QMC_MAX_MOVES} moves per step on the GPU path")
+        arr = (_lib.Move * len(names))()
+        n_atoms = self.batch.n_atoms.cpu().numpy()
+        any_exchange = any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE for n in names)
+        keep = []
+        for i, n in enumerate(names):
+            st = self.moves[n]
+            st.criteria._check_supported()
+            m = st.move.lower()
+            if type(st.criteria).__name__ not in self._criteria_for[m.type]:
+                raise NotImplementedError(
+                    f"{type(st.criteria).__name__} with {type(st.move).__name__} is not a combination of the GPU path"
+                )
+            m.probability = float(st.probability)
+            if m.type in (_lib.MOVE_DISPLACEMENT, _lib.MOVE_EXCHANGE):
+                if not hasattr(st, "_label_tensor"):
+                    if any_exchange or not st.move.is_identity(n_atoms):
+                        lab = st.move.validated_labels(self.batch.R, self.batch.n_max, n_atoms)
+                        st._label_tensor = torch.from_numpy(lab).to(self.batch.device)
+                    else:
+                        st._label_tensor = None
+                elif st._label_tensor is None and any_exchange:
+                    lab = st.move.validated_labels(self.batch.R, self.batch.n_max, n_atoms)
+                    st._label_tensor = torch.from_numpy(lab).to(self.batch.device)
+                m.labels = st._label_tensor.data_ptr() if st._label_tensor is not None else None
+                keep.append(st._label_tensor)
+            arr[i] = m
+        self._lowered = (key, arr, keep)
+        return arr, keep
+
+    def labels(self, name: str) -> np.ndarray | None:
+        """Current label table [R][n_max] of a displacement / exchange move (None = arange)."""
+        t = getattr(self.moves[name], "_label_tensor", None)
+        return None if t is None else t.cpu().numpy()
+
+    # -- driver loop (mc/driver.py:91-132) -------------------------------------------------------------
+    def attach(self, function: Callable[[], Any], interval: int = 1, name: str | None = None) -> None:
+        """Attach an observer called every ``interval`` steps (``interval < 0``: once, at step ``abs(interval)``)."""
+        self.observers[name or f"observer_{len(self.observers)}"] = (function, int(interval))
+
+    def call_observers(self) -> None:
+        for function, interval in self.observers.values():
+            if (interval > 0 and self.step_count % interval == 0) or (interval < 0 and self.step_count == abs(interval)):
+                function()
+
+    def validate_simulation(self) -> None:
+        if len(self.moves) == 0:
+            warn("No moves have been added to the Monte Carlo simulation. Please add moves using the `add_move` method.", UserWarning, 2)
+        if not self._primed:
+            self.batch.energy_full()
+            self._primed = True
+
+    def converged(self) -> bool:
+        return self.step_count >= self.max_steps
+
+    def _steps_this_launch(self) -> int:
+        k = min(self.steps_per_launch, self.max_steps - self.step_count)
+        if any(st.interval != 1 for st in self.moves.values()):
+            return 1
+        for _, interval in self.observers.values():
+            if interval > 0:
+                k = min(k, interval - self.step_count % interval)
+            elif interval < 0 and abs(interval) > self.step_count:
+                k = min(k, abs(interval) - self.step_count)
+        if self.resync_interval > 0:
+            k = min(k, self.resync_interval - self.step_count % self.resync_interval)
+        return max(1, k)
+
+    def irun(self, steps: int = 100_000_000):
+        self.validate_simulation()
+        self.max_steps = self.step_count + steps
+        if self.step_count == 0:
+            self.call_observers()
+        while not self.converged():
+            k = self._steps_this_launch()
+            yield self.step(k)
+            self.step_count += k
+            if self.resync_interval > 0 and self.step_count % self.resync_interval == 0:
+                self.batch.energy_full()
+            self.call_observers()
+
+    def srun(self, steps: int = 100_000_000):
+        for step in self.irun(steps):
+            for _ in step:
+                pass
+            yield step
+
+    def run(self, steps: int = 100_000_000) -> None:
+        for step in self.irun(steps):
+            for _ in step:
+                pass
+        self.batch.raise_on_status()
+
+    def yield_moves(self):
+        """Names of the moves available at this step (``mc/core.py:326-333``); the per-cycle choice is made on the
+        device from ``u_select`` with the normalised probabilities."""
+        return [name for name in self.moves if self.step_count % self.moves[name].interval == 0]
+
+    def step(self, n_steps: int = 1):
+        """One (or ``n_steps`` fused) Monte Carlo step(s): ``n_steps * max_cycles`` attempts per replica in one launch."""
+        self.move_history = []
+        names = self.yield_moves()
+        if not names:
+            return
+        if not self._primed:
+            self.validate_simulation()
+        for name in names:
+            yield name
+        n_attempts = int(n_steps) * int(self.max_cycles)
+        self._launch(names, n_attempts)
+        self.attempt_counter += n_attempts
+        self._cycles_last_launch = n_attempts
+        self.move_history = [(name, None) for name in names]
+
+    def _launch(self, names: list[str], n_attempts: int) -> None:
+        moves, _keep = self._lower(names)
+        b = self.batch
+        self._counters_before = b.counters.clone()
+        tr = None
+        bufs = None
+        if self.trace:
+            R = b.R
+            bufs = {
+                "move": torch.zeros((R, n_attempts), dtype=torch.int8, device=b.device),
+                "accepted": torch.zeros((R, n_attempts), dtype=torch.int8, device=b.device),
+                "energy": torch.zeros((R, n_attempts), dtype=torch.float64, device=b.device),
+                "delta": torch.zeros((R, n_attempts), dtype=torch.float64, device=b.device),
+                "moved": torch.zeros((R, n_attempts), dtype=torch.int32, device=b.device),
+            }
+            tr = _lib.Trace(*[bufs[k].data_ptr() for k in ("move", "accepted", "energy", "delta", "moved")])
+        with torch.cuda.device(b.device):
+            bs = b.struct()
+            if moves[0].type == _lib.MOVE_HMC:
+                if len(names) != 1:
+                    raise NotImplementedError("Hamiltonian moves cannot be mixed with other moves in one step on the GPU path")
+                ws_bytes = int(b.lib.qmc_hmc_workspace_bytes(C.byref(bs)))
+                if getattr(self, "_hmc_ws", None) is None or self._hmc_ws.numel() < ws_bytes:
+                    self._hmc_ws = torch.zeros(max(ws_bytes, 8), dtype=torch.uint8, device=b.device)
+                rc = b.lib.qmc_hmc(
+                    C.byref(b.potential), C.byref(bs), C.byref(moves[0]), self._seed, self.attempt_counter, n_attempts,
+                    C.byref(tr) if tr is not None else None, self._hmc_ws.data_ptr(), self._hmc_ws.numel(), b.stream(),
+                )  # fmt: skip
+            else:
+                rc = b.lib.qmc_sweep(
+                    C.byref(b.potential), C.byref(bs), moves, len(names), self._seed, self.attempt_counter, n_attempts,
+                    C.byref(tr) if tr is not None else None, b.stream(),
+                )  # fmt: skip
+        _lib.check(rc)
+        if bufs is not None:
+            self.last_trace = {k: v.cpu().numpy() for k, v in bufs.items()}
+
+    # -- results ------------------------------------------------------------------------------------
+    def counters(self) -> np.ndarray:
+        """[R][move slot][attempted, accepted, failed], accumulated since construction."""
+        return self.batch.counters.cpu().numpy()
+
+    def update_acceptance_rate(self) -> np.ndarray:
+        """``acceptance_rate`` of the last launch per replica: accepted / cycles (failed moves count as rejected,
+        ``mc/core.py:382-384``)."""
+        if self._counters_before is None or self._cycles_last_launch == 0:
+            self.acceptance_rate = np.zeros(self.batch.R)
+        else:
+            d = (self.batch.counters - self._counters_before)[:, :, 1].sum(dim=1).cpu().numpy()
+            self.acceptance_rate = d / float(self._cycles_last_launch)
+        return self.acceptance_rate
+
+    def download(self) -> BatchedAtoms:
+        """Copy the device state back into ``self.atoms`` and return it."""
+        self.batch.download(self.atoms)
+        return self.atoms
+
+    def to_dict(self) -> dict[str, Any]:
+        return {
+            "name": self.__class__.__name__,
+            "kwargs": {"seed": self._seed, "max_cycles": self.max_cycles, "logging_interval": self.logging_interval},
+            "attributes": {"step_count": self.step_count, "attempt_counter": self.attempt_counter},
+            "context": self.context.to_dict(),
+            "moves": {name: st.to_dict() for name, st in self.moves.items()},
+        }
+
+    todict = to_dict

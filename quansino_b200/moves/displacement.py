@@ -1,0 +1,111 @@
+"""Displacement moves (``src/quansino/moves/displacement.py``)."""
+
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+
+from quansino_b200 import _lib
+from quansino_b200.integrators.displacement import Verlet
+from quansino_b200.moves.core import BaseMove
+from quansino_b200.operations.displacement import Ball
+from quansino_b200.utils.dynamics import maxwell_boltzmann_distribution
+
+
+class DisplacementMove(BaseMove):
+    """``DisplacementMove(labels, operation=None, apply_constraints=True)`` (``moves/displacement.py:28-273``).
+
+    ``labels`` has shape (n_atoms,) -- shared by every replica -- or (n_replicas, n_max).  Atoms with negative labels
+    are not displaced.  First pass of the GPU path: every non-negative label marks exactly ONE atom, and the
+    non-negative labels increase with the atom index (what ``arange`` and the reference's own ``max + 1`` appending
+    produce); label groups (molecules) are refused."""
+
+    move_type = _lib.MOVE_DISPLACEMENT
+
+    def __init__(self, labels, operation=None, apply_constraints: bool = True) -> None:
+        self.to_displace_labels = None
+        self.displaced_labels = None
+        self.default_label: int | None = None
+        self.set_labels(labels)
+        super().__init__(operation, apply_constraints)
+
+    def set_labels(self, new_labels) -> None:
+        self.labels = np.asarray(new_labels)
+        self.unique_labels = np.unique(self.labels[self.labels >= 0])
+
+    @property
+    def default_operation(self):
+        return Ball(0.1)
+
+    def validated_labels(self, n_replicas: int, n_max: int, n_atoms: np.ndarray) -> np.ndarray:
+        """int32 [R][n_max] label table (padding -1), checked against the first-pass restrictions."""
+        lab = np.asarray(self.labels)
+        if lab.ndim == 1:
+            lab = np.broadcast_to(lab, (n_replicas, lab.shape[0]))
+        if lab.shape[0] != n_replicas or lab.shape[1] > n_max:
+            raise ValueError("labels must have shape (n_atoms,) or (n_replicas, n_max)")
+        out = np.full((n_replicas, n_max), -1, dtype=np.int32)
+        out[:, : lab.shape[1]] = lab
+        for r in range(n_replicas):
+            if lab.shape[1] < n_atoms[r]:
+                raise ValueError("Labels must have the same length as the number of atoms.")
+            out[r, n_atoms[r] :] = -1
+            v = out[r, : n_atoms[r]]
+            v = v[v >= 0]
+            if len(v) and np.any(np.diff(v) <= 0):
+                raise NotImplementedError(
+                    "the GPU path needs every non-negative label to mark exactly one atom, increasing with the atom "
+                    "index; label groups (molecular moves) are SURVEY.md section 8f"
+                )
+        return out
+
+    def is_identity(self, n_atoms: np.ndarray) -> bool:
+        lab = np.asarray(self.labels)
+        if lab.ndim != 1 or self.default_label:
+            return False
+        return bool(np.all(n_atoms == len(lab)) and np.array_equal(lab, np.arange(len(lab))))
+
+    def lower(self) -> _lib.Move:
+        self._check_supported()
+        if self.default_label:
+            raise NotImplementedError("a fixed `default_label` creates label groups; not available on the GPU path")
+        m = _lib.Move()
+        m.type = self.move_type
+        m.op, m.step = self.operation.lower()
+        if m.op not in (_lib.OP_BALL, _lib.OP_BOX, _lib.OP_SPHERE):
+            raise NotImplementedError(f"{type(self.operation).__name__} is not a displacement operation of the GPU path")
+        m.default_label = _lib.LABEL_NONE if self.default_label is None else int(self.default_label)
+        return m
+
+    def to_dict(self) -> dict[str, Any]:
+        d = super().to_dict()
+        d["kwargs"]["labels"] = self.labels
+        d["attributes"]["default_label"] = self.default_label
+        return d
+
+
+class HamiltonianDisplacementMove(BaseMove):
+    """``HamiltonianDisplacementMove(distribution=maxwell_boltzmann_distribution, operation=None)``
+    (``moves/displacement.py:275-360``): momentum refresh + Verlet trajectory, fused in one kernel."""
+
+    move_type = _lib.MOVE_HMC
+
+    def __init__(self, distribution=maxwell_boltzmann_distribution, operation=None) -> None:
+        super().__init__(operation, apply_constraints=True)
+        self.max_attempts = 10
+        self.distribution = distribution
+
+    @property
+    def default_operation(self):
+        return Verlet()
+
+    def lower(self) -> _lib.Move:
+        self._check_supported()
+        if self.distribution is not maxwell_boltzmann_distribution:
+            raise NotImplementedError("only maxwell_boltzmann_distribution can be sampled on the device")
+        m = _lib.Move()
+        m.type = self.move_type
+        m.op, m.dt, m.n_steps = self.operation.lower()
+        m.default_label = _lib.LABEL_NONE
+        return m
