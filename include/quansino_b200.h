@@ -159,6 +159,10 @@ int qmc_pt_swap(double *temperatures_all, const double *energies_all, int32_t n_
  * DFMA loop and returns achieved FLOP/s in *flops (2 flop per DFMA). */
 int qmc_fp64_peak(double *flops, void *stream);
 
+/* numerics check of the kernels' branch-free FP64 functions (csrc/fastmath.cuh): out[i] = f(in[i]) on the device,
+ * which = 0 exp, 1 log, 2 sqrt, 3 reciprocal, 4 sin(in) for in in [0, 2 pi], 5 cos(in).  Device pointers. */
+int qmc_debug_math(int32_t which, const double *in, double *out, int32_t n, void *stream);
+
 /* host-buffer convenience: upload `batch_host` (same struct, HOST pointers), prime, run, download. */
 int qmc_sweep_host(const qmc_potential_t *pot, const qmc_batch_t *batch_host, const qmc_move_t *moves_host,
                    int32_t n_moves, uint64_t seed, uint64_t attempt_base, int32_t n_attempts,

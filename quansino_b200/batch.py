@@ -48,8 +48,8 @@ class BatchedAtoms:
             cell = np.diag(cell)
         if cell.shape == (3, 3):
             cell = np.broadcast_to(cell, (R, 3, 3))
-        self.cell = np.ascontiguousarray(cell, dtype=np.float64)
-        self.n_atoms = np.ascontiguousarray(np.broadcast_to(np.asarray(self.n_atoms, dtype=np.int32), (R,)))
+        self.cell = np.array(cell, dtype=np.float64, order="C", copy=True)
+        self.n_atoms = np.array(np.broadcast_to(np.asarray(self.n_atoms, dtype=np.int32), (R,)), order="C", copy=True)
         self.pbc = tuple(bool(b) for b in np.broadcast_to(np.asarray(self.pbc), (3,)))
         if self.momenta is not None:
             self.momenta = np.ascontiguousarray(self.momenta, dtype=np.float64)
@@ -206,7 +206,7 @@ class ReplicaBatch:
         t = np.broadcast_to(np.asarray(temperature, dtype=np.float64), (self.R,))
         if np.any(t == 0.0):
             raise ZeroDivisionError("float division by zero")  # what mc/criteria.py:108-110 raises at T = 0
-        self.temperature.copy_(torch.from_numpy(np.ascontiguousarray(t)))
+        self.temperature.copy_(torch.from_numpy(np.array(t, order="C", copy=True)))
 
     # -- C struct ----------------------------------------------------------------------------------
     def struct(self) -> _lib.Batch:

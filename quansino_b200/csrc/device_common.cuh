@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "../../include/quansino_b200.h"
+#include "fastmath.cuh"
 
 namespace qmc {
 
@@ -80,12 +81,12 @@ struct PotDev {
 };
 
 // sigma_1 and sigma_2 contributions of one neighbour image at squared distance r2 (_calc_theta, _calc_dsigma1,
-// _calc_dsigma2 with chi = 1); zero outside `r < rc_list` (_get_neighbors).
+// _calc_dsigma2 with chi = 1); zero outside `r < rc_list` (_get_neighbors).  Branch-free: 1 sqrt, 3 exp, 1 reciprocal.
 __device__ __forceinline__ void emt_pair(const PotDev &p, double r2, double &s1, double &s2) {
-    const double r = sqrt(r2);
-    const double w = 1.0 / (1.0 + exp(p.acut * (r - p.rc)));
-    const double a = exp(-p.eta2 * (r - p.beta_s0)) * w;
-    const double b = exp(-p.kappa * (r * p.inv_beta - p.s0)) * w;
+    const double r = sqrt_fast(fmax(r2, 1e-200));
+    const double w = rcp_fast(1.0 + exp_fast(p.acut * (r - p.rc)));
+    const double a = exp_fast(-p.eta2 * (r - p.beta_s0)) * w;
+    const double b = exp_fast(-p.kappa * (r * p.inv_beta - p.s0)) * w;
     const bool in = r < p.rc_list;
     s1 = in ? a : 0.0;
     s2 = in ? b : 0.0;
@@ -95,9 +96,9 @@ __device__ __forceinline__ void emt_pair(const PotDev &p, double r2, double &s1,
 // an atom without neighbours keeps energy 0 - E0.
 __device__ __forceinline__ double emt_embed(const PotDev &p, double sigma1) {
     const double sg = sigma1 > 1e-14 ? sigma1 : 1.0;
-    const double ds = log(sg * p.inv12gamma1) * p.neg_inv_beta_eta2;
+    const double ds = log_fast(sg * p.inv12gamma1) * p.neg_inv_beta_eta2;
     const double x = p.lambda * ds;
-    const double e = p.E0 * (1.0 + x) * exp(-x) + p.V0x6 * exp(-p.kappa * ds) - p.E0;
+    const double e = p.E0 * (1.0 + x) * exp_fast(-x) + p.V0x6 * exp_fast(-p.kappa * ds) - p.E0;
     return sigma1 > 1e-14 ? e : -p.E0;
 }
 
@@ -118,7 +119,7 @@ __device__ __forceinline__ double emt_embed_deds(const PotDev &p, double sigma1,
 
 // pair energy of one neighbour image (LennardJones.calculate: c6[r2 > rc^2] = 0; e = 4 eps (c12 - c6) - e0 (c6 != 0))
 __device__ __forceinline__ double lj_pair(const PotDev &p, double r2) {
-    const double q = p.sigma2 / r2;
+    const double q = p.sigma2 * rcp_fast(fmax(r2, 1e-200));
     const double c6 = q * q * q;
     const double e = p.eps4 * (c6 * c6 - c6) - p.lj_e0;
     return (r2 > p.lj_rc2) ? 0.0 : e;

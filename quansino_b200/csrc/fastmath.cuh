@@ -1,0 +1,113 @@
+// Branch-free FP64 elementary functions for the hot kernels (sm_100a).
+//
+// The CUDA math library versions carry a special-case branch (BSSY / BSYNC / slow-path call) per call and
+// re-materialise their coefficients; in the sweep kernel that overhead was 4x the FP64 work itself
+// (profiles/r1_a_baseline.md).  These versions are straight-line DFMA chains with coefficients in the constant
+// bank, valid on the argument ranges the kernels guarantee (stated per function), accurate to <= 1-2 ulp --
+// far inside the 1e-10 parity budget.  tests/test_gpu_math.py checks each against numpy float64.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace qmc {
+
+__device__ __constant__ double FM_EXP[12] = {
+    // 1/k!, k = 2..13
+    5.0e-01, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03, 1.3888888888888889e-03,
+    1.9841269841269841e-04, 2.4801587301587302e-05, 2.7557319223985893e-06, 2.7557319223985888e-07,
+    2.5052108385441720e-08, 2.0876756987868100e-09, 1.6059043836821613e-10};
+__device__ __constant__ double FM_LOG[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
+                                            2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
+                                            1.479819860511658591e-01};
+__device__ __constant__ double FM_SIN[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                                            2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+__device__ __constant__ double FM_COS[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                            -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
+
+constexpr double FM_MAGIC = 6755399441055744.0;  // 1.5 * 2^52
+constexpr double FM_LN2_HI = 6.93147180369123816490e-01, FM_LN2_LO = 1.90821492927058770002e-10;
+
+// 1 / d for normal d (|d| in [1e-300, 1e300]): MUFU.RCP64H seed (2^-20) + two Newton steps
+__device__ __forceinline__ double rcp_fast(double d) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = fma(-d, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-d, y, 1.0);
+    return fma(y, e, y);
+}
+
+// sqrt(x) for normal positive x: MUFU.RSQ64H seed + Goldschmidt, with a final residual correction
+__device__ __forceinline__ double sqrt_fast(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double g = x * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    const double d = fma(-g, g, x);
+    return fma(d, h, g);
+}
+
+// exp(x) for x in [-700, 700]
+__device__ __forceinline__ double exp_fast(double x) {
+    const double t = fma(x, 1.4426950408889634, FM_MAGIC);
+    const double k = t - FM_MAGIC;
+    double r = fma(k, -FM_LN2_HI, x);
+    r = fma(k, -FM_LN2_LO, r);
+    double q = FM_EXP[11];
+#pragma unroll
+    for (int i = 10; i >= 0; --i) q = fma(q, r, FM_EXP[i]);
+    const double r2 = r * r;
+    const double p = fma(r2, q, r) + 1.0;
+    const int n = __double2loint(t);
+    return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// log(x) for normal positive x (fdlibm e_log.c scheme)
+__device__ __forceinline__ double log_fast(double x) {
+    int hx = __double2hiint(x);
+    const int lx = __double2loint(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    const int i = (hx + 0x95f64) & 0x100000;
+    k += i >> 20;
+    const double m = __hiloint2double(hx | (i ^ 0x3ff00000), lx);  // in [sqrt(2)/2, sqrt(2))
+    const double f = m - 1.0;
+    const double s = f * rcp_fast(2.0 + f);
+    const double z = s * s;
+    double R = FM_LOG[6];
+#pragma unroll
+    for (int j = 5; j >= 0; --j) R = fma(R, z, FM_LOG[j]);
+    R *= z;
+    const double hfsq = 0.5 * f * f;
+    const double dk = (double)k;
+    return dk * FM_LN2_HI - ((hfsq - (s * (hfsq + R) + dk * FM_LN2_LO)) - f);
+}
+
+// sin and cos of phi in [0, 2 pi]  (fdlibm k_sin / k_cos kernels after a two-term pi/2 reduction)
+__device__ __forceinline__ void sincos_2pi(double phi, double &sn, double &cs) {
+    const double t = fma(phi, 6.36619772367581382433e-01, FM_MAGIC);
+    const double q = t - FM_MAGIC;
+    double r = fma(q, -1.57079632673412561417e+00, phi);
+    r = fma(q, -6.07710050650619224932e-11, r);
+    const double z = r * r;
+    double ps = FM_SIN[5], pc = FM_COS[5];
+#pragma unroll
+    for (int j = 4; j >= 0; --j) {
+        ps = fma(ps, z, FM_SIN[j]);
+        pc = fma(pc, z, FM_COS[j]);
+    }
+    const double s = fma(r * z, ps, r);
+    const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int n = __double2loint(t) & 3;
+    const double a = (n & 1) ? c : s, b = (n & 1) ? s : c;
+    sn = (n & 2) ? -a : a;
+    cs = ((n + 1) & 2) ? -b : b;
+}
+
+}  // namespace qmc

@@ -117,21 +117,29 @@ int set_smem(K kernel, size_t bytes) {
     return QMC_OK;
 }
 
-template <int POT>
-int launch_sweep(const qmc::SweepArgs &a, const Geometry &g, cudaStream_t s) {
+template <int POT, int FEAT>
+int launch_sweep_feat(const qmc::SweepArgs &a, const Geometry &g, cudaStream_t s) {
     int rc;
     if (g.warps == 4) {
-        if ((rc = set_smem(qmc::sweep_kernel<POT, 4, 7>, g.smem))) return rc;
-        qmc::sweep_kernel<POT, 4, 7><<<g.grid, 128, g.smem, s>>>(a);
+        if ((rc = set_smem(qmc::sweep_kernel<POT, 4, 7, FEAT>, g.smem))) return rc;
+        qmc::sweep_kernel<POT, 4, 7, FEAT><<<g.grid, 128, g.smem, s>>>(a);
     } else if (g.warps == 2) {
-        if ((rc = set_smem(qmc::sweep_kernel<POT, 2, 14>, g.smem))) return rc;
-        qmc::sweep_kernel<POT, 2, 14><<<g.grid, 64, g.smem, s>>>(a);
+        if ((rc = set_smem(qmc::sweep_kernel<POT, 2, 14, FEAT>, g.smem))) return rc;
+        qmc::sweep_kernel<POT, 2, 14, FEAT><<<g.grid, 64, g.smem, s>>>(a);
     } else {
-        if ((rc = set_smem(qmc::sweep_kernel<POT, 1, 16>, g.smem))) return rc;
-        qmc::sweep_kernel<POT, 1, 16><<<g.grid, 32, g.smem, s>>>(a);
+        if ((rc = set_smem(qmc::sweep_kernel<POT, 1, 16, FEAT>, g.smem))) return rc;
+        qmc::sweep_kernel<POT, 1, 16, FEAT><<<g.grid, 32, g.smem, s>>>(a);
     }
     CUDA_TRY(cudaGetLastError());
     return QMC_OK;
+}
+
+// three instantiations per potential: canonical fast path, + cell moves, everything (labels + exchange + cell)
+template <int POT>
+int launch_sweep(const qmc::SweepArgs &a, const Geometry &g, int feat, cudaStream_t s) {
+    if (feat == 0) return launch_sweep_feat<POT, 0>(a, g, s);
+    if (feat == qmc::F_CELL) return launch_sweep_feat<POT, qmc::F_CELL>(a, g, s);
+    return launch_sweep_feat<POT, qmc::F_LABELS | qmc::F_CELL | qmc::F_EXCHANGE>(a, g, s);
 }
 
 template <int POT>
@@ -160,6 +168,21 @@ __global__ void fp64_peak_kernel(double *out, int iters) {
         a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
     }
     if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 123.456) out[0] = a0;
+}
+
+__global__ void debug_math_kernel(int which, const double *in, double *out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = in[i];
+    double s, c;
+    switch (which) {
+        case 0: out[i] = qmc::exp_fast(x); break;
+        case 1: out[i] = qmc::log_fast(x); break;
+        case 2: out[i] = qmc::sqrt_fast(x); break;
+        case 3: out[i] = qmc::rcp_fast(x); break;
+        case 4: qmc::sincos_2pi(x, s, c); out[i] = s; break;
+        default: qmc::sincos_2pi(x, s, c); out[i] = c; break;
+    }
 }
 
 }  // namespace
@@ -261,12 +284,21 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     a.seed = seed;
     a.attempt_base = attempt_base;
     a.n_attempts = n_attempts;
-    if (trace) a.tr = *trace;
+    if (trace) {
+        a.tr = *trace;
+        a.has_trace = 1;
+    }
+    int feat = 0;
+    for (int m = 0; m < n_moves; ++m) {
+        if (moves[m].labels) feat |= qmc::F_LABELS;
+        if (moves[m].type == QMC_MOVE_CELL) feat |= qmc::F_CELL;
+        if (moves[m].type == QMC_MOVE_EXCHANGE) feat |= qmc::F_EXCHANGE;
+    }
     Geometry g;
     if ((rc = pick_geometry(pot->kind, batch->n_max, batch->n_replicas, g))) return rc;
     a.smem_per_warp = (long long)(g.smem / g.warps);
     cudaStream_t s = (cudaStream_t)stream;
-    return pot->kind == QMC_POT_EMT ? launch_sweep<QMC_POT_EMT>(a, g, s) : launch_sweep<QMC_POT_LJ>(a, g, s);
+    return pot->kind == QMC_POT_EMT ? launch_sweep<QMC_POT_EMT>(a, g, feat, s) : launch_sweep<QMC_POT_LJ>(a, g, feat, s);
 }
 
 int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double *forces, void *stream) {
@@ -339,6 +371,14 @@ int qmc_fp64_peak(double *flops, void *stream) {
     cudaFree(d);
     CUDA_TRY(cudaGetLastError());
     *flops = best;
+    return QMC_OK;
+}
+
+int qmc_debug_math(int32_t which, const double *in, double *out, int32_t n, void *stream) {
+    if (!in || !out || n < 0 || which < 0 || which > 5) return fail(QMC_ERR_INVALID, "bad arguments");
+    if (n == 0) return QMC_OK;
+    debug_math_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(which, in, out, n);
+    CUDA_TRY(cudaGetLastError());
     return QMC_OK;
 }
 

@@ -34,6 +34,7 @@ struct SweepArgs {
     int need_coin;  // any exchange move present
     unsigned long long seed, attempt_base;
     int n_attempts;
+    int has_trace;
     qmc_trace_t tr;
     long long smem_per_warp;
 };
@@ -109,20 +110,31 @@ __device__ inline void shift_down(double *arr, int removed, int n) {
 
 // --- local energy delta -----------------------------------------------------------------------------------------
 struct Trial {
-    double dE;       // energy difference of the whole system
-    double sig_i;    // sigma_1 of the moved atom at its new position (EMT)
-    double eat_i;    // its embedding energy there
-    int n2;          // atoms whose sigma_1 changed (entries of l2; trial sigma in dsig[j], trial energy in lr[e])
-    int pairs;       // pair evaluations done (warp total)
+    double dE;     // energy difference of the whole system
+    double sig_i;  // sigma_1 of the moved atom at its new position (EMT)
+    double eat_i;  // its embedding energy there
+    int n2;        // atoms whose sigma_1 changed: l2[0..n2); their trial embedding energies sit in lr[cape + e]
+    int pairs;     // pair evaluations done (per-lane partial)
 };
 
+// sigma_1 change of touched atom j, gathered from the list through pp[j] (terms of second images were added onto the
+// nearest-image slots by eval_list)
+__device__ __forceinline__ double gathered_dsigma(const Replica &R, int j) {
+    const unsigned code = R.pp[j];
+    const unsigned po = code & 0xFFFFu, pn = code >> 16;
+    const double so = po != NOPOS ? R.lr[po] : 0.0;
+    const double sn = pn != NOPOS ? R.lr[pn] : 0.0;
+    return sn - so;
+}
+
 template <int POT>
-__device__ __forceinline__ Trial local_delta(const PotDev &pot, Replica &R, int n_scan, int i, bool has_old, bool has_new,
-                                             const double po[3], const double pn[3]) {
-    const int lane = lane_id();
+__device__ __forceinline__ Trial local_delta(const PotDev &pot, Replica &R, const int lane, const unsigned lt, int n_scan, int i,
+                                             bool has_old, bool has_new, const double po[3], const double pn[3], int &status) {
     Trial T;
     DeltaAcc acc = {0.0, 0.0, 0};
-    T.n2 = scan_and_accumulate<POT, 0>(pot, R, n_scan, has_old ? i : -1, has_old, has_new, po, pn, acc);
+    int xstart;
+    const int cnt = scan_neighbours<POT, 0>(pot, R, lane, lt, n_scan, has_old ? i : -1, has_old, has_new, po, pn, T.n2, xstart, status);
+    eval_list<POT, 0>(pot, R, lane, cnt, xstart, acc);
     const double vs = warp_sum(acc.v);
     T.pairs = acc.pairs;
     T.sig_i = 0.0;
@@ -132,21 +144,18 @@ __device__ __forceinline__ Trial local_delta(const PotDev &pot, Replica &R, int 
         return T;
     }
     if (has_new) T.sig_i = warp_sum(acc.snew);
+    double *et = R.lr + R.cape;
     double part = 0.0, e_i_lane = 0.0;
     const int total = T.n2 + (has_new ? 1 : 0);
     for (int e = lane; e < total; e += 32) {
         const bool nb = e < T.n2;
         const int j = nb ? R.l2[e] : 0;
-        const double sn = nb ? (R.sig[j] + R.dsig[j]) : T.sig_i;
+        const double sn = nb ? (R.sig[j] + gathered_dsigma(R, j)) : T.sig_i;
         const double eold = nb ? R.eat[j] : (has_old ? R.eat[i] : 0.0);
         const double en = emt_embed(pot, sn);
         part += en - eold;
-        if (nb) {
-            R.dsig[j] = sn;
-            R.lr[e] = en;
-        } else {
-            e_i_lane = en;
-        }
+        if (nb) et[e] = en;
+        else e_i_lane = en;
     }
     if (has_new) T.eat_i = __shfl_sync(FULL, e_i_lane, T.n2 & 31);
     if (!has_new && lane == 0) part -= R.eat[i];  // deletion: the atom's own embedding energy disappears
@@ -156,16 +165,15 @@ __device__ __forceinline__ Trial local_delta(const PotDev &pot, Replica &R, int 
     return T;
 }
 
+// commit the trial values of the touched atoms (accepted moves only; a rejected trial leaves no trace)
 template <int POT>
-__device__ __forceinline__ void finish_trial(Replica &R, const Trial &T, bool accept) {
+__device__ __forceinline__ void commit_trial(Replica &R, const int lane, const Trial &T) {
     if (POT != QMC_POT_EMT) return;
-    for (int e = lane_id(); e < T.n2; e += 32) {
+    const double *et = R.lr + R.cape;
+    for (int e = lane; e < T.n2; e += 32) {
         const int j = R.l2[e];
-        if (accept) {
-            R.sig[j] = R.dsig[j];
-            R.eat[j] = R.lr[e];
-        }
-        R.dsig[j] = 0.0;
+        R.sig[j] = R.sig[j] + gathered_dsigma(R, j);
+        R.eat[j] = et[e];
     }
     __syncwarp();
 }
@@ -184,10 +192,45 @@ __device__ inline double gc_probability(double dE, int delta, int n_ex, double a
     return exp(exponential) * prefactor;
 }
 
-template <int POT, int WARPS, int MINB>
+// feature bits of a sweep-kernel instantiation: code for move types that are not in the table is compiled out, which
+// keeps the canonical fast path inside its register budget
+constexpr int F_LABELS = 1;    // label tables in global memory (not arange)
+constexpr int F_CELL = 2;      // cell moves
+constexpr int F_EXCHANGE = 4;  // exchange moves
+
+// the random numbers of one attempt: lanes 0..3 run one Philox block each, the six / seven doubles are broadcast
+struct Draws {
+    double u_select, u_label, o0, o1, o2, u_accept, u_coin;
+};
+
+__device__ __forceinline__ Draws draw_attempt(PhiloxKey key, unsigned long long attempt, uint32_t replica, const int lane,
+                                              bool need_coin) {
+    double d0, d1;
+    uniform_pair(key, attempt, replica, (uint32_t)(lane & 3), d0, d1);
+    Draws D;
+    D.u_select = __shfl_sync(FULL, d0, 0);
+    D.u_label = __shfl_sync(FULL, d1, 0);
+    D.o0 = __shfl_sync(FULL, d0, 1);
+    D.o1 = __shfl_sync(FULL, d1, 1);
+    D.o2 = __shfl_sync(FULL, d0, 2);
+    D.u_accept = __shfl_sync(FULL, d1, 2);
+    D.u_coin = need_coin ? __shfl_sync(FULL, d0, 3) : 0.0;
+    return D;
+}
+
+// u < exp(x) without evaluating exp where the answer is already decided; flags the reference's OverflowError
+__device__ __forceinline__ bool metropolis(double u, double x, int &status) {
+    if (x > EXP_OVERFLOW) status |= QMC_STATUS_EXP_OVERFLOW;
+    if (x >= 0.0) return true;  // exp(x) >= 1 > u
+    if (!(x > -700.0)) return false;  // exp(x) < 1e-304: below every u > 0 (u == 0 has probability 2^-53; DESIGN.md ties)
+    return u < exp_fast(x);
+}
+
+template <int POT, int WARPS, int MINB, int FEAT>
 __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_constant__ SweepArgs a) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
     const int r = blockIdx.x * WARPS + warp;
     if (r >= a.b.n_replicas) return;  // whole warp exits; no block-wide barrier is used below
     const PotDev &pot = a.pot;
@@ -208,7 +251,6 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
         if (POT == QMC_POT_EMT) {
             R.sig[j] = in ? gs[j] : 0.0;
             R.eat[j] = in ? ge[j] : 0.0;
-            R.dsig[j] = 0.0;
         }
     }
     double cell[3] = {a.b.cell[(size_t)r * 9 + 0], a.b.cell[(size_t)r * 9 + 4], a.b.cell[(size_t)r * 9 + 8]};
@@ -217,7 +259,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
     double E = a.b.energy[r];
     const double temperature = a.b.temperature[r];
     const double kT = temperature * KB;
-    int n_ex = a.b.n_exchange ? a.b.n_exchange[r] : 0;
+    int n_ex = (FEAT & F_EXCHANGE) ? a.b.n_exchange[r] : 0;
     const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
     const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
     long long n_pairs = 0;
@@ -225,16 +267,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
 
     for (int k = 0; k < a.n_attempts; ++k) {
         const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
-        double u_select, u_label, o0, o1, o2, u_accept, u_coin = 0.0, u_spare;
-        uniform_pair(key, attempt, grep, 0, u_select, u_label);
-        uniform_pair(key, attempt, grep, 1, o0, o1);
-        uniform_pair(key, attempt, grep, 2, o2, u_accept);
-        if (a.need_coin) uniform_pair(key, attempt, grep, 3, u_coin, u_spare);
+        const Draws D = draw_attempt(key, attempt, grep, lane, (FEAT & F_EXCHANGE) != 0);
 
         int m = 0;
-        while (m < a.n_moves - 1 && a.cdf[m] <= u_select) ++m;
+        while (m < a.n_moves - 1 && a.cdf[m] <= D.u_select) ++m;
         const MoveDev &mv = a.mv[m];
-        const int *lab = mv.labels ? mv.labels + (size_t)r * nmax : nullptr;
+        const int *lab = ((FEAT & F_LABELS) && mv.labels) ? mv.labels + (size_t)r * nmax : nullptr;
 
         int accepted = -1, moved = -1;
         double delta = __longlong_as_double(0x7ff8000000000000LL);  // NaN
@@ -242,41 +280,39 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
         if (mv.type == QMC_MOVE_DISPLACEMENT) {
             const int nu = lab ? count_labelled(lab, R.n) : R.n;
             if (nu > 0) {
-                const int idx = (int)(u_label * (double)nu);
+                const int idx = (int)(D.u_label * (double)nu);
                 const int i = lab ? select_labelled(lab, R.n, idx) : idx;
                 double t[3];
                 if (mv.op == QMC_OP_BALL) {
-                    const double rr = mv.step * o0, phi = TWO_PI * o1, c = -1.0 + 2.0 * o2;
-                    const double s = sqrt(__dsub_rn(1.0, __dmul_rn(c, c)));
+                    const double rr = mv.step * D.o0, phi = TWO_PI * D.o1, c = -1.0 + 2.0 * D.o2;
+                    const double s = sqrt_fast(fmax(__dsub_rn(1.0, __dmul_rn(c, c)), 1e-300));
                     double sp, cp;
-                    sincos(phi, &sp, &cp);
+                    sincos_2pi(phi, sp, cp);
                     t[0] = __dmul_rn(__dmul_rn(rr, s), cp);
                     t[1] = __dmul_rn(__dmul_rn(rr, s), sp);
                     t[2] = __dmul_rn(rr, c);
                 } else if (mv.op == QMC_OP_SPHERE) {
-                    const double phi = TWO_PI * o0, c = -1.0 + 2.0 * o1;
-                    const double s = sqrt(__dsub_rn(1.0, __dmul_rn(c, c)));
+                    const double phi = TWO_PI * D.o0, c = -1.0 + 2.0 * D.o1;
+                    const double s = sqrt_fast(fmax(__dsub_rn(1.0, __dmul_rn(c, c)), 1e-300));
                     double sp, cp;
-                    sincos(phi, &sp, &cp);
+                    sincos_2pi(phi, sp, cp);
                     t[0] = __dmul_rn(mv.step, __dmul_rn(s, cp));
                     t[1] = __dmul_rn(mv.step, __dmul_rn(s, sp));
                     t[2] = __dmul_rn(mv.step, c);
                 } else {  // QMC_OP_BOX
                     const double w = mv.step - -mv.step;
-                    t[0] = __dadd_rn(-mv.step, __dmul_rn(w, o0));
-                    t[1] = __dadd_rn(-mv.step, __dmul_rn(w, o1));
-                    t[2] = __dadd_rn(-mv.step, __dmul_rn(w, o2));
+                    t[0] = __dadd_rn(-mv.step, __dmul_rn(w, D.o0));
+                    t[1] = __dadd_rn(-mv.step, __dmul_rn(w, D.o1));
+                    t[2] = __dadd_rn(-mv.step, __dmul_rn(w, D.o2));
                 }
                 const double po[3] = {R.x[i], R.y[i], R.z[i]};
                 const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
-                const Trial T = local_delta<POT>(pot, R, R.n, i, true, true, po, pn);
+                const Trial T = local_delta<POT>(pot, R, lane, lt, R.n, i, true, true, po, pn, status);
                 n_pairs += T.pairs;
                 delta = T.dE;
-                const double x = -delta / kT;
-                if (x > EXP_OVERFLOW) status |= QMC_STATUS_EXP_OVERFLOW;
-                const bool acc = u_accept < exp(x);
-                finish_trial<POT>(R, T, acc);
+                const bool acc = metropolis(D.u_accept, -delta / kT, status);
                 if (acc) {
+                    commit_trial<POT>(R, lane, T);
                     if (lane == 0) {
                         R.x[i] = pn[0];
                         R.y[i] = pn[1];
@@ -292,7 +328,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
                 accepted = acc ? 1 : 0;
                 moved = i;
             }
-        } else if (mv.type == QMC_MOVE_CELL) {
+        } else if ((FEAT & F_CELL) && mv.type == QMC_MOVE_CELL) {
             // snapshot the last accepted state in global memory, deform in place, recompute everything
             for (int j = lane; j < R.n; j += 32) {
                 gx[j] = R.x[j];
@@ -303,7 +339,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
                     ge[j] = R.eat[j];
                 }
             }
-            const double s = exp(__dadd_rn(-mv.step, __dmul_rn(mv.step - -mv.step, o0)));
+            const double s = exp(__dadd_rn(-mv.step, __dmul_rn(mv.step - -mv.step, D.o0)));
             double ncell[3], scale[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
@@ -319,13 +355,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
             const bool cell_ok = replica_set_cell(R, ncell, a.b.pbc, pot.cut);
             if (!cell_ok) status |= QMC_STATUS_CELL_TOO_SMALL;
             long long fp = 0;
-            const double e_new = cell_ok ? replica_full_energy<POT>(pot, R, fp) : E;
+            const double e_new = cell_ok ? replica_full_energy<POT>(pot, R, lane, fp, status) : E;
             n_pairs += fp;
             delta = e_new - E;
             const double v_new = fabs((ncell[0] * ncell[1]) * ncell[2]), v_old = fabs((cell[0] * cell[1]) * cell[2]);
             const double x = -(delta + a.b.pressure * (v_new - v_old)) / kT + (double)(R.n + 1) * log(v_new / v_old);
-            if (x > EXP_OVERFLOW) status |= QMC_STATUS_EXP_OVERFLOW;
-            const bool acc = cell_ok && (u_accept < exp(x));
+            const bool acc = cell_ok && metropolis(D.u_accept, x, status);
             if (acc) {
                 E = e_new;
                 cell[0] = ncell[0];
@@ -345,8 +380,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
             }
             __syncwarp();
             accepted = acc ? 1 : 0;
-        } else if (mv.type == QMC_MOVE_EXCHANGE) {
-            const bool is_add = u_coin < mv.bias;
+        } else if ((FEAT & F_EXCHANGE) && mv.type == QMC_MOVE_EXCHANGE) {
+            const bool is_add = D.u_coin < mv.bias;
             int pd = 0, i = -1;
             Trial T;
             double pn[3] = {0, 0, 0}, po[3] = {0, 0, 0};
@@ -355,25 +390,25 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
                     status |= QMC_STATUS_CAPACITY;
                 } else {
                     // Translation: uniform(0,1,(1,3)) @ cell - mean(positions[moving]); diagonal cell
-                    const double f[3] = {o0, o1, o2};
+                    const double f[3] = {D.o0, D.o1, D.o2};
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
                         const double fc = __dmul_rn(f[d], cell[d]);
                         pn[d] = __dadd_rn(a.b.exchange_pos[d], __dsub_rn(fc, a.b.exchange_pos[d]));
                     }
                     i = R.n;
-                    T = local_delta<POT>(pot, R, R.n, i, false, true, po, pn);
+                    T = local_delta<POT>(pot, R, lane, lt, R.n, i, false, true, po, pn, status);
                     pd = 1;
                 }
             } else {
                 const int nu = lab ? count_labelled(lab, R.n) : R.n;
                 if (nu > 0) {
-                    const int idx = (int)(u_label * (double)nu);
+                    const int idx = (int)(D.u_label * (double)nu);
                     i = lab ? select_labelled(lab, R.n, idx) : idx;
                     po[0] = R.x[i];
                     po[1] = R.y[i];
                     po[2] = R.z[i];
-                    T = local_delta<POT>(pot, R, R.n, i, true, false, po, pn);
+                    T = local_delta<POT>(pot, R, lane, lt, R.n, i, true, false, po, pn, status);
                     pd = -1;
                 }
             }
@@ -384,9 +419,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
                 const double prob = gc_probability(delta, pd, n_ex, a.b.accessible_volume, a.b.exchange_mass, temperature,
                                                    a.b.chemical_potential, ov);
                 if (ov) status |= QMC_STATUS_EXP_OVERFLOW;
-                const bool acc = u_accept < prob;
-                finish_trial<POT>(R, T, acc);
+                const bool acc = D.u_accept < prob;
                 if (acc) {
+                    commit_trial<POT>(R, lane, T);
                     // GrandCanonical.save_state (mc/gcmc.py:207-214): every registered move re-labels
                     for (int q = 0; q < a.n_moves; ++q)
                         if (a.mv[q].labels)
@@ -426,12 +461,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
             atomicAdd(cnt + 0, 1ull);
             if (accepted == 1) atomicAdd(cnt + 1, 1ull);
             if (accepted < 0) atomicAdd(cnt + 2, 1ull);
-            const size_t ti = (size_t)r * a.n_attempts + k;
-            if (a.tr.move) a.tr.move[ti] = (int8_t)m;
-            if (a.tr.accepted) a.tr.accepted[ti] = (int8_t)accepted;
-            if (a.tr.energy) a.tr.energy[ti] = E;
-            if (a.tr.delta) a.tr.delta[ti] = delta;
-            if (a.tr.moved) a.tr.moved[ti] = moved;
+            if (a.has_trace) {
+                const size_t ti = (size_t)r * a.n_attempts + k;
+                if (a.tr.move) a.tr.move[ti] = (int8_t)m;
+                if (a.tr.accepted) a.tr.accepted[ti] = (int8_t)accepted;
+                if (a.tr.energy) a.tr.energy[ti] = E;
+                if (a.tr.delta) a.tr.delta[ti] = delta;
+                if (a.tr.moved) a.tr.moved[ti] = moved;
+            }
         }
     }
 
@@ -452,7 +489,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
         a.b.cell[(size_t)r * 9 + 0] = cell[0];
         a.b.cell[(size_t)r * 9 + 4] = cell[1];
         a.b.cell[(size_t)r * 9 + 8] = cell[2];
-        if (a.b.n_exchange) a.b.n_exchange[r] = n_ex;
+        if (FEAT & F_EXCHANGE) a.b.n_exchange[r] = n_ex;
         if (status) atomicOr(a.b.status + r, status);
     }
     if (a.b.pair_evals) {
@@ -478,13 +515,13 @@ __global__ void __launch_bounds__(WARPS * 32) energy_kernel(const __grid_constan
         R.x[j] = in ? gx[j] : 0.0;
         R.y[j] = in ? gy[j] : 0.0;
         R.z[j] = in ? gz[j] : 0.0;
-        if (POT == QMC_POT_EMT) R.dsig[j] = 0.0;
     }
     const double cell[3] = {a.b.cell[(size_t)r * 9 + 0], a.b.cell[(size_t)r * 9 + 4], a.b.cell[(size_t)r * 9 + 8]};
     const bool ok = replica_set_cell(R, cell, a.b.pbc, a.pot.cut);
     __syncwarp();
     long long pairs = 0;
-    const double E = ok ? replica_full_energy<POT>(a.pot, R, pairs) : __longlong_as_double(0x7ff8000000000000LL);
+    int status = 0;
+    const double E = ok ? replica_full_energy<POT>(a.pot, R, lane, pairs, status) : __longlong_as_double(0x7ff8000000000000LL);
     if (POT == QMC_POT_EMT) {
         for (int j = lane; j < R.n; j += 32) {
             a.b.sigma1[(size_t)r * nmax + j] = R.sig[j];
@@ -495,7 +532,8 @@ __global__ void __launch_bounds__(WARPS * 32) energy_kernel(const __grid_constan
     if (lane == 0) {
         a.b.energy[r] = E;
         if (pair_count) pair_count[r] = pairs;
-        if (!ok) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
+        if (!ok) status |= QMC_STATUS_CELL_TOO_SMALL;
+        if (status) atomicOr(a.b.status + r, status);
     }
 }
 

@@ -108,7 +108,7 @@ class ExchangeContext(DisplacementContext):
     def number_of_exchange_particles(self, value) -> None:
         import torch
 
-        v = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=np.int32), (self.batch.R,)))
+        v = np.array(np.broadcast_to(np.asarray(value, dtype=np.int32), (self.batch.R,)), order="C", copy=True)
         self.batch.n_exchange.copy_(torch.from_numpy(v))
 
     @property
