@@ -91,6 +91,9 @@ typedef struct qmc_batch {
     int32_t n_max;          /* per-replica atom capacity (row stride of the per-atom arrays) */
     int32_t replica_offset; /* global id of local replica 0 */
     int32_t pbc[3];
+    int32_t cells_uniform;  /* != 0: every replica has the fixed cell diag(cell_diag) (fast path); cell moves clear it */
+    int32_t _pad;
+    double cell_diag[3];
     double *pos;            /* [R][3][n_max]  x-row, y-row, z-row per replica */
     double *cell;           /* [R][9] row-major, diagonal */
     int32_t *n_atoms;       /* [R] */

@@ -59,6 +59,9 @@ class Batch(C.Structure):
         ("n_max", C.c_int32),
         ("replica_offset", C.c_int32),
         ("pbc", C.c_int32 * 3),
+        ("cells_uniform", C.c_int32),
+        ("_pad", C.c_int32),
+        ("cell_diag", C.c_double * 3),
         ("pos", C.c_void_p),
         ("cell", C.c_void_p),
         ("n_atoms", C.c_void_p),

@@ -165,6 +165,8 @@ class ReplicaBatch:
         self.accessible_volume = float(abs(np.linalg.det(atoms.cell[0]))) if R else 0.0
         self.exchange_mass = 0.0
         self.exchange_pos = (0.0, 0.0, 0.0)
+        self.cells_uniform = False
+        self.cell_diag = (0.0, 0.0, 0.0)
         self.set_temperature(temperature)
         self.upload(atoms)
 
@@ -178,6 +180,9 @@ class ReplicaBatch:
         self.cell.copy_(cell, non_blocking=non_blocking)
         self.n_atoms.copy_(n, non_blocking=non_blocking)
         nbytes = pos.numel() * 8 + cell.numel() * 8 + n.numel() * 4
+        # one fixed cell shared by every replica: the kernels read it from their arguments (fast path)
+        self.cells_uniform = bool(self.R > 0 and np.all(atoms.cell == atoms.cell[0]))
+        self.cell_diag = tuple(float(atoms.cell[0, k, k]) for k in range(3)) if self.R else (0.0, 0.0, 0.0)
         if self.momenta is not None and atoms.momenta is not None:
             mom = torch.from_numpy(np.ascontiguousarray(atoms.momenta.transpose(0, 2, 1)))
             self.momenta.copy_(mom, non_blocking=non_blocking)
@@ -213,6 +218,8 @@ class ReplicaBatch:
         b = _lib.Batch()
         b.n_replicas, b.n_max, b.replica_offset = self.R, self.n_max, self.replica_offset
         b.pbc = (C.c_int32 * 3)(*[int(x) for x in self.pbc])
+        b.cells_uniform = int(self.cells_uniform)
+        b.cell_diag = (C.c_double * 3)(*self.cell_diag)
         b.pos, b.cell, b.n_atoms = self.pos.data_ptr(), self.cell.data_ptr(), self.n_atoms.data_ptr()
         b.energy, b.temperature = self.energy.data_ptr(), self.temperature.data_ptr()
         b.sigma1, b.eatom = self.sigma1.data_ptr(), self.eatom.data_ptr()

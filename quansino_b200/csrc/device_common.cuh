@@ -70,7 +70,7 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 struct PotDev {
     int kind;
     // neighbour cutoff, slightly widened for the distance prefilter; the exact test happens in the pair function
-    double cut, cut_pre2;
+    double cut, cut_pre, cut_pre2;
     // EMT (ase/calculators/emt.py, single species)
     double acut, rc, rc_list, eta2, beta_s0, kappa, inv_beta, s0, lambda, E0, V0x6, inv12gamma1, neg_inv_beta_eta2;
     double neghalfv0overgamma2;

@@ -11,7 +11,7 @@
 
 #include "../../include/quansino_b200.h"
 #include "hmc_kernel.cuh"
-#include "sweep_kernel.cuh"
+#include "launchers.h"
 
 namespace {
 
@@ -65,8 +65,8 @@ int make_potdev(const qmc_potential_t *p, qmc::PotDev &d) {
     } else {
         return fail(QMC_ERR_INVALID, "unknown potential kind %d", p->kind);
     }
-    const double cp = d.cut * (1.0 + 1e-9);
-    d.cut_pre2 = cp * cp;
+    d.cut_pre = d.cut * (1.0 + 1e-9);
+    d.cut_pre2 = d.cut_pre * d.cut_pre;
     return QMC_OK;
 }
 
@@ -80,82 +80,30 @@ int check_batch(const qmc_batch_t *b, int kind) {
     return QMC_OK;
 }
 
-struct Geometry {
-    int warps;   // warps (= replicas) per CTA
-    int grid;
-    size_t smem;  // dynamic shared memory per CTA
+struct Inst {
+    int ns;
+    qmc::sweep_launch_fn sweep;
+    qmc::energy_launch_fn energy;
 };
 
-// choose the CTA width that packs the most replicas (warps) onto one SM
-int pick_geometry(int kind, int n_max, int n_replicas, Geometry &g) {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    int smem_sm = 0, smem_blk = 0;
-    CUDA_TRY(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    CUDA_TRY(cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    const int64_t spw = qmc::replica_smem_bytes(kind, n_max);
-    int best_w = 0, best_occ = 0;
-    for (int w : {4, 2, 1}) {
-        const int64_t per_block = spw * w;
-        if (per_block > smem_blk) continue;
-        int blocks = (int)(smem_sm / (per_block + 1024));
-        blocks = std::min(blocks, w == 4 ? 7 : (w == 2 ? 14 : 16));  // __launch_bounds__ minimum-blocks promise
-        const int occ = blocks * w;
-        if (occ > best_occ) { best_occ = occ; best_w = w; }
-    }
-    if (!best_w) return fail(QMC_ERR_UNSUPPORTED, "replica of %d atoms needs %lld B of shared memory (> %d B per CTA)", n_max,
-                             (long long)spw, smem_blk);
-    g.warps = best_w;
-    g.grid = (n_replicas + best_w - 1) / best_w;
-    g.smem = (size_t)spw * best_w;
-    return QMC_OK;
+#define QMC_TABLE_ROW(POT, NS) {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS},
+const Inst g_inst[2][7] = {{QMC_FOR_EACH_NS(QMC_TABLE_ROW, 0)}, {QMC_FOR_EACH_NS(QMC_TABLE_ROW, 1)}};
+
+const Inst *find_inst(int kind, int n_max) {
+    const int ns = qmc::capacity_class(n_max);
+    if (ns == 0 || kind < 0 || kind > 1) return nullptr;
+    for (const Inst &i : g_inst[kind])
+        if (i.ns == ns) return &i;
+    return nullptr;
 }
 
-template <typename K>
-int set_smem(K kernel, size_t bytes) {
-    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return QMC_OK;
-}
-
-template <int POT, int FEAT>
-int launch_sweep_feat(const qmc::SweepArgs &a, const Geometry &g, cudaStream_t s) {
-    int rc;
-    if (g.warps == 4) {
-        if ((rc = set_smem(qmc::sweep_kernel<POT, 4, 7, FEAT>, g.smem))) return rc;
-        qmc::sweep_kernel<POT, 4, 7, FEAT><<<g.grid, 128, g.smem, s>>>(a);
-    } else if (g.warps == 2) {
-        if ((rc = set_smem(qmc::sweep_kernel<POT, 2, 14, FEAT>, g.smem))) return rc;
-        qmc::sweep_kernel<POT, 2, 14, FEAT><<<g.grid, 64, g.smem, s>>>(a);
-    } else {
-        if ((rc = set_smem(qmc::sweep_kernel<POT, 1, 16, FEAT>, g.smem))) return rc;
-        qmc::sweep_kernel<POT, 1, 16, FEAT><<<g.grid, 32, g.smem, s>>>(a);
-    }
-    CUDA_TRY(cudaGetLastError());
-    return QMC_OK;
-}
-
-// three instantiations per potential: canonical fast path, + cell moves, everything (labels + exchange + cell)
-template <int POT>
-int launch_sweep(const qmc::SweepArgs &a, const Geometry &g, int feat, cudaStream_t s) {
-    if (feat == 0) return launch_sweep_feat<POT, 0>(a, g, s);
-    if (feat == qmc::F_CELL) return launch_sweep_feat<POT, qmc::F_CELL>(a, g, s);
-    return launch_sweep_feat<POT, qmc::F_LABELS | qmc::F_CELL | qmc::F_EXCHANGE>(a, g, s);
-}
-
-template <int POT>
-int launch_energy(const qmc::SweepArgs &a, const Geometry &g, long long *pair_count, cudaStream_t s) {
-    int rc;
-    if (g.warps == 4) {
-        if ((rc = set_smem(qmc::energy_kernel<POT, 4>, g.smem))) return rc;
-        qmc::energy_kernel<POT, 4><<<g.grid, 128, g.smem, s>>>(a, pair_count);
-    } else if (g.warps == 2) {
-        if ((rc = set_smem(qmc::energy_kernel<POT, 2>, g.smem))) return rc;
-        qmc::energy_kernel<POT, 2><<<g.grid, 64, g.smem, s>>>(a, pair_count);
-    } else {
-        if ((rc = set_smem(qmc::energy_kernel<POT, 1>, g.smem))) return rc;
-        qmc::energy_kernel<POT, 1><<<g.grid, 32, g.smem, s>>>(a, pair_count);
-    }
-    CUDA_TRY(cudaGetLastError());
+// fills pbc flags and, for batches whose replicas all share one fixed cell, the cell constants in the arguments
+int fill_cell_args(const qmc_batch_t *b, const qmc::PotDev &pd, qmc::SweepArgs &a) {
+    const double diag[3] = {b->cell_diag[0], b->cell_diag[1], b->cell_diag[2]};
+    const double one[3] = {1.0, 1.0, 1.0};
+    const bool ok = qmc::cell_constants(b->cells_uniform ? diag : one, b->pbc, pd.cut_pre, a.cell);
+    if (b->cells_uniform && !ok)
+        return fail(QMC_ERR_UNSUPPORTED, "a periodic cell edge is shorter than the neighbour cutoff %.3f A", pd.cut);
     return QMC_OK;
 }
 
@@ -202,7 +150,12 @@ int qmc_device_count(void) {
 
 int64_t qmc_sweep_smem_per_replica(const qmc_potential_t *pot, int32_t n_max) {
     if (!pot || n_max <= 0) return fail(QMC_ERR_INVALID, "bad arguments");
-    return qmc::replica_smem_bytes(pot->kind, n_max);
+    const bool emt = pot->kind == QMC_POT_EMT;
+    switch (qmc::capacity_class(n_max)) {
+#define QMC_BYTES_CASE(POT, NS) case NS: return emt ? qmc::Layout<0, NS>::BYTES : qmc::Layout<1, NS>::BYTES;
+        QMC_FOR_EACH_NS(QMC_BYTES_CASE, 0)
+        default: return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica sweep kernel");
+    }
 }
 
 int qmc_energy_full(const qmc_potential_t *pot, const qmc_batch_t *batch, int64_t *pair_count, void *stream) {
@@ -214,12 +167,10 @@ int qmc_energy_full(const qmc_potential_t *pot, const qmc_batch_t *batch, int64_
     std::memset(&a, 0, sizeof(a));
     if ((rc = make_potdev(pot, a.pot))) return rc;
     a.b = *batch;
-    Geometry g;
-    if ((rc = pick_geometry(pot->kind, batch->n_max, batch->n_replicas, g))) return rc;
-    a.smem_per_warp = (long long)(g.smem / g.warps);
-    cudaStream_t s = (cudaStream_t)stream;
-    return pot->kind == QMC_POT_EMT ? launch_energy<QMC_POT_EMT>(a, g, (long long *)pair_count, s)
-                                    : launch_energy<QMC_POT_LJ>(a, g, (long long *)pair_count, s);
+    if ((rc = fill_cell_args(batch, a.pot, a))) return rc;
+    const Inst *inst = find_inst(pot->kind, batch->n_max);
+    if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica kernels");
+    return inst->energy(a, (long long *)pair_count, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 
 int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move_t *moves, int32_t n_moves, uint64_t seed,
@@ -288,17 +239,16 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         a.tr = *trace;
         a.has_trace = 1;
     }
-    int feat = 0;
+    int feat = batch->cells_uniform ? 0 : qmc::F_CELLVAR;
     for (int m = 0; m < n_moves; ++m) {
         if (moves[m].labels) feat |= qmc::F_LABELS;
-        if (moves[m].type == QMC_MOVE_CELL) feat |= qmc::F_CELL;
+        if (moves[m].type == QMC_MOVE_CELL) feat |= qmc::F_CELL | qmc::F_CELLVAR;
         if (moves[m].type == QMC_MOVE_EXCHANGE) feat |= qmc::F_EXCHANGE;
     }
-    Geometry g;
-    if ((rc = pick_geometry(pot->kind, batch->n_max, batch->n_replicas, g))) return rc;
-    a.smem_per_warp = (long long)(g.smem / g.warps);
-    cudaStream_t s = (cudaStream_t)stream;
-    return pot->kind == QMC_POT_EMT ? launch_sweep<QMC_POT_EMT>(a, g, feat, s) : launch_sweep<QMC_POT_LJ>(a, g, feat, s);
+    if ((rc = fill_cell_args(batch, a.pot, a))) return rc;
+    const Inst *inst = find_inst(pot->kind, batch->n_max);
+    if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica sweep kernel");
+    return inst->sweep(feat, a, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 
 int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double *forces, void *stream) {
@@ -400,6 +350,7 @@ int qmc_sweep_host(const qmc_potential_t *pot, const qmc_batch_t *h, const qmc_m
     };
     auto cleanup = [&]() { for (void *p : owned) cudaFree(p); };
     qmc_batch_t d = *h;
+    d.cells_uniform = 0;
     int rc = QMC_OK;
 #define UP(field, bytes, src) if (rc == QMC_OK) rc = dev_alloc(bytes, src, (void **)&d.field)
     UP(pos, R * 3 * N * 8, h->pos);

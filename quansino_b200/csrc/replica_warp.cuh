@@ -18,6 +18,9 @@
 //            pp[j] and gets its embedding energy re-evaluated; trial energies go to the tail of the list buffer.
 //   commit   on acceptance sigma_1 / embedding energy of the touched atoms are overwritten; a rejected trial is never
 //            written anywhere.
+//
+// The shared-memory layout is a compile-time function of (potential, NS = padded atom capacity): every array sits at a
+// constant byte offset from the warp's base, so an access is one LDS / STS with an immediate offset.
 #pragma once
 
 #include "device_common.cuh"
@@ -26,78 +29,104 @@ namespace qmc {
 
 constexpr int XCAP = 64;             // capacity for second-image list entries of one attempt
 constexpr unsigned NOPOS = 0xFFFFu;  // pp half-word: no list entry
+constexpr int SMEM_PER_SM = 232448;  // 227 KB usable per SM on sm_100
+constexpr int SMEM_PER_CTA_MAX = 232448 - 1024;
 
-// Per-warp view of the replica in shared memory.
-struct Replica {
-    double *x, *y, *z;  // [ns]
-    double *sig;        // [ns]    sigma_1 cache (EMT)
-    double *eat;        // [ns]    embedding-energy cache (EMT)
-    double *lr;         // [capl]  list: +-r^2 of a hit (sign = side: + new, - old), overwritten by its sigma_1 term;
-                        //         tail [cape, capl) = work-item queue during the scan, trial energies afterwards
-    uint32_t *pp;       // [ns]    list position of atom j's nearest-image hit: old | new << 16 (EMT delta)
-    uint16_t *l2;       // [ns]    atoms whose sigma_1 changes (EMT delta)
-    uint16_t *xj;       // [XCAP]  atom index of each second-image list entry (EMT delta)
-    int n;              // atoms
-    int ns;             // padded capacity
-    int cape;           // list entry capacity (= capl - ns)
-    double L[3], invL[3], thr[3];  // edge, 1/edge, edge - cutoff (a second image exists iff |d| > thr)
-    bool per[3];
+__host__ __device__ constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// atom capacities the kernels are instantiated for
+__host__ __device__ constexpr int capacity_class(int n_max) {
+    return n_max <= 32 ? 32 : n_max <= 64 ? 64 : n_max <= 108 ? 108 : n_max <= 128 ? 128 : n_max <= 256 ? 256 : n_max <= 512 ? 512 : n_max <= 1024 ? 1024 : 0;
+}
+
+template <int POT, int NS>
+struct Layout {
+    static constexpr bool EMT = POT == QMC_POT_EMT;
+    static constexpr int CAPL = round_up(NS + 212, 32);  // list doubles: entries + tail of NS doubles
+    static constexpr int CAPE = CAPL - NS;               // list entry capacity
+    // offsets in doubles / bytes from the warp base
+    static constexpr int X = 0, Y = NS, Z = 2 * NS;
+    static constexpr int SIG = 3 * NS, EAT = 4 * NS;
+    static constexpr int LR = EMT ? 5 * NS : 3 * NS;
+    static constexpr int TAIL = LR + CAPE;
+    static constexpr int CELLC = LR + CAPL;  // 9 doubles: L[3], invL[3], thr[3] (per-replica cells only)
+    static constexpr int PP_B = (CELLC + 10) * 8;  // bytes
+    static constexpr int L2_B = PP_B + (EMT ? NS * 4 : 0);
+    static constexpr int XJ_B = L2_B + (EMT ? NS * 2 : 0);
+    static constexpr int BYTES = round_up(XJ_B + (EMT ? XCAP * 2 : 0), 16);
+    // launch geometry: the CTA width that packs most replicas (warps) onto one SM
+    static constexpr int blocks_for(int w) {
+        const int b = SMEM_PER_SM / (w * BYTES + 1024);
+        const int cap = w == 4 ? 7 : (w == 2 ? 14 : 16);
+        return b < cap ? b : cap;
+    }
+    static constexpr int WARPS = (blocks_for(4) * 4 >= blocks_for(2) * 2 && blocks_for(4) * 4 >= blocks_for(1)) ? 4
+                                 : (blocks_for(2) * 2 >= blocks_for(1) ? 2 : 1);
+    static constexpr int MINB = blocks_for(WARPS) > 0 ? blocks_for(WARPS) : 1;
+    static constexpr bool FITS = WARPS * BYTES <= SMEM_PER_CTA_MAX && blocks_for(WARPS) > 0;
 };
 
-__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
-__host__ __device__ inline int list_capacity(int ns) { return round_up(ns + 212, 32); }
+// Per-warp view of the replica: base pointer + runtime atom count.  Arrays are reached through the layout constants.
+template <class LY>
+struct Rep {
+    double *b;  // warp base in shared memory
+    int n;      // atoms
+    __device__ __forceinline__ double &x(int j) const { return b[LY::X + j]; }
+    __device__ __forceinline__ double &y(int j) const { return b[LY::Y + j]; }
+    __device__ __forceinline__ double &z(int j) const { return b[LY::Z + j]; }
+    __device__ __forceinline__ double &sig(int j) const { return b[LY::SIG + j]; }
+    __device__ __forceinline__ double &eat(int j) const { return b[LY::EAT + j]; }
+    __device__ __forceinline__ double &lr(int e) const { return b[LY::LR + e]; }
+    __device__ __forceinline__ double &tail(int e) const { return b[LY::TAIL + e]; }
+    __device__ __forceinline__ double &cellc(int k) const { return b[LY::CELLC + k]; }
+    __device__ __forceinline__ uint32_t *queue() const { return reinterpret_cast<uint32_t *>(b + LY::TAIL); }
+    __device__ __forceinline__ uint32_t &pp(int j) const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(b) + LY::PP_B)[j]; }
+    __device__ __forceinline__ uint16_t &l2(int e) const { return reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(b) + LY::L2_B)[e]; }
+    __device__ __forceinline__ uint16_t &xj(int e) const { return reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(b) + LY::XJ_B)[e]; }
+};
 
-// shared-memory bytes of one replica
-__host__ __device__ inline int64_t replica_smem_bytes(int kind, int n_max) {
-    const int ns = round_up(n_max, 4);
-    int64_t b = 3 * (int64_t)ns * 8 + (int64_t)list_capacity(ns) * 8;
-    if (kind == QMC_POT_EMT) b += 2 * (int64_t)ns * 8 + (int64_t)ns * 4 + (int64_t)ns * 2 + XCAP * 2;
-    return (b + 15) / 16 * 16;
-}
+// cell constants of one axis: edge, 1 / edge, edge - cutoff' (a second image can be inside the cutoff iff |d| > thr)
+struct Axis {
+    double L, invL, thr;
+};
 
-__device__ inline void replica_carve(Replica &R, unsigned char *base, int kind, int n_max) {
-    const int ns = round_up(n_max, 4);
-    const int capl = list_capacity(ns);
-    R.ns = ns;
-    R.cape = capl - ns;
-    double *d = reinterpret_cast<double *>(base);
-    R.x = d; d += ns;
-    R.y = d; d += ns;
-    R.z = d; d += ns;
-    R.sig = R.eat = nullptr;
-    if (kind == QMC_POT_EMT) {
-        R.sig = d; d += ns;
-        R.eat = d; d += ns;
-    }
-    R.lr = d; d += capl;
-    R.pp = reinterpret_cast<uint32_t *>(d);
-    R.l2 = reinterpret_cast<uint16_t *>(R.pp + ns);
-    R.xj = R.l2 + ns;
-}
+// The cell as the kernels see it.  UNIFORM: every replica shares one constant cell, values come straight from the kernel
+// arguments (constant bank operands, no registers); otherwise per-replica values are kept in shared memory.
+struct CellArgs {
+    double L[3], invL[3], thr[3];
+    int per[3];
+};
 
-// returns false if a periodic edge is shorter than the cutoff (more than two images per axis would be needed)
-__device__ inline bool replica_set_cell(Replica &R, const double cell_diag[3], const int pbc[3], double cut) {
+__host__ __device__ inline bool cell_constants(const double diag[3], const int pbc[3], double cut_pre, CellArgs &c) {
     bool ok = true;
-    const double cutp = cut * (1.0 + 1e-9);
-#pragma unroll
     for (int k = 0; k < 3; ++k) {
-        R.L[k] = cell_diag[k];
-        R.per[k] = pbc[k] != 0;
-        R.invL[k] = R.per[k] ? 1.0 / cell_diag[k] : 0.0;
-        R.thr[k] = R.per[k] ? cell_diag[k] - cutp : 1e300;
-        if (R.per[k] && !(cell_diag[k] >= cutp)) ok = false;
+        c.per[k] = pbc[k] != 0;
+        c.L[k] = diag[k];
+        c.invL[k] = c.per[k] ? 1.0 / diag[k] : 0.0;
+        c.thr[k] = c.per[k] ? diag[k] - cut_pre : 1e300;
+        if (c.per[k] && !(diag[k] >= cut_pre)) ok = false;
     }
     return ok;
 }
 
+template <class LY, bool UNIFORM>
+struct CellView {
+    const CellArgs *u;  // kernel-argument cell (uniform) -- also carries the pbc flags
+    double *s;          // shared-memory cell constants of this replica (per-replica cells)
+    __device__ __forceinline__ Axis axis(int k) const {
+        if (UNIFORM) return Axis{u->L[k], u->invL[k], u->thr[k]};
+        return Axis{s[k], s[3 + k], s[6 + k]};
+    }
+    __device__ __forceinline__ bool per(int k) const { return u->per[k] != 0; }
+};
+
 // nearest image d0 of (xj - xi) along one axis; sets `bit` in `extra` if the second image d0 -+ L can be inside the cutoff
-__device__ __forceinline__ double axis_nearest(double xi, double xj, double L, double invL, double thr, bool per, unsigned &extra,
-                                               unsigned bit) {
+__device__ __forceinline__ double axis_nearest(double xi, double xj, const Axis &A, bool per, unsigned &extra, unsigned bit) {
     if (per) {
-        const double q = (xi - xj) * invL;
+        const double q = (xi - xj) * A.invL;
         const double k0 = (q + RINT_MAGIC) - RINT_MAGIC;
-        const double d0 = fma(k0, L, xj) - xi;
-        extra |= (fabs(d0) > thr) ? bit : 0u;
+        const double d0 = fma(k0, A.L, xj) - xi;
+        extra |= (fabs(d0) > A.thr) ? bit : 0u;
         return d0;
     }
     return xj - xi;
@@ -106,7 +135,8 @@ __device__ __forceinline__ double axis_nearest(double xi, double xj, double L, d
 // kept for the trajectory kernel: nearest and second image
 __device__ __forceinline__ void axis_images(double xi, double xj, double L, double invL, double thr, bool per, double &d0,
                                             double &d1, unsigned &extra, unsigned bit) {
-    d0 = axis_nearest(xi, xj, L, invL, thr, per, extra, bit);
+    const Axis A{L, invL, thr};
+    d0 = axis_nearest(xi, xj, A, per, extra, bit);
     d1 = per ? d0 - copysign(L, d0) : d0;
 }
 
@@ -120,18 +150,21 @@ struct DeltaAcc {
 // scan: fills the list.  MODE 0 = local delta (pp, l2, xj maintained for EMT), MODE 1 = one row of a full evaluation.
 // Returns the number of list entries; n2 = entries of l2; xstart = first second-image entry.
 // ---------------------------------------------------------------------------------------------------
-template <int POT, int MODE>
-__device__ __forceinline__ int scan_neighbours(const PotDev &pot, Replica &R, const int lane, const unsigned lt, int n_scan,
-                                               int i_excl, bool has_old, bool has_new, const double po[3], const double pn[3],
-                                               int &n2, int &xstart, int &status) {
-    constexpr bool TRACK = (MODE == 0 && POT == QMC_POT_EMT);
-    uint32_t *queue = reinterpret_cast<uint32_t *>(R.lr + R.cape);  // 2 * ns items fit in the tail (ns doubles)
+template <class LY, int MODE, class CELL>
+__device__ __forceinline__ int scan_neighbours(const PotDev &pot, const Rep<LY> &R, const CELL &C, const int lane, const unsigned lt,
+                                               int n_scan, int i_excl, bool has_old, bool has_new, const double po[3],
+                                               const double pn[3], int &n2, int &xstart, int &status) {
+    constexpr bool TRACK = (MODE == 0 && LY::EMT);
+    uint32_t *queue = R.queue();  // 2 * NS work items fit in the tail (NS doubles)
+    const bool p0 = C.per(0), p1 = C.per(1), p2 = C.per(2);
+    const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);
     int cnt = 0, nq = 0;
     n2 = 0;
     for (int base = 0; base < n_scan; base += 32) {
         const int j = base + lane;
         const bool valid = j < n_scan && j != i_excl;
-        const double xj = valid ? R.x[j] : 0.0, yj = valid ? R.y[j] : 0.0, zj = valid ? R.z[j] : 0.0;
+        const int jc = valid ? j : 0;
+        const double xj = R.x(jc), yj = R.y(jc), zj = R.z(jc);
         unsigned code = NOPOS | (NOPOS << 16);
         bool touched = false;
 #pragma unroll
@@ -139,14 +172,14 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, Replica &R, co
             if (side == 0 ? !has_old : !has_new) continue;  // warp-uniform
             const double *p = side == 0 ? po : pn;
             unsigned fl = 0;
-            const double dx = axis_nearest(p[0], xj, R.L[0], R.invL[0], R.thr[0], R.per[0], fl, 1u);
-            const double dy = axis_nearest(p[1], yj, R.L[1], R.invL[1], R.thr[1], R.per[1], fl, 2u);
-            const double dz = axis_nearest(p[2], zj, R.L[2], R.invL[2], R.thr[2], R.per[2], fl, 4u);
+            const double dx = axis_nearest(p[0], xj, A0, p0, fl, 1u);
+            const double dy = axis_nearest(p[1], yj, A1, p1, fl, 2u);
+            const double dz = axis_nearest(p[2], zj, A2, p2, fl, 4u);
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
             const bool in = valid && r2 < pot.cut_pre2;
             const unsigned b = __ballot_sync(FULL, in);
-            const int pos = cnt + __popc(b & lt);
-            if (in && pos < R.cape) R.lr[pos] = side ? r2 : -r2;
+            const int pos = min(cnt + __popc(b & lt), LY::CAPE - 1);
+            if (in) R.lr(pos) = side ? r2 : -r2;
             if (in) code = side ? ((code & 0xFFFFu) | ((unsigned)pos << 16)) : ((code & 0xFFFF0000u) | (unsigned)pos);
             cnt += __popc(b);
             touched |= in;
@@ -157,9 +190,9 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, Replica &R, co
             nq += __popc(bq);
         }
         if (TRACK) {
-            if (valid) R.pp[j] = code;
+            if (valid) R.pp(j) = code;
             const unsigned b2 = __ballot_sync(FULL, touched);
-            if (touched) R.l2[n2 + __popc(b2 & lt)] = (uint16_t)j;
+            if (touched) R.l2(n2 + __popc(b2 & lt)) = (uint16_t)j;
             n2 += __popc(b2);
         }
     }
@@ -175,10 +208,10 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, Replica &R, co
             const unsigned side = (item >> 15) & 1u, fl = item >> 16;
             const double *p = side ? pn : po;
             unsigned dummy = 0;
-            const double dx0 = axis_nearest(p[0], R.x[j], R.L[0], R.invL[0], R.thr[0], R.per[0], dummy, 1u);
-            const double dy0 = axis_nearest(p[1], R.y[j], R.L[1], R.invL[1], R.thr[1], R.per[1], dummy, 2u);
-            const double dz0 = axis_nearest(p[2], R.z[j], R.L[2], R.invL[2], R.thr[2], R.per[2], dummy, 4u);
-            const double dx1 = dx0 - copysign(R.L[0], dx0), dy1 = dy0 - copysign(R.L[1], dy0), dz1 = dz0 - copysign(R.L[2], dz0);
+            const double dx0 = axis_nearest(p[0], R.x(j), A0, p0, dummy, 1u);
+            const double dy0 = axis_nearest(p[1], R.y(j), A1, p1, dummy, 2u);
+            const double dz0 = axis_nearest(p[2], R.z(j), A2, p2, dummy, 4u);
+            const double dx1 = dx0 - copysign(A0.L, dx0), dy1 = dy0 - copysign(A1.L, dy0), dz1 = dz0 - copysign(A2.L, dz0);
             unsigned c = fl & (0u - fl);  // first non-empty subset of fl
             bool more = has;
             while (__any_sync(FULL, more)) {
@@ -186,10 +219,10 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, Replica &R, co
                 const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
                 const bool in = more && r2 < pot.cut_pre2;
                 const unsigned b = __ballot_sync(FULL, in);
-                const int pos = cnt + __popc(b & lt);
-                if (in && pos < R.cape) {
-                    R.lr[pos] = side ? r2 : -r2;
-                    if (TRACK && pos - xstart < XCAP) R.xj[pos - xstart] = (uint16_t)j;
+                const int pos = min(cnt + __popc(b & lt), LY::CAPE - 1);
+                if (in) {
+                    R.lr(pos) = side ? r2 : -r2;
+                    if (TRACK) R.xj(min(pos - xstart, XCAP - 1)) = (uint16_t)j;
                 }
                 cnt += __popc(b);
                 if (more) {
@@ -199,9 +232,9 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, Replica &R, co
             }
         }
     }
-    if (cnt > R.cape || (TRACK && cnt - xstart > XCAP)) {
+    if (cnt > LY::CAPE || (TRACK && cnt - xstart > XCAP)) {
         status |= QMC_STATUS_LIST_OVERFLOW;
-        cnt = min(cnt, R.cape);
+        cnt = min(cnt, LY::CAPE);
         if (TRACK && cnt - xstart > XCAP) cnt = xstart + XCAP;
     }
     __syncwarp();
@@ -210,16 +243,16 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, Replica &R, co
 
 // pairs: evaluate the list.  MODE 0 leaves the sigma_1 term of every nearest-image entry in lr[e], with the terms of
 // the second images of the same atom and side added onto it.
-template <int POT, int MODE>
-__device__ __forceinline__ void eval_list(const PotDev &pot, Replica &R, const int lane, int cnt, int xstart, DeltaAcc &acc) {
-    constexpr bool TRACK = (MODE == 0 && POT == QMC_POT_EMT);
+template <class LY, int MODE>
+__device__ __forceinline__ void eval_list(const PotDev &pot, const Rep<LY> &R, const int lane, int cnt, int xstart, DeltaAcc &acc) {
+    constexpr bool TRACK = (MODE == 0 && LY::EMT);
     for (int e0 = 0; e0 < cnt; e0 += 32) {
         const int e = e0 + lane;
         const bool act = e < cnt;
-        const double r2s = act ? R.lr[e] : 1.0;
+        const double r2s = act ? R.lr(e) : 1.0;
         const bool isnew = r2s > 0.0;
         const double r2 = fabs(r2s);
-        if (POT == QMC_POT_EMT) {
+        if (LY::EMT) {
             double s1, s2;
             emt_pair(pot, r2, s1, s2);
             s1 = act ? s1 : 0.0;
@@ -228,14 +261,14 @@ __device__ __forceinline__ void eval_list(const PotDev &pot, Replica &R, const i
             acc.snew += isnew ? s1 : 0.0;
             if (TRACK) {
                 if (e0 + 32 <= xstart) {  // nearest images only: every entry owns its slot
-                    R.lr[e] = s1;
+                    R.lr(e) = s1;
                 } else {
                     const bool is_x = act && e >= xstart;
-                    if (act && !is_x) R.lr[e] = s1;
+                    if (act && !is_x) R.lr(e) = s1;
                     __syncwarp();
                     unsigned tgt = 0x10000u + lane;
                     if (is_x) {
-                        const unsigned code = R.pp[R.xj[e - xstart]];
+                        const unsigned code = R.pp(R.xj(e - xstart));
                         tgt = isnew ? (code >> 16) : (code & 0xFFFFu);
                     }
                     const unsigned grp = __match_any_sync(FULL, tgt);
@@ -250,7 +283,7 @@ __device__ __forceinline__ void eval_list(const PotDev &pot, Replica &R, const i
                             rem &= rem - 1;
                         }
                     }
-                    if (is_x && lane == (__ffs(grp) - 1)) R.lr[tgt] += a;
+                    if (is_x && lane == (__ffs(grp) - 1)) R.lr(tgt) += a;
                     __syncwarp();
                 }
             }
@@ -265,35 +298,36 @@ __device__ __forceinline__ void eval_list(const PotDev &pot, Replica &R, const i
 
 // Full evaluation of the replica in shared memory: fills sig / eat (EMT), returns the total energy on every lane.
 // `pairs` (per-lane partial) counts the evaluated (atom, image) pairs.
-template <int POT>
-__device__ inline double replica_full_energy(const PotDev &pot, Replica &R, const int lane, long long &pairs, int &status) {
+template <class LY, class CELL>
+__device__ inline double replica_full_energy(const PotDev &pot, const Rep<LY> &R, const CELL &C, const int lane, long long &pairs,
+                                             int &status) {
     const unsigned lt = lanemask_lt();
     double epart = 0.0;  // lane partial of per-atom energies
     for (int a = 0; a < R.n; ++a) {
-        const double pa[3] = {R.x[a], R.y[a], R.z[a]};
+        const double pa[3] = {R.x(a), R.y(a), R.z(a)};
         DeltaAcc acc = {0.0, 0.0, 0};
         int n2, xstart;
-        const int cnt = scan_neighbours<POT, 1>(pot, R, lane, lt, R.n, a, false, true, pa, pa, n2, xstart, status);
-        eval_list<POT, 1>(pot, R, lane, cnt, xstart, acc);
+        const int cnt = scan_neighbours<LY, 1>(pot, R, C, lane, lt, R.n, a, false, true, pa, pa, n2, xstart, status);
+        eval_list<LY, 1>(pot, R, lane, cnt, xstart, acc);
         pairs += acc.pairs;
         const double vs = warp_sum(acc.v);
-        if (POT == QMC_POT_EMT) {
+        if (LY::EMT) {
             const double s1 = warp_sum(acc.snew);
             if (lane == 0) {
-                R.sig[a] = s1;
-                R.eat[a] = vs;  // sigma_2 sum parked here until the embedding pass below
+                R.sig(a) = s1;
+                R.eat(a) = vs;  // sigma_2 sum parked here until the embedding pass below
             }
         } else {
             if (lane == (a & 31)) epart += 0.5 * vs;  // energies[ii] = 0.5 * pairwise_energies.sum()
         }
         __syncwarp();
     }
-    if (POT == QMC_POT_EMT) {
+    if (LY::EMT) {
         for (int a = lane; a < R.n; a += 32) {
-            const double ea = emt_embed(pot, R.sig[a]);
+            const double ea = emt_embed(pot, R.sig(a));
             // energies[a] = E_c + E_AS,2 - E0 + 0.5 * sum(es + eo), es = eo = neghalfv0overgamma2 * dsigma2
-            epart += ea + pot.neghalfv0overgamma2 * R.eat[a];
-            R.eat[a] = ea;
+            epart += ea + pot.neghalfv0overgamma2 * R.eat(a);
+            R.eat(a) = ea;
         }
         __syncwarp();
     }

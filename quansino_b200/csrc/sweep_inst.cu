@@ -1,0 +1,54 @@
+// One (potential, capacity class) instantiation of the sweep and energy kernels.
+// Compile with -DINST_POT=<0|1> -DINST_NS=<32|64|108|128|256|512|1024>.
+#include <cstdio>
+
+#include "launchers.h"
+
+#ifndef INST_POT
+#error "compile with -DINST_POT and -DINST_NS"
+#endif
+
+#define CAT_(a, b, c, d) a##b##_##d
+#define CAT(a, b, c, d) CAT_(a, b, c, d)
+
+namespace qmc {
+
+static inline int report(cudaError_t e, const char *what, char *err, size_t errn) {
+    if (e == cudaSuccess) return QMC_OK;
+    snprintf(err, errn, "%s failed: %s", what, cudaGetErrorString(e));
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? QMC_ERR_NO_DEVICE : QMC_ERR_CUDA;
+}
+
+template <int FEAT>
+static inline int launch_feat(const SweepArgs &a, cudaStream_t s, char *err, size_t errn) {
+    using LY = Layout<INST_POT, INST_NS>;
+    static_assert(LY::FITS, "replica does not fit in shared memory");
+    constexpr size_t smem = (size_t)LY::WARPS * LY::BYTES;
+    auto kernel = sweep_kernel<INST_POT, INST_NS, FEAT>;
+    int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
+    if (rc) return rc;
+    const int grid = (a.b.n_replicas + LY::WARPS - 1) / LY::WARPS;
+    kernel<<<grid, LY::WARPS * 32, smem, s>>>(a);
+    return report(cudaGetLastError(), "sweep kernel launch", err, errn);
+}
+
+int CAT(sweep_launch_, INST_POT, _, INST_NS)(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn) {
+    // instantiated feature sets: canonical fast path; per-replica cells; + cell moves; everything
+    if (feat == 0) return launch_feat<0>(a, s, err, errn);
+    if ((feat & ~F_CELLVAR) == 0) return launch_feat<F_CELLVAR>(a, s, err, errn);
+    if ((feat & ~(F_CELLVAR | F_CELL)) == 0) return launch_feat<F_CELLVAR | F_CELL>(a, s, err, errn);
+    return launch_feat<F_CELLVAR | F_CELL | F_LABELS | F_EXCHANGE>(a, s, err, errn);
+}
+
+int CAT(energy_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn) {
+    using LY = Layout<INST_POT, INST_NS>;
+    constexpr size_t smem = (size_t)LY::WARPS * LY::BYTES;
+    auto kernel = energy_kernel<INST_POT, INST_NS>;
+    int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
+    if (rc) return rc;
+    const int grid = (a.b.n_replicas + LY::WARPS - 1) / LY::WARPS;
+    kernel<<<grid, LY::WARPS * 32, smem, s>>>(a, pair_count);
+    return report(cudaGetLastError(), "energy kernel launch", err, errn);
+}
+
+}  // namespace qmc

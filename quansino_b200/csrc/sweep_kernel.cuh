@@ -27,6 +27,7 @@ struct MoveDev {
 
 struct SweepArgs {
     PotDev pot;
+    CellArgs cell;  // pbc flags; cell constants when every replica shares one fixed cell
     qmc_batch_t b;
     MoveDev mv[QMC_MAX_MOVES];
     double cdf[QMC_MAX_MOVES];
@@ -36,7 +37,6 @@ struct SweepArgs {
     int n_attempts;
     int has_trace;
     qmc_trace_t tr;
-    long long smem_per_warp;
 };
 
 // --- label bookkeeping (moves/displacement.py:173-184, 226-253); labels live in global memory -------------------
@@ -119,46 +119,47 @@ struct Trial {
 
 // sigma_1 change of touched atom j, gathered from the list through pp[j] (terms of second images were added onto the
 // nearest-image slots by eval_list)
-__device__ __forceinline__ double gathered_dsigma(const Replica &R, int j) {
-    const unsigned code = R.pp[j];
+template <class LY>
+__device__ __forceinline__ double gathered_dsigma(const Rep<LY> &R, int j) {
+    const unsigned code = R.pp(j);
     const unsigned po = code & 0xFFFFu, pn = code >> 16;
-    const double so = po != NOPOS ? R.lr[po] : 0.0;
-    const double sn = pn != NOPOS ? R.lr[pn] : 0.0;
+    const double so = po != NOPOS ? R.lr(po) : 0.0;
+    const double sn = pn != NOPOS ? R.lr(pn) : 0.0;
     return sn - so;
 }
 
-template <int POT>
-__device__ __forceinline__ Trial local_delta(const PotDev &pot, Replica &R, const int lane, const unsigned lt, int n_scan, int i,
-                                             bool has_old, bool has_new, const double po[3], const double pn[3], int &status) {
+template <class LY, class CELL>
+__device__ __forceinline__ Trial local_delta(const PotDev &pot, const Rep<LY> &R, const CELL &C, const int lane, const unsigned lt,
+                                             int n_scan, int i, bool has_old, bool has_new, const double po[3], const double pn[3],
+                                             int &status) {
     Trial T;
     DeltaAcc acc = {0.0, 0.0, 0};
     int xstart;
-    const int cnt = scan_neighbours<POT, 0>(pot, R, lane, lt, n_scan, has_old ? i : -1, has_old, has_new, po, pn, T.n2, xstart, status);
-    eval_list<POT, 0>(pot, R, lane, cnt, xstart, acc);
+    const int cnt = scan_neighbours<LY, 0>(pot, R, C, lane, lt, n_scan, has_old ? i : -1, has_old, has_new, po, pn, T.n2, xstart, status);
+    eval_list<LY, 0>(pot, R, lane, cnt, xstart, acc);
     const double vs = warp_sum(acc.v);
     T.pairs = acc.pairs;
     T.sig_i = 0.0;
     T.eat_i = 0.0;
-    if (POT == QMC_POT_LJ) {
+    if (!LY::EMT) {
         T.dE = vs;  // E = 1/2 sum_i sum_j e_ij: the moved atom's row and column change together
         return T;
     }
     if (has_new) T.sig_i = warp_sum(acc.snew);
-    double *et = R.lr + R.cape;
     double part = 0.0, e_i_lane = 0.0;
     const int total = T.n2 + (has_new ? 1 : 0);
     for (int e = lane; e < total; e += 32) {
         const bool nb = e < T.n2;
-        const int j = nb ? R.l2[e] : 0;
-        const double sn = nb ? (R.sig[j] + gathered_dsigma(R, j)) : T.sig_i;
-        const double eold = nb ? R.eat[j] : (has_old ? R.eat[i] : 0.0);
+        const int j = nb ? R.l2(e) : 0;
+        const double sn = nb ? (R.sig(j) + gathered_dsigma(R, j)) : T.sig_i;
+        const double eold = nb ? R.eat(j) : (has_old ? R.eat(i) : 0.0);
         const double en = emt_embed(pot, sn);
         part += en - eold;
-        if (nb) et[e] = en;
+        if (nb) R.tail(e) = en;
         else e_i_lane = en;
     }
     if (has_new) T.eat_i = __shfl_sync(FULL, e_i_lane, T.n2 & 31);
-    if (!has_new && lane == 0) part -= R.eat[i];  // deletion: the atom's own embedding energy disappears
+    if (!has_new && lane == 0) part -= R.eat(i);  // deletion: the atom's own embedding energy disappears
     // pair part: rows (i, j) and (j, i) change together: 2 * 0.5 * (es + eo) = 2 * neghalfv0overgamma2 * dsigma2
     T.dE = warp_sum(part) + 2.0 * pot.neghalfv0overgamma2 * vs;
     __syncwarp();
@@ -166,14 +167,13 @@ __device__ __forceinline__ Trial local_delta(const PotDev &pot, Replica &R, cons
 }
 
 // commit the trial values of the touched atoms (accepted moves only; a rejected trial leaves no trace)
-template <int POT>
-__device__ __forceinline__ void commit_trial(Replica &R, const int lane, const Trial &T) {
-    if (POT != QMC_POT_EMT) return;
-    const double *et = R.lr + R.cape;
+template <class LY>
+__device__ __forceinline__ void commit_trial(const Rep<LY> &R, const int lane, const Trial &T) {
+    if (!LY::EMT) return;
     for (int e = lane; e < T.n2; e += 32) {
-        const int j = R.l2[e];
-        R.sig[j] = R.sig[j] + gathered_dsigma(R, j);
-        R.eat[j] = et[e];
+        const int j = R.l2(e);
+        R.sig(j) = R.sig(j) + gathered_dsigma(R, j);
+        R.eat(j) = R.tail(e);
     }
     __syncwarp();
 }
@@ -197,6 +197,7 @@ __device__ inline double gc_probability(double dE, int delta, int n_ex, double a
 constexpr int F_LABELS = 1;    // label tables in global memory (not arange)
 constexpr int F_CELL = 2;      // cell moves
 constexpr int F_EXCHANGE = 4;  // exchange moves
+constexpr int F_CELLVAR = 8;   // per-replica cells (kept in shared memory); otherwise one constant cell for all
 
 // the random numbers of one attempt: lanes 0..3 run one Philox block each, the six / seven doubles are broadcast
 struct Draws {
@@ -226,17 +227,38 @@ __device__ __forceinline__ bool metropolis(double u, double x, int &status) {
     return u < exp_fast(x);
 }
 
-template <int POT, int WARPS, int MINB, int FEAT>
-__global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_constant__ SweepArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
+// per-replica cell constants in shared memory (F_CELLVAR); returns false if an edge is below the cutoff
+template <class LY>
+__device__ __forceinline__ bool store_cell(const Rep<LY> &R, const double diag[3], const int pbc[3], double cut_pre, int lane) {
+    CellArgs c;
+    const bool ok = cell_constants(diag, pbc, cut_pre, c);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            R.cellc(k) = c.L[k];
+            R.cellc(3 + k) = c.invL[k];
+            R.cellc(6 + k) = c.thr[k];
+        }
+    }
+    __syncwarp();
+    return ok;
+}
+
+template <int POT, int NS, int FEAT>
+__global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::MINB) sweep_kernel(const __grid_constant__ SweepArgs a) {
+    using LY = Layout<POT, NS>;
+    constexpr int WARPS = LY::WARPS;
+    constexpr bool UNIFORM = (FEAT & F_CELLVAR) == 0;
+    extern __shared__ __align__(16) double smem_d[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const int r = blockIdx.x * WARPS + warp;
     if (r >= a.b.n_replicas) return;  // whole warp exits; no block-wide barrier is used below
     const PotDev &pot = a.pot;
     const int nmax = a.b.n_max;
-    Replica R;
-    replica_carve(R, smem + (size_t)warp * a.smem_per_warp, POT, nmax);
+    Rep<LY> R;
+    R.b = smem_d + warp * (LY::BYTES / 8);
+    const CellView<LY, UNIFORM> C{&a.cell, R.b + LY::CELLC};
 
     // ---- load the replica ----
     R.n = a.b.n_atoms[r];
@@ -245,17 +267,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
     double *ge = POT == QMC_POT_EMT ? a.b.eatom + (size_t)r * nmax : nullptr;
     for (int j = lane; j < nmax; j += 32) {
         const bool in = j < R.n;
-        R.x[j] = in ? gx[j] : 0.0;
-        R.y[j] = in ? gy[j] : 0.0;
-        R.z[j] = in ? gz[j] : 0.0;
+        R.x(j) = in ? gx[j] : 0.0;
+        R.y(j) = in ? gy[j] : 0.0;
+        R.z(j) = in ? gz[j] : 0.0;
         if (POT == QMC_POT_EMT) {
-            R.sig[j] = in ? gs[j] : 0.0;
-            R.eat[j] = in ? ge[j] : 0.0;
+            R.sig(j) = in ? gs[j] : 0.0;
+            R.eat(j) = in ? ge[j] : 0.0;
         }
     }
-    double cell[3] = {a.b.cell[(size_t)r * 9 + 0], a.b.cell[(size_t)r * 9 + 4], a.b.cell[(size_t)r * 9 + 8]};
     int status = 0;
-    if (!replica_set_cell(R, cell, a.b.pbc, pot.cut)) status |= QMC_STATUS_CELL_TOO_SMALL;
+    double cell[3] = {0.0, 0.0, 0.0};
+    if (!UNIFORM) {
+        cell[0] = a.b.cell[(size_t)r * 9 + 0];
+        cell[1] = a.b.cell[(size_t)r * 9 + 4];
+        cell[2] = a.b.cell[(size_t)r * 9 + 8];
+        if (!store_cell(R, cell, a.b.pbc, pot.cut_pre, lane)) status |= QMC_STATUS_CELL_TOO_SMALL;
+    }
     double E = a.b.energy[r];
     const double temperature = a.b.temperature[r];
     const double kT = temperature * KB;
@@ -305,21 +332,21 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
                     t[1] = __dadd_rn(-mv.step, __dmul_rn(w, D.o1));
                     t[2] = __dadd_rn(-mv.step, __dmul_rn(w, D.o2));
                 }
-                const double po[3] = {R.x[i], R.y[i], R.z[i]};
+                const double po[3] = {R.x(i), R.y(i), R.z(i)};
                 const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
-                const Trial T = local_delta<POT>(pot, R, lane, lt, R.n, i, true, true, po, pn, status);
+                const Trial T = local_delta<LY>(pot, R, C, lane, lt, R.n, i, true, true, po, pn, status);
                 n_pairs += T.pairs;
                 delta = T.dE;
                 const bool acc = metropolis(D.u_accept, -delta / kT, status);
                 if (acc) {
-                    commit_trial<POT>(R, lane, T);
+                    commit_trial<LY>(R, lane, T);
                     if (lane == 0) {
-                        R.x[i] = pn[0];
-                        R.y[i] = pn[1];
-                        R.z[i] = pn[2];
+                        R.x(i) = pn[0];
+                        R.y(i) = pn[1];
+                        R.z(i) = pn[2];
                         if (POT == QMC_POT_EMT) {
-                            R.sig[i] = T.sig_i;
-                            R.eat[i] = T.eat_i;
+                            R.sig(i) = T.sig_i;
+                            R.eat(i) = T.eat_i;
                         }
                     }
                     E += delta;
@@ -331,12 +358,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
         } else if ((FEAT & F_CELL) && mv.type == QMC_MOVE_CELL) {
             // snapshot the last accepted state in global memory, deform in place, recompute everything
             for (int j = lane; j < R.n; j += 32) {
-                gx[j] = R.x[j];
-                gy[j] = R.y[j];
-                gz[j] = R.z[j];
+                gx[j] = R.x(j);
+                gy[j] = R.y(j);
+                gz[j] = R.z(j);
                 if (POT == QMC_POT_EMT) {
-                    gs[j] = R.sig[j];
-                    ge[j] = R.eat[j];
+                    gs[j] = R.sig(j);
+                    ge[j] = R.eat(j);
                 }
             }
             const double s = exp(__dadd_rn(-mv.step, __dmul_rn(mv.step - -mv.step, D.o0)));
@@ -347,15 +374,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
                 scale[d] = ncell[d] / cell[d];  // solve(old_cell, new_cell), diagonal
             }
             for (int j = lane; j < R.n; j += 32) {
-                R.x[j] = R.x[j] * scale[0];
-                R.y[j] = R.y[j] * scale[1];
-                R.z[j] = R.z[j] * scale[2];
+                R.x(j) = R.x(j) * scale[0];
+                R.y(j) = R.y(j) * scale[1];
+                R.z(j) = R.z(j) * scale[2];
             }
             __syncwarp();
-            const bool cell_ok = replica_set_cell(R, ncell, a.b.pbc, pot.cut);
+            const bool cell_ok = store_cell(R, ncell, a.b.pbc, pot.cut_pre, lane);
             if (!cell_ok) status |= QMC_STATUS_CELL_TOO_SMALL;
             long long fp = 0;
-            const double e_new = cell_ok ? replica_full_energy<POT>(pot, R, lane, fp, status) : E;
+            const double e_new = cell_ok ? replica_full_energy<LY>(pot, R, C, lane, fp, status) : E;
             n_pairs += fp;
             delta = e_new - E;
             const double v_new = fabs((ncell[0] * ncell[1]) * ncell[2]), v_old = fabs((cell[0] * cell[1]) * cell[2]);
@@ -368,15 +395,15 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
                 cell[2] = ncell[2];
             } else {
                 for (int j = lane; j < R.n; j += 32) {
-                    R.x[j] = gx[j];
-                    R.y[j] = gy[j];
-                    R.z[j] = gz[j];
+                    R.x(j) = gx[j];
+                    R.y(j) = gy[j];
+                    R.z(j) = gz[j];
                     if (POT == QMC_POT_EMT) {
-                        R.sig[j] = gs[j];
-                        R.eat[j] = ge[j];
+                        R.sig(j) = gs[j];
+                        R.eat(j) = ge[j];
                     }
                 }
-                replica_set_cell(R, cell, a.b.pbc, pot.cut);
+                store_cell(R, cell, a.b.pbc, pot.cut_pre, lane);
             }
             __syncwarp();
             accepted = acc ? 1 : 0;
@@ -393,11 +420,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
                     const double f[3] = {D.o0, D.o1, D.o2};
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        const double fc = __dmul_rn(f[d], cell[d]);
+                        const double fc = __dmul_rn(f[d], UNIFORM ? a.cell.L[d] : cell[d]);
                         pn[d] = __dadd_rn(a.b.exchange_pos[d], __dsub_rn(fc, a.b.exchange_pos[d]));
                     }
                     i = R.n;
-                    T = local_delta<POT>(pot, R, lane, lt, R.n, i, false, true, po, pn, status);
+                    T = local_delta<LY>(pot, R, C, lane, lt, R.n, i, false, true, po, pn, status);
                     pd = 1;
                 }
             } else {
@@ -405,10 +432,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
                 if (nu > 0) {
                     const int idx = (int)(D.u_label * (double)nu);
                     i = lab ? select_labelled(lab, R.n, idx) : idx;
-                    po[0] = R.x[i];
-                    po[1] = R.y[i];
-                    po[2] = R.z[i];
-                    T = local_delta<POT>(pot, R, lane, lt, R.n, i, true, false, po, pn, status);
+                    po[0] = R.x(i);
+                    po[1] = R.y(i);
+                    po[2] = R.z(i);
+                    T = local_delta<LY>(pot, R, C, lane, lt, R.n, i, true, false, po, pn, status);
                     pd = -1;
                 }
             }
@@ -421,29 +448,29 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
                 if (ov) status |= QMC_STATUS_EXP_OVERFLOW;
                 const bool acc = D.u_accept < prob;
                 if (acc) {
-                    commit_trial<POT>(R, lane, T);
+                    commit_trial<LY>(R, lane, T);
                     // GrandCanonical.save_state (mc/gcmc.py:207-214): every registered move re-labels
                     for (int q = 0; q < a.n_moves; ++q)
                         if (a.mv[q].labels)
                             labels_changed(a.mv[q].labels + (size_t)r * nmax, R.n, pd > 0, pd < 0 ? i : -1, a.mv[q].default_label);
                     if (pd > 0) {
                         if (lane == 0) {
-                            R.x[i] = pn[0];
-                            R.y[i] = pn[1];
-                            R.z[i] = pn[2];
+                            R.x(i) = pn[0];
+                            R.y(i) = pn[1];
+                            R.z(i) = pn[2];
                             if (POT == QMC_POT_EMT) {
-                                R.sig[i] = T.sig_i;
-                                R.eat[i] = T.eat_i;
+                                R.sig(i) = T.sig_i;
+                                R.eat(i) = T.eat_i;
                             }
                         }
                         R.n += 1;
                     } else {
-                        shift_down(R.x, i, R.n);
-                        shift_down(R.y, i, R.n);
-                        shift_down(R.z, i, R.n);
+                        shift_down(&R.x(0), i, R.n);
+                        shift_down(&R.y(0), i, R.n);
+                        shift_down(&R.z(0), i, R.n);
                         if (POT == QMC_POT_EMT) {
-                            shift_down(R.sig, i, R.n);
-                            shift_down(R.eat, i, R.n);
+                            shift_down(&R.sig(0), i, R.n);
+                            shift_down(&R.eat(0), i, R.n);
                         }
                         R.n -= 1;
                     }
@@ -475,20 +502,22 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
     // ---- store the replica ----
     __syncwarp();
     for (int j = lane; j < R.n; j += 32) {
-        gx[j] = R.x[j];
-        gy[j] = R.y[j];
-        gz[j] = R.z[j];
+        gx[j] = R.x(j);
+        gy[j] = R.y(j);
+        gz[j] = R.z(j);
         if (POT == QMC_POT_EMT) {
-            gs[j] = R.sig[j];
-            ge[j] = R.eat[j];
+            gs[j] = R.sig(j);
+            ge[j] = R.eat(j);
         }
     }
     if (lane == 0) {
         a.b.n_atoms[r] = R.n;
         a.b.energy[r] = E;
-        a.b.cell[(size_t)r * 9 + 0] = cell[0];
-        a.b.cell[(size_t)r * 9 + 4] = cell[1];
-        a.b.cell[(size_t)r * 9 + 8] = cell[2];
+        if (FEAT & F_CELL) {
+            a.b.cell[(size_t)r * 9 + 0] = cell[0];
+            a.b.cell[(size_t)r * 9 + 4] = cell[1];
+            a.b.cell[(size_t)r * 9 + 8] = cell[2];
+        }
         if (FEAT & F_EXCHANGE) a.b.n_exchange[r] = n_ex;
         if (status) atomicOr(a.b.status + r, status);
     }
@@ -498,34 +527,35 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) sweep_kernel(const __grid_co
     }
 }
 
-// validate_simulation: full energy of every replica, caches primed
-template <int POT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) energy_kernel(const __grid_constant__ SweepArgs a, long long *pair_count) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = lane_id();
-    const int r = blockIdx.x * WARPS + warp;
+// validate_simulation: full energy of every replica, caches primed (per-replica cells always)
+template <int POT, int NS>
+__global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32) energy_kernel(const __grid_constant__ SweepArgs a, long long *pair_count) {
+    using LY = Layout<POT, NS>;
+    extern __shared__ __align__(16) double smem_d[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * LY::WARPS + warp;
     if (r >= a.b.n_replicas) return;
     const int nmax = a.b.n_max;
-    Replica R;
-    replica_carve(R, smem + (size_t)warp * a.smem_per_warp, POT, nmax);
+    Rep<LY> R;
+    R.b = smem_d + warp * (LY::BYTES / 8);
+    const CellView<LY, false> C{&a.cell, R.b + LY::CELLC};
     R.n = a.b.n_atoms[r];
     const double *gx = a.b.pos + (size_t)r * 3 * nmax, *gy = gx + nmax, *gz = gy + nmax;
     for (int j = lane; j < nmax; j += 32) {
         const bool in = j < R.n;
-        R.x[j] = in ? gx[j] : 0.0;
-        R.y[j] = in ? gy[j] : 0.0;
-        R.z[j] = in ? gz[j] : 0.0;
+        R.x(j) = in ? gx[j] : 0.0;
+        R.y(j) = in ? gy[j] : 0.0;
+        R.z(j) = in ? gz[j] : 0.0;
     }
     const double cell[3] = {a.b.cell[(size_t)r * 9 + 0], a.b.cell[(size_t)r * 9 + 4], a.b.cell[(size_t)r * 9 + 8]};
-    const bool ok = replica_set_cell(R, cell, a.b.pbc, a.pot.cut);
-    __syncwarp();
+    const bool ok = store_cell(R, cell, a.b.pbc, a.pot.cut_pre, lane);
     long long pairs = 0;
     int status = 0;
-    const double E = ok ? replica_full_energy<POT>(a.pot, R, lane, pairs, status) : __longlong_as_double(0x7ff8000000000000LL);
+    const double E = ok ? replica_full_energy<LY>(a.pot, R, C, lane, pairs, status) : __longlong_as_double(0x7ff8000000000000LL);
     if (POT == QMC_POT_EMT) {
         for (int j = lane; j < R.n; j += 32) {
-            a.b.sigma1[(size_t)r * nmax + j] = R.sig[j];
-            a.b.eatom[(size_t)r * nmax + j] = R.eat[j];
+            a.b.sigma1[(size_t)r * nmax + j] = R.sig(j);
+            a.b.eatom[(size_t)r * nmax + j] = R.eat(j);
         }
     }
     for (int o = 16; o > 0; o >>= 1) pairs += __shfl_xor_sync(FULL, pairs, o);

@@ -281,6 +281,8 @@ class MonteCarlo:
                     C.byref(tr) if tr is not None else None, b.stream(),
                 )  # fmt: skip
         _lib.check(rc)
+        if any(m.type == _lib.MOVE_CELL for m in moves):
+            b.cells_uniform = False  # accepted cell moves make the cells replica-specific
         if bufs is not None:
             self.last_trace = {k: v.cpu().numpy() for k, v in bufs.items()}
 
