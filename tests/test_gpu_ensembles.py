@@ -1,0 +1,252 @@
+"""Parity of the isobaric, grand-canonical and Hamiltonian paths against the CPU oracle (configs C3 / C4 / C5 of
+BASELINE.json at test sizes), plus the parallel-tempering swap kernel.
+
+Bar (north_star): energies within 1e-10 relative, identical accept / reject sequences, bit-exact integer state."""
+
+import numpy as np
+import pytest
+
+from oracle import capi
+from oracle.potentials import LJParams, emt_params
+from tests.helpers import cu_replicas
+
+pytestmark = pytest.mark.gpu
+
+BAR = 6.241509125883258e-07  # ase.units.bar
+
+
+def _emt_atoms(pos, cell, n):
+    from quansino_b200 import EMT, BatchedAtoms
+
+    return BatchedAtoms(pos.copy(), cell, np.full(len(pos), n, dtype=np.int32), "Cu", (True, True, True), EMT())
+
+
+@pytest.mark.parametrize("p_cell", [None, 0.15])
+def test_isobaric_matches_oracle(cuda_lib, p_cell):
+    from quansino_b200.mc import Isobaric
+    from quansino_b200.moves import CellMove, DisplacementMove
+    from quansino_b200.operations import Ball, IsotropicDeformation
+
+    R, steps = 6, 2
+    pos, cell, n = cu_replicas(3, R, seed=11)
+    pressure = 1000.0 * BAR
+    mc = Isobaric(
+        _emt_atoms(pos, cell, n), temperature=300.0, pressure=pressure, seed=77, trace=True, steps_per_launch=steps, resync_interval=0,
+        default_displacement_move=DisplacementMove(np.arange(n), Ball(0.1)), default_cell_move=CellMove(IsotropicDeformation(0.05)),
+    )  # fmt: skip
+    if p_cell is None:
+        assert mc.moves["default_cell_move"].probability == 1 / (n + 1)  # mc/isobaric.py:124-127
+        assert mc.moves["default_displacement_move"].probability == 1 / (1 + 1 / n)
+    else:
+        mc.moves["default_cell_move"].probability = p_cell
+        mc.moves["default_displacement_move"].probability = 1 - p_cell
+    probs = [mc.moves["default_displacement_move"].probability, mc.moves["default_cell_move"].probability]
+    mc.run(steps)
+    tr = mc.last_trace
+    out = mc.download()
+    par = emt_params("Cu")
+    n_cell_moves = 0
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, temperature=300.0, pressure=pressure)
+        specs = [
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.1, probability=probs[0], labels=np.arange(n, dtype=np.int32)),
+            capi.MoveSpec(capi.MOVE_CELL, capi.OP_ISOTROPIC, step=0.05, probability=probs[1]),
+        ]
+        ref = capi.mc_run(par, rep, specs, 77, r, 0, steps * n)
+        n_cell_moves += int((ref["move"] == 1).sum())
+        assert np.array_equal(tr["move"][r], ref["move"])
+        assert np.array_equal(tr["accepted"][r], ref["accepted"]), f"accept/reject sequence differs for replica {r}"
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(out.positions[r], rep.positions, rtol=0, atol=1e-11)
+        np.testing.assert_allclose(out.cell[r], rep.cell, rtol=1e-14)
+    if p_cell is not None:
+        assert n_cell_moves > 20  # the cell branch really ran
+
+
+def _gc_setup(R, n_max, mu):
+    from quansino_b200 import BatchedAtoms, LennardJones
+    from quansino_b200.systems import octahedron, rattle
+
+    pos0, cell = octahedron("Pt", 4, 10.0)
+    n = len(pos0)
+    pos = np.zeros((R, n_max, 3))
+    for r in range(R):
+        pos[r, :n] = rattle(pos0, 0.02, 500 + r)
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Pt", (False, False, False), LennardJones(sigma=2.5, epsilon=0.1))
+    return atoms, pos, cell, n
+
+
+def test_grand_canonical_lj_matches_oracle(cuda_lib):
+    from quansino_b200.mc import GrandCanonical
+    from quansino_b200.moves import DisplacementMove, ExchangeMove
+
+    R, n_max, mu, n_attempts = 6, 64, -0.5, 1500
+    atoms, pos, cell, n = _gc_setup(R, n_max, mu)
+    lab_d = np.arange(n)
+    lab_x = np.full(n, -1)
+    mc = GrandCanonical(
+        atoms, exchange_atoms=("Pt", (0.0, 0.0, 0.0)), temperature=300.0, chemical_potential=mu, number_of_exchange_particles=0,
+        max_cycles=n_attempts, seed=11, trace=True, resync_interval=0,
+        default_displacement_move=DisplacementMove(lab_d), default_exchange_move=ExchangeMove(lab_x),
+    )  # fmt: skip
+    mc.moves["default_displacement_move"].probability = 0.5
+    mc.moves["default_exchange_move"].probability = 0.5
+    mc.run(1)
+    tr = mc.last_trace
+    out = mc.download()
+    n_ex = mc.number_of_exchange_particles
+    labels_d, labels_x = mc.labels("default_displacement_move"), mc.labels("default_exchange_move")
+    par = LJParams(sigma=2.5, epsilon=0.1)
+    volume = float(np.prod(np.diag(cell)))
+    seen = {"insert": 0, "delete": 0, "failed": 0}
+    for r in range(R):
+        P = pos[r].copy()
+        rep = capi.Replica(positions=P, cell=cell, pbc=(0, 0, 0), n_atoms=n, temperature=300.0, mass=195.084, chemical_potential=mu,
+                           exchange_mass=195.084, n_exchange=0, accessible_volume=volume)  # fmt: skip
+        ld = np.full(n_max, -1, np.int32)
+        ld[:n] = lab_d
+        lx = np.full(n_max, -1, np.int32)
+        specs = [
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.1, probability=0.5, labels=ld),
+            capi.MoveSpec(capi.MOVE_EXCHANGE, capi.OP_TRANSLATION, probability=0.5, labels=lx),
+        ]
+        ref = capi.mc_run(par, rep, specs, 11, r, 0, n_attempts)
+        assert np.array_equal(tr["move"][r], ref["move"])
+        assert np.array_equal(tr["accepted"][r], ref["accepted"]), f"accept/reject sequence differs for replica {r}"
+        assert np.array_equal(tr["moved"][r], ref["moved"])  # bit-exact indices
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-11)
+        # bit-exact integer state: atom count, exchange count, both label tables
+        assert out.n_atoms[r] == rep.n_atoms
+        assert n_ex[r] == rep.n_exchange
+        assert np.array_equal(labels_d[r, : rep.n_atoms], ld[: rep.n_atoms])
+        assert np.array_equal(labels_x[r, : rep.n_atoms], lx[: rep.n_atoms])
+        np.testing.assert_allclose(out.positions[r, : rep.n_atoms], rep.positions[: rep.n_atoms], rtol=0, atol=1e-11)
+        ex = ref["move"] == 1
+        d_n = np.diff(np.concatenate([[n], ref["n_atoms"]]))
+        seen["insert"] += int((d_n == 1).sum())
+        seen["delete"] += int((d_n == -1).sum())
+        seen["failed"] += int((ref["accepted"][ex] == -1).sum())
+    assert seen["insert"] > 10 and seen["delete"] > 5 and seen["failed"] > 5, seen
+
+
+def test_grand_canonical_emt_matches_oracle(cuda_lib):
+    """Insert / delete with the many-body potential: periodic Cu with one vacancy-rich cell, EMT."""
+    from quansino_b200 import EMT, BatchedAtoms
+    from quansino_b200.mc import GrandCanonical
+    from quansino_b200.moves import DisplacementMove, ExchangeMove
+
+    R, n_max, n_attempts, mu = 4, 128, 400, -3.4
+    pos108, cell, n = cu_replicas(3, R, seed=5, n_max=n_max)
+    atoms = BatchedAtoms(pos108.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    lab = np.arange(n)
+    mc = GrandCanonical(
+        atoms, exchange_atoms=("Cu", (0.0, 0.0, 0.0)), temperature=3000.0, chemical_potential=mu, number_of_exchange_particles=n,
+        max_cycles=n_attempts, seed=5, trace=True, resync_interval=0,
+        default_displacement_move=DisplacementMove(lab), default_exchange_move=ExchangeMove(lab),
+    )  # fmt: skip
+    mc.moves["default_displacement_move"].probability = 0.3
+    mc.moves["default_exchange_move"].probability = 0.7
+    mc.run(1)
+    tr = mc.last_trace
+    out = mc.download()
+    par = emt_params("Cu")
+    volume = float(np.prod(np.diag(cell)))
+    changed = 0
+    for r in range(R):
+        rep = capi.Replica(positions=pos108[r].copy(), cell=cell, n_atoms=n, temperature=3000.0, mass=63.546, chemical_potential=mu,
+                           exchange_mass=63.546, n_exchange=n, accessible_volume=volume)  # fmt: skip
+        ld = np.full(n_max, -1, np.int32)
+        ld[:n] = lab
+        lx = ld.copy()
+        specs = [
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.1, probability=0.3, labels=ld),
+            capi.MoveSpec(capi.MOVE_EXCHANGE, capi.OP_TRANSLATION, probability=0.7, labels=lx),
+        ]
+        ref = capi.mc_run(par, rep, specs, 5, r, 0, n_attempts)
+        assert np.array_equal(tr["accepted"][r], ref["accepted"])
+        assert np.array_equal(tr["moved"][r], ref["moved"])
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10)
+        assert out.n_atoms[r] == rep.n_atoms
+        changed += int((np.diff(ref["n_atoms"]) != 0).sum())
+        np.testing.assert_allclose(out.positions[r, : rep.n_atoms], rep.positions[: rep.n_atoms], rtol=0, atol=1e-11)
+    assert changed > 5
+
+
+def test_forces_match_oracle(cuda_lib):
+    from quansino_b200 import ReplicaBatch
+
+    R = 4
+    pos, cell, n = cu_replicas(3, R, seed=21)
+    batch = ReplicaBatch(_emt_atoms(pos, cell, n), temperature=300.0)
+    f = batch.forces_full().cpu().numpy().transpose(0, 2, 1)
+    e = batch.energy.cpu().numpy()
+    par = emt_params("Cu")
+    for r in range(R):
+        ref = capi.energy(par, pos[r], cell, (1, 1, 1), want_forces=True)
+        np.testing.assert_allclose(f[r], ref["forces"], rtol=1e-9, atol=1e-11)
+        assert abs(e[r] - ref["energy"]) <= 1e-10 * abs(ref["energy"])
+
+
+def test_hmc_matches_oracle(cuda_lib):
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.mc import HamiltonianCanonical
+    from quansino_b200.moves import HamiltonianDisplacementMove
+
+    R, n_attempts, n_steps = 4, 3, 12
+    pos, cell, n = cu_replicas(3, R, seed=31, stdev=0.03)
+    temps = np.array([300.0, 500.0, 800.0, 1200.0])
+    mc = HamiltonianCanonical(
+        _emt_atoms(pos, cell, n), temperature=temps, max_cycles=1, seed=99, trace=True, resync_interval=0, steps_per_launch=n_attempts,
+        default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=2.0, max_steps=n_steps)),
+    )  # fmt: skip
+    mc.run(n_attempts)
+    tr = mc.last_trace
+    out = mc.download()
+    par = emt_params("Cu")
+    from quansino_b200.integrators.displacement import fs
+
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, temperature=float(temps[r]), mass=63.546, momenta=np.zeros((n, 3)))
+        specs = [capi.MoveSpec(capi.MOVE_HMC, capi.OP_VERLET, dt=2.0 * fs, n_steps=n_steps)]
+        ref = capi.mc_run(par, rep, specs, 99, r, 0, n_attempts)
+        assert np.array_equal(tr["accepted"][r], ref["accepted"])
+        np.testing.assert_allclose(tr["delta"][r], ref["delta"], rtol=1e-7, atol=1e-9)  # sums of O(100 eV) terms
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(out.positions[r], rep.positions, rtol=0, atol=1e-10)
+        np.testing.assert_allclose(out.momenta[r], rep.momenta, rtol=0, atol=1e-10)
+        assert abs(mc.batch.kinetic.cpu().numpy()[r] - rep.last_kinetic) <= 1e-9 * abs(rep.last_kinetic)
+    assert tr["accepted"].sum() > 0
+
+
+def test_parallel_tempering_swap_matches_oracle(cuda_lib):
+    import ctypes as C
+
+    import torch
+
+    from oracle import capi as oc
+    from quansino_b200 import _lib
+
+    lib = _lib.load()
+    n = 64
+    rng = np.random.default_rng(3)
+    temps0 = 300.0 * (1200.0 / 300.0) ** (np.arange(n) / (n - 1))
+    perm = rng.permutation(n)
+    temps = temps0[perm].copy()  # replica r currently holds temperature temps[r]
+    energies = 2.0 + 0.004 * temps + rng.normal(scale=0.3, size=n)
+    t_dev = torch.from_numpy(temps.copy()).cuda()
+    e_dev = torch.from_numpy(energies).cuda()
+    acc = torch.zeros(n, dtype=torch.int8, device="cuda")
+    expect = temps.copy()
+    n_swaps = 0
+    for rnd in range(6):
+        _lib.check(lib.qmc_pt_swap(t_dev.data_ptr(), e_dev.data_ptr(), n, 4242, rnd, acc.data_ptr(), None))
+        order = np.argsort(expect, kind="stable")
+        for k in range(rnd & 1, n - 1, 2):
+            ra, rb = order[k], order[k + 1]
+            u = oc.uniform_pair(4242, rnd, k, 3)[1]
+            if oc.lib().qo_pt_swap_accept(energies[ra], energies[rb], expect[ra], expect[rb], u):
+                expect[ra], expect[rb] = expect[rb], expect[ra]
+                n_swaps += 1
+        assert np.array_equal(t_dev.cpu().numpy(), expect), f"round {rnd}"
+    assert n_swaps > 10
+    assert np.array_equal(np.sort(expect), np.sort(temps))  # temperatures are only permuted
