@@ -1,0 +1,211 @@
+#!/usr/bin/env python
+"""Generate golden traces by running the GENUINE quansino sources.  TEST INFRASTRUCTURE (see oracle/__init__.py).
+
+Runs the unmodified reference (``/root/reference/src/quansino``, v0.1.3) in this container:
+
+* ``ase`` is absent, so ``oracle/ase_shim`` stands in for it (``Atoms``, ``Cell``, units, calculator cache) and its
+  ``EMT`` / ``LennardJones`` evaluate the numpy restatement ``oracle/potentials.py``;
+* ``importlib.metadata.version("quansino")`` is answered with "0.1.3" (the tree is not pip-installed);
+* the drivers' ``rng`` is replaced by ``oracle.philox.InjectedStream`` -- quansino only stores and calls it
+  (``src/quansino/mc/contexts.py:49-52``) -- so the draws are the Philox slots the kernels use.
+
+Everything else -- move selection, proposals, criteria, save / revert, label bookkeeping, Verlet -- is quansino's own
+code.  The traces pin the C oracle (tests/test_golden.py) and the CUDA path (tests/test_gpu_golden.py).
+
+Usage (in the build container only; the GPU box has no /root/reference):  python oracle/gen_golden.py
+"""
+
+from __future__ import annotations
+
+import importlib.metadata as _md
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path[:0] = [str(ROOT), str(ROOT / "oracle" / "ase_shim"), "/root/reference/src"]
+
+_orig_version = _md.version
+_md.version = lambda name: "0.1.3" if name == "quansino" else _orig_version(name)
+
+from ase import Atoms  # noqa: E402  (the shim)
+from ase.calculators.emt import EMT  # noqa: E402
+from ase.calculators.lj import LennardJones  # noqa: E402
+from quansino.integrators.displacement import Verlet  # noqa: E402
+from quansino.mc.canonical import Canonical, HamiltonianCanonical  # noqa: E402
+from quansino.mc.gcmc import GrandCanonical  # noqa: E402
+from quansino.mc.isobaric import Isobaric  # noqa: E402
+from quansino.moves.cell import CellMove  # noqa: E402
+from quansino.moves.displacement import DisplacementMove, HamiltonianDisplacementMove  # noqa: E402
+from quansino.moves.exchange import ExchangeMove  # noqa: E402
+from quansino.operations.cell import IsotropicDeformation  # noqa: E402
+from quansino.operations.displacement import Ball, Box, Sphere  # noqa: E402
+
+from oracle.philox import InjectedStream  # noqa: E402
+from oracle.units import bar  # noqa: E402
+from quansino_b200.systems import fcc_cubic, octahedron, rattle  # noqa: E402
+
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def inject(mc, seed, replica):
+    stream = InjectedStream(seed, replica)
+    mc._rng = stream
+    mc.context.rng = stream
+    return stream
+
+
+def run_steps(mc, steps):
+    """Drive ``MonteCarlo.step`` exactly like ``Driver.irun`` (mc/driver.py:91-119) and record every attempt."""
+    mc.validate_simulation()
+    rec = {"move": [], "accepted": [], "energy": [], "n_atoms": []}
+    names = list(mc.moves)
+
+    def record():
+        name, acc = mc.move_history[-1]
+        rec["move"].append(names.index(name))
+        rec["accepted"].append(-1 if acc is None else int(bool(acc)))
+        rec["energy"].append(float(mc.context.last_potential_energy))
+        rec["n_atoms"].append(len(mc.atoms))
+
+    for _ in range(steps):
+        seen = 0
+        for _name in mc.step():
+            if len(mc.move_history) > seen:
+                record()
+                seen = len(mc.move_history)
+        if len(mc.move_history) > seen:
+            record()
+        mc.step_count += 1
+    return {
+        "move": np.array(rec["move"], dtype=np.int8),
+        "accepted": np.array(rec["accepted"], dtype=np.int8),
+        "energy": np.array(rec["energy"]),
+        "n_atoms": np.array(rec["n_atoms"], dtype=np.int32),
+    }
+
+
+def cu_atoms(repeat, stdev, seed):
+    pos, cell = fcc_cubic("Cu", repeat)
+    pos = rattle(pos, stdev, seed)
+    return Atoms(f"Cu{len(pos)}", positions=pos, cell=cell, pbc=True, calculator=EMT()), pos, cell
+
+
+def case_canonical(opname, op, seed, steps):
+    atoms, pos0, cell = cu_atoms(3, 0.05, 4242)
+    n = len(atoms)
+    mc = Canonical(atoms, temperature=300.0, default_displacement_move=DisplacementMove(np.arange(n), op(0.1)))
+    inject(mc, seed, 3)
+    tr = run_steps(mc, steps)
+    return dict(
+        kind="canonical", op=opname, step_size=0.1, seed=seed, replica=3, temperature=300.0, positions0=pos0, cell=cell,
+        positions=atoms.positions.copy(), n_calculations=atoms.calc.n_calculations, **tr,
+    )  # fmt: skip
+
+
+def case_isobaric(seed, steps, p_cell):
+    atoms, pos0, cell = cu_atoms(3, 0.05, 777)
+    n = len(atoms)
+    pressure = 1000.0 * bar
+    mc = Isobaric(
+        atoms, temperature=300.0, pressure=pressure, default_displacement_move=DisplacementMove(np.arange(n), Ball(0.1)),
+        default_cell_move=CellMove(IsotropicDeformation(0.05)),
+    )  # fmt: skip
+    default_probabilities = np.array([mc.moves["default_displacement_move"].probability, mc.moves["default_cell_move"].probability])
+    if p_cell is not None:
+        mc.moves["default_cell_move"].probability = p_cell
+        mc.moves["default_displacement_move"].probability = 1 - p_cell
+    probabilities = np.array([mc.moves["default_displacement_move"].probability, mc.moves["default_cell_move"].probability])
+    inject(mc, seed, 1)
+    tr = run_steps(mc, steps)
+    return dict(
+        kind="isobaric", seed=seed, replica=1, temperature=300.0, pressure=pressure, step_size=0.1, max_value=0.05,
+        default_probabilities=default_probabilities, probabilities=probabilities, positions0=pos0, cell0=cell,
+        positions=atoms.positions.copy(), cell=atoms.cell.array.copy(), **tr,
+    )  # fmt: skip
+
+
+def case_gc_lj(seed, n_attempts, mu):
+    pos0, cell = octahedron("Pt", 4, 10.0)
+    pos0 = rattle(pos0, 0.02, 99)
+    n = len(pos0)
+    atoms = Atoms(f"Pt{n}", positions=pos0, cell=cell, pbc=False, calculator=LennardJones(sigma=2.5, epsilon=0.1))
+    disp = DisplacementMove(np.arange(n))
+    exch = ExchangeMove(np.full(n, -1))
+    mc = GrandCanonical(
+        atoms, exchange_atoms=Atoms("Pt"), temperature=300.0, chemical_potential=mu, number_of_exchange_particles=0,
+        max_cycles=n_attempts, default_displacement_move=disp, default_exchange_move=exch,
+    )  # fmt: skip
+    mc.moves["default_displacement_move"].probability = 0.5
+    mc.moves["default_exchange_move"].probability = 0.5
+    inject(mc, seed, 2)
+    tr = run_steps(mc, 1)
+    return dict(
+        kind="gc_lj", seed=seed, replica=2, temperature=300.0, chemical_potential=mu, sigma=2.5, epsilon=0.1, step_size=0.1,
+        accessible_volume=float(mc.accessible_volume), exchange_mass=float(mc.exchange_atoms.get_masses().sum()),
+        positions0=pos0, cell=cell, positions=atoms.positions.copy(), labels_displacement=np.asarray(disp.labels),
+        labels_exchange=np.asarray(exch.labels), n_exchange=int(mc.number_of_exchange_particles), **tr,
+    )  # fmt: skip
+
+
+def case_gc_emt(seed, n_attempts, mu, temperature):
+    atoms, pos0, cell = cu_atoms(3, 0.05, 31337)
+    n = len(atoms)
+    disp = DisplacementMove(np.arange(n))
+    exch = ExchangeMove(np.arange(n))
+    mc = GrandCanonical(
+        atoms, exchange_atoms=Atoms("Cu"), temperature=temperature, chemical_potential=mu, number_of_exchange_particles=n,
+        max_cycles=n_attempts, default_displacement_move=disp, default_exchange_move=exch,
+    )  # fmt: skip
+    mc.moves["default_displacement_move"].probability = 0.3
+    mc.moves["default_exchange_move"].probability = 0.7
+    inject(mc, seed, 0)
+    tr = run_steps(mc, 1)
+    return dict(
+        kind="gc_emt", seed=seed, replica=0, temperature=temperature, chemical_potential=mu, step_size=0.1,
+        accessible_volume=float(mc.accessible_volume), exchange_mass=float(mc.exchange_atoms.get_masses().sum()),
+        positions0=pos0, cell=cell, positions=atoms.positions.copy(), labels_displacement=np.asarray(disp.labels),
+        labels_exchange=np.asarray(exch.labels), n_exchange=int(mc.number_of_exchange_particles), n_exchange0=n, **tr,
+    )  # fmt: skip
+
+
+def case_hmc(seed, n_attempts, dt_fs, n_steps, temperature):
+    atoms, pos0, cell = cu_atoms(3, 0.03, 2718)
+    mc = HamiltonianCanonical(
+        atoms, temperature=temperature, max_cycles=1,
+        default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=dt_fs, max_steps=n_steps)),
+    )  # fmt: skip
+    inject(mc, seed, 5)
+    tr = run_steps(mc, n_attempts)
+    return dict(
+        kind="hmc", seed=seed, replica=5, temperature=temperature, dt_fs=dt_fs, n_steps=n_steps, positions0=pos0, cell=cell,
+        positions=atoms.positions.copy(), momenta=atoms.get_momenta(), last_kinetic=float(mc.context.last_kinetic_energy), **tr,
+    )  # fmt: skip
+
+
+def main():
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    cases = {
+        "canonical_ball": lambda: case_canonical("Ball", Ball, 1001, 2),
+        "canonical_box": lambda: case_canonical("Box", Box, 1002, 1),
+        "canonical_sphere": lambda: case_canonical("Sphere", Sphere, 1003, 1),
+        "isobaric_default": lambda: case_isobaric(2001, 1, None),
+        "isobaric_pcell": lambda: case_isobaric(2002, 1, 0.2),
+        "gc_lj": lambda: case_gc_lj(3001, 700, -0.5),
+        "gc_emt": lambda: case_gc_emt(3002, 150, -3.4, 3000.0),
+        "hmc": lambda: case_hmc(4001, 3, 2.0, 12, 800.0),
+    }
+    only = set(sys.argv[1:])
+    for name, fn in cases.items():
+        if only and name not in only:
+            continue
+        data = fn()
+        np.savez_compressed(GOLDEN / f"{name}.npz", **data)
+        acc = data["accepted"]
+        print(f"{name}: {len(acc)} attempts, accepted {int((acc == 1).sum())}, rejected {int((acc == 0).sum())}, failed {int((acc == -1).sum())}, "
+              f"E_last = {data['energy'][-1]:.12f}")  # fmt: skip
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,156 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol, the quansino-facing
+classes validate like the reference, and the GPU path refuses (never silently ignores) what it cannot run."""
+
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_library_exports_every_declared_symbol():
+    from quansino_b200 import _lib
+
+    lib = _lib.load()
+    header = (ROOT / "include" / "quansino_b200.h").read_text()
+    declared = set(re.findall(r"\b(qmc_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(_lib.EXPORTS)
+    for name in sorted(declared):
+        assert getattr(lib, name) is not None, name
+    assert lib.qmc_abi_version() == 1
+
+
+def test_struct_layouts_match_the_header():
+    """ctypes mirrors of the header structs: sizes as the C compiler lays them out."""
+    import ctypes as C
+    import subprocess
+    import tempfile
+
+    from quansino_b200 import _lib
+
+    src = '#include <stdio.h>\n#include "quansino_b200.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(qmc_potential_t), sizeof(qmc_move_t), sizeof(qmc_batch_t), sizeof(qmc_trace_t));return 0;}\n'
+    with tempfile.TemporaryDirectory() as d:
+        (Path(d) / "t.c").write_text(src)
+        subprocess.run(["gcc", "-I", str(ROOT / "include"), "-o", f"{d}/t", f"{d}/t.c"], check=True)
+        sizes = [int(x) for x in subprocess.run([f"{d}/t"], capture_output=True, text=True, check=True).stdout.split()]
+    assert sizes == [C.sizeof(_lib.Potential), C.sizeof(_lib.Move), C.sizeof(_lib.Batch), C.sizeof(_lib.Trace)]
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import torch
+
+    from quansino_b200 import EMT, BatchedAtoms, ReplicaBatch, _lib
+    from quansino_b200.systems import fcc_cubic
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert _lib.load().qmc_device_count() == _lib.ERR_NO_DEVICE
+    pos, cell = fcc_cubic("Cu", 3)
+    atoms = BatchedAtoms.replicate(pos, cell, 2, calc=EMT())
+    with pytest.raises(_lib.NoDeviceError):
+        ReplicaBatch(atoms)
+
+
+def test_product_never_imports_the_oracle():
+    for path in (ROOT / "quansino_b200").rglob("*.py"):
+        text = path.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f"{path} imports the oracle"
+    for path in (ROOT / "quansino_b200" / "csrc").glob("*"):
+        assert "qmc_oracle" not in path.read_text(), f"{path} references the oracle"
+
+
+def test_emt_and_lj_descriptions_match_the_oracle_constants():
+    from oracle.potentials import LJParams, emt_params
+    from quansino_b200 import EMT, LennardJones
+
+    for sym in ("Cu", "Pt", "Al", "Au"):
+        p, ref = EMT().lower(sym), emt_params(sym)
+        for a, b in [("E0", "E0"), ("s0", "s0"), ("V0", "V0"), ("eta2", "eta2"), ("kappa", "kappa"), ("lmbda", "lmbda"), ("rc", "rc"),
+                     ("rc_list", "rc_list"), ("acut", "acut"), ("gamma1", "gamma1"), ("gamma2", "gamma2")]:  # fmt: skip
+            assert getattr(p, a) == getattr(ref, b), (sym, a)
+    p, ref = LennardJones(sigma=2.5, epsilon=0.1).lower("Pt"), LJParams(sigma=2.5, epsilon=0.1)
+    assert (p.sigma, p.epsilon, p.lj_rc, p.lj_e0) == (ref.sigma, ref.epsilon, ref.cutoff, ref.e0)
+    with pytest.raises(NotImplementedError):
+        EMT().lower("Fe")
+    with pytest.raises(NotImplementedError):
+        EMT(asap_cutoff=True)
+
+
+def test_moves_lower_like_the_reference_defaults():
+    from quansino_b200 import _lib
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.moves import CellMove, DisplacementMove, ExchangeMove, HamiltonianDisplacementMove
+    from quansino_b200.operations import Ball, Box, IsotropicDeformation, Rotation, Sphere, Translation
+
+    m = DisplacementMove(np.arange(10)).lower()
+    assert (m.type, m.op, m.step) == (_lib.MOVE_DISPLACEMENT, _lib.OP_BALL, 0.1)  # default Ball(0.1), moves/displacement.py:214-224
+    assert DisplacementMove(np.arange(4), Box(0.3)).lower().op == _lib.OP_BOX
+    assert DisplacementMove(np.arange(4), Sphere(0.3)).lower().op == _lib.OP_SPHERE
+    c = CellMove().lower()
+    assert (c.type, c.op, c.step) == (_lib.MOVE_CELL, _lib.OP_ISOTROPIC, 0.05)  # moves/cell.py:112-122
+    x = ExchangeMove(np.arange(4)).lower()
+    assert (x.type, x.op, x.bias_insert) == (_lib.MOVE_EXCHANGE, _lib.OP_TRANSLATION, 0.5)
+    h = HamiltonianDisplacementMove().lower()
+    assert (h.type, h.op, h.n_steps) == (_lib.MOVE_HMC, _lib.OP_VERLET, 100) and abs(h.dt - 0.09822694788464063) < 1e-16
+    assert HamiltonianDisplacementMove().max_attempts == 10 and DisplacementMove(np.arange(2)).max_attempts == 10000
+    # refused, never ignored
+    with pytest.raises(NotImplementedError):
+        DisplacementMove(np.arange(4), Rotation()).lower()
+    with pytest.raises(NotImplementedError):
+        DisplacementMove(np.arange(4), Translation()).lower()
+    with pytest.raises(NotImplementedError):
+        CellMove(scale_atoms=False).lower()
+    with pytest.raises(NotImplementedError):
+        CellMove(IsotropicDeformation(0.05, mask=np.diag([True, True, False]))).lower()
+    mv = DisplacementMove(np.arange(4))
+    mv.check_move = lambda ctx: True
+    with pytest.raises(NotImplementedError):
+        mv.lower()
+    with pytest.raises(NotImplementedError):
+        Verlet(apply_constraints=False).lower()
+    with pytest.raises(NotImplementedError):
+        Ball(0.1).calculate(None)
+    with pytest.raises(TypeError):
+        DisplacementMove(np.arange(4)) + 3
+    with pytest.raises(NotImplementedError):
+        DisplacementMove(np.arange(4)) + DisplacementMove(np.arange(4))
+
+
+def test_label_validation():
+    from quansino_b200.moves import DisplacementMove
+
+    mv = DisplacementMove(np.array([0, -1, 1, 2, -1]))
+    assert np.array_equal(mv.unique_labels, [0, 1, 2])
+    lab = mv.validated_labels(2, 6, np.array([5, 5]))
+    assert lab.shape == (2, 6) and np.array_equal(lab[0], [0, -1, 1, 2, -1, -1])
+    with pytest.raises(NotImplementedError):  # label groups (molecules)
+        DisplacementMove(np.array([0, 0, 1])).validated_labels(1, 3, np.array([3]))
+    with pytest.raises(ValueError):
+        DisplacementMove(np.arange(3)).validated_labels(1, 8, np.array([5]))
+    assert DisplacementMove(np.arange(5)).is_identity(np.array([5, 5]))
+    assert not DisplacementMove(np.arange(5)).is_identity(np.array([5, 4]))
+
+
+def test_cell_checks():
+    from quansino_b200.batch import _check_cell
+
+    _check_cell(np.diag([10.83, 10.83, 10.83])[None], (True,) * 3, 5.8768)
+    with pytest.raises(NotImplementedError):
+        _check_cell(np.diag([3.61, 3.61, 3.61])[None], (True,) * 3, 5.8768)  # the reference's 4-atom fixture
+    _check_cell(np.diag([3.61, 3.61, 3.61])[None], (False,) * 3, 5.8768)
+    tri = np.array([[10.0, 0, 0], [1.0, 10.0, 0], [0, 0, 10.0]])[None]
+    with pytest.raises(NotImplementedError):
+        _check_cell(tri, (True,) * 3, 5.0)
+
+
+def test_shard_is_a_partition():
+    from quansino_b200.mc.tempering import shard
+
+    for n, w in [(64, 8), (4096, 8), (10, 4), (7, 8), (1, 1)]:
+        blocks = [shard(n, w, r) for r in range(w)]
+        assert blocks[0][0] == 0 and sum(c for _, c in blocks) == n
+        assert all(blocks[r][0] + blocks[r][1] == blocks[r + 1][0] for r in range(w - 1))
+        assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
