@@ -97,6 +97,38 @@ def cpu_reference(seconds_target: float = 12.0, threads: int | None = None):
     }
 
 
+def quansino_over_shim(seconds: float = 6.0):
+    """Secondary, informational: the UNMODIFIED quansino sources (baseline/_ref, installed with --no-deps) driving the
+    same workload single-threaded over oracle/ase_shim (ase itself is not installable).  None if unavailable."""
+    ref = ROOT / "baseline" / "_ref"
+    if not (ref / "quansino").exists():
+        return None
+    code = f"""
+import sys, time
+sys.path[:0] = [{str(ROOT)!r}, {str(ROOT / 'oracle' / 'ase_shim')!r}, {str(ref)!r}]
+import numpy as np
+from ase import Atoms
+from ase.calculators.emt import EMT
+from quansino.mc.canonical import Canonical
+from quansino.moves.displacement import DisplacementMove
+from quansino.operations.displacement import Ball
+from bench import make_inputs, N_ATOMS, TEMPERATURE, STEP_SIZE
+pos, cell = make_inputs(1)
+atoms = Atoms('Cu108', positions=pos[0], cell=cell, pbc=True, calculator=EMT())
+mc = Canonical(atoms, temperature=TEMPERATURE, max_cycles=27, seed=5, default_displacement_move=DisplacementMove(np.arange(N_ATOMS), Ball(STEP_SIZE)))
+mc.run(1)
+t0 = time.perf_counter(); n = 0
+while time.perf_counter() - t0 < {seconds}:
+    mc.run(1); n += 27
+print(n / (time.perf_counter() - t0))
+"""
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=str(ROOT))
+        return float(out.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -112,6 +144,7 @@ def run_reference_arm(args):
             vals.append(last["value"])
     v = float(np.mean(vals))
     last["value"] = v
+    last["quansino_over_ase_shim_attempts_per_s_1_thread"] = quansino_over_shim()
     line = {
         "impl": "reference",
         "metric": "MC move attempts/sec (all replicas)",
@@ -376,7 +409,7 @@ def run_native(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--replicas", type=int, default=4096, help="replicas per GPU")

@@ -96,3 +96,63 @@ def test_replica_offset_independence(cuda_lib):
     part.run(2)
     assert np.array_equal(full.download().positions[4:], part.download().positions)
     assert np.array_equal(full.batch.energy.cpu().numpy()[4:], part.batch.energy.cpu().numpy())
+
+
+def test_host_buffer_entry_point(cuda_lib):
+    """qmc_sweep_host: the C-ABI call with HOST buffers (what INTEGRATION.md's stub binds), against the oracle."""
+    import ctypes as C
+
+    from quansino_b200 import EMT, _lib
+
+    R = 3
+    pos, cell, n = cu_replicas(3, R, seed=13)
+    hp = np.ascontiguousarray(pos.transpose(0, 2, 1))
+    hc = np.ascontiguousarray(np.broadcast_to(cell.reshape(9), (R, 9)))
+    n_atoms = np.full(R, n, np.int32)
+    energy = np.zeros(R)
+    temp = np.full(R, 300.0)
+    counters = np.zeros((R, 4, 3), np.int64)
+    status = np.zeros(R, np.int32)
+    acc = np.zeros((R, n), np.int8)
+    etr = np.zeros((R, n))
+    b = _lib.Batch()
+    b.n_replicas, b.n_max, b.replica_offset = R, n, 0
+    b.pbc = (C.c_int32 * 3)(1, 1, 1)
+    b.pos, b.cell, b.n_atoms, b.energy, b.temperature = (a.ctypes.data for a in (hp, hc, n_atoms, energy, temp))
+    b.counters, b.status = counters.ctypes.data, status.ctypes.data
+    mv = (_lib.Move * 1)()
+    mv[0].type, mv[0].op, mv[0].step, mv[0].probability, mv[0].default_label = _lib.MOVE_DISPLACEMENT, _lib.OP_BALL, 0.1, 1.0, _lib.LABEL_NONE
+    tr = _lib.Trace()
+    tr.accepted, tr.energy = acc.ctypes.data, etr.ctypes.data
+    pot = EMT().lower("Cu")
+    _lib.check(cuda_lib.qmc_sweep_host(C.byref(pot), C.byref(b), mv, 1, 555, 0, n, C.byref(tr)))
+    assert not status.any()
+    par = oracle_par(EMT())
+    reps, otr = oracle_run(par, pos, n_atoms, cell, (1, 1, 1), [dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_BALL, step=0.1)], 555, n, range(R), temperature=300.0)
+    for r in range(R):
+        assert np.array_equal(acc[r], otr[r]["accepted"])
+        np.testing.assert_allclose(etr[r], otr[r]["energy"], rtol=RTOL_E, atol=1e-12)
+        np.testing.assert_allclose(hp[r].T, reps[r].positions, rtol=0, atol=1e-12)
+        assert counters[r, 0, 0] == n and counters[r, 0, 1] == otr[r]["accepted"].sum()
+
+
+def test_unsupported_requests_are_refused(cuda_lib):
+    from quansino_b200 import EMT, BatchedAtoms
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+    from quansino_b200.systems import fcc_cubic
+
+    pos, cell = fcc_cubic("Cu", 3)
+    atoms = BatchedAtoms.replicate(pos, cell, 2, calc=EMT())
+    mc = Canonical(atoms, temperature=300.0)
+    with pytest.raises(NotImplementedError):
+        mc.add_move(DisplacementMove(np.arange(108)), minimum_count=1)
+    with pytest.raises(ValueError):
+        mc.add_move(DisplacementMove(np.arange(108)), minimum_count=1000)
+    with pytest.raises(ValueError):
+        mc.add_move(object())
+    with pytest.raises(ZeroDivisionError):
+        Canonical(atoms, temperature=0.0)
+    pos1, cell1 = fcc_cubic("Cu", 1)  # the reference's 4-atom fixture: cell shorter than the EMT cutoff
+    with pytest.raises(NotImplementedError):
+        Canonical(BatchedAtoms.replicate(pos1, cell1, 2, calc=EMT()), temperature=300.0)
