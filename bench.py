@@ -170,26 +170,53 @@ def run_reference_arm(args):
 # clocks sampler
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region (NVML; falls back to nvidia-smi)."""
+
     QUERY = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self._stop = threading.Event()
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.sm.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)))
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        for name, bit in (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(
+            ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
+            capture_output=True, text=True, timeout=5,
+        ).stdout.strip()  # fmt: skip
+        s = [x.strip() for x in out.split(",")]
+        self.sm.append(float(s[0]))
+        self.mx.append(float(s[1]))
+        for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+            if v.lower().startswith("active"):
+                self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5,
-                ).stdout.strip()  # fmt: skip
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self._sample_nvml() if self._nvml is not None else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.005 if self._nvml is not None else 0.1)
 
     def __enter__(self):
         self._t.start()
@@ -200,18 +227,12 @@ class ClockSampler:
         self._t.join(timeout=6)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
         return {
-            "sm_mhz": float(np.median(sm)) if sm else None,
-            "sm_max_mhz": float(max(mx)) if mx else None,
-            "reasons": sorted(reasons),
-            "samples": len(self.samples),
+            "sm_mhz": float(np.median(self.sm)) if self.sm else None,
+            "sm_max_mhz": float(max(self.mx)) if self.mx else None,
+            "reasons": sorted(self.reasons),
+            "samples": len(self.sm),
+            "source": "nvml" if self._nvml is not None else "nvidia-smi",
         }
 
 

@@ -1,0 +1,103 @@
+#!/usr/bin/env python
+"""Secondary measurements: the other configurations of BASELINE.json (C3 isobaric, C4 grand-canonical LJ, C5 HMC) on one
+GPU.  Not part of the bench.py contract; results are recorded under profiles/.  Usage: python bench_configs.py [c3|c4|c5] ..."""
+
+from __future__ import annotations
+
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from quansino_b200 import EMT, BatchedAtoms, LennardJones  # noqa: E402
+from quansino_b200.integrators import Verlet  # noqa: E402
+from quansino_b200.mc import GrandCanonical, HamiltonianCanonical, Isobaric  # noqa: E402
+from quansino_b200.moves import CellMove, DisplacementMove, ExchangeMove, HamiltonianDisplacementMove  # noqa: E402
+from quansino_b200.operations import Ball, IsotropicDeformation  # noqa: E402
+from quansino_b200.systems import fcc_cubic, octahedron  # noqa: E402
+
+BAR = 6.241509125883258e-07
+
+
+def timed(mc, steps, warmup):
+    mc.validate_simulation()
+    mc.max_steps = 10**12
+    for _ in range(warmup):
+        for _ in mc.step():
+            pass
+        mc.step_count += 1
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0 = int(mc.batch.pair_evals.sum().item())
+    e0.record()
+    for _ in range(steps):
+        for _ in mc.step():
+            pass
+        mc.step_count += 1
+    e1.record()
+    torch.cuda.synchronize()
+    mc.batch.raise_on_status()
+    return e0.elapsed_time(e1) * 1e-3, int(mc.batch.pair_evals.sum().item()) - p0
+
+
+def c3(R=1024, steps=3):
+    pos0, cell = fcc_cubic("Cu", 5)
+    n = len(pos0)
+    rng = np.random.default_rng(1)
+    pos = pos0[None] + rng.normal(scale=0.05, size=(R, n, 3))
+    atoms = BatchedAtoms(pos, cell, np.full(R, n, np.int32), "Cu", (True,) * 3, EMT())
+    mc = Isobaric(atoms, temperature=300.0, pressure=1.0 * BAR, seed=3, resync_interval=0,
+                  default_displacement_move=DisplacementMove(np.arange(n), Ball(0.1)), default_cell_move=CellMove(IsotropicDeformation(0.05)))  # fmt: skip
+    t, pairs = timed(mc, steps, 1)
+    c = mc.counters()
+    return {"config": "C3 isobaric Cu 500-atom EMT, CellMove + DisplacementMove, 1024 replicas/GPU", "attempts_per_s": R * n * steps / t,
+            "pair_evals_per_s": pairs / t, "ms_per_step": 1e3 * t / steps, "cell_moves": int(c[:, 1, 0].sum()), "cell_accepted": int(c[:, 1, 1].sum()),
+            "disp_acceptance": float(c[:, 0, 1].sum() / c[:, 0, 0].sum())}  # fmt: skip
+
+
+def c4(R=4096, steps=5, n_max=128, mu=-0.5):
+    pos0, cell = octahedron("Pt", 4, 10.0)
+    n = len(pos0)
+    pos = np.zeros((R, n_max, 3))
+    pos[:, :n] = pos0
+    atoms = BatchedAtoms(pos, cell, np.full(R, n, np.int32), "Pt", (False,) * 3, LennardJones(sigma=2.5, epsilon=0.1))
+    mc = GrandCanonical(atoms, exchange_atoms=("Pt", (0, 0, 0)), temperature=300.0, chemical_potential=mu, max_cycles=100, seed=4, resync_interval=0,
+                        default_displacement_move=DisplacementMove(np.arange(n)), default_exchange_move=ExchangeMove(np.full(n, -1)))  # fmt: skip
+    mc.moves["default_displacement_move"].probability = 0.9
+    mc.moves["default_exchange_move"].probability = 0.1
+    t, pairs = timed(mc, steps, 2)
+    return {"config": "C4 grand-canonical Pt44 octahedron in box, LJ, ExchangeMove 0.1 / DisplacementMove 0.9, N_max 128, 4096 replicas/GPU",
+            "attempts_per_s": R * 100 * steps / t, "pair_evals_per_s": pairs / t, "ms_per_step": 1e3 * t / steps,
+            "mean_atoms": float(mc.batch.n_atoms.double().mean().item())}  # fmt: skip
+
+
+def c5(R=64, repeat=8, n_steps=100, attempts=1):
+    pos0, cell = fcc_cubic("Cu", repeat)
+    n = len(pos0)
+    rng = np.random.default_rng(5)
+    pos = pos0[None] + rng.normal(scale=0.03, size=(R, n, 3))
+    temps = 300.0 * 4.0 ** (np.arange(R) / max(R - 1, 1))
+    atoms = BatchedAtoms(pos, cell, np.full(R, n, np.int32), "Cu", (True,) * 3, EMT())
+    mc = HamiltonianCanonical(atoms, temperature=temps, max_cycles=1, seed=5, resync_interval=0,
+                              default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=1.0, max_steps=n_steps)))  # fmt: skip
+    t0 = time.perf_counter()
+    t, _ = timed(mc, attempts, 0)
+    force_evals = R * attempts * (n_steps + 1)
+    return {"config": f"C5 HMC Cu {n}-atom EMT, {R} temperatures, Verlet {n_steps} x 1 fs", "trajectories_per_s": R * attempts / t,
+            "force_evals_per_s": force_evals / t, "directional_pair_evals_per_s": force_evals * n * 78 * 2 / t, "s_per_attempt": t / attempts,
+            "acceptance": float(mc.counters()[:, 0, 1].sum() / (R * attempts)), "wall": time.perf_counter() - t0}  # fmt: skip
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c3", "c4", "c5"]
+    for w in which:
+        if w == "c5small":
+            print(json.dumps(c5(R=64, repeat=4, n_steps=20)), flush=True)
+        else:
+            print(json.dumps({"c3": c3, "c4": c4, "c5": c5}[w]()), flush=True)

@@ -10,7 +10,7 @@ import ctypes as C
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "libquansino_b200.so"
+LIB_PATH = Path(__import__("os").environ.get("QUANSINO_B200_LIB", _PKG / "libquansino_b200.so"))
 
 QMC_MAX_MOVES = 4
 LABEL_NONE = -(2**31)

@@ -70,6 +70,33 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> Path:
+    """Experimental build for kernel tuning: recompiles the EMT / NS=108 instantiation with extra -D flags and links it
+    with the standard objects into libquansino_b200_<name>.so (select it with QUANSINO_B200_LIB)."""
+    build()
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    vdir = OBJ / name
+    vdir.mkdir(parents=True, exist_ok=True)
+    obj = vdir / "sweep_inst_0_108.o"
+    cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v", "-DINST_POT=0", "-DINST_NS=108", *defines, "-c", str(CSRC / "sweep_inst.cu"), "-o", str(obj)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("variant build failed")
+    for line in (res.stdout + res.stderr).splitlines():
+        if "ELi0EEEv" in line or "registers" in line or "spill" in line:
+            pass
+    info = [l for l in (res.stdout + res.stderr).splitlines() if "registers" in l or "spill" in l]
+    sys.stderr.write(f"[{name}] " + " | ".join(info[:2]) + "\n")
+    objs = [str(o) for _, o, _ in _jobs() if o.name != "sweep_inst_0_108.o"] + [str(obj)]
+    lib = PKG / f"libquansino_b200_{name}.so"
+    res = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(lib), *objs], capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("variant link failed")
+    return lib
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(LIB)

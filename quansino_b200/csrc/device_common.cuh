@@ -74,6 +74,7 @@ struct PotDev {
     // EMT (ase/calculators/emt.py, single species)
     double acut, rc, rc_list, eta2, beta_s0, kappa, inv_beta, s0, lambda, E0, V0x6, inv12gamma1, neg_inv_beta_eta2;
     double neghalfv0overgamma2;
+    double theta_c, sig1_a, sig1_c, sig2_a, sig2_c;  // exponent = a * r + c for theta, sigma_1, sigma_2
     // LJ (ase/calculators/lj.py, smooth=False)
     double sigma2, eps4, lj_rc2, lj_e0;
     // forces
@@ -84,9 +85,10 @@ struct PotDev {
 // _calc_dsigma2 with chi = 1); zero outside `r < rc_list` (_get_neighbors).  Branch-free: 1 sqrt, 3 exp, 1 reciprocal.
 __device__ __forceinline__ void emt_pair(const PotDev &p, double r2, double &s1, double &s2) {
     const double r = sqrt_fast(fmax(r2, 1e-200));
-    const double w = rcp_fast(1.0 + exp_fast(p.acut * (r - p.rc)));
-    const double a = exp_fast(-p.eta2 * (r - p.beta_s0)) * w;
-    const double b = exp_fast(-p.kappa * (r * p.inv_beta - p.s0)) * w;
+    // the three exponents are linear in r: one FMA each (constants folded on the host)
+    const double w = rcp_fast(1.0 + exp_fast(fma(p.acut, r, p.theta_c)));
+    const double a = exp_fast(fma(p.sig1_a, r, p.sig1_c)) * w;
+    const double b = exp_fast(fma(p.sig2_a, r, p.sig2_c)) * w;
     const bool in = r < p.rc_list;
     s1 = in ? a : 0.0;
     s2 = in ? b : 0.0;

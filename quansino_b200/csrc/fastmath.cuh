@@ -12,11 +12,11 @@
 
 namespace qmc {
 
-__device__ __constant__ double FM_EXP[12] = {
-    // 1/k!, k = 2..13
-    5.0e-01, 1.6666666666666666e-01, 4.1666666666666664e-02, 8.3333333333333332e-03, 1.3888888888888889e-03,
-    1.9841269841269841e-04, 2.4801587301587302e-05, 2.7557319223985893e-06, 2.7557319223985888e-07,
-    2.5052108385441720e-08, 2.0876756987868100e-09, 1.6059043836821613e-10};
+// exp(r) = 1 + r + r^2 q(r) on |r| <= ln(2)/2: q = degree-9 Chebyshev fit of (exp(r) - 1 - r) / r^2 (mpmath, 50 digits),
+// maximum relative error of the whole expression 1.6e-17 with the coefficients rounded to double
+__device__ __constant__ double FM_EXP[10] = {0.5000000000000001,    0.16666666666666669,   0.041666666666624164,  0.008333333333330065,
+                                             0.0013888888917196736, 0.00019841269863040559, 2.480152132234228e-05, 2.7557268480289716e-06,
+                                             2.7620075892548164e-07, 2.51003758422237e-08};
 __device__ __constant__ double FM_LOG[7] = {6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,
                                             2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01,
                                             1.479819860511658591e-01};
@@ -59,9 +59,9 @@ __device__ __forceinline__ double exp_fast(double x) {
     const double k = t - FM_MAGIC;
     double r = fma(k, -FM_LN2_HI, x);
     r = fma(k, -FM_LN2_LO, r);
-    double q = FM_EXP[11];
+    double q = FM_EXP[9];
 #pragma unroll
-    for (int i = 10; i >= 0; --i) q = fma(q, r, FM_EXP[i]);
+    for (int i = 8; i >= 0; --i) q = fma(q, r, FM_EXP[i]);
     const double r2 = r * r;
     const double p = fma(r2, q, r) + 1.0;
     const int n = __double2loint(t);

@@ -55,6 +55,11 @@ int make_potdev(const qmc_potential_t *p, qmc::PotDev &d) {
         d.neg_inv_beta_eta2 = -1.0 / (p->beta * p->eta2);
         d.neghalfv0overgamma2 = -0.5 * p->V0 / p->gamma2;
         d.kappa_over_beta = p->kappa / p->beta;
+        d.theta_c = -p->acut * p->rc;
+        d.sig1_a = -p->eta2;
+        d.sig1_c = p->eta2 * p->beta * p->s0;
+        d.sig2_a = -p->kappa / p->beta;
+        d.sig2_c = p->kappa * p->s0;
     } else if (p->kind == QMC_POT_LJ) {
         if (!(p->sigma > 0) || !(p->lj_rc > 0)) return fail(QMC_ERR_INVALID, "LJ parameters not initialised");
         d.cut = p->lj_rc;

@@ -27,6 +27,11 @@
 
 namespace qmc {
 
+#ifdef QMC_SCAN_UNROLL
+constexpr int kScanUnroll = QMC_SCAN_UNROLL;
+#else
+constexpr int kScanUnroll = 1;
+#endif
 constexpr int XCAP = 64;             // capacity for second-image list entries of one attempt
 constexpr unsigned NOPOS = 0xFFFFu;  // pp half-word: no list entry
 constexpr int SMEM_PER_SM = 232448;  // 227 KB usable per SM on sm_100
@@ -89,6 +94,7 @@ struct Rep {
 struct Axis {
     double L, invL, thr;
 };
+
 
 // The cell as the kernels see it.  UNIFORM: every replica shares one constant cell, values come straight from the kernel
 // arguments (constant bank operands, no registers); otherwise per-replica values are kept in shared memory.
@@ -160,6 +166,7 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const Rep<LY> 
     const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);
     int cnt = 0, nq = 0;
     n2 = 0;
+#pragma unroll kScanUnroll
     for (int base = 0; base < n_scan; base += 32) {
         const int j = base + lane;
         const bool valid = j < n_scan && j != i_excl;
@@ -244,55 +251,69 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const Rep<LY> 
 // pairs: evaluate the list.  MODE 0 leaves the sigma_1 term of every nearest-image entry in lr[e], with the terms of
 // the second images of the same atom and side added onto it.
 template <class LY, int MODE>
-__device__ __forceinline__ void eval_list(const PotDev &pot, const Rep<LY> &R, const int lane, int cnt, int xstart, DeltaAcc &acc) {
+__device__ __forceinline__ void eval_pass(const PotDev &pot, const Rep<LY> &R, const int lane, int e0, int cnt, int xstart,
+                                          DeltaAcc &acc) {
     constexpr bool TRACK = (MODE == 0 && LY::EMT);
-    for (int e0 = 0; e0 < cnt; e0 += 32) {
-        const int e = e0 + lane;
-        const bool act = e < cnt;
-        const double r2s = act ? R.lr(e) : 1.0;
-        const bool isnew = r2s > 0.0;
-        const double r2 = fabs(r2s);
-        if (LY::EMT) {
-            double s1, s2;
-            emt_pair(pot, r2, s1, s2);
-            s1 = act ? s1 : 0.0;
-            s2 = act ? s2 : 0.0;
-            acc.v += isnew ? s2 : -s2;
-            acc.snew += isnew ? s1 : 0.0;
-            if (TRACK) {
-                if (e0 + 32 <= xstart) {  // nearest images only: every entry owns its slot
-                    R.lr(e) = s1;
-                } else {
-                    const bool is_x = act && e >= xstart;
-                    if (act && !is_x) R.lr(e) = s1;
-                    __syncwarp();
-                    unsigned tgt = 0x10000u + lane;
-                    if (is_x) {
-                        const unsigned code = R.pp(R.xj(e - xstart));
-                        tgt = isnew ? (code >> 16) : (code & 0xFFFFu);
-                    }
-                    const unsigned grp = __match_any_sync(FULL, tgt);
-                    const int maxc = __reduce_max_sync(FULL, __popc(grp));
-                    double a = 0.0;
-                    unsigned rem = grp;
-                    for (int t = 0; t < maxc; ++t) {
-                        const int src = rem ? (__ffs(rem) - 1) : lane;
-                        const double val = __shfl_sync(FULL, s1, src);
-                        if (rem) {
-                            a += val;
-                            rem &= rem - 1;
-                        }
-                    }
-                    if (is_x && lane == (__ffs(grp) - 1)) R.lr(tgt) += a;
-                    __syncwarp();
+    const int e = e0 + lane;
+    const bool act = e < cnt;
+    const double r2s = act ? R.lr(e) : 1.0;
+    const bool isnew = r2s > 0.0;
+    const double r2 = fabs(r2s);
+    if (LY::EMT) {
+        double s1, s2;
+        emt_pair(pot, r2, s1, s2);
+        s1 = act ? s1 : 0.0;
+        s2 = act ? s2 : 0.0;
+        acc.v += isnew ? s2 : -s2;
+        acc.snew += isnew ? s1 : 0.0;
+        if (TRACK) {
+            if (e0 + 32 <= xstart) {  // nearest images only: every entry owns its slot
+                R.lr(e) = s1;
+            } else {
+                const bool is_x = act && e >= xstart;
+                if (act && !is_x) R.lr(e) = s1;
+                __syncwarp();
+                unsigned tgt = 0x10000u + lane;
+                if (is_x) {
+                    const unsigned code = R.pp(R.xj(e - xstart));
+                    tgt = isnew ? (code >> 16) : (code & 0xFFFFu);
                 }
+                const unsigned grp = __match_any_sync(FULL, tgt);
+                const int maxc = __reduce_max_sync(FULL, __popc(grp));
+                double a = 0.0;
+                unsigned rem = grp;
+                for (int t = 0; t < maxc; ++t) {
+                    const int src = rem ? (__ffs(rem) - 1) : lane;
+                    const double val = __shfl_sync(FULL, s1, src);
+                    if (rem) {
+                        a += val;
+                        rem &= rem - 1;
+                    }
+                }
+                if (is_x && lane == (__ffs(grp) - 1)) R.lr(tgt) += a;
+                __syncwarp();
             }
-        } else {
-            const double ep = act ? lj_pair(pot, r2) : 0.0;
-            acc.v += isnew ? ep : -ep;
         }
-        acc.pairs += act ? 1 : 0;
+    } else {
+        const double ep = act ? lj_pair(pot, r2) : 0.0;
+        acc.v += isnew ? ep : -ep;
     }
+    acc.pairs += act ? 1 : 0;
+}
+
+template <class LY, int MODE>
+__device__ __forceinline__ void eval_list(const PotDev &pot, const Rep<LY> &R, const int lane, int cnt, int xstart, DeltaAcc &acc) {
+#ifdef QMC_PAIR_UNROLL2
+    // two independent passes per iteration: twice the instruction-level parallelism in the FP64 chains
+    int e0 = 0;
+    for (; e0 + 32 < cnt; e0 += 64) {
+        eval_pass<LY, MODE>(pot, R, lane, e0, cnt, xstart, acc);
+        eval_pass<LY, MODE>(pot, R, lane, e0 + 32, cnt, xstart, acc);
+    }
+    if (e0 < cnt) eval_pass<LY, MODE>(pot, R, lane, e0, cnt, xstart, acc);
+#else
+    for (int e0 = 0; e0 < cnt; e0 += 32) eval_pass<LY, MODE>(pot, R, lane, e0, cnt, xstart, acc);
+#endif
     __syncwarp();
 }
 
