@@ -137,8 +137,9 @@ int64_t qmc_sweep_smem_per_replica(const qmc_potential_t *pot, int32_t n_max);
  * of (atom, neighbour image) pairs evaluated. */
 int qmc_energy_full(const qmc_potential_t *pot, const qmc_batch_t *batch, int64_t *pair_count, void *stream);
 
-/* full energy AND forces (device [R][3][n_max]) -- `atoms.get_forces()` */
-int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double *forces, void *stream);
+/* full energy AND forces (device [R][3][n_max]) -- `atoms.get_forces()`; workspace as for qmc_hmc */
+int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double *forces, void *workspace,
+                    int64_t workspace_bytes, void *stream);
 
 /* n_attempts cycles of MonteCarlo.step (src/quansino/mc/core.py:353-384) for every replica: move types
  * displacement / cell / exchange; state committed in place. */
@@ -149,7 +150,8 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
 int qmc_hmc(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move_t *move, uint64_t seed,
             uint64_t attempt_base, int32_t n_attempts, const qmc_trace_t *trace, void *workspace,
             int64_t workspace_bytes, void *stream);
-int64_t qmc_hmc_workspace_bytes(const qmc_batch_t *batch);
+/* device scratch the Hamiltonian kernels need (double-buffered positions, momenta, neighbour list, partial sums) */
+int64_t qmc_hmc_workspace_bytes(const qmc_potential_t *pot, const qmc_batch_t *batch);
 
 /* parallel tempering between temperature-adjacent replicas (no counterpart in the reference):
  * `energies_all` / `temperatures_all` are device [R_global] arrays every rank holds after the all-gather;

@@ -119,10 +119,10 @@ def load() -> C.CDLL:
     L.qmc_sweep_smem_per_replica.argtypes = [C.POINTER(Potential), i32]
     L.qmc_sweep_smem_per_replica.restype = i64
     L.qmc_energy_full.argtypes = [C.POINTER(Potential), C.POINTER(Batch), vp, vp]
-    L.qmc_forces_full.argtypes = [C.POINTER(Potential), C.POINTER(Batch), vp, vp]
+    L.qmc_forces_full.argtypes = [C.POINTER(Potential), C.POINTER(Batch), vp, vp, i64, vp]
     L.qmc_sweep.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), i32, u64, u64, i32, C.POINTER(Trace), vp]
     L.qmc_hmc.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), u64, u64, i32, C.POINTER(Trace), vp, i64, vp]
-    L.qmc_hmc_workspace_bytes.argtypes = [C.POINTER(Batch)]
+    L.qmc_hmc_workspace_bytes.argtypes = [C.POINTER(Potential), C.POINTER(Batch)]
     L.qmc_hmc_workspace_bytes.restype = i64
     L.qmc_pt_swap.argtypes = [vp, vp, i32, u64, u64, vp, vp]
     L.qmc_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]

@@ -237,7 +237,13 @@ class ReplicaBatch:
 
     # -- kernels -----------------------------------------------------------------------------------
     def energy_full(self, pair_count: torch.Tensor | None = None) -> torch.Tensor:
-        """Full potential energy of every replica; primes the EMT caches (``validate_simulation``)."""
+        """Full potential energy of every replica; primes the EMT caches (``validate_simulation``).
+
+        Replicas beyond the shared-memory capacity of the warp-per-replica kernels (> 1024 atoms: the Hamiltonian
+        configurations) are evaluated by the neighbour-list kernels instead (energy only, no sweep caches)."""
+        if self.n_max > 1024 and pair_count is None:
+            self.forces_full()
+            return self.energy
         with torch.cuda.device(self.device):
             b = self.struct()
             _lib.check(
@@ -252,8 +258,20 @@ class ReplicaBatch:
         f = torch.zeros_like(self.pos)
         with torch.cuda.device(self.device):
             b = self.struct()
-            _lib.check(self.lib.qmc_forces_full(C.byref(self.potential), C.byref(b), f.data_ptr(), self.stream()))
+            ws = self.hmc_workspace(b)
+            _lib.check(self.lib.qmc_forces_full(C.byref(self.potential), C.byref(b), f.data_ptr(), ws.data_ptr(), ws.numel(), self.stream()))
         return f
+
+    def hmc_workspace(self, b: _lib.Batch | None = None) -> torch.Tensor:
+        """Device scratch of the Hamiltonian kernels (allocated once, reused)."""
+        b = b if b is not None else self.struct()
+        need = int(self.lib.qmc_hmc_workspace_bytes(C.byref(self.potential), C.byref(b)))
+        if need < 0:
+            _lib.check(need)
+        ws = getattr(self, "_hmc_ws", None)
+        if ws is None or ws.numel() < need:
+            self._hmc_ws = ws = torch.zeros(max(need, 256), dtype=torch.uint8, device=self.device)
+        return ws
 
     def raise_on_status(self) -> None:
         """Turn status bits the kernels recorded into the exceptions the reference would have raised."""

@@ -110,12 +110,12 @@ __device__ __forceinline__ double emt_embed_deds(const PotDev &p, double sigma1,
         deds = 0.0;
         return -p.E0;
     }
-    const double ds = log(sigma1 * p.inv12gamma1) * p.neg_inv_beta_eta2;
+    const double ds = log_fast(sigma1 * p.inv12gamma1) * p.neg_inv_beta_eta2;
     const double x = p.lambda * ds;
-    const double ex = exp(-x);
-    const double z = p.V0x6 * exp(-p.kappa * ds);
+    const double ex = exp_fast(-x);
+    const double z = p.V0x6 * exp_fast(-p.kappa * ds);
     // deds = (-E0 lambda x e^-x - kappa z) / (-beta eta2 sigma1)
-    deds = (-p.E0 * p.lambda * x * ex - p.kappa * z) * p.neg_inv_beta_eta2 / sigma1;
+    deds = (-p.E0 * p.lambda * x * ex - p.kappa * z) * p.neg_inv_beta_eta2 * rcp_fast(sigma1);
     return p.E0 * (1.0 + x) * ex + z - p.E0;
 }
 
@@ -125,6 +125,14 @@ __device__ __forceinline__ double lj_pair(const PotDev &p, double r2) {
     const double c6 = q * q * q;
     const double e = p.eps4 * (c6 * c6 - c6) - p.lj_e0;
     return (r2 > p.lj_rc2) ? 0.0 : e;
+}
+
+// u < exp(x) without evaluating exp where the answer is already decided; flags the reference's OverflowError
+__device__ __forceinline__ bool metropolis(double u, double x, int &status) {
+    if (x > EXP_OVERFLOW) status |= QMC_STATUS_EXP_OVERFLOW;
+    if (x >= 0.0) return true;  // exp(x) >= 1 > u
+    if (!(x > -700.0)) return false;  // exp(x) < 1e-304: below every u > 0 (u == 0 has probability 2^-53; DESIGN.md ties)
+    return u < exp_fast(x);
 }
 
 }  // namespace qmc

@@ -1,4 +1,4 @@
-// Hamiltonian Monte Carlo: fused force + velocity-Verlet trajectory + acceptance, and parallel-tempering swaps.
+// Hamiltonian Monte Carlo: force + velocity-Verlet trajectory + acceptance, and parallel-tempering swaps.
 //
 // One attempt (reference file:line):
 //   momenta     p = z sqrt(m kB T), z ~ N(0,1) in row-major (N,3) order            [utils/dynamics.py:27-43]
@@ -6,64 +6,102 @@
 //   trajectory  F = forces; max_steps x { p += F dt/2; x += p/m dt; p = (x_new - x) m / dt (apply_constraints);
 //               F = forces(x); p += F dt/2 }                                        [integrators/displacement.py:52-81]
 //   criteria    u < exp(-((E_pot + E_kin) - last_pot - last_kin) / kT)              [mc/criteria.py:117-140]
-//   commit      positions / momenta / energies kept on accept, positions reloaded on reject
-//                                                                                   [mc/contexts.py:144-156,186-198]
+//   commit      positions / momenta / energies kept on accept, untouched on reject  [mc/contexts.py:144-156,186-198]
 //
-// Layout: one CTA per replica; positions, momenta, forces, sigma_1 and dE/dsigma_1 of the replica stay in shared
-// memory for the whole launch (88 B per atom: 2048 atoms = 176 KB of the 227 KB a B200 CTA can own).  Forces
-// are the analytic gradient of exactly the energy expression of the sweep kernel, two passes like ASE
-// (sigma_1 first, then the dE/dsigma_1-weighted pair terms: emt.py _calc_e_c_a2 / _calc_fs_c_a2 / _calc_efs_a1).
+// Organisation (config C5: 64 replicas x 2048 atoms, 8 per GPU on 8 GPUs): LPA lanes per atom (chosen so that the whole
+// GPU is busy whatever the replica count), a Verlet neighbour list with skin in global memory ([slot][atom]: coalesced
+// for LPA = 1, L2-resident), double-buffered positions, and four kernels per force evaluation:
+//   build   (only when an atom moved more than skin / 2 since the last build: the kernel exits at once otherwise)
+//   pass 1  sigma_1, pair energy, embedding energy and dE/dsigma_1 per atom          [emt.py _calc_e_c_a2]
+//   pass 2  forces (recomputing the pair functions rather than streaming 32 B per pair through HBM), fused with the
+//           velocity-Verlet update of the atom and the displacement check            [emt.py _calc_fs_c_a2 / _calc_efs_a1]
+//   finish  deterministic reductions (fixed-order sums of per-CTA partials), acceptance test, commit
+// Forces are the analytic gradient of exactly the energy expression of the sweep kernel.
 #pragma once
+
+#include <cstdio>
+#include <cstring>
 
 #include "replica_warp.cuh"
 
 namespace qmc {
 
-constexpr int HMC_THREADS = 1024;
+constexpr int HMC_THREADS = 128;
+constexpr double HMC_SKIN = 1.0;  // Angstrom
+
+struct HmcWork {  // carved from the caller's workspace
+    double *x[2];      // [R][3][N] double-buffered positions
+    double *p;         // [R][3][N] momenta
+    double *deds;      // [R][N]
+    double *ref;       // [R][3][N] positions at the last list build
+    double *partial;   // [R][NB][2] per-CTA partial sums (energy, kinetic)
+    double *ke0;       // [R][NB]
+    double *result;    // [R][2] accepted (energy, kinetic) of the attempt, published after every CTA has read the old values
+    unsigned *list;    // [R][max_nb][N]
+    int *nnb;          // [R][N]
+    int *flags;        // [R] rebuild requested
+    int max_nb, nb_blocks;
+};
 
 struct HmcArgs {
     PotDev pot;
     qmc_batch_t b;
+    HmcWork w;
     double dt;
     int n_steps;
-    unsigned long long seed, attempt_base;
-    int n_attempts;
+    unsigned long long seed, attempt;
+    int trace_index, n_attempts;
     qmc_trace_t tr;
-    double *forces_out;  // qmc_forces_full only
-    int ns;
+    double *forces_out;
+    int lpa;   // lanes per atom (power of two <= 32)
+    int cur;   // position buffer holding the current positions
+    int mode;  // pass 2: 0 first evaluation, 1 middle, 2 last, 3 forces only, 4 single evaluation of a zero-step trajectory
 };
 
-struct HmcSmem {
-    double *x, *y, *z, *px, *py, *pz, *fx, *fy, *fz, *sig, *deds;
-    double *red;  // [32] block reduction scratch
-    double *bc;   // [8] broadcast scratch
-};
+__host__ inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 
-__host__ __device__ inline int64_t hmc_smem_bytes(int n_max) {
-    const int ns = round_up(n_max, 4);
-    return (int64_t)ns * 8 * 11 + 48 * 8;
+__host__ inline int hmc_max_neighbours(const PotDev &pot, const qmc_batch_t &b) {
+    const double rl = pot.cut + HMC_SKIN;
+    double est = 512.0;
+    if (b.cells_uniform && b.cell_diag[0] > 0 && b.cell_diag[1] > 0 && b.cell_diag[2] > 0) {
+        const double density = (double)b.n_max / (b.cell_diag[0] * b.cell_diag[1] * b.cell_diag[2]);
+        est = density * 4.18879 * rl * rl * rl * 1.5 + 24.0;
+    }
+    int m = (int)est;
+    m = (m + 7) / 8 * 8;
+    return m < 32 ? 32 : (m > 1024 ? 1024 : m);
 }
 
-__device__ inline void hmc_carve(HmcSmem &S, unsigned char *base, int ns) {
-    double *d = reinterpret_cast<double *>(base);
-    S.x = d; d += ns; S.y = d; d += ns; S.z = d; d += ns;
-    S.px = d; d += ns; S.py = d; d += ns; S.pz = d; d += ns;
-    S.fx = d; d += ns; S.fy = d; d += ns; S.fz = d; d += ns;
-    S.sig = d; d += ns; S.deds = d; d += ns;
-    S.red = d; d += 32;
-    S.bc = d;
+__host__ inline int64_t hmc_carve(const PotDev &pot, const qmc_batch_t &b, void *base, HmcWork *w) {
+    const int64_t R = b.n_replicas, N = b.n_max;
+    const int max_nb = hmc_max_neighbours(pot, b);
+    const int nb_blocks = (int)((N * 32 + HMC_THREADS - 1) / HMC_THREADS);  // upper bound over all lanes-per-atom choices
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        void *p = base ? (char *)base + off : nullptr;
+        off += align256(bytes);
+        return p;
+    };
+    void *x0 = take(R * 3 * N * 8), *x1 = take(R * 3 * N * 8), *p = take(R * 3 * N * 8), *deds = take(R * N * 8), *ref = take(R * 3 * N * 8);
+    void *partial = take(R * nb_blocks * 2 * 8), *ke0 = take(R * nb_blocks * 8), *list = take(R * (int64_t)max_nb * N * 4);
+    void *nnb = take(R * N * 4), *flags = take(R * 4), *result = take(R * 2 * 8);
+    if (w) {
+        w->x[0] = (double *)x0; w->x[1] = (double *)x1; w->p = (double *)p; w->deds = (double *)deds; w->ref = (double *)ref;
+        w->partial = (double *)partial; w->ke0 = (double *)ke0; w->list = (unsigned *)list; w->nnb = (int *)nnb; w->flags = (int *)flags; w->result = (double *)result;
+        w->max_nb = max_nb; w->nb_blocks = nb_blocks;
+    }
+    return off;
 }
 
 // deterministic block sum (fixed tree); result on every thread
 __device__ inline double block_sum(double v, double *red) {
     v = warp_sum(v);
-    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const int wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     __syncthreads();
-    if ((threadIdx.x & 31) == 0) red[w] = v;
+    if ((threadIdx.x & 31) == 0) red[wid] = v;
     __syncthreads();
-    double t = (threadIdx.x & 31) < nw ? red[threadIdx.x & 31] : 0.0;
-    t = warp_sum(t);
-    return t;
+    double t = (int)(threadIdx.x & 31) < nw ? red[threadIdx.x & 31] : 0.0;
+    return warp_sum(t);
 }
 
 struct CellDev {
@@ -71,102 +109,17 @@ struct CellDev {
     bool per[3];
 };
 
-// Energy and forces of the replica in shared memory.  Returns the potential energy on every thread.
-template <int POT>
-__device__ inline double hmc_energy_forces(const PotDev &pot, const HmcSmem &S, const CellDev &C, int n) {
-    double epart = 0.0;
-    // pass 1: sigma_1, pair energy, embedding energy and its derivative
-    for (int a = threadIdx.x; a < n; a += blockDim.x) {
-        const double xa = S.x[a], ya = S.y[a], za = S.z[a];
-        double s1 = 0.0, s2 = 0.0;
-        for (int j = 0; j < n; ++j) {
-            if (j == a) continue;
-            double d0[3], d1[3];
-            unsigned avail = 0;
-            axis_images(xa, S.x[j], C.L[0], C.invL[0], C.thr[0], C.per[0], d0[0], d1[0], avail, 1u);
-            axis_images(ya, S.y[j], C.L[1], C.invL[1], C.thr[1], C.per[1], d0[1], d1[1], avail, 2u);
-            axis_images(za, S.z[j], C.L[2], C.invL[2], C.thr[2], C.per[2], d0[2], d1[2], avail, 4u);
-            unsigned c = 0;
-            while (true) {
-                const double dx = (c & 1u) ? d1[0] : d0[0], dy = (c & 2u) ? d1[1] : d0[1], dz = (c & 4u) ? d1[2] : d0[2];
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 < pot.cut_pre2) {
-                    if (POT == QMC_POT_EMT) {
-                        double t1, t2;
-                        emt_pair(pot, r2, t1, t2);
-                        s1 += t1;
-                        s2 += t2;
-                    } else {
-                        s2 += lj_pair(pot, r2);
-                    }
-                }
-                if (c == avail) break;
-                c = ((c | (~avail & 7u)) + 1u) & avail;
-            }
-        }
-        if (POT == QMC_POT_EMT) {
-            double de;
-            const double ea = emt_embed_deds(pot, s1, de);
-            S.sig[a] = s1;
-            S.deds[a] = de;
-            epart += ea + pot.neghalfv0overgamma2 * s2;
-        } else {
-            epart += 0.5 * s2;
-        }
+__device__ inline bool hmc_cell(const HmcArgs &a, int r, double cut, CellDev &C) {
+    bool ok = true;
+    for (int k = 0; k < 3; ++k) {
+        const double L = a.b.cell[(size_t)r * 9 + 4 * k];
+        C.L[k] = L;
+        C.per[k] = a.b.pbc[k] != 0;
+        C.invL[k] = C.per[k] ? 1.0 / L : 0.0;
+        C.thr[k] = C.per[k] ? L - cut : 1e300;
+        if (C.per[k] && !(L >= cut)) ok = false;
     }
-    const double energy = block_sum(epart, S.red);
-    __syncthreads();
-    // pass 2: forces
-    for (int a = threadIdx.x; a < n; a += blockDim.x) {
-        const double xa = S.x[a], ya = S.y[a], za = S.z[a];
-        const double da = POT == QMC_POT_EMT ? S.deds[a] : 0.0;
-        double f0 = 0.0, f1 = 0.0, f2 = 0.0;
-        for (int j = 0; j < n; ++j) {
-            if (j == a) continue;
-            double d0[3], d1[3];
-            unsigned avail = 0;
-            axis_images(xa, S.x[j], C.L[0], C.invL[0], C.thr[0], C.per[0], d0[0], d1[0], avail, 1u);
-            axis_images(ya, S.y[j], C.L[1], C.invL[1], C.thr[1], C.per[1], d0[1], d1[1], avail, 2u);
-            axis_images(za, S.z[j], C.L[2], C.invL[2], C.thr[2], C.per[2], d0[2], d1[2], avail, 4u);
-            unsigned c = 0;
-            while (true) {
-                const double dx = (c & 1u) ? d1[0] : d0[0], dy = (c & 2u) ? d1[1] : d0[1], dz = (c & 4u) ? d1[2] : d0[2];
-                const double r2 = dx * dx + dy * dy + dz * dz;
-                if (r2 < pot.cut_pre2) {
-                    double g = 0.0;
-                    if (POT == QMC_POT_EMT) {
-                        const double r = sqrt(r2);
-                        if (r < pot.rc_list) {
-                            const double w = 1.0 / (1.0 + exp(pot.acut * (r - pot.rc)));
-                            const double dwdroverw = pot.acut * (w - 1.0);
-                            const double ds1 = exp(-pot.eta2 * (r - pot.beta_s0)) * w;
-                            const double ds2 = exp(-pot.kappa * (r * pot.inv_beta - pot.s0)) * w;
-                            const double es = pot.neghalfv0overgamma2 * ds2;
-                            const double dedr_pair = es * (dwdroverw - pot.kappa_over_beta);
-                            const double dds1dr = ds1 * (dwdroverw - pot.eta2);
-                            g = ((dedr_pair + dedr_pair) + (da * dds1dr + S.deds[j] * dds1dr)) / r;
-                        }
-                    } else {
-                        if (!(r2 > pot.lj_rc2)) {
-                            const double q = pot.sigma2 / r2;
-                            const double c6 = q * q * q;
-                            g = -6.0 * pot.eps4 * (2.0 * c6 * c6 - c6) / r2;  // -24 eps (2 c12 - c6) / r2
-                        }
-                    }
-                    f0 += g * dx;
-                    f1 += g * dy;
-                    f2 += g * dz;
-                }
-                if (c == avail) break;
-                c = ((c | (~avail & 7u)) + 1u) & avail;
-            }
-        }
-        S.fx[a] = f0;
-        S.fy[a] = f1;
-        S.fz[a] = f2;
-    }
-    __syncthreads();
-    return energy;
+    return ok;
 }
 
 __device__ inline double hmc_normal(PhiloxKey key, unsigned long long attempt, uint32_t replica, uint32_t m) {
@@ -177,190 +130,420 @@ __device__ inline double hmc_normal(PhiloxKey key, unsigned long long attempt, u
     return (m % 2u == 0u) ? rr * cos(t) : rr * sin(t);
 }
 
-template <int POT, bool FORCES_ONLY>
-__global__ void __launch_bounds__(HMC_THREADS, 1) hmc_kernel(const __grid_constant__ HmcArgs a) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    const int r = blockIdx.x;
-    const PotDev &pot = a.pot;
+// ---- init: working copies, momenta, KE_0 partials, rebuild request --------------------------------------------
+__global__ void __launch_bounds__(HMC_THREADS) hmc_init_kernel(const __grid_constant__ HmcArgs a) {
+    __shared__ double red[32];
+    const int r = blockIdx.y, nmax = a.b.n_max, n = a.b.n_atoms[r];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t base = (size_t)r * 3 * nmax;
+    double ke = 0.0;
+    if (i < n) {
+        const double mass = a.b.mass;
+        const double pscale = sqrt(mass * (a.b.temperature[r] * KB));
+        const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
+        const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            a.w.x[0][base + (size_t)c * nmax + i] = a.b.pos[base + (size_t)c * nmax + i];
+            const double p = hmc_normal(key, a.attempt, grep, 3u * i + c) * pscale;
+            a.w.p[base + (size_t)c * nmax + i] = p;
+            ke += p * (p / mass);
+        }
+    }
+    const double s = block_sum(ke, red);
+    if (threadIdx.x == 0) {
+        a.w.ke0[(size_t)r * a.w.nb_blocks + blockIdx.x] = s;
+        if (blockIdx.x == 0) a.w.flags[r] = 1;
+    }
+}
+
+// ---- neighbour list (brute force over tiles staged in shared memory; only when requested) ----------------------
+__global__ void __launch_bounds__(HMC_THREADS) hmc_build_kernel(const __grid_constant__ HmcArgs a) {
+    __shared__ double sx[HMC_THREADS], sy[HMC_THREADS], sz[HMC_THREADS];
+    const int r = blockIdx.y;
+    if (a.w.flags[r] == 0) return;
     const int nmax = a.b.n_max, n = a.b.n_atoms[r];
-    HmcSmem S;
-    hmc_carve(S, smem, a.ns);
-    double *gx = a.b.pos + (size_t)r * 3 * nmax, *gy = gx + nmax, *gz = gy + nmax;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        S.x[j] = gx[j];
-        S.y[j] = gy[j];
-        S.z[j] = gz[j];
-    }
+    const double rl = a.pot.cut + HMC_SKIN, rl2 = rl * rl;
     CellDev C;
-    bool cell_ok = true;
-    {
-        const double cutp = pot.cut * (1.0 + 1e-9);
-        for (int k = 0; k < 3; ++k) {
-            const double L = a.b.cell[(size_t)r * 9 + 4 * k];
-            C.L[k] = L;
-            C.per[k] = a.b.pbc[k] != 0;
-            C.invL[k] = C.per[k] ? 1.0 / L : 0.0;
-            C.thr[k] = C.per[k] ? L - cutp : 1e300;
-            if (C.per[k] && !(L >= cutp)) cell_ok = false;
-        }
-    }
-    __syncthreads();
-    if (!cell_ok) {
-        if (threadIdx.x == 0) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
+    if (!hmc_cell(a, r, rl * (1.0 + 1e-9), C)) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
         return;
     }
-    if (FORCES_ONLY) {
-        const double e = hmc_energy_forces<POT>(pot, S, C, n);
-        double *fo = a.forces_out + (size_t)r * 3 * nmax;
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            fo[j] = S.fx[j];
-            fo[nmax + j] = S.fy[j];
-            fo[2 * nmax + j] = S.fz[j];
-        }
-        if (threadIdx.x == 0) a.b.energy[r] = e;
-        return;
-    }
-
-    double *gpx = a.b.momenta + (size_t)r * 3 * nmax, *gpy = gpx + nmax, *gpz = gpy + nmax;
-    const double mass = a.b.mass, dt = a.dt;
-    const double temperature = a.b.temperature[r];
-    const double kT = temperature * KB;
-    const double pscale = sqrt(mass * kT);
-    const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
-    const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
-    double last_pot = a.b.energy[r];
-    int status = 0;
-
-    for (int k = 0; k < a.n_attempts; ++k) {
-        const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
-        double ke0p = 0.0;
-        for (int j = threadIdx.x; j < n; j += blockDim.x) {
-            const double p0 = hmc_normal(key, attempt, grep, 3u * j) * pscale;
-            const double p1 = hmc_normal(key, attempt, grep, 3u * j + 1u) * pscale;
-            const double p2 = hmc_normal(key, attempt, grep, 3u * j + 2u) * pscale;
-            S.px[j] = p0;
-            S.py[j] = p1;
-            S.pz[j] = p2;
-            ke0p += p0 * (p0 / mass) + p1 * (p1 / mass) + p2 * (p2 / mass);
-        }
-        const double last_kin = 0.5 * block_sum(ke0p, S.red);
-        double e_pot = hmc_energy_forces<POT>(pot, S, C, n);
-        for (int s = 0; s < a.n_steps; ++s) {
-            for (int j = threadIdx.x; j < n; j += blockDim.x) {
-                // new_momenta = p + 0.5 F dt; x += new_momenta / m * dt; p = (x_new - x) * m / dt
-                double nm, xo, xn;
-                nm = S.px[j] + __dmul_rn(__dmul_rn(0.5, S.fx[j]), dt); xo = S.x[j]; xn = xo + __dmul_rn(nm / mass, dt); S.x[j] = xn; S.px[j] = __dmul_rn(xn - xo, mass) / dt;
-                nm = S.py[j] + __dmul_rn(__dmul_rn(0.5, S.fy[j]), dt); xo = S.y[j]; xn = xo + __dmul_rn(nm / mass, dt); S.y[j] = xn; S.py[j] = __dmul_rn(xn - xo, mass) / dt;
-                nm = S.pz[j] + __dmul_rn(__dmul_rn(0.5, S.fz[j]), dt); xo = S.z[j]; xn = xo + __dmul_rn(nm / mass, dt); S.z[j] = xn; S.pz[j] = __dmul_rn(xn - xo, mass) / dt;
-            }
-            __syncthreads();
-            e_pot = hmc_energy_forces<POT>(pot, S, C, n);
-            for (int j = threadIdx.x; j < n; j += blockDim.x) {
-                S.px[j] = S.px[j] + __dmul_rn(__dmul_rn(0.5, S.fx[j]), dt);
-                S.py[j] = S.py[j] + __dmul_rn(__dmul_rn(0.5, S.fy[j]), dt);
-                S.pz[j] = S.pz[j] + __dmul_rn(__dmul_rn(0.5, S.fz[j]), dt);
-            }
-            __syncthreads();
-        }
-        double kep = 0.0;
-        for (int j = threadIdx.x; j < n; j += blockDim.x)
-            kep += S.px[j] * (S.px[j] / mass) + S.py[j] * (S.py[j] / mass) + S.pz[j] * (S.pz[j] / mass);
-        const double e_kin = 0.5 * block_sum(kep, S.red);
-        const double delta = (e_pot + e_kin) - last_pot - last_kin;
-        double u_accept, o2;
-        uniform_pair(key, attempt, grep, 2, o2, u_accept);
-        const double x = -delta / kT;
-        if (x > EXP_OVERFLOW) status |= QMC_STATUS_EXP_OVERFLOW;
-        const bool acc = u_accept < exp(x);
-        if (acc) {
-            for (int j = threadIdx.x; j < n; j += blockDim.x) {
-                gx[j] = S.x[j]; gy[j] = S.y[j]; gz[j] = S.z[j];
-                gpx[j] = S.px[j]; gpy[j] = S.py[j]; gpz[j] = S.pz[j];
-            }
-            last_pot = e_pot;
-            if (threadIdx.x == 0) a.b.kinetic[r] = e_kin;
-        } else {
-            for (int j = threadIdx.x; j < n; j += blockDim.x) {
-                S.x[j] = gx[j]; S.y[j] = gy[j]; S.z[j] = gz[j];
-            }
-            if (threadIdx.x == 0) a.b.kinetic[r] = last_kin;
+    const double *x = a.w.x[a.cur] + (size_t)r * 3 * nmax, *y = x + nmax, *z = y + nmax;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool own = i < n;
+    const double xi = own ? x[i] : 0.0, yi = own ? y[i] : 0.0, zi = own ? z[i] : 0.0;
+    unsigned *list = a.w.list + (size_t)r * a.w.max_nb * nmax;
+    int k = 0, overflow = 0;
+    for (int j0 = 0; j0 < n; j0 += HMC_THREADS) {
+        __syncthreads();
+        const int jl = j0 + threadIdx.x;
+        if (jl < n) {
+            sx[threadIdx.x] = x[jl];
+            sy[threadIdx.x] = y[jl];
+            sz[threadIdx.x] = z[jl];
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(a.b.counters) + (size_t)r * QMC_MAX_MOVES * 3;
-            cnt[0] += 1;
-            if (acc) cnt[1] += 1;
-            const size_t ti = (size_t)r * a.n_attempts + k;
-            if (a.tr.move) a.tr.move[ti] = 0;
-            if (a.tr.accepted) a.tr.accepted[ti] = acc ? 1 : 0;
-            if (a.tr.energy) a.tr.energy[ti] = last_pot;
-            if (a.tr.delta) a.tr.delta[ti] = delta;
-            if (a.tr.moved) a.tr.moved[ti] = -1;
+        if (!own) continue;
+        const int jn = min(HMC_THREADS, n - j0);
+        for (int t = 0; t < jn; ++t) {
+            const int j = j0 + t;
+            if (j == i) continue;
+            double d0[3], d1[3], k0[3];
+            unsigned avail = 0;
+            const double pj[3] = {sx[t], sy[t], sz[t]}, pi[3] = {xi, yi, zi};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (C.per[c]) {
+                    const double q = (pi[c] - pj[c]) * C.invL[c];
+                    k0[c] = (q + RINT_MAGIC) - RINT_MAGIC;
+                    d0[c] = fma(k0[c], C.L[c], pj[c]) - pi[c];
+                    d1[c] = d0[c] - copysign(C.L[c], d0[c]);
+                    if (fabs(d0[c]) > C.thr[c]) avail |= 1u << c;
+                } else {
+                    k0[c] = 0.0;
+                    d0[c] = d1[c] = pj[c] - pi[c];
+                }
+            }
+            unsigned c = 0;
+            while (true) {
+                const double dx = (c & 1u) ? d1[0] : d0[0], dy = (c & 2u) ? d1[1] : d0[1], dz = (c & 4u) ? d1[2] : d0[2];
+                if (dx * dx + dy * dy + dz * dz < rl2) {
+                    // integer image shift per axis: nearest image k0, second image k0 -+ 1
+                    int sh[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) sh[q] = (int)k0[q] - (((c >> q) & 1u) ? (d0[q] > 0.0 ? 1 : -1) : 0);
+                    if (abs(sh[0]) > 15 || abs(sh[1]) > 15 || abs(sh[2]) > 15 || k >= a.w.max_nb) {
+                        overflow = 1;
+                    } else {
+                        list[(size_t)k * nmax + i] = (unsigned)j | ((unsigned)(sh[0] + 16) << 16) | ((unsigned)(sh[1] + 16) << 21) | ((unsigned)(sh[2] + 16) << 26);
+                        ++k;
+                    }
+                }
+                if (c == avail) break;
+                c = ((c | (~avail & 7u)) + 1u) & avail;
+            }
         }
     }
-    if (threadIdx.x == 0) {
-        a.b.energy[r] = last_pot;
+    if (own) {
+        a.w.nnb[(size_t)r * nmax + i] = k;
+        double *ref = a.w.ref + (size_t)r * 3 * nmax;
+        ref[i] = xi;
+        ref[nmax + i] = yi;
+        ref[2 * nmax + i] = zi;
+        if (overflow) atomicOr(a.b.status + r, (int)QMC_STATUS_LIST_OVERFLOW);
+    }
+}
+
+// the build kernels of all CTAs must have seen the flag before it is cleared: separate tiny kernel
+__global__ void hmc_clear_flags_kernel(int *flags, int n) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) flags[r] = 0;
+}
+
+// image vector of list entry e for atom i
+__device__ __forceinline__ void entry_vector(unsigned e, const double *x, const double *y, const double *z, const CellDev &C, double xi,
+                                             double yi, double zi, int &j, double &dx, double &dy, double &dz) {
+    j = (int)(e & 0xFFFFu);
+    const int sx = (int)((e >> 16) & 31u) - 16, sy = (int)((e >> 21) & 31u) - 16, sz = (int)((e >> 26) & 31u) - 16;
+    dx = fma((double)sx, C.L[0], x[j]) - xi;
+    dy = fma((double)sy, C.L[1], y[j]) - yi;
+    dz = fma((double)sz, C.L[2], z[j]) - zi;
+}
+
+// ---- pass 1: sigma_1, energies, dE/dsigma_1 ----------------------------------------------------------------------
+template <int POT>
+__global__ void __launch_bounds__(HMC_THREADS) hmc_pass1_kernel(const __grid_constant__ HmcArgs a) {
+    __shared__ double red[32];
+    const int r = blockIdx.y, nmax = a.b.n_max, n = a.b.n_atoms[r];
+    const int lpa = a.lpa, sub = threadIdx.x & (lpa - 1);
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / lpa;
+    const bool own = i < n;
+    CellDev C;
+    hmc_cell(a, r, a.pot.cut_pre, C);
+    const double *x = a.w.x[a.cur] + (size_t)r * 3 * nmax, *y = x + nmax, *z = y + nmax;
+    const unsigned *list = a.w.list + (size_t)r * a.w.max_nb * nmax;
+    double s1 = 0.0, s2 = 0.0;
+    if (own) {
+        const double xi = x[i], yi = y[i], zi = z[i];
+        const int nn = a.w.nnb[(size_t)r * nmax + i];
+        for (int k = sub; k < nn; k += lpa) {
+            int j;
+            double dx, dy, dz;
+            entry_vector(list[(size_t)k * nmax + i], x, y, z, C, xi, yi, zi, j, dx, dy, dz);
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            if (r2 < a.pot.cut_pre2) {
+                if (POT == QMC_POT_EMT) {
+                    double t1, t2;
+                    emt_pair(a.pot, r2, t1, t2);
+                    s1 += t1;
+                    s2 += t2;
+                } else {
+                    s2 += lj_pair(a.pot, r2);
+                }
+            }
+        }
+    }
+    for (int o = lpa >> 1; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(FULL, s1, o);
+        s2 += __shfl_xor_sync(FULL, s2, o);
+    }
+    double e = 0.0;
+    if (own && sub == 0) {
+        if (POT == QMC_POT_EMT) {
+            double de;
+            const double ea = emt_embed_deds(a.pot, s1, de);
+            a.w.deds[(size_t)r * nmax + i] = de;
+            e = ea + a.pot.neghalfv0overgamma2 * s2;
+        } else {
+            e = 0.5 * s2;
+        }
+    }
+    const double s = block_sum(e, red);
+    if (threadIdx.x == 0) a.w.partial[((size_t)r * a.w.nb_blocks + blockIdx.x) * 2] = s;
+}
+
+// ---- pass 2: forces + velocity-Verlet update --------------------------------------------------------------------
+template <int POT>
+__global__ void __launch_bounds__(HMC_THREADS) hmc_pass2_kernel(const __grid_constant__ HmcArgs a) {
+    __shared__ double red[32];
+    const int r = blockIdx.y, nmax = a.b.n_max, n = a.b.n_atoms[r];
+    const int lpa = a.lpa, sub = threadIdx.x & (lpa - 1);
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / lpa;
+    const bool own = i < n;
+    CellDev C;
+    hmc_cell(a, r, a.pot.cut_pre, C);
+    const size_t base = (size_t)r * 3 * nmax;
+    const double *x = a.w.x[a.cur] + base, *y = x + nmax, *z = y + nmax;
+    const unsigned *list = a.w.list + (size_t)r * a.w.max_nb * nmax;
+    const double *deds = a.w.deds + (size_t)r * nmax;
+    double f0 = 0.0, f1 = 0.0, f2 = 0.0, xi = 0.0, yi = 0.0, zi = 0.0;
+    if (own) {
+        xi = x[i]; yi = y[i]; zi = z[i];
+        const double da = POT == QMC_POT_EMT ? deds[i] : 0.0;
+        const int nn = a.w.nnb[(size_t)r * nmax + i];
+        for (int k = sub; k < nn; k += lpa) {
+            int j;
+            double dx, dy, dz;
+            entry_vector(list[(size_t)k * nmax + i], x, y, z, C, xi, yi, zi, j, dx, dy, dz);
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            if (r2 < a.pot.cut_pre2) {
+                double g = 0.0;
+                if (POT == QMC_POT_EMT) {
+                    const double rr = sqrt_fast(fmax(r2, 1e-200));
+                    if (rr < a.pot.rc_list) {
+                        const double w = rcp_fast(1.0 + exp_fast(fma(a.pot.acut, rr, a.pot.theta_c)));
+                        const double dwdroverw = a.pot.acut * (w - 1.0);
+                        const double ds1 = exp_fast(fma(a.pot.sig1_a, rr, a.pot.sig1_c)) * w;
+                        const double ds2 = exp_fast(fma(a.pot.sig2_a, rr, a.pot.sig2_c)) * w;
+                        const double es = a.pot.neghalfv0overgamma2 * ds2;
+                        const double dedr_pair = es * (dwdroverw - a.pot.kappa_over_beta);
+                        const double dds1dr = ds1 * (dwdroverw - a.pot.eta2);
+                        g = ((dedr_pair + dedr_pair) + (da * dds1dr + deds[j] * dds1dr)) * rcp_fast(rr);
+                    }
+                } else if (!(r2 > a.pot.lj_rc2)) {
+                    const double q = a.pot.sigma2 * rcp_fast(r2);
+                    const double c6 = q * q * q;
+                    g = -6.0 * a.pot.eps4 * (2.0 * c6 * c6 - c6) * rcp_fast(r2);  // -24 eps (2 c12 - c6) / r2
+                }
+                f0 = fma(g, dx, f0);
+                f1 = fma(g, dy, f1);
+                f2 = fma(g, dz, f2);
+            }
+        }
+    }
+    for (int o = lpa >> 1; o > 0; o >>= 1) {
+        f0 += __shfl_xor_sync(FULL, f0, o);
+        f1 += __shfl_xor_sync(FULL, f1, o);
+        f2 += __shfl_xor_sync(FULL, f2, o);
+    }
+    double ke = 0.0;
+    if (own && sub == 0) {
+        const double f[3] = {f0, f1, f2}, xo[3] = {xi, yi, zi};
+        if (a.mode == 3) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) a.forces_out[base + (size_t)c * nmax + i] = f[c];
+        } else {
+            const double mass = a.b.mass, dt = a.dt;
+            double *xn = a.w.x[a.cur ^ 1] + base;
+            const double *ref = a.w.ref + base;
+            double dsq = 0.0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double p = a.w.p[base + (size_t)c * nmax + i];
+                const double half_kick = __dmul_rn(__dmul_rn(0.5, f[c]), dt);
+                if (a.mode == 1 || a.mode == 2) p = p + half_kick;  // complete the previous step: p = p_half + 0.5 F dt
+                if (a.mode == 0 || a.mode == 1) {                   // start the next one
+                    const double nm = p + half_kick;
+                    const double xnew = xo[c] + __dmul_rn(nm / mass, dt);
+                    xn[(size_t)c * nmax + i] = xnew;
+                    p = __dmul_rn(xnew - xo[c], mass) / dt;  // apply_constraints=True re-derivation (:74-75)
+                    const double dd = xnew - ref[(size_t)c * nmax + i];
+                    dsq = fma(dd, dd, dsq);
+                } else {
+                    ke += p * (p / mass);
+                }
+                a.w.p[base + (size_t)c * nmax + i] = p;
+            }
+            if (dsq > 0.25 * HMC_SKIN * HMC_SKIN) a.w.flags[r] = 1;
+        }
+    }
+    if (a.mode == 2 || a.mode == 4) {
+        const double s = block_sum(ke, red);
+        if (threadIdx.x == 0) a.w.partial[((size_t)r * a.w.nb_blocks + blockIdx.x) * 2 + 1] = s;
+    }
+}
+
+// ---- finish: fixed-order reductions, acceptance, commit ------------------------------------------------------------
+__global__ void __launch_bounds__(HMC_THREADS) hmc_finish_kernel(const __grid_constant__ HmcArgs a, int nb1, int nb2) {
+    const int r = blockIdx.y, nmax = a.b.n_max, n = a.b.n_atoms[r];
+    // every CTA of the replica recomputes the same decision from the same partials in the same order
+    double e_pot = 0.0, ke = 0.0, ke0 = 0.0;
+    for (int b = 0; b < nb2; ++b) {
+        e_pot += a.w.partial[((size_t)r * a.w.nb_blocks + b) * 2];
+        ke += a.w.partial[((size_t)r * a.w.nb_blocks + b) * 2 + 1];
+    }
+    for (int b = 0; b < nb1; ++b) ke0 += a.w.ke0[(size_t)r * a.w.nb_blocks + b];
+    const double e_kin = 0.5 * ke, last_kin = 0.5 * ke0;
+    const double last_pot = a.b.energy[r];
+    const double delta = (e_pot + e_kin) - last_pot - last_kin;
+    const double kT = a.b.temperature[r] * KB;
+    const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
+    const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+    double o2, u_accept;
+    uniform_pair(key, a.attempt, grep, 2, o2, u_accept);
+    int status = 0;
+    const bool acc = metropolis(u_accept, -delta / kT, status);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t base = (size_t)r * 3 * nmax;
+    __syncthreads();
+    if (acc && i < n) {
+        const double *xf = a.w.x[a.cur] + base;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            a.b.pos[base + (size_t)c * nmax + i] = xf[(size_t)c * nmax + i];
+            a.b.momenta[base + (size_t)c * nmax + i] = a.w.p[base + (size_t)c * nmax + i];
+        }
+    }
+    // energy[r] / kinetic[r] are still being read by the other CTAs of this replica: results go to a mailbox, published by
+    // hmc_publish_kernel afterwards
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double *out = a.w.result + (size_t)r * 2;
+        out[0] = acc ? e_pot : last_pot;
+        out[1] = acc ? e_kin : last_kin;
+        unsigned long long *cnt = reinterpret_cast<unsigned long long *>(a.b.counters) + (size_t)r * QMC_MAX_MOVES * 3;
+        cnt[0] += 1;
+        if (acc) cnt[1] += 1;
         if (status) atomicOr(a.b.status + r, status);
+        const size_t ti = (size_t)r * a.n_attempts + a.trace_index;
+        if (a.tr.move) a.tr.move[ti] = 0;
+        if (a.tr.accepted) a.tr.accepted[ti] = acc ? 1 : 0;
+        if (a.tr.energy) a.tr.energy[ti] = acc ? e_pot : last_pot;
+        if (a.tr.delta) a.tr.delta[ti] = delta;
+        if (a.tr.moved) a.tr.moved[ti] = -1;
     }
 }
 
-inline int64_t hmc_workspace_bytes(const qmc_batch_t &b) {
-    (void)b;
-    return 256;  // the one-CTA-per-replica trajectory kernel keeps everything in shared memory
+__global__ void hmc_publish_kernel(const __grid_constant__ HmcArgs a) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.b.n_replicas) return;
+    const double *out = a.w.result + (size_t)r * 2;
+    a.b.energy[r] = out[0];
+    a.b.kinetic[r] = out[1];
 }
 
-template <bool FORCES_ONLY>
-inline int hmc_launch(const HmcArgs &a, cudaStream_t s, char *err, size_t errn) {
-    const size_t smem = (size_t)hmc_smem_bytes(a.b.n_max);
-    cudaError_t e;
-    int dev = 0, smem_blk = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&smem_blk, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if ((int64_t)smem > smem_blk) {
-        snprintf(err, errn, "Hamiltonian replica of %d atoms needs %zu B of shared memory (> %d B per CTA)", a.b.n_max, smem, smem_blk);
-        return QMC_ERR_UNSUPPORTED;
-    }
+__global__ void hmc_energy_publish_kernel(const __grid_constant__ HmcArgs a, int nb2) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.b.n_replicas) return;
+    double e = 0.0;
+    for (int b = 0; b < nb2; ++b) e += a.w.partial[((size_t)r * a.w.nb_blocks + b) * 2];
+    a.b.energy[r] = e;
+}
+
+// ---- host side ---------------------------------------------------------------------------------------------------
+inline int hmc_pick_lpa(const qmc_batch_t &b) {
+    const long long atoms = (long long)b.n_replicas * b.n_max;
+    int lpa = 1;
+    while (lpa < 32 && atoms * lpa < 148LL * 1024) lpa <<= 1;
+    return lpa;
+}
+
+inline int hmc_check(cudaError_t e, const char *what, char *err, size_t errn) {
+    if (e == cudaSuccess) return QMC_OK;
+    snprintf(err, errn, "%s failed: %s", what, cudaGetErrorString(e));
+    return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? QMC_ERR_NO_DEVICE : QMC_ERR_CUDA;
+}
+
+// one force evaluation at the positions in buffer a.cur: (build) + pass 1 + pass 2
+inline void hmc_force_eval(HmcArgs &a, cudaStream_t s) {
+    const int N = a.b.n_max, R = a.b.n_replicas;
+    const dim3 g1((N + HMC_THREADS - 1) / HMC_THREADS, R), gl((N * a.lpa + HMC_THREADS - 1) / HMC_THREADS, R);
+    hmc_build_kernel<<<g1, HMC_THREADS, 0, s>>>(a);
+    hmc_clear_flags_kernel<<<(R + 127) / 128, 128, 0, s>>>(a.w.flags, R);
     if (a.pot.kind == QMC_POT_EMT) {
-        e = cudaFuncSetAttribute(hmc_kernel<QMC_POT_EMT, FORCES_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) hmc_kernel<QMC_POT_EMT, FORCES_ONLY><<<a.b.n_replicas, HMC_THREADS, smem, s>>>(a);
+        hmc_pass1_kernel<QMC_POT_EMT><<<gl, HMC_THREADS, 0, s>>>(a);
+        hmc_pass2_kernel<QMC_POT_EMT><<<gl, HMC_THREADS, 0, s>>>(a);
     } else {
-        e = cudaFuncSetAttribute(hmc_kernel<QMC_POT_LJ, FORCES_ONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) hmc_kernel<QMC_POT_LJ, FORCES_ONLY><<<a.b.n_replicas, HMC_THREADS, smem, s>>>(a);
+        hmc_pass1_kernel<QMC_POT_LJ><<<gl, HMC_THREADS, 0, s>>>(a);
+        hmc_pass2_kernel<QMC_POT_LJ><<<gl, HMC_THREADS, 0, s>>>(a);
     }
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        snprintf(err, errn, "hmc launch failed: %s", cudaGetErrorString(e));
-        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? QMC_ERR_NO_DEVICE : QMC_ERR_CUDA;
-    }
-    return QMC_OK;
 }
 
-inline int hmc_forces(const PotDev &pot, const qmc_batch_t &b, double *forces, cudaStream_t s, char *err, size_t errn) {
+inline int64_t hmc_workspace_bytes(const PotDev &pot, const qmc_batch_t &b) { return hmc_carve(pot, b, nullptr, nullptr); }
+
+inline int hmc_forces(const PotDev &pot, const qmc_batch_t &b, double *forces, void *workspace, cudaStream_t s, char *err, size_t errn) {
     HmcArgs a;
     memset(&a, 0, sizeof(a));
     a.pot = pot;
     a.b = b;
+    hmc_carve(pot, b, workspace, &a.w);
     a.forces_out = forces;
-    a.ns = round_up(b.n_max, 4);
-    return hmc_launch<true>(a, s, err, errn);
+    a.lpa = hmc_pick_lpa(b);
+    a.cur = 0;
+    a.mode = 3;
+    const int N = b.n_max, R = b.n_replicas;
+    int rc = hmc_check(cudaMemcpyAsync(a.w.x[0], b.pos, (size_t)R * 3 * N * 8, cudaMemcpyDeviceToDevice, s), "position copy", err, errn);
+    if (rc) return rc;
+    if ((rc = hmc_check(cudaMemsetAsync(a.w.flags, 1, (size_t)R * 4, s), "flag reset", err, errn))) return rc;
+    hmc_force_eval(a, s);
+    const int nb2 = (N * a.lpa + HMC_THREADS - 1) / HMC_THREADS;
+    hmc_energy_publish_kernel<<<(R + 127) / 128, 128, 0, s>>>(a, nb2);
+    return hmc_check(cudaGetLastError(), "force kernels", err, errn);
 }
 
 inline int hmc_run(const PotDev &pot, const qmc_batch_t &b, double dt, int n_steps, unsigned long long seed,
                    unsigned long long attempt_base, int n_attempts, const qmc_trace_t &tr, void *workspace, cudaStream_t s, char *err,
                    size_t errn) {
-    (void)workspace;
     HmcArgs a;
     memset(&a, 0, sizeof(a));
     a.pot = pot;
     a.b = b;
+    hmc_carve(pot, b, workspace, &a.w);
     a.dt = dt;
     a.n_steps = n_steps;
     a.seed = seed;
-    a.attempt_base = attempt_base;
-    a.n_attempts = n_attempts;
     a.tr = tr;
-    a.ns = round_up(b.n_max, 4);
-    return hmc_launch<false>(a, s, err, errn);
+    a.n_attempts = n_attempts;
+    a.lpa = hmc_pick_lpa(b);
+    const int N = b.n_max, R = b.n_replicas;
+    const int nb1 = (N + HMC_THREADS - 1) / HMC_THREADS, nb2 = (N * a.lpa + HMC_THREADS - 1) / HMC_THREADS;
+    const dim3 g1(nb1, R);
+    for (int k = 0; k < n_attempts; ++k) {
+        a.attempt = attempt_base + (unsigned long long)k;
+        a.trace_index = k;
+        a.cur = 0;
+        hmc_init_kernel<<<g1, HMC_THREADS, 0, s>>>(a);
+        for (int step = 0; step <= n_steps; ++step) {
+            a.mode = n_steps == 0 ? 4 : (step == 0 ? 0 : (step == n_steps ? 2 : 1));
+            hmc_force_eval(a, s);
+            if (a.mode == 0 || a.mode == 1) a.cur ^= 1;
+        }
+        hmc_finish_kernel<<<g1, HMC_THREADS, 0, s>>>(a, nb1, nb2);
+        hmc_publish_kernel<<<(R + 127) / 128, 128, 0, s>>>(a);
+        int rc = hmc_check(cudaGetLastError(), "trajectory kernels", err, errn);
+        if (rc) return rc;
+    }
+    return QMC_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -408,12 +591,7 @@ inline int pt_swap(double *temps, const double *energies, int n, unsigned long l
     }
     const int threads = (n + 31) / 32 * 32;
     pt_swap_kernel<<<1, threads, n * sizeof(int), s>>>(temps, energies, n, seed, round, accepted);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        snprintf(err, errn, "pt_swap launch failed: %s", cudaGetErrorString(e));
-        return e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver ? QMC_ERR_NO_DEVICE : QMC_ERR_CUDA;
-    }
-    return QMC_OK;
+    return hmc_check(cudaGetLastError(), "pt_swap launch", err, errn);
 }
 
 }  // namespace qmc

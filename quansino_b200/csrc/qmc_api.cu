@@ -256,19 +256,24 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     return inst->sweep(feat, a, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 
-int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double *forces, void *stream) {
+int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double *forces, void *workspace, int64_t workspace_bytes,
+                    void *stream) {
     if (!pot || !forces) return fail(QMC_ERR_INVALID, "potential / forces is NULL");
     int rc;
     if ((rc = check_batch(batch, pot->kind))) return rc;
     if (batch->n_replicas == 0) return QMC_OK;
     qmc::PotDev pd;
     if ((rc = make_potdev(pot, pd))) return rc;
-    return qmc::hmc_forces(pd, *batch, forces, (cudaStream_t)stream, g_err, sizeof(g_err));
+    if (!workspace || workspace_bytes < qmc::hmc_workspace_bytes(pd, *batch)) return fail(QMC_ERR_INVALID, "workspace too small");
+    return qmc::hmc_forces(pd, *batch, forces, workspace, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 
-int64_t qmc_hmc_workspace_bytes(const qmc_batch_t *batch) {
-    if (!batch) return fail(QMC_ERR_INVALID, "batch is NULL");
-    return qmc::hmc_workspace_bytes(*batch);
+int64_t qmc_hmc_workspace_bytes(const qmc_potential_t *pot, const qmc_batch_t *batch) {
+    if (!batch || !pot) return fail(QMC_ERR_INVALID, "potential / batch is NULL");
+    qmc::PotDev pd;
+    int rc;
+    if ((rc = make_potdev(pot, pd))) return rc;
+    return qmc::hmc_workspace_bytes(pd, *batch);
 }
 
 int qmc_hmc(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move_t *move, uint64_t seed, uint64_t attempt_base,
@@ -279,10 +284,11 @@ int qmc_hmc(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move
     if (move->type != QMC_MOVE_HMC || move->op != QMC_OP_VERLET)
         return fail(QMC_ERR_UNSUPPORTED, "qmc_hmc runs HamiltonianDisplacementMove + Verlet only");
     if (!batch->momenta || !batch->kinetic) return fail(QMC_ERR_INVALID, "Hamiltonian moves need batch.momenta and batch.kinetic");
-    if (workspace_bytes < qmc::hmc_workspace_bytes(*batch) || !workspace) return fail(QMC_ERR_INVALID, "workspace too small");
-    if (batch->n_replicas == 0 || n_attempts <= 0) return QMC_OK;
+    if (move->n_steps < 0) return fail(QMC_ERR_INVALID, "negative number of Verlet steps");
     qmc::PotDev pd;
     if ((rc = make_potdev(pot, pd))) return rc;
+    if (workspace_bytes < qmc::hmc_workspace_bytes(pd, *batch) || !workspace) return fail(QMC_ERR_INVALID, "workspace too small");
+    if (batch->n_replicas == 0 || n_attempts <= 0) return QMC_OK;
     qmc_trace_t tr;
     std::memset(&tr, 0, sizeof(tr));
     if (trace) tr = *trace;

@@ -219,14 +219,6 @@ __device__ __forceinline__ Draws draw_attempt(PhiloxKey key, unsigned long long 
     return D;
 }
 
-// u < exp(x) without evaluating exp where the answer is already decided; flags the reference's OverflowError
-__device__ __forceinline__ bool metropolis(double u, double x, int &status) {
-    if (x > EXP_OVERFLOW) status |= QMC_STATUS_EXP_OVERFLOW;
-    if (x >= 0.0) return true;  // exp(x) >= 1 > u
-    if (!(x > -700.0)) return false;  // exp(x) < 1e-304: below every u > 0 (u == 0 has probability 2^-53; DESIGN.md ties)
-    return u < exp_fast(x);
-}
-
 // per-replica cell constants in shared memory (F_CELLVAR); returns false if an edge is below the cutoff
 template <class LY>
 __device__ __forceinline__ bool store_cell(const Rep<LY> &R, const double diag[3], const int pbc[3], double cut_pre, int lane) {

@@ -268,12 +268,10 @@ class MonteCarlo:
             if moves[0].type == _lib.MOVE_HMC:
                 if len(names) != 1:
                     raise NotImplementedError("Hamiltonian moves cannot be mixed with other moves in one step on the GPU path")
-                ws_bytes = int(b.lib.qmc_hmc_workspace_bytes(C.byref(bs)))
-                if getattr(self, "_hmc_ws", None) is None or self._hmc_ws.numel() < ws_bytes:
-                    self._hmc_ws = torch.zeros(max(ws_bytes, 8), dtype=torch.uint8, device=b.device)
+                ws = b.hmc_workspace(bs)
                 rc = b.lib.qmc_hmc(
                     C.byref(b.potential), C.byref(bs), C.byref(moves[0]), self._seed, self.attempt_counter, n_attempts,
-                    C.byref(tr) if tr is not None else None, self._hmc_ws.data_ptr(), self._hmc_ws.numel(), b.stream(),
+                    C.byref(tr) if tr is not None else None, ws.data_ptr(), ws.numel(), b.stream(),
                 )  # fmt: skip
             else:
                 rc = b.lib.qmc_sweep(
