@@ -5,7 +5,7 @@
 
 #include <cuda_runtime.h>
 
-#include "sweep_kernel.cuh"
+#include "sweep_block.cuh"
 
 namespace qmc {
 
@@ -16,7 +16,8 @@ typedef int (*energy_launch_fn)(const SweepArgs &a, long long *pair_count, cudaS
 
 #define QMC_DECLARE_INST(POT, NS)                                                                           \
     int sweep_launch_##POT##_##NS(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn);     \
-    int energy_launch_##POT##_##NS(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn);
+    int energy_launch_##POT##_##NS(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn); \
+    int sweep_block_launch_##POT##_##NS(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn);
 
 QMC_FOR_EACH_NS(QMC_DECLARE_INST, 0)
 QMC_FOR_EACH_NS(QMC_DECLARE_INST, 1)

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -89,9 +90,12 @@ struct Inst {
     int ns;
     qmc::sweep_launch_fn sweep;
     qmc::energy_launch_fn energy;
+    qmc::sweep_launch_fn sweep_block;
+    int block_minb;  // CTAs (= replicas) of the block kernel one SM holds
 };
 
-#define QMC_TABLE_ROW(POT, NS) {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS},
+#define QMC_TABLE_ROW(POT, NS) \
+    {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS, qmc::sweep_block_launch_##POT##_##NS, qmc::LayoutB<POT, NS>::MINB},
 const Inst g_inst[2][7] = {{QMC_FOR_EACH_NS(QMC_TABLE_ROW, 0)}, {QMC_FOR_EACH_NS(QMC_TABLE_ROW, 1)}};
 
 const Inst *find_inst(int kind, int n_max) {
@@ -253,7 +257,12 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     if ((rc = fill_cell_args(batch, a.pot, a))) return rc;
     const Inst *inst = find_inst(pot->kind, batch->n_max);
     if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica sweep kernel");
-    return inst->sweep(feat, a, (cudaStream_t)stream, g_err, sizeof(g_err));
+    // one warp per replica fills the GPU only with thousands of replicas; smaller batches run CTA-per-replica
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    bool block = batch->n_replicas <= 2 * sms * inst->block_minb;
+    if (const char *force = std::getenv("QMC_FORCE_KERNEL")) block = std::strcmp(force, "block") == 0;
+    return (block ? inst->sweep_block : inst->sweep)(feat, a, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 
 int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double *forces, void *workspace, int64_t workspace_bytes,

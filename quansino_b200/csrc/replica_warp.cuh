@@ -74,6 +74,10 @@ struct Layout {
 // Per-warp view of the replica: base pointer + runtime atom count.  Arrays are reached through the layout constants.
 template <class LY>
 struct Rep {
+    static constexpr bool EMT = LY::EMT;
+    static constexpr int CAPE = LY::CAPE;
+    static constexpr int XCAPN = XCAP;
+    static constexpr int QCAP = 2 * (LY::CAPL - LY::CAPE);  // work items the tail can hold
     double *b;  // warp base in shared memory
     int n;      // atoms
     __device__ __forceinline__ double &x(int j) const { return b[LY::X + j]; }
@@ -156,18 +160,18 @@ struct DeltaAcc {
 // scan: fills the list.  MODE 0 = local delta (pp, l2, xj maintained for EMT), MODE 1 = one row of a full evaluation.
 // Returns the number of list entries; n2 = entries of l2; xstart = first second-image entry.
 // ---------------------------------------------------------------------------------------------------
-template <class LY, int MODE, class CELL>
-__device__ __forceinline__ int scan_neighbours(const PotDev &pot, const Rep<LY> &R, const CELL &C, const int lane, const unsigned lt,
+template <class RV, int MODE, class CELL>
+__device__ __forceinline__ int scan_neighbours(const PotDev &pot, const RV &R, const CELL &C, const int lane, const unsigned lt,
                                                int n_scan, int i_excl, bool has_old, bool has_new, const double po[3],
-                                               const double pn[3], int &n2, int &xstart, int &status) {
-    constexpr bool TRACK = (MODE == 0 && LY::EMT);
+                                               const double pn[3], int &n2, int &xstart, int &status, int tile_first = 0,
+                                               int tile_step = 1) {
+    constexpr bool TRACK = (MODE == 0 && RV::EMT);
     uint32_t *queue = R.queue();  // 2 * NS work items fit in the tail (NS doubles)
     const bool p0 = C.per(0), p1 = C.per(1), p2 = C.per(2);
     const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);
     int cnt = 0, nq = 0;
     n2 = 0;
-#pragma unroll kScanUnroll
-    for (int base = 0; base < n_scan; base += 32) {
+    for (int base = tile_first * 32; base < n_scan; base += 32 * tile_step) {
         const int j = base + lane;
         const bool valid = j < n_scan && j != i_excl;
         const int jc = valid ? j : 0;
@@ -185,7 +189,7 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const Rep<LY> 
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
             const bool in = valid && r2 < pot.cut_pre2;
             const unsigned b = __ballot_sync(FULL, in);
-            const int pos = min(cnt + __popc(b & lt), LY::CAPE - 1);
+            const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
             if (in) R.lr(pos) = side ? r2 : -r2;
             if (in) code = side ? ((code & 0xFFFFu) | ((unsigned)pos << 16)) : ((code & 0xFFFF0000u) | (unsigned)pos);
             cnt += __popc(b);
@@ -193,7 +197,7 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const Rep<LY> 
             // second images: only if the nearest image is inside (it is the closest of all images)
             const bool ex = in && fl != 0u;
             const unsigned bq = __ballot_sync(FULL, ex);
-            if (ex) queue[nq + __popc(bq & lt)] = (unsigned)j | ((unsigned)side << 15) | (fl << 16);
+            if (ex) queue[min(nq + __popc(bq & lt), RV::QCAP - 1)] = (unsigned)j | ((unsigned)side << 15) | (fl << 16);
             nq += __popc(bq);
         }
         if (TRACK) {
@@ -204,6 +208,10 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const Rep<LY> 
         }
     }
     xstart = cnt;
+    if (nq > RV::QCAP) {
+        status |= QMC_STATUS_LIST_OVERFLOW;
+        nq = RV::QCAP;
+    }
     // second images, appended after every nearest image
     if (nq > 0) {
         __syncwarp();
@@ -226,10 +234,10 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const Rep<LY> 
                 const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
                 const bool in = more && r2 < pot.cut_pre2;
                 const unsigned b = __ballot_sync(FULL, in);
-                const int pos = min(cnt + __popc(b & lt), LY::CAPE - 1);
+                const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
                 if (in) {
                     R.lr(pos) = side ? r2 : -r2;
-                    if (TRACK) R.xj(min(pos - xstart, XCAP - 1)) = (uint16_t)j;
+                    if (TRACK) R.xj(min(pos - xstart, RV::XCAPN - 1)) = (uint16_t)j;
                 }
                 cnt += __popc(b);
                 if (more) {
@@ -239,10 +247,10 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const Rep<LY> 
             }
         }
     }
-    if (cnt > LY::CAPE || (TRACK && cnt - xstart > XCAP)) {
+    if (cnt > RV::CAPE || (TRACK && cnt - xstart > RV::XCAPN)) {
         status |= QMC_STATUS_LIST_OVERFLOW;
-        cnt = min(cnt, LY::CAPE);
-        if (TRACK && cnt - xstart > XCAP) cnt = xstart + XCAP;
+        cnt = min(cnt, RV::CAPE);
+        if (TRACK && cnt - xstart > RV::XCAPN) cnt = xstart + RV::XCAPN;
     }
     __syncwarp();
     return cnt;
@@ -250,16 +258,16 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const Rep<LY> 
 
 // pairs: evaluate the list.  MODE 0 leaves the sigma_1 term of every nearest-image entry in lr[e], with the terms of
 // the second images of the same atom and side added onto it.
-template <class LY, int MODE>
-__device__ __forceinline__ void eval_pass(const PotDev &pot, const Rep<LY> &R, const int lane, int e0, int cnt, int xstart,
+template <class RV, int MODE>
+__device__ __forceinline__ void eval_pass(const PotDev &pot, const RV &R, const int lane, int e0, int cnt, int xstart,
                                           DeltaAcc &acc) {
-    constexpr bool TRACK = (MODE == 0 && LY::EMT);
+    constexpr bool TRACK = (MODE == 0 && RV::EMT);
     const int e = e0 + lane;
     const bool act = e < cnt;
     const double r2s = act ? R.lr(e) : 1.0;
     const bool isnew = r2s > 0.0;
     const double r2 = fabs(r2s);
-    if (LY::EMT) {
+    if (RV::EMT) {
         double s1, s2;
         emt_pair(pot, r2, s1, s2);
         s1 = act ? s1 : 0.0;
@@ -301,18 +309,18 @@ __device__ __forceinline__ void eval_pass(const PotDev &pot, const Rep<LY> &R, c
     acc.pairs += act ? 1 : 0;
 }
 
-template <class LY, int MODE>
-__device__ __forceinline__ void eval_list(const PotDev &pot, const Rep<LY> &R, const int lane, int cnt, int xstart, DeltaAcc &acc) {
+template <class RV, int MODE>
+__device__ __forceinline__ void eval_list(const PotDev &pot, const RV &R, const int lane, int cnt, int xstart, DeltaAcc &acc) {
 #ifdef QMC_PAIR_UNROLL2
     // two independent passes per iteration: twice the instruction-level parallelism in the FP64 chains
     int e0 = 0;
     for (; e0 + 32 < cnt; e0 += 64) {
-        eval_pass<LY, MODE>(pot, R, lane, e0, cnt, xstart, acc);
-        eval_pass<LY, MODE>(pot, R, lane, e0 + 32, cnt, xstart, acc);
+        eval_pass<RV, MODE>(pot, R, lane, e0, cnt, xstart, acc);
+        eval_pass<RV, MODE>(pot, R, lane, e0 + 32, cnt, xstart, acc);
     }
-    if (e0 < cnt) eval_pass<LY, MODE>(pot, R, lane, e0, cnt, xstart, acc);
+    if (e0 < cnt) eval_pass<RV, MODE>(pot, R, lane, e0, cnt, xstart, acc);
 #else
-    for (int e0 = 0; e0 < cnt; e0 += 32) eval_pass<LY, MODE>(pot, R, lane, e0, cnt, xstart, acc);
+    for (int e0 = 0; e0 < cnt; e0 += 32) eval_pass<RV, MODE>(pot, R, lane, e0, cnt, xstart, acc);
 #endif
     __syncwarp();
 }
@@ -328,8 +336,8 @@ __device__ inline double replica_full_energy(const PotDev &pot, const Rep<LY> &R
         const double pa[3] = {R.x(a), R.y(a), R.z(a)};
         DeltaAcc acc = {0.0, 0.0, 0};
         int n2, xstart;
-        const int cnt = scan_neighbours<LY, 1>(pot, R, C, lane, lt, R.n, a, false, true, pa, pa, n2, xstart, status);
-        eval_list<LY, 1>(pot, R, lane, cnt, xstart, acc);
+        const int cnt = scan_neighbours<Rep<LY>, 1>(pot, R, C, lane, lt, R.n, a, false, true, pa, pa, n2, xstart, status);
+        eval_list<Rep<LY>, 1>(pot, R, lane, cnt, xstart, acc);
         pairs += acc.pairs;
         const double vs = warp_sum(acc.v);
         if (LY::EMT) {

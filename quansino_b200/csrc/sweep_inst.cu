@@ -40,6 +40,25 @@ int CAT(sweep_launch_, INST_POT, _, INST_NS)(int feat, const SweepArgs &a, cudaS
     return launch_feat<F_CELLVAR | F_CELL | F_LABELS | F_EXCHANGE>(a, s, err, errn);
 }
 
+template <int FEAT>
+static inline int launch_block_feat(const SweepArgs &a, cudaStream_t s, char *err, size_t errn) {
+    using LY = LayoutB<INST_POT, INST_NS>;
+    static_assert(LY::FITS, "replica does not fit in shared memory");
+    constexpr size_t smem = (size_t)LY::BYTES;
+    auto kernel = sweep_block_kernel<INST_POT, INST_NS, FEAT>;
+    int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
+    if (rc) return rc;
+    kernel<<<a.b.n_replicas, BW * 32, smem, s>>>(a);
+    return report(cudaGetLastError(), "sweep block kernel launch", err, errn);
+}
+
+// CTA-per-replica variant (csrc/sweep_block.cuh); instantiated feature sets: canonical, + per-replica cells + cell moves, everything
+int CAT(sweep_block_launch_, INST_POT, _, INST_NS)(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn) {
+    if (feat == 0) return launch_block_feat<0>(a, s, err, errn);
+    if ((feat & ~(F_CELLVAR | F_CELL)) == 0) return launch_block_feat<F_CELLVAR | F_CELL>(a, s, err, errn);
+    return launch_block_feat<F_CELLVAR | F_CELL | F_LABELS | F_EXCHANGE>(a, s, err, errn);
+}
+
 int CAT(energy_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn) {
     using LY = Layout<INST_POT, INST_NS>;
     constexpr size_t smem = (size_t)LY::WARPS * LY::BYTES;

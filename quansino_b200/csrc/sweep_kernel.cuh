@@ -119,8 +119,8 @@ struct Trial {
 
 // sigma_1 change of touched atom j, gathered from the list through pp[j] (terms of second images were added onto the
 // nearest-image slots by eval_list)
-template <class LY>
-__device__ __forceinline__ double gathered_dsigma(const Rep<LY> &R, int j) {
+template <class RV>
+__device__ __forceinline__ double gathered_dsigma(const RV &R, int j) {
     const unsigned code = R.pp(j);
     const unsigned po = code & 0xFFFFu, pn = code >> 16;
     const double so = po != NOPOS ? R.lr(po) : 0.0;
@@ -135,8 +135,8 @@ __device__ __forceinline__ Trial local_delta(const PotDev &pot, const Rep<LY> &R
     Trial T;
     DeltaAcc acc = {0.0, 0.0, 0};
     int xstart;
-    const int cnt = scan_neighbours<LY, 0>(pot, R, C, lane, lt, n_scan, has_old ? i : -1, has_old, has_new, po, pn, T.n2, xstart, status);
-    eval_list<LY, 0>(pot, R, lane, cnt, xstart, acc);
+    const int cnt = scan_neighbours<Rep<LY>, 0>(pot, R, C, lane, lt, n_scan, has_old ? i : -1, has_old, has_new, po, pn, T.n2, xstart, status);
+    eval_list<Rep<LY>, 0>(pot, R, lane, cnt, xstart, acc);
     const double vs = warp_sum(acc.v);
     T.pairs = acc.pairs;
     T.sig_i = 0.0;

@@ -18,3 +18,11 @@ def cuda_lib():
     from quansino_b200 import _lib
 
     return _lib.load()
+
+
+@pytest.fixture(params=["warp", "block"])
+def kernel_variant(request, monkeypatch):
+    """Run a sweep test through both organisations of the sweep kernel: one warp per replica (csrc/sweep_kernel.cuh)
+    and one CTA per replica (csrc/sweep_block.cuh).  Without the variable the library picks by batch size."""
+    monkeypatch.setenv("QMC_FORCE_KERNEL", request.param)
+    return request.param

@@ -8,7 +8,7 @@ import pytest
 from oracle import capi
 from tests.helpers import cu_replicas, oracle_par, oracle_run
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_variant")]
 
 RTOL_E = 1e-10
 

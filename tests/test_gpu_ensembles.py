@@ -10,7 +10,7 @@ from oracle import capi
 from oracle.potentials import LJParams, emt_params
 from tests.helpers import cu_replicas
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_variant")]
 
 BAR = 6.241509125883258e-07  # ase.units.bar
 

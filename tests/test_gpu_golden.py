@@ -5,7 +5,7 @@ import pytest
 
 from tests.golden_cases import CASES, gpu_replay, load
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_variant")]
 
 
 @pytest.mark.parametrize("name", CASES)
