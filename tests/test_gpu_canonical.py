@@ -156,3 +156,94 @@ def test_unsupported_requests_are_refused(cuda_lib):
     pos1, cell1 = fcc_cubic("Cu", 1)  # the reference's 4-atom fixture: cell shorter than the EMT cutoff
     with pytest.raises(NotImplementedError):
         Canonical(BatchedAtoms.replicate(pos1, cell1, 2, calc=EMT()), temperature=300.0)
+
+
+def test_ragged_batch_and_frozen_atoms(cuda_lib):
+    """Replicas with different atom counts (padded rows) and atoms excluded by negative labels, against the oracle."""
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+
+    R, n_max = 5, 108
+    pos, cell, n = cu_replicas(3, R, seed=23)
+    n_atoms = np.array([108, 107, 100, 108, 64], dtype=np.int32)  # vacancies: trailing atoms removed
+    labels = np.tile(np.arange(n_max), (R, 1))
+    labels[:, ::7] = -1  # every 7th atom is frozen
+    for r in range(R):
+        pos[r, n_atoms[r] :] = 0.0
+    atoms = BatchedAtoms(pos.copy(), cell, n_atoms, "Cu", (True, True, True), EMT())
+    mc = Canonical(atoms, temperature=600.0, seed=31, trace=True, max_cycles=150, resync_interval=0,
+                   default_displacement_move=DisplacementMove(labels, operations.Ball(0.15)))  # fmt: skip
+    mc.run(1)
+    tr = mc.last_trace
+    out = mc.download()
+    par = oracle_par(EMT())
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, n_atoms=int(n_atoms[r]), temperature=600.0)
+        lab = labels[r].astype(np.int32).copy()
+        lab[n_atoms[r] :] = -1
+        ref = capi.mc_run(par, rep, [capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.15, labels=lab)], 31, r, 0, 150)
+        assert np.array_equal(tr["accepted"][r], ref["accepted"])
+        assert np.array_equal(tr["moved"][r], ref["moved"])
+        assert not np.any(ref["moved"] % 7 == 0)  # frozen atoms never move
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=RTOL_E, atol=1e-12)
+        np.testing.assert_allclose(out.positions[r, : n_atoms[r]], rep.positions[: n_atoms[r]], rtol=0, atol=1e-12)
+    assert np.array_equal(out.n_atoms, n_atoms)
+
+
+def test_no_movable_atoms_means_failed_moves(cuda_lib):
+    """All labels negative: every attempt fails (the reference's None), nothing changes, failed counter counts."""
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+
+    pos, cell, n = cu_replicas(3, 2, seed=29)
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(2, n, np.int32), "Cu", (True, True, True), EMT())
+    mc = Canonical(atoms, temperature=300.0, seed=1, trace=True, max_cycles=20, resync_interval=0,
+                   default_displacement_move=DisplacementMove(np.full(n, -1), operations.Ball(0.1)))  # fmt: skip
+    e0 = mc.batch.energy_full().cpu().numpy().copy()
+    mc.run(1)
+    assert np.all(mc.last_trace["accepted"] == -1)
+    assert np.array_equal(mc.download().positions, pos)
+    assert np.array_equal(mc.counters()[:, 0], np.array([[20, 0, 20], [20, 0, 20]]))
+    assert np.array_equal(mc.batch.energy.cpu().numpy(), e0)
+    assert np.allclose(mc.update_acceptance_rate(), 0.0)
+
+
+def test_lennard_jones_periodic_canonical(cuda_lib):
+    """The pair potential on a periodic cell whose edge is below twice the cutoff (second images needed)."""
+    from quansino_b200 import BatchedAtoms, LennardJones, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+    from oracle.potentials import LJParams
+
+    R = 4
+    pos, cell, n = cu_replicas(3, R, seed=37)
+    calc = LennardJones(sigma=2.3, epsilon=0.2, rc=5.6)  # L = 10.83 < 2 * 5.6
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, np.int32), "Cu", (True, True, True), calc)
+    mc = Canonical(atoms, temperature=500.0, seed=41, trace=True, max_cycles=200, resync_interval=0,
+                   default_displacement_move=DisplacementMove(np.arange(n), operations.Box(0.12)))  # fmt: skip
+    mc.run(1)
+    tr = mc.last_trace
+    par = LJParams(sigma=2.3, epsilon=0.2, rc=5.6)
+    reps, otr = oracle_run(par, pos, np.full(R, n), cell, (1, 1, 1), [dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_BOX, step=0.12)], 41, 200,
+                           range(R), temperature=500.0, mass=63.546)  # fmt: skip
+    for r in range(R):
+        assert np.array_equal(tr["accepted"][r], otr[r]["accepted"])
+        np.testing.assert_allclose(tr["energy"][r], otr[r]["energy"], rtol=RTOL_E, atol=1e-11)
+
+
+def test_overflow_is_reported_like_the_reference(cuda_lib):
+    """A hugely favourable move makes exp(-dE/kT) overflow: the reference raises OverflowError (mc/criteria.py:108)."""
+    from quansino_b200 import BatchedAtoms, LennardJones, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+
+    pos = np.zeros((1, 2, 3))
+    pos[0, 1] = [0.9, 0.0, 0.0]  # two LJ atoms far up the repulsive wall: any move apart releases > 1e4 eV
+    cell = np.eye(3) * 40.0
+    atoms = BatchedAtoms(pos, cell, np.array([2], np.int32), "Cu", (False, False, False), LennardJones(sigma=2.5, epsilon=1.0))
+    mc = Canonical(atoms, temperature=1.0, seed=3, max_cycles=64, resync_interval=0,
+                   default_displacement_move=DisplacementMove(np.arange(2), operations.Ball(0.3)))  # fmt: skip
+    with pytest.raises(OverflowError):
+        mc.run(1)
