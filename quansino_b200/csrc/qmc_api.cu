@@ -260,7 +260,9 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     // one warp per replica fills the GPU only with thousands of replicas; smaller batches run CTA-per-replica
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    bool block = batch->n_replicas <= 2 * sms * inst->block_minb;
+    // (measured on B200: at 108 atoms a warp owns a single 32-atom tile and the block kernel loses, 1.5e8 vs 1.7e8 attempts/s at
+    // 1024 replicas; at 500 atoms it wins 1.9x -- profiles/r1_e_kernel_choice.md)
+    bool block = inst->ns >= 256 && batch->n_replicas <= 2 * sms * inst->block_minb;
     if (const char *force = std::getenv("QMC_FORCE_KERNEL")) block = std::strcmp(force, "block") == 0;
     return (block ? inst->sweep_block : inst->sweep)(feat, a, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
