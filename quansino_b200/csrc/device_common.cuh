@@ -86,12 +86,12 @@ struct PotDev {
 __device__ __forceinline__ void emt_pair(const PotDev &p, double r2, double &s1, double &s2) {
     const double r = sqrt_fast(fmax(r2, 1e-200));
     // the three exponents are linear in r: one FMA each (constants folded on the host)
-    const double w = rcp_fast(1.0 + exp_fast(fma(p.acut, r, p.theta_c)));
-    const double a = exp_fast(fma(p.sig1_a, r, p.sig1_c)) * w;
-    const double b = exp_fast(fma(p.sig2_a, r, p.sig2_c)) * w;
-    const bool in = r < p.rc_list;
-    s1 = in ? a : 0.0;
-    s2 = in ? b : 0.0;
+    double et, e1, e2;
+    exp3_fast(fma(p.acut, r, p.theta_c), fma(p.sig1_a, r, p.sig1_c), fma(p.sig2_a, r, p.sig2_c), et, e1, e2);
+    const double w = rcp_fast(1.0 + et);
+    const bool in = r < p.rc_list;  // also discards whatever a padding entry (r2 = 1e6) produced
+    s1 = in ? e1 * w : 0.0;
+    s2 = in ? e2 * w : 0.0;
 }
 
 // E_c + second term of E_AS - E0 for one atom given its sigma_1 (_calc_e_c_a2 and the final `energies -= E0`);

@@ -68,6 +68,29 @@ __device__ __forceinline__ double exp_fast(double x) {
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
 }
 
+// three exponentials in lockstep: one coefficient fetch per Horner step serves all three chains
+__device__ __forceinline__ void exp3_fast(double x0, double x1, double x2, double &e0, double &e1, double &e2) {
+    const double t0 = fma(x0, 1.4426950408889634, FM_MAGIC), t1 = fma(x1, 1.4426950408889634, FM_MAGIC),
+                 t2 = fma(x2, 1.4426950408889634, FM_MAGIC);
+    const double k0 = t0 - FM_MAGIC, k1 = t1 - FM_MAGIC, k2 = t2 - FM_MAGIC;
+    double r0 = fma(k0, -FM_LN2_HI, x0), r1 = fma(k1, -FM_LN2_HI, x1), r2 = fma(k2, -FM_LN2_HI, x2);
+    r0 = fma(k0, -FM_LN2_LO, r0);
+    r1 = fma(k1, -FM_LN2_LO, r1);
+    r2 = fma(k2, -FM_LN2_LO, r2);
+    double q0 = FM_EXP[9], q1 = FM_EXP[9], q2 = FM_EXP[9];
+#pragma unroll
+    for (int i = 8; i >= 0; --i) {
+        const double c = FM_EXP[i];
+        q0 = fma(q0, r0, c);
+        q1 = fma(q1, r1, c);
+        q2 = fma(q2, r2, c);
+    }
+    const double p0 = fma(r0 * r0, q0, r0) + 1.0, p1 = fma(r1 * r1, q1, r1) + 1.0, p2 = fma(r2 * r2, q2, r2) + 1.0;
+    e0 = __hiloint2double(__double2hiint(p0) + (__double2loint(t0) << 20), __double2loint(p0));
+    e1 = __hiloint2double(__double2hiint(p1) + (__double2loint(t1) << 20), __double2loint(p1));
+    e2 = __hiloint2double(__double2hiint(p2) + (__double2loint(t2) << 20), __double2loint(p2));
+}
+
 // log(x) for normal positive x (fdlibm e_log.c scheme)
 __device__ __forceinline__ double log_fast(double x) {
     int hx = __double2hiint(x);

@@ -264,15 +264,13 @@ __device__ __forceinline__ void eval_pass(const PotDev &pot, const RV &R, const 
     constexpr bool TRACK = (MODE == 0 && RV::EMT);
     const int e = e0 + lane;
     const bool act = e < cnt;
-    const double r2s = act ? R.lr(e) : 1.0;
+    const double r2s = act ? R.lr(e) : 1.0e6;  // padding lanes sit far outside every cutoff: their terms come out as zero
     const bool isnew = r2s > 0.0;
     const double r2 = fabs(r2s);
     if (RV::EMT) {
         double s1, s2;
         emt_pair(pot, r2, s1, s2);
-        s1 = act ? s1 : 0.0;
-        s2 = act ? s2 : 0.0;
-        acc.v += isnew ? s2 : -s2;
+        acc.v = fma(copysign(1.0, r2s), s2, acc.v);
         acc.snew += isnew ? s1 : 0.0;
         if (TRACK) {
             if (e0 + 32 <= xstart) {  // nearest images only: every entry owns its slot
@@ -303,8 +301,7 @@ __device__ __forceinline__ void eval_pass(const PotDev &pot, const RV &R, const 
             }
         }
     } else {
-        const double ep = act ? lj_pair(pot, r2) : 0.0;
-        acc.v += isnew ? ep : -ep;
+        acc.v = fma(copysign(1.0, r2s), lj_pair(pot, r2), acc.v);
     }
     acc.pairs += act ? 1 : 0;
 }
