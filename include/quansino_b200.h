@@ -92,7 +92,8 @@ typedef struct qmc_batch {
     int32_t replica_offset; /* global id of local replica 0 */
     int32_t pbc[3];
     int32_t cells_uniform;  /* != 0: every replica has the fixed cell diag(cell_diag) (fast path); cell moves clear it */
-    int32_t _pad;
+    int32_t pair_cache_valid; /* != 0: pair_cache holds the terms of the CURRENT positions (filled by qmc_energy_full, kept by
+                                  displacement-only qmc_sweep calls); anything else that moves atoms must clear it */
     double cell_diag[3];
     double *pos;            /* [R][3][n_max]  x-row, y-row, z-row per replica */
     double *cell;           /* [R][9] row-major, diagonal */
@@ -107,6 +108,9 @@ typedef struct qmc_batch {
     int64_t *counters;      /* [R][QMC_MAX_MOVES][3] attempted, accepted, failed -- accumulated */
     int32_t *status;        /* [R] qmc_status bits, OR-ed */
     int64_t *pair_evals;    /* [R] pair evaluations performed by the sweeps, accumulated, or NULL */
+    double *pair_cache;     /* [R][n_max][n_max][2] image-summed (sigma_1, sigma_2) terms of every pair, or NULL: the canonical
+                               EMT fast path reads the old-position terms from here instead of recomputing them */
+    double *pair_pending;   /* [R][n_max][2] scratch row of the attempt in flight (with pair_cache) */
     double mass;            /* amu, single species */
     double pressure;        /* eV / A^3 */
     double chemical_potential;

@@ -60,7 +60,7 @@ class Batch(C.Structure):
         ("replica_offset", C.c_int32),
         ("pbc", C.c_int32 * 3),
         ("cells_uniform", C.c_int32),
-        ("_pad", C.c_int32),
+        ("pair_cache_valid", C.c_int32),
         ("cell_diag", C.c_double * 3),
         ("pos", C.c_void_p),
         ("cell", C.c_void_p),
@@ -75,6 +75,8 @@ class Batch(C.Structure):
         ("counters", C.c_void_p),
         ("status", C.c_void_p),
         ("pair_evals", C.c_void_p),
+        ("pair_cache", C.c_void_p),
+        ("pair_pending", C.c_void_p),
         ("mass", C.c_double),
         ("pressure", C.c_double),
         ("chemical_potential", C.c_double),

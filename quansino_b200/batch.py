@@ -127,6 +127,7 @@ class ReplicaBatch:
         device: str | torch.device = "cuda",
         replica_offset: int = 0,
         with_momenta: bool = False,
+        pair_cache: bool | None = None,
     ):
         self.lib = _lib.load()
         self.calc = calc if calc is not None else atoms.calc
@@ -167,6 +168,14 @@ class ReplicaBatch:
         self.exchange_pos = (0.0, 0.0, 0.0)
         self.cells_uniform = False
         self.cell_diag = (0.0, 0.0, 0.0)
+        # optional pair-term cache of the canonical EMT path (csrc/sweep_cached.cuh): 16 B per ordered pair of atoms.  Off by
+        # default: measured SLOWER than recomputing (2.45e8 vs 3.10e8 attempts/s, profiles/r1_f_pair_cache.md)
+        want_cache = bool(pair_cache)
+        self.pair_cache = self.pair_pending = None
+        self.pair_cache_valid = False
+        if want_cache and self.potential.kind == _lib.POT_EMT and N <= 128 and R > 0:
+            self.pair_cache = torch.zeros((R, N, N, 2), dtype=f64, device=dev)
+            self.pair_pending = torch.zeros((R, N, 2), dtype=f64, device=dev)
         self.set_temperature(temperature)
         self.upload(atoms)
 
@@ -180,6 +189,7 @@ class ReplicaBatch:
         self.cell.copy_(cell, non_blocking=non_blocking)
         self.n_atoms.copy_(n, non_blocking=non_blocking)
         nbytes = pos.numel() * 8 + cell.numel() * 8 + n.numel() * 4
+        self.pair_cache_valid = False
         # one fixed cell shared by every replica: the kernels read it from their arguments (fast path)
         self.cells_uniform = bool(self.R > 0 and np.all(atoms.cell == atoms.cell[0]))
         self.cell_diag = tuple(float(atoms.cell[0, k, k]) for k in range(3)) if self.R else (0.0, 0.0, 0.0)
@@ -219,6 +229,9 @@ class ReplicaBatch:
         b.n_replicas, b.n_max, b.replica_offset = self.R, self.n_max, self.replica_offset
         b.pbc = (C.c_int32 * 3)(*[int(x) for x in self.pbc])
         b.cells_uniform = int(self.cells_uniform)
+        b.pair_cache_valid = int(self.pair_cache_valid and self.pair_cache is not None)
+        b.pair_cache = self.pair_cache.data_ptr() if self.pair_cache is not None else None
+        b.pair_pending = self.pair_pending.data_ptr() if self.pair_pending is not None else None
         b.cell_diag = (C.c_double * 3)(*self.cell_diag)
         b.pos, b.cell, b.n_atoms = self.pos.data_ptr(), self.cell.data_ptr(), self.n_atoms.data_ptr()
         b.energy, b.temperature = self.energy.data_ptr(), self.temperature.data_ptr()
@@ -251,6 +264,8 @@ class ReplicaBatch:
                     C.byref(self.potential), C.byref(b), pair_count.data_ptr() if pair_count is not None else None, self.stream()
                 )
             )
+        # qmc_energy_full fills the pair-term cache whenever the cached path can serve the batch (EMT, one fixed cell)
+        self.pair_cache_valid = self.pair_cache is not None and self.cells_uniform
         return self.energy
 
     def forces_full(self) -> torch.Tensor:

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include "sweep_block.cuh"
+#include "sweep_cached.cuh"
 
 namespace qmc {
 
@@ -18,6 +19,13 @@ typedef int (*energy_launch_fn)(const SweepArgs &a, long long *pair_count, cudaS
     int sweep_launch_##POT##_##NS(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn);     \
     int energy_launch_##POT##_##NS(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn); \
     int sweep_block_launch_##POT##_##NS(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn);
+
+// cached canonical fast path: EMT, capacity classes served by the warp kernel
+#define QMC_FOR_EACH_CACHED_NS(X) X(32) X(64) X(108) X(128)
+#define QMC_DECLARE_CACHED(NS)                                                                        \
+    int sweep_cached_launch_##NS(const SweepArgs &a, cudaStream_t s, char *err, size_t errn);         \
+    int energy_cached_launch_##NS(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn);
+QMC_FOR_EACH_CACHED_NS(QMC_DECLARE_CACHED)
 
 QMC_FOR_EACH_NS(QMC_DECLARE_INST, 0)
 QMC_FOR_EACH_NS(QMC_DECLARE_INST, 1)

@@ -98,6 +98,23 @@ struct Inst {
     {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS, qmc::sweep_block_launch_##POT##_##NS, qmc::LayoutB<POT, NS>::MINB},
 const Inst g_inst[2][7] = {{QMC_FOR_EACH_NS(QMC_TABLE_ROW, 0)}, {QMC_FOR_EACH_NS(QMC_TABLE_ROW, 1)}};
 
+struct CachedInst {
+    int ns;
+    int (*sweep)(const qmc::SweepArgs &, cudaStream_t, char *, size_t);
+    int (*energy)(const qmc::SweepArgs &, long long *, cudaStream_t, char *, size_t);
+};
+#define QMC_CACHED_ROW(NS) {NS, qmc::sweep_cached_launch_##NS, qmc::energy_cached_launch_##NS},
+const CachedInst g_cached[] = {QMC_FOR_EACH_CACHED_NS(QMC_CACHED_ROW)};
+
+// the pair-term cache serves EMT batches with one fixed cell whose capacity class runs one warp per replica
+const CachedInst *find_cached(const qmc_potential_t *pot, const qmc_batch_t *b) {
+    if (pot->kind != QMC_POT_EMT || !b->pair_cache || !b->pair_pending || !b->cells_uniform) return nullptr;
+    const int ns = qmc::capacity_class(b->n_max);
+    for (const CachedInst &c : g_cached)
+        if (c.ns == ns) return &c;
+    return nullptr;
+}
+
 const Inst *find_inst(int kind, int n_max) {
     const int ns = qmc::capacity_class(n_max);
     if (ns == 0 || kind < 0 || kind > 1) return nullptr;
@@ -177,6 +194,8 @@ int qmc_energy_full(const qmc_potential_t *pot, const qmc_batch_t *batch, int64_
     if ((rc = make_potdev(pot, a.pot))) return rc;
     a.b = *batch;
     if ((rc = fill_cell_args(batch, a.pot, a))) return rc;
+    if (const CachedInst *c = find_cached(pot, batch))  // also fills the pair-term cache
+        return c->energy(a, (long long *)pair_count, (cudaStream_t)stream, g_err, sizeof(g_err));
     const Inst *inst = find_inst(pot->kind, batch->n_max);
     if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica kernels");
     return inst->energy(a, (long long *)pair_count, (cudaStream_t)stream, g_err, sizeof(g_err));
@@ -263,7 +282,11 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     // (measured on B200: at 108 atoms a warp owns a single 32-atom tile and the block kernel loses, 1.5e8 vs 1.7e8 attempts/s at
     // 1024 replicas; at 500 atoms it wins 1.9x -- profiles/r1_e_kernel_choice.md)
     bool block = inst->ns >= 256 && batch->n_replicas <= 2 * sms * inst->block_minb;
-    if (const char *force = std::getenv("QMC_FORCE_KERNEL")) block = std::strcmp(force, "block") == 0;
+    const char *force = std::getenv("QMC_FORCE_KERNEL");
+    if (force) block = std::strcmp(force, "block") == 0;
+    // canonical fast path: old-position pair terms come from the HBM cache instead of being recomputed
+    if (feat == 0 && batch->pair_cache_valid && !block && !(force && std::strcmp(force, "cached") != 0))
+        if (const CachedInst *c = find_cached(pot, batch)) return c->sweep(a, (cudaStream_t)stream, g_err, sizeof(g_err));
     return (block ? inst->sweep_block : inst->sweep)(feat, a, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 
@@ -373,6 +396,9 @@ int qmc_sweep_host(const qmc_potential_t *pot, const qmc_batch_t *h, const qmc_m
     auto cleanup = [&]() { for (void *p : owned) cudaFree(p); };
     qmc_batch_t d = *h;
     d.cells_uniform = 0;
+    d.pair_cache = nullptr;
+    d.pair_pending = nullptr;
+    d.pair_cache_valid = 0;
     int rc = QMC_OK;
 #define UP(field, bytes, src) if (rc == QMC_OK) rc = dev_alloc(bytes, src, (void **)&d.field)
     UP(pos, R * 3 * N * 8, h->pos);

@@ -70,4 +70,31 @@ int CAT(energy_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, long long *pai
     return report(cudaGetLastError(), "energy kernel launch", err, errn);
 }
 
+#if INST_POT == 0 && INST_NS <= 128
+#define CATC_(a, b) a##b
+#define CATC(a, b) CATC_(a, b)
+int CATC(sweep_cached_launch_, INST_NS)(const SweepArgs &a, cudaStream_t s, char *err, size_t errn) {
+    using LY = LayoutC<INST_NS>;
+    static_assert(LY::FITS, "replica does not fit in shared memory");
+    constexpr size_t smem = (size_t)LY::WARPS * LY::BYTES;
+    auto kernel = sweep_cached_kernel<INST_NS>;
+    int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
+    if (rc) return rc;
+    const int grid = (a.b.n_replicas + LY::WARPS - 1) / LY::WARPS;
+    kernel<<<grid, LY::WARPS * 32, smem, s>>>(a);
+    return report(cudaGetLastError(), "cached sweep kernel launch", err, errn);
+}
+
+int CATC(energy_cached_launch_, INST_NS)(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn) {
+    using LY = LayoutC<INST_NS>;
+    constexpr size_t smem = (size_t)LY::WARPS * LY::BYTES;
+    auto kernel = energy_cached_kernel<INST_NS>;
+    int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
+    if (rc) return rc;
+    const int grid = (a.b.n_replicas + LY::WARPS - 1) / LY::WARPS;
+    kernel<<<grid, LY::WARPS * 32, smem, s>>>(a, pair_count);
+    return report(cudaGetLastError(), "cached energy kernel launch", err, errn);
+}
+#endif
+
 }  // namespace qmc

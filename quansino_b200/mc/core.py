@@ -72,6 +72,7 @@ class MonteCarlo:
         resync_interval: int = 100,
         trace: bool = False,
         logging_interval: int = 1,
+        pair_cache: bool | None = None,
     ) -> None:
         self.moves: dict[str, MoveStorage] = {}
         self.max_cycles = max_cycles
@@ -92,7 +93,7 @@ class MonteCarlo:
             atoms = BatchedAtoms.from_ase(atoms, replicas=replicas if not isinstance(atoms, (list, tuple)) else None, calc=calc)
         self.atoms = atoms
         self.batch = ReplicaBatch(
-            atoms, calc=calc, device=device, replica_offset=replica_offset, with_momenta=self.needs_momenta
+            atoms, calc=calc, device=device, replica_offset=replica_offset, with_momenta=self.needs_momenta, pair_cache=pair_cache
         )
         self.context = self.default_context(atoms, self.batch, self._seed)
         self._lowered: tuple | None = None
@@ -263,6 +264,15 @@ class MonteCarlo:
                 "moved": torch.zeros((R, n_attempts), dtype=torch.int32, device=b.device),
             }
             tr = _lib.Trace(*[bufs[k].data_ptr() for k in ("move", "accepted", "energy", "delta", "moved")])
+        # the pair-term cache follows displacement-only sweeps of a fixed cell; everything else leaves it stale
+        keeps_cache = (
+            b.pair_cache is not None and b.cells_uniform and os.environ.get("QMC_FORCE_KERNEL") in (None, "cached")
+            and all(m.type == _lib.MOVE_DISPLACEMENT and not m.labels for m in moves)
+        )  # fmt: skip
+        if keeps_cache and not b.pair_cache_valid:
+            b.energy_full()
+        if not keeps_cache:
+            b.pair_cache_valid = False
         with torch.cuda.device(b.device):
             bs = b.struct()
             if moves[0].type == _lib.MOVE_HMC:

@@ -20,9 +20,11 @@ def cuda_lib():
     return _lib.load()
 
 
-@pytest.fixture(params=["warp", "block"])
+@pytest.fixture(params=["warp", "block", "cached"])
 def kernel_variant(request, monkeypatch):
     """Run a sweep test through both organisations of the sweep kernel: one warp per replica (csrc/sweep_kernel.cuh)
-    and one CTA per replica (csrc/sweep_block.cuh).  Without the variable the library picks by batch size."""
+    one CTA per replica (csrc/sweep_block.cuh), and the canonical fast path with the HBM pair-term cache
+    (csrc/sweep_cached.cuh; it only engages for displacement-only EMT sweeps, other tables run as "auto").  Without the
+    variable the library picks by batch size."""
     monkeypatch.setenv("QMC_FORCE_KERNEL", request.param)
     return request.param

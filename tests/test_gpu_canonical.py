@@ -19,6 +19,9 @@ def _driver(pos, cell, n, op, temperature=300.0, seed=1234, trace=True, **kw):
     from quansino_b200.moves import DisplacementMove
 
     atoms = BatchedAtoms(pos.copy(), cell, np.full(len(pos), n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    import os
+
+    kw.setdefault("pair_cache", os.environ.get("QMC_FORCE_KERNEL") == "cached")
     mc = Canonical(atoms, temperature=temperature, seed=seed, trace=trace, default_displacement_move=DisplacementMove(np.arange(n), op), **kw)
     return mc
 
