@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/quansino_b200.h"
@@ -97,6 +99,30 @@ struct Inst {
 #define QMC_TABLE_ROW(POT, NS) \
     {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS, qmc::sweep_block_launch_##POT##_##NS, qmc::LayoutB<POT, NS>::MINB},
 const Inst g_inst[2][7] = {{QMC_FOR_EACH_NS(QMC_TABLE_ROW, 0)}, {QMC_FOR_EACH_NS(QMC_TABLE_ROW, 1)}};
+
+// per-(device, stream) scratch of the dynamic work distribution: one work counter + one progress counter per replica
+struct Scratch {
+    int *buf = nullptr;
+    size_t ints = 0;
+};
+std::mutex g_scratch_mu;
+std::map<std::pair<int, cudaStream_t>, Scratch> g_scratch;
+
+int get_scratch(cudaStream_t s, size_t ints, int **out) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    Scratch &sc = g_scratch[{dev, s}];
+    if (sc.ints < ints) {
+        if (sc.buf) CUDA_TRY(cudaFree(sc.buf));
+        sc.buf = nullptr;
+        sc.ints = 0;
+        CUDA_TRY(cudaMalloc(&sc.buf, ints * sizeof(int)));
+        sc.ints = ints;
+    }
+    *out = sc.buf;
+    return QMC_OK;
+}
 
 struct CachedInst {
     int ns;
@@ -287,6 +313,22 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     // canonical fast path: old-position pair terms come from the HBM cache instead of being recomputed
     if (feat == 0 && batch->pair_cache_valid && !block && !(force && std::strcmp(force, "cached") != 0))
         if (const CachedInst *c = find_cached(pot, batch)) return c->sweep(a, (cudaStream_t)stream, g_err, sizeof(g_err));
+    if (!block) {
+        // dynamic (chunk, replica) work items: warps the scheduler favours take over from the ones it starves
+        // (measured neutral at best when every replica already owns a warp -- a replica is a sequential chain, so nobody can
+        // help a starved one; it pays only through multi-wave batches.  Off unless QMC_CHUNK is set.)
+        int chunk = 0;
+        if (const char *c = std::getenv("QMC_CHUNK")) chunk = std::atoi(c);
+        if (chunk > 0 && n_attempts > chunk) {
+            int *buf = nullptr;
+            if ((rc = get_scratch((cudaStream_t)stream, (size_t)batch->n_replicas + 1, &buf))) return rc;
+            CUDA_TRY(cudaMemsetAsync(buf, 0, ((size_t)batch->n_replicas + 1) * sizeof(int), (cudaStream_t)stream));
+            a.chunk_len = chunk;
+            a.n_chunks = (n_attempts + chunk - 1) / chunk;
+            a.work_counter = buf;
+            a.done = buf + 1;
+        }
+    }
     return (block ? inst->sweep_block : inst->sweep)(feat, a, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 

@@ -59,16 +59,19 @@ struct Layout {
     static constexpr int L2_B = PP_B + (EMT ? NS * 4 : 0);
     static constexpr int XJ_B = L2_B + (EMT ? NS * 2 : 0);
     static constexpr int BYTES = round_up(XJ_B + (EMT ? XCAP * 2 : 0), 16);
-    // launch geometry: the CTA width that packs most replicas (warps) onto one SM
-    static constexpr int blocks_for(int w) {
-        const int b = SMEM_PER_SM / (w * BYTES + 1024);
-        const int cap = w == 4 ? 7 : (w == 2 ? 14 : 16);
-        return b < cap ? b : cap;
-    }
-    static constexpr int WARPS = (blocks_for(4) * 4 >= blocks_for(2) * 2 && blocks_for(4) * 4 >= blocks_for(1)) ? 4
-                                 : (blocks_for(2) * 2 >= blocks_for(1) ? 2 : 1);
-    static constexpr int MINB = blocks_for(WARPS) > 0 ? blocks_for(WARPS) : 1;
-    static constexpr bool FITS = WARPS * BYTES <= SMEM_PER_CTA_MAX && blocks_for(WARPS) > 0;
+    // launch geometry: ONE wide CTA per SM holding as many replicas (warps) as shared memory and the 72-register budget allow.
+    // Measured on B200 (4096 x 108-atom Cu EMT): 7 CTAs x 4 warps 3.10e8 attempts/s, 2 x 14 warps 3.35e8, 1 x 28 warps 3.68e8 --
+    // the warp schedulers favour the warps of older CTAs, so replicas in separate CTAs finish 0.77 .. 1.39 ms into a 1.43 ms launch
+    // and leave the SM under-occupied; the warps of one CTA progress evenly (profiles/r1_g_cta_width.md).
+    static constexpr int fit = (SMEM_PER_SM - 1024) / BYTES;
+#ifdef QMC_WARPS_PER_CTA
+    static constexpr int WARPS = QMC_WARPS_PER_CTA;  // tuning experiments
+    static constexpr int MINB = 28 / QMC_WARPS_PER_CTA > 0 ? 28 / QMC_WARPS_PER_CTA : 1;
+#else
+    static constexpr int WARPS = fit > 28 ? 28 : (fit < 1 ? 1 : fit);
+    static constexpr int MINB = 1;
+#endif
+    static constexpr bool FITS = WARPS * BYTES <= SMEM_PER_CTA_MAX && fit > 0;
 };
 
 // Per-warp view of the replica: base pointer + runtime atom count.  Arrays are reached through the layout constants.

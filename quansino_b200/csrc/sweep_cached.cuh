@@ -34,9 +34,9 @@ struct LayoutC {
     static constexpr int L2_B = PP_B + NS * 2;
     static constexpr int XJ_B = L2_B + NS * 2;
     static constexpr int BYTES = round_up(XJ_B + XCAPC * 2, 16);
-    static constexpr int WARPS = 4;
-    static constexpr int raw_blocks = SMEM_PER_SM / (WARPS * BYTES + 1024);
-    static constexpr int MINB = raw_blocks > 7 ? 7 : (raw_blocks < 1 ? 1 : raw_blocks);
+    static constexpr int fit = (SMEM_PER_SM - 1024) / BYTES;
+    static constexpr int WARPS = fit > 28 ? 28 : (fit < 1 ? 1 : fit);  // one wide CTA per SM (see Layout in replica_warp.cuh)
+    static constexpr int MINB = 1;
     static constexpr bool FITS = WARPS * BYTES <= SMEM_PER_CTA_MAX;
 };
 

@@ -36,6 +36,10 @@ struct SweepArgs {
     unsigned long long seed, attempt_base;
     int n_attempts;
     int has_trace;
+    // dynamic work distribution of the warp-per-replica kernel: items = (chunk of attempts, replica), taken in order from a
+    // global counter; done[r] = number of finished chunks of replica r (a chunk waits for its predecessor)
+    int chunk_len, n_chunks;
+    int *work_counter, *done;
     qmc_trace_t tr;
 };
 
@@ -44,7 +48,7 @@ __device__ inline int count_labelled(const int *lab, int n) {
     int c = 0;
     for (int base = 0; base < n; base += 32) {
         const int j = base + lane_id();
-        c += __popc(__ballot_sync(FULL, j < n && lab[j] >= 0));
+        c += __popc(__ballot_sync(FULL, j < n && __ldcg(lab + min(j, n - 1)) >= 0));
     }
     return c;
 }
@@ -55,7 +59,7 @@ __device__ inline int select_labelled(const int *lab, int n, int idx) {
     int run = 0, found = -1;
     for (int base = 0; base < n; base += 32) {
         const int j = base + lane_id();
-        const unsigned b = __ballot_sync(FULL, j < n && lab[j] >= 0);
+        const unsigned b = __ballot_sync(FULL, j < n && __ldcg(lab + min(j, n - 1)) >= 0);
         const int c = __popc(b);
         if (found < 0 && idx < run + c) found = base + (int)__fns(b, 0, idx - run + 1);
         run += c;
@@ -67,7 +71,7 @@ __device__ inline int max_label(const int *lab, int n) {
     int m = -1;
     for (int base = 0; base < n; base += 32) {
         const int j = base + lane_id();
-        const int v = (j < n) ? lab[j] : -1;
+        const int v = (j < n) ? __ldcg(lab + j) : -1;
         m = max(m, __reduce_max_sync(FULL, v));
     }
     return m;
@@ -88,7 +92,7 @@ __device__ inline void labels_changed(int *lab, int n, bool added, int removed, 
         for (int base = removed; base < n - 1; base += 32) {
             const int j = base + lane;
             int t = 0;
-            if (j < n - 1) t = lab[j + 1];
+            if (j < n - 1) t = __ldcg(lab + j + 1);
             __syncwarp();
             if (j < n - 1) lab[j] = t;
             __syncwarp();
@@ -244,47 +248,66 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
     extern __shared__ __align__(16) double smem_d[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
-    const int r = blockIdx.x * WARPS + warp;
-    if (r >= a.b.n_replicas) return;  // whole warp exits; no block-wide barrier is used below
     const PotDev &pot = a.pot;
     const int nmax = a.b.n_max;
     Rep<LY> R;
     R.b = smem_d + warp * (LY::BYTES / 8);
     const CellView<LY, UNIFORM> C{&a.cell, R.b + LY::CELLC};
-
-    // ---- load the replica ----
-    R.n = a.b.n_atoms[r];
+    const bool dynamic = a.n_chunks > 1;
+    // Work items.  Static: warp w of the grid owns replica w for the whole launch.  Dynamic: (chunk, replica) items are taken
+    // in order from a global counter, so that warps the hardware scheduler favours take over work from the ones it starves
+    // (measured: per-replica time 0.77 .. 1.39 ms inside one launch, profiles/r1_g_dynamic_chunks.md).
+    for (int item = blockIdx.x * WARPS + warp;; ) {
+        if (dynamic) {
+            if (lane == 0) item = atomicAdd(a.work_counter, 1);
+            item = __shfl_sync(FULL, item, 0);
+            if (item >= a.n_chunks * a.b.n_replicas) break;
+        } else if (item >= a.b.n_replicas) {
+            break;
+        }
+        const int r = dynamic ? item % a.b.n_replicas : item;
+        const int chunk = dynamic ? item / a.b.n_replicas : 0;
+        if (dynamic && chunk > 0) {  // the previous chunk of this replica was taken earlier by a running warp: wait for it
+            if (lane == 0)
+                while (*reinterpret_cast<volatile int *>(a.done + r) < chunk) __nanosleep(100);
+            __syncwarp();
+            __threadfence();
+        }
+        const int k_begin = dynamic ? chunk * a.chunk_len : 0;
+        const int k_end = dynamic ? min(k_begin + a.chunk_len, a.n_attempts) : a.n_attempts;
+    // ---- load the replica (L1 bypassed: another SM may have written the state in an earlier chunk) ----
+    R.n = __ldcg(a.b.n_atoms + r);
     double *gx = a.b.pos + (size_t)r * 3 * nmax, *gy = gx + nmax, *gz = gy + nmax;
     double *gs = POT == QMC_POT_EMT ? a.b.sigma1 + (size_t)r * nmax : nullptr;
     double *ge = POT == QMC_POT_EMT ? a.b.eatom + (size_t)r * nmax : nullptr;
     for (int j = lane; j < nmax; j += 32) {
         const bool in = j < R.n;
-        R.x(j) = in ? gx[j] : 0.0;
-        R.y(j) = in ? gy[j] : 0.0;
-        R.z(j) = in ? gz[j] : 0.0;
+        R.x(j) = in ? __ldcg(gx + j) : 0.0;
+        R.y(j) = in ? __ldcg(gy + j) : 0.0;
+        R.z(j) = in ? __ldcg(gz + j) : 0.0;
         if (POT == QMC_POT_EMT) {
-            R.sig(j) = in ? gs[j] : 0.0;
-            R.eat(j) = in ? ge[j] : 0.0;
+            R.sig(j) = in ? __ldcg(gs + j) : 0.0;
+            R.eat(j) = in ? __ldcg(ge + j) : 0.0;
         }
     }
     int status = 0;
     double cell[3] = {0.0, 0.0, 0.0};
     if (!UNIFORM) {
-        cell[0] = a.b.cell[(size_t)r * 9 + 0];
-        cell[1] = a.b.cell[(size_t)r * 9 + 4];
-        cell[2] = a.b.cell[(size_t)r * 9 + 8];
+        cell[0] = __ldcg(a.b.cell + (size_t)r * 9 + 0);
+        cell[1] = __ldcg(a.b.cell + (size_t)r * 9 + 4);
+        cell[2] = __ldcg(a.b.cell + (size_t)r * 9 + 8);
         if (!store_cell(R, cell, a.b.pbc, pot.cut_pre, lane)) status |= QMC_STATUS_CELL_TOO_SMALL;
     }
-    double E = a.b.energy[r];
+    double E = __ldcg(a.b.energy + r);
     const double temperature = a.b.temperature[r];
     const double kT = temperature * KB;
-    int n_ex = (FEAT & F_EXCHANGE) ? a.b.n_exchange[r] : 0;
+    int n_ex = (FEAT & F_EXCHANGE) ? __ldcg(a.b.n_exchange + r) : 0;
     const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
     const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
     long long n_pairs = 0;
     __syncwarp();
 
-    for (int k = 0; k < a.n_attempts; ++k) {
+    for (int k = k_begin; k < k_end; ++k) {
         const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
         const Draws D = draw_attempt(key, attempt, grep, lane, (FEAT & F_EXCHANGE) != 0);
 
@@ -516,6 +539,11 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
     if (a.b.pair_evals) {
         for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(FULL, n_pairs, o);
         if (lane == 0) a.b.pair_evals[r] += n_pairs;
+    }
+        if (!dynamic) break;
+        __threadfence();  // the stored state is visible before the chunk is published
+        __syncwarp();
+        if (lane == 0) atomicExch(a.done + r, chunk + 1);
     }
 }
 
