@@ -97,7 +97,7 @@ struct Inst {
 };
 
 #define QMC_TABLE_ROW(POT, NS) \
-    {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS, qmc::sweep_block_launch_##POT##_##NS, qmc::LayoutB<POT, NS>::MINB},
+    {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS, qmc::sweep_block_launch_##POT##_##NS, qmc::LayoutB<POT, NS>::REPS},
 const Inst g_inst[2][7] = {{QMC_FOR_EACH_NS(QMC_TABLE_ROW, 0)}, {QMC_FOR_EACH_NS(QMC_TABLE_ROW, 1)}};
 
 // per-(device, stream) scratch of the dynamic work distribution: one work counter + one progress counter per replica

@@ -13,6 +13,11 @@
 
 namespace qmc {
 
+// barrier over the BW warps of ONE replica (several replicas share a CTA): named barrier 1 + replica slot
+__device__ __forceinline__ void rep_sync() {
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x >> 7)), "r"(128) : "memory");
+}
+
 constexpr int BW = 4;      // warps per replica
 constexpr int XCAPB = 32;  // second-image entries per warp region
 
@@ -33,9 +38,11 @@ struct LayoutB {
     static constexpr int XJ_OFF = L2_OFF + (EMT ? (NSW + 8) * 2 : 0);
     static constexpr int REG_B = round_up(XJ_OFF + (EMT ? XCAPB * 2 : 0), 8);
     static constexpr int BYTES = round_up(REG0_B + BW * REG_B, 16);
-    static constexpr int raw_blocks = SMEM_PER_SM / (BYTES + 1024);
-    static constexpr int MINB = raw_blocks < 1 ? 1 : (raw_blocks > 7 ? 7 : raw_blocks);  // <= 7: keeps the 72-register budget
-    static constexpr bool FITS = BYTES <= SMEM_PER_CTA_MAX;
+    // one wide CTA per SM holding REPS replicas of BW warps each (the warps of one CTA progress evenly, see Layout)
+    static constexpr int fit = (SMEM_PER_SM - 1024) / BYTES;
+    static constexpr int REPS = fit > 7 ? 7 : (fit < 1 ? 1 : fit);  // <= 7: 28 warps keep the 72-register budget
+    static constexpr int MINB = 1;
+    static constexpr bool FITS = BYTES <= SMEM_PER_CTA_MAX && fit > 0;
 };
 
 template <class LY>
@@ -79,8 +86,8 @@ template <class LY>
 __device__ __forceinline__ bool store_cell_block(const RepB<LY> &R, const double diag[3], const int pbc[3], double cut_pre) {
     CellArgs c;
     const bool ok = cell_constants(diag, pbc, cut_pre, c);
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    rep_sync();
+    if ((threadIdx.x & 127) == 0) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             R.cellc(k) = c.L[k];
@@ -88,7 +95,7 @@ __device__ __forceinline__ bool store_cell_block(const RepB<LY> &R, const double
             R.cellc(6 + k) = c.thr[k];
         }
     }
-    __syncthreads();
+    rep_sync();
     return ok;
 }
 
@@ -116,11 +123,11 @@ __device__ inline double block_full_energy(const PotDev &pot, const RepB<LY> &R,
         }
         __syncwarp();
     }
-    __syncthreads();
+    rep_sync();
     double ew = erow;
     if (LY::EMT) {
         double epart = 0.0;
-        for (int a = threadIdx.x; a < R.n; a += BW * 32) {
+        for (int a = threadIdx.x & 127; a < R.n; a += BW * 32) {
             const double ea = emt_embed(pot, R.sig(a));
             epart += ea + pot.neghalfv0overgamma2 * R.eat(a);
             R.eat(a) = ea;
@@ -128,26 +135,29 @@ __device__ inline double block_full_energy(const PotDev &pot, const RepB<LY> &R,
         ew = warp_sum(epart);
     }
     block_put(R, warp, lane, 2, ew);
-    __syncthreads();
+    rep_sync();
     const double e = block_get(R, 2);
-    __syncthreads();
+    rep_sync();
     return e;
 }
 
 template <int POT, int NS, int FEAT>
-__global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_kernel(const __grid_constant__ SweepArgs a) {
+__global__ void __launch_bounds__(LayoutB<POT, NS>::REPS * BW * 32, 1) sweep_block_kernel(const __grid_constant__ SweepArgs a) {
     using LY = LayoutB<POT, NS>;
     using RV = RepB<LY>;
     constexpr bool UNIFORM = (FEAT & F_CELLVAR) == 0;
     extern __shared__ __align__(16) double smem_d[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = threadIdx.x >> 7;              // replica slot inside the CTA
+    const int tid = threadIdx.x & 127;              // thread inside the replica's group of BW warps
+    const int warp = tid >> 5, lane = tid & 31;
     const unsigned lt = lanemask_lt();
-    const int r = blockIdx.x;
+    const int r = blockIdx.x * LY::REPS + slot;
+    if (r >= a.b.n_replicas) return;  // the whole group leaves; barriers are per group
     const PotDev &pot = a.pot;
     const int nmax = a.b.n_max;
     RV R;
-    R.b = smem_d;
-    R.wb = reinterpret_cast<double *>(reinterpret_cast<char *>(smem_d) + LY::REG0_B + warp * LY::REG_B);
+    R.b = smem_d + slot * (LY::BYTES / 8);
+    R.wb = reinterpret_cast<double *>(reinterpret_cast<char *>(R.b) + LY::REG0_B + warp * LY::REG_B);
     const CellView<LY, UNIFORM> C{&a.cell, R.b + LY::CELLC};
 
     // ---- load the replica ----
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
     double *gx = a.b.pos + (size_t)r * 3 * nmax, *gy = gx + nmax, *gz = gy + nmax;
     double *gs = POT == QMC_POT_EMT ? a.b.sigma1 + (size_t)r * nmax : nullptr;
     double *ge = POT == QMC_POT_EMT ? a.b.eatom + (size_t)r * nmax : nullptr;
-    for (int j = threadIdx.x; j < nmax; j += BW * 32) {
+    for (int j = tid; j < nmax; j += BW * 32) {
         const bool in = j < R.n;
         R.x(j) = in ? gx[j] : 0.0;
         R.y(j) = in ? gy[j] : 0.0;
@@ -180,7 +190,7 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
     const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
     const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
     long long n_pairs = 0;
-    __syncthreads();
+    rep_sync();
 
     for (int k = 0; k < a.n_attempts; ++k) {
         const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
@@ -267,7 +277,7 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
                 n_pairs += acc.pairs;
                 block_put(R, warp, lane, 0, warp_sum(acc.v));
                 if (POT == QMC_POT_EMT) block_put(R, warp, lane, 1, warp_sum(acc.snew));
-                __syncthreads();  // B1
+                rep_sync();  // B1
                 const double vs = block_get(R, 0);
                 double sig_i = 0.0, eat_i = 0.0;
                 if (POT == QMC_POT_EMT) {
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
                     if (extra) eat_i = __shfl_sync(FULL, e_i_lane, n2 & 31);
                     if (!has_new && warp == 0 && lane == 0) part -= R.eat(i);
                     block_put(R, warp, lane, 2, warp_sum(part));
-                    __syncthreads();  // B2
+                    rep_sync();  // B2
                     delta = block_get(R, 2) + 2.0 * pot.neghalfv0overgamma2 * vs;
                 } else {
                     delta = vs;
@@ -323,7 +333,7 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
                     }
                     E += delta;
                     if (is_exch) {
-                        __syncthreads();
+                        rep_sync();
                         if (warp == 0) {
                             for (int q = 0; q < a.n_moves; ++q)
                                 if (a.mv[q].labels)
@@ -342,12 +352,12 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
                         n_ex += pd;
                     }
                 }
-                __syncthreads();  // B3: the committed state is visible to every warp before the next scan
+                rep_sync();  // B3: the committed state is visible to every warp before the next scan
                 accepted = acc_ok ? 1 : 0;
                 moved = i;
             }
         } else if ((FEAT & F_CELL) && mv.type == QMC_MOVE_CELL) {
-            for (int j = threadIdx.x; j < R.n; j += BW * 32) {  // snapshot of the last accepted state
+            for (int j = tid; j < R.n; j += BW * 32) {  // snapshot of the last accepted state
                 gx[j] = R.x(j);
                 gy[j] = R.y(j);
                 gz[j] = R.z(j);
@@ -363,7 +373,7 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
                 ncell[d] = s * cell[d];
                 scale[d] = ncell[d] / cell[d];
             }
-            for (int j = threadIdx.x; j < R.n; j += BW * 32) {
+            for (int j = tid; j < R.n; j += BW * 32) {
                 R.x(j) = R.x(j) * scale[0];
                 R.y(j) = R.y(j) * scale[1];
                 R.z(j) = R.z(j) * scale[2];
@@ -383,8 +393,8 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
                 cell[1] = ncell[1];
                 cell[2] = ncell[2];
             } else {
-                __syncthreads();
-                for (int j = threadIdx.x; j < R.n; j += BW * 32) {
+                rep_sync();
+                for (int j = tid; j < R.n; j += BW * 32) {
                     R.x(j) = gx[j];
                     R.y(j) = gy[j];
                     R.z(j) = gz[j];
@@ -395,11 +405,11 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
                 }
                 store_cell_block(R, cell, a.b.pbc, pot.cut_pre);
             }
-            __syncthreads();
+            rep_sync();
             accepted = acc_ok ? 1 : 0;
         }
 
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             unsigned long long *cnt = reinterpret_cast<unsigned long long *>(a.b.counters) + ((size_t)r * QMC_MAX_MOVES + m) * 3;
             atomicAdd(cnt + 0, 1ull);
             if (accepted == 1) atomicAdd(cnt + 1, 1ull);
@@ -416,8 +426,8 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
     }
 
     // ---- store the replica ----
-    __syncthreads();
-    for (int j = threadIdx.x; j < R.n; j += BW * 32) {
+    rep_sync();
+    for (int j = tid; j < R.n; j += BW * 32) {
         gx[j] = R.x(j);
         gy[j] = R.y(j);
         gz[j] = R.z(j);
@@ -426,7 +436,7 @@ __global__ void __launch_bounds__(BW * 32, LayoutB<POT, NS>::MINB) sweep_block_k
             ge[j] = R.eat(j);
         }
     }
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         a.b.n_atoms[r] = R.n;
         a.b.energy[r] = E;
         if (FEAT & F_CELL) {

@@ -44,11 +44,11 @@ template <int FEAT>
 static inline int launch_block_feat(const SweepArgs &a, cudaStream_t s, char *err, size_t errn) {
     using LY = LayoutB<INST_POT, INST_NS>;
     static_assert(LY::FITS, "replica does not fit in shared memory");
-    constexpr size_t smem = (size_t)LY::BYTES;
+    constexpr size_t smem = (size_t)LY::REPS * LY::BYTES;
     auto kernel = sweep_block_kernel<INST_POT, INST_NS, FEAT>;
     int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
     if (rc) return rc;
-    kernel<<<a.b.n_replicas, BW * 32, smem, s>>>(a);
+    kernel<<<(a.b.n_replicas + LY::REPS - 1) / LY::REPS, LY::REPS * BW * 32, smem, s>>>(a);
     return report(cudaGetLastError(), "sweep block kernel launch", err, errn);
 }
 
