@@ -81,17 +81,26 @@ struct PotDev {
     double kappa_over_beta;
 };
 
-// sigma_1 and sigma_2 contributions of one neighbour image at squared distance r2 (_calc_theta, _calc_dsigma1,
-// _calc_dsigma2 with chi = 1); zero outside `r < rc_list` (_get_neighbors).  Branch-free: 1 sqrt, 3 exp, 1 reciprocal.
-__device__ __forceinline__ void emt_pair(const PotDev &p, double r2, double &s1, double &s2) {
-    const double r = sqrt_fast(fmax(r2, 1e-200));
+// Exponential factors e1 (sigma_1), e2 (sigma_2) of one neighbour image at squared distance r2 > 0 and its cutoff weight
+// w = theta(r) inside `r < rc_list` (_get_neighbors), 0 outside: the contributions are e1 * w and e2 * w (_calc_theta,
+// _calc_dsigma1, _calc_dsigma2 with chi = 1).  Branch-free: 1 sqrt, 3 exp, 1 reciprocal.  Returns `r < rc_list`.
+__device__ __forceinline__ bool emt_pair_w(const PotDev &p, double r2, double &e1, double &e2, double &w) {
+    const double r = sqrt_fast(r2);
     // the three exponents are linear in r: one FMA each (constants folded on the host)
-    double et, e1, e2;
+    double et;
     exp3_fast(fma(p.acut, r, p.theta_c), fma(p.sig1_a, r, p.sig1_c), fma(p.sig2_a, r, p.sig2_c), et, e1, e2);
-    const double w = rcp_fast(1.0 + et);
+    const double t = rcp_fast(1.0 + et);
     const bool in = r < p.rc_list;  // also discards whatever a padding entry (r2 = 1e6) produced
-    s1 = in ? e1 * w : 0.0;
-    s2 = in ? e2 * w : 0.0;
+    w = in ? t : 0.0;
+    return in;
+}
+
+// sigma_1 and sigma_2 contributions of one neighbour image at squared distance r2 (any r2 >= 0)
+__device__ __forceinline__ void emt_pair(const PotDev &p, double r2, double &s1, double &s2) {
+    double e1, e2, w;
+    emt_pair_w(p, fmax(r2, 1e-200), e1, e2, w);
+    s1 = e1 * w;
+    s2 = e2 * w;
 }
 
 // E_c + second term of E_AS - E0 for one atom given its sigma_1 (_calc_e_c_a2 and the final `energies -= E0`);
@@ -119,12 +128,18 @@ __device__ __forceinline__ double emt_embed_deds(const PotDev &p, double sigma1,
     return p.E0 * (1.0 + x) * ex + z - p.E0;
 }
 
-// pair energy of one neighbour image (LennardJones.calculate: c6[r2 > rc^2] = 0; e = 4 eps (c12 - c6) - e0 (c6 != 0))
-__device__ __forceinline__ double lj_pair(const PotDev &p, double r2) {
+// pair energy of one neighbour image (LennardJones.calculate: c6[r2 > rc^2] = 0; e = 4 eps (c12 - c6) - e0 (c6 != 0));
+// `in` = inside the cutoff
+__device__ __forceinline__ double lj_pair(const PotDev &p, double r2, bool &in) {
     const double q = p.sigma2 * rcp_fast(fmax(r2, 1e-200));
     const double c6 = q * q * q;
     const double e = p.eps4 * (c6 * c6 - c6) - p.lj_e0;
-    return (r2 > p.lj_rc2) ? 0.0 : e;
+    in = !(r2 > p.lj_rc2);
+    return in ? e : 0.0;
+}
+__device__ __forceinline__ double lj_pair(const PotDev &p, double r2) {
+    bool in;
+    return lj_pair(p, r2, in);
 }
 
 // u < exp(x) without evaluating exp where the answer is already decided; flags the reference's OverflowError

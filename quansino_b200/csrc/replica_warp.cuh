@@ -133,16 +133,24 @@ struct CellView {
     __device__ __forceinline__ bool per(int k) const { return u->per[k] != 0; }
 };
 
-// nearest image d0 of (xj - xi) along one axis; sets `bit` in `extra` if the second image d0 -+ L can be inside the cutoff
-__device__ __forceinline__ double axis_nearest(double xi, double xj, const Axis &A, bool per, unsigned &extra, unsigned bit) {
-    if (per) {
-        const double q = (xi - xj) * A.invL;
-        const double k0 = (q + RINT_MAGIC) - RINT_MAGIC;
-        const double d0 = fma(k0, A.L, xj) - xi;
-        extra |= (fabs(d0) > A.thr) ? bit : 0u;
-        return d0;
-    }
-    return xj - xi;
+// nearest image d0 of (xj - xi) along one axis (4 FP64 operations, branch-free); sets `bit` in `extra` if the second image
+// d0 -+ L can be inside the cutoff.  Positions are never wrapped (moves/displacement.py:109-141), so |xj - xi| may span
+// several cells.  A non-periodic axis has invL = 0 and thr = 1e300 (cell_constants): k = 0, d0 = d exactly, never flagged.
+__device__ __forceinline__ double axis_nearest(double xi, double xj, const Axis &A, bool /*per*/, unsigned &extra, unsigned bit) {
+    const double d = xj - xi;
+    const double k = fma(d, A.invL, RINT_MAGIC) - RINT_MAGIC;
+    const double d0 = fma(-k, A.L, d);
+    extra |= (fabs(d0) > A.thr) ? bit : 0u;
+    return d0;
+}
+
+// the same with a boolean "a second image may be inside" that accumulates over axes (one chained compare per axis)
+__device__ __forceinline__ double axis_nearest_any(double xi, double xj, const Axis &A, bool &extra) {
+    const double d = xj - xi;
+    const double k = fma(d, A.invL, RINT_MAGIC) - RINT_MAGIC;
+    const double d0 = fma(-k, A.L, d);
+    extra = extra || fabs(d0) > A.thr;
+    return d0;
 }
 
 // kept for the trajectory kernel: nearest and second image
@@ -259,6 +267,106 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const RV &R, c
     return cnt;
 }
 
+// Two-sided scan for a single-atom displacement (old and new position of atom i_excl): every neighbour that is inside the cutoff on
+// EITHER side gets an aligned PAIR of list slots, lr[pos] = -r2_old, lr[pos + 1] = +r2_new (a side that is outside keeps its
+// r2 >= cut_pre2 and evaluates to zero), so that one ballot / popc compaction serves both sides, the list of touched atoms
+// is simply l2[pos / 2] = j and the gather reads both terms with one 16-byte load.  The queue of second-image candidates
+// holds j only; the image flags are recomputed when the queue is expanded.
+template <class RV, class CELL>
+__device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const CELL &C, const int lane, const unsigned lt, int n_scan,
+                                         int i_excl, const double po[3], const double pn[3], int &n2, int &xstart, int &status) {
+    constexpr bool TRACK = RV::EMT;
+    static_assert(RV::CAPE % 2 == 0, "paired list slots need an even capacity");
+    uint32_t *queue = R.queue();
+    const bool p0 = C.per(0), p1 = C.per(1), p2 = C.per(2);
+    const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);
+    int cnt = 0, nq = 0;
+    for (int base = 0; base < n_scan; base += 32) {
+        const int j = base + lane;
+        const bool valid = j < n_scan && j != i_excl;
+        const int jc = valid ? j : 0;
+        const double xj = R.x(jc), yj = R.y(jc), zj = R.z(jc);
+        bool fo = false, fn = false;
+        const double dxo = axis_nearest_any(po[0], xj, A0, fo);
+        const double dyo = axis_nearest_any(po[1], yj, A1, fo);
+        const double dzo = axis_nearest_any(po[2], zj, A2, fo);
+        const double dxn = axis_nearest_any(pn[0], xj, A0, fn);
+        const double dyn = axis_nearest_any(pn[1], yj, A1, fn);
+        const double dzn = axis_nearest_any(pn[2], zj, A2, fn);
+        const double r2o = fma(dzo, dzo, fma(dyo, dyo, dxo * dxo));
+        const double r2n = fma(dzn, dzn, fma(dyn, dyn, dxn * dxn));
+        const bool in_o = valid && r2o < pot.cut_pre2, in_n = valid && r2n < pot.cut_pre2;
+        const bool any = in_o || in_n;
+        const unsigned b = __ballot_sync(FULL, any);
+        const int pos = min(cnt + 2 * __popc(b & lt), RV::CAPE - 2);
+        if (any) {
+            *reinterpret_cast<double2 *>(&R.lr(pos)) = make_double2(-r2o, r2n);
+            if (TRACK) R.l2(pos >> 1) = (uint16_t)j;
+        }
+        if (TRACK && valid) R.pp(j) = any ? ((unsigned)pos | ((unsigned)(pos + 1) << 16)) : (NOPOS | (NOPOS << 16));
+        cnt += 2 * __popc(b);
+        // second images: only if the nearest image is inside (it is the closest of all images)
+        const bool ex = (in_o && fo) || (in_n && fn);
+        const unsigned bq = __ballot_sync(FULL, ex);
+        if (ex) queue[min(nq + __popc(bq & lt), RV::QCAP - 1)] = (unsigned)j;
+        nq += __popc(bq);
+    }
+    if (cnt > RV::CAPE) {
+        status |= QMC_STATUS_LIST_OVERFLOW;
+        cnt = RV::CAPE;
+    }
+    n2 = cnt >> 1;
+    xstart = cnt;
+    if (nq > RV::QCAP) {
+        status |= QMC_STATUS_LIST_OVERFLOW;
+        nq = RV::QCAP;
+    }
+    if (nq > 0) {
+        __syncwarp();
+        for (int q0 = 0; q0 < nq; q0 += 32) {
+            const int q = q0 + lane;
+            const bool has = q < nq;
+            const int j = has ? (int)queue[q] : 0;
+            const double xj = R.x(j), yj = R.y(j), zj = R.z(j);
+#pragma unroll
+            for (int side = 0; side < 2; ++side) {
+                const double *p = side ? pn : po;
+                unsigned fl = 0;
+                const double dx0 = axis_nearest(p[0], xj, A0, p0, fl, 1u);
+                const double dy0 = axis_nearest(p[1], yj, A1, p1, fl, 2u);
+                const double dz0 = axis_nearest(p[2], zj, A2, p2, fl, 4u);
+                const double dx1 = dx0 - copysign(A0.L, dx0), dy1 = dy0 - copysign(A1.L, dy0), dz1 = dz0 - copysign(A2.L, dz0);
+                const double r20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
+                unsigned c = fl & (0u - fl);  // first non-empty subset of fl
+                bool more = has && fl != 0u && r20 < pot.cut_pre2;
+                while (__any_sync(FULL, more)) {
+                    const double dx = (c & 1u) ? dx1 : dx0, dy = (c & 2u) ? dy1 : dy0, dz = (c & 4u) ? dz1 : dz0;
+                    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                    const bool in = more && r2 < pot.cut_pre2;
+                    const unsigned b = __ballot_sync(FULL, in);
+                    const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
+                    if (in) {
+                        R.lr(pos) = side ? r2 : -r2;
+                        if (TRACK) R.xj(min(pos - xstart, RV::XCAPN - 1)) = (uint16_t)j;
+                    }
+                    cnt += __popc(b);
+                    if (more) {
+                        if (c == fl) more = false;
+                        else c = ((c | (~fl & 7u)) + 1u) & fl;
+                    }
+                }
+            }
+        }
+    }
+    if (cnt > RV::CAPE || (TRACK && cnt - xstart > RV::XCAPN)) {
+        status |= QMC_STATUS_LIST_OVERFLOW;
+        cnt = min(cnt, RV::CAPE);
+        if (TRACK && cnt - xstart > RV::XCAPN) cnt = xstart + RV::XCAPN;
+    }
+    __syncwarp();
+    return cnt;
+}
+
 // pairs: evaluate the list.  MODE 0 leaves the sigma_1 term of every nearest-image entry in lr[e], with the terms of
 // the second images of the same atom and side added onto it.
 template <class RV, int MODE>
@@ -268,13 +376,15 @@ __device__ __forceinline__ void eval_pass(const PotDev &pot, const RV &R, const 
     const int e = e0 + lane;
     const bool act = e < cnt;
     const double r2s = act ? R.lr(e) : 1.0e6;  // padding lanes sit far outside every cutoff: their terms come out as zero
-    const bool isnew = r2s > 0.0;
+    const bool isnew = __double2hiint(r2s) >= 0;
     const double r2 = fabs(r2s);
     if (RV::EMT) {
-        double s1, s2;
-        emt_pair(pot, r2, s1, s2);
-        acc.v = fma(copysign(1.0, r2s), s2, acc.v);
-        acc.snew += isnew ? s1 : 0.0;
+        double e1, e2, w;
+        const bool in = emt_pair_w(pot, r2, e1, e2, w);
+        const double s1 = e1 * w;
+        acc.v = fma(e2, copysign(w, r2s), acc.v);
+        if (isnew) acc.snew += s1;
+        acc.pairs += in ? 1 : 0;
         if (TRACK) {
             if (e0 + 32 <= xstart) {  // nearest images only: every entry owns its slot
                 R.lr(e) = s1;
@@ -304,9 +414,11 @@ __device__ __forceinline__ void eval_pass(const PotDev &pot, const RV &R, const 
             }
         }
     } else {
-        acc.v = fma(copysign(1.0, r2s), lj_pair(pot, r2), acc.v);
+        bool in;
+        const double e = lj_pair(pot, r2, in);
+        acc.v = fma(copysign(1.0, r2s), e, acc.v);
+        acc.pairs += (act && in) ? 1 : 0;
     }
-    acc.pairs += act ? 1 : 0;
 }
 
 template <class RV, int MODE>

@@ -182,6 +182,57 @@ __device__ __forceinline__ void commit_trial(const Rep<LY> &R, const int lane, c
     __syncwarp();
 }
 
+// Displacement of one atom (both sides present): paired list slots (scan_both).  Touched atom l2[e] owns the slots 2e (old term)
+// and 2e + 1 (new term); after the embedding pass they hold its trial sigma_1 and trial embedding energy.
+template <class LY, class CELL>
+__device__ __forceinline__ Trial local_delta_move(const PotDev &pot, const Rep<LY> &R, const CELL &C, const int lane, const unsigned lt,
+                                                  int n_scan, int i, const double po[3], const double pn[3], int &status) {
+    Trial T;
+    DeltaAcc acc = {0.0, 0.0, 0};
+    int xstart;
+    const int cnt = scan_both<Rep<LY>>(pot, R, C, lane, lt, n_scan, i, po, pn, T.n2, xstart, status);
+    eval_list<Rep<LY>, 0>(pot, R, lane, cnt, xstart, acc);
+    const double vs = warp_sum(acc.v);
+    T.pairs = acc.pairs;
+    T.sig_i = 0.0;
+    T.eat_i = 0.0;
+    if (!LY::EMT) {
+        T.dE = vs;  // E = 1/2 sum_i sum_j e_ij: the moved atom's row and column change together
+        return T;
+    }
+    T.sig_i = warp_sum(acc.snew);
+    double part = 0.0, e_i_lane = 0.0;
+    double2 *slots = reinterpret_cast<double2 *>(&R.lr(0));
+    for (int e = lane; e <= T.n2; e += 32) {
+        const bool nb = e < T.n2;
+        const int j = nb ? R.l2(e) : i;
+        const double2 t = nb ? slots[e] : make_double2(0.0, 0.0);
+        const double sn = nb ? R.sig(j) + (t.y - t.x) : T.sig_i;
+        const double en = emt_embed(pot, sn);
+        part += en - R.eat(j);
+        if (nb) slots[e] = make_double2(sn, en);
+        else e_i_lane = en;
+    }
+    T.eat_i = __shfl_sync(FULL, e_i_lane, T.n2 & 31);
+    // pair part: rows (i, j) and (j, i) change together: 2 * 0.5 * (es + eo) = 2 * neghalfv0overgamma2 * dsigma2
+    T.dE = warp_sum(part) + 2.0 * pot.neghalfv0overgamma2 * vs;
+    __syncwarp();
+    return T;
+}
+
+template <class LY>
+__device__ __forceinline__ void commit_move(const Rep<LY> &R, const int lane, const Trial &T) {
+    if (!LY::EMT) return;
+    const double2 *slots = reinterpret_cast<const double2 *>(&R.lr(0));
+    for (int e = lane; e < T.n2; e += 32) {
+        const int j = R.l2(e);
+        const double2 t = slots[e];
+        R.sig(j) = t.x;
+        R.eat(j) = t.y;
+    }
+    __syncwarp();
+}
+
 // GrandCanonicalCriteria.evaluate (mc/criteria.py:243-278): criteria * prefactor
 __device__ inline double gc_probability(double dE, int delta, int n_ex, double acc_volume, double mass, double temperature,
                                         double mu, bool &overflow) {
@@ -349,12 +400,12 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                 }
                 const double po[3] = {R.x(i), R.y(i), R.z(i)};
                 const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
-                const Trial T = local_delta<LY>(pot, R, C, lane, lt, R.n, i, true, true, po, pn, status);
+                const Trial T = local_delta_move<LY>(pot, R, C, lane, lt, R.n, i, po, pn, status);
                 n_pairs += T.pairs;
                 delta = T.dE;
                 const bool acc = metropolis(D.u_accept, -delta / kT, status);
                 if (acc) {
-                    commit_trial<LY>(R, lane, T);
+                    commit_move<LY>(R, lane, T);
                     if (lane == 0) {
                         R.x(i) = pn[0];
                         R.y(i) = pn[1];
