@@ -34,6 +34,8 @@ constexpr int kScanUnroll = 1;
 #endif
 constexpr int XCAP = 64;             // capacity for second-image list entries of one attempt
 constexpr unsigned NOPOS = 0xFFFFu;  // pp half-word: no list entry
+constexpr unsigned NOITEM = 0xFFFFFFFFu;  // queue word: empty
+constexpr int DRAW_AHEAD = 4;  // attempts whose random numbers one Philox round of the warp produces (4 lanes per attempt)
 constexpr int SMEM_PER_SM = 232448;  // 227 KB usable per SM on sm_100
 constexpr int SMEM_PER_CTA_MAX = 232448 - 1024;
 
@@ -58,7 +60,8 @@ struct Layout {
     static constexpr int PP_B = (CELLC + 10) * 8;  // bytes
     static constexpr int L2_B = PP_B + (EMT ? NS * 4 : 0);
     static constexpr int XJ_B = L2_B + (EMT ? NS * 2 : 0);
-    static constexpr int BYTES = round_up(XJ_B + (EMT ? XCAP * 2 : 0), 16);
+    static constexpr int DRAW_B = round_up(XJ_B + (EMT ? XCAP * 2 : 0), 16);  // DRAW_AHEAD attempts x 4 Philox blocks x 2 doubles
+    static constexpr int BYTES = DRAW_B + DRAW_AHEAD * 64;
     // launch geometry: ONE wide CTA per SM holding as many replicas (warps) as shared memory and the 72-register budget allow.
     // Measured on B200 (4096 x 108-atom Cu EMT): 7 CTAs x 4 warps 3.10e8 attempts/s, 2 x 14 warps 3.35e8, 1 x 28 warps 3.68e8 --
     // the warp schedulers favour the warps of older CTAs, so replicas in separate CTAs finish 0.77 .. 1.39 ms into a 1.43 ms launch
@@ -95,6 +98,7 @@ struct Rep {
     __device__ __forceinline__ uint32_t &pp(int j) const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(b) + LY::PP_B)[j]; }
     __device__ __forceinline__ uint16_t &l2(int e) const { return reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(b) + LY::L2_B)[e]; }
     __device__ __forceinline__ uint16_t &xj(int e) const { return reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(b) + LY::XJ_B)[e]; }
+    __device__ __forceinline__ double2 *draws() const { return reinterpret_cast<double2 *>(reinterpret_cast<char *>(b) + LY::DRAW_B); }
 };
 
 // cell constants of one axis: edge, 1 / edge, edge - cutoff' (a second image can be inside the cutoff iff |d| > thr)
@@ -305,11 +309,13 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
         }
         if (TRACK && valid) R.pp(j) = any ? ((unsigned)pos | ((unsigned)(pos + 1) << 16)) : (NOPOS | (NOPOS << 16));
         cnt += 2 * __popc(b);
-        // second images: only if the nearest image is inside (it is the closest of all images)
-        const bool ex = (in_o && fo) || (in_n && fn);
-        const unsigned bq = __ballot_sync(FULL, ex);
-        if (ex) queue[min(nq + __popc(bq & lt), RV::QCAP - 1)] = (unsigned)j;
-        nq += __popc(bq);
+        // second images: only if the nearest image is inside (it is the closest of all images).  A flagged lane pushes two
+        // queue words (old side, new side; NOITEM for a side that is not flagged): at most 2 (n - 1) < QCAP words in total.
+        const bool exo = in_o && fo, exn = in_n && fn;
+        const unsigned bq = __ballot_sync(FULL, exo || exn);
+        if (exo || exn)
+            *reinterpret_cast<uint2 *>(queue + nq + 2 * __popc(bq & lt)) = make_uint2(exo ? (unsigned)j : NOITEM, exn ? ((unsigned)j | 0x8000u) : NOITEM);
+        nq += 2 * __popc(bq);
     }
     if (cnt > RV::CAPE) {
         status |= QMC_STATUS_LIST_OVERFLOW;
@@ -317,43 +323,35 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
     }
     n2 = cnt >> 1;
     xstart = cnt;
-    if (nq > RV::QCAP) {
-        status |= QMC_STATUS_LIST_OVERFLOW;
-        nq = RV::QCAP;
-    }
     if (nq > 0) {
         __syncwarp();
         for (int q0 = 0; q0 < nq; q0 += 32) {
             const int q = q0 + lane;
-            const bool has = q < nq;
-            const int j = has ? (int)queue[q] : 0;
-            const double xj = R.x(j), yj = R.y(j), zj = R.z(j);
-#pragma unroll
-            for (int side = 0; side < 2; ++side) {
-                const double *p = side ? pn : po;
-                unsigned fl = 0;
-                const double dx0 = axis_nearest(p[0], xj, A0, p0, fl, 1u);
-                const double dy0 = axis_nearest(p[1], yj, A1, p1, fl, 2u);
-                const double dz0 = axis_nearest(p[2], zj, A2, p2, fl, 4u);
-                const double dx1 = dx0 - copysign(A0.L, dx0), dy1 = dy0 - copysign(A1.L, dy0), dz1 = dz0 - copysign(A2.L, dz0);
-                const double r20 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
-                unsigned c = fl & (0u - fl);  // first non-empty subset of fl
-                bool more = has && fl != 0u && r20 < pot.cut_pre2;
-                while (__any_sync(FULL, more)) {
-                    const double dx = (c & 1u) ? dx1 : dx0, dy = (c & 2u) ? dy1 : dy0, dz = (c & 4u) ? dz1 : dz0;
-                    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                    const bool in = more && r2 < pot.cut_pre2;
-                    const unsigned b = __ballot_sync(FULL, in);
-                    const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
-                    if (in) {
-                        R.lr(pos) = side ? r2 : -r2;
-                        if (TRACK) R.xj(min(pos - xstart, RV::XCAPN - 1)) = (uint16_t)j;
-                    }
-                    cnt += __popc(b);
-                    if (more) {
-                        if (c == fl) more = false;
-                        else c = ((c | (~fl & 7u)) + 1u) & fl;
-                    }
+            const unsigned item = q < nq ? queue[q] : NOITEM;
+            const bool has = item != NOITEM;
+            const int j = has ? (int)(item & 0x7FFFu) : 0;
+            const bool side = (item & 0x8000u) != 0u;  // false: old position, true: new position
+            unsigned fl = 0;
+            const double dx0 = axis_nearest(side ? pn[0] : po[0], R.x(j), A0, p0, fl, 1u);
+            const double dy0 = axis_nearest(side ? pn[1] : po[1], R.y(j), A1, p1, fl, 2u);
+            const double dz0 = axis_nearest(side ? pn[2] : po[2], R.z(j), A2, p2, fl, 4u);
+            const double dx1 = dx0 - copysign(A0.L, dx0), dy1 = dy0 - copysign(A1.L, dy0), dz1 = dz0 - copysign(A2.L, dz0);
+            unsigned c = fl & (0u - fl);  // first non-empty subset of fl
+            bool more = has && fl != 0u;
+            while (__any_sync(FULL, more)) {
+                const double dx = (c & 1u) ? dx1 : dx0, dy = (c & 2u) ? dy1 : dy0, dz = (c & 4u) ? dz1 : dz0;
+                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                const bool in = more && r2 < pot.cut_pre2;
+                const unsigned b = __ballot_sync(FULL, in);
+                const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
+                if (in) {
+                    R.lr(pos) = side ? r2 : -r2;
+                    if (TRACK) R.xj(min(pos - xstart, RV::XCAPN - 1)) = (uint16_t)j;
+                }
+                cnt += __popc(b);
+                if (more) {
+                    if (c == fl) more = false;
+                    else c = ((c | (~fl & 7u)) + 1u) & fl;
                 }
             }
         }

@@ -274,6 +274,33 @@ __device__ __forceinline__ Draws draw_attempt(PhiloxKey key, unsigned long long 
     return D;
 }
 
+// The same numbers, DRAW_AHEAD attempts at a time: lane 4 a + b runs Philox block b of attempt k0 + a and parks its two doubles
+// in shared memory; every attempt then reads its seven doubles with broadcast loads.  One Philox evaluation per
+// DRAW_AHEAD attempts instead of one per attempt; the values are identical (keyed by attempt index, not by call order).
+template <class RV>
+__device__ __forceinline__ void draw_ahead(const RV &R, PhiloxKey key, unsigned long long attempt0, uint32_t replica, const int lane) {
+    double d0, d1;
+    uniform_pair(key, attempt0 + (unsigned long long)((lane >> 2) & (DRAW_AHEAD - 1)), replica, (uint32_t)(lane & 3), d0, d1);
+    __syncwarp();
+    if (lane < 4 * DRAW_AHEAD) R.draws()[lane] = make_double2(d0, d1);
+    __syncwarp();
+}
+
+template <class RV>
+__device__ __forceinline__ Draws read_draws(const RV &R, int a, bool need_coin) {
+    const double2 *d = R.draws() + 4 * a;
+    const double2 b0 = d[0], b1 = d[1], b2 = d[2];
+    Draws D;
+    D.u_select = b0.x;
+    D.u_label = b0.y;
+    D.o0 = b1.x;
+    D.o1 = b1.y;
+    D.o2 = b2.x;
+    D.u_accept = b2.y;
+    D.u_coin = need_coin ? d[3].x : 0.0;
+    return D;
+}
+
 // per-replica cell constants in shared memory (F_CELLVAR); returns false if an edge is below the cutoff
 template <class LY>
 __device__ __forceinline__ bool store_cell(const Rep<LY> &R, const double diag[3], const int pbc[3], double cut_pre, int lane) {
@@ -360,7 +387,9 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
 
     for (int k = k_begin; k < k_end; ++k) {
         const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
-        const Draws D = draw_attempt(key, attempt, grep, lane, (FEAT & F_EXCHANGE) != 0);
+        const int ahead = (k - k_begin) & (DRAW_AHEAD - 1);
+        if (ahead == 0) draw_ahead(R, key, attempt, grep, lane);
+        const Draws D = read_draws(R, ahead, (FEAT & F_EXCHANGE) != 0);
 
         int m = 0;
         while (m < a.n_moves - 1 && a.cdf[m] <= D.u_select) ++m;
