@@ -109,7 +109,9 @@ __device__ __forceinline__ double emt_embed(const PotDev &p, double sigma1) {
     const double sg = sigma1 > 1e-14 ? sigma1 : 1.0;
     const double ds = log_fast(sg * p.inv12gamma1) * p.neg_inv_beta_eta2;
     const double x = p.lambda * ds;
-    const double e = p.E0 * (1.0 + x) * exp_fast(-x) + p.V0x6 * exp_fast(-p.kappa * ds) - p.E0;
+    double ex, ek;
+    exp2_fast(-x, -p.kappa * ds, ex, ek);
+    const double e = p.E0 * (1.0 + x) * ex + p.V0x6 * ek - p.E0;
     return sigma1 > 1e-14 ? e : -p.E0;
 }
 

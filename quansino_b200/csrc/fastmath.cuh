@@ -42,14 +42,11 @@ __device__ __forceinline__ double rcp_fast(double d) {
 __device__ __forceinline__ double sqrt_fast(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double g = x * y, h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
+    double g = x * y, h = 0.5 * y;  // g ~ sqrt(x), h ~ 1 / (2 sqrt(x)), relative error ~2^-20
+    const double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);  // ~2^-39
     h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    const double d = fma(-g, g, x);
+    const double d = fma(-g, g, x);  // exact residual: the correction is one more Newton step (~2^-77 before rounding)
     return fma(d, h, g);
 }
 
@@ -62,10 +59,28 @@ __device__ __forceinline__ double exp_fast(double x) {
     double q = FM_EXP[9];
 #pragma unroll
     for (int i = 8; i >= 0; --i) q = fma(q, r, FM_EXP[i]);
-    const double r2 = r * r;
-    const double p = fma(r2, q, r) + 1.0;
+    const double p = fma(r, fma(r, q, 1.0), 1.0);
     const int n = __double2loint(t);
     return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+}
+
+// two exponentials in lockstep
+__device__ __forceinline__ void exp2_fast(double x0, double x1, double &e0, double &e1) {
+    const double t0 = fma(x0, 1.4426950408889634, FM_MAGIC), t1 = fma(x1, 1.4426950408889634, FM_MAGIC);
+    const double k0 = t0 - FM_MAGIC, k1 = t1 - FM_MAGIC;
+    double r0 = fma(k0, -FM_LN2_HI, x0), r1 = fma(k1, -FM_LN2_HI, x1);
+    r0 = fma(k0, -FM_LN2_LO, r0);
+    r1 = fma(k1, -FM_LN2_LO, r1);
+    double q0 = FM_EXP[9], q1 = FM_EXP[9];
+#pragma unroll
+    for (int i = 8; i >= 0; --i) {
+        const double c = FM_EXP[i];
+        q0 = fma(q0, r0, c);
+        q1 = fma(q1, r1, c);
+    }
+    const double p0 = fma(r0, fma(r0, q0, 1.0), 1.0), p1 = fma(r1, fma(r1, q1, 1.0), 1.0);
+    e0 = __hiloint2double(__double2hiint(p0) + (__double2loint(t0) << 20), __double2loint(p0));
+    e1 = __hiloint2double(__double2hiint(p1) + (__double2loint(t1) << 20), __double2loint(p1));
 }
 
 // three exponentials in lockstep: one coefficient fetch per Horner step serves all three chains
@@ -85,7 +100,7 @@ __device__ __forceinline__ void exp3_fast(double x0, double x1, double x2, doubl
         q1 = fma(q1, r1, c);
         q2 = fma(q2, r2, c);
     }
-    const double p0 = fma(r0 * r0, q0, r0) + 1.0, p1 = fma(r1 * r1, q1, r1) + 1.0, p2 = fma(r2 * r2, q2, r2) + 1.0;
+    const double p0 = fma(r0, fma(r0, q0, 1.0), 1.0), p1 = fma(r1, fma(r1, q1, 1.0), 1.0), p2 = fma(r2, fma(r2, q2, 1.0), 1.0);
     e0 = __hiloint2double(__double2hiint(p0) + (__double2loint(t0) << 20), __double2loint(p0));
     e1 = __hiloint2double(__double2hiint(p1) + (__double2loint(t1) << 20), __double2loint(p1));
     e2 = __hiloint2double(__double2hiint(p2) + (__double2loint(t2) << 20), __double2loint(p2));

@@ -379,6 +379,8 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
     double E = __ldcg(a.b.energy + r);
     const double temperature = a.b.temperature[r];
     const double kT = temperature * KB;
+    const double inv_kT = 1.0 / kT;  // the acceptance exponents multiply by this (<= 1 ulp from the reference's division)
+    if (lane < QMC_MAX_MOVES * 3) R.counts()[lane] = 0u;
     int n_ex = (FEAT & F_EXCHANGE) ? __ldcg(a.b.n_exchange + r) : 0;
     const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
     const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                 const Trial T = local_delta_move<LY>(pot, R, C, lane, lt, R.n, i, po, pn, status);
                 n_pairs += T.pairs;
                 delta = T.dE;
-                const bool acc = metropolis(D.u_accept, -delta / kT, status);
+                const bool acc = metropolis(D.u_accept, -delta * inv_kT, status);
                 if (acc) {
                     commit_move<LY>(R, lane, T);
                     if (lane == 0) {
@@ -579,10 +581,10 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
         }
 
         if (lane == 0) {
-            unsigned long long *cnt = reinterpret_cast<unsigned long long *>(a.b.counters) + ((size_t)r * QMC_MAX_MOVES + m) * 3;
-            atomicAdd(cnt + 0, 1ull);
-            if (accepted == 1) atomicAdd(cnt + 1, 1ull);
-            if (accepted < 0) atomicAdd(cnt + 2, 1ull);
+            uint32_t *cnt = R.counts() + m * 3;  // flushed to the global counters when the replica is stored
+            cnt[0] += 1u;
+            if (accepted == 1) cnt[1] += 1u;
+            if (accepted < 0) cnt[2] += 1u;
             if (a.has_trace) {
                 const size_t ti = (size_t)r * a.n_attempts + k;
                 if (a.tr.move) a.tr.move[ti] = (int8_t)m;
@@ -604,6 +606,10 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
             gs[j] = R.sig(j);
             ge[j] = R.eat(j);
         }
+    }
+    if (lane < QMC_MAX_MOVES * 3) {
+        const uint32_t c = R.counts()[lane];
+        if (c) atomicAdd(reinterpret_cast<unsigned long long *>(a.b.counters) + (size_t)r * QMC_MAX_MOVES * 3 + lane, (unsigned long long)c);
     }
     if (lane == 0) {
         a.b.n_atoms[r] = R.n;
