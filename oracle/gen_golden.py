@@ -34,6 +34,7 @@ from ase.calculators.emt import EMT  # noqa: E402
 from ase.calculators.lj import LennardJones  # noqa: E402
 from quansino.integrators.displacement import Verlet  # noqa: E402
 from quansino.mc.canonical import Canonical, HamiltonianCanonical  # noqa: E402
+from quansino.mc.criteria import CanonicalCriteria  # noqa: E402
 from quansino.mc.gcmc import GrandCanonical  # noqa: E402
 from quansino.mc.isobaric import Isobaric  # noqa: E402
 from quansino.moves.cell import CellMove  # noqa: E402
@@ -101,6 +102,38 @@ def case_canonical(opname, op, seed, steps):
     return dict(
         kind="canonical", op=opname, step_size=0.1, seed=seed, replica=3, temperature=300.0, positions0=pos0, cell=cell,
         positions=atoms.positions.copy(), n_calculations=atoms.calc.n_calculations, **tr,
+    )  # fmt: skip
+
+
+def case_composite(variant, seed, n_attempts):
+    """CompositeDisplacementMove (moves/displacement.py:363-455) built with the reference's own `*` and `+`."""
+    atoms, pos0, cell = cu_atoms(3, 0.05, 5151)
+    n = len(atoms)
+    labels = np.arange(n)
+    if variant == "mul":  # a plain move and a triple move, selected with equal probability
+        mc = Canonical(atoms, temperature=300.0, max_cycles=n_attempts, default_displacement_move=DisplacementMove(labels, Ball(0.1)))
+        mc.add_move(DisplacementMove(labels, Ball(0.06)) * 3, criteria=CanonicalCriteria(), name="triple", probability=1.0)
+        spec = [[("Ball", 0.1, 1)], [("Ball", 0.06, 3)]]
+    elif variant == "add":  # three different operations in one composite
+        mc = Canonical(atoms, temperature=300.0, max_cycles=n_attempts)
+        mc.add_move(DisplacementMove(labels, Ball(0.08)) + DisplacementMove(labels, Box(0.04)) + DisplacementMove(labels, Sphere(0.05)),
+                    criteria=CanonicalCriteria(), name="mixed")  # fmt: skip
+        spec = [[("Ball", 0.08, 1), ("Box", 0.04, 1), ("Sphere", 0.05, 1)]]
+    elif variant == "exhaust":  # only two movable atoms: the third and fourth sub-moves find no candidate
+        labels = np.full(n, -1)
+        labels[7] = 0
+        labels[40] = 1
+        mc = Canonical(atoms, temperature=300.0, max_cycles=n_attempts)
+        mc.add_move(DisplacementMove(labels, Ball(0.1)) * 4, criteria=CanonicalCriteria(), name="four")
+        spec = [[("Ball", 0.1, 4)]]
+    else:
+        raise ValueError(variant)
+    inject(mc, seed, 4)
+    tr = run_steps(mc, 1)
+    flat = np.array([(i, ["Ball", "Box", "Sphere"].index(o), s, r) for i, chain in enumerate(spec) for (o, s, r) in chain], dtype=float)
+    return dict(
+        kind="composite", variant=variant, seed=seed, replica=4, temperature=300.0, positions0=pos0, cell=cell, labels=labels,
+        spec=flat, probabilities=np.array([mc.moves[k].probability for k in mc.moves]), positions=atoms.positions.copy(), **tr,
     )  # fmt: skip
 
 
@@ -195,6 +228,9 @@ def main():
         "gc_lj": lambda: case_gc_lj(3001, 700, -0.5),
         "gc_emt": lambda: case_gc_emt(3002, 150, -3.4, 3000.0),
         "hmc": lambda: case_hmc(4001, 3, 2.0, 12, 800.0),
+        "composite_mul": lambda: case_composite("mul", 5001, 120),
+        "composite_add": lambda: case_composite("add", 5002, 80),
+        "composite_exhaust": lambda: case_composite("exhaust", 5003, 40),
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():

@@ -20,6 +20,9 @@ Layout (DESIGN.md section "Random stream"):
     block 2: d0 = operation draw 2           (Ball: cos(theta) -- ``:148``)
              d1 = u_accept                   (``mc/criteria.py:108``)
     block 3: d0 = u_coin  (insert / delete, ``moves/exchange.py:148``)   d1 = u_swap (parallel tempering)
+    block 32 + 2 (c - 1), 33 + 2 (c - 1): sub-move c >= 1 of a CompositeDisplacementMove (``moves/displacement.py:392-431``;
+             c counts the sub-moves that draw, the first one uses the standard slots above):
+             (u_label, operation draw 0) and (operation draw 1, operation draw 2)
     block 16 + p: Box-Muller pair p of the 3N momentum normals (``utils/dynamics.py:31``), row-major:
              normal m = 3*atom + axis lives in pair p = m // 2; z_even = r cos(t), z_odd = r sin(t),
              r = sqrt(-2 ln(1 - d0)), t = 2 pi d1.
@@ -39,6 +42,7 @@ BLOCK_OP01 = 1
 BLOCK_OP2_ACCEPT = 2
 BLOCK_COIN_SWAP = 3
 BLOCK_NORMALS = 16
+BLOCK_COMPOSITE = 32
 
 _MASK = 0xFFFFFFFF
 
@@ -86,7 +90,9 @@ class InjectedStream:
     of the current attempt, in the order the reference makes them:
 
     * ``choice(a, p=p)``            -> new attempt; u_select; ``searchsorted(cumsum(p), u, 'right')``
-    * ``choice(a)`` (no ``p``)      -> u_label; ``a[floor(u * len(a))]``
+    * ``choice(a)`` (no ``p``)      -> u_label; ``a[floor(u * len(a))]``.  The c-th such call of an attempt (c >= 1, only
+                                       ``CompositeDisplacementMove`` makes more than one) starts sub-move c: its label and
+                                       operation draws come from blocks 32 + 2 (c - 1) and 33 + 2 (c - 1)
     * ``choice(arange, size=0, replace=False)`` -> consumes nothing (forced-move placement, unsupported > 0)
     * ``uniform(lo, hi, size)``     -> operation draws, in call order: ``lo + (hi - lo) * u``
     * ``random()``                  -> u_coin when it is the FIRST draw after the selection (only
@@ -101,6 +107,7 @@ class InjectedStream:
         self.attempt = int(attempt_base) - 1
         self._op_draws = 0
         self._calls = 0
+        self._labels = 0  # label draws of this attempt
         self.log: list[tuple[str, float]] = []
 
     # -- slots ---------------------------------------------------------------------------------
@@ -111,11 +118,19 @@ class InjectedStream:
         self.attempt += 1
         self._op_draws = 0
         self._calls = 0
+        self._labels = 0
 
     def _op_draw(self) -> float:
         k = self._op_draws
         self._op_draws += 1
         self._calls += 1
+        if self._labels > 1:  # sub-move c = _labels - 1 >= 1 of a composite displacement move
+            c = self._labels - 1
+            if k == 0:
+                return self._pair(BLOCK_COMPOSITE + 2 * (c - 1))[1]
+            if k in (1, 2):
+                return self._pair(BLOCK_COMPOSITE + 2 * (c - 1) + 1)[k - 1]
+            raise RuntimeError("more than three operation draws in one sub-move: not a supported operation")
         if k == 0:
             return self._pair(BLOCK_OP01)[0]
         if k == 1:
@@ -139,7 +154,10 @@ class InjectedStream:
             cdf /= cdf[-1]
             return a[int(np.searchsorted(cdf, u, side="right"))]
         self._calls += 1
-        u = self._pair(BLOCK_SELECT_LABEL)[1]
+        self._labels += 1
+        self._op_draws = 0
+        c = self._labels - 1
+        u = self._pair(BLOCK_SELECT_LABEL)[1] if c == 0 else self._pair(BLOCK_COMPOSITE + 2 * (c - 1))[0]
         self.log.append(("label", u))
         return a[int(u * len(a))]
 

@@ -436,9 +436,14 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
 
     /* yield_moves (mc/core.py:340-349): probabilities normalised, numpy choice(p=) = searchsorted(cdf, u, 'right') */
     {
+        /* a composite move is ONE MoveStorage: only the head of a chain carries a probability */
         double tot = 0.0, acc = 0.0;
-        for (int m = 0; m < n_moves; ++m) tot += moves[m].probability;
-        for (int m = 0; m < n_moves; ++m) { acc += moves[m].probability / tot; cdf[m] = acc; }
+        for (int m = 0; m < n_moves; ++m)
+            if (m == 0 || !moves[m - 1].chain) tot += moves[m].probability;
+        for (int m = 0; m < n_moves; ++m) {
+            if (m == 0 || !moves[m - 1].chain) acc += moves[m].probability / tot;
+            cdf[m] = acc;
+        }
         double last = cdf[n_moves - 1];
         for (int m = 0; m < n_moves; ++m) cdf[m] /= last;
     }
@@ -460,7 +465,77 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
         int accepted = -1, moved = -1;
         double delta = NAN;
 
-        if (mv->type == QO_MOVE_DISPLACEMENT) {
+        if (mv->type == QO_MOVE_DISPLACEMENT && (mv->repeat > 1 || mv->chain)) {
+            /* CompositeDisplacementMove.__call__ (moves/displacement.py:392-431): every sub-move picks a label nobody
+             * displaced yet in this composite (rng.choice over the sorted set difference), sub-moves without candidates
+             * fail silently; then ONE CanonicalCriteria.evaluate on the whole displacement (mc/core.py:369-377).
+             * Draws: the first drawing sub-move uses the standard slots, drawing sub-move c >= 1 uses
+             * block 32 + 2 (c - 1) = (u_label, op draw 0) and block 33 + 2 (c - 1) = (op draw 1, op draw 2). */
+            memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
+            int n_moved = 0, c = 0; /* disp[]: label VALUES displaced so far (the reference compares labels, not atoms) */
+            int *disp = (int *)malloc(sizeof(int) * (size_t)(n + 1));
+            if (!disp) { rc = -1; goto done; }
+            for (int mm = m; mm < n_moves; ++mm) {
+                qo_move_t *sm = &moves[mm];
+                if (sm->type != QO_MOVE_DISPLACEMENT) { free(disp); rc = -1; goto done; }
+                const int reps = sm->repeat > 0 ? sm->repeat : 1;
+                for (int rep_i = 0; rep_i < reps; ++rep_i) {
+                    int nu = unique_labels(sm->labels, n, uniq);
+                    int na = 0;
+                    for (int q = 0; q < nu; ++q) { /* setdiff1d(unique_labels, displaced_labels): sorted, as unique_labels is */
+                        int taken = 0;
+                        for (int d = 0; d < n_moved; ++d) taken |= disp[d] == uniq[q];
+                        if (!taken) uniq[na++] = uniq[q];
+                    }
+                    if (na == 0) continue; /* register_failure, nothing drawn */
+                    double ul, od[3];
+                    if (c == 0) { ul = u_label; od[0] = opd[0]; od[1] = opd[1]; od[2] = opd[2]; }
+                    else {
+                        double e0[2], e1[2];
+                        qo_uniform_pair(seed, attempt, replica, (uint32_t)(32 + 2 * (c - 1)), e0);
+                        qo_uniform_pair(seed, attempt, replica, (uint32_t)(33 + 2 * (c - 1)), e1);
+                        ul = e0[0]; od[0] = e0[1]; od[1] = e1[0]; od[2] = e1[1];
+                    }
+                    ++c;
+                    const int label = uniq[(int)(ul * (double)na)];
+                    int a = atom_of_label(sm->labels, n, label);
+                    if (a < 0) { free(disp); rc = -2; goto done; }
+                    double t[3];
+                    if (sm->op == QO_OP_BALL) {
+                        double r = 0.0 + (sm->step - 0.0) * od[0];
+                        double phi = 0.0 + (TWO_PI - 0.0) * od[1];
+                        double cc = -1.0 + (1.0 - -1.0) * od[2];
+                        double s = sqrt(1 - cc * cc);
+                        t[0] = r * s * cos(phi); t[1] = r * s * sin(phi); t[2] = r * cc;
+                    } else if (sm->op == QO_OP_SPHERE) {
+                        double phi = 0.0 + (TWO_PI - 0.0) * od[0];
+                        double cc = -1.0 + (1.0 - -1.0) * od[1];
+                        double s = sqrt(1 - cc * cc);
+                        t[0] = sm->step * (s * cos(phi)); t[1] = sm->step * (s * sin(phi)); t[2] = sm->step * cc;
+                    } else if (sm->op == QO_OP_BOX) {
+                        for (int x = 0; x < 3; ++x) t[x] = -sm->step + (sm->step - -sm->step) * od[x];
+                    } else { free(disp); rc = -1; goto done; }
+                    for (int x = 0; x < 3; ++x) trial[3 * a + x] = trial[3 * a + x] + t[x];
+                    disp[n_moved++] = label;
+                    moved = a;
+                }
+                if (!sm->chain) break;
+            }
+            free(disp);
+            if (n_moved > 0) {
+                double e_new;
+                int64_t np_ = qo_energy(pot, n, trial, st->cell, st->pbc, &e_new, NULL, NULL);
+                cnt[0] += np_; cnt[3] += 1;
+                delta = e_new - st->last_energy;
+                double x = -delta / kT;
+                if (x > 709.782712893384) { rc = -4; goto done; }
+                accepted = u_accept < exp(x);
+                if (accepted) {
+                    memcpy(st->pos, trial, sizeof(double) * 3 * (size_t)n);
+                    st->last_energy = e_new;
+                }
+            }
+        } else if (mv->type == QO_MOVE_DISPLACEMENT) {
             int nu = unique_labels(mv->labels, n, uniq);
             if (nu > 0) {
                 int label = uniq[(int)(u_label * (double)nu)];

@@ -49,6 +49,8 @@ class Move(C.Structure):
         ("dt", C.c_double),
         ("n_steps", C.c_int32),
         ("default_label", C.c_int32),
+        ("repeat", C.c_int32),
+        ("chain", C.c_int32),
         ("labels", C.c_void_p),
     ]
 

@@ -239,12 +239,20 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     std::memset(&a, 0, sizeof(a));
     if ((rc = make_potdev(pot, a.pot))) return rc;
     a.b = *batch;
-    bool any_exchange = false;
+    bool any_exchange = false, any_composite = false;
     double tot = 0.0;
     for (int m = 0; m < n_moves; ++m) {
         const qmc_move_t &mv = moves[m];
-        if (!(mv.probability >= 0.0)) return fail(QMC_ERR_INVALID, "move %d: negative probability", m);
-        tot += mv.probability;
+        const bool head = m == 0 || !moves[m - 1].chain;  // a composite move carries ONE probability, on its first entry
+        if (head && !(mv.probability >= 0.0)) return fail(QMC_ERR_INVALID, "move %d: negative probability", m);
+        if (head) tot += mv.probability;
+        if (mv.repeat < 0) return fail(QMC_ERR_INVALID, "move %d: negative repeat", m);
+        if (mv.chain && m + 1 == n_moves) return fail(QMC_ERR_INVALID, "move %d: chain = 1 on the last table entry", m);
+        if ((mv.chain || !head || mv.repeat > 1) && mv.type != QMC_MOVE_DISPLACEMENT)
+            return fail(QMC_ERR_UNSUPPORTED, "move %d: only displacement moves can form a composite move on the GPU path", m);
+        if (!head && mv.labels != moves[m - 1].labels)
+            return fail(QMC_ERR_UNSUPPORTED, "move %d: the sub-moves of a composite move must share one label array", m);
+        any_composite |= mv.chain || mv.repeat > 1;
         switch (mv.type) {
             case QMC_MOVE_DISPLACEMENT:
                 if (mv.op != QMC_OP_BALL && mv.op != QMC_OP_BOX && mv.op != QMC_OP_SPHERE)
@@ -270,6 +278,8 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         a.mv[m].step = mv.step;
         a.mv[m].bias = mv.bias_insert;
         a.mv[m].default_label = mv.default_label;
+        a.mv[m].repeat = mv.repeat > 0 ? mv.repeat : 1;
+        a.mv[m].chain = mv.chain ? 1 : 0;
         a.mv[m].labels = mv.labels;
     }
     if (!(tot > 0.0)) return fail(QMC_ERR_INVALID, "move probabilities sum to zero");
@@ -280,8 +290,8 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     // mc/core.py:344-347 + numpy choice(p=): p /= sum(p); cdf = cumsum(p); cdf /= cdf[-1]
     double acc = 0.0;
     for (int m = 0; m < n_moves; ++m) {
-        acc += moves[m].probability / tot;
-        a.cdf[m] = acc;
+        if (m == 0 || !moves[m - 1].chain) acc += moves[m].probability / tot;
+        a.cdf[m] = acc;  // the later entries of a chain repeat the head's value: searchsorted never lands on them
     }
     for (int m = 0; m < n_moves; ++m) a.cdf[m] /= acc;
     a.n_moves = n_moves;
@@ -299,6 +309,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         if (moves[m].type == QMC_MOVE_CELL) feat |= qmc::F_CELL | qmc::F_CELLVAR;
         if (moves[m].type == QMC_MOVE_EXCHANGE) feat |= qmc::F_EXCHANGE;
     }
+    if (any_composite) feat |= qmc::F_COMPOSITE;
     if ((rc = fill_cell_args(batch, a.pot, a))) return rc;
     const Inst *inst = find_inst(pot->kind, batch->n_max);
     if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica sweep kernel");
@@ -310,6 +321,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     bool block = inst->ns >= 256 && batch->n_replicas <= 2 * sms * inst->block_minb;
     const char *force = std::getenv("QMC_FORCE_KERNEL");
     if (force) block = std::strcmp(force, "block") == 0;
+    if (any_composite) block = false;  // composite moves exist in the warp-per-replica kernel only
     // canonical fast path: old-position pair terms come from the HBM cache instead of being recomputed
     if (feat == 0 && batch->pair_cache_valid && !block && !(force && std::strcmp(force, "cached") != 0))
         if (const CachedInst *c = find_cached(pot, batch)) return c->sweep(a, (cudaStream_t)stream, g_err, sizeof(g_err));

@@ -33,7 +33,8 @@ static inline int launch_feat(const SweepArgs &a, cudaStream_t s, char *err, siz
 }
 
 int CAT(sweep_launch_, INST_POT, _, INST_NS)(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn) {
-    // instantiated feature sets: canonical fast path; per-replica cells; + cell moves; everything
+    // instantiated feature sets: canonical fast path; per-replica cells; + cell moves; everything; everything + composite moves
+    if (feat & F_COMPOSITE) return launch_feat<F_COMPOSITE | F_CELLVAR | F_CELL | F_LABELS | F_EXCHANGE>(a, s, err, errn);
     if (feat == 0) return launch_feat<0>(a, s, err, errn);
     if ((feat & ~F_CELLVAR) == 0) return launch_feat<F_CELLVAR>(a, s, err, errn);
     if ((feat & ~(F_CELLVAR | F_CELL)) == 0) return launch_feat<F_CELLVAR | F_CELL>(a, s, err, errn);

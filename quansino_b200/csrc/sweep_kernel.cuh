@@ -22,6 +22,7 @@ struct MoveDev {
     int type, op;
     double step, bias;
     int default_label;
+    int repeat, chain;  // composite displacement moves: this entry `repeat` times, then on to the next entry if `chain`
     int *labels;  // device [R][n_max] or nullptr (= arange, no exchange)
 };
 
@@ -60,6 +61,30 @@ __device__ inline int select_labelled(const int *lab, int n, int idx) {
     for (int base = 0; base < n; base += 32) {
         const int j = base + lane_id();
         const unsigned b = __ballot_sync(FULL, j < n && __ldcg(lab + min(j, n - 1)) >= 0);
+        const int c = __popc(b);
+        if (found < 0 && idx < run + c) found = base + (int)__fns(b, 0, idx - run + 1);
+        run += c;
+    }
+    return found;
+}
+
+// CompositeDisplacementMove (moves/displacement.py:408-416): candidates = labelled atoms that no earlier sub-move of this
+// attempt displaced (`displaced` = bitmap over atom indices; one atom per label, so this is setdiff1d on the labels)
+__device__ inline int count_available(const int *lab, int n, const uint32_t *displaced) {
+    int c = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane_id();
+        const unsigned b = __ballot_sync(FULL, j < n && (!lab || __ldcg(lab + min(j, n - 1)) >= 0));
+        c += __popc(b & ~displaced[base >> 5]);
+    }
+    return c;
+}
+
+__device__ inline int select_available(const int *lab, int n, const uint32_t *displaced, int idx) {
+    int run = 0, found = -1;
+    for (int base = 0; base < n; base += 32) {
+        const int j = base + lane_id();
+        const unsigned b = __ballot_sync(FULL, j < n && (!lab || __ldcg(lab + min(j, n - 1)) >= 0)) & ~displaced[base >> 5];
         const int c = __popc(b);
         if (found < 0 && idx < run + c) found = base + (int)__fns(b, 0, idx - run + 1);
         run += c;
@@ -173,13 +198,14 @@ __device__ __forceinline__ Trial local_delta(const PotDev &pot, const Rep<LY> &R
 // commit the trial values of the touched atoms (accepted moves only; a rejected trial leaves no trace)
 template <class LY>
 __device__ __forceinline__ void commit_trial(const Rep<LY> &R, const int lane, const Trial &T) {
-    if (!LY::EMT) return;
-    for (int e = lane; e < T.n2; e += 32) {
-        const int j = R.l2(e);
-        R.sig(j) = R.sig(j) + gathered_dsigma(R, j);
-        R.eat(j) = R.tail(e);
+    if constexpr (LY::EMT) {
+        for (int e = lane; e < T.n2; e += 32) {
+            const int j = R.l2(e);
+            R.sig(j) = R.sig(j) + gathered_dsigma(R, j);
+            R.eat(j) = R.tail(e);
+        }
+        __syncwarp();
     }
-    __syncwarp();
 }
 
 // Displacement of one atom (both sides present): paired list slots (scan_both).  Touched atom l2[e] owns the slots 2e (old term)
@@ -222,15 +248,16 @@ __device__ __forceinline__ Trial local_delta_move(const PotDev &pot, const Rep<L
 
 template <class LY>
 __device__ __forceinline__ void commit_move(const Rep<LY> &R, const int lane, const Trial &T) {
-    if (!LY::EMT) return;
-    const double2 *slots = reinterpret_cast<const double2 *>(&R.lr(0));
-    for (int e = lane; e < T.n2; e += 32) {
-        const int j = R.l2(e);
-        const double2 t = slots[e];
-        R.sig(j) = t.x;
-        R.eat(j) = t.y;
+    if constexpr (LY::EMT) {
+        const double2 *slots = reinterpret_cast<const double2 *>(&R.lr(0));
+        for (int e = lane; e < T.n2; e += 32) {
+            const int j = R.l2(e);
+            const double2 t = slots[e];
+            R.sig(j) = t.x;
+            R.eat(j) = t.y;
+        }
+        __syncwarp();
     }
-    __syncwarp();
 }
 
 // GrandCanonicalCriteria.evaluate (mc/criteria.py:243-278): criteria * prefactor
@@ -253,6 +280,33 @@ constexpr int F_LABELS = 1;    // label tables in global memory (not arange)
 constexpr int F_CELL = 2;      // cell moves
 constexpr int F_EXCHANGE = 4;  // exchange moves
 constexpr int F_CELLVAR = 8;   // per-replica cells (kept in shared memory); otherwise one constant cell for all
+constexpr int F_COMPOSITE = 16;  // composite displacement moves (chains of move-table entries)
+
+// translation of one displacement sub-move from its three operation draws (operations/displacement.py:67-153)
+__device__ __forceinline__ void propose_translation(int op, double step, double o0, double o1, double o2, double t[3]) {
+    if (op == QMC_OP_BALL) {
+        const double rr = step * o0, phi = TWO_PI * o1, c = -1.0 + 2.0 * o2;
+        const double s = sqrt_fast(fmax(__dsub_rn(1.0, __dmul_rn(c, c)), 1e-300));
+        double sp, cp;
+        sincos_2pi(phi, sp, cp);
+        t[0] = __dmul_rn(__dmul_rn(rr, s), cp);
+        t[1] = __dmul_rn(__dmul_rn(rr, s), sp);
+        t[2] = __dmul_rn(rr, c);
+    } else if (op == QMC_OP_SPHERE) {
+        const double phi = TWO_PI * o0, c = -1.0 + 2.0 * o1;
+        const double s = sqrt_fast(fmax(__dsub_rn(1.0, __dmul_rn(c, c)), 1e-300));
+        double sp, cp;
+        sincos_2pi(phi, sp, cp);
+        t[0] = __dmul_rn(step, __dmul_rn(s, cp));
+        t[1] = __dmul_rn(step, __dmul_rn(s, sp));
+        t[2] = __dmul_rn(step, c);
+    } else {  // QMC_OP_BOX
+        const double w = step - -step;
+        t[0] = __dadd_rn(-step, __dmul_rn(w, o0));
+        t[1] = __dadd_rn(-step, __dmul_rn(w, o1));
+        t[2] = __dadd_rn(-step, __dmul_rn(w, o2));
+    }
+}
 
 // the random numbers of one attempt: lanes 0..3 run one Philox block each, the six / seven doubles are broadcast
 struct Draws {
@@ -401,34 +455,92 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
         int accepted = -1, moved = -1;
         double delta = __longlong_as_double(0x7ff8000000000000LL);  // NaN
 
-        if (mv.type == QMC_MOVE_DISPLACEMENT) {
+        if ((FEAT & F_COMPOSITE) && mv.type == QMC_MOVE_DISPLACEMENT && (mv.repeat > 1 || mv.chain)) {
+            // CompositeDisplacementMove.__call__ (moves/displacement.py:392-431) + one criteria evaluation (mc/core.py:369-377):
+            // snapshot the last accepted state in global memory, displace sub-move by sub-move with the local delta of each
+            // (committed at once: the next sub-move sees the moved atoms), test the accumulated difference, restore on reject.
+            for (int j = lane; j < R.n; j += 32) {
+                gx[j] = R.x(j);
+                gy[j] = R.y(j);
+                gz[j] = R.z(j);
+                if (POT == QMC_POT_EMT) {
+                    gs[j] = R.sig(j);
+                    ge[j] = R.eat(j);
+                }
+            }
+            uint32_t *disp = R.displaced();
+            if (lane < (NS + 31) / 32) disp[lane] = 0u;
+            __syncwarp();
+            double de_total = 0.0;
+            int n_moved = 0, n_drawn = 0;
+            for (int mm = m;; ++mm) {
+                const MoveDev &sm = a.mv[mm];
+                const int *slab = ((FEAT & F_LABELS) && sm.labels) ? sm.labels + (size_t)r * nmax : nullptr;
+                const int reps = sm.repeat > 0 ? sm.repeat : 1;
+                for (int q = 0; q < reps; ++q) {
+                    const int na = count_available(slab, R.n, disp);
+                    if (na == 0) continue;  // register_failure: nothing drawn
+                    double ul = D.u_label, o0 = D.o0, o1 = D.o1, o2 = D.o2;
+                    if (n_drawn > 0) {  // drawing sub-move c >= 1: blocks 32 + 2 (c - 1) and 33 + 2 (c - 1)
+                        double d0, d1;
+                        uniform_pair(key, attempt, grep, (uint32_t)(32 + 2 * (n_drawn - 1) + (lane & 1)), d0, d1);
+                        ul = __shfl_sync(FULL, d0, 0);
+                        o0 = __shfl_sync(FULL, d1, 0);
+                        o1 = __shfl_sync(FULL, d0, 1);
+                        o2 = __shfl_sync(FULL, d1, 1);
+                    }
+                    ++n_drawn;
+                    const int i = select_available(slab, R.n, disp, (int)(ul * (double)na));
+                    double t[3];
+                    propose_translation(sm.op, sm.step, o0, o1, o2, t);
+                    const double po[3] = {R.x(i), R.y(i), R.z(i)};
+                    const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
+                    const Trial T = local_delta_move<LY>(pot, R, C, lane, lt, R.n, i, po, pn, status);
+                    n_pairs += T.pairs;
+                    de_total += T.dE;
+                    commit_move<LY>(R, lane, T);
+                    if (lane == 0) {
+                        R.x(i) = pn[0];
+                        R.y(i) = pn[1];
+                        R.z(i) = pn[2];
+                        if (POT == QMC_POT_EMT) {
+                            R.sig(i) = T.sig_i;
+                            R.eat(i) = T.eat_i;
+                        }
+                        disp[i >> 5] |= 1u << (i & 31);
+                    }
+                    __syncwarp();
+                    moved = i;
+                    ++n_moved;
+                }
+                if (!sm.chain || mm + 1 >= a.n_moves) break;
+            }
+            if (n_moved > 0) {
+                delta = de_total;
+                const bool acc = metropolis(D.u_accept, -delta * inv_kT, status);
+                if (acc) {
+                    E += delta;
+                } else {
+                    for (int j = lane; j < R.n; j += 32) {
+                        R.x(j) = gx[j];
+                        R.y(j) = gy[j];
+                        R.z(j) = gz[j];
+                        if (POT == QMC_POT_EMT) {
+                            R.sig(j) = gs[j];
+                            R.eat(j) = ge[j];
+                        }
+                    }
+                }
+                __syncwarp();
+                accepted = acc ? 1 : 0;
+            }
+        } else if (mv.type == QMC_MOVE_DISPLACEMENT) {
             const int nu = lab ? count_labelled(lab, R.n) : R.n;
             if (nu > 0) {
                 const int idx = (int)(D.u_label * (double)nu);
                 const int i = lab ? select_labelled(lab, R.n, idx) : idx;
                 double t[3];
-                if (mv.op == QMC_OP_BALL) {
-                    const double rr = mv.step * D.o0, phi = TWO_PI * D.o1, c = -1.0 + 2.0 * D.o2;
-                    const double s = sqrt_fast(fmax(__dsub_rn(1.0, __dmul_rn(c, c)), 1e-300));
-                    double sp, cp;
-                    sincos_2pi(phi, sp, cp);
-                    t[0] = __dmul_rn(__dmul_rn(rr, s), cp);
-                    t[1] = __dmul_rn(__dmul_rn(rr, s), sp);
-                    t[2] = __dmul_rn(rr, c);
-                } else if (mv.op == QMC_OP_SPHERE) {
-                    const double phi = TWO_PI * D.o0, c = -1.0 + 2.0 * D.o1;
-                    const double s = sqrt_fast(fmax(__dsub_rn(1.0, __dmul_rn(c, c)), 1e-300));
-                    double sp, cp;
-                    sincos_2pi(phi, sp, cp);
-                    t[0] = __dmul_rn(mv.step, __dmul_rn(s, cp));
-                    t[1] = __dmul_rn(mv.step, __dmul_rn(s, sp));
-                    t[2] = __dmul_rn(mv.step, c);
-                } else {  // QMC_OP_BOX
-                    const double w = mv.step - -mv.step;
-                    t[0] = __dadd_rn(-mv.step, __dmul_rn(w, D.o0));
-                    t[1] = __dadd_rn(-mv.step, __dmul_rn(w, D.o1));
-                    t[2] = __dadd_rn(-mv.step, __dmul_rn(w, D.o2));
-                }
+                propose_translation(mv.op, mv.step, D.o0, D.o1, D.o2, t);
                 const double po[3] = {R.x(i), R.y(i), R.z(i)};
                 const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
                 const Trial T = local_delta_move<LY>(pot, R, C, lane, lt, R.n, i, po, pn, status);

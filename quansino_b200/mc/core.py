@@ -97,6 +97,7 @@ class MonteCarlo:
         )
         self.context = self.default_context(atoms, self.batch, self._seed)
         self._lowered: tuple | None = None
+        self._slots: dict[str, int] = {}
         self._primed = False
         self._counters_before: torch.Tensor | None = None
         self._cycles_last_launch = 0
@@ -127,22 +128,21 @@ class MonteCarlo:
     }
 
     def _lower(self, names: list[str]):
-        """POD move table for the given (available) move names; label tables are created once per move."""
+        """POD move table for the given (available) move names; label tables are created once per move.  A composite
+        move occupies a chain of consecutive entries; ``self._slots[name]`` is the entry of its head (counters, trace)."""
         key = tuple(names)
         if self._lowered is not None and self._lowered[0] == key:
-            for i, n in enumerate(names):  # probabilities may be changed between steps (mc/core.py:344-347)
-                self._lowered[1][i].probability = float(self.moves[n].probability)
+            for n in names:  # probabilities may be changed between steps (mc/core.py:344-347)
+                self._lowered[1][self._slots[n]].probability = float(self.moves[n].probability)
             return self._lowered[1], self._lowered[2]
-        if len(names) > _lib.QMC_MAX_MOVES:
-            raise NotImplementedError(f"at most {_lib.QMC_MAX_MOVES} moves per step on the GPU path")
-        arr = (_lib.Move * len(names))()
         n_atoms = self.batch.n_atoms.cpu().numpy()
         any_exchange = any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE for n in names)
-        keep = []
-        for i, n in enumerate(names):
+        entries, keep, slots = [], [], {}
+        for n in names:
             st = self.moves[n]
             st.criteria._check_supported()
-            m = st.move.lower()
+            chain = st.move.lower_chain() if hasattr(st.move, "lower_chain") else [st.move.lower()]
+            m = chain[0]
             if type(st.criteria).__name__ not in self._criteria_for[m.type]:
                 raise NotImplementedError(
                     f"{type(st.criteria).__name__} with {type(st.move).__name__} is not a combination of the GPU path"
@@ -158,9 +158,17 @@ class MonteCarlo:
                 elif st._label_tensor is None and any_exchange:
                     lab = st.move.validated_labels(self.batch.R, self.batch.n_max, n_atoms)
                     st._label_tensor = torch.from_numpy(lab).to(self.batch.device)
-                m.labels = st._label_tensor.data_ptr() if st._label_tensor is not None else None
+                for sub in chain:  # the sub-moves of a composite share one label table
+                    sub.labels = st._label_tensor.data_ptr() if st._label_tensor is not None else None
                 keep.append(st._label_tensor)
+            slots[n] = len(entries)
+            entries.extend(chain)
+        if len(entries) > _lib.QMC_MAX_MOVES:
+            raise NotImplementedError(f"at most {_lib.QMC_MAX_MOVES} move-table entries per step on the GPU path")
+        arr = (_lib.Move * len(entries))()
+        for i, m in enumerate(entries):
             arr[i] = m
+        self._slots = slots
         self._lowered = (key, arr, keep)
         return arr, keep
 
@@ -267,7 +275,7 @@ class MonteCarlo:
         # the pair-term cache follows displacement-only sweeps of a fixed cell; everything else leaves it stale
         keeps_cache = (
             b.pair_cache is not None and b.cells_uniform and os.environ.get("QMC_FORCE_KERNEL") in (None, "cached")
-            and all(m.type == _lib.MOVE_DISPLACEMENT and not m.labels for m in moves)
+            and all(m.type == _lib.MOVE_DISPLACEMENT and not m.labels and not m.chain and m.repeat <= 1 for m in moves)
         )  # fmt: skip
         if keeps_cache and not b.pair_cache_valid:
             b.energy_full()
@@ -285,7 +293,7 @@ class MonteCarlo:
                 )  # fmt: skip
             else:
                 rc = b.lib.qmc_sweep(
-                    C.byref(b.potential), C.byref(bs), moves, len(names), self._seed, self.attempt_counter, n_attempts,
+                    C.byref(b.potential), C.byref(bs), moves, len(moves), self._seed, self.attempt_counter, n_attempts,
                     C.byref(tr) if tr is not None else None, b.stream(),
                 )  # fmt: skip
         _lib.check(rc)

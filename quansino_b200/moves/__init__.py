@@ -1,8 +1,9 @@
 """Mirror of ``quansino.moves`` for the GPU path."""
 
 from quansino_b200.moves.cell import CellMove
+from quansino_b200.moves.composite import CompositeDisplacementMove, CompositeMove
 from quansino_b200.moves.core import BaseMove
 from quansino_b200.moves.displacement import DisplacementMove, HamiltonianDisplacementMove
 from quansino_b200.moves.exchange import ExchangeMove
 
-__all__ = ["BaseMove", "CellMove", "DisplacementMove", "ExchangeMove", "HamiltonianDisplacementMove"]
+__all__ = ["BaseMove", "CellMove", "CompositeDisplacementMove", "CompositeMove", "DisplacementMove", "ExchangeMove", "HamiltonianDisplacementMove"]

@@ -1,0 +1,140 @@
+"""Composite moves (``src/quansino/moves/composite.py:22-247``, ``src/quansino/moves/displacement.py:363-455``).
+
+``move * k`` and ``move_a + move_b`` build a composite exactly like the reference's move algebra
+(``moves/core.py:185-243``).  On the GPU path a ``CompositeDisplacementMove`` lowers to a CHAIN of ``qmc_move_t``
+entries (``repeat`` / ``chain``, include/quansino_b200.h): all sub-moves are displaced inside one attempt, no label is
+displaced twice, one criteria evaluation, one save / revert.  Composites of other move types (the docs' hybrid
+``DisplacementMove * N + CellMove``) are described but not lowered yet -- they raise ``NotImplementedError``."""
+
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+
+from quansino_b200 import _lib
+
+
+class CompositeMove:
+    """Mirror of ``quansino.moves.composite.CompositeMove``: a list of moves executed inside ONE attempt."""
+
+    move_type: int = -1
+
+    def __init__(self, moves: list) -> None:
+        self.moves = list(moves)
+
+    def __call__(self, context) -> bool:
+        raise NotImplementedError(
+            f"{type(self).__name__} executes inside the CUDA kernels as part of a sweep; it cannot be called per attempt "
+            "on the host (quansino_b200 has no CPU fallback)"
+        )
+
+    def __add__(self, other):
+        from quansino_b200.moves.core import BaseMove
+
+        if isinstance(other, CompositeMove):
+            if type(self) is type(other):
+                return type(self)(self.moves + other.moves)
+            return CompositeMove(self.moves + other.moves)
+        if isinstance(other, BaseMove):
+            if type(self) is other.composite_move_type:
+                return other.composite_move_type([*self.moves, other])
+            return CompositeMove([*self.moves, other])
+        raise TypeError(f"Cannot add {self.__class__.__name__} to {other.__class__.__name__}")
+
+    def __mul__(self, n: int):
+        if not isinstance(n, int):
+            raise TypeError(f"The number of times the move is repeated must be a positive, non-zero integer. Got {type(n)}.")
+        if n < 1:
+            raise ValueError("The number of times the move is repeated must be a positive, non-zero integer.")
+        return type(self)(self.moves * n)
+
+    def on_atoms_changed(self, added_indices, removed_indices) -> None:
+        for move in self.moves:
+            move.on_atoms_changed(added_indices, removed_indices)
+
+    def on_cell_changed(self, new_cell) -> None:
+        for move in self.moves:
+            move.on_cell_changed(new_cell)
+
+    def __getitem__(self, index: int):
+        return self.moves[index]
+
+    def __len__(self) -> int:
+        return len(self.moves)
+
+    def __iter__(self):
+        return iter(self.moves)
+
+    def lower_chain(self) -> list:
+        raise NotImplementedError(
+            f"{type(self).__name__} of {sorted({type(m).__name__ for m in self.moves})} is not lowered to the GPU path yet; "
+            "only CompositeDisplacementMove is (SURVEY.md section 8f)"
+        )
+
+    def to_dict(self) -> dict[str, Any]:
+        return {"name": self.__class__.__name__, "kwargs": {"moves": [move.to_dict() for move in self.moves]}}
+
+
+class CompositeDisplacementMove(CompositeMove):
+    """Mirror of ``quansino.moves.displacement.CompositeDisplacementMove``.
+
+    Every sub-move picks a label that no earlier sub-move of the same attempt displaced (``rng.choice`` over the sorted
+    set difference), sub-moves without candidates fail silently, and the move counts as performed if at least one
+    particle moved.  GPU-path restriction: all sub-moves share ONE label array (then "label already displaced" and
+    "atom already displaced" are the same statement, which is what the kernel tracks)."""
+
+    move_type = _lib.MOVE_DISPLACEMENT
+
+    def __init__(self, moves: list) -> None:
+        super().__init__(moves)
+        self.displaced_labels: list = []
+
+    @property
+    def number_of_moved_particles(self) -> int:
+        return sum(True for label in self.displaced_labels if label is not None)
+
+    def reset(self) -> None:
+        self.displaced_labels = []
+
+    # the driver treats the composite like a DisplacementMove when it builds the label table
+    @property
+    def labels(self):
+        return self.moves[0].labels
+
+    def validated_labels(self, n_replicas: int, n_max: int, n_atoms) -> np.ndarray:
+        return self.moves[0].validated_labels(n_replicas, n_max, n_atoms)
+
+    def is_identity(self, n_atoms) -> bool:
+        return self.moves[0].is_identity(n_atoms)
+
+    def lower_chain(self) -> list:
+        """One ``qmc_move_t`` per run of identical consecutive sub-moves (``repeat``), chained (``chain = 1``)."""
+        from quansino_b200.moves.displacement import DisplacementMove
+
+        if not self.moves:
+            raise ValueError("a composite move needs at least one move")
+        first = self.moves[0]
+        entries: list = []
+        keys: list = []
+        for mv in self.moves:
+            if type(mv) is not DisplacementMove:
+                raise NotImplementedError(f"{type(mv).__name__} inside a CompositeDisplacementMove is not available on the GPU path")
+            if mv is not first and not (np.array_equal(np.asarray(mv.labels), np.asarray(first.labels)) and mv.default_label == first.default_label):
+                raise NotImplementedError(
+                    "the sub-moves of a CompositeDisplacementMove must share one label array on the GPU path"
+                )  # fmt: skip
+            m = mv.lower()
+            key = (m.op, m.step)
+            if keys and keys[-1] == key:
+                entries[-1].repeat += 1
+            else:
+                m.repeat = 1
+                entries.append(m)
+                keys.append(key)
+        if len(entries) > _lib.QMC_MAX_MOVES:
+            raise NotImplementedError(f"a composite move may use at most {_lib.QMC_MAX_MOVES} different sub-moves on the GPU path")
+        for m in entries[:-1]:
+            m.chain = 1
+        entries[-1].chain = 0
+        return entries

@@ -57,13 +57,30 @@ class BaseMove:
             "attributes": {"max_attempts": self.max_attempts},
         }
 
+    # move algebra (moves/core.py:185-243): `a + b` and `a * k` build composite moves
+    @property
+    def composite_move_type(self):
+        from quansino_b200.moves.composite import CompositeMove
+
+        return CompositeMove
+
     def __add__(self, other):
-        if not isinstance(other, BaseMove):
-            raise TypeError(f"Cannot add {type(self).__name__} to {type(other).__name__}")
-        raise NotImplementedError("CompositeMove is not available on the GPU path (SURVEY.md section 8f)")
+        from quansino_b200.moves.composite import CompositeMove
+
+        if isinstance(other, CompositeMove):
+            if self.composite_move_type is type(other):
+                return self.composite_move_type([self, *other.moves])
+            return CompositeMove([self, *other.moves])
+        if isinstance(other, BaseMove):
+            if self.composite_move_type is other.composite_move_type:
+                return other.composite_move_type([self, other])
+            return CompositeMove([self, other])
+        raise TypeError(f"Cannot add {self.__class__.__name__} to {other.__class__.__name__}")
 
     def __mul__(self, n: int):
-        raise NotImplementedError("CompositeMove is not available on the GPU path (SURVEY.md section 8f)")
+        if not isinstance(n, int) or isinstance(n, bool) or n < 1:
+            raise ValueError("The number of times the move is repeated must be a positive, non-zero integer.")
+        return self.composite_move_type([self] * n)
 
     __rmul__ = __mul__
 

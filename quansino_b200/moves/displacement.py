@@ -38,6 +38,12 @@ class DisplacementMove(BaseMove):
     def default_operation(self):
         return Ball(0.1)
 
+    @property
+    def composite_move_type(self):
+        from quansino_b200.moves.composite import CompositeDisplacementMove
+
+        return CompositeDisplacementMove
+
     def validated_labels(self, n_replicas: int, n_max: int, n_atoms: np.ndarray) -> np.ndarray:
         """int32 [R][n_max] label table (padding -1), checked against the first-pass restrictions."""
         lab = np.asarray(self.labels)

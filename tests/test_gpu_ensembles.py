@@ -8,7 +8,7 @@ import pytest
 
 from oracle import capi
 from oracle.potentials import LJParams, emt_params
-from tests.helpers import cu_replicas
+from tests.helpers import cu_replicas, oracle_par, oracle_run
 
 pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_variant")]
 
@@ -250,3 +250,43 @@ def test_parallel_tempering_swap_matches_oracle(cuda_lib):
         assert np.array_equal(t_dev.cpu().numpy(), expect), f"round {rnd}"
     assert n_swaps > 10
     assert np.array_equal(np.sort(expect), np.sort(temps))  # temperatures are only permuted
+
+
+def test_composite_displacement_matches_oracle(cuda_lib):
+    """CompositeDisplacementMove: `a * 2 + b` next to a plain move, 8 replicas, against the C oracle."""
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.mc.criteria import CanonicalCriteria
+    from quansino_b200.moves import DisplacementMove
+
+    R, n_attempts = 8, 150
+    pos, cell, n = cu_replicas(3, R)
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    lab = np.arange(n)
+    mc = Canonical(atoms, temperature=600.0, seed=99, trace=True, max_cycles=n_attempts, resync_interval=0,
+                   default_displacement_move=DisplacementMove(lab, operations.Ball(0.1)))  # fmt: skip
+    combo = DisplacementMove(lab, operations.Ball(0.07)) * 2 + DisplacementMove(lab, operations.Box(0.03))
+    mc.add_move(combo, criteria=CanonicalCriteria(), name="combo", probability=2.0)
+    mc.run(1)
+    tr = mc.last_trace
+    par = oracle_par(mc.batch.calc)
+    moves = [
+        dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_BALL, step=0.1, probability=1.0),
+        dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_BALL, step=0.07, probability=2.0, repeat=2, chain=1),
+        dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_BOX, step=0.03, chain=0),
+    ]
+    reps, otr = oracle_run(par, pos, np.full(R, n), cell, (1, 1, 1), moves, 99, n_attempts, range(R), temperature=600.0)
+    out = mc.download()
+    for r in range(R):
+        assert np.array_equal(tr["move"][r], otr[r]["move"])
+        assert np.array_equal(tr["accepted"][r], otr[r]["accepted"]), f"accept/reject sequence differs for replica {r}"
+        assert np.array_equal(tr["moved"][r], otr[r]["moved"])
+        np.testing.assert_allclose(tr["energy"][r], otr[r]["energy"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(out.positions[r], reps[r].positions, rtol=0, atol=1e-12)
+    cnt = mc.counters()
+    assert np.array_equal(cnt[:, 0, 0] + cnt[:, 1, 0], np.full(R, n_attempts)) and np.all(cnt[:, 2] == 0)
+    assert np.array_equal(cnt[:, 1, 0], np.array([(t["move"] == 1).sum() for t in otr]))
+    assert np.array_equal(cnt[:, 1, 1], np.array([((t["move"] == 1) & (t["accepted"] == 1)).sum() for t in otr]))
+    # the tracked energy still equals a fresh full evaluation after composite commits and restores
+    tracked = mc.batch.energy.cpu().numpy().copy()
+    np.testing.assert_allclose(tracked, mc.batch.energy_full().cpu().numpy(), rtol=1e-11, atol=1e-12)

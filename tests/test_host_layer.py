@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in sorted(declared):
         assert getattr(lib, name) is not None, name
-    assert lib.qmc_abi_version() == 1
+    assert lib.qmc_abi_version() == 2
 
 
 def test_struct_layouts_match_the_header():
@@ -115,8 +115,45 @@ def test_moves_lower_like_the_reference_defaults():
         Ball(0.1).calculate(None)
     with pytest.raises(TypeError):
         DisplacementMove(np.arange(4)) + 3
+
+
+def test_move_algebra_builds_composites_like_the_reference():
+    """moves/core.py:185-243, moves/composite.py:62-151, tests/moves/test_displacement_moves.py of the reference."""
+    from quansino_b200 import _lib
+    from quansino_b200.moves import CellMove, CompositeDisplacementMove, CompositeMove, DisplacementMove
+    from quansino_b200.operations import Ball, Box, Sphere
+
+    lab = np.arange(6)
+    a, b, c = DisplacementMove(lab, Ball(0.1)), DisplacementMove(lab, Box(0.2)), DisplacementMove(lab, Sphere(0.3))
+    triple = a * 3
+    assert type(triple) is CompositeDisplacementMove and len(triple) == 3 and triple[0] is a and list(triple) == [a, a, a]
+    assert type(3 * a) is CompositeDisplacementMove
+    mixed = a + b + c
+    assert type(mixed) is CompositeDisplacementMove and mixed.moves == [a, b, c]
+    assert type(mixed + a) is CompositeDisplacementMove and len(mixed + a) == 4
+    assert type(a + (b + c)) is CompositeDisplacementMove and (a + (b + c)).moves == [a, b, c]
+    assert len(mixed * 2) == 6 and type(mixed * 2) is CompositeDisplacementMove
+    hybrid = a * 2 + CellMove()  # the docs' hybrid NPT move: a plain CompositeMove
+    assert type(hybrid) is CompositeMove and len(hybrid) == 3
+    assert type(a + CellMove()) is CompositeMove and type(CellMove() + a) is CompositeMove
+    for bad in (0, -1, 1.5):
+        with pytest.raises((ValueError, TypeError)):
+            a * bad
+    with pytest.raises(TypeError):
+        mixed + 3
+    # lowering: runs of identical sub-moves collapse into `repeat`, the entries are chained
+    chain = (a * 3 + b + c * 2).lower_chain()
+    assert [(m.op, m.step, m.repeat, m.chain) for m in chain] == [
+        (_lib.OP_BALL, 0.1, 3, 1), (_lib.OP_BOX, 0.2, 1, 1), (_lib.OP_SPHERE, 0.3, 2, 0),
+    ]  # fmt: skip
     with pytest.raises(NotImplementedError):
-        DisplacementMove(np.arange(4)) + DisplacementMove(np.arange(4))
+        hybrid.lower_chain()
+    with pytest.raises(NotImplementedError):  # different label arrays inside one composite
+        (a + DisplacementMove(np.array([0, 1, 2, -1, -1, -1]))).lower_chain()
+    with pytest.raises(NotImplementedError):
+        triple(None)
+    d = mixed.to_dict()
+    assert d["name"] == "CompositeDisplacementMove" and len(d["kwargs"]["moves"]) == 3
 
 
 def test_label_validation():
