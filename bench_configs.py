@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Secondary measurements: the other configurations of BASELINE.json (C3 isobaric, C4 grand-canonical LJ, C5 HMC) on one
-GPU.  Not part of the bench.py contract; results are recorded under profiles/.  Usage: python bench_configs.py [c3|c4|c5] ..."""
+GPU.  Not part of the bench.py contract; results are recorded under profiles/.  Usage: python bench_configs.py [c3|c4|c5|composite] ..."""
 
 from __future__ import annotations
 
@@ -94,10 +94,29 @@ def c5(R=64, repeat=8, n_steps=100, attempts=1):
             "acceptance": float(mc.counters()[:, 0, 1].sum() / (R * attempts)), "wall": time.perf_counter() - t0}  # fmt: skip
 
 
+def composite(R=4096, k=4, steps=20):
+    """C2 workload with CompositeDisplacementMove = DisplacementMove * k (k atoms per criteria evaluation)."""
+    from quansino_b200.mc import Canonical
+    from quansino_b200.mc.criteria import CanonicalCriteria
+
+    pos0, cell = fcc_cubic("Cu", 3)
+    n = len(pos0)
+    rng = np.random.default_rng(6)
+    pos = pos0[None] + rng.normal(scale=0.05, size=(R, n, 3))
+    atoms = BatchedAtoms(pos, cell, np.full(R, n, np.int32), "Cu", (True,) * 3, EMT())
+    mc = Canonical(atoms, temperature=300.0, max_cycles=n // k, seed=6, resync_interval=0)
+    mc.add_move(DisplacementMove(np.arange(n), Ball(0.1 / np.sqrt(k))) * k, criteria=CanonicalCriteria(), name="composite")
+    t, pairs = timed(mc, steps, 3)
+    c = mc.counters()
+    return {"config": f"C2 workload with DisplacementMove * {k} (CompositeDisplacementMove), {R} replicas/GPU, max_cycles {n // k}",
+            "attempts_per_s": R * (n // k) * steps / t, "displacements_per_s": R * (n // k) * k * steps / t, "pair_evals_per_s": pairs / t,
+            "ms_per_step": 1e3 * t / steps, "acceptance": float(c[:, 0, 1].sum() / c[:, 0, 0].sum())}  # fmt: skip
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c3", "c4", "c5"]
     for w in which:
         if w == "c5small":
             print(json.dumps(c5(R=64, repeat=4, n_steps=20)), flush=True)
         else:
-            print(json.dumps({"c3": c3, "c4": c4, "c5": c5}[w]()), flush=True)
+            print(json.dumps({"c3": c3, "c4": c4, "c5": c5, "composite": composite}[w]()), flush=True)
