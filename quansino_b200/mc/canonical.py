@@ -24,6 +24,10 @@ class Canonical(MonteCarlo):
         self.temperature = temperature
         if default_displacement_move:
             self.add_move(default_displacement_move, name="default_displacement_move")
+        if self.default_logger:  # mc/canonical.py:78-79; here the mean acceptance rate over the replicas of the last step
+            import numpy as np
+
+            self.default_logger.add_field("AcptRate", lambda: float(np.mean(self.update_acceptance_rate())))
 
     @property
     def temperature(self):

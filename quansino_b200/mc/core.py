@@ -71,7 +71,11 @@ class MonteCarlo:
         steps_per_launch: int = 1,
         resync_interval: int = 100,
         trace: bool = False,
+        logfile=None,
+        trajectory=None,
+        restart_file=None,
         logging_interval: int = 1,
+        logging_mode: str = "a",
         pair_cache: bool | None = None,
     ) -> None:
         self.moves: dict[str, MoveStorage] = {}
@@ -80,6 +84,7 @@ class MonteCarlo:
         self.move_history: list[tuple[str, Any]] = []
         self._seed = int(seed) if seed else int.from_bytes(os.urandom(8), "little")
         self.logging_interval = logging_interval
+        self.logging_mode = logging_mode
         self.step_count = 0
         self.max_steps = 0
         self.attempt_counter = 0
@@ -96,6 +101,28 @@ class MonteCarlo:
             atoms, calc=calc, device=device, replica_offset=replica_offset, with_momenta=self.needs_momenta, pair_cache=pair_cache
         )
         self.context = self.default_context(atoms, self.batch, self._seed)
+        # default observers (mc/driver.py:42-63, 196-262): created from a path / stream, or attached as given
+        self.default_logger = self.default_trajectory = self.default_restart = None
+        if logfile is not None:
+            from quansino_b200.io import Logger
+
+            self.default_logger = logfile if isinstance(logfile, Logger) else Logger(logfile, logging_interval, logging_mode)
+            self.default_logger.add_mc_fields(self)
+            self.attach(self.default_logger, name="default_logger")
+        if trajectory is not None:
+            from quansino_b200.io import TrajectoryObserver
+
+            self.default_trajectory = (
+                trajectory if isinstance(trajectory, TrajectoryObserver) else TrajectoryObserver(atoms, trajectory, logging_interval, logging_mode)
+            )
+            self.attach(self.default_trajectory, name="default_trajectory")
+        if restart_file is not None:
+            from quansino_b200.io import RestartObserver
+
+            self.default_restart = (
+                restart_file if isinstance(restart_file, RestartObserver) else RestartObserver(self, restart_file, logging_interval, logging_mode)
+            )
+            self.attach(self.default_restart, name="default_restart")
         self._lowered: tuple | None = None
         self._slots: dict[str, int] = {}
         self._primed = False
@@ -178,12 +205,33 @@ class MonteCarlo:
         return None if t is None else t.cpu().numpy()
 
     # -- driver loop (mc/driver.py:91-132) -------------------------------------------------------------
-    def attach(self, function: Callable[[], Any], interval: int = 1, name: str | None = None) -> None:
-        """Attach an observer called every ``interval`` steps (``interval < 0``: once, at step ``abs(interval)``)."""
-        self.observers[name or f"observer_{len(self.observers)}"] = (function, int(interval))
+    def attach(self, function: Callable[[], Any], interval: int | None = None, name: str | None = None) -> None:
+        """Attach an observer called every ``interval`` steps (``interval < 0``: once, at step ``abs(interval)``).
+        ``function`` is a plain callable or a ``quansino_b200.io.Observer`` (its own ``interval`` is used)."""
+        from quansino_b200.io.core import Observer
+
+        if isinstance(function, Observer):
+            if interval is not None:
+                function.interval = int(interval)
+            function.attach_simulation(self)
+            entry = (function, function)
+        else:
+            entry = (function, 1 if interval is None else int(interval))
+        self.observers[name or f"observer_{len(self.observers)}"] = entry
+
+    @staticmethod
+    def _interval_of(entry) -> int:
+        return int(entry[1].interval) if hasattr(entry[1], "interval") else int(entry[1])
+
+    def close(self) -> None:
+        """Close the files of the attached observers (``mc/driver.py:264-266``)."""
+        for function, _ in self.observers.values():
+            if hasattr(function, "close"):
+                function.close()
 
     def call_observers(self) -> None:
-        for function, interval in self.observers.values():
+        for entry in self.observers.values():
+            function, interval = entry[0], self._interval_of(entry)
             if (interval > 0 and self.step_count % interval == 0) or (interval < 0 and self.step_count == abs(interval)):
                 function()
 
@@ -201,7 +249,8 @@ class MonteCarlo:
         k = min(self.steps_per_launch, self.max_steps - self.step_count)
         if any(st.interval != 1 for st in self.moves.values()):
             return 1
-        for _, interval in self.observers.values():
+        for entry in self.observers.values():
+            interval = self._interval_of(entry)
             if interval > 0:
                 k = min(k, interval - self.step_count % interval)
             elif interval < 0 and abs(interval) > self.step_count:
@@ -323,12 +372,64 @@ class MonteCarlo:
         return self.atoms
 
     def to_dict(self) -> dict[str, Any]:
+        """Everything a restart needs (``mc/driver.py:177-194``, ``mc/core.py:244-309``).  The reference stores
+        ``rng.bit_generator.state``; here ``seed`` and ``attempt_counter`` ARE the state of the counter-based stream.  The
+        incrementally tracked energies and EMT caches are stored too, so that a restart continues bit-identically."""
+        b = self.batch
+        self.download()
+        state = {
+            "positions": self.atoms.positions, "cell": self.atoms.cell, "n_atoms": self.atoms.n_atoms, "symbol": self.atoms.symbol,
+            "pbc": list(self.atoms.pbc), "energy": b.energy.cpu().numpy(), "sigma1": b.sigma1.cpu().numpy(), "eatom": b.eatom.cpu().numpy(),
+            "temperature": b.temperature.cpu().numpy(), "counters": b.counters.cpu().numpy(), "n_exchange": b.n_exchange.cpu().numpy(),
+            "replica_offset": b.replica_offset, "cells_uniform": bool(b.cells_uniform),
+        }  # fmt: skip
+        if b.momenta is not None:
+            state["momenta"] = self.atoms.momenta
+            state["kinetic"] = b.kinetic.cpu().numpy()
+        labels = {name: self.labels(name) for name in self.moves if getattr(self.moves[name], "_label_tensor", None) is not None}
         return {
             "name": self.__class__.__name__,
-            "kwargs": {"seed": self._seed, "max_cycles": self.max_cycles, "logging_interval": self.logging_interval},
-            "attributes": {"step_count": self.step_count, "attempt_counter": self.attempt_counter},
+            "kwargs": {"seed": self._seed, "max_cycles": self.max_cycles, "logging_interval": self.logging_interval,
+                       "logging_mode": self.logging_mode},
+            "attributes": {"step_count": self.step_count, "attempt_counter": self.attempt_counter, "primed": self._primed},
             "context": self.context.to_dict(),
             "moves": {name: st.to_dict() for name, st in self.moves.items()},
-        }
+            "state": state,
+            "labels": labels,
+        }  # fmt: skip
+
+    def load_state(self, data: dict[str, Any]) -> None:
+        """Continue a run from ``to_dict()`` / ``quansino_b200.io.read_restart``.  The simulation must have been constructed
+        like the one that wrote the restart (same class, moves in the same order, same batch shape)."""
+        if data.get("name") != self.__class__.__name__:
+            raise ValueError(f"restart data of a {data.get('name')} cannot be loaded into a {self.__class__.__name__}")
+        if list(data.get("moves", {})) != list(self.moves):
+            raise ValueError("the restart data was written with a different set of moves")
+        st, b = data["state"], self.batch
+        pos = np.asarray(st["positions"], dtype=np.float64)
+        if pos.shape != self.atoms.positions.shape:
+            raise ValueError(f"restart batch shape {pos.shape} differs from this simulation's {self.atoms.positions.shape}")
+        if int(data["kwargs"]["seed"]) != self._seed:
+            self._seed = int(data["kwargs"]["seed"])
+            self.context.seed = self._seed
+        self.atoms.positions[...] = pos
+        self.atoms.cell[...] = np.asarray(st["cell"], dtype=np.float64)
+        self.atoms.n_atoms[...] = np.asarray(st["n_atoms"], dtype=np.int32)
+        if "momenta" in st and b.momenta is not None:
+            self.atoms.momenta = np.array(st["momenta"], dtype=np.float64)
+        b.upload(self.atoms)
+        dev = b.device
+        for name, dtype in (("energy", np.float64), ("sigma1", np.float64), ("eatom", np.float64), ("temperature", np.float64),
+                            ("counters", np.int64), ("n_exchange", np.int32)):  # fmt: skip
+            getattr(b, name).copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(st[name], dtype=dtype))).to(dev))
+        if "kinetic" in st and b.kinetic is not None:
+            b.kinetic.copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(st["kinetic"], dtype=np.float64))).to(dev))
+        b.cells_uniform = bool(st.get("cells_uniform", b.cells_uniform)) and b.cells_uniform
+        self.step_count = int(data["attributes"]["step_count"])
+        self.attempt_counter = int(data["attributes"]["attempt_counter"])
+        self._primed = bool(data["attributes"].get("primed", True))
+        self._lowered = None
+        for name, table in data.get("labels", {}).items():
+            self.moves[name]._label_tensor = torch.from_numpy(np.ascontiguousarray(np.asarray(table, dtype=np.int32))).to(dev)
 
     todict = to_dict
