@@ -329,23 +329,26 @@ def run_native(args):
     value = attempts / (ms_total * 1e-3)
 
     # ---- e2e: host buffers in / out every step through the public driver ----
-    host_pos = torch.from_numpy(np.ascontiguousarray(pos.transpose(0, 2, 1))).pin_memory()
-    host_out = torch.empty_like(host_pos).pin_memory()
+    # two pinned buffers used in turn: the output of one step is the input of the next, on the host, without a host copy
+    host_bufs = [torch.from_numpy(np.ascontiguousarray(pos.transpose(0, 2, 1))).pin_memory(), None]
+    host_bufs[1] = torch.empty_like(host_bufs[0]).pin_memory()
     host_e = torch.empty(R, dtype=torch.float64).pin_memory()
     e2e_steps = max(3, min(args.steps, 20))
-    h2d = host_pos.numel() * 8
-    d2h = host_out.numel() * 8 + host_e.numel() * 8
+    h2d = host_bufs[0].numel() * 8
+    d2h = host_bufs[1].numel() * 8 + host_e.numel() * 8
+    turn = [0]
 
     def e2e_step():
-        mc.batch.pos.copy_(host_pos, non_blocking=True)
+        src, dst = host_bufs[turn[0]], host_bufs[1 - turn[0]]
+        mc.batch.pos.copy_(src, non_blocking=True)
         mc.batch.energy_full()
         for _ in mc.step():
             pass
         mc.step_count += 1
-        host_out.copy_(mc.batch.pos, non_blocking=True)
+        dst.copy_(mc.batch.pos, non_blocking=True)
         host_e.copy_(mc.batch.energy, non_blocking=True)
         torch.cuda.current_stream(device).synchronize()
-        host_pos.copy_(host_out)  # the next step's input is this step's output, on the host
+        turn[0] = 1 - turn[0]  # the next step reads what this step wrote
 
     for _ in range(2):
         e2e_step()
