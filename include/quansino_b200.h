@@ -71,11 +71,13 @@ typedef struct qmc_potential {
  * ExchangeMove + Translation (moves/exchange.py:134-176, operations/displacement.py:170-175),
  * HamiltonianDisplacementMove + Verlet (moves/displacement.py:307-345, integrators/displacement.py:52-81).
  *
- * CompositeDisplacementMove (moves/displacement.py:363-455; `move * k`, `move_a + move_b`, moves/core.py:185-243,
- * moves/composite.py:62-151): consecutive table entries with `chain = 1` on all but the last form ONE move -- one
- * selection probability (the first entry's; the others are ignored), every entry displaced `repeat` times, no atom
- * displaced twice, ONE criteria evaluation on the accumulated energy difference, all displacements reverted together.
- * Counters and the trace refer to the first entry of the chain. */
+ * Composite moves (`move * k`, `move_a + move_b`, moves/core.py:185-243, moves/composite.py:62-151): consecutive table
+ * entries with `chain` bit 0 set on all but the last form ONE move -- one selection probability (the first entry's; the
+ * others are ignored), every entry performed `repeat` times, ONE criteria evaluation on the whole change, everything
+ * reverted together.  `chain` bit 1 clear: CompositeDisplacementMove (moves/displacement.py:363-455), no label is
+ * displaced twice.  Bit 1 set (on every entry of the chain): plain CompositeMove (moves/composite.py:43-62), the
+ * sub-moves choose independently, and a CellMove may be the last entry (the docs' hybrid NPT move
+ * `DisplacementMove * N + CellMove`, judged by IsobaricCriteria).  Counters and the trace refer to the first entry. */
 enum qmc_move_type { QMC_MOVE_DISPLACEMENT = 0, QMC_MOVE_CELL = 1, QMC_MOVE_EXCHANGE = 2, QMC_MOVE_HMC = 3 };
 enum qmc_op { QMC_OP_BALL = 0, QMC_OP_BOX = 1, QMC_OP_SPHERE = 2, QMC_OP_TRANSLATION = 3, QMC_OP_ISOTROPIC = 4, QMC_OP_VERLET = 5 };
 #define QMC_LABEL_NONE INT32_MIN
@@ -89,7 +91,7 @@ typedef struct qmc_move {
     int32_t n_steps;       /* Verlet max_steps */
     int32_t default_label; /* DisplacementMove.default_label; QMC_LABEL_NONE = None */
     int32_t repeat;        /* displacement moves: how many times this entry is performed per attempt (>= 1; 0 reads as 1) */
-    int32_t chain;         /* 1: the next table entry belongs to the same composite move */
+    int32_t chain;         /* bit 0: the next table entry belongs to the same composite move; bit 1: plain CompositeMove */
     int32_t *labels;       /* device [n_replicas][n_max]; NULL = arange(n_atoms) and no exchange moves */
 } qmc_move_t;
 

@@ -34,7 +34,8 @@ from ase.calculators.emt import EMT  # noqa: E402
 from ase.calculators.lj import LennardJones  # noqa: E402
 from quansino.integrators.displacement import Verlet  # noqa: E402
 from quansino.mc.canonical import Canonical, HamiltonianCanonical  # noqa: E402
-from quansino.mc.criteria import CanonicalCriteria  # noqa: E402
+from quansino.mc.criteria import CanonicalCriteria, IsobaricCriteria  # noqa: E402
+from quansino.moves.composite import CompositeMove  # noqa: E402
 from quansino.mc.gcmc import GrandCanonical  # noqa: E402
 from quansino.mc.isobaric import Isobaric  # noqa: E402
 from quansino.moves.cell import CellMove  # noqa: E402
@@ -137,6 +138,32 @@ def case_composite(variant, seed, n_attempts):
     )  # fmt: skip
 
 
+def case_hybrid(seed, n_attempts, k):
+    """The docs' hybrid NPT move (examples/orb-v3_isobaric_bulk_cu.py:45-48): `DisplacementMove * k + CellMove` is a plain
+    CompositeMove -- k independent displacements (labels may repeat), one cell deformation, ONE IsobaricCriteria test -- next
+    to a plain displacement move; plus a plain CompositeMove of two displacement moves under CanonicalCriteria."""
+    atoms, pos0, cell = cu_atoms(3, 0.05, 6161)
+    n = len(atoms)
+    labels = np.arange(n)
+    pressure = 2000.0 * bar
+    mc = Isobaric(atoms, temperature=500.0, pressure=pressure, max_cycles=n_attempts,
+                  default_displacement_move=DisplacementMove(labels, Ball(0.1)))  # fmt: skip
+    hybrid = DisplacementMove(labels, Ball(0.05)) * k + CellMove(IsotropicDeformation(0.01))
+    assert type(hybrid) is CompositeMove and len(hybrid) == k + 1
+    mc.add_move(hybrid, criteria=IsobaricCriteria(), name="hybrid", probability=1.0)
+    pair = CompositeMove([DisplacementMove(labels, Box(0.04)), DisplacementMove(labels, Box(0.04))])
+    mc.add_move(pair, criteria=CanonicalCriteria(), name="pair", probability=0.5)
+    mc.moves["default_displacement_move"].probability = 1.0
+    inject(mc, seed, 6)
+    tr = run_steps(mc, 1)
+    # (named move, type 0 = displacement / 1 = cell, operation, step, repeat, chain bits)
+    spec = np.array([(0, 0, 0, 0.1, 1, 0), (1, 0, 0, 0.05, k, 3), (1, 1, 4, 0.01, 1, 2), (2, 0, 1, 0.04, 2, 2)], dtype=float)
+    return dict(
+        kind="hybrid", seed=seed, replica=6, temperature=500.0, pressure=pressure, positions0=pos0, cell0=cell, labels=labels, spec=spec,
+        probabilities=np.array([mc.moves[q].probability for q in mc.moves]), positions=atoms.positions.copy(), cell=atoms.cell.array.copy(), **tr,
+    )  # fmt: skip
+
+
 def case_isobaric(seed, steps, p_cell):
     atoms, pos0, cell = cu_atoms(3, 0.05, 777)
     n = len(atoms)
@@ -231,6 +258,7 @@ def main():
         "composite_mul": lambda: case_composite("mul", 5001, 120),
         "composite_add": lambda: case_composite("add", 5002, 80),
         "composite_exhaust": lambda: case_composite("exhaust", 5003, 40),
+        "composite_hybrid": lambda: case_hybrid(5004, 90, 3),
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():

@@ -22,7 +22,9 @@ Layout (DESIGN.md section "Random stream"):
     block 3: d0 = u_coin  (insert / delete, ``moves/exchange.py:148``)   d1 = u_swap (parallel tempering)
     block 32 + 2 (c - 1), 33 + 2 (c - 1): sub-move c >= 1 of a CompositeDisplacementMove (``moves/displacement.py:392-431``;
              c counts the sub-moves that draw, the first one uses the standard slots above):
-             (u_label, operation draw 0) and (operation draw 1, operation draw 2)
+             (u_label, operation draw 0) and (operation draw 1, operation draw 2); the CellMove closing a hybrid
+             ``CompositeMove`` (``DisplacementMove * N + CellMove``) draws block 3's second double if a displacement drew
+             before it, operation draw 0 otherwise
     block 16 + p: Box-Muller pair p of the 3N momentum normals (``utils/dynamics.py:31``), row-major:
              normal m = 3*atom + axis lives in pair p = m // 2; z_even = r cos(t), z_odd = r sin(t),
              r = sqrt(-2 ln(1 - d0)), t = 2 pi d1.
@@ -124,6 +126,8 @@ class InjectedStream:
         k = self._op_draws
         self._op_draws += 1
         self._calls += 1
+        if k == 3 and self._labels >= 1:  # a fourth draw after a label: the CellMove that closes a hybrid CompositeMove
+            return self._pair(BLOCK_COIN_SWAP)[1]
         if self._labels > 1:  # sub-move c = _labels - 1 >= 1 of a composite displacement move
             c = self._labels - 1
             if k == 0:

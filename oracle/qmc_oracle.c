@@ -439,9 +439,9 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
         /* a composite move is ONE MoveStorage: only the head of a chain carries a probability */
         double tot = 0.0, acc = 0.0;
         for (int m = 0; m < n_moves; ++m)
-            if (m == 0 || !moves[m - 1].chain) tot += moves[m].probability;
+            if (m == 0 || !(moves[m - 1].chain & 1)) tot += moves[m].probability;
         for (int m = 0; m < n_moves; ++m) {
-            if (m == 0 || !moves[m - 1].chain) acc += moves[m].probability / tot;
+            if (m == 0 || !(moves[m - 1].chain & 1)) acc += moves[m].probability / tot;
             cdf[m] = acc;
         }
         double last = cdf[n_moves - 1];
@@ -466,17 +466,32 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
         double delta = NAN;
 
         if (mv->type == QO_MOVE_DISPLACEMENT && (mv->repeat > 1 || mv->chain)) {
-            /* CompositeDisplacementMove.__call__ (moves/displacement.py:392-431): every sub-move picks a label nobody
-             * displaced yet in this composite (rng.choice over the sorted set difference), sub-moves without candidates
-             * fail silently; then ONE CanonicalCriteria.evaluate on the whole displacement (mc/core.py:369-377).
+            /* Composite moves.  chain bit 0: the next entry belongs to the same move; chain bit 1: plain CompositeMove
+             * (moves/composite.py:43-62: every sub-move is called on its own, labels may repeat) instead of
+             * CompositeDisplacementMove (moves/displacement.py:392-431: every sub-move picks a label nobody displaced yet
+             * in this composite -- rng.choice over the sorted set difference -- and sub-moves without candidates fail
+             * silently).  A CellMove may close a plain chain (the docs' hybrid NPT move `DisplacementMove * N + CellMove`).
+             * Then ONE criteria evaluation on the whole change (mc/core.py:369-377).
              * Draws: the first drawing sub-move uses the standard slots, drawing sub-move c >= 1 uses
-             * block 32 + 2 (c - 1) = (u_label, op draw 0) and block 33 + 2 (c - 1) = (op draw 1, op draw 2). */
+             * block 32 + 2 (c - 1) = (u_label, op draw 0) and block 33 + 2 (c - 1) = (op draw 1, op draw 2); the cell draw
+             * is op draw 0 if no displacement drew, else the second double of block 3. */
             memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
-            int n_moved = 0, c = 0; /* disp[]: label VALUES displaced so far (the reference compares labels, not atoms) */
+            const int exclusive = !(mv->chain & 2);
+            int n_moved = 0, c = 0, did_cell = 0; /* disp[]: label VALUES displaced so far (the reference compares labels, not atoms) */
+            double new_cell[9];
             int *disp = (int *)malloc(sizeof(int) * (size_t)(n + 1));
             if (!disp) { rc = -1; goto done; }
             for (int mm = m; mm < n_moves; ++mm) {
                 qo_move_t *sm = &moves[mm];
+                if (sm->type == QO_MOVE_CELL) {
+                    if (exclusive || (sm->chain & 1)) { free(disp); rc = -1; goto done; } /* last entry of a plain chain only */
+                    const double u_cell = c == 0 ? opd[0] : b3[1];
+                    double sc = exp(-sm->step + (sm->step - -sm->step) * u_cell);
+                    for (int q = 0; q < 9; ++q) new_cell[q] = sc * st->cell[q];
+                    scale_positions(n, trial, st->cell, new_cell);
+                    did_cell = 1;
+                    break;
+                }
                 if (sm->type != QO_MOVE_DISPLACEMENT) { free(disp); rc = -1; goto done; }
                 const int reps = sm->repeat > 0 ? sm->repeat : 1;
                 for (int rep_i = 0; rep_i < reps; ++rep_i) {
@@ -484,7 +499,8 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                     int na = 0;
                     for (int q = 0; q < nu; ++q) { /* setdiff1d(unique_labels, displaced_labels): sorted, as unique_labels is */
                         int taken = 0;
-                        for (int d = 0; d < n_moved; ++d) taken |= disp[d] == uniq[q];
+                        if (exclusive)
+                            for (int d = 0; d < n_moved; ++d) taken |= disp[d] == uniq[q];
                         if (!taken) uniq[na++] = uniq[q];
                     }
                     if (na == 0) continue; /* register_failure, nothing drawn */
@@ -519,19 +535,26 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                     disp[n_moved++] = label;
                     moved = a;
                 }
-                if (!sm->chain) break;
+                if (!(sm->chain & 1)) break;
             }
             free(disp);
-            if (n_moved > 0) {
+            if (n_moved > 0 || did_cell) {
                 double e_new;
-                int64_t np_ = qo_energy(pot, n, trial, st->cell, st->pbc, &e_new, NULL, NULL);
+                const double *cell_new = did_cell ? new_cell : st->cell;
+                int64_t np_ = qo_energy(pot, n, trial, cell_new, st->pbc, &e_new, NULL, NULL);
                 cnt[0] += np_; cnt[3] += 1;
                 delta = e_new - st->last_energy;
                 double x = -delta / kT;
+                if (did_cell) { /* IsobaricCriteria (mc/criteria.py:160-172) */
+                    double v_new = volume(new_cell), v_old = volume(st->cell);
+                    x = -(delta + st->pressure * (v_new - v_old)) / kT + (double)(n + 1) * log(v_new / v_old);
+                    moved = -1;
+                }
                 if (x > 709.782712893384) { rc = -4; goto done; }
                 accepted = u_accept < exp(x);
                 if (accepted) {
                     memcpy(st->pos, trial, sizeof(double) * 3 * (size_t)n);
+                    if (did_cell) memcpy(st->cell, new_cell, sizeof(new_cell));
                     st->last_energy = e_new;
                 }
             }

@@ -243,14 +243,19 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     double tot = 0.0;
     for (int m = 0; m < n_moves; ++m) {
         const qmc_move_t &mv = moves[m];
-        const bool head = m == 0 || !moves[m - 1].chain;  // a composite move carries ONE probability, on its first entry
+        const bool head = m == 0 || !(moves[m - 1].chain & 1);  // a composite move carries ONE probability, on its first entry
         if (head && !(mv.probability >= 0.0)) return fail(QMC_ERR_INVALID, "move %d: negative probability", m);
         if (head) tot += mv.probability;
         if (mv.repeat < 0) return fail(QMC_ERR_INVALID, "move %d: negative repeat", m);
-        if (mv.chain && m + 1 == n_moves) return fail(QMC_ERR_INVALID, "move %d: chain = 1 on the last table entry", m);
-        if ((mv.chain || !head || mv.repeat > 1) && mv.type != QMC_MOVE_DISPLACEMENT)
-            return fail(QMC_ERR_UNSUPPORTED, "move %d: only displacement moves can form a composite move on the GPU path", m);
-        if (!head && mv.labels != moves[m - 1].labels)
+        if (mv.chain < 0 || mv.chain > 3) return fail(QMC_ERR_INVALID, "move %d: chain must be a combination of bits 0 and 1", m);
+        if ((mv.chain & 1) && m + 1 == n_moves) return fail(QMC_ERR_INVALID, "move %d: chain bit 0 set on the last table entry", m);
+        if (!head && (mv.chain & 2) != (moves[m - 1].chain & 2))
+            return fail(QMC_ERR_INVALID, "move %d: chain bit 1 (plain CompositeMove) must be the same on every entry of a chain", m);
+        // a CellMove may close a plain CompositeMove chain (the hybrid NPT move); everything else in a chain is a displacement
+        const bool closing_cell = !head && mv.type == QMC_MOVE_CELL && (mv.chain & 2) && !(mv.chain & 1) && mv.repeat <= 1;
+        if ((mv.chain || !head || mv.repeat > 1) && mv.type != QMC_MOVE_DISPLACEMENT && !closing_cell)
+            return fail(QMC_ERR_UNSUPPORTED, "move %d: a composite move is a chain of displacement moves, optionally closed by a cell move", m);
+        if (!head && mv.type == QMC_MOVE_DISPLACEMENT && mv.labels != moves[m - 1].labels)
             return fail(QMC_ERR_UNSUPPORTED, "move %d: the sub-moves of a composite move must share one label array", m);
         any_composite |= mv.chain || mv.repeat > 1;
         switch (mv.type) {
@@ -279,7 +284,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         a.mv[m].bias = mv.bias_insert;
         a.mv[m].default_label = mv.default_label;
         a.mv[m].repeat = mv.repeat > 0 ? mv.repeat : 1;
-        a.mv[m].chain = mv.chain ? 1 : 0;
+        a.mv[m].chain = mv.chain;
         a.mv[m].labels = mv.labels;
     }
     if (!(tot > 0.0)) return fail(QMC_ERR_INVALID, "move probabilities sum to zero");
@@ -290,7 +295,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     // mc/core.py:344-347 + numpy choice(p=): p /= sum(p); cdf = cumsum(p); cdf /= cdf[-1]
     double acc = 0.0;
     for (int m = 0; m < n_moves; ++m) {
-        if (m == 0 || !moves[m - 1].chain) acc += moves[m].probability / tot;
+        if (m == 0 || !(moves[m - 1].chain & 1)) acc += moves[m].probability / tot;
         a.cdf[m] = acc;  // the later entries of a chain repeat the head's value: searchsorted never lands on them
     }
     for (int m = 0; m < n_moves; ++m) a.cdf[m] /= acc;

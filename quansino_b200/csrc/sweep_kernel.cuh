@@ -310,7 +310,7 @@ __device__ __forceinline__ void propose_translation(int op, double step, double 
 
 // the random numbers of one attempt: lanes 0..3 run one Philox block each, the six / seven doubles are broadcast
 struct Draws {
-    double u_select, u_label, o0, o1, o2, u_accept, u_coin;
+    double u_select, u_label, o0, o1, o2, u_accept, u_coin, u_swap;
 };
 
 __device__ __forceinline__ Draws draw_attempt(PhiloxKey key, unsigned long long attempt, uint32_t replica, const int lane,
@@ -325,6 +325,7 @@ __device__ __forceinline__ Draws draw_attempt(PhiloxKey key, unsigned long long 
     D.o2 = __shfl_sync(FULL, d0, 2);
     D.u_accept = __shfl_sync(FULL, d1, 2);
     D.u_coin = need_coin ? __shfl_sync(FULL, d0, 3) : 0.0;
+    D.u_swap = 0.0;
     return D;
 }
 
@@ -352,6 +353,7 @@ __device__ __forceinline__ Draws read_draws(const RV &R, int a, bool need_coin) 
     D.o2 = b2.x;
     D.u_accept = b2.y;
     D.u_coin = need_coin ? d[3].x : 0.0;
+    D.u_swap = need_coin ? d[3].y : 0.0;
     return D;
 }
 
@@ -445,7 +447,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
         const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
         const int ahead = (k - k_begin) & (DRAW_AHEAD - 1);
         if (ahead == 0) draw_ahead(R, key, attempt, grep, lane);
-        const Draws D = read_draws(R, ahead, (FEAT & F_EXCHANGE) != 0);
+        const Draws D = read_draws(R, ahead, (FEAT & (F_EXCHANGE | F_COMPOSITE)) != 0);
 
         int m = 0;
         while (m < a.n_moves - 1 && a.cdf[m] <= D.u_select) ++m;
@@ -456,9 +458,11 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
         double delta = __longlong_as_double(0x7ff8000000000000LL);  // NaN
 
         if ((FEAT & F_COMPOSITE) && mv.type == QMC_MOVE_DISPLACEMENT && (mv.repeat > 1 || mv.chain)) {
-            // CompositeDisplacementMove.__call__ (moves/displacement.py:392-431) + one criteria evaluation (mc/core.py:369-377):
-            // snapshot the last accepted state in global memory, displace sub-move by sub-move with the local delta of each
-            // (committed at once: the next sub-move sees the moved atoms), test the accumulated difference, restore on reject.
+            // Composite moves + one criteria evaluation (mc/core.py:369-377).  chain bit 1 clear: CompositeDisplacementMove
+            // (moves/displacement.py:392-431: no label displaced twice); set: plain CompositeMove (moves/composite.py:43-62:
+            // independent sub-moves, optionally closed by a CellMove -- the hybrid NPT move).  Snapshot the last accepted state
+            // in global memory, displace sub-move by sub-move with the local delta of each (committed at once: the next sub-move
+            // sees the moved atoms), deform + recompute if a CellMove closes the chain, test once, restore on reject.
             for (int j = lane; j < R.n; j += 32) {
                 gx[j] = R.x(j);
                 gy[j] = R.y(j);
@@ -468,17 +472,42 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     ge[j] = R.eat(j);
                 }
             }
+            const bool exclusive = !(mv.chain & 2);
             uint32_t *disp = R.displaced();
             if (lane < (NS + 31) / 32) disp[lane] = 0u;
             __syncwarp();
-            double de_total = 0.0;
+            double de_total = 0.0, e_new = E, ncell[3] = {cell[0], cell[1], cell[2]};
             int n_moved = 0, n_drawn = 0;
+            bool did_cell = false, cell_ok = true;
             for (int mm = m;; ++mm) {
                 const MoveDev &sm = a.mv[mm];
+                if ((FEAT & F_CELL) && sm.type == QMC_MOVE_CELL) {  // closes a plain chain (validated by the library)
+                    const double u_cell = n_drawn == 0 ? D.o0 : D.u_swap;
+                    const double s = exp(__dadd_rn(-sm.step, __dmul_rn(sm.step - -sm.step, u_cell)));
+                    double scale[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        ncell[d] = s * cell[d];
+                        scale[d] = ncell[d] / cell[d];
+                    }
+                    for (int j = lane; j < R.n; j += 32) {
+                        R.x(j) = R.x(j) * scale[0];
+                        R.y(j) = R.y(j) * scale[1];
+                        R.z(j) = R.z(j) * scale[2];
+                    }
+                    __syncwarp();
+                    cell_ok = store_cell(R, ncell, a.b.pbc, pot.cut_pre, lane);
+                    if (!cell_ok) status |= QMC_STATUS_CELL_TOO_SMALL;
+                    long long fp = 0;
+                    e_new = cell_ok ? replica_full_energy<LY>(pot, R, C, lane, fp, status) : E;
+                    n_pairs += fp;
+                    did_cell = true;
+                    break;
+                }
                 const int *slab = ((FEAT & F_LABELS) && sm.labels) ? sm.labels + (size_t)r * nmax : nullptr;
                 const int reps = sm.repeat > 0 ? sm.repeat : 1;
                 for (int q = 0; q < reps; ++q) {
-                    const int na = count_available(slab, R.n, disp);
+                    const int na = count_available(slab, R.n, disp);  // `disp` stays empty for a plain CompositeMove
                     if (na == 0) continue;  // register_failure: nothing drawn
                     double ul = D.u_label, o0 = D.o0, o1 = D.o1, o2 = D.o2;
                     if (n_drawn > 0) {  // drawing sub-move c >= 1: blocks 32 + 2 (c - 1) and 33 + 2 (c - 1)
@@ -507,19 +536,31 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                             R.sig(i) = T.sig_i;
                             R.eat(i) = T.eat_i;
                         }
-                        disp[i >> 5] |= 1u << (i & 31);
+                        if (exclusive) disp[i >> 5] |= 1u << (i & 31);
                     }
                     __syncwarp();
                     moved = i;
                     ++n_moved;
                 }
-                if (!sm.chain || mm + 1 >= a.n_moves) break;
+                if (!(sm.chain & 1) || mm + 1 >= a.n_moves) break;
             }
-            if (n_moved > 0) {
-                delta = de_total;
-                const bool acc = metropolis(D.u_accept, -delta * inv_kT, status);
+            if (n_moved > 0 || did_cell) {
+                bool acc;
+                if (did_cell) {  // IsobaricCriteria on the whole change (mc/criteria.py:160-172)
+                    delta = e_new - E;
+                    const double v_new = fabs((ncell[0] * ncell[1]) * ncell[2]), v_old = fabs((cell[0] * cell[1]) * cell[2]);
+                    const double x = -(delta + a.b.pressure * (v_new - v_old)) / kT + (double)(R.n + 1) * log(v_new / v_old);
+                    acc = cell_ok && metropolis(D.u_accept, x, status);
+                    moved = -1;
+                } else {
+                    delta = de_total;
+                    acc = metropolis(D.u_accept, -delta * inv_kT, status);
+                }
                 if (acc) {
-                    E += delta;
+                    E = did_cell ? e_new : E + delta;
+                    cell[0] = ncell[0];
+                    cell[1] = ncell[1];
+                    cell[2] = ncell[2];
                 } else {
                     for (int j = lane; j < R.n; j += 32) {
                         R.x(j) = gx[j];
@@ -530,6 +571,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                             R.eat(j) = ge[j];
                         }
                     }
+                    if (did_cell) store_cell(R, cell, a.b.pbc, pot.cut_pre, lane);
                 }
                 __syncwarp();
                 accepted = acc ? 1 : 0;

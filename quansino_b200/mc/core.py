@@ -170,7 +170,8 @@ class MonteCarlo:
             st.criteria._check_supported()
             chain = st.move.lower_chain() if hasattr(st.move, "lower_chain") else [st.move.lower()]
             m = chain[0]
-            if type(st.criteria).__name__ not in self._criteria_for[m.type]:
+            judged_as = _lib.MOVE_CELL if any(c.type == _lib.MOVE_CELL for c in chain) else m.type  # a hybrid changes the volume
+            if type(st.criteria).__name__ not in self._criteria_for[judged_as]:
                 raise NotImplementedError(
                     f"{type(st.criteria).__name__} with {type(st.move).__name__} is not a combination of the GPU path"
                 )
@@ -185,8 +186,9 @@ class MonteCarlo:
                 elif st._label_tensor is None and any_exchange:
                     lab = st.move.validated_labels(self.batch.R, self.batch.n_max, n_atoms)
                     st._label_tensor = torch.from_numpy(lab).to(self.batch.device)
-                for sub in chain:  # the sub-moves of a composite share one label table
-                    sub.labels = st._label_tensor.data_ptr() if st._label_tensor is not None else None
+                for sub in chain:  # the displacement sub-moves of a composite share one label table
+                    if sub.type != _lib.MOVE_CELL:
+                        sub.labels = st._label_tensor.data_ptr() if st._label_tensor is not None else None
                 keep.append(st._label_tensor)
             slots[n] = len(entries)
             entries.extend(chain)

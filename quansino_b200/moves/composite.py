@@ -1,10 +1,11 @@
 """Composite moves (``src/quansino/moves/composite.py:22-247``, ``src/quansino/moves/displacement.py:363-455``).
 
 ``move * k`` and ``move_a + move_b`` build a composite exactly like the reference's move algebra
-(``moves/core.py:185-243``).  On the GPU path a ``CompositeDisplacementMove`` lowers to a CHAIN of ``qmc_move_t``
-entries (``repeat`` / ``chain``, include/quansino_b200.h): all sub-moves are displaced inside one attempt, no label is
-displaced twice, one criteria evaluation, one save / revert.  Composites of other move types (the docs' hybrid
-``DisplacementMove * N + CellMove``) are described but not lowered yet -- they raise ``NotImplementedError``."""
+(``moves/core.py:185-243``).  On the GPU path a composite lowers to a CHAIN of ``qmc_move_t`` entries (``repeat`` /
+``chain``, include/quansino_b200.h): all sub-moves are performed inside one attempt, one criteria evaluation, one
+save / revert.  ``CompositeDisplacementMove`` never displaces a label twice; a plain ``CompositeMove`` lets every sub-move
+choose independently and may be closed by ONE ``CellMove`` (the docs' hybrid ``DisplacementMove * N + CellMove``).  Other
+mixtures raise ``NotImplementedError``."""
 
 from __future__ import annotations
 
@@ -66,11 +67,65 @@ class CompositeMove:
     def __iter__(self):
         return iter(self.moves)
 
+    # the driver treats the composite like a DisplacementMove when it builds the label table
+    def _displacements(self) -> list:
+        from quansino_b200.moves.displacement import DisplacementMove
+
+        return [m for m in self.moves if type(m) is DisplacementMove]
+
+    @property
+    def labels(self):
+        return self._displacements()[0].labels
+
+    def validated_labels(self, n_replicas: int, n_max: int, n_atoms) -> np.ndarray:
+        return self._displacements()[0].validated_labels(n_replicas, n_max, n_atoms)
+
+    def is_identity(self, n_atoms) -> bool:
+        return self._displacements()[0].is_identity(n_atoms)
+
+    exclusive_labels: bool = False  # plain CompositeMove: every sub-move chooses its label independently
+
     def lower_chain(self) -> list:
-        raise NotImplementedError(
-            f"{type(self).__name__} of {sorted({type(m).__name__ for m in self.moves})} is not lowered to the GPU path yet; "
-            "only CompositeDisplacementMove is (SURVEY.md section 8f)"
-        )
+        """One ``qmc_move_t`` per run of identical consecutive displacement sub-moves (``repeat``), chained (``chain`` bit 0);
+        a ``CellMove`` may close a plain ``CompositeMove`` (the hybrid NPT move ``DisplacementMove * N + CellMove``)."""
+        from quansino_b200.moves.cell import CellMove
+        from quansino_b200.moves.displacement import DisplacementMove
+
+        if not self.moves:
+            raise ValueError("a composite move needs at least one move")
+        body, tail = list(self.moves), None
+        if not self.exclusive_labels and type(body[-1]) is CellMove:
+            tail = body.pop()
+        if not body or any(type(m) is not DisplacementMove for m in body):
+            raise NotImplementedError(
+                f"{type(self).__name__} of {[type(m).__name__ for m in self.moves]} is not lowered to the GPU path: a composite is a "
+                "run of DisplacementMoves" + ("" if self.exclusive_labels else ", optionally closed by ONE CellMove")
+            )
+        first = body[0]
+        entries: list = []
+        keys: list = []
+        for mv in body:
+            if mv is not first and not (np.array_equal(np.asarray(mv.labels), np.asarray(first.labels)) and mv.default_label == first.default_label):
+                raise NotImplementedError("the sub-moves of a composite move must share one label array on the GPU path")
+            m = mv.lower()
+            key = (m.op, m.step)
+            if keys and keys[-1] == key:
+                entries[-1].repeat += 1
+            else:
+                m.repeat = 1
+                entries.append(m)
+                keys.append(key)
+        if tail is not None:
+            c = tail.lower()
+            c.repeat = 1
+            entries.append(c)
+        if len(entries) > _lib.QMC_MAX_MOVES:
+            raise NotImplementedError(f"a composite move may use at most {_lib.QMC_MAX_MOVES} different sub-moves on the GPU path")
+        kind = 0 if self.exclusive_labels else 2
+        for m in entries[:-1]:
+            m.chain = kind | 1
+        entries[-1].chain = kind
+        return entries
 
     def to_dict(self) -> dict[str, Any]:
         return {"name": self.__class__.__name__, "kwargs": {"moves": [move.to_dict() for move in self.moves]}}
@@ -97,44 +152,4 @@ class CompositeDisplacementMove(CompositeMove):
     def reset(self) -> None:
         self.displaced_labels = []
 
-    # the driver treats the composite like a DisplacementMove when it builds the label table
-    @property
-    def labels(self):
-        return self.moves[0].labels
-
-    def validated_labels(self, n_replicas: int, n_max: int, n_atoms) -> np.ndarray:
-        return self.moves[0].validated_labels(n_replicas, n_max, n_atoms)
-
-    def is_identity(self, n_atoms) -> bool:
-        return self.moves[0].is_identity(n_atoms)
-
-    def lower_chain(self) -> list:
-        """One ``qmc_move_t`` per run of identical consecutive sub-moves (``repeat``), chained (``chain = 1``)."""
-        from quansino_b200.moves.displacement import DisplacementMove
-
-        if not self.moves:
-            raise ValueError("a composite move needs at least one move")
-        first = self.moves[0]
-        entries: list = []
-        keys: list = []
-        for mv in self.moves:
-            if type(mv) is not DisplacementMove:
-                raise NotImplementedError(f"{type(mv).__name__} inside a CompositeDisplacementMove is not available on the GPU path")
-            if mv is not first and not (np.array_equal(np.asarray(mv.labels), np.asarray(first.labels)) and mv.default_label == first.default_label):
-                raise NotImplementedError(
-                    "the sub-moves of a CompositeDisplacementMove must share one label array on the GPU path"
-                )  # fmt: skip
-            m = mv.lower()
-            key = (m.op, m.step)
-            if keys and keys[-1] == key:
-                entries[-1].repeat += 1
-            else:
-                m.repeat = 1
-                entries.append(m)
-                keys.append(key)
-        if len(entries) > _lib.QMC_MAX_MOVES:
-            raise NotImplementedError(f"a composite move may use at most {_lib.QMC_MAX_MOVES} different sub-moves on the GPU path")
-        for m in entries[:-1]:
-            m.chain = 1
-        entries[-1].chain = 0
-        return entries
+    exclusive_labels = True  # no label is displaced twice within one attempt (moves/displacement.py:408-416)

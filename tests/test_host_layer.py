@@ -146,8 +146,14 @@ def test_move_algebra_builds_composites_like_the_reference():
     assert [(m.op, m.step, m.repeat, m.chain) for m in chain] == [
         (_lib.OP_BALL, 0.1, 3, 1), (_lib.OP_BOX, 0.2, 1, 1), (_lib.OP_SPHERE, 0.3, 2, 0),
     ]  # fmt: skip
+    assert [(m.type, m.op, m.repeat, m.chain) for m in hybrid.lower_chain()] == [
+        (_lib.MOVE_DISPLACEMENT, _lib.OP_BALL, 2, 3), (_lib.MOVE_CELL, _lib.OP_ISOTROPIC, 1, 2),
+    ]  # fmt: skip  (plain CompositeMove: chain bit 1; the CellMove closes the chain)
+    assert [(m.repeat, m.chain) for m in CompositeMove([a, a]).lower_chain()] == [(2, 2)]
     with pytest.raises(NotImplementedError):
-        hybrid.lower_chain()
+        (CellMove() + a).lower_chain()  # a cell move anywhere but last
+    with pytest.raises(NotImplementedError):
+        CompositeMove([a, CellMove(), CellMove()]).lower_chain()
     with pytest.raises(NotImplementedError):  # different label arrays inside one composite
         (a + DisplacementMove(np.array([0, 1, 2, -1, -1, -1]))).lower_chain()
     with pytest.raises(NotImplementedError):
