@@ -77,7 +77,11 @@ typedef struct qmc_potential {
  * reverted together.  `chain` bit 1 clear: CompositeDisplacementMove (moves/displacement.py:363-455), no label is
  * displaced twice.  Bit 1 set (on every entry of the chain): plain CompositeMove (moves/composite.py:43-62), the
  * sub-moves choose independently, and a CellMove may be the last entry (the docs' hybrid NPT move
- * `DisplacementMove * N + CellMove`, judged by IsobaricCriteria).  Counters and the trace refer to the first entry. */
+ * `DisplacementMove * N + CellMove`, judged by IsobaricCriteria).  Counters and the trace refer to the first entry.
+ *
+ * Label groups (moves/displacement.py:164-167: `where(labels == label)` may select several atoms, which then move by ONE
+ * translation): `chain` bit 2 on a single displacement entry says that `labels` holds dense group ranks 0..G-1 in the
+ * order of the reference's sorted unique labels (-1 = not movable); every atom of the selected rank is displaced. */
 enum qmc_move_type { QMC_MOVE_DISPLACEMENT = 0, QMC_MOVE_CELL = 1, QMC_MOVE_EXCHANGE = 2, QMC_MOVE_HMC = 3 };
 enum qmc_op { QMC_OP_BALL = 0, QMC_OP_BOX = 1, QMC_OP_SPHERE = 2, QMC_OP_TRANSLATION = 3, QMC_OP_ISOTROPIC = 4, QMC_OP_VERLET = 5 };
 #define QMC_LABEL_NONE INT32_MIN
@@ -91,7 +95,8 @@ typedef struct qmc_move {
     int32_t n_steps;       /* Verlet max_steps */
     int32_t default_label; /* DisplacementMove.default_label; QMC_LABEL_NONE = None */
     int32_t repeat;        /* displacement moves: how many times this entry is performed per attempt (>= 1; 0 reads as 1) */
-    int32_t chain;         /* bit 0: the next table entry belongs to the same composite move; bit 1: plain CompositeMove */
+    int32_t chain;         /* bit 0: the next table entry belongs to the same composite move; bit 1: plain CompositeMove;
+                              bit 2: label groups (labels = dense group ranks) */
     int32_t *labels;       /* device [n_replicas][n_max]; NULL = arange(n_atoms) and no exchange moves */
 } qmc_move_t;
 

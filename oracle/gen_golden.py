@@ -138,6 +138,24 @@ def case_composite(variant, seed, n_attempts):
     )  # fmt: skip
 
 
+def case_groups(seed, n_attempts):
+    """Label groups (moves/displacement.py:164-167): every atom carrying the selected label moves by the same translation.
+    Dimers, one group of five, single atoms, frozen atoms (label -1); label values are neither dense nor ordered by atom."""
+    atoms, pos0, cell = cu_atoms(3, 0.05, 7171)
+    n = len(atoms)
+    labels = np.full(n, -1)
+    labels[0:40] = 100 + np.repeat(np.arange(20), 2)  # dimers (0,1), (2,3), ...
+    labels[[50, 61, 72, 83, 94]] = 7  # one group of five, with the SMALLEST label
+    labels[100:108] = 300 - np.arange(8)  # single atoms, labels decreasing with the atom index
+    mc = Canonical(atoms, temperature=300.0, max_cycles=n_attempts, default_displacement_move=DisplacementMove(labels, Ball(0.06)))
+    inject(mc, seed, 7)
+    tr = run_steps(mc, 1)
+    return dict(
+        kind="groups", seed=seed, replica=7, temperature=300.0, step_size=0.06, positions0=pos0, cell=cell, labels=labels,
+        positions=atoms.positions.copy(), **tr,
+    )  # fmt: skip
+
+
 def case_hybrid(seed, n_attempts, k):
     """The docs' hybrid NPT move (examples/orb-v3_isobaric_bulk_cu.py:45-48): `DisplacementMove * k + CellMove` is a plain
     CompositeMove -- k independent displacements (labels may repeat), one cell deformation, ONE IsobaricCriteria test -- next
@@ -259,6 +277,7 @@ def main():
         "composite_add": lambda: case_composite("add", 5002, 80),
         "composite_exhaust": lambda: case_composite("exhaust", 5003, 40),
         "composite_hybrid": lambda: case_hybrid(5004, 90, 3),
+        "label_groups": lambda: case_groups(6001, 100),
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():

@@ -562,7 +562,11 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
             int nu = unique_labels(mv->labels, n, uniq);
             if (nu > 0) {
                 int label = uniq[(int)(u_label * (double)nu)];
-                int a = atom_of_label(mv->labels, n, label);
+                /* moving indices = where(labels == label) (moves/displacement.py:164): a label GROUP moves rigidly by one
+                 * translation (translation[_moving_indices] = operation.calculate(context), :126-127) */
+                int a = -1;
+                for (int i = 0; i < n && a < 0; ++i)
+                    if (mv->labels[i] == label) a = i;
                 if (a < 0) { rc = -2; goto done; }
                 double t[3];
                 if (mv->op == QO_OP_BALL) { /* operations/displacement.py:146-153 */
@@ -580,15 +584,20 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                     for (int x = 0; x < 3; ++x) t[x] = -mv->step + (mv->step - -mv->step) * opd[x];
                 } else { rc = -1; goto done; }
                 memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
-                for (int x = 0; x < 3; ++x) trial[3 * a + x] = st->pos[3 * a + x] + t[x];
-                moved = a;
+                for (int i = 0; i < n; ++i)
+                    if (mv->labels[i] == label)
+                        for (int x = 0; x < 3; ++x) trial[3 * i + x] = st->pos[3 * i + x] + t[x];
+                moved = a; /* first member of the group */
                 double e_new;
                 int64_t np_ = qo_energy(pot, n, trial, st->cell, st->pbc, &e_new, NULL, NULL);
                 cnt[0] += np_; cnt[3] += 1;
                 memset(seen, 0, (size_t)n);
-                seen[a] = 1;
-                cnt[1] += count_neighbours(pot, n, st->pos, st->cell, st->pbc, a, seen);
-                cnt[1] += count_neighbours(pot, n, trial, st->cell, st->pbc, a, seen);
+                for (int i = 0; i < n; ++i)
+                    if (mv->labels[i] == label) {
+                        seen[i] = 1;
+                        cnt[1] += count_neighbours(pot, n, st->pos, st->cell, st->pbc, i, seen);
+                        cnt[1] += count_neighbours(pot, n, trial, st->cell, st->pbc, i, seen);
+                    }
                 for (int i = 0; i < n; ++i) cnt[2] += seen[i];
                 delta = e_new - st->last_energy;
                 double x = -delta / kT; /* mc/criteria.py:104-110 */

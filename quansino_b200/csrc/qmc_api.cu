@@ -247,7 +247,9 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         if (head && !(mv.probability >= 0.0)) return fail(QMC_ERR_INVALID, "move %d: negative probability", m);
         if (head) tot += mv.probability;
         if (mv.repeat < 0) return fail(QMC_ERR_INVALID, "move %d: negative repeat", m);
-        if (mv.chain < 0 || mv.chain > 3) return fail(QMC_ERR_INVALID, "move %d: chain must be a combination of bits 0 and 1", m);
+        if (mv.chain < 0 || mv.chain > 4) return fail(QMC_ERR_INVALID, "move %d: chain must be bits 0 / 1 (composite) or bit 2 alone (label groups)", m);
+        if ((mv.chain & 4) && (mv.type != QMC_MOVE_DISPLACEMENT || !mv.labels || !head || mv.repeat > 1))
+            return fail(QMC_ERR_UNSUPPORTED, "move %d: label groups need a single displacement move with a label array", m);
         if ((mv.chain & 1) && m + 1 == n_moves) return fail(QMC_ERR_INVALID, "move %d: chain bit 0 set on the last table entry", m);
         if (!head && (mv.chain & 2) != (moves[m - 1].chain & 2))
             return fail(QMC_ERR_INVALID, "move %d: chain bit 1 (plain CompositeMove) must be the same on every entry of a chain", m);
@@ -288,6 +290,9 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         a.mv[m].labels = mv.labels;
     }
     if (!(tot > 0.0)) return fail(QMC_ERR_INVALID, "move probabilities sum to zero");
+    if (any_exchange)
+        for (int m = 0; m < n_moves; ++m)
+            if (moves[m].chain & 4) return fail(QMC_ERR_UNSUPPORTED, "label groups cannot be combined with exchange moves on the GPU path");
     if (any_exchange)
         for (int m = 0; m < n_moves; ++m)
             if (moves[m].type != QMC_MOVE_CELL && !moves[m].labels)

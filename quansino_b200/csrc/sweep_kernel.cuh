@@ -457,7 +457,75 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
         int accepted = -1, moved = -1;
         double delta = __longlong_as_double(0x7ff8000000000000LL);  // NaN
 
-        if ((FEAT & F_COMPOSITE) && mv.type == QMC_MOVE_DISPLACEMENT && (mv.repeat > 1 || mv.chain)) {
+        if ((FEAT & F_COMPOSITE) && mv.type == QMC_MOVE_DISPLACEMENT && (mv.chain & 4)) {
+            // Label groups (moves/displacement.py:164-167, 126-127): every atom whose label equals the selected one moves by the
+            // SAME translation; one criteria evaluation.  `lab` holds dense group ranks (the library's caller normalises them in the
+            // order of the sorted unique labels), so unique_labels[idx] is rank idx.  Same snapshot / commit / restore scheme as the
+            // composite moves below.
+            const int ng = lab ? max_label(lab, R.n) + 1 : 0;
+            if (ng > 0) {
+                const int g = (int)(D.u_label * (double)ng);
+                double t[3];
+                propose_translation(mv.op, mv.step, D.o0, D.o1, D.o2, t);
+                for (int j = lane; j < R.n; j += 32) {
+                    gx[j] = R.x(j);
+                    gy[j] = R.y(j);
+                    gz[j] = R.z(j);
+                    if (POT == QMC_POT_EMT) {
+                        gs[j] = R.sig(j);
+                        ge[j] = R.eat(j);
+                    }
+                }
+                __syncwarp();
+                double de_total = 0.0;
+                int n_moved = 0;
+                for (int base = 0; base < R.n; base += 32) {
+                    const int j = base + lane;
+                    unsigned members = __ballot_sync(FULL, j < R.n && __ldcg(lab + min(j, R.n - 1)) == g);
+                    while (members) {
+                        const int i = base + __ffs(members) - 1;
+                        members &= members - 1;
+                        const double po[3] = {R.x(i), R.y(i), R.z(i)};
+                        const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
+                        const Trial T = local_delta_move<LY>(pot, R, C, lane, lt, R.n, i, po, pn, status);
+                        n_pairs += T.pairs;
+                        de_total += T.dE;
+                        commit_move<LY>(R, lane, T);
+                        if (lane == 0) {
+                            R.x(i) = pn[0];
+                            R.y(i) = pn[1];
+                            R.z(i) = pn[2];
+                            if (POT == QMC_POT_EMT) {
+                                R.sig(i) = T.sig_i;
+                                R.eat(i) = T.eat_i;
+                            }
+                        }
+                        __syncwarp();
+                        if (n_moved == 0) moved = i;
+                        ++n_moved;
+                    }
+                }
+                if (n_moved > 0) {
+                    delta = de_total;
+                    const bool acc = metropolis(D.u_accept, -delta * inv_kT, status);
+                    if (acc) {
+                        E += delta;
+                    } else {
+                        for (int j = lane; j < R.n; j += 32) {
+                            R.x(j) = gx[j];
+                            R.y(j) = gy[j];
+                            R.z(j) = gz[j];
+                            if (POT == QMC_POT_EMT) {
+                                R.sig(j) = gs[j];
+                                R.eat(j) = ge[j];
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    accepted = acc ? 1 : 0;
+                }
+            }
+        } else if ((FEAT & F_COMPOSITE) && mv.type == QMC_MOVE_DISPLACEMENT && (mv.repeat > 1 || (mv.chain & 3))) {
             // Composite moves + one criteria evaluation (mc/core.py:369-377).  chain bit 1 clear: CompositeDisplacementMove
             // (moves/displacement.py:392-431: no label displaced twice); set: plain CompositeMove (moves/composite.py:43-62:
             // independent sub-moves, optionally closed by a CellMove -- the hybrid NPT move).  Snapshot the last accepted state

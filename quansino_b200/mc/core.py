@@ -186,6 +186,14 @@ class MonteCarlo:
                 elif st._label_tensor is None and any_exchange:
                     lab = st.move.validated_labels(self.batch.R, self.batch.n_max, n_atoms)
                     st._label_tensor = torch.from_numpy(lab).to(self.batch.device)
+                grouped = bool(getattr(st.move, "_grouped", False) or getattr(getattr(st.move, "moves", [None])[0], "_grouped", False))
+                if grouped and (any_exchange or len(chain) > 1 or chain[0].repeat > 1 or m.type != _lib.MOVE_DISPLACEMENT):
+                    raise NotImplementedError(
+                        "label groups (several atoms per label, or labels not increasing with the atom index) cannot be combined "
+                        "with exchange moves or composite moves on the GPU path (SURVEY.md section 8f)"
+                    )
+                if grouped:
+                    m.chain = 4  # labels are dense group ranks (include/quansino_b200.h)
                 for sub in chain:  # the displacement sub-moves of a composite share one label table
                     if sub.type != _lib.MOVE_CELL:
                         sub.labels = st._label_tensor.data_ptr() if st._label_tensor is not None else None

@@ -17,9 +17,10 @@ class DisplacementMove(BaseMove):
     """``DisplacementMove(labels, operation=None, apply_constraints=True)`` (``moves/displacement.py:28-273``).
 
     ``labels`` has shape (n_atoms,) -- shared by every replica -- or (n_replicas, n_max).  Atoms with negative labels
-    are not displaced.  First pass of the GPU path: every non-negative label marks exactly ONE atom, and the
-    non-negative labels increase with the atom index (what ``arange`` and the reference's own ``max + 1`` appending
-    produce); label groups (molecules) are refused."""
+    are not displaced.  Label groups (several atoms per label) move rigidly by one translation, like
+    ``where(labels == label)`` in the reference; they run in the general instantiation of the sweep kernel and cannot be
+    combined with exchange moves or composite moves yet.  The fast path needs every non-negative label to mark exactly
+    ONE atom, increasing with the atom index (what ``arange`` and the reference's own ``max + 1`` appending produce)."""
 
     move_type = _lib.MOVE_DISPLACEMENT
 
@@ -27,6 +28,7 @@ class DisplacementMove(BaseMove):
         self.to_displace_labels = None
         self.displaced_labels = None
         self.default_label: int | None = None
+        self._grouped = False
         self.set_labels(labels)
         super().__init__(operation, apply_constraints)
 
@@ -53,6 +55,7 @@ class DisplacementMove(BaseMove):
             raise ValueError("labels must have shape (n_atoms,) or (n_replicas, n_max)")
         out = np.full((n_replicas, n_max), -1, dtype=np.int32)
         out[:, : lab.shape[1]] = lab
+        self._grouped = False
         for r in range(n_replicas):
             if lab.shape[1] < n_atoms[r]:
                 raise ValueError("Labels must have the same length as the number of atoms.")
@@ -60,10 +63,16 @@ class DisplacementMove(BaseMove):
             v = out[r, : n_atoms[r]]
             v = v[v >= 0]
             if len(v) and np.any(np.diff(v) <= 0):
-                raise NotImplementedError(
-                    "the GPU path needs every non-negative label to mark exactly one atom, increasing with the atom "
-                    "index; label groups (molecular moves) are SURVEY.md section 8f"
-                )
+                self._grouped = True
+        if self._grouped:
+            # label groups (several atoms per label) or labels that do not increase with the atom index: the kernel selects by
+            # RANK among the sorted unique labels (`unique_labels[idx]`, moves/displacement.py:164, 180-184), so the table is
+            # rewritten as dense ranks; every atom of the selected rank moves by the same translation
+            for r in range(n_replicas):
+                v = out[r, : n_atoms[r]]
+                movable = v >= 0
+                if movable.any():
+                    v[movable] = np.unique(v[movable], return_inverse=True)[1].astype(np.int32)
         return out
 
     def is_identity(self, n_atoms: np.ndarray) -> bool:

@@ -194,6 +194,39 @@ def test_ragged_batch_and_frozen_atoms(cuda_lib):
     assert np.array_equal(out.n_atoms, n_atoms)
 
 
+def test_label_groups_move_rigidly(cuda_lib):
+    """Per-replica label tables with groups of different sizes, ragged atom counts and frozen atoms, against the oracle."""
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+
+    R, n_max, n_att = 4, 108, 120
+    pos, cell, n = cu_replicas(3, R, seed=29)
+    n_atoms = np.array([108, 108, 96, 70], dtype=np.int32)
+    rng = np.random.default_rng(5)
+    labels = np.full((R, n_max), -1)
+    for r in range(R):
+        labels[r, : n_atoms[r]] = rng.integers(-1, 25 + 10 * r, size=n_atoms[r]) * 3  # sparse, unordered, repeated label values
+        pos[r, n_atoms[r] :] = 0.0
+    atoms = BatchedAtoms(pos.copy(), cell, n_atoms, "Cu", (True, True, True), EMT())
+    mc = Canonical(atoms, temperature=500.0, seed=47, trace=True, max_cycles=n_att, resync_interval=0,
+                   default_displacement_move=DisplacementMove(labels, operations.Box(0.05)))  # fmt: skip
+    mc.run(1)
+    tr, out, par = mc.last_trace, mc.download(), oracle_par(EMT())
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, n_atoms=int(n_atoms[r]), temperature=500.0)
+        lab = np.where(labels[r] < 0, -1, labels[r]).astype(np.int32)
+        ref = capi.mc_run(par, rep, [capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BOX, step=0.05, labels=lab)], 47, r, 0, n_att)
+        assert np.array_equal(tr["accepted"][r], ref["accepted"])
+        assert np.array_equal(tr["moved"][r], ref["moved"])  # first member of the displaced group
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=RTOL_E, atol=1e-12)
+        np.testing.assert_allclose(out.positions[r, : n_atoms[r]], rep.positions[: n_atoms[r]], rtol=0, atol=1e-12)
+        moved_rows = np.any(np.abs(out.positions[r, : n_atoms[r]] - pos[r, : n_atoms[r]]) > 0, axis=1)
+        assert not np.any(moved_rows & (lab[: n_atoms[r]] < 0))  # frozen atoms never move
+    tracked = mc.batch.energy.cpu().numpy().copy()
+    np.testing.assert_allclose(tracked, mc.batch.energy_full().cpu().numpy(), rtol=1e-11, atol=1e-12)
+
+
 def test_no_movable_atoms_means_failed_moves(cuda_lib):
     """All labels negative: every attempt fails (the reference's None), nothing changes, failed counter counts."""
     from quansino_b200 import EMT, BatchedAtoms, operations

@@ -169,8 +169,10 @@ def test_label_validation():
     assert np.array_equal(mv.unique_labels, [0, 1, 2])
     lab = mv.validated_labels(2, 6, np.array([5, 5]))
     assert lab.shape == (2, 6) and np.array_equal(lab[0], [0, -1, 1, 2, -1, -1])
-    with pytest.raises(NotImplementedError):  # label groups (molecules)
-        DisplacementMove(np.array([0, 0, 1])).validated_labels(1, 3, np.array([3]))
+    assert not mv._grouped
+    grp = DisplacementMove(np.array([40, 40, 7, -1, 300, 7]))  # label groups: rewritten as ranks of the sorted unique labels
+    assert np.array_equal(grp.unique_labels, [7, 40, 300])
+    assert np.array_equal(grp.validated_labels(1, 7, np.array([6]))[0], [1, 1, 0, -1, 2, 0, -1]) and grp._grouped
     with pytest.raises(ValueError):
         DisplacementMove(np.arange(3)).validated_labels(1, 8, np.array([5]))
     assert DisplacementMove(np.arange(5)).is_identity(np.array([5, 5]))
