@@ -282,14 +282,15 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const RV &R, c
 // holds j only; the image flags are recomputed when the queue is expanded.
 template <class RV, class CELL>
 __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const CELL &C, const int lane, const unsigned lt, int n_scan,
-                                         int i_excl, const double po[3], const double pn[3], int &n2, int &xstart, int &status) {
+                                         int i_excl, const double po[3], const double pn[3], int &n2, int &xstart, int &status,
+                                         int tile_first = 0, int tile_step = 1) {
     constexpr bool TRACK = RV::EMT;
     static_assert(RV::CAPE % 2 == 0, "paired list slots need an even capacity");
     uint32_t *queue = R.queue();
     const bool p0 = C.per(0), p1 = C.per(1), p2 = C.per(2);
     const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);
     int cnt = 0, nq = 0;
-    for (int base = 0; base < n_scan; base += 32) {
+    for (int base = tile_first * 32; base < n_scan; base += 32 * tile_step) {
         const int j = base + lane;
         const bool valid = j < n_scan && j != i_excl;
         const int jc = valid ? j : 0;

@@ -32,11 +32,12 @@ struct LayoutB {
     static constexpr int CELLC = EMT ? 5 * NS : 3 * NS;  // 10 doubles
     static constexpr int RED = CELLC + 10;               // BW * 4 doubles
     static constexpr int PP_B = (RED + BW * 4) * 8;      // bytes
-    static constexpr int REG0_B = round_up(PP_B + (EMT ? NS * 4 : 0), 8);
+    static constexpr int DRAW_B = round_up(PP_B + (EMT ? NS * 4 : 0), 16);  // the draws of DRAW_AHEAD attempts, shared by the BW warps
+    static constexpr int REG0_B = DRAW_B + DRAW_AHEAD * 64;
     // one warp region: lr [CAPE + TAILN] doubles, l2 [NSW + 8] u16, xj [XCAPB] u16
     static constexpr int L2_OFF = (CAPE + TAILN) * 8;
     static constexpr int XJ_OFF = L2_OFF + (EMT ? (NSW + 8) * 2 : 0);
-    static constexpr int REG_B = round_up(XJ_OFF + (EMT ? XCAPB * 2 : 0), 8);
+    static constexpr int REG_B = round_up(XJ_OFF + (EMT ? XCAPB * 2 : 0), 16);  // list regions are 16-byte aligned (paired slots)
     static constexpr int BYTES = round_up(REG0_B + BW * REG_B, 16);
     // one wide CTA per SM holding REPS replicas of BW warps each (the warps of one CTA progress evenly, see Layout)
     static constexpr int fit = (SMEM_PER_SM - 1024) / BYTES;
@@ -62,6 +63,7 @@ struct RepB {
     __device__ __forceinline__ double &cellc(int k) const { return b[LY::CELLC + k]; }
     __device__ __forceinline__ double &red(int k) const { return b[LY::RED + k]; }
     __device__ __forceinline__ uint32_t &pp(int j) const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(b) + LY::PP_B)[j]; }
+    __device__ __forceinline__ double2 *draws() const { return reinterpret_cast<double2 *>(reinterpret_cast<char *>(b) + LY::DRAW_B); }
     __device__ __forceinline__ double &lr(int e) const { return wb[e]; }
     __device__ __forceinline__ double &tail(int e) const { return wb[LY::CAPE + e]; }
     __device__ __forceinline__ uint32_t *queue() const { return reinterpret_cast<uint32_t *>(wb + LY::CAPE); }
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(LayoutB<POT, NS>::REPS * BW * 32, 1) sweep_blo
     double E = a.b.energy[r];
     const double temperature = a.b.temperature[r];
     const double kT = temperature * KB;
+    const double inv_kT = 1.0 / kT;
     int n_ex = (FEAT & F_EXCHANGE) ? a.b.n_exchange[r] : 0;
     const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
     const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
@@ -194,7 +197,14 @@ __global__ void __launch_bounds__(LayoutB<POT, NS>::REPS * BW * 32, 1) sweep_blo
 
     for (int k = 0; k < a.n_attempts; ++k) {
         const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
-        const Draws D = draw_attempt(key, attempt, grep, lane, (FEAT & F_EXCHANGE) != 0);  // every warp draws the same numbers
+        // the draws of DRAW_AHEAD attempts at a time, into one region shared by the BW warps: every warp writes the same values;
+        // the barrier keeps a warp that ran ahead through attempts without barriers (failed moves) from overwriting them early
+        const int ahead = k & (DRAW_AHEAD - 1);
+        if (ahead == 0) {
+            rep_sync();
+            draw_ahead(R, key, attempt, grep, lane);
+        }
+        const Draws D = read_draws(R, ahead, (FEAT & F_EXCHANGE) != 0);
         int m = 0;
         while (m < a.n_moves - 1 && a.cdf[m] <= D.u_select) ++m;
         const MoveDev &mv = a.mv[m];
@@ -267,12 +277,14 @@ __global__ void __launch_bounds__(LayoutB<POT, NS>::REPS * BW * 32, 1) sweep_blo
                     }
                 }
             }
+            const bool paired = has_old && has_new;  // displacement: old / new terms of a neighbour in adjacent slots (scan_both)
             if (has_old || has_new) {  // block-uniform
                 // ---- phase 1: own tiles: scan + pair functions ----
                 DeltaAcc acc = {0.0, 0.0, 0};
                 int n2, xstart;
-                const int cnt = scan_neighbours<RV, 0>(pot, R, C, lane, lt, R.n, has_old ? i : -1, has_old, has_new, po, pn, n2, xstart,
-                                                        status, warp, BW);
+                const int cnt = paired ? scan_both<RV>(pot, R, C, lane, lt, R.n, i, po, pn, n2, xstart, status, warp, BW)
+                                       : scan_neighbours<RV, 0>(pot, R, C, lane, lt, R.n, has_old ? i : -1, has_old, has_new, po, pn, n2,
+                                                                xstart, status, warp, BW);
                 eval_list<RV, 0>(pot, R, lane, cnt, xstart, acc);
                 n_pairs += acc.pairs;
                 block_put(R, warp, lane, 0, warp_sum(acc.v));
@@ -286,15 +298,26 @@ __global__ void __launch_bounds__(LayoutB<POT, NS>::REPS * BW * 32, 1) sweep_blo
                     double part = 0.0, e_i_lane = 0.0;
                     const bool extra = has_new && warp == 0;
                     const int total = n2 + (extra ? 1 : 0);
+                    double2 *slots = reinterpret_cast<double2 *>(&R.lr(0));
                     for (int e = lane; e < total; e += 32) {
                         const bool nb = e < n2;
                         const int j = nb ? R.l2(e) : 0;
-                        const double sn = nb ? (R.sig(j) + gathered_dsigma(R, j)) : sig_i;
+                        double sn;
+                        if (paired) {
+                            const double2 t = nb ? slots[e] : make_double2(0.0, 0.0);
+                            sn = nb ? R.sig(j) + (t.y - t.x) : sig_i;
+                        } else {
+                            sn = nb ? (R.sig(j) + gathered_dsigma(R, j)) : sig_i;
+                        }
                         const double eold = nb ? R.eat(j) : (has_old ? R.eat(i) : 0.0);
                         const double en = emt_embed(pot, sn);
                         part += en - eold;
-                        if (nb) R.tail(e) = en;
-                        else e_i_lane = en;
+                        if (nb) {
+                            if (paired) slots[e] = make_double2(sn, en);  // trial (sigma_1, E_atom) back into the pair of slots
+                            else R.tail(e) = en;
+                        } else {
+                            e_i_lane = en;
+                        }
                     }
                     if (extra) eat_i = __shfl_sync(FULL, e_i_lane, n2 & 31);
                     if (!has_new && warp == 0 && lane == 0) part -= R.eat(i);
@@ -306,7 +329,7 @@ __global__ void __launch_bounds__(LayoutB<POT, NS>::REPS * BW * 32, 1) sweep_blo
                 }
                 bool acc_ok;
                 if (is_disp) {
-                    acc_ok = metropolis(D.u_accept, -delta / kT, status);
+                    acc_ok = metropolis(D.u_accept, -delta * inv_kT, status);
                 } else {
                     bool ov;
                     const double prob = gc_probability(delta, pd, n_ex, a.b.accessible_volume, a.b.exchange_mass, temperature,
@@ -316,10 +339,17 @@ __global__ void __launch_bounds__(LayoutB<POT, NS>::REPS * BW * 32, 1) sweep_blo
                 }
                 if (acc_ok) {
                     if (POT == QMC_POT_EMT) {
+                        const double2 *slots = reinterpret_cast<const double2 *>(&R.lr(0));
                         for (int e = lane; e < n2; e += 32) {
                             const int j = R.l2(e);
-                            R.sig(j) = R.sig(j) + gathered_dsigma(R, j);
-                            R.eat(j) = R.tail(e);
+                            if (paired) {
+                                const double2 t = slots[e];
+                                R.sig(j) = t.x;
+                                R.eat(j) = t.y;
+                            } else {
+                                R.sig(j) = R.sig(j) + gathered_dsigma(R, j);
+                                R.eat(j) = R.tail(e);
+                            }
                         }
                     }
                     if (has_new && warp == 0 && lane == 0) {
