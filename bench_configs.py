@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Secondary measurements: the other configurations of BASELINE.json (C3 isobaric, C4 grand-canonical LJ, C5 HMC) on one
-GPU.  Not part of the bench.py contract; results are recorded under profiles/.  Usage: python bench_configs.py [c3|c4|c5|composite] ..."""
+GPU.  Not part of the bench.py contract; results are recorded under profiles/.  Usage: python bench_configs.py [c3|c4|c5|c5pt|composite] ... (c5pt also under torchrun)"""
 
 from __future__ import annotations
 
@@ -94,6 +94,70 @@ def c5(R=64, repeat=8, n_steps=100, attempts=1):
             "acceptance": float(mc.counters()[:, 0, 1].sum() / (R * attempts)), "wall": time.perf_counter() - t0}  # fmt: skip
 
 
+def c5pt(R_global=64, repeat=8, n_steps=100, rounds=4):
+    """C5 as BASELINE.json states it: 64-temperature parallel tempering of 2048-atom Cu EMT under HMC, replicas sharded over
+    the ranks of one node (run under torchrun for N > 1), one swap round after every trajectory: all-gather of the energies and
+    temperatures over NCCL, the swap kernel on every rank, temperatures move, configurations never do.  Prints whole-job
+    throughput, the share of the exchange step, and checksums that must not depend on the number of ranks."""
+    import os
+
+    import torch.distributed as dist
+
+    from quansino_b200.mc.tempering import ReplicaExchange, shard
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    offset, count = shard(R_global, world, rank)
+    pos0, cell = fcc_cubic("Cu", repeat)
+    n = len(pos0)
+    rng = np.random.default_rng(5)
+    pos_all = pos0[None] + rng.normal(scale=0.03, size=(R_global, n, 3))
+    temps_all = 300.0 * 4.0 ** (np.arange(R_global) / max(R_global - 1, 1))  # geometric ladder 300 -> 1200 K
+    atoms = BatchedAtoms(pos_all[offset : offset + count], cell, np.full(count, n, np.int32), "Cu", (True,) * 3, EMT())
+    mc = HamiltonianCanonical(atoms, temperature=temps_all[offset : offset + count], max_cycles=1, seed=5, resync_interval=0, device=device,
+                              replica_offset=offset, default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=1.0, max_steps=n_steps)))  # fmt: skip
+    pt = ReplicaExchange.for_driver(mc, n_global=R_global)
+    mc.validate_simulation()
+    mc.max_steps = 10**12
+
+    def one_round():
+        for _ in mc.step():
+            pass
+        mc.step_count += 1
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        pt.exchange()
+        ev1.record()
+        return ev0, ev1
+
+    one_round()  # warm-up (neighbour lists, NCCL channels)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    evs = [one_round() for _ in range(rounds)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t_all = pt.temperatures if world == 1 else None
+    from quansino_b200.mc.tempering import gather_replicas
+
+    e_all = gather_replicas(mc.batch.energy, pt.counts).cpu().numpy()
+    t_all = gather_replicas(mc.batch.temperature, pt.counts).cpu().numpy()
+    exch_ms = sum(a.elapsed_time(b) for a, b in evs) / rounds
+    out = {"config": f"C5 parallel tempering: {R_global} temperatures x {n}-atom Cu EMT HMC ({n_steps} x 1 fs), {world} GPU(s)",
+           "trajectories_per_s": R_global * rounds / dt, "s_per_round": dt / rounds, "exchange_ms_per_round": exch_ms,
+           "swap_acceptance": pt.n_accepted / max(pt.n_pairs, 1), "ladder_is_permutation": bool(np.allclose(np.sort(t_all), temps_all)),
+           "checksum_energy": float(np.sum(e_all * np.arange(1, R_global + 1))), "checksum_ladder": float(np.sum(t_all * np.arange(1, R_global + 1)))}  # fmt: skip
+    if world > 1:
+        dist.destroy_process_group()
+    return out if rank == 0 else None
+
+
 def composite(R=4096, k=4, steps=20):
     """C2 workload with CompositeDisplacementMove = DisplacementMove * k (k atoms per criteria evaluation)."""
     from quansino_b200.mc import Canonical
@@ -119,4 +183,6 @@ if __name__ == "__main__":
         if w == "c5small":
             print(json.dumps(c5(R=64, repeat=4, n_steps=20)), flush=True)
         else:
-            print(json.dumps({"c3": c3, "c4": c4, "c5": c5, "composite": composite}[w]()), flush=True)
+            res = {"c3": c3, "c4": c4, "c5": c5, "c5pt": c5pt, "composite": composite}[w]()
+            if res is not None:
+                print(json.dumps(res), flush=True)
