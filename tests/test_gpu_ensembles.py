@@ -290,3 +290,39 @@ def test_composite_displacement_matches_oracle(cuda_lib):
     # the tracked energy still equals a fresh full evaluation after composite commits and restores
     tracked = mc.batch.energy.cpu().numpy().copy()
     np.testing.assert_allclose(tracked, mc.batch.energy_full().cpu().numpy(), rtol=1e-11, atol=1e-12)
+
+
+def test_composite_and_label_groups_with_lennard_jones(cuda_lib):
+    """The composite and label-group paths on the pair potential (no embedding caches), non-periodic cluster, against the oracle."""
+    from quansino_b200 import operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.mc.criteria import CanonicalCriteria
+    from quansino_b200.moves import DisplacementMove
+
+    R, n_max, n_att = 4, 64, 160
+    atoms, pos, cell, n = _gc_setup(R, n_max, 0.0)
+    groups = np.concatenate([np.repeat(np.arange(10), 2) * 5 + 3, np.full(n - 20, -1)])  # ten dimers, the rest frozen
+    groups[30:36] = 1  # and one group of six with the smallest label
+    lab = np.arange(n)
+    mc = Canonical(atoms, temperature=300.0, seed=321, trace=True, max_cycles=n_att, resync_interval=0,
+                   default_displacement_move=DisplacementMove(groups, operations.Ball(0.08)))  # fmt: skip
+    mc.add_move(DisplacementMove(lab, operations.Box(0.05)) * 3, criteria=CanonicalCriteria(), name="triple", probability=1.0)
+    mc.run(1)
+    tr, out = mc.last_trace, mc.download()
+    par = LJParams(sigma=2.5, epsilon=0.1)
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, pbc=(0, 0, 0), n_atoms=n, temperature=300.0, mass=195.084)
+        lg = np.full(n_max, -1, np.int32)
+        lg[:n] = groups
+        la = np.full(n_max, -1, np.int32)
+        la[:n] = lab
+        specs = [
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.08, probability=1.0, labels=lg),
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BOX, step=0.05, probability=1.0, repeat=3, chain=0, labels=la),
+        ]
+        ref = capi.mc_run(par, rep, specs, 321, r, 0, n_att)
+        assert np.array_equal(tr["move"][r], ref["move"]) and (ref["move"] == 0).sum() > 20 and (ref["move"] == 1).sum() > 20
+        assert np.array_equal(tr["accepted"][r], ref["accepted"]), f"accept/reject sequence differs for replica {r}"
+        assert np.array_equal(tr["moved"][r], ref["moved"])
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(out.positions[r, :n], rep.positions[:n], rtol=0, atol=1e-11)

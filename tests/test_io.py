@@ -155,3 +155,49 @@ def test_default_observers_write_logger_and_trajectory(cuda_lib, tmp_path):
     assert len(frames) == 3 * 2 and [f["info"]["replica"] for f in frames[:2]] == ["0", "3"] and frames[-1]["info"]["step"] == "4"
     np.testing.assert_allclose(frames[-1]["positions"], mc.download().positions[3], atol=5e-9)
     assert abs(float(frames[-1]["info"]["energy"]) - mc.context.last_potential_energy[3]) < 1e-12
+
+
+@pytest.mark.gpu
+def test_grand_canonical_restart_keeps_integer_state(cuda_lib, tmp_path):
+    """Variable atom counts, label tables and exchange counters survive a restart bit for bit."""
+    from quansino_b200 import BatchedAtoms, LennardJones
+    from quansino_b200.io import RestartObserver, read_restart
+    from quansino_b200.mc import GrandCanonical
+    from quansino_b200.moves import DisplacementMove, ExchangeMove
+    from quansino_b200.systems import octahedron, rattle
+
+    pos0, cell = octahedron("Pt", 4, 10.0)
+    n, R, n_max = len(pos0), 3, 64
+    pos = np.zeros((R, n_max, 3))
+    for r in range(R):
+        pos[r, :n] = rattle(pos0, 0.02, 900 + r)
+
+    def build():
+        atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Pt", (False,) * 3, LennardJones(sigma=2.5, epsilon=0.1))
+        mc = GrandCanonical(atoms, exchange_atoms=("Pt", (0.0, 0.0, 0.0)), temperature=300.0, chemical_potential=-0.5,
+                            number_of_exchange_particles=0, max_cycles=200, seed=5, resync_interval=0,
+                            default_displacement_move=DisplacementMove(np.arange(n)), default_exchange_move=ExchangeMove(np.full(n, -1)))  # fmt: skip
+        mc.moves["default_displacement_move"].probability = 0.5
+        mc.moves["default_exchange_move"].probability = 0.5
+        return mc
+
+    straight = build()
+    straight.run(4)
+    first = build()
+    first.attach(RestartObserver(first, tmp_path / "gc.json", interval=2, mode="w"), name="restart")
+    first.run(2)
+    first.close()
+    data = read_restart(tmp_path / "gc.json")
+    assert data["attributes"]["step_count"] == 2 and set(data["labels"]) == {"default_displacement_move", "default_exchange_move"}
+    second = build()
+    second.validate_simulation()  # creates nothing that load_state does not overwrite
+    second.load_state(data)
+    second.run(2)
+    a, b = straight.download(), second.download()
+    assert np.array_equal(a.n_atoms, b.n_atoms) and np.array_equal(a.positions, b.positions)
+    assert np.array_equal(straight.number_of_exchange_particles, second.number_of_exchange_particles)
+    for name in ("default_displacement_move", "default_exchange_move"):
+        assert np.array_equal(straight.labels(name), second.labels(name))
+    assert np.array_equal(straight.counters(), second.counters())
+    assert np.array_equal(straight.batch.energy.cpu().numpy(), second.batch.energy.cpu().numpy())
+    assert (a.n_atoms != n).any()  # the run did insert / delete atoms
