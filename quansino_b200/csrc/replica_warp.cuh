@@ -32,7 +32,7 @@ constexpr int kScanUnroll = QMC_SCAN_UNROLL;
 #else
 constexpr int kScanUnroll = 1;
 #endif
-constexpr int XCAP = 64;             // capacity for second-image list entries of one attempt
+constexpr int XCAP = 64;             // capacity for second-image list entries of one attempt (cells of >= 64 atoms)
 constexpr unsigned NOPOS = 0xFFFFu;  // pp half-word: no list entry
 constexpr unsigned NOITEM = 0xFFFFFFFFu;  // queue word: empty
 constexpr int DRAW_AHEAD = 4;  // attempts whose random numbers one Philox round of the warp produces (4 lanes per attempt)
@@ -60,7 +60,10 @@ struct Layout {
     static constexpr int PP_B = (CELLC + 10) * 8;  // bytes
     static constexpr int L2_B = PP_B + (EMT ? NS * 4 : 0);
     static constexpr int XJ_B = L2_B + (EMT ? NS * 2 : 0);
-    static constexpr int DRAW_B = round_up(XJ_B + (EMT ? XCAP * 2 : 0), 16);  // DRAW_AHEAD attempts x 4 Philox blocks x 2 doubles
+    // second-image entries of one attempt: a 32-atom cell (L = 7.2 A) holds 31 nearest images but 78 neighbour images per
+    // position, i.e. ~47 second images per side and ~94 for a displacement; from 64 atoms on, two dozen
+    static constexpr int XCAPN = NS <= 64 ? 128 : XCAP;
+    static constexpr int DRAW_B = round_up(XJ_B + (EMT ? XCAPN * 2 : 0), 16);  // DRAW_AHEAD attempts x 4 Philox blocks x 2 doubles
     static constexpr int CNT_B = DRAW_B + DRAW_AHEAD * 64;  // attempted / accepted / failed of this launch per move, u32
     static constexpr int DISP_B = CNT_B + QMC_MAX_MOVES * 3 * 4;  // bitmap of the atoms a composite move displaced so far
     static constexpr int BYTES = round_up(DISP_B + round_up(NS, 32) / 8, 16);
@@ -84,7 +87,7 @@ template <class LY>
 struct Rep {
     static constexpr bool EMT = LY::EMT;
     static constexpr int CAPE = LY::CAPE;
-    static constexpr int XCAPN = XCAP;
+    static constexpr int XCAPN = LY::XCAPN;
     static constexpr int QCAP = 2 * (LY::CAPL - LY::CAPE);  // work items the tail can hold
     double *b;  // warp base in shared memory
     int n;      // atoms

@@ -1,0 +1,104 @@
+"""Every atom-capacity class of the sweep kernels (32 ... 1024 atoms per replica) against the CPU oracle: the 32-atom cell needs
+up to seven periodic images per neighbour, the 500-atom cell is BASELINE.json's isobaric configuration, 864 atoms fill the
+largest class.  Also a batch of several waves of CTAs."""
+
+import numpy as np
+import pytest
+
+from oracle import capi
+from tests.helpers import cu_replicas, oracle_par, oracle_run
+
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_variant")]
+
+BAR = 6.241509125883258e-07
+
+
+@pytest.mark.parametrize("repeat,n_attempts", [(2, 200), (4, 120), (6, 60)])
+def test_canonical_capacity_classes(cuda_lib, repeat, n_attempts):
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+    import os
+
+    if repeat == 2 and os.environ.get("QMC_FORCE_KERNEL") in ("block", "cached"):
+        pytest.skip("the CTA-per-replica and pair-cache kernels are sized for cells of >= 64 atoms (never selected below 256 / on request only)")
+    R = 3
+    pos, cell, n = cu_replicas(repeat, R, seed=40 + repeat)
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    mc = Canonical(atoms, temperature=400.0, seed=700 + repeat, trace=True, max_cycles=n_attempts, resync_interval=0,
+                   pair_cache=os.environ.get("QMC_FORCE_KERNEL") == "cached",
+                   default_displacement_move=DisplacementMove(np.arange(n), operations.Ball(0.12)))  # fmt: skip
+    e0 = mc.batch.energy_full().cpu().numpy().copy()
+    mc.run(1)
+    tr, out = mc.last_trace, mc.download()
+    par = oracle_par(mc.batch.calc)
+    reps, otr = oracle_run(par, pos, np.full(R, n), cell, (1, 1, 1), [dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_BALL, step=0.12)],
+                           700 + repeat, n_attempts, range(R), temperature=400.0)  # fmt: skip
+    for r in range(R):
+        ref0 = capi.energy(par, pos[r], cell, (1, 1, 1))
+        assert abs(e0[r] - ref0["energy"]) <= 1e-10 * abs(ref0["energy"])
+        assert np.array_equal(tr["accepted"][r], otr[r]["accepted"]), f"accept/reject sequence differs for replica {r}"
+        assert np.array_equal(tr["moved"][r], otr[r]["moved"])
+        np.testing.assert_allclose(tr["energy"][r], otr[r]["energy"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(out.positions[r], reps[r].positions, rtol=0, atol=1e-12)
+    assert int(mc.batch.status.max().item()) == 0
+
+
+def test_isobaric_500_atoms(cuda_lib):
+    """BASELINE.json configuration C3 at test size: 500-atom cells, displacement and cell moves (cell probability raised)."""
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Isobaric
+    from quansino_b200.moves import CellMove, DisplacementMove
+
+    R, n_attempts, p_cell = 3, 60, 0.12
+    pos, cell, n = cu_replicas(5, R, seed=55)
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    mc = Isobaric(atoms, temperature=300.0, pressure=1.0 * BAR, seed=808, trace=True, max_cycles=n_attempts, resync_interval=0,
+                  default_displacement_move=DisplacementMove(np.arange(n), operations.Ball(0.1)),
+                  default_cell_move=CellMove(operations.IsotropicDeformation(0.01)))  # fmt: skip
+    mc.moves["default_cell_move"].probability = p_cell
+    mc.moves["default_displacement_move"].probability = 1.0 - p_cell
+    mc.run(1)
+    tr, out = mc.last_trace, mc.download()
+    par = oracle_par(mc.batch.calc)
+    moves = [dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_BALL, step=0.1, probability=1.0 - p_cell),
+             dict(type=capi.MOVE_CELL, op=capi.OP_ISOTROPIC, step=0.01, probability=p_cell)]  # fmt: skip
+    reps, otr = oracle_run(par, pos, np.full(R, n), cell, (1, 1, 1), moves, 808, n_attempts, range(R), temperature=300.0, pressure=1.0 * BAR)
+    n_cell = 0
+    for r in range(R):
+        assert np.array_equal(tr["move"][r], otr[r]["move"])
+        assert np.array_equal(tr["accepted"][r], otr[r]["accepted"]), f"accept/reject sequence differs for replica {r}"
+        np.testing.assert_allclose(tr["energy"][r], otr[r]["energy"], rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(out.positions[r], reps[r].positions, rtol=0, atol=1e-10)
+        np.testing.assert_allclose(out.cell[r], reps[r].cell, rtol=1e-13)
+        n_cell += int((otr[r]["move"] == 1).sum())
+    assert n_cell >= 6
+
+
+def test_several_waves_of_replicas(cuda_lib):
+    """10 000 replicas = 2.4 waves of CTAs: every replica is written exactly once, sampled replicas match the oracle."""
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+    import os
+
+    if os.environ.get("QMC_FORCE_KERNEL") == "cached":
+        pytest.skip("the pair-term cache of 10 000 replicas is a 3.7 GB allocation; covered at smaller sizes")
+    R = 10000
+    pos, cell, n = cu_replicas(3, R, seed=3)
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    mc = Canonical(atoms, temperature=300.0, seed=4242, trace=True, max_cycles=n, resync_interval=0,
+                   default_displacement_move=DisplacementMove(np.arange(n), operations.Ball(0.1)))  # fmt: skip
+    mc.run(1)
+    tr, out = mc.last_trace, mc.download()
+    cnt = mc.counters()
+    assert np.array_equal(cnt[:, 0, 0], np.full(R, n)) and np.array_equal(cnt[:, 0, 1], tr["accepted"].sum(axis=1))
+    ids = [0, 4143, 4144, 8287, 8288, 9999]
+    par = oracle_par(mc.batch.calc)
+    reps, otr = oracle_run(par, pos[ids], np.full(len(ids), n), cell, (1, 1, 1), [dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_BALL, step=0.1)],
+                           4242, n, ids, temperature=300.0)  # fmt: skip
+    for k, r in enumerate(ids):
+        assert np.array_equal(tr["accepted"][r], otr[k]["accepted"])
+        np.testing.assert_allclose(out.positions[r], reps[k].positions, rtol=0, atol=1e-12)
+    tracked = mc.batch.energy.cpu().numpy().copy()
+    np.testing.assert_allclose(tracked, mc.batch.energy_full().cpu().numpy(), rtol=1e-11, atol=1e-12)
