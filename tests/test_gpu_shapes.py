@@ -102,3 +102,54 @@ def test_several_waves_of_replicas(cuda_lib):
         np.testing.assert_allclose(out.positions[r], reps[k].positions, rtol=0, atol=1e-12)
     tracked = mc.batch.energy.cpu().numpy().copy()
     np.testing.assert_allclose(tracked, mc.batch.energy_full().cpu().numpy(), rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["orthorhombic", "slab", "unwrapped"])
+def test_cell_geometries(cuda_lib, case):
+    """Unequal cell edges, a slab (pbc T, T, F) and atoms that drifted several cells away from the box: positions are never
+    wrapped by the reference (moves/displacement.py:109-141), the images must still be found."""
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+    from quansino_b200.systems import fcc_cubic, rattle
+    import os
+
+    R, n_attempts = 3, 150
+    pos0, cell0 = fcc_cubic("Cu", 3)
+    L = cell0[0, 0]
+    pbc = (True, True, True)
+    if case == "orthorhombic":  # two cubes stacked along z: 216 atoms in a 10.83 x 10.83 x 21.66 cell
+        pos0 = np.concatenate([pos0, pos0 + np.array([0.0, 0.0, L])])
+        cell = np.diag([L, L, 2 * L])
+    elif case == "slab":
+        cell = np.diag([L, L, L + 12.0])
+        pbc = (True, True, False)
+    else:
+        cell = cell0
+    n = len(pos0)
+    pos = np.stack([rattle(pos0, 0.05, 60 + r) for r in range(R)])
+    if case == "unwrapped":
+        rng = np.random.default_rng(8)
+        pos += rng.integers(-3, 4, size=(R, n, 3)) * L  # every atom somewhere within +-3 cells
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", pbc, EMT())
+    mc = Canonical(atoms, temperature=500.0, seed=99, trace=True, max_cycles=n_attempts, resync_interval=0,
+                   pair_cache=os.environ.get("QMC_FORCE_KERNEL") == "cached",
+                   default_displacement_move=DisplacementMove(np.arange(n), operations.Sphere(0.1)))  # fmt: skip
+    mc.run(1)
+    tr, out = mc.last_trace, mc.download()
+    par = oracle_par(mc.batch.calc)
+    pbc_i = tuple(int(b) for b in pbc)
+    reps, otr = oracle_run(par, pos, np.full(R, n), cell, pbc_i, [dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_SPHERE, step=0.1)], 99,
+                           n_attempts, range(R), temperature=500.0)  # fmt: skip
+    for r in range(R):
+        assert np.array_equal(tr["accepted"][r], otr[r]["accepted"]), f"accept/reject sequence differs for replica {r}"
+        assert np.array_equal(tr["moved"][r], otr[r]["moved"])
+        np.testing.assert_allclose(tr["energy"][r], otr[r]["energy"], rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(out.positions[r], reps[r].positions, rtol=0, atol=1e-10)
+    if case == "unwrapped":  # the same configuration wrapped back has the same energy
+        wrapped = BatchedAtoms(pos - np.floor(pos / L) * L, cell, np.full(R, n, dtype=np.int32), "Cu", pbc, EMT())
+        from quansino_b200 import ReplicaBatch
+
+        e_w = ReplicaBatch(wrapped, temperature=500.0).energy_full().cpu().numpy()
+        e_u = ReplicaBatch(BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", pbc, EMT()), temperature=500.0).energy_full().cpu().numpy()
+        np.testing.assert_allclose(e_u, e_w, rtol=1e-11)
