@@ -275,6 +275,7 @@ class ReplicaBatch:
             b = self.struct()
             ws = self.hmc_workspace(b)
             _lib.check(self.lib.qmc_forces_full(C.byref(self.potential), C.byref(b), f.data_ptr(), ws.data_ptr(), ws.numel(), self.stream()))
+        self.raise_on_status()  # a truncated neighbour list must never pass as forces
         return f
 
     def hmc_workspace(self, b: _lib.Batch | None = None) -> torch.Tensor:

@@ -19,6 +19,8 @@
 // Forces are the analytic gradient of exactly the energy expression of the sweep kernel.
 #pragma once
 
+#include <cmath>
+
 #include <cstdio>
 #include <cstring>
 
@@ -61,11 +63,17 @@ struct HmcArgs {
 __host__ inline int64_t align256(int64_t v) { return (v + 255) / 256 * 256; }
 
 __host__ inline int hmc_max_neighbours(const PotDev &pot, const qmc_batch_t &b) {
-    const double rl = pot.cut + HMC_SKIN;
-    double est = 512.0;
-    if (b.cells_uniform && b.cell_diag[0] > 0 && b.cell_diag[1] > 0 && b.cell_diag[2] > 0) {
+    // List slots per atom.  A fully periodic box shared by every replica is sized from its mean density (x 1.5); anything with
+    // vacuum in it (slabs, clusters, per-replica cells) cannot be: the atoms sit at condensed-phase density whatever the box
+    // volume says, so those are sized for the densest packing the potential supports (0.10 atoms / A^3 covers the EMT metals,
+    // 1.4 / sigma^3 a compressed Lennard-Jones solid).
+    const double rl = pot.cut + HMC_SKIN, sphere = 4.18879 * rl * rl * rl;
+    const double dense = pot.kind == QMC_POT_EMT ? 0.10 : 1.4 / (pot.sigma2 * std::sqrt(pot.sigma2));
+    double est = dense * sphere * 1.3 + 24.0;
+    const bool periodic = b.pbc[0] && b.pbc[1] && b.pbc[2];
+    if (periodic && b.cells_uniform && b.cell_diag[0] > 0 && b.cell_diag[1] > 0 && b.cell_diag[2] > 0) {
         const double density = (double)b.n_max / (b.cell_diag[0] * b.cell_diag[1] * b.cell_diag[2]);
-        est = density * 4.18879 * rl * rl * rl * 1.5 + 24.0;
+        est = density * sphere * 1.5 + 24.0;
     }
     int m = (int)est;
     m = (m + 7) / 8 * 8;

@@ -2,6 +2,8 @@
 up to seven periodic images per neighbour, the 500-atom cell is BASELINE.json's isobaric configuration, 864 atoms fill the
 largest class.  Also a batch of several waves of CTAs."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -153,3 +155,38 @@ def test_cell_geometries(cuda_lib, case):
         e_w = ReplicaBatch(wrapped, temperature=500.0).energy_full().cpu().numpy()
         e_u = ReplicaBatch(BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", pbc, EMT()), temperature=500.0).energy_full().cpu().numpy()
         np.testing.assert_allclose(e_u, e_w, rtol=1e-11)
+
+
+@pytest.mark.parametrize("case", ["cell32", "cell864", "cell2048", "slab", "unwrapped", "lj_cluster"])
+def test_neighbour_list_forces_on_other_shapes(cuda_lib, case):
+    """The Hamiltonian kernels' forces and energies (Verlet-list build, image shifts, lanes per atom) against the oracle."""
+    from quansino_b200 import EMT, BatchedAtoms, LennardJones, ReplicaBatch
+    from quansino_b200.systems import fcc_cubic, octahedron, rattle
+    from oracle.potentials import LJParams, emt_params
+
+    if os.environ.get("QMC_FORCE_KERNEL") not in (None, "warp"):
+        pytest.skip("the force kernels do not depend on the sweep-kernel variant")
+    pbc, calc, par, symbol = (True, True, True), EMT(), emt_params("Cu"), "Cu"
+    if case == "lj_cluster":
+        pos0, cell = octahedron("Pt", 4, 10.0)
+        pbc, calc, par, symbol = (False, False, False), LennardJones(sigma=2.5, epsilon=0.1), LJParams(sigma=2.5, epsilon=0.1), "Pt"
+    else:
+        repeat = {"cell32": 2, "cell864": 6, "cell2048": 8}.get(case, 3)
+        pos0, cell = fcc_cubic("Cu", repeat)
+    R = 1 if case == "cell2048" else 2
+    L = cell[0, 0]
+    if case == "slab":
+        cell = np.diag([L, L, L + 12.0])
+        pbc = (True, True, False)
+    pos = np.stack([rattle(pos0, 0.05, 70 + r) for r in range(R)])
+    if case == "unwrapped":
+        pos += np.random.default_rng(9).integers(-3, 4, size=pos.shape) * L
+    n = pos.shape[1]
+    batch = ReplicaBatch(BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), symbol, pbc, calc), temperature=300.0)
+    f = batch.forces_full().cpu().numpy().transpose(0, 2, 1)
+    e = batch.energy.cpu().numpy()
+    for r in range(R):
+        ref = capi.energy(par, pos[r], cell, tuple(int(b) for b in pbc), want_forces=True)
+        np.testing.assert_allclose(f[r], ref["forces"], rtol=1e-9, atol=1e-10)
+        assert abs(e[r] - ref["energy"]) <= 1e-10 * abs(ref["energy"]) + 1e-12
+    assert int(batch.status.max().item()) == 0
