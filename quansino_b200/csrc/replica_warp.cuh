@@ -49,7 +49,10 @@ __host__ __device__ constexpr int capacity_class(int n_max) {
 template <int POT, int NS>
 struct Layout {
     static constexpr bool EMT = POT == QMC_POT_EMT;
-    static constexpr int CAPL = round_up(NS + 212, 32);  // list doubles: entries + tail of NS doubles
+    // list doubles: entries + tail of NS doubles.  EMT has 78 neighbour images per position at Cu density (2 x 78 + second images
+    // of the other side ~ 180 entries per displacement; 212 leaves room for ~ 20 % compression); a Lennard-Jones solid with
+    // the default cutoff 3 sigma has ~ 125 per position, and no sigma_1 / E_atom arrays to pay for
+    static constexpr int CAPL = round_up(NS + (EMT ? 212 : 360), 32);
     static constexpr int CAPE = CAPL - NS;               // list entry capacity
     // offsets in doubles / bytes from the warp base
     static constexpr int X = 0, Y = NS, Z = 2 * NS;

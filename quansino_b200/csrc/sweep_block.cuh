@@ -26,7 +26,8 @@ struct LayoutB {
     static constexpr bool EMT = POT == QMC_POT_EMT;
     static constexpr int TILES = (NS + 31) / 32;
     static constexpr int NSW = ((TILES + BW - 1) / BW) * 32;  // atoms owned by one warp (tiles dealt round-robin)
-    static constexpr int CAPE = 112;                          // list entries per warp region (a full row must fit, too)
+    static constexpr int CAPE = EMT ? 112 : 176;              // list entries per warp region; a full row (78 images for EMT at Cu
+                                                              // density, ~125 for a Lennard-Jones solid with rc = 3 sigma) must fit, too
     static constexpr int TAILN = NSW + 8;                     // work-item queue / trial energies of the owned atoms
     static constexpr int X = 0, Y = NS, Z = 2 * NS, SIG = 3 * NS, EAT = 4 * NS;
     static constexpr int CELLC = EMT ? 5 * NS : 3 * NS;  // 10 doubles

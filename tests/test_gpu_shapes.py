@@ -190,3 +190,61 @@ def test_neighbour_list_forces_on_other_shapes(cuda_lib, case):
         np.testing.assert_allclose(f[r], ref["forces"], rtol=1e-9, atol=1e-10)
         assert abs(e[r] - ref["energy"]) <= 1e-10 * abs(ref["energy"]) + 1e-12
     assert int(batch.status.max().item()) == 0
+
+
+def test_lennard_jones_isobaric_and_hamiltonian(cuda_lib):
+    """The pair potential through the cell-move (full recompute) and Hamiltonian (forces + Verlet) paths: periodic LJ solid
+    with two images per axis, and the non-periodic Pt44 cluster."""
+    from quansino_b200 import BatchedAtoms, LennardJones, operations
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.integrators.displacement import fs
+    from quansino_b200.mc import HamiltonianCanonical, Isobaric
+    from quansino_b200.moves import CellMove, DisplacementMove, HamiltonianDisplacementMove
+    from quansino_b200.systems import fcc_cubic, octahedron, rattle
+    from oracle.potentials import LJParams
+
+    par = LJParams(sigma=2.5, epsilon=0.1)
+    calc = LennardJones(sigma=2.5, epsilon=0.1)
+    # --- isobaric, periodic: fcc with a = 3.92 (Pt spacing), 108 atoms, L = 11.76 < 2 x 7.5
+    R, n_att, p_cell = 3, 120, 0.15
+    pos0, cell = fcc_cubic("Pt", 3)
+    n = len(pos0)
+    pos = np.stack([rattle(pos0, 0.05, 80 + r) for r in range(R)])
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Pt", (True, True, True), calc)
+    mc = Isobaric(atoms, temperature=300.0, pressure=500.0 * BAR, seed=31, trace=True, max_cycles=n_att, resync_interval=0,
+                  default_displacement_move=DisplacementMove(np.arange(n), operations.Ball(0.1)),
+                  default_cell_move=CellMove(operations.IsotropicDeformation(0.01)))  # fmt: skip
+    mc.moves["default_cell_move"].probability = p_cell
+    mc.moves["default_displacement_move"].probability = 1.0 - p_cell
+    mc.run(1)
+    tr, out = mc.last_trace, mc.download()
+    moves = [dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_BALL, step=0.1, probability=1.0 - p_cell),
+             dict(type=capi.MOVE_CELL, op=capi.OP_ISOTROPIC, step=0.01, probability=p_cell)]  # fmt: skip
+    reps, otr = oracle_run(par, pos, np.full(R, n), cell, (1, 1, 1), moves, 31, n_att, range(R), temperature=300.0, pressure=500.0 * BAR,
+                           mass=195.084)  # fmt: skip
+    for r in range(R):
+        assert np.array_equal(tr["move"][r], otr[r]["move"]) and (otr[r]["move"] == 1).sum() > 5
+        assert np.array_equal(tr["accepted"][r], otr[r]["accepted"]), f"accept/reject sequence differs for replica {r}"
+        np.testing.assert_allclose(tr["energy"][r], otr[r]["energy"], rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(out.cell[r], reps[r].cell, rtol=1e-13)
+    if os.environ.get("QMC_FORCE_KERNEL") not in (None, "warp"):
+        return  # the Hamiltonian kernels do not depend on the sweep-kernel variant
+    # --- Hamiltonian, non-periodic cluster
+    pos0, cell = octahedron("Pt", 4, 10.0)
+    n = len(pos0)
+    R, n_attempts, n_steps = 2, 3, 10
+    pos = np.stack([rattle(pos0, 0.02, 90 + r) for r in range(R)])
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Pt", (False, False, False), calc)
+    hm = HamiltonianCanonical(atoms, temperature=np.array([300.0, 700.0]), max_cycles=1, seed=17, trace=True, resync_interval=0,
+                              steps_per_launch=n_attempts,
+                              default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=2.0, max_steps=n_steps)))  # fmt: skip
+    hm.run(n_attempts)
+    tr, out = hm.last_trace, hm.download()
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, pbc=(0, 0, 0), temperature=float([300.0, 700.0][r]), mass=195.084,
+                           momenta=np.zeros((n, 3)))  # fmt: skip
+        ref = capi.mc_run(par, rep, [capi.MoveSpec(capi.MOVE_HMC, capi.OP_VERLET, dt=2.0 * fs, n_steps=n_steps)], 17, r, 0, n_attempts)
+        assert np.array_equal(tr["accepted"][r], ref["accepted"])
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(out.positions[r], rep.positions, rtol=0, atol=1e-10)
+        np.testing.assert_allclose(out.momenta[r], rep.momenta, rtol=0, atol=1e-10)
