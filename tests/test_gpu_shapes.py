@@ -248,3 +248,41 @@ def test_lennard_jones_isobaric_and_hamiltonian(cuda_lib):
         np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10)
         np.testing.assert_allclose(out.positions[r], rep.positions, rtol=0, atol=1e-10)
         np.testing.assert_allclose(out.momenta[r], rep.momenta, rtol=0, atol=1e-10)
+
+
+def test_tiny_and_empty_replicas(cuda_lib):
+    """Replicas with 0, 1, 2 and 3 atoms in one batch (an empty replica fails every move; a single atom has energy -E0 and
+    accepts everything), canonical and grand-canonical, against the oracle."""
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+
+    n_max, n_att = 32, 60
+    cell = np.diag([14.0, 15.0, 16.0])
+    n_atoms = np.array([0, 1, 2, 3], dtype=np.int32)
+    R = len(n_atoms)
+    rng = np.random.default_rng(12)
+    pos = np.zeros((R, n_max, 3))
+    for r in range(R):
+        pos[r, : n_atoms[r]] = 6.0 + rng.normal(scale=1.2, size=(n_atoms[r], 3))  # a loose clump: pairs inside the cutoff
+    atoms = BatchedAtoms(pos.copy(), cell, n_atoms, "Cu", (True, True, True), EMT())
+    labels = np.tile(np.arange(n_max), (R, 1))
+    mc = Canonical(atoms, temperature=2000.0, seed=64, trace=True, max_cycles=n_att, resync_interval=0,
+                   default_displacement_move=DisplacementMove(labels, operations.Ball(0.3)))  # fmt: skip
+    e0 = mc.batch.energy_full().cpu().numpy().copy()
+    mc.run(1)
+    tr, out, par = mc.last_trace, mc.download(), oracle_par(EMT())
+    for r in range(R):
+        n = int(n_atoms[r])
+        ref0 = capi.energy(par, pos[r, :n], cell, (1, 1, 1)) if n else {"energy": 0.0}
+        assert abs(e0[r] - ref0["energy"]) <= 1e-10 * abs(ref0["energy"]) + 1e-14
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, n_atoms=n, temperature=2000.0)
+        lab = labels[r].astype(np.int32).copy()
+        lab[n:] = -1
+        ref = capi.mc_run(par, rep, [capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.3, labels=lab)], 64, r, 0, n_att)
+        assert np.array_equal(tr["accepted"][r], ref["accepted"]), f"replica with {n} atoms"
+        assert np.array_equal(tr["moved"][r], ref["moved"])
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(out.positions[r, :n], rep.positions[:n], rtol=0, atol=1e-12)
+    assert np.all(tr["accepted"][0] == -1) and np.all(tr["accepted"][1] == 1)
+    assert abs(e0[1] - 3.51) < 1e-12  # an isolated Cu atom sits at -E0 = +3.51 eV on ASE-EMT's energy scale
