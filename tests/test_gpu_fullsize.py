@@ -75,3 +75,24 @@ def test_sharding_and_determinism_are_bit_exact(full_run):
     again.run(SWEEPS)
     assert np.array_equal(again.download().positions, ref)
     assert np.array_equal(again.batch.energy.cpu().numpy(), mc.tracked_energy)
+
+
+def test_long_run_drift_of_the_tracked_energy(cuda_lib):
+    """64 replicas x 300 sweeps (32 400 attempts each) WITHOUT re-priming: the incrementally tracked energy and sigma_1 stay
+    within 1e-10 relative of a fresh full evaluation (the driver's default resync_interval = 100 keeps it far below that)."""
+    pos, cell, n = cu_replicas(3, 64, seed=77)
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(64, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    mc = Canonical(atoms, temperature=600.0, seed=5, resync_interval=0, steps_per_launch=50,
+                   default_displacement_move=DisplacementMove(np.arange(n), operations.Ball(0.1)))  # fmt: skip
+    mc.run(300)
+    tracked = mc.batch.energy.cpu().numpy().copy()
+    sig = mc.batch.sigma1.cpu().numpy().copy()
+    fresh = mc.batch.energy_full().cpu().numpy()
+    drift = np.max(np.abs(tracked - fresh) / np.abs(fresh))
+    assert drift < 1e-10, drift
+    np.testing.assert_allclose(sig, mc.batch.sigma1.cpu().numpy(), rtol=1e-11)
+    assert mc.counters()[:, 0, 0].min() == 300 * n
