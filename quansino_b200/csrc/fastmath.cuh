@@ -25,6 +25,10 @@ __device__ __constant__ double FM_SIN[6] = {-1.66666666666666324348e-01, 8.33333
 __device__ __constant__ double FM_COS[6] = {4.16666666666666019037e-02,  -1.38888888888741095749e-03, 2.48015872894767294178e-05,
                                             -2.75573143513906633035e-07, 2.08757232129817482790e-09,  -1.13596475577881948265e-11};
 
+// log2(e), -ln2 (high part), -ln2 (low part): in the constant bank next to the coefficients, so that one 16-byte uniform load
+// brings two of them (as 64-bit immediates each costs two instructions every time the compiler re-materialises it)
+__device__ __constant__ double FM_RED[4] = {1.4426950408889634, -6.93147180369123816490e-01, -1.90821492927058770002e-10, 0.0};
+
 constexpr double FM_MAGIC = 6755399441055744.0;  // 1.5 * 2^52
 constexpr double FM_LN2_HI = 6.93147180369123816490e-01, FM_LN2_LO = 1.90821492927058770002e-10;
 
@@ -52,10 +56,10 @@ __device__ __forceinline__ double sqrt_fast(double x) {
 
 // exp(x) for x in [-700, 700]
 __device__ __forceinline__ double exp_fast(double x) {
-    const double t = fma(x, 1.4426950408889634, FM_MAGIC);
+    const double t = fma(x, FM_RED[0], FM_MAGIC);
     const double k = t - FM_MAGIC;
-    double r = fma(k, -FM_LN2_HI, x);
-    r = fma(k, -FM_LN2_LO, r);
+    double r = fma(k, FM_RED[1], x);
+    r = fma(k, FM_RED[2], r);
     double q = FM_EXP[9];
 #pragma unroll
     for (int i = 8; i >= 0; --i) q = fma(q, r, FM_EXP[i]);
@@ -66,11 +70,12 @@ __device__ __forceinline__ double exp_fast(double x) {
 
 // two exponentials in lockstep
 __device__ __forceinline__ void exp2_fast(double x0, double x1, double &e0, double &e1) {
-    const double t0 = fma(x0, 1.4426950408889634, FM_MAGIC), t1 = fma(x1, 1.4426950408889634, FM_MAGIC);
+    const double l2e = FM_RED[0], nl2h = FM_RED[1], nl2l = FM_RED[2];
+    const double t0 = fma(x0, l2e, FM_MAGIC), t1 = fma(x1, l2e, FM_MAGIC);
     const double k0 = t0 - FM_MAGIC, k1 = t1 - FM_MAGIC;
-    double r0 = fma(k0, -FM_LN2_HI, x0), r1 = fma(k1, -FM_LN2_HI, x1);
-    r0 = fma(k0, -FM_LN2_LO, r0);
-    r1 = fma(k1, -FM_LN2_LO, r1);
+    double r0 = fma(k0, nl2h, x0), r1 = fma(k1, nl2h, x1);
+    r0 = fma(k0, nl2l, r0);
+    r1 = fma(k1, nl2l, r1);
     double q0 = FM_EXP[9], q1 = FM_EXP[9];
 #pragma unroll
     for (int i = 8; i >= 0; --i) {
@@ -85,13 +90,13 @@ __device__ __forceinline__ void exp2_fast(double x0, double x1, double &e0, doub
 
 // three exponentials in lockstep: one coefficient fetch per Horner step serves all three chains
 __device__ __forceinline__ void exp3_fast(double x0, double x1, double x2, double &e0, double &e1, double &e2) {
-    const double t0 = fma(x0, 1.4426950408889634, FM_MAGIC), t1 = fma(x1, 1.4426950408889634, FM_MAGIC),
-                 t2 = fma(x2, 1.4426950408889634, FM_MAGIC);
+    const double l2e = FM_RED[0], nl2h = FM_RED[1], nl2l = FM_RED[2];
+    const double t0 = fma(x0, l2e, FM_MAGIC), t1 = fma(x1, l2e, FM_MAGIC), t2 = fma(x2, l2e, FM_MAGIC);
     const double k0 = t0 - FM_MAGIC, k1 = t1 - FM_MAGIC, k2 = t2 - FM_MAGIC;
-    double r0 = fma(k0, -FM_LN2_HI, x0), r1 = fma(k1, -FM_LN2_HI, x1), r2 = fma(k2, -FM_LN2_HI, x2);
-    r0 = fma(k0, -FM_LN2_LO, r0);
-    r1 = fma(k1, -FM_LN2_LO, r1);
-    r2 = fma(k2, -FM_LN2_LO, r2);
+    double r0 = fma(k0, nl2h, x0), r1 = fma(k1, nl2h, x1), r2 = fma(k2, nl2h, x2);
+    r0 = fma(k0, nl2l, r0);
+    r1 = fma(k1, nl2l, r1);
+    r2 = fma(k2, nl2l, r2);
     double q0 = FM_EXP[9], q1 = FM_EXP[9], q2 = FM_EXP[9];
 #pragma unroll
     for (int i = 8; i >= 0; --i) {
@@ -124,7 +129,8 @@ __device__ __forceinline__ double log_fast(double x) {
     R *= z;
     const double hfsq = 0.5 * f * f;
     const double dk = (double)k;
-    return dk * FM_LN2_HI - ((hfsq - (s * (hfsq + R) + dk * FM_LN2_LO)) - f);
+    // dk * ln2_hi - ((hfsq - (s * (hfsq + R) + dk * ln2_lo)) - f), with the two constants taken (negated, exactly) from FM_RED
+    return -(dk * FM_RED[1]) - ((hfsq - (s * (hfsq + R) - dk * FM_RED[2])) - f);
 }
 
 // sin and cos of phi in [0, 2 pi]  (fdlibm k_sin / k_cos kernels after a two-term pi/2 reduction)
