@@ -286,7 +286,7 @@ constexpr int F_COMPOSITE = 16;  // composite displacement moves (chains of move
 __device__ __forceinline__ void propose_translation(int op, double step, double o0, double o1, double o2, double t[3]) {
     if (op == QMC_OP_BALL) {
         const double rr = step * o0, phi = TWO_PI * o1, c = -1.0 + 2.0 * o2;
-        const double s = sqrt_fast(fmax(__dsub_rn(1.0, __dmul_rn(c, c)), 1e-300));
+        const double s = sqrt_fast(__dsub_rn(1.0, __dmul_rn(c, c)) + 1e-300);  // + 1e-300: exact no-op unless c = +-1 (keeps rsqrt finite)
         double sp, cp;
         sincos_2pi(phi, sp, cp);
         t[0] = __dmul_rn(__dmul_rn(rr, s), cp);
@@ -294,7 +294,7 @@ __device__ __forceinline__ void propose_translation(int op, double step, double 
         t[2] = __dmul_rn(rr, c);
     } else if (op == QMC_OP_SPHERE) {
         const double phi = TWO_PI * o0, c = -1.0 + 2.0 * o1;
-        const double s = sqrt_fast(fmax(__dsub_rn(1.0, __dmul_rn(c, c)), 1e-300));
+        const double s = sqrt_fast(__dsub_rn(1.0, __dmul_rn(c, c)) + 1e-300);  // + 1e-300: exact no-op unless c = +-1 (keeps rsqrt finite)
         double sp, cp;
         sincos_2pi(phi, sp, cp);
         t[0] = __dmul_rn(step, __dmul_rn(s, cp));
@@ -386,6 +386,11 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
     const int nmax = a.b.n_max;
     Rep<LY> R;
     R.b = smem_d + warp * (LY::BYTES / 8);
+    {  // keep the (32-bit shared-window) base in a register: otherwise it is re-derived from the thread id at every other use
+        unsigned sb = (unsigned)__cvta_generic_to_shared(R.b);  // (S2R x 2 + 4 integer instructions each time; +0.8 % measured)
+        asm volatile("" : "+r"(sb));
+        R.b = reinterpret_cast<double *>(__cvta_shared_to_generic((size_t)sb));
+    }
     const CellView<LY, UNIFORM> C{&a.cell, R.b + LY::CELLC};
     const bool dynamic = a.n_chunks > 1;
     // Work items.  Static: warp w of the grid owns replica w for the whole launch.  Dynamic: (chunk, replica) items are taken
