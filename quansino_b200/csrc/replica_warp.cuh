@@ -315,7 +315,8 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
         const unsigned b = __ballot_sync(FULL, any);
         const int pos = min(cnt + 2 * __popc(b & lt), RV::CAPE - 2);
         if (any) {
-            *reinterpret_cast<double2 *>(&R.lr(pos)) = make_double2(-r2o, r2n);
+            const double neg_r2o = __hiloint2double(__double2hiint(r2o) ^ (int)0x80000000, __double2loint(r2o));  // sign flip, integer pipe
+            *reinterpret_cast<double2 *>(&R.lr(pos)) = make_double2(neg_r2o, r2n);
             if (TRACK) R.l2(pos >> 1) = (uint16_t)j;
         }
         if (TRACK && valid) R.pp(j) = any ? ((unsigned)pos | ((unsigned)(pos + 1) << 16)) : (NOPOS | (NOPOS << 16));
@@ -386,7 +387,7 @@ __device__ __forceinline__ void eval_pass(const PotDev &pot, const RV &R, const 
     const bool act = e < cnt;
     const double r2s = act ? R.lr(e) : 1.0e6;  // padding lanes sit far outside every cutoff: their terms come out as zero
     const bool isnew = __double2hiint(r2s) >= 0;
-    const double r2 = fabs(r2s);
+    const double r2 = __hiloint2double(__double2hiint(r2s) & 0x7fffffff, __double2loint(r2s));  // |r2s| on the integer pipe
     if (RV::EMT) {
         double e1, e2, w;
         const bool in = emt_pair_w(pot, r2, e1, e2, w);
