@@ -412,7 +412,7 @@ def run_native(args):
             "unit": "TFLOP/s",
             "frac": achieved_tflops / (fp64_peak / 1e12),
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH if R == 4096 and world == 1 else None,
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch, ncu --set full (profiles/r1_i_summary.md); bytes, algorithmic 35.7e6",
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch, ncu --set full (profiles/r1_l_summary.md); bytes, algorithmic 35.7e6",
             "peak_source": "register-resident DFMA loop measured in this process (qmc_fp64_peak); nominal 37.2",
             "flop_per_attempt": flop_per_attempt,
             "pair_evals_per_attempt": p_per_attempt,
