@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define QMC_ABI_VERSION 2
+#define QMC_ABI_VERSION 3
 #define QMC_MAX_MOVES 4
 
 enum qmc_error {
@@ -97,6 +97,9 @@ typedef struct qmc_move {
     int32_t repeat;        /* displacement moves: how many times this entry is performed per attempt (>= 1; 0 reads as 1) */
     int32_t chain;         /* bit 0: the next table entry belongs to the same composite move; bit 1: plain CompositeMove;
                               bit 2: label groups (labels = dense group ranks) */
+    int32_t axes;          /* cell moves: bit d set = axis d is deformed (the diagonal of IsotropicDeformation.mask,
+                              operations/cell.py:167-169); 0 reads as all three axes */
+    int32_t _pad;
     int32_t *labels;       /* device [n_replicas][n_max]; NULL = arange(n_atoms) and no exchange moves */
 } qmc_move_t;
 

@@ -182,13 +182,13 @@ def case_hybrid(seed, n_attempts, k):
     )  # fmt: skip
 
 
-def case_isobaric(seed, steps, p_cell):
+def case_isobaric(seed, steps, p_cell, mask=None):
     atoms, pos0, cell = cu_atoms(3, 0.05, 777)
     n = len(atoms)
     pressure = 1000.0 * bar
     mc = Isobaric(
         atoms, temperature=300.0, pressure=pressure, default_displacement_move=DisplacementMove(np.arange(n), Ball(0.1)),
-        default_cell_move=CellMove(IsotropicDeformation(0.05)),
+        default_cell_move=CellMove(IsotropicDeformation(0.05, mask=mask)),
     )  # fmt: skip
     default_probabilities = np.array([mc.moves["default_displacement_move"].probability, mc.moves["default_cell_move"].probability])
     if p_cell is not None:
@@ -200,7 +200,8 @@ def case_isobaric(seed, steps, p_cell):
     return dict(
         kind="isobaric", seed=seed, replica=1, temperature=300.0, pressure=pressure, step_size=0.1, max_value=0.05,
         default_probabilities=default_probabilities, probabilities=probabilities, positions0=pos0, cell0=cell,
-        positions=atoms.positions.copy(), cell=atoms.cell.array.copy(), **tr,
+        positions=atoms.positions.copy(), cell=atoms.cell.array.copy(),
+        axes=7 if mask is None else int(sum(int(mask[d, d]) << d for d in range(3))), **tr,
     )  # fmt: skip
 
 
@@ -270,6 +271,7 @@ def main():
         "canonical_sphere": lambda: case_canonical("Sphere", Sphere, 1003, 1),
         "isobaric_default": lambda: case_isobaric(2001, 1, None),
         "isobaric_pcell": lambda: case_isobaric(2002, 1, 0.2),
+        "isobaric_masked": lambda: case_isobaric(2003, 1, 0.25, mask=np.diag([True, False, True])),
         "gc_lj": lambda: case_gc_lj(3001, 700, -0.5),
         "gc_emt": lambda: case_gc_emt(3002, 150, -3.4, 3000.0),
         "hmc": lambda: case_hmc(4001, 3, 2.0, 12, 800.0),

@@ -487,7 +487,8 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                     if (exclusive || (sm->chain & 1)) { free(disp); rc = -1; goto done; } /* last entry of a plain chain only */
                     const double u_cell = c == 0 ? opd[0] : b3[1];
                     double sc = exp(-sm->step + (sm->step - -sm->step) * u_cell);
-                    for (int q = 0; q < 9; ++q) new_cell[q] = sc * st->cell[q];
+                    for (int q = 0; q < 9; ++q) /* F = eye * s * mask + eye * ~mask, F @ cell: row r scaled by F[r][r] */
+                        new_cell[q] = ((sm->axes == 0 || ((sm->axes >> (q / 3)) & 1)) ? sc : 1.0) * st->cell[q];
                     scale_positions(n, trial, st->cell, new_cell);
                     did_cell = 1;
                     break;
@@ -612,8 +613,9 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
             /* operations/cell.py:167-169, moves/cell.py:73-84, mc/criteria.py:160-172 */
             double s = exp(-mv->step + (mv->step - -mv->step) * opd[0]);
             double new_cell[9];
-            for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) new_cell[3 * r + c] = s * st->cell[3 * r + c]; /* (s I) @ cell */
+            for (int r = 0; r < 3; ++r) /* F = eye * s * mask + eye * ~mask (operations/cell.py:167-169); F @ cell */
+                for (int c = 0; c < 3; ++c)
+                    new_cell[3 * r + c] = ((mv->axes == 0 || ((mv->axes >> r) & 1)) ? s : 1.0) * st->cell[3 * r + c];
             memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
             scale_positions(n, trial, st->cell, new_cell);
             double e_new;

@@ -51,6 +51,8 @@ class Move(C.Structure):
         ("default_label", C.c_int32),
         ("repeat", C.c_int32),
         ("chain", C.c_int32),
+        ("axes", C.c_int32),
+        ("_pad", C.c_int32),
         ("labels", C.c_void_p),
     ]
 

@@ -266,6 +266,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
                     return fail(QMC_ERR_UNSUPPORTED, "move %d: displacement operation %d is not available on the GPU path", m, mv.op);
                 break;
             case QMC_MOVE_CELL:
+                if (mv.axes < 0 || mv.axes > 7) return fail(QMC_ERR_INVALID, "move %d: axes must be a mask of bits 0..2", m);
                 if (mv.op != QMC_OP_ISOTROPIC)
                     return fail(QMC_ERR_UNSUPPORTED, "move %d: only IsotropicDeformation is available on the GPU path", m);
                 break;
@@ -287,6 +288,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         a.mv[m].default_label = mv.default_label;
         a.mv[m].repeat = mv.repeat > 0 ? mv.repeat : 1;
         a.mv[m].chain = mv.chain;
+        a.mv[m].axes = (mv.axes & 7) ? (mv.axes & 7) : 7;
         a.mv[m].labels = mv.labels;
     }
     if (!(tot > 0.0)) return fail(QMC_ERR_INVALID, "move probabilities sum to zero");

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(LayoutB<POT, NS>::REPS * BW * 32, 1) sweep_blo
             double ncell[3], scale[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                ncell[d] = s * cell[d];
+                ncell[d] = (((mv.axes >> d) & 1) ? s : 1.0) * cell[d];
                 scale[d] = ncell[d] / cell[d];
             }
             for (int j = tid; j < R.n; j += BW * 32) {

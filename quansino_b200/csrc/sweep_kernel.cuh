@@ -23,6 +23,7 @@ struct MoveDev {
     double step, bias;
     int default_label;
     int repeat, chain;  // composite displacement moves: this entry `repeat` times, then on to the next entry if `chain`
+    int axes;           // cell moves: bit d set = axis d is deformed (never 0 here)
     int *labels;  // device [R][n_max] or nullptr (= arange, no exchange)
 };
 
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     double scale[3];
 #pragma unroll
                     for (int d = 0; d < 3; ++d) {
-                        ncell[d] = s * cell[d];
+                        ncell[d] = (((sm.axes >> d) & 1) ? s : 1.0) * cell[d];
                         scale[d] = ncell[d] / cell[d];
                     }
                     for (int j = lane; j < R.n; j += 32) {
@@ -694,8 +695,8 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
             double ncell[3], scale[3];
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
-                ncell[d] = s * cell[d];         // (s I) @ cell
-                scale[d] = ncell[d] / cell[d];  // solve(old_cell, new_cell), diagonal
+                ncell[d] = (((mv.axes >> d) & 1) ? s : 1.0) * cell[d];  // F @ cell, F = eye * s * mask + eye * ~mask
+                scale[d] = ncell[d] / cell[d];                          // solve(old_cell, new_cell), diagonal
             }
             for (int j = lane; j < R.n; j += 32) {
                 R.x(j) = R.x(j) * scale[0];

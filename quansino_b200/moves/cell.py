@@ -30,6 +30,7 @@ class CellMove(BaseMove):
         if m.op != _lib.OP_ISOTROPIC:
             raise NotImplementedError(f"{type(self.operation).__name__} is not a cell operation of the GPU path")
         m.default_label = _lib.LABEL_NONE
+        m.axes = self.operation.axes  # the diagonal of IsotropicDeformation.mask
         return m
 
     def to_dict(self):

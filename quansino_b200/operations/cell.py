@@ -24,9 +24,17 @@ class IsotropicDeformation(DeformationOperation):
 
     op_code = _lib.OP_ISOTROPIC
 
+    @property
+    def axes(self) -> int:
+        """Bit mask of the deformed axes: the diagonal of ``mask`` (off-diagonal entries multiply zeros of ``eye(3)``)."""
+        d = np.diag(self.mask)
+        return int(d[0]) | (int(d[1]) << 1) | (int(d[2]) << 2)
+
     def lower(self):
-        if not np.all(np.diag(self.mask)):
-            raise NotImplementedError("masked isotropic deformations are not available on the GPU path")
+        if self.mask.shape != (3, 3):
+            raise ValueError("mask must be a 3x3 boolean array")
+        if self.axes == 0:
+            raise NotImplementedError("a mask without any deformed axis describes no move")
         return super().lower()
 
 

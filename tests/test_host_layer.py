@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in sorted(declared):
         assert getattr(lib, name) is not None, name
-    assert lib.qmc_abi_version() == 2
+    assert lib.qmc_abi_version() == 3
 
 
 def test_struct_layouts_match_the_header():
@@ -103,8 +103,10 @@ def test_moves_lower_like_the_reference_defaults():
         DisplacementMove(np.arange(4), Translation()).lower()
     with pytest.raises(NotImplementedError):
         CellMove(scale_atoms=False).lower()
+    assert CellMove().lower().axes == 7
+    assert CellMove(IsotropicDeformation(0.05, mask=np.diag([True, True, False]))).lower().axes == 3  # the slab case: z is fixed
     with pytest.raises(NotImplementedError):
-        CellMove(IsotropicDeformation(0.05, mask=np.diag([True, True, False]))).lower()
+        CellMove(IsotropicDeformation(0.05, mask=np.zeros((3, 3), dtype=bool))).lower()
     mv = DisplacementMove(np.arange(4))
     mv.check_move = lambda ctx: True
     with pytest.raises(NotImplementedError):
