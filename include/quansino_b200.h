@@ -33,7 +33,8 @@
 extern "C" {
 #endif
 
-#define QMC_ABI_VERSION 3
+#define QMC_ABI_VERSION 4
+#define QMC_MAX_FORCED 16 /* sum of minimum_count over the move table */
 #define QMC_MAX_MOVES 4
 
 enum qmc_error {
@@ -79,6 +80,12 @@ typedef struct qmc_potential {
  * sub-moves choose independently, and a CellMove may be the last entry (the docs' hybrid NPT move
  * `DisplacementMove * N + CellMove`, judged by IsobaricCriteria).  Counters and the trace refer to the first entry.
  *
+ * Forced moves (`minimum_count`, mc/core.py:331-342): at the start of every step (every `max_cycles` attempts, counted from
+ * `attempt_base`, which must be a multiple of `max_cycles`) K = sum of minimum_count distinct cycle indices are drawn --
+ * a partial Fisher-Yates shuffle of arange(max_cycles) with the doubles of Philox blocks 4 + j / 2 of the step's first
+ * attempt: t = j + floor(u_j (max_cycles - j)), swap(perm[j], perm[t]), index_j = perm[j] -- and forced move j (the
+ * table's heads repeated minimum_count times, in table order) is performed at cycle index_j instead of a selected one.
+ *
  * Label groups (moves/displacement.py:164-167: `where(labels == label)` may select several atoms, which then move by ONE
  * translation): `chain` bit 2 on a single displacement entry says that `labels` holds dense group ranks 0..G-1 in the
  * order of the reference's sorted unique labels (-1 = not movable); every atom of the selected rank is displaced. */
@@ -99,6 +106,8 @@ typedef struct qmc_move {
                               bit 2: label groups (labels = dense group ranks) */
     int32_t axes;          /* cell moves: bit d set = axis d is deformed (the diagonal of IsotropicDeformation.mask,
                               operations/cell.py:167-169); 0 reads as all three axes */
+    int32_t minimum_count; /* MoveStorage.minimum_count: forced occurrences of this move per step (mc/core.py:331-342) */
+    int32_t max_cycles;    /* cycles per step; read from entry 0, needed only if some minimum_count > 0 */
     int32_t _pad;
     int32_t *labels;       /* device [n_replicas][n_max]; NULL = arange(n_atoms) and no exchange moves */
 } qmc_move_t;

@@ -43,6 +43,8 @@ class Move(C.Structure):
         ("repeat", C.c_int32),
         ("chain", C.c_int32),
         ("axes", C.c_int32),
+        ("minimum_count", C.c_int32),
+        ("max_cycles", C.c_int32),
         ("_pad", C.c_int32),
         ("labels", C.POINTER(C.c_int32)),
     ]
@@ -177,6 +179,8 @@ class MoveSpec:
     repeat: int = 1  # CompositeDisplacementMove: consecutive copies of this sub-move
     chain: int = 0  # bit 0: the next MoveSpec belongs to the same composite move; bit 1: plain CompositeMove
     axes: int = 0  # CellMove: deformed axes (bit mask), 0 = all
+    minimum_count: int = 0  # forced occurrences per step
+    max_cycles: int = 0  # cycles per step (needed with forced moves)
 
 
 @dataclass
@@ -232,6 +236,7 @@ def mc_run(par, rep: Replica, moves: list[MoveSpec], seed: int, replica_id: int,
         mv[i].type, mv[i].op, mv[i].step, mv[i].probability = m.type, m.op, m.step, m.probability
         mv[i].bias_insert, mv[i].dt, mv[i].n_steps, mv[i].default_label = m.bias_insert, m.dt, m.n_steps, m.default_label
         mv[i].repeat, mv[i].chain, mv[i].axes = m.repeat, m.chain, m.axes
+        mv[i].minimum_count, mv[i].max_cycles = m.minimum_count, m.max_cycles
         if m.labels is not None:
             assert m.labels.dtype == np.int32 and len(m.labels) >= n_max and m.labels.flags.c_contiguous
             mv[i].labels = m.labels.ctypes.data_as(C.POINTER(C.c_int32))

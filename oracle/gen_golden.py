@@ -74,6 +74,8 @@ def run_steps(mc, steps):
     for _ in range(steps):
         seen = 0
         for _name in mc.step():
+            if hasattr(mc.context.rng, "mark_cycle"):
+                mc.context.rng.mark_cycle()
             if len(mc.move_history) > seen:
                 record()
                 seen = len(mc.move_history)
@@ -182,6 +184,27 @@ def case_hybrid(seed, n_attempts, k):
     )  # fmt: skip
 
 
+def case_forced(seed, steps):
+    """Forced moves (minimum_count, mc/core.py:331-342): two cell moves and three Box displacements are guaranteed per step of 40
+    cycles; the remaining cycles choose between the default displacement move and the (rarely selected) others."""
+    atoms, pos0, cell = cu_atoms(3, 0.05, 8181)
+    n = len(atoms)
+    pressure = 1500.0 * bar
+    mc = Isobaric(atoms, temperature=400.0, pressure=pressure, max_cycles=40, default_displacement_move=DisplacementMove(np.arange(n), Ball(0.1)),
+                  default_cell_move=CellMove(IsotropicDeformation(0.01)))  # fmt: skip
+    mc.moves["default_displacement_move"].probability = 1.0
+    mc.moves["default_cell_move"].probability = 0.02
+    mc.moves["default_cell_move"].minimum_count = 2
+    mc.add_move(DisplacementMove(np.arange(n), Box(0.05)), name="box", probability=0.05, minimum_count=3)
+    inject(mc, seed, 8)
+    tr = run_steps(mc, steps)
+    return dict(
+        kind="forced", seed=seed, replica=8, temperature=400.0, pressure=pressure, max_cycles=40, positions0=pos0, cell0=cell,
+        probabilities=np.array([mc.moves[q].probability for q in mc.moves]), minimum_counts=np.array([0, 2, 3]),
+        positions=atoms.positions.copy(), cell=atoms.cell.array.copy(), **tr,
+    )  # fmt: skip
+
+
 def case_isobaric(seed, steps, p_cell, mask=None):
     atoms, pos0, cell = cu_atoms(3, 0.05, 777)
     n = len(atoms)
@@ -280,6 +303,7 @@ def main():
         "composite_exhaust": lambda: case_composite("exhaust", 5003, 40),
         "composite_hybrid": lambda: case_hybrid(5004, 90, 3),
         "label_groups": lambda: case_groups(6001, 100),
+        "forced_moves": lambda: case_forced(7001, 3),
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():

@@ -20,6 +20,7 @@ Layout (DESIGN.md section "Random stream"):
     block 2: d0 = operation draw 2           (Ball: cos(theta) -- ``:148``)
              d1 = u_accept                   (``mc/criteria.py:108``)
     block 3: d0 = u_coin  (insert / delete, ``moves/exchange.py:148``)   d1 = u_swap (parallel tempering)
+    block 4 + j / 2 (of the FIRST attempt of a step): forced-move placement draw j (``mc/core.py:335-337``)
     block 32 + 2 (c - 1), 33 + 2 (c - 1): sub-move c >= 1 of a CompositeDisplacementMove (``moves/displacement.py:392-431``;
              c counts the sub-moves that draw, the first one uses the standard slots above):
              (u_label, operation draw 0) and (operation draw 1, operation draw 2); the CellMove closing a hybrid
@@ -43,6 +44,7 @@ BLOCK_SELECT_LABEL = 0
 BLOCK_OP01 = 1
 BLOCK_OP2_ACCEPT = 2
 BLOCK_COIN_SWAP = 3
+BLOCK_FORCED = 4
 BLOCK_NORMALS = 16
 BLOCK_COMPOSITE = 32
 
@@ -95,7 +97,11 @@ class InjectedStream:
     * ``choice(a)`` (no ``p``)      -> u_label; ``a[floor(u * len(a))]``.  The c-th such call of an attempt (c >= 1, only
                                        ``CompositeDisplacementMove`` makes more than one) starts sub-move c: its label and
                                        operation draws come from blocks 32 + 2 (c - 1) and 33 + 2 (c - 1)
-    * ``choice(arange, size=0, replace=False)`` -> consumes nothing (forced-move placement, unsupported > 0)
+    * ``choice(arange(M), size=K, replace=False)`` -> the forced-move placement of a step (``mc/core.py:335-337``): nothing for
+                                       K = 0, else a partial Fisher-Yates shuffle fed from blocks 4 + j / 2 of the step's first
+                                       attempt (include/quansino_b200.h, "Forced moves")
+    * ``mark_cycle()``              -> called by the driving loop once per yielded cycle: a cycle that made no selection draw
+                                       (a forced one) still advances the attempt index
     * ``uniform(lo, hi, size)``     -> operation draws, in call order: ``lo + (hi - lo) * u``
     * ``random()``                  -> u_coin when it is the FIRST draw after the selection (only
                                        ``ExchangeMove.__call__`` does that, ``moves/exchange.py:148``);
@@ -110,6 +116,7 @@ class InjectedStream:
         self._op_draws = 0
         self._calls = 0
         self._labels = 0  # label draws of this attempt
+        self._select_pending = False  # a selection draw opened the attempt that the next mark_cycle() belongs to
         self.log: list[tuple[str, float]] = []
 
     # -- slots ---------------------------------------------------------------------------------
@@ -149,9 +156,17 @@ class InjectedStream:
         if size is not None:
             if size == 0 or (hasattr(size, "__len__") and len(size) == 0):
                 return a[:0]
-            raise NotImplementedError("forced moves (minimum_count > 0) are not part of the injected stream")
+            if replace or p is not None:
+                raise NotImplementedError("only choice(arange(M), size=K, replace=False) is part of the injected stream")
+            perm = list(range(len(a)))  # partial Fisher-Yates with the step's first attempt (= the next one)
+            for j in range(int(size)):
+                u = uniform_pair(self.seed, self.attempt + 1, self.replica, BLOCK_FORCED + j // 2)[j & 1]
+                t = j + int(u * (len(a) - j))
+                perm[j], perm[t] = perm[t], perm[j]
+            return a[perm[: int(size)]]
         if p is not None:
             self._next_attempt()
+            self._select_pending = True
             u = self._pair(BLOCK_SELECT_LABEL)[0]
             self.log.append(("select", u))
             cdf = np.cumsum(np.asarray(p, dtype=float))
@@ -164,6 +179,12 @@ class InjectedStream:
         u = self._pair(BLOCK_SELECT_LABEL)[1] if c == 0 else self._pair(BLOCK_COMPOSITE + 2 * (c - 1))[0]
         self.log.append(("label", u))
         return a[int(u * len(a))]
+
+    def mark_cycle(self):
+        """Once per cycle the driver yields, before the move runs."""
+        if not self._select_pending:
+            self._next_attempt()  # a forced cycle: no selection draw opened this attempt
+        self._select_pending = False
 
     def uniform(self, low=0.0, high=1.0, size=None):
         if size is None:

@@ -448,8 +448,36 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
         for (int m = 0; m < n_moves; ++m) cdf[m] /= last;
     }
 
+    /* forced moves (mc/core.py:331-342): forced = repeat(available, minimum_count), placed at distinct cycle indices that are
+     * drawn once per step -- here by a partial Fisher-Yates shuffle of arange(max_cycles) fed from blocks 4 + j / 2 of the
+     * step's first attempt (include/quansino_b200.h) */
+    int n_forced = 0, forced_move[16], forced_index[16];
+    const int max_cycles = moves[0].max_cycles;
+    for (int m = 0; m < n_moves; ++m)
+        if (m == 0 || !(moves[m - 1].chain & 1))
+            for (int q = 0; q < moves[m].minimum_count; ++q) {
+                if (n_forced >= 16) { rc = -1; goto done; }
+                forced_move[n_forced++] = m;
+            }
+    if (n_forced > 0 && (max_cycles < n_forced || attempt_base % (uint64_t)max_cycles != 0)) { rc = -1; goto done; }
+
     for (int k = 0; k < n_attempts; ++k) {
         const uint64_t attempt = attempt_base + (uint64_t)k;
+        if (n_forced > 0 && k % max_cycles == 0) {
+            int key[16], val[16], n_over = 0; /* sparse permutation: perm[key] = val, identity elsewhere */
+            for (int j = 0; j < n_forced; ++j) {
+                double u[2];
+                qo_uniform_pair(seed, attempt, replica, (uint32_t)(4 + j / 2), u);
+                const int t = j + (int)(u[j & 1] * (double)(max_cycles - j));
+                int vt = t, vj = j, it = -1;
+                for (int q = 0; q < n_over; ++q) {
+                    if (key[q] == t) { vt = val[q]; it = q; }
+                    if (key[q] == j) vj = val[q];
+                }
+                if (it >= 0) val[it] = vj; else { key[n_over] = t; val[n_over++] = vj; } /* perm[t] = perm[j] */
+                forced_index[j] = vt;                                                    /* perm[j] = old perm[t] */
+            }
+        }
         double b0[2], b1[2], b2[2], b3[2];
         qo_uniform_pair(seed, attempt, replica, 0, b0);
         qo_uniform_pair(seed, attempt, replica, 1, b1);
@@ -459,6 +487,8 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
         const double opd[3] = {b1[0], b1[1], b2[0]};
         int m = 0;
         while (m < n_moves - 1 && cdf[m] <= u_select) ++m;
+        for (int j = 0; j < n_forced; ++j)
+            if (forced_index[j] == k % max_cycles) m = forced_move[j]; /* a forced cycle: no selection draw */
         qo_move_t *mv = &moves[m];
         const int n = st->n_atoms;
         const double kT = st->temperature * KB;

@@ -43,6 +43,8 @@ typedef struct {
     int32_t chain;         /* bit 0: the next entry of moves[] belongs to the same composite move (moves/displacement.py:363-455);
                               bit 1: plain CompositeMove (moves/composite.py:43-62): labels may repeat, a CellMove may close it */
     int32_t axes;          /* CellMove: bit d set = axis d is deformed (diagonal of IsotropicDeformation.mask); 0 = all three */
+    int32_t minimum_count; /* MoveStorage.minimum_count (mc/core.py:331-342) */
+    int32_t max_cycles;    /* cycles per step (entry 0), needed if some minimum_count > 0 */
     int32_t _pad;
     int32_t *labels;       /* [n_max] this move's labels, updated in place on accepted exchanges */
 } qo_move_t;

@@ -52,6 +52,8 @@ class Move(C.Structure):
         ("repeat", C.c_int32),
         ("chain", C.c_int32),
         ("axes", C.c_int32),
+        ("minimum_count", C.c_int32),
+        ("max_cycles", C.c_int32),
         ("_pad", C.c_int32),
         ("labels", C.c_void_p),
     ]

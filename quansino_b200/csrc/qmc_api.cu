@@ -260,6 +260,12 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         if (!head && mv.type == QMC_MOVE_DISPLACEMENT && mv.labels != moves[m - 1].labels)
             return fail(QMC_ERR_UNSUPPORTED, "move %d: the sub-moves of a composite move must share one label array", m);
         any_composite |= mv.chain || mv.repeat > 1;
+        if (mv.minimum_count < 0) return fail(QMC_ERR_INVALID, "move %d: negative minimum_count", m);
+        if (head)
+            for (int q = 0; q < mv.minimum_count; ++q) {
+                if (a.n_forced >= QMC_MAX_FORCED) return fail(QMC_ERR_UNSUPPORTED, "at most %d forced moves per step on the GPU path", QMC_MAX_FORCED);
+                a.forced_move[a.n_forced++] = m;
+            }
         switch (mv.type) {
             case QMC_MOVE_DISPLACEMENT:
                 if (mv.op != QMC_OP_BALL && mv.op != QMC_OP_BOX && mv.op != QMC_OP_SPHERE)
@@ -292,6 +298,13 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         a.mv[m].labels = mv.labels;
     }
     if (!(tot > 0.0)) return fail(QMC_ERR_INVALID, "move probabilities sum to zero");
+    if (a.n_forced > 0) {  // mc/core.py:161-165: the forced moves must fit into a step; steps are counted from attempt 0
+        a.max_cycles = moves[0].max_cycles;
+        if (a.max_cycles < a.n_forced) return fail(QMC_ERR_INVALID, "The number of forced moves exceeds the number of cycles.");
+        if (attempt_base % (uint64_t)a.max_cycles != 0 || n_attempts % a.max_cycles != 0)
+            return fail(QMC_ERR_INVALID, "with forced moves a launch must cover whole steps of max_cycles attempts");
+        any_composite = true;  // forced moves live in the general instantiation of the warp-per-replica kernel
+    }
     if (any_exchange)
         for (int m = 0; m < n_moves; ++m)
             if (moves[m].chain & 4) return fail(QMC_ERR_UNSUPPORTED, "label groups cannot be combined with exchange moves on the GPU path");
@@ -343,7 +356,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         // help a starved one; it pays only through multi-wave batches.  Off unless QMC_CHUNK is set.)
         int chunk = 0;
         if (const char *c = std::getenv("QMC_CHUNK")) chunk = std::atoi(c);
-        if (chunk > 0 && n_attempts > chunk) {
+        if (chunk > 0 && n_attempts > chunk && !any_composite) {
             int *buf = nullptr;
             if ((rc = get_scratch((cudaStream_t)stream, (size_t)batch->n_replicas + 1, &buf))) return rc;
             CUDA_TRY(cudaMemsetAsync(buf, 0, ((size_t)batch->n_replicas + 1) * sizeof(int), (cudaStream_t)stream));

@@ -34,6 +34,8 @@ struct SweepArgs {
     MoveDev mv[QMC_MAX_MOVES];
     double cdf[QMC_MAX_MOVES];
     int n_moves;
+    int n_forced, max_cycles;             // forced moves (minimum_count): how many per step, cycles per step
+    int forced_move[QMC_MAX_FORCED];      // table index of forced move j (heads repeated minimum_count times, table order)
     int need_coin;  // any exchange move present
     unsigned long long seed, attempt_base;
     int n_attempts;
@@ -457,6 +459,39 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
 
         int m = 0;
         while (m < a.n_moves - 1 && a.cdf[m] <= D.u_select) ++m;
+        if ((FEAT & F_COMPOSITE) && a.n_forced > 0) {
+            // forced moves (mc/core.py:331-342): at the start of a step draw n_forced distinct cycle indices -- a partial
+            // Fisher-Yates shuffle of arange(max_cycles), lane q holding override q of the sparse permutation -- then a cycle
+            // whose index was drawn performs its forced move instead of the selected one
+            const int c = k % a.max_cycles;
+            if (c == 0) {
+                double d0, d1;
+                uniform_pair(key, attempt, grep, 4u + (uint32_t)(lane >> 1), d0, d1);
+                const double u_mine = (lane & 1) ? d1 : d0;
+                int okey = -1, oval = 0, n_over = 0;
+                for (int j = 0; j < a.n_forced; ++j) {
+                    const double u = __shfl_sync(FULL, u_mine, j);
+                    const int t = j + (int)(u * (double)(a.max_cycles - j));
+                    const unsigned bt = __ballot_sync(FULL, lane < n_over && okey == t);
+                    const unsigned bj = __ballot_sync(FULL, lane < n_over && okey == j);
+                    const int vt = bt ? __shfl_sync(FULL, oval, __ffs(bt) - 1) : t;
+                    const int vj = bj ? __shfl_sync(FULL, oval, __ffs(bj) - 1) : j;
+                    if (bt) {
+                        if (lane == __ffs(bt) - 1) oval = vj;  // perm[t] = perm[j]
+                    } else {
+                        if (lane == n_over) {
+                            okey = t;
+                            oval = vj;
+                        }
+                        ++n_over;
+                    }
+                    if (lane == 0) R.forced()[j] = vt;  // perm[j] = old perm[t]
+                }
+                __syncwarp();
+            }
+            const unsigned bf = __ballot_sync(FULL, lane < a.n_forced && R.forced()[lane] == c);
+            if (bf) m = a.forced_move[__ffs(bf) - 1];
+        }
         const MoveDev &mv = a.mv[m];
         const int *lab = ((FEAT & F_LABELS) && mv.labels) ? mv.labels + (size_t)r * nmax : nullptr;
 

@@ -10,7 +10,7 @@ Deviations from the reference, all explicit:
 * ``step()`` still is a generator, but it yields the names of the moves available in this step once per launch, not
   one name per cycle (the per-cycle selection happens on the device, independently per replica);
 * ``seed`` keys a counter-based Philox stream (DESIGN.md "Random stream") instead of PCG64;
-* forced moves (``minimum_count > 0``), user-defined Python hooks and everything listed in SURVEY.md section 8f raise
+* user-defined Python hooks and everything still listed as "next" in DESIGN.md section 0 raise
   ``NotImplementedError`` -- nothing falls back to the CPU.
 """
 
@@ -141,8 +141,6 @@ class MonteCarlo:
                     break
         if criteria is None:
             raise ValueError(f"No criteria provided, and no default criteria found for move type {type(move)}.")
-        if minimum_count:
-            raise NotImplementedError("forced moves (minimum_count > 0) are not available on the GPU path")
         self.moves[name] = MoveStorage(move=move, criteria=criteria, interval=interval, probability=probability, minimum_count=minimum_count)
         self._lowered = None
 
@@ -159,8 +157,10 @@ class MonteCarlo:
         move occupies a chain of consecutive entries; ``self._slots[name]`` is the entry of its head (counters, trace)."""
         key = tuple(names)
         if self._lowered is not None and self._lowered[0] == key:
-            for n in names:  # probabilities may be changed between steps (mc/core.py:344-347)
+            for n in names:  # probabilities and forced counts may be changed between steps (mc/core.py:331-347)
                 self._lowered[1][self._slots[n]].probability = float(self.moves[n].probability)
+                self._lowered[1][self._slots[n]].minimum_count = int(self.moves[n].minimum_count)
+            self._lowered[1][0].max_cycles = int(self.max_cycles)
             return self._lowered[1], self._lowered[2]
         n_atoms = self.batch.n_atoms.cpu().numpy()
         any_exchange = any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE for n in names)
@@ -176,6 +176,9 @@ class MonteCarlo:
                     f"{type(st.criteria).__name__} with {type(st.move).__name__} is not a combination of the GPU path"
                 )
             m.probability = float(st.probability)
+            m.minimum_count = int(st.minimum_count)  # forced occurrences per step (mc/core.py:331-342), placed by the kernel
+            if m.minimum_count and m.type == _lib.MOVE_HMC:
+                raise NotImplementedError("forced Hamiltonian moves are not available on the GPU path")
             if m.type in (_lib.MOVE_DISPLACEMENT, _lib.MOVE_EXCHANGE):
                 if not hasattr(st, "_label_tensor"):
                     if any_exchange or not st.move.is_identity(n_atoms):
@@ -205,6 +208,7 @@ class MonteCarlo:
         arr = (_lib.Move * len(entries))()
         for i, m in enumerate(entries):
             arr[i] = m
+        arr[0].max_cycles = int(self.max_cycles)
         self._slots = slots
         self._lowered = (key, arr, keep)
         return arr, keep

@@ -20,7 +20,7 @@ def test_oracle_reproduces_genuine_quansino(name):
     assert np.array_equal(tr["n_atoms"], g["n_atoms"])
     n = rep.n_atoms
     np.testing.assert_allclose(rep.positions[:n], g["positions"], rtol=0, atol=1e-11)
-    if g["kind"] in ("isobaric", "hybrid"):
+    if g["kind"] in ("isobaric", "hybrid", "forced"):
         np.testing.assert_allclose(rep.cell, g["cell"], rtol=1e-14)
     if g["kind"] in ("gc_lj", "gc_emt"):
         assert rep.n_exchange == g["n_exchange"]

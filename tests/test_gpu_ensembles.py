@@ -326,3 +326,45 @@ def test_composite_and_label_groups_with_lennard_jones(cuda_lib):
         assert np.array_equal(tr["moved"][r], ref["moved"])
         np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-11)
         np.testing.assert_allclose(out.positions[r, :n], rep.positions[:n], rtol=0, atol=1e-11)
+
+
+def test_forced_moves_match_oracle(cuda_lib):
+    """minimum_count (mc/core.py:331-342) over several launches: every step contains its forced moves at the cycles the oracle
+    places them, for every replica."""
+    from quansino_b200 import operations
+    from quansino_b200.mc import Canonical
+    from quansino_b200.moves import DisplacementMove
+
+    R, M, steps = 6, 25, 6
+    pos, cell, n = cu_replicas(3, R, seed=66)
+    lab = np.arange(n)
+    mc = Canonical(_emt_atoms(pos, cell, n), temperature=500.0, seed=515, trace=True, max_cycles=M, resync_interval=0, steps_per_launch=2,
+                   default_displacement_move=DisplacementMove(lab, operations.Ball(0.1)))  # fmt: skip
+    mc.add_move(DisplacementMove(lab, operations.Sphere(0.03)), name="sphere", probability=0.0, minimum_count=4)
+    mc.add_move(DisplacementMove(lab, operations.Box(0.2)) * 2, criteria=type(mc.moves["sphere"].criteria)(), name="pair", probability=0.1,
+                minimum_count=1)  # fmt: skip
+    traces = []
+    for step in mc.irun(steps):
+        for _ in step:
+            pass
+        traces.append({k: v.copy() for k, v in mc.last_trace.items()})
+    move = np.concatenate([t["move"] for t in traces], axis=1)
+    accepted = np.concatenate([t["accepted"] for t in traces], axis=1)
+    energy = np.concatenate([t["energy"] for t in traces], axis=1)
+    par = emt_params("Cu")
+    la = lab.astype(np.int32)
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, temperature=500.0)
+        specs = [
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.1, probability=1.0, max_cycles=M, labels=la.copy()),
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_SPHERE, step=0.03, probability=0.0, minimum_count=4, labels=la.copy()),
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BOX, step=0.2, probability=0.1, minimum_count=1, repeat=2, labels=la.copy()),
+        ]
+        ref = capi.mc_run(par, rep, specs, 515, r, 0, steps * M)
+        assert np.array_equal(move[r], ref["move"])
+        assert np.array_equal(accepted[r], ref["accepted"])
+        np.testing.assert_allclose(energy[r], ref["energy"], rtol=1e-10, atol=1e-12)
+        per_step = move[r].reshape(steps, M)
+        assert np.all((per_step == 1).sum(axis=1) == 4)  # probability 0: exactly the forced ones
+        assert np.all((per_step == 2).sum(axis=1) >= 1)
+    assert len({tuple(np.where(move[r].reshape(steps, M)[0] == 1)[0]) for r in range(R)}) > 1  # placements differ between replicas

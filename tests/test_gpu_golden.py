@@ -20,7 +20,7 @@ def test_cuda_reproduces_genuine_quansino(cuda_lib, name):
     n = int(out.n_atoms[0])
     assert n == g["n_atoms"][-1]
     np.testing.assert_allclose(out.positions[0, :n], g["positions"], rtol=0, atol=1e-10)
-    if g["kind"] in ("isobaric", "hybrid"):
+    if g["kind"] in ("isobaric", "hybrid", "forced"):
         np.testing.assert_allclose(out.cell[0], g["cell"], rtol=1e-13)
     if g["kind"] in ("gc_lj", "gc_emt"):
         assert mc.number_of_exchange_particles[0] == g["n_exchange"]
