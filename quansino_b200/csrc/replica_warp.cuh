@@ -27,11 +27,6 @@
 
 namespace qmc {
 
-#ifdef QMC_SCAN_UNROLL
-constexpr int kScanUnroll = QMC_SCAN_UNROLL;
-#else
-constexpr int kScanUnroll = 1;
-#endif
 constexpr int XCAP = 64;             // capacity for second-image list entries of one attempt (cells of >= 64 atoms)
 constexpr unsigned NOPOS = 0xFFFFu;  // pp half-word: no list entry
 constexpr unsigned NOITEM = 0xFFFFFFFFu;  // queue word: empty
@@ -167,14 +162,6 @@ __device__ __forceinline__ double axis_nearest_any(double xi, double xj, const A
     const double d0 = fma(-k, A.L, d);
     extra = extra || fabs(d0) > A.thr;
     return d0;
-}
-
-// kept for the trajectory kernel: nearest and second image
-__device__ __forceinline__ void axis_images(double xi, double xj, double L, double invL, double thr, bool per, double &d0,
-                                            double &d1, unsigned &extra, unsigned bit) {
-    const Axis A{L, invL, thr};
-    d0 = axis_nearest(xi, xj, A, per, extra, bit);
-    d1 = per ? d0 - copysign(L, d0) : d0;
 }
 
 struct DeltaAcc {
@@ -435,17 +422,7 @@ __device__ __forceinline__ void eval_pass(const PotDev &pot, const RV &R, const 
 
 template <class RV, int MODE>
 __device__ __forceinline__ void eval_list(const PotDev &pot, const RV &R, const int lane, int cnt, int xstart, DeltaAcc &acc) {
-#ifdef QMC_PAIR_UNROLL2
-    // two independent passes per iteration: twice the instruction-level parallelism in the FP64 chains
-    int e0 = 0;
-    for (; e0 + 32 < cnt; e0 += 64) {
-        eval_pass<RV, MODE>(pot, R, lane, e0, cnt, xstart, acc);
-        eval_pass<RV, MODE>(pot, R, lane, e0 + 32, cnt, xstart, acc);
-    }
-    if (e0 < cnt) eval_pass<RV, MODE>(pot, R, lane, e0, cnt, xstart, acc);
-#else
     for (int e0 = 0; e0 < cnt; e0 += 32) eval_pass<RV, MODE>(pot, R, lane, e0, cnt, xstart, acc);
-#endif
     __syncwarp();
 }
 

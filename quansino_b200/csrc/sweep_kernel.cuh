@@ -2,16 +2,19 @@
 // every replica of the batch, one warp per replica, replica state resident in shared memory.
 //
 // Per attempt, for one replica (reference file:line in brackets):
-//   draws      Philox blocks 0..3 of (attempt, global replica)                  [mc/core.py:344-349 and below]
-//   select     searchsorted(cdf, u_select, 'right') over the move table         [mc/core.py:344-349]
-//   propose    DisplacementMove + Ball / Box / Sphere                           [moves/displacement.py:143-171,
-//                                                                                 operations/displacement.py:67-153]
-//              CellMove + IsotropicDeformation                                  [moves/cell.py:57-94, operations/cell.py:153-169]
-//              ExchangeMove + Translation                                       [moves/exchange.py:134-176]
-//   energy     LOCAL delta of the moved / inserted / deleted atom (the reference recomputes the whole system
+//   draws      Philox blocks 0..3 of (attempt, global replica), four attempts at a time       [mc/core.py:344-349 and below]
+//   select     searchsorted(cdf, u_select, 'right') over the move table; forced moves         [mc/core.py:331-349]
+//              (minimum_count) placed once per step
+//   propose    DisplacementMove + Ball / Box / Sphere, label groups move rigidly               [moves/displacement.py:143-171,
+//                                                                                               operations/displacement.py:67-153]
+//              CompositeDisplacementMove / CompositeMove chains (+ closing CellMove)            [moves/displacement.py:392-431,
+//                                                                                               moves/composite.py:43-62]
+//              CellMove + IsotropicDeformation (axis mask)                                      [moves/cell.py:57-94, operations/cell.py:153-169]
+//              ExchangeMove + Translation                                                       [moves/exchange.py:134-176]
+//   energy     LOCAL delta of the moved / inserted / deleted atom(s) (the reference recomputes the whole system
 //              through ASE: mc/criteria.py:104-106); full recompute only for cell moves
-//   criteria   Canonical / Isobaric / GrandCanonical                            [mc/criteria.py:89-110,146-172,226-278]
-//   commit     in place on accept; nothing to undo on reject                    [mc/contexts.py:144-156,350-368]
+//   criteria   Canonical / Isobaric / GrandCanonical                                            [mc/criteria.py:89-110,146-172,226-278]
+//   commit     in place on accept; nothing to undo on reject (composites restore a snapshot)    [mc/contexts.py:144-156,350-368]
 #pragma once
 
 #include "replica_warp.cuh"
