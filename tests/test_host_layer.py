@@ -39,6 +39,21 @@ def test_struct_layouts_match_the_header():
     assert sizes == [C.sizeof(_lib.Potential), C.sizeof(_lib.Move), C.sizeof(_lib.Batch), C.sizeof(_lib.Trace)]
 
 
+def test_integration_stub_structs_match_the_library():
+    """The ctypes structs printed in INTEGRATION.md are the ones a maintainer would paste: same sizes as the library's."""
+    import ctypes as C
+
+    from quansino_b200 import _lib
+
+    text = (ROOT / "INTEGRATION.md").read_text()
+    ns = {"C": C}
+    for name in ("qmc_potential", "qmc_move", "qmc_batch"):
+        m = re.search(rf"class {name}\(C\.Structure\):.*?(_fields_ = .*?)\n\n(?:class|def) ", text, re.S)
+        assert m, name
+        exec("class T(C.Structure):\n    " + m.group(1).replace("\n", "\n    "), ns)
+        assert C.sizeof(ns["T"]) == C.sizeof({"qmc_potential": _lib.Potential, "qmc_move": _lib.Move, "qmc_batch": _lib.Batch}[name]), name
+
+
 def test_no_gpu_means_loud_failure_not_fallback():
     import torch
 
