@@ -19,7 +19,8 @@ Parity status
   ``tests/golden/``; the C and numpy restatements are checked against them, and
   against the known-answer constants of the reference's own tests
   (``tests/mc/test_grand_canonical.py:557-600``).
-* ASE-owned arithmetic (EMT, Lennard-Jones, neighbour enumeration): PARITY
+* ASE-owned arithmetic (EMT, Lennard-Jones, neighbour enumeration, and
+  ``Atoms.euler_rotate`` / ``get_center_of_mass`` behind ``Rotation``): PARITY
   UNPINNED.  ``ase`` (pinned 3.26.0, ``uv.lock:6-7``) is a third-party dependency
   that is neither vendored in ``/root/reference`` nor installable here (no
   network), and no reference test pins an EMT/LJ energy.  ``potentials.py`` and

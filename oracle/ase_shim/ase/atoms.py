@@ -155,6 +155,32 @@ class Atoms:
     def get_chemical_symbols(self):
         return [_symbol_of[int(z)] for z in self.arrays["numbers"]]
 
+    # -- rigid rotations (ase/atoms.py: get_center_of_mass, euler_rotate) [ASE-recalled, see oracle/__init__.py] --------
+    def get_center_of_mass(self, scaled=False):
+        masses = self.get_masses()
+        return masses @ self.arrays["positions"] / masses.sum()
+
+    def euler_rotate(self, phi=0.0, theta=0.0, psi=0.0, center=(0, 0, 0)):
+        """z-x-z Euler rotation about `center`; the angles are in DEGREES (quansino's Rotation passes radians: a quirk to
+        reproduce, operations/displacement.py:196-197)."""
+        from math import cos, pi, sin
+
+        if isinstance(center, str):
+            if center.lower() != "com":
+                raise NotImplementedError("the shim rotates about the centre of mass or a point")
+            center = self.get_center_of_mass()
+        center = np.asarray(center, dtype=float)
+        phi *= pi / 180
+        theta *= pi / 180
+        psi *= pi / 180
+        rcoords = self.arrays["positions"] - center
+        D = np.array(((cos(phi), sin(phi), 0.0), (-sin(phi), cos(phi), 0.0), (0.0, 0.0, 1.0)))
+        C = np.array(((1.0, 0.0, 0.0), (0.0, cos(theta), sin(theta)), (0.0, -sin(theta), cos(theta))))
+        B = np.array(((cos(psi), sin(psi), 0.0), (-sin(psi), cos(psi), 0.0), (0.0, 0.0, 1.0)))
+        A = np.dot(B, np.dot(C, D))
+        rcoords = np.dot(A, np.transpose(rcoords))
+        self.arrays["positions"] = np.transpose(rcoords) + center
+
     # -- dynamics -----------------------------------------------------------------------------------
     def get_masses(self):
         if "masses" in self.arrays:

@@ -42,7 +42,7 @@ from quansino.moves.cell import CellMove  # noqa: E402
 from quansino.moves.displacement import DisplacementMove, HamiltonianDisplacementMove  # noqa: E402
 from quansino.moves.exchange import ExchangeMove  # noqa: E402
 from quansino.operations.cell import IsotropicDeformation  # noqa: E402
-from quansino.operations.displacement import Ball, Box, Sphere  # noqa: E402
+from quansino.operations.displacement import Ball, Box, Rotation, Sphere  # noqa: E402
 
 from oracle.philox import InjectedStream  # noqa: E402
 from oracle.units import bar  # noqa: E402
@@ -154,6 +154,24 @@ def case_groups(seed, n_attempts):
     tr = run_steps(mc, 1)
     return dict(
         kind="groups", seed=seed, replica=7, temperature=300.0, step_size=0.06, positions0=pos0, cell=cell, labels=labels,
+        positions=atoms.positions.copy(), **tr,
+    )  # fmt: skip
+
+
+def case_rotation(seed, n_attempts):
+    """Rotation (operations/displacement.py:178-200) of label groups -- trimers and one group of six -- next to rigid translations
+    of the same groups."""
+    atoms, pos0, cell = cu_atoms(3, 0.05, 9191)
+    n = len(atoms)
+    labels = np.full(n, -1)
+    labels[0:36] = np.repeat(np.arange(12), 3) * 2 + 11  # trimers (0,1,2), (3,4,5), ...
+    labels[[40, 51, 62, 73, 84, 95]] = 4
+    mc = Canonical(atoms, temperature=4000.0, max_cycles=n_attempts, default_displacement_move=DisplacementMove(labels, Ball(0.05)))
+    mc.add_move(DisplacementMove(labels, Rotation()), name="rotation", probability=1.0)
+    inject(mc, seed, 9)
+    tr = run_steps(mc, 1)
+    return dict(
+        kind="rotation", seed=seed, replica=9, temperature=4000.0, step_size=0.05, positions0=pos0, cell=cell, labels=labels,
         positions=atoms.positions.copy(), **tr,
     )  # fmt: skip
 
@@ -304,6 +322,7 @@ def main():
         "composite_hybrid": lambda: case_hybrid(5004, 90, 3),
         "label_groups": lambda: case_groups(6001, 100),
         "forced_moves": lambda: case_forced(7001, 3),
+        "group_rotation": lambda: case_rotation(8001, 100),
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():

@@ -613,10 +613,41 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                     t[0] = mv->step * (s * cos(phi)); t[1] = mv->step * (s * sin(phi)); t[2] = mv->step * c;
                 } else if (mv->op == QO_OP_BOX) { /* :67-68 */
                     for (int x = 0; x < 3; ++x) t[x] = -mv->step + (mv->step - -mv->step) * opd[x];
+                } else if (mv->op == QO_OP_ROTATION) {
+                    t[0] = t[1] = t[2] = 0.0; /* per-atom displacements below */
                 } else { rc = -1; goto done; }
                 memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
+                if (mv->op == QO_OP_ROTATION) {
+                    /* Rotation.calculate (operations/displacement.py:192-200): molecule.euler_rotate(phi, theta, psi, center="COM")
+                     * with phi, theta, psi = uniform(0, 2 pi, 3); ASE reads the angles as DEGREES [ASE-recalled: ase/atoms.py
+                     * euler_rotate, get_center_of_mass]; the move adds molecule.positions - positions[moving] */
+                    double ang[3], com[3] = {0, 0, 0}, msum = 0.0;
+                    for (int q = 0; q < 3; ++q) ang[q] = (0.0 + (TWO_PI - 0.0) * opd[q]) * (3.141592653589793 / 180);
+                    for (int i = 0; i < n; ++i)
+                        if (mv->labels[i] == label) {
+                            for (int x = 0; x < 3; ++x) com[x] += st->mass * st->pos[3 * i + x];
+                            msum += st->mass;
+                        }
+                    for (int x = 0; x < 3; ++x) com[x] /= msum;
+                    const double cphi = cos(ang[0]), sphi = sin(ang[0]), cth = cos(ang[1]), sth = sin(ang[1]), cpsi = cos(ang[2]), spsi = sin(ang[2]);
+                    const double D[3][3] = {{cphi, sphi, 0.0}, {-sphi, cphi, 0.0}, {0.0, 0.0, 1.0}};
+                    const double Cm[3][3] = {{1.0, 0.0, 0.0}, {0.0, cth, sth}, {0.0, -sth, cth}};
+                    const double B[3][3] = {{cpsi, spsi, 0.0}, {-spsi, cpsi, 0.0}, {0.0, 0.0, 1.0}};
+                    double CD[3][3], A[3][3];
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) CD[i][j] = (Cm[i][0] * D[0][j] + Cm[i][1] * D[1][j]) + Cm[i][2] * D[2][j];
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) A[i][j] = (B[i][0] * CD[0][j] + B[i][1] * CD[1][j]) + B[i][2] * CD[2][j];
+                    for (int i = 0; i < n; ++i)
+                        if (mv->labels[i] == label) {
+                            double rcv[3], xn[3];
+                            for (int x = 0; x < 3; ++x) rcv[x] = st->pos[3 * i + x] - com[x];
+                            for (int x = 0; x < 3; ++x) xn[x] = ((A[x][0] * rcv[0] + A[x][1] * rcv[1]) + A[x][2] * rcv[2]) + com[x];
+                            for (int x = 0; x < 3; ++x) trial[3 * i + x] = st->pos[3 * i + x] + (xn[x] - st->pos[3 * i + x]);
+                        }
+                }
                 for (int i = 0; i < n; ++i)
-                    if (mv->labels[i] == label)
+                    if (mv->op != QO_OP_ROTATION && mv->labels[i] == label)
                         for (int x = 0; x < 3; ++x) trial[3 * i + x] = st->pos[3 * i + x] + t[x];
                 moved = a; /* first member of the group */
                 double e_new;

@@ -17,7 +17,7 @@ LABEL_NONE = -(2**31)
 
 POT_EMT, POT_LJ = 0, 1
 MOVE_DISPLACEMENT, MOVE_CELL, MOVE_EXCHANGE, MOVE_HMC = 0, 1, 2, 3
-OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET = 0, 1, 2, 3, 4, 5
+OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET, OP_ROTATION = 0, 1, 2, 3, 4, 5, 6
 
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
 STATUS_EXP_OVERFLOW, STATUS_CAPACITY, STATUS_CELL_TOO_SMALL, STATUS_LIST_OVERFLOW = 1, 2, 4, 8

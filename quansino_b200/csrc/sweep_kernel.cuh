@@ -509,8 +509,49 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
             const int ng = lab ? max_label(lab, R.n) + 1 : 0;
             if (ng > 0) {
                 const int g = (int)(D.u_label * (double)ng);
-                double t[3];
-                propose_translation(mv.op, mv.step, D.o0, D.o1, D.o2, t);
+                const bool rot = mv.op == QMC_OP_ROTATION;
+                double t[3] = {0.0, 0.0, 0.0}, A[9], com[3] = {0.0, 0.0, 0.0};
+                if (!rot) {
+                    propose_translation(mv.op, mv.step, D.o0, D.o1, D.o2, t);
+                } else {
+                    // Rotation.calculate (operations/displacement.py:192-200): euler_rotate(phi, theta, psi, center="COM") with
+                    // phi, theta, psi = uniform(0, 2 pi, 3) -- ASE reads them as DEGREES -- z-x-z, A = B (C D); products and sums in
+                    // numpy's order, without contraction
+                    double ms = 0.0;
+                    for (int base = 0; base < R.n; base += 32) {
+                        const int j = base + lane;
+                        unsigned members = __ballot_sync(FULL, j < R.n && __ldcg(lab + min(j, R.n - 1)) == g);
+                        while (members) {
+                            const int i = base + __ffs(members) - 1;
+                            members &= members - 1;
+                            com[0] = __dadd_rn(com[0], __dmul_rn(a.b.mass, R.x(i)));
+                            com[1] = __dadd_rn(com[1], __dmul_rn(a.b.mass, R.y(i)));
+                            com[2] = __dadd_rn(com[2], __dmul_rn(a.b.mass, R.z(i)));
+                            ms = __dadd_rn(ms, a.b.mass);
+                        }
+                    }
+                    double sn[3], cs[3];
+                    const double u3[3] = {D.o0, D.o1, D.o2};
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        com[q] = __ddiv_rn(com[q], ms);
+                        sincos_2pi(__dmul_rn(__dmul_rn(TWO_PI, u3[q]), 3.141592653589793 / 180), sn[q], cs[q]);
+                    }
+                    const double Dm[9] = {cs[0], sn[0], 0.0, -sn[0], cs[0], 0.0, 0.0, 0.0, 1.0};
+                    const double Cm[9] = {1.0, 0.0, 0.0, 0.0, cs[1], sn[1], 0.0, -sn[1], cs[1]};
+                    const double Bm[9] = {cs[2], sn[2], 0.0, -sn[2], cs[2], 0.0, 0.0, 0.0, 1.0};
+                    double CD[9];
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int i3 = q / 3 * 3, j3 = q % 3;
+                        CD[q] = __dadd_rn(__dadd_rn(__dmul_rn(Cm[i3], Dm[j3]), __dmul_rn(Cm[i3 + 1], Dm[3 + j3])), __dmul_rn(Cm[i3 + 2], Dm[6 + j3]));
+                    }
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const int i3 = q / 3 * 3, j3 = q % 3;
+                        A[q] = __dadd_rn(__dadd_rn(__dmul_rn(Bm[i3], CD[j3]), __dmul_rn(Bm[i3 + 1], CD[3 + j3])), __dmul_rn(Bm[i3 + 2], CD[6 + j3]));
+                    }
+                }
                 for (int j = lane; j < R.n; j += 32) {
                     gx[j] = R.x(j);
                     gy[j] = R.y(j);
@@ -530,6 +571,14 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                         const int i = base + __ffs(members) - 1;
                         members &= members - 1;
                         const double po[3] = {R.x(i), R.y(i), R.z(i)};
+                        if (rot) {  // molecule.positions - positions[moving]: A (x - com) + com - x
+                            const double rc[3] = {__dsub_rn(po[0], com[0]), __dsub_rn(po[1], com[1]), __dsub_rn(po[2], com[2])};
+#pragma unroll
+                            for (int q = 0; q < 3; ++q) {
+                                const double ar = __dadd_rn(__dadd_rn(__dmul_rn(A[3 * q], rc[0]), __dmul_rn(A[3 * q + 1], rc[1])), __dmul_rn(A[3 * q + 2], rc[2]));
+                                t[q] = __dsub_rn(__dadd_rn(ar, com[q]), po[q]);
+                            }
+                        }
                         const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
                         const Trial T = local_delta_move<LY>(pot, R, C, lane, lt, R.n, i, po, pn, status);
                         n_pairs += T.pairs;

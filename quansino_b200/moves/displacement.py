@@ -55,7 +55,7 @@ class DisplacementMove(BaseMove):
             raise ValueError("labels must have shape (n_atoms,) or (n_replicas, n_max)")
         out = np.full((n_replicas, n_max), -1, dtype=np.int32)
         out[:, : lab.shape[1]] = lab
-        self._grouped = False
+        self._grouped = getattr(self.operation, "op_code", -1) == _lib.OP_ROTATION  # rotations always take the group path
         for r in range(n_replicas):
             if lab.shape[1] < n_atoms[r]:
                 raise ValueError("Labels must have the same length as the number of atoms.")
@@ -77,8 +77,8 @@ class DisplacementMove(BaseMove):
 
     def is_identity(self, n_atoms: np.ndarray) -> bool:
         lab = np.asarray(self.labels)
-        if lab.ndim != 1 or self.default_label:
-            return False
+        if lab.ndim != 1 or self.default_label or getattr(self.operation, "op_code", -1) == _lib.OP_ROTATION:
+            return False  # (rotations run through the label-group path, which needs the label table)
         return bool(np.all(n_atoms == len(lab)) and np.array_equal(lab, np.arange(len(lab))))
 
     def lower(self) -> _lib.Move:
@@ -88,7 +88,7 @@ class DisplacementMove(BaseMove):
         m = _lib.Move()
         m.type = self.move_type
         m.op, m.step = self.operation.lower()
-        if m.op not in (_lib.OP_BALL, _lib.OP_BOX, _lib.OP_SPHERE):
+        if m.op not in (_lib.OP_BALL, _lib.OP_BOX, _lib.OP_SPHERE, _lib.OP_ROTATION):
             raise NotImplementedError(f"{type(self.operation).__name__} is not a displacement operation of the GPU path")
         m.default_label = _lib.LABEL_NONE if self.default_label is None else int(self.default_label)
         return m

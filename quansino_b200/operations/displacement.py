@@ -46,7 +46,11 @@ class Translation(BaseOperation):
 
 
 class Rotation(BaseOperation):
-    """Molecular rotations are not available on the GPU path."""
+    """Rigid rotation of the selected label group about its centre of mass (``operations/displacement.py:178-200``): three
+    angles ``uniform(0, 2 pi)`` handed to ASE's ``euler_rotate`` -- which reads them as DEGREES, so the rotation is at most
+    6.3 degrees per axis; the quirk is reproduced."""
+
+    op_code = _lib.OP_ROTATION
 
 
 class TranslationRotation(BaseOperation):

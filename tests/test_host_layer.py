@@ -112,8 +112,7 @@ def test_moves_lower_like_the_reference_defaults():
     assert (h.type, h.op, h.n_steps) == (_lib.MOVE_HMC, _lib.OP_VERLET, 100) and abs(h.dt - 0.09822694788464063) < 1e-16
     assert HamiltonianDisplacementMove().max_attempts == 10 and DisplacementMove(np.arange(2)).max_attempts == 10000
     # refused, never ignored
-    with pytest.raises(NotImplementedError):
-        DisplacementMove(np.arange(4), Rotation()).lower()
+    assert DisplacementMove(np.arange(4), Rotation()).lower().op == _lib.OP_ROTATION  # label groups rotate rigidly
     with pytest.raises(NotImplementedError):
         DisplacementMove(np.arange(4), Translation()).lower()
     with pytest.raises(NotImplementedError):
