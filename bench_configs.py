@@ -46,19 +46,50 @@ def timed(mc, steps, warmup):
     return e0.elapsed_time(e1) * 1e-3, int(mc.batch.pair_evals.sum().item()) - p0
 
 
+def _dist_setup():
+    """(world, rank, device); initialises NCCL under torchrun."""
+    import os
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=device)
+    return world, rank, device
+
+
 def c3(R=1024, steps=3):
+    """C3 as BASELINE.json states it: 1024 replicas per GPU (8192 over 8 GPUs under torchrun), replicas sharded, no collective in
+    the data path; the whole-job rate uses the slowest rank's time."""
+    world, rank, device = _dist_setup()
     pos0, cell = fcc_cubic("Cu", 5)
     n = len(pos0)
-    rng = np.random.default_rng(1)
+    rng = np.random.default_rng(1 + rank)
     pos = pos0[None] + rng.normal(scale=0.05, size=(R, n, 3))
     atoms = BatchedAtoms(pos, cell, np.full(R, n, np.int32), "Cu", (True,) * 3, EMT())
-    mc = Isobaric(atoms, temperature=300.0, pressure=1.0 * BAR, seed=3, resync_interval=0,
+    mc = Isobaric(atoms, temperature=300.0, pressure=1.0 * BAR, seed=3, resync_interval=0, device=device, replica_offset=rank * R,
                   default_displacement_move=DisplacementMove(np.arange(n), Ball(0.1)), default_cell_move=CellMove(IsotropicDeformation(0.05)))  # fmt: skip
     t, pairs = timed(mc, steps, 1)
     c = mc.counters()
-    return {"config": "C3 isobaric Cu 500-atom EMT, CellMove + DisplacementMove, 1024 replicas/GPU", "attempts_per_s": R * n * steps / t,
-            "pair_evals_per_s": pairs / t, "ms_per_step": 1e3 * t / steps, "cell_moves": int(c[:, 1, 0].sum()), "cell_accepted": int(c[:, 1, 1].sum()),
-            "disp_acceptance": float(c[:, 0, 1].sum() / c[:, 0, 0].sum())}  # fmt: skip
+    stats = torch.tensor([t, float(pairs), float(c[:, 1, 0].sum()), float(c[:, 1, 1].sum()), float(c[:, 0, 1].sum()), float(c[:, 0, 0].sum())],
+                         dtype=torch.float64, device=device)  # fmt: skip
+    if world > 1:
+        import torch.distributed as dist
+
+        tmax = stats[:1].clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(stats)
+        stats[0] = tmax[0]
+        dist.destroy_process_group()
+    t, pairs, cm, ca, da, dn = (float(x) for x in stats.tolist())
+    if rank != 0:
+        return None
+    return {"config": f"C3 isobaric Cu 500-atom EMT, CellMove + DisplacementMove, {R} replicas/GPU x {world} GPU(s)",
+            "attempts_per_s": world * R * n * steps / t, "pair_evals_per_s": pairs / t, "ms_per_step": 1e3 * t / steps, "cell_moves": int(cm),
+            "cell_accepted": int(ca), "disp_acceptance": da / dn}  # fmt: skip
 
 
 def c4(R=4096, steps=5, n_max=128, mu=-0.5):
