@@ -171,8 +171,11 @@ struct DeltaAcc {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// scan: fills the list.  MODE 0 = local delta (pp, l2, xj maintained for EMT), MODE 1 = one row of a full evaluation.
-// Returns the number of list entries; n2 = entries of l2; xstart = first second-image entry.
+// One-sided scan (an inserted atom or a row of a full evaluation: new side; a deleted atom: old side): fills the list with the
+// signed r^2 (+ new, - old) of every neighbour image inside the cutoff.  MODE 0 = local delta (pp, l2, xj maintained for EMT:
+// list slot e belongs to touched atom l2[e]), MODE 1 = one row of a full evaluation.  Exactly one of has_old / has_new is
+// set (displacements, which have both, go through scan_both below).  Returns the number of list entries; n2 = touched atoms;
+// xstart = first second-image entry.
 // ---------------------------------------------------------------------------------------------------
 template <class RV, int MODE, class CELL>
 __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const RV &R, const CELL &C, const int lane, const unsigned lt,
@@ -180,69 +183,59 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const RV &R, c
                                                const double pn[3], int &n2, int &xstart, int &status, int tile_first = 0,
                                                int tile_step = 1) {
     constexpr bool TRACK = (MODE == 0 && RV::EMT);
-    uint32_t *queue = R.queue();  // 2 * NS work items fit in the tail (NS doubles)
+    uint32_t *queue = R.queue();  // one word per flagged neighbour: at most n - 1 <= QCAP
     const bool p0 = C.per(0), p1 = C.per(1), p2 = C.per(2);
     const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);
+    const bool side = has_new;  // true: new position (positive r^2), false: old position (negative)
+    const double px = side ? pn[0] : po[0], py = side ? pn[1] : po[1], pz = side ? pn[2] : po[2];
     int cnt = 0, nq = 0;
-    n2 = 0;
     for (int base = tile_first * 32; base < n_scan; base += 32 * tile_step) {
         const int j = base + lane;
         const bool valid = j < n_scan && j != i_excl;
         const int jc = valid ? j : 0;
-        const double xj = R.x(jc), yj = R.y(jc), zj = R.z(jc);
-        unsigned code = NOPOS | (NOPOS << 16);
-        bool touched = false;
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            if (side == 0 ? !has_old : !has_new) continue;  // warp-uniform
-            const double *p = side == 0 ? po : pn;
-            unsigned fl = 0;
-            const double dx = axis_nearest(p[0], xj, A0, p0, fl, 1u);
-            const double dy = axis_nearest(p[1], yj, A1, p1, fl, 2u);
-            const double dz = axis_nearest(p[2], zj, A2, p2, fl, 4u);
-            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            const bool in = valid && r2 < pot.cut_pre2;
-            const unsigned b = __ballot_sync(FULL, in);
-            const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
-            if (in) R.lr(pos) = side ? r2 : -r2;
-            if (in) code = side ? ((code & 0xFFFFu) | ((unsigned)pos << 16)) : ((code & 0xFFFF0000u) | (unsigned)pos);
-            cnt += __popc(b);
-            touched |= in;
-            // second images: only if the nearest image is inside (it is the closest of all images)
-            const bool ex = in && fl != 0u;
-            const unsigned bq = __ballot_sync(FULL, ex);
-            if (ex) queue[min(nq + __popc(bq & lt), RV::QCAP - 1)] = (unsigned)j | ((unsigned)side << 15) | (fl << 16);
-            nq += __popc(bq);
+        bool f = false;
+        const double dx = axis_nearest_any(px, R.x(jc), A0, f);
+        const double dy = axis_nearest_any(py, R.y(jc), A1, f);
+        const double dz = axis_nearest_any(pz, R.z(jc), A2, f);
+        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        const bool in = valid && r2 < pot.cut_pre2;
+        const unsigned b = __ballot_sync(FULL, in);
+        const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
+        if (in) {
+            R.lr(pos) = side ? r2 : -r2;
+            if (TRACK) R.l2(pos) = (uint16_t)j;  // slot e of the nearest images belongs to touched atom l2[e]
         }
-        if (TRACK) {
-            if (valid) R.pp(j) = code;
-            const unsigned b2 = __ballot_sync(FULL, touched);
-            if (touched) R.l2(n2 + __popc(b2 & lt)) = (uint16_t)j;
-            n2 += __popc(b2);
-        }
+        if (TRACK && valid) R.pp(j) = !in ? (NOPOS | (NOPOS << 16)) : side ? (NOPOS | ((unsigned)pos << 16)) : ((NOPOS << 16) | (unsigned)pos);
+        cnt += __popc(b);
+        // second images: only if the nearest image is inside (it is the closest of all images)
+        const bool ex = in && f;
+        const unsigned bq = __ballot_sync(FULL, ex);
+        if (ex) queue[min(nq + __popc(bq & lt), RV::QCAP - 1)] = (unsigned)j;
+        nq += __popc(bq);
     }
+    if (cnt > RV::CAPE) {
+        status |= QMC_STATUS_LIST_OVERFLOW;
+        cnt = RV::CAPE;
+    }
+    n2 = cnt;
     xstart = cnt;
     if (nq > RV::QCAP) {
         status |= QMC_STATUS_LIST_OVERFLOW;
         nq = RV::QCAP;
     }
-    // second images, appended after every nearest image
     if (nq > 0) {
         __syncwarp();
         for (int q0 = 0; q0 < nq; q0 += 32) {
             const int q = q0 + lane;
             const bool has = q < nq;
-            const unsigned item = has ? queue[q] : 0u;
-            const int j = item & 0x7FFFu;
-            const unsigned side = (item >> 15) & 1u, fl = item >> 16;
-            const double *p = side ? pn : po;
-            unsigned dummy = 0;
-            const double dx0 = axis_nearest(p[0], R.x(j), A0, p0, dummy, 1u);
-            const double dy0 = axis_nearest(p[1], R.y(j), A1, p1, dummy, 2u);
-            const double dz0 = axis_nearest(p[2], R.z(j), A2, p2, dummy, 4u);
+            const int j = has ? (int)queue[q] : 0;
+            unsigned fl = 0;
+            const double dx0 = axis_nearest(px, R.x(j), A0, p0, fl, 1u);
+            const double dy0 = axis_nearest(py, R.y(j), A1, p1, fl, 2u);
+            const double dz0 = axis_nearest(pz, R.z(j), A2, p2, fl, 4u);
             const double dx1 = dx0 - copysign(A0.L, dx0), dy1 = dy0 - copysign(A1.L, dy0), dz1 = dz0 - copysign(A2.L, dz0);
             unsigned c = fl & (0u - fl);  // first non-empty subset of fl
-            bool more = has;
+            bool more = has && fl != 0u;
             while (__any_sync(FULL, more)) {
                 const double dx = (c & 1u) ? dx1 : dx0, dy = (c & 2u) ? dy1 : dy0, dz = (c & 4u) ? dz1 : dz0;
                 const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
