@@ -65,7 +65,9 @@ struct Layout {
     static constexpr int CNT_B = DRAW_B + DRAW_AHEAD * 64;  // attempted / accepted / failed of this launch per move, u32
     static constexpr int DISP_B = CNT_B + QMC_MAX_MOVES * 3 * 4;  // bitmap of the atoms a composite move displaced so far
     static constexpr int FORCED_B = round_up(DISP_B + round_up(NS, 32) / 8, 4);  // cycle indices of this step's forced moves, i32
-    static constexpr int BYTES = round_up(FORCED_B + QMC_MAX_FORCED * 4, 16);
+    static constexpr int LABW = round_up(NS, 32) / 32;               // words of one "movable atoms" bitmap
+    static constexpr int LABBIT_B = FORCED_B + QMC_MAX_FORCED * 4;  // one bitmap per move-table entry (label >= 0, atom < n)
+    static constexpr int BYTES = round_up(LABBIT_B + QMC_MAX_MOVES * LABW * 4, 16);
     // launch geometry: ONE wide CTA per SM holding as many replicas (warps) as shared memory and the 72-register budget allow.
     // Measured on B200 (4096 x 108-atom Cu EMT): 7 CTAs x 4 warps 3.10e8 attempts/s, 2 x 14 warps 3.35e8, 1 x 28 warps 3.68e8 --
     // the warp schedulers favour the warps of older CTAs, so replicas in separate CTAs finish 0.77 .. 1.39 ms into a 1.43 ms launch
@@ -102,6 +104,7 @@ struct Rep {
     __device__ __forceinline__ uint32_t &pp(int j) const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(b) + LY::PP_B)[j]; }
     __device__ __forceinline__ uint16_t &l2(int e) const { return reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(b) + LY::L2_B)[e]; }
     __device__ __forceinline__ uint16_t &xj(int e) const { return reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(b) + LY::XJ_B)[e]; }
+    __device__ __forceinline__ uint32_t *labbits(int m) const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(b) + LY::LABBIT_B) + m * LY::LABW; }
     __device__ __forceinline__ int *forced() const { return reinterpret_cast<int *>(reinterpret_cast<char *>(b) + LY::FORCED_B); }
     __device__ __forceinline__ uint32_t *displaced() const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(b) + LY::DISP_B); }
     __device__ __forceinline__ uint32_t *counts() const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(b) + LY::CNT_B); }

@@ -98,6 +98,49 @@ __device__ inline int select_available(const int *lab, int n, const uint32_t *di
     return found;
 }
 
+// --- the same selections from a bitmap of the movable atoms kept in shared memory (one per move-table entry): the label VALUES
+// only matter to the caller (and to max + 1 on insertion); with one atom per label, increasing with the atom index,
+// unique_labels[idx] is the idx-th set bit.  The bitmaps are rebuilt from the global label tables when a replica is loaded and
+// after every accepted exchange, so an attempt reads no label from global memory.
+template <class RV>
+__device__ inline void rebuild_movable(const RV &R, const MoveDev *mv, int n_moves, int r, int nmax, int words) {
+    const int lane = lane_id();
+    for (int q = 0; q < n_moves; ++q) {
+        const int *lab = mv[q].labels ? mv[q].labels + (size_t)r * nmax : nullptr;
+        uint32_t *bits = R.labbits(q);
+        for (int w = 0; w < words; ++w) {
+            const int j = w * 32 + lane;
+            const unsigned b = __ballot_sync(FULL, j < R.n && (!lab || __ldcg(lab + min(j, nmax - 1)) >= 0));
+            if (lane == 0) bits[w] = b;
+        }
+    }
+    __syncwarp();
+}
+
+__device__ inline int count_bits(const uint32_t *bits, const uint32_t *without, int words) {
+    const int lane = lane_id();
+    const unsigned w = lane < words ? (bits[lane] & ~(without ? without[lane] : 0u)) : 0u;
+    return __reduce_add_sync(FULL, __popc(w));
+}
+
+// atom index of the idx-th set bit (idx < count_bits)
+__device__ inline int select_bit(const uint32_t *bits, const uint32_t *without, int words, int idx) {
+    const int lane = lane_id();
+    const unsigned w = lane < words ? (bits[lane] & ~(without ? without[lane] : 0u)) : 0u;
+    const int c = __popc(w);
+    int incl = c;  // inclusive prefix sum over the lanes
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int excl = incl - c;
+    const bool mine = idx >= excl && idx < incl;
+    const unsigned who = __ballot_sync(FULL, mine);
+    const int found = mine ? lane * 32 + (int)__fns(w, 0, idx - excl + 1) : 0;
+    return who ? __shfl_sync(FULL, found, __ffs(who) - 1) : -1;
+}
+
 __device__ inline int max_label(const int *lab, int n) {
     int m = -1;
     for (int base = 0; base < n; base += 32) {
@@ -453,6 +496,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
     const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
     long long n_pairs = 0;
     __syncwarp();
+    if (FEAT & F_LABELS) rebuild_movable(R, a.mv, a.n_moves, r, nmax, LY::LABW);
 
     for (int k = k_begin; k < k_end; ++k) {
         const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
@@ -668,7 +712,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                 const int *slab = ((FEAT & F_LABELS) && sm.labels) ? sm.labels + (size_t)r * nmax : nullptr;
                 const int reps = sm.repeat > 0 ? sm.repeat : 1;
                 for (int q = 0; q < reps; ++q) {
-                    const int na = count_available(slab, R.n, disp);  // `disp` stays empty for a plain CompositeMove
+                    const int na = (FEAT & F_LABELS) ? count_bits(R.labbits(mm), disp, LY::LABW) : count_available(slab, R.n, disp);  // `disp` stays empty for a plain CompositeMove
                     if (na == 0) continue;  // register_failure: nothing drawn
                     double ul = D.u_label, o0 = D.o0, o1 = D.o1, o2 = D.o2;
                     if (n_drawn > 0) {  // drawing sub-move c >= 1: blocks 32 + 2 (c - 1) and 33 + 2 (c - 1)
@@ -680,7 +724,8 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                         o2 = __shfl_sync(FULL, d1, 1);
                     }
                     ++n_drawn;
-                    const int i = select_available(slab, R.n, disp, (int)(ul * (double)na));
+                    const int i = (FEAT & F_LABELS) ? select_bit(R.labbits(mm), disp, LY::LABW, (int)(ul * (double)na))
+                                                    : select_available(slab, R.n, disp, (int)(ul * (double)na));
                     double t[3];
                     propose_translation(sm.op, sm.step, o0, o1, o2, t);
                     const double po[3] = {R.x(i), R.y(i), R.z(i)};
@@ -738,10 +783,10 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                 accepted = acc ? 1 : 0;
             }
         } else if (mv.type == QMC_MOVE_DISPLACEMENT) {
-            const int nu = lab ? count_labelled(lab, R.n) : R.n;
+            const int nu = (FEAT & F_LABELS) ? count_bits(R.labbits(m), nullptr, LY::LABW) : R.n;
             if (nu > 0) {
                 const int idx = (int)(D.u_label * (double)nu);
-                const int i = lab ? select_labelled(lab, R.n, idx) : idx;
+                const int i = (FEAT & F_LABELS) ? select_bit(R.labbits(m), nullptr, LY::LABW, idx) : idx;
                 double t[3];
                 propose_translation(mv.op, mv.step, D.o0, D.o1, D.o2, t);
                 const double po[3] = {R.x(i), R.y(i), R.z(i)};
@@ -840,10 +885,10 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     pd = 1;
                 }
             } else {
-                const int nu = lab ? count_labelled(lab, R.n) : R.n;
+                const int nu = (FEAT & F_LABELS) ? count_bits(R.labbits(m), nullptr, LY::LABW) : R.n;
                 if (nu > 0) {
                     const int idx = (int)(D.u_label * (double)nu);
-                    i = lab ? select_labelled(lab, R.n, idx) : idx;
+                    i = (FEAT & F_LABELS) ? select_bit(R.labbits(m), nullptr, LY::LABW, idx) : idx;
                     po[0] = R.x(i);
                     po[1] = R.y(i);
                     po[2] = R.z(i);
@@ -888,6 +933,8 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     }
                     n_ex += pd;
                     E += delta;
+                    __syncwarp();
+                    if (FEAT & F_LABELS) rebuild_movable(R, a.mv, a.n_moves, r, nmax, LY::LABW);  // the tables changed
                 }
                 __syncwarp();
                 accepted = acc ? 1 : 0;
