@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Secondary measurements: the other configurations of BASELINE.json (C3 isobaric, C4 grand-canonical LJ, C5 HMC) on one
-GPU.  Not part of the bench.py contract; results are recorded under profiles/.  Usage: python bench_configs.py [c3|c4|c5|c5pt|composite] ... (c5pt also under torchrun)"""
+GPU.  Not part of the bench.py contract; results are recorded under profiles/.  Usage: python bench_configs.py [c3|c4|c5|c5pt|composite|fbmc] ... (c5pt also under torchrun)"""
 
 from __future__ import annotations
 
@@ -189,6 +189,28 @@ def c5pt(R_global=64, repeat=8, n_steps=100, rounds=4):
     return out if rank == 0 else None
 
 
+def fbmc(R=4096, steps=20):
+    """ForceBias (mc/fbmc.py) on the C2 system: every atom of every replica moves every step."""
+    from quansino_b200.mc import ForceBias
+
+    pos0, cell = fcc_cubic("Cu", 3)
+    n = len(pos0)
+    rng = np.random.default_rng(7)
+    pos = pos0[None] + rng.normal(scale=0.05, size=(R, n, 3))
+    fb = ForceBias(BatchedAtoms(pos, cell, np.full(R, n, np.int32), "Cu", (True,) * 3, EMT()), delta=0.1, temperature=300.0, seed=7)
+    fb.run(3)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    fb.run(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3
+    return {"config": f"ForceBias, {R} replicas x {n}-atom Cu EMT, delta 0.1 A, 300 K", "steps_per_s": steps / t,
+            "atom_moves_per_s": R * n * steps / t, "ms_per_step": 1e3 * t / steps, "rejection_rounds": float(fb.rejection_rounds.mean()),
+            "gamma_max": float(fb.gamma.max())}  # fmt: skip
+
+
 def composite(R=4096, k=4, steps=20):
     """C2 workload with CompositeDisplacementMove = DisplacementMove * k (k atoms per criteria evaluation)."""
     from quansino_b200.mc import Canonical
@@ -214,6 +236,6 @@ if __name__ == "__main__":
         if w == "c5small":
             print(json.dumps(c5(R=64, repeat=4, n_steps=20)), flush=True)
         else:
-            res = {"c3": c3, "c4": c4, "c5": c5, "c5pt": c5pt, "composite": composite}[w]()
+            res = {"c3": c3, "c4": c4, "c5": c5, "c5pt": c5pt, "composite": composite, "fbmc": fbmc}[w]()
             if res is not None:
                 print(json.dumps(res), flush=True)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define QMC_ABI_VERSION 4
+#define QMC_ABI_VERSION 5
 #define QMC_MAX_FORCED 16 /* sum of minimum_count over the move table */
 #define QMC_MAX_MOVES 4
 
@@ -184,6 +184,18 @@ int qmc_hmc(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move
             int64_t workspace_bytes, void *stream);
 /* device scratch the Hamiltonian kernels need (double-buffered positions, momenta, neighbour list, partial sums) */
 int64_t qmc_hmc_workspace_bytes(const qmc_potential_t *pot, const qmc_batch_t *batch);
+
+/* replaces ForceBias.step (src/quansino/mc/fbmc.py:202-251; force-bias Monte Carlo, doi 10.1063/1.4902136): forces at the
+ * current positions -> gamma = clip(F delta / (2 kB T), +-709.782712) -> every coordinate draws zeta in (-1, 1) by rejection
+ * against the trial probability (fbmc.py:254-273), redrawing call after call exactly the coordinates still refused ->
+ * positions += zeta * delta (momenta round trip m d / m as in the reference) -> energy (and forces) at the new positions.
+ * `forces` is a device buffer [R][3][n_max], in / out: if `forces_valid` it holds the forces at the current positions (the
+ * previous call left them there), otherwise they are evaluated first; on return it holds the forces at the NEW positions
+ * and batch.energy the new energies.  Draws: element p of call c (zeta calls even, uniform calls odd) of step `step` =
+ * Philox block ((c + 1) << 16) | (p >> 1) of attempt `step`, half p & 1.  gamma_max, n_calls: device [R], may be NULL.
+ * Single species: the mass scaling (min(m) / m)^0.25 is 1. */
+int qmc_fbmc_step(const qmc_potential_t *pot, const qmc_batch_t *batch, double delta, uint64_t seed, uint64_t step, double *forces,
+                  int32_t forces_valid, double *gamma_max, int32_t *n_calls, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* parallel tempering between temperature-adjacent replicas (no counterpart in the reference):
  * `energies_all` / `temperatures_all` are device [R_global] arrays every rank holds after the all-gather;

@@ -268,8 +268,26 @@ def mc_run(par, rep: Replica, moves: list[MoveSpec], seed: int, replica_id: int,
     return {"move": tr_move, "accepted": tr_acc, "energy": tr_e, "delta": tr_d, "n_atoms": tr_n, "moved": tr_m}
 
 
+def fbmc_step(par, positions, cell, pbc, mass, temperature, delta, seed, replica_id, step):
+    """One ForceBias step in place on ``positions`` (n, 3); returns (energy after, max |gamma|, rejection iterations)."""
+    L = lib()
+    L.qo_fbmc_step.restype = C.c_int
+    pos = np.ascontiguousarray(positions, dtype=np.float64)
+    assert pos is positions or np.shares_memory(pos, positions)
+    pot = make_potential(par)
+    cellf = np.ascontiguousarray(np.asarray(cell, dtype=np.float64).reshape(9))
+    pb = (C.c_int32 * 3)(*[int(b) for b in pbc])
+    e, g, it = C.c_double(), C.c_double(), C.c_int32()
+    rc = L.qo_fbmc_step(C.byref(pot), C.c_int32(len(pos)), pos.ctypes.data_as(C.POINTER(C.c_double)), cellf.ctypes.data_as(C.POINTER(C.c_double)),
+                        pb, C.c_double(mass), C.c_double(temperature), C.c_double(delta), C.c_uint64(seed), C.c_uint32(replica_id),
+                        C.c_uint64(step), C.byref(e), C.byref(g), C.byref(it))  # fmt: skip
+    if rc != 0:
+        raise RuntimeError(f"qo_fbmc_step failed with code {rc}")
+    return e.value, g.value, it.value
+
+
 __all__ = [
     "LABEL_NONE", "MOVE_CELL", "MOVE_DISPLACEMENT", "MOVE_EXCHANGE", "MOVE_HMC", "OP_BALL", "OP_BOX", "OP_ISOTROPIC",
-    "OP_ROTATION", "OP_SPHERE", "OP_TRANSLATION", "OP_VERLET", "MoveSpec", "Replica", "build", "emt_params", "energy", "lib", "mc_run",
+    "OP_ROTATION", "OP_SPHERE", "OP_TRANSLATION", "OP_VERLET", "MoveSpec", "Replica", "build", "emt_params", "energy", "fbmc_step", "lib", "mc_run",
     "philox", "uniform_pair",
 ]  # fmt: skip

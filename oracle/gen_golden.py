@@ -35,6 +35,7 @@ from ase.calculators.lj import LennardJones  # noqa: E402
 from quansino.integrators.displacement import Verlet  # noqa: E402
 from quansino.mc.canonical import Canonical, HamiltonianCanonical  # noqa: E402
 from quansino.mc.criteria import CanonicalCriteria, IsobaricCriteria  # noqa: E402
+from quansino.mc.fbmc import ForceBias  # noqa: E402
 from quansino.moves.composite import CompositeMove  # noqa: E402
 from quansino.mc.gcmc import GrandCanonical  # noqa: E402
 from quansino.mc.isobaric import Isobaric  # noqa: E402
@@ -174,6 +175,27 @@ def case_rotation(seed, n_attempts):
         kind="rotation", seed=seed, replica=9, temperature=4000.0, step_size=0.05, positions0=pos0, cell=cell, labels=labels,
         positions=atoms.positions.copy(), **tr,
     )  # fmt: skip
+
+
+def case_fbmc(seed, steps, delta, temperature):
+    """ForceBias (mc/fbmc.py:202-241): every atom moves every step, zeta drawn by rejection against the force-biased trial
+    probability; no acceptance test."""
+    import warnings
+
+    atoms, pos0, cell = cu_atoms(3, 0.05, 1212)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")  # "No FixCom constraint found"
+        fb = ForceBias(atoms, delta=delta, temperature=temperature, seed=1)
+    fb._rng = InjectedStream(seed, 10, mode="fbmc")
+    traj, energies, gmax = [], [], []
+    for _ in range(steps):
+        fb.step()
+        traj.append(atoms.positions.copy())
+        energies.append(float(atoms.get_potential_energy()))
+        gmax.append(float(np.max(np.abs(fb.gamma))))
+    return dict(kind="fbmc", seed=seed, replica=10, temperature=temperature, delta=delta, positions0=pos0, cell=cell,
+                trajectory=np.array(traj), energy=np.array(energies), gamma_max=np.array(gmax), positions=atoms.positions.copy(),
+                accepted=np.ones(steps, np.int8), move=np.zeros(steps, np.int8), n_atoms=np.full(steps, len(atoms), np.int32))  # fmt: skip
 
 
 def case_hybrid(seed, n_attempts, k):
@@ -323,6 +345,7 @@ def main():
         "label_groups": lambda: case_groups(6001, 100),
         "forced_moves": lambda: case_forced(7001, 3),
         "group_rotation": lambda: case_rotation(8001, 100),
+        "force_bias": lambda: case_fbmc(9001, 4, 0.1, 600.0),
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():

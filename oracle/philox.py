@@ -86,6 +86,11 @@ def normal(seed: int, attempt: int, replica: int, m: int) -> float:
     return float(r * np.cos(t)) if m % 2 == 0 else float(r * np.sin(t))
 
 
+def fbmc_draw(seed: int, step: int, replica: int, call: int, p: int) -> float:
+    """Element ``p`` of draw call ``call`` of ForceBias step ``step`` (include/quansino_b200.h, qmc_fbmc_step)."""
+    return uniform_pair(seed, step, replica, ((call + 1) << 16) | (p >> 1))[p & 1]
+
+
 class InjectedStream:
     """A ``numpy.random.Generator`` stand-in that hands the slot layout above to the GENUINE quansino code.
 
@@ -109,7 +114,9 @@ class InjectedStream:
     * ``standard_normal(shape)``    -> Box-Muller normals of the attempt, row-major
     """
 
-    def __init__(self, seed: int, replica: int = 0, attempt_base: int = 0):
+    def __init__(self, seed: int, replica: int = 0, attempt_base: int = 0, mode: str = "mc"):
+        self.mode = mode  # "mc": the per-attempt slots above; "fbmc": ForceBias (see fbmc_draw)
+        self._fb_call = 0
         self.seed = int(seed)
         self.replica = int(replica)
         self.attempt = int(attempt_base) - 1
@@ -186,14 +193,32 @@ class InjectedStream:
             self._next_attempt()  # a forced cycle: no selection draw opened this attempt
         self._select_pending = False
 
+    # -- ForceBias (mc/fbmc.py:224-241): step s draws zeta = uniform(-1, 1, (N, 3)) and random((N, 3)), then again for the
+    # coordinates whose trial was refused, until none is left.  Call c of step s (0, 1, 2, ...; zeta calls even, random calls
+    # odd), element p of that call -> Philox(seed; attempt = s, replica, block = ((c + 1) << 16) | (p >> 1)), half p & 1.
+    def _fbmc(self, size, new_step_if_2d):
+        shape = (size,) if isinstance(size, (int, np.integer)) else tuple(size)
+        if new_step_if_2d and len(shape) == 2:
+            self._next_attempt()
+            self._fb_call = 0
+        c = self._fb_call
+        self._fb_call += 1
+        n = int(np.prod(shape))
+        out = np.array([fbmc_draw(self.seed, self.attempt, self.replica, c, p) for p in range(n)])
+        return out.reshape(shape)
+
     def uniform(self, low=0.0, high=1.0, size=None):
+        if self.mode == "fbmc":
+            return low + (high - low) * self._fbmc(size, True)
         if size is None:
             return low + (high - low) * self._op_draw()
         n = int(np.prod(size))
         out = np.array([low + (high - low) * self._op_draw() for _ in range(n)])
         return out.reshape(size)
 
-    def random(self):
+    def random(self, size=None):
+        if self.mode == "fbmc":
+            return self._fbmc(size, False)
         first = self._calls == 0
         self._calls += 1
         if first:

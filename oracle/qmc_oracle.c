@@ -414,6 +414,60 @@ static void scale_positions(int n, double *pos, const double old_cell[9], const 
     }
 }
 
+int qo_fbmc_step(const qo_potential_t *pot, int32_t n, double *pos, const double *cell, const int32_t *pbc, double mass,
+                 double temperature, double delta, uint64_t seed, uint32_t replica, uint64_t step, double *energy,
+                 double *gamma_max, int32_t *n_iter) {
+    const int M = 3 * n;
+    double *frc = (double *)malloc(sizeof(double) * (size_t)M), *gam = (double *)malloc(sizeof(double) * (size_t)M);
+    double *den = (double *)malloc(sizeof(double) * (size_t)M), *zeta = (double *)malloc(sizeof(double) * (size_t)M);
+    char *conv = (char *)calloc((size_t)M, 1);
+    int rc = 0;
+    if (!frc || !gam || !den || !zeta || !conv) { rc = -1; goto out; }
+    double e0;
+    if (qo_energy(pot, n, pos, cell, pbc, &e0, frc, NULL) < 0) { rc = -1; goto out; }
+    const double gmaxv = 709.782712; /* ForceBias.gamma_max_value */
+    double gm = 0.0;
+    for (int m = 0; m < M; ++m) { /* calculate_gamma (mc/fbmc.py:93-108) */
+        double g = (frc[m] * delta) / (2 * temperature * KB);
+        g = g < -gmaxv ? -gmaxv : (g > gmaxv ? gmaxv : g);
+        gam[m] = g;
+        den[m] = exp(g) - exp(-g);
+        if (fabs(g) > gm) gm = fabs(g);
+    }
+    int remaining = M, iter = 0;
+    while (remaining > 0) { /* mc/fbmc.py:224-241 */
+        int p = 0;
+        for (int m = 0; m < M; ++m) {
+            if (conv[m]) continue;
+            double uz[2], ur[2];
+            qo_uniform_pair(seed, step, replica, (uint32_t)(((2 * iter + 1) << 16) | (p >> 1)), uz);
+            qo_uniform_pair(seed, step, replica, (uint32_t)(((2 * iter + 2) << 16) | (p >> 1)), ur);
+            const double z = -1 + (1 - -1) * uz[p & 1], u = ur[p & 1];
+            const double sg = z > 0 ? 1.0 : (z < 0 ? -1.0 : 0.0); /* np.sign */
+            double pt = exp(sg * gam[m]) - exp(gam[m] * (2 * z - sg)); /* calculate_trial_probability (:254-273) */
+            pt *= sg;
+            const double ptrial = den[m] != 0 ? pt / den[m] : 1.0;
+            zeta[m] = z;
+            conv[m] = ptrial > u;
+            ++p;
+        }
+        remaining = 0;
+        for (int m = 0; m < M; ++m) remaining += !conv[m];
+        ++iter;
+        if (iter > 10000) { rc = -1; goto out; }
+    }
+    for (int m = 0; m < M; ++m) { /* displacement = zeta delta (min(m) / m)^0.25; momenta round trip (:243-251) */
+        const double d = zeta[m] * delta * pow(mass / mass, 0.25);
+        pos[m] = pos[m] + (mass * d) / mass;
+    }
+    if (qo_energy(pot, n, pos, cell, pbc, energy, NULL, NULL) < 0) { rc = -1; goto out; }
+    if (gamma_max) *gamma_max = gm;
+    if (n_iter) *n_iter = iter;
+out:
+    free(frc); free(gam); free(den); free(zeta); free(conv);
+    return rc;
+}
+
 int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32_t n_moves, uint64_t seed, uint32_t replica,
               uint64_t attempt_base, int32_t n_attempts, qo_trace_t *trace, int64_t counters[4]) {
     const int nmax = st->n_max;

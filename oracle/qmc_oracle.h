@@ -95,6 +95,13 @@ int64_t qo_energy(const qo_potential_t *pot, int32_t n, const double *pos, const
 
 /* n_attempts cycles of MonteCarlo.step (mc/core.py:353-384) with every move in moves[] available.
  * Returns 0, or a negative error code (-2 unsupported label groups, -3 capacity, -4 exp overflow). */
+/* One ForceBias step (mc/fbmc.py:202-241) of one replica: forces -> gamma -> zeta by rejection -> positions += zeta delta.
+ * Draws: element p of call c of step `step` = Philox(seed; step, replica, ((c + 1) << 16) | (p >> 1)), half p & 1.
+ * pos [n][3] in/out; returns the energy after the move in *energy and max |gamma| in *gamma_max; iterations in *n_iter. */
+int qo_fbmc_step(const qo_potential_t *pot, int32_t n, double *pos, const double *cell, const int32_t *pbc, double mass,
+                 double temperature, double delta, uint64_t seed, uint32_t replica, uint64_t step, double *energy,
+                 double *gamma_max, int32_t *n_iter);
+
 int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32_t n_moves, uint64_t seed,
               uint32_t replica, uint64_t attempt_base, int32_t n_attempts, qo_trace_t *trace,
               int64_t counters[4]);

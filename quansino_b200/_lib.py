@@ -25,7 +25,7 @@ STATUS_EXP_OVERFLOW, STATUS_CAPACITY, STATUS_CELL_TOO_SMALL, STATUS_LIST_OVERFLO
 EXPORTS = (
     "qmc_abi_version", "qmc_last_error", "qmc_device_count", "qmc_sweep_smem_per_replica", "qmc_energy_full",
     "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_hmc_workspace_bytes", "qmc_pt_swap", "qmc_fp64_peak",
-    "qmc_sweep_host", "qmc_debug_math",
+    "qmc_sweep_host", "qmc_debug_math", "qmc_fbmc_step",
 )  # fmt: skip
 
 
@@ -135,6 +135,8 @@ def load() -> C.CDLL:
     L.qmc_pt_swap.argtypes = [vp, vp, i32, u64, u64, vp, vp]
     L.qmc_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
     L.qmc_sweep_host.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), i32, u64, u64, i32, C.POINTER(Trace)]
+    L.qmc_fbmc_step.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.c_double, u64, u64, vp, i32, vp, vp, vp, i64, vp]
+    L.qmc_fbmc_step.restype = C.c_int
     L.qmc_debug_math.argtypes = [i32, vp, vp, i32, vp]
     L.qmc_debug_math.restype = C.c_int
     for name in ("qmc_energy_full", "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_pt_swap", "qmc_fp64_peak", "qmc_sweep_host"):

@@ -14,6 +14,7 @@
 
 #include "../../include/quansino_b200.h"
 #include "hmc_kernel.cuh"
+#include "fbmc_kernel.cuh"
 #include "launchers.h"
 
 namespace {
@@ -409,6 +410,31 @@ int qmc_hmc(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move
     if (trace) tr = *trace;
     return qmc::hmc_run(pd, *batch, move->dt, move->n_steps, seed, attempt_base, n_attempts, tr, workspace, (cudaStream_t)stream,
                         g_err, sizeof(g_err));
+}
+
+int qmc_fbmc_step(const qmc_potential_t *pot, const qmc_batch_t *batch, double delta, uint64_t seed, uint64_t step, double *forces,
+                  int32_t forces_valid, double *gamma_max, int32_t *n_calls, void *workspace, int64_t workspace_bytes, void *stream) {
+    if (!pot || !forces) return fail(QMC_ERR_INVALID, "potential / forces is NULL");
+    int rc;
+    if ((rc = check_batch(batch, pot->kind))) return rc;
+    if (!(delta > 0.0)) return fail(QMC_ERR_INVALID, "delta must be positive");
+    if (batch->n_replicas == 0) return QMC_OK;
+    qmc::PotDev pd;
+    if ((rc = make_potdev(pot, pd))) return rc;
+    if (!workspace || workspace_bytes < qmc::hmc_workspace_bytes(pd, *batch)) return fail(QMC_ERR_INVALID, "workspace too small");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!forces_valid && (rc = qmc::hmc_forces(pd, *batch, forces, workspace, s, g_err, sizeof(g_err)))) return rc;
+    qmc::FbmcArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.b = *batch;
+    a.forces = forces;
+    a.delta = delta;
+    a.seed = seed;
+    a.step = step;
+    a.gamma_max = gamma_max;
+    a.n_calls = n_calls;
+    if ((rc = qmc::fbmc_launch(a, s, g_err, sizeof(g_err)))) return rc;
+    return qmc::hmc_forces(pd, *batch, forces, workspace, s, g_err, sizeof(g_err));  // energy + forces at the new positions
 }
 
 int qmc_pt_swap(double *temperatures_all, const double *energies_all, int32_t n_global, uint64_t seed, uint64_t round,

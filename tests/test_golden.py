@@ -37,3 +37,17 @@ def test_golden_cases_exercise_every_branch():
     assert (d == 1).sum() > 5 and (d == -1).sum() > 5 and (g["accepted"] == -1).sum() > 0
     g = load("isobaric_pcell")
     assert ((g["move"] == 1) & (g["accepted"] == 1)).sum() > 0 and ((g["move"] == 1) & (g["accepted"] == 0)).sum() > 0
+
+
+def test_oracle_reproduces_genuine_force_bias():
+    """ForceBias.step (mc/fbmc.py:202-251) run by the genuine sources: same positions bit for bit, same energies."""
+    from oracle import capi
+    from oracle.potentials import emt_params
+
+    g = load("force_bias")
+    pos = g["positions0"].copy()
+    par = emt_params("Cu")
+    for s in range(len(g["energy"])):
+        e, gmax, calls = capi.fbmc_step(par, pos, g["cell"], (1, 1, 1), 63.546, g["temperature"], g["delta"], int(g["seed"]), int(g["replica"]), s)
+        assert np.array_equal(pos, g["trajectory"][s])
+        assert abs(e - g["energy"][s]) <= 1e-11 * abs(g["energy"][s]) and abs(gmax - g["gamma_max"][s]) <= 1e-12 and calls >= 5

@@ -28,3 +28,41 @@ def test_cuda_reproduces_genuine_quansino(cuda_lib, name):
         assert np.array_equal(mc.labels("default_exchange_move")[0, :n], g["labels_exchange"])
     if g["kind"] == "hmc":
         np.testing.assert_allclose(out.momenta[0], g["momenta"], rtol=0, atol=1e-9)
+
+
+def test_cuda_reproduces_genuine_force_bias(cuda_lib):
+    """ForceBias over the batch API against the trajectory of the genuine sources, and 6 more replicas against the oracle."""
+    from oracle import capi
+    from oracle.potentials import emt_params
+    from quansino_b200 import EMT, BatchedAtoms
+    from quansino_b200.mc import ForceBias
+    from tests.helpers import cu_replicas
+
+    g = load("force_bias")
+    steps, n = len(g["energy"]), len(g["positions0"])
+    atoms = BatchedAtoms(g["positions0"][None].copy(), g["cell"], np.array([n], np.int32), "Cu", (True,) * 3, EMT())
+    fb = ForceBias(atoms, delta=g["delta"], temperature=g["temperature"], seed=int(g["seed"]), replica_offset=int(g["replica"]))
+    for s in range(steps):
+        fb.run(1)
+        np.testing.assert_allclose(fb.download().positions[0], g["trajectory"][s], rtol=0, atol=1e-12)
+        assert abs(fb.context.last_potential_energy[0] - g["energy"][s]) <= 1e-10 * abs(g["energy"][s])
+        assert abs(fb.gamma[0] - g["gamma_max"][s]) <= 1e-9 * g["gamma_max"][s]
+    assert fb.step_count == steps and np.all(fb.rejection_rounds >= 5)
+    with pytest.raises(NotImplementedError):
+        fb.add_move(None)
+    # a batch at several temperatures, several steps, against the oracle replica by replica
+    R, steps = 6, 3
+    pos, cell, n = cu_replicas(3, R, seed=91)
+    temps = np.linspace(200.0, 1500.0, R)
+    fb = ForceBias(BatchedAtoms(pos.copy(), cell, np.full(R, n, np.int32), "Cu", (True,) * 3, EMT()), delta=0.08, temperature=temps, seed=77)
+    fb.run(steps)
+    out, e_gpu, par = fb.download(), fb.context.last_potential_energy, emt_params("Cu")
+    for r in range(R):
+        p = pos[r].copy()
+        for s in range(steps):
+            e, _, _ = capi.fbmc_step(par, p, cell, (1, 1, 1), 63.546, float(temps[r]), 0.08, 77, r, s)
+        np.testing.assert_allclose(out.positions[r], p, rtol=0, atol=1e-11)
+        assert abs(e_gpu[r] - e) <= 1e-10 * abs(e)
+    f = fb.forces  # the forces left by the last step are the forces at the final positions
+    ref = capi.energy(par, out.positions[0], cell, (1, 1, 1), want_forces=True)
+    np.testing.assert_allclose(f[0], ref["forces"], rtol=1e-9, atol=1e-10)
