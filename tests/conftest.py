@@ -10,6 +10,13 @@ if str(ROOT) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+    # a fresh checkout has no built library (it is git-ignored): build it once, like `__graft_entry__.build()` does
+    from quansino_b200 import _lib
+
+    if not _lib.LIB_PATH.exists():
+        from quansino_b200.build import build
+
+        build()
 
 
 @pytest.fixture(scope="session")
