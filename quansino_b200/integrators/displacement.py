@@ -20,6 +20,10 @@ class BaseIntegrator:
     def to_dict(self) -> dict[str, Any]:
         return {"name": self.__class__.__name__}
 
+    @classmethod
+    def from_dict(cls, data: dict[str, Any]):
+        return cls(**data.get("kwargs", {}))
+
 
 class Verlet(BaseIntegrator):
     """Velocity Verlet, ``dt`` in femtoseconds, ``max_steps`` force evaluations per trajectory."""

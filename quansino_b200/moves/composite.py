@@ -130,6 +130,17 @@ class CompositeMove:
     def to_dict(self) -> dict[str, Any]:
         return {"name": self.__class__.__name__, "kwargs": {"moves": [move.to_dict() for move in self.moves]}}
 
+    @classmethod
+    def from_dict(cls, data: dict[str, Any]):
+        """``moves/composite.py:218-247``."""
+        from quansino_b200.registry import get_class
+
+        moves = [get_class(m["name"]).from_dict(m) for m in data.get("kwargs", {}).get("moves", [])]
+        instance = cls(moves)
+        for key, value in data.get("attributes", {}).items():
+            setattr(instance, key, value)
+        return instance
+
 
 class CompositeDisplacementMove(CompositeMove):
     """Mirror of ``quansino.moves.displacement.CompositeDisplacementMove``.

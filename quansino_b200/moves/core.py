@@ -57,6 +57,22 @@ class BaseMove:
             "attributes": {"max_attempts": self.max_attempts},
         }
 
+    @classmethod
+    def from_dict(cls, data: dict[str, Any]):
+        """``moves/core.py:151-183``: rebuild the operation through the registry, then the move, then its attributes."""
+        from copy import deepcopy
+
+        from quansino_b200.registry import get_class
+
+        kwargs = deepcopy(data.get("kwargs", {}))
+        if "operation" in kwargs:
+            op = kwargs["operation"]
+            kwargs["operation"] = get_class(op["name"]).from_dict(op)
+        instance = cls(**kwargs)
+        for key, value in data.get("attributes", {}).items():
+            setattr(instance, key, value)
+        return instance
+
     # move algebra (moves/core.py:185-243): `a + b` and `a * k` build composite moves
     @property
     def composite_move_type(self):

@@ -115,6 +115,11 @@ class HamiltonianDisplacementMove(BaseMove):
     def default_operation(self):
         return Verlet()
 
+    def to_dict(self) -> dict[str, Any]:
+        d = super().to_dict()
+        d["kwargs"].pop("apply_constraints", None)  # not a constructor argument of this move (moves/displacement.py:295-305)
+        return d
+
     def lower(self) -> _lib.Move:
         self._check_supported()
         if self.distribution is not maxwell_boltzmann_distribution:

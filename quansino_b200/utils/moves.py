@@ -27,3 +27,13 @@ class MoveStorage:
                 "minimum_count": self.minimum_count,
             },
         }
+
+    @classmethod
+    def from_dict(cls, data: dict[str, Any]):
+        """``utils/moves.py:62-102``: move and criteria are rebuilt through the registry."""
+        from quansino_b200.registry import get_class
+
+        kw = dict(data.get("kwargs", {}))
+        kw["move"] = get_class(kw["move"]["name"]).from_dict(kw["move"])
+        kw["criteria"] = get_class(kw["criteria"]["name"]).from_dict(kw["criteria"])
+        return cls(**kw)

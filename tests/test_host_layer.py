@@ -215,3 +215,54 @@ def test_shard_is_a_partition():
         assert blocks[0][0] == 0 and sum(c for _, c in blocks) == n
         assert all(blocks[r][0] + blocks[r][1] == blocks[r + 1][0] for r in range(w - 1))
         assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
+
+
+def test_to_dict_from_dict_round_trips_through_the_registry():
+    """``to_dict`` / ``from_dict`` with the class registry (src/quansino/registry.py, moves/core.py:151-183,
+    moves/composite.py:218-247, utils/moves.py:62-102): the rebuilt objects lower to the same POD."""
+    import json
+
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.io.restart import _Encoder, _decode
+    from quansino_b200.mc.criteria import CanonicalCriteria, IsobaricCriteria
+    from quansino_b200.moves import CellMove, DisplacementMove, ExchangeMove, HamiltonianDisplacementMove
+    from quansino_b200.operations import Ball, Box, IsotropicDeformation, Rotation, Sphere
+    from quansino_b200.registry import get_class, get_typed_class, register_class
+    from quansino_b200.utils.moves import MoveStorage
+
+    def pod(m):
+        return tuple(getattr(m, f) for f, _ in m._fields_ if f != "labels")
+
+    def through_json(d):
+        return _decode(json.loads(json.dumps(d, cls=_Encoder)))
+
+    lab = np.array([0, 1, -1, 2, 3])
+    moves = [
+        DisplacementMove(lab, Box(0.25)), DisplacementMove(lab, Sphere(0.05)), DisplacementMove(np.array([5, 5, 7, 7, -1]), Rotation()),
+        CellMove(IsotropicDeformation(0.02, mask=np.diag([True, False, True]))), ExchangeMove(lab, bias_towards_insert=0.3),
+        HamiltonianDisplacementMove(operation=Verlet(dt=2.0, max_steps=7)),
+    ]  # fmt: skip
+    for mv in moves:
+        again = get_class(mv.to_dict()["name"]).from_dict(through_json(mv.to_dict()))
+        assert type(again) is type(mv) and pod(again.lower()) == pod(mv.lower())
+        if hasattr(mv, "labels"):
+            assert np.array_equal(again.labels, mv.labels)
+    combo = DisplacementMove(lab, Ball(0.1)) * 2 + DisplacementMove(lab, Box(0.2))
+    again = get_class("CompositeDisplacementMove").from_dict(through_json(combo.to_dict()))
+    assert [pod(m) for m in again.lower_chain()] == [pod(m) for m in combo.lower_chain()]
+    hybrid = DisplacementMove(lab, Ball(0.1)) * 3 + CellMove()
+    again = get_class("CompositeMove").from_dict(through_json(hybrid.to_dict()))
+    assert [pod(m) for m in again.lower_chain()] == [pod(m) for m in hybrid.lower_chain()]
+    st = MoveStorage(move=moves[3], criteria=IsobaricCriteria(), interval=2, probability=0.25, minimum_count=1)
+    again = MoveStorage.from_dict(through_json(st.to_dict()))
+    assert (again.interval, again.probability, again.minimum_count) == (2, 0.25, 1) and type(again.criteria) is IsobaricCriteria
+    assert pod(again.move.lower()) == pod(moves[3].lower())
+    assert get_typed_class("CanonicalCriteria", type(CanonicalCriteria()).__mro__[1]) is CanonicalCriteria
+    with pytest.raises(KeyError):
+        get_class("NoSuchMove")
+
+    class MyBall(Ball):
+        pass
+
+    register_class(MyBall)
+    assert get_class("MyBall") is MyBall
