@@ -3,7 +3,7 @@
 
 from quansino_b200.io.core import Observer, TextObserver
 from quansino_b200.io.logger import Logger
-from quansino_b200.io.restart import RestartObserver, read_restart
+from quansino_b200.io.restart import RestartObserver, read_restart, restore_simulation
 from quansino_b200.io.trajectory import TrajectoryObserver, read_extxyz, write_extxyz
 
-__all__ = ["Logger", "Observer", "RestartObserver", "TextObserver", "TrajectoryObserver", "read_extxyz", "read_restart", "write_extxyz"]
+__all__ = ["Logger", "Observer", "RestartObserver", "TextObserver", "TrajectoryObserver", "read_extxyz", "read_restart", "restore_simulation", "write_extxyz"]

@@ -74,3 +74,47 @@ class RestartObserver(TextObserver):
         self._file.truncate()
         write_json(self._file, obj=self.simulation, **self.write_kwargs)
         self._file.flush()
+
+
+def restore_simulation(data: dict[str, Any] | IO | str | Path, calc, device="cuda", **overrides: Any):
+    """Rebuild a simulation from a restart dictionary / file: the driver class, its moves and criteria come back through the
+    class registry (``quansino_b200.registry``), the batch from the stored state, and the run continues bit-identically.
+    ``calc`` is the potential description (``quansino_b200.calculators``); it is not stored in the file, like the ASE
+    calculator of the reference."""
+    import numpy as np
+
+    from quansino_b200.batch import BatchedAtoms
+    from quansino_b200.registry import get_class
+    from quansino_b200.utils.moves import MoveStorage
+
+    if not isinstance(data, dict):
+        data = read_restart(data)
+    cls = get_class(data["name"])
+    st, ctx, kw0 = data["state"], data.get("context", {}), data.get("kwargs", {})
+    atoms = BatchedAtoms(np.array(st["positions"]), np.array(st["cell"]), np.array(st["n_atoms"], dtype=np.int32), st["symbol"],
+                         tuple(bool(b) for b in st["pbc"]), calc, momenta=np.array(st["momenta"]) if "momenta" in st else None)  # fmt: skip
+    kw: dict[str, Any] = {"seed": int(kw0["seed"]), "device": device, "replica_offset": int(st.get("replica_offset", 0))}
+    names = {c.__name__ for c in cls.__mro__}
+    if "ForceBias" in names:
+        kw["delta"] = float(kw0["delta"])
+    else:
+        kw["max_cycles"] = int(kw0["max_cycles"])
+    if "Canonical" in names or "ForceBias" in names:
+        kw["temperature"] = np.array(st["temperature"])
+    if "Isobaric" in names:
+        kw["pressure"] = float(ctx["pressure"])
+    if "GrandCanonical" in names:
+        kw["chemical_potential"] = float(ctx["chemical_potential"])
+        kw["number_of_exchange_particles"] = np.array(st["n_exchange"])
+        ex = ctx.get("exchange_atoms")
+        if ex is not None:
+            kw["exchange_atoms"] = (ex[0], tuple(ex[1])) if isinstance(ex, (list, tuple)) else ex
+    kw.update(overrides)
+    sim = cls(atoms, **kw)
+    if "GrandCanonical" in names and "accessible_volume" in ctx:
+        sim.accessible_volume = float(ctx["accessible_volume"])
+    for name, stored in data.get("moves", {}).items():
+        ms = MoveStorage.from_dict(stored)
+        sim.add_move(ms.move, criteria=ms.criteria, name=name, interval=ms.interval, probability=ms.probability, minimum_count=ms.minimum_count)
+    sim.load_state(data)
+    return sim

@@ -126,6 +126,13 @@ def test_restart_continues_bit_identically(cuda_lib, tmp_path):
     second = _canonical()
     second.load_state(data)
     assert second.step_count == 2
+    from quansino_b200 import EMT
+    from quansino_b200.io import restore_simulation
+
+    third = restore_simulation(tmp_path / "restart.json", EMT(), resync_interval=3)  # class, moves and criteria from the registry
+    assert type(third).__name__ == "Canonical" and list(third.moves) == ["default_displacement_move"] and third.step_count == 2
+    third.run(3)
+    assert np.array_equal(third.download().positions, ref_pos) and np.array_equal(third.batch.energy.cpu().numpy(), ref_e)
     second.run(3)
     assert second.step_count == 5
     assert np.array_equal(second.download().positions, ref_pos)
@@ -193,6 +200,12 @@ def test_grand_canonical_restart_keeps_integer_state(cuda_lib, tmp_path):
     second.validate_simulation()  # creates nothing that load_state does not overwrite
     second.load_state(data)
     second.run(2)
+    from quansino_b200.io import restore_simulation
+
+    third = restore_simulation(data, LennardJones(sigma=2.5, epsilon=0.1), resync_interval=0)
+    third.run(2)
+    assert np.array_equal(third.download().positions, second.download().positions)
+    assert np.array_equal(third.labels("default_exchange_move"), second.labels("default_exchange_move"))
     a, b = straight.download(), second.download()
     assert np.array_equal(a.n_atoms, b.n_atoms) and np.array_equal(a.positions, b.positions)
     assert np.array_equal(straight.number_of_exchange_particles, second.number_of_exchange_particles)
