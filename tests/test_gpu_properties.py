@@ -1,5 +1,6 @@
-"""Force-bias Monte Carlo beyond the golden trajectory: the statistical property the reference tests
-(tests/mc/test_fbmc.py:12-26: mean |displacement| = delta / 3 at weak bias), the driver plumbing, restart."""
+"""Statistical and conservation properties the reference's own tests assert, on the CUDA path: force-bias mean displacement
+(tests/mc/test_fbmc.py:12-26), Maxwell-Boltzmann temperature (tests/utils/test_dynamics.py:23-32), Verlet energy
+conservation (tests/integrators/test_verlet_integrator.py:22-31); plus the ForceBias driver plumbing and restart."""
 
 import numpy as np
 import pytest
@@ -56,3 +57,26 @@ def test_force_bias_restart_and_dictionary(cuda_lib, tmp_path):
     second.run(3)
     assert np.array_equal(second.download().positions, straight.download().positions)
     np.testing.assert_allclose(second.context.last_potential_energy, straight.context.last_potential_energy, rtol=1e-13)
+
+
+def test_hamiltonian_known_properties(cuda_lib):
+    """The reference's property tests for the Hamiltonian path: Maxwell-Boltzmann momenta give <T> = 300 K
+    (tests/utils/test_dynamics.py:23-32) and Verlet with dt = 0.01 fs x 20 conserves the total energy to four decimals
+    (tests/integrators/test_verlet_integrator.py:22-31)."""
+    from quansino_b200 import EMT, BatchedAtoms
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.mc import HamiltonianCanonical
+    from quansino_b200.moves import HamiltonianDisplacementMove
+    from tests.helpers import cu_replicas
+
+    R = 256
+    pos, cell, n = cu_replicas(3, R, seed=5, stdev=0.03)
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    mc = HamiltonianCanonical(atoms, temperature=300.0, max_cycles=1, seed=8, trace=True, resync_interval=0,
+                              default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=0.01, max_steps=20)))  # fmt: skip
+    mc.run(1)
+    kB = 8.617330337217213e-05
+    t_kin = 2.0 * mc.context.last_kinetic_energy / (3 * n * kB)  # after a (practically always accepted) trajectory
+    assert abs(t_kin.mean() - 300.0) < 1.5 and abs(t_kin.std() - 300.0 * np.sqrt(2.0 / (3 * n))) < 3.0
+    assert np.max(np.abs(mc.last_trace["delta"])) < 1e-4  # H is conserved along the 0.2 fs trajectory
+    assert mc.last_trace["accepted"].mean() > 0.99
