@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define QMC_ABI_VERSION 5
+#define QMC_ABI_VERSION 6
 #define QMC_MAX_FORCED 16 /* sum of minimum_count over the move table */
 #define QMC_MAX_MOVES 4
 
@@ -109,7 +109,10 @@ typedef struct qmc_move {
                               operations/cell.py:167-169); 0 reads as all three axes */
     int32_t minimum_count; /* MoveStorage.minimum_count: forced occurrences of this move per step (mc/core.py:331-342) */
     int32_t max_cycles;    /* cycles per step; read from entry 0, needed only if some minimum_count > 0 */
-    int32_t _pad;
+    int32_t n_extra_ops;   /* CompositeOperation (operations/composite.py:22-109): 0..2 further displacement operations whose */
+    int32_t extra_op[2];   /* translations are ADDED to the first one's (np.sum in list order), each drawing in turn: their */
+    int32_t _pad;          /* draws are the attempt's "extra" draws e = 0, 1, ... = Philox block 64 + e / 2, half e & 1 */
+    double extra_step[2];
     int32_t *labels;       /* device [n_replicas][n_max]; NULL = arange(n_atoms) and no exchange moves */
 } qmc_move_t;
 

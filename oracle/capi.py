@@ -45,7 +45,10 @@ class Move(C.Structure):
         ("axes", C.c_int32),
         ("minimum_count", C.c_int32),
         ("max_cycles", C.c_int32),
+        ("n_extra_ops", C.c_int32),
+        ("extra_op", C.c_int32 * 2),
         ("_pad", C.c_int32),
+        ("extra_step", C.c_double * 2),
         ("labels", C.POINTER(C.c_int32)),
     ]
 
@@ -181,6 +184,7 @@ class MoveSpec:
     axes: int = 0  # CellMove: deformed axes (bit mask), 0 = all
     minimum_count: int = 0  # forced occurrences per step
     max_cycles: int = 0  # cycles per step (needed with forced moves)
+    extra_ops: tuple = ()  # CompositeOperation: up to two further (op, step) pairs
 
 
 @dataclass
@@ -237,6 +241,9 @@ def mc_run(par, rep: Replica, moves: list[MoveSpec], seed: int, replica_id: int,
         mv[i].bias_insert, mv[i].dt, mv[i].n_steps, mv[i].default_label = m.bias_insert, m.dt, m.n_steps, m.default_label
         mv[i].repeat, mv[i].chain, mv[i].axes = m.repeat, m.chain, m.axes
         mv[i].minimum_count, mv[i].max_cycles = m.minimum_count, m.max_cycles
+        mv[i].n_extra_ops = len(m.extra_ops)
+        for q, (op, step) in enumerate(m.extra_ops):
+            mv[i].extra_op[q], mv[i].extra_step[q] = op, step
         if m.labels is not None:
             assert m.labels.dtype == np.int32 and len(m.labels) >= n_max and m.labels.flags.c_contiguous
             mv[i].labels = m.labels.ctypes.data_as(C.POINTER(C.c_int32))

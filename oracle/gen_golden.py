@@ -198,6 +198,20 @@ def case_fbmc(seed, steps, delta, temperature):
                 accepted=np.ones(steps, np.int8), move=np.zeros(steps, np.int8), n_atoms=np.full(steps, len(atoms), np.int32))  # fmt: skip
 
 
+def case_composite_operation(seed, n_attempts):
+    """CompositeOperation (operations/composite.py:22-109): `Ball(0.06) + Box(0.03) + Sphere(0.02)` and `Box(0.04) * 2` built with
+    the reference's own operator algebra; the displacement is the sum of the parts."""
+    atoms, pos0, cell = cu_atoms(3, 0.05, 2323)
+    n = len(atoms)
+    mc = Canonical(atoms, temperature=400.0, max_cycles=n_attempts,
+                   default_displacement_move=DisplacementMove(np.arange(n), Ball(0.06) + Box(0.03) + Sphere(0.02)))  # fmt: skip
+    mc.add_move(DisplacementMove(np.arange(n), Box(0.04) * 2), name="double_box", probability=1.0)
+    inject(mc, seed, 11)
+    tr = run_steps(mc, 1)
+    return dict(kind="composite_operation", seed=seed, replica=11, temperature=400.0, positions0=pos0, cell=cell,
+                positions=atoms.positions.copy(), **tr)  # fmt: skip
+
+
 def case_hybrid(seed, n_attempts, k):
     """The docs' hybrid NPT move (examples/orb-v3_isobaric_bulk_cu.py:45-48): `DisplacementMove * k + CellMove` is a plain
     CompositeMove -- k independent displacements (labels may repeat), one cell deformation, ONE IsobaricCriteria test -- next
@@ -346,6 +360,7 @@ def main():
         "forced_moves": lambda: case_forced(7001, 3),
         "group_rotation": lambda: case_rotation(8001, 100),
         "force_bias": lambda: case_fbmc(9001, 4, 0.1, 600.0),
+        "composite_operation": lambda: case_composite_operation(9501, 90),
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():

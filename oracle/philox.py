@@ -23,9 +23,10 @@ Layout (DESIGN.md section "Random stream"):
     block 4 + j / 2 (of the FIRST attempt of a step): forced-move placement draw j (``mc/core.py:335-337``)
     block 32 + 2 (c - 1), 33 + 2 (c - 1): sub-move c >= 1 of a CompositeDisplacementMove (``moves/displacement.py:392-431``;
              c counts the sub-moves that draw, the first one uses the standard slots above):
-             (u_label, operation draw 0) and (operation draw 1, operation draw 2); the CellMove closing a hybrid
-             ``CompositeMove`` (``DisplacementMove * N + CellMove``) draws block 3's second double if a displacement drew
-             before it, operation draw 0 otherwise
+             (u_label, operation draw 0) and (operation draw 1, operation draw 2); operation draws beyond the third of a
+             (sub-)move -- the further operations of a ``CompositeOperation`` (``Ball(0.1) + Box(0.05)``), the CellMove
+             closing a hybrid ``CompositeMove`` after displacements drew -- are numbered e = 0, 1, ... through the attempt
+             and live in block 64 + e / 2, half e & 1
     block 16 + p: Box-Muller pair p of the 3N momentum normals (``utils/dynamics.py:31``), row-major:
              normal m = 3*atom + axis lives in pair p = m // 2; z_even = r cos(t), z_odd = r sin(t),
              r = sqrt(-2 ln(1 - d0)), t = 2 pi d1.
@@ -47,6 +48,7 @@ BLOCK_COIN_SWAP = 3
 BLOCK_FORCED = 4
 BLOCK_NORMALS = 16
 BLOCK_COMPOSITE = 32
+BLOCK_EXTRA = 64
 
 _MASK = 0xFFFFFFFF
 
@@ -123,6 +125,7 @@ class InjectedStream:
         self._op_draws = 0
         self._calls = 0
         self._labels = 0  # label draws of this attempt
+        self._extra = 0  # operation draws of this attempt beyond the third of a (sub-)move
         self._select_pending = False  # a selection draw opened the attempt that the next mark_cycle() belongs to
         self.log: list[tuple[str, float]] = []
 
@@ -135,13 +138,16 @@ class InjectedStream:
         self._op_draws = 0
         self._calls = 0
         self._labels = 0
+        self._extra = 0
 
     def _op_draw(self) -> float:
         k = self._op_draws
         self._op_draws += 1
         self._calls += 1
-        if k == 3 and self._labels >= 1:  # a fourth draw after a label: the CellMove that closes a hybrid CompositeMove
-            return self._pair(BLOCK_COIN_SWAP)[1]
+        if k >= 3:  # beyond the three operation draws of a (sub-)move: the further operations of a CompositeOperation
+            e = self._extra  # (operations/composite.py:58-73) and the CellMove that closes a hybrid CompositeMove
+            self._extra += 1
+            return self._pair(BLOCK_EXTRA + e // 2)[e & 1]
         if self._labels > 1:  # sub-move c = _labels - 1 >= 1 of a composite displacement move
             c = self._labels - 1
             if k == 0:

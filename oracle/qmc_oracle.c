@@ -549,7 +549,7 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
         int accepted = -1, moved = -1;
         double delta = NAN;
 
-        if (mv->type == QO_MOVE_DISPLACEMENT && (mv->repeat > 1 || mv->chain)) {
+        if (mv->type == QO_MOVE_DISPLACEMENT && (mv->repeat > 1 || (mv->chain & 3))) {
             /* Composite moves.  chain bit 0: the next entry belongs to the same move; chain bit 1: plain CompositeMove
              * (moves/composite.py:43-62: every sub-move is called on its own, labels may repeat) instead of
              * CompositeDisplacementMove (moves/displacement.py:392-431: every sub-move picks a label nobody displaced yet
@@ -558,7 +558,7 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
              * Then ONE criteria evaluation on the whole change (mc/core.py:369-377).
              * Draws: the first drawing sub-move uses the standard slots, drawing sub-move c >= 1 uses
              * block 32 + 2 (c - 1) = (u_label, op draw 0) and block 33 + 2 (c - 1) = (op draw 1, op draw 2); the cell draw
-             * is op draw 0 if no displacement drew, else the second double of block 3. */
+             * is op draw 0 if no displacement drew, else the first "extra" draw of the attempt (block 64, first double). */
             memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
             const int exclusive = !(mv->chain & 2);
             int n_moved = 0, c = 0, did_cell = 0; /* disp[]: label VALUES displaced so far (the reference compares labels, not atoms) */
@@ -569,7 +569,9 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                 qo_move_t *sm = &moves[mm];
                 if (sm->type == QO_MOVE_CELL) {
                     if (exclusive || (sm->chain & 1)) { free(disp); rc = -1; goto done; } /* last entry of a plain chain only */
-                    const double u_cell = c == 0 ? opd[0] : b3[1];
+                    double bx[2];
+                    qo_uniform_pair(seed, attempt, replica, 64, bx);
+                    const double u_cell = c == 0 ? opd[0] : bx[0]; /* first extra draw of the attempt */
                     double sc = exp(-sm->step + (sm->step - -sm->step) * u_cell);
                     for (int q = 0; q < 9; ++q) /* F = eye * s * mask + eye * ~mask, F @ cell: row r scaled by F[r][r] */
                         new_cell[q] = ((sm->axes == 0 || ((sm->axes >> (q / 3)) & 1)) ? sc : 1.0) * st->cell[q];
@@ -670,6 +672,30 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                 } else if (mv->op == QO_OP_ROTATION) {
                     t[0] = t[1] = t[2] = 0.0; /* per-atom displacements below */
                 } else { rc = -1; goto done; }
+                /* CompositeOperation (operations/composite.py:58-73): np.sum of the operations' displacements, each drawing
+                 * in turn.  Their draws are the attempt's extra draws e = 0, 1, ... (block 64 + e / 2, half e & 1). */
+                for (int xo = 0, e = 0; xo < mv->n_extra_ops; ++xo) {
+                    struct { int op; double step; } one = {mv->extra_op[xo], mv->extra_step[xo]}, *om = &one;
+                    double od[3], t2[3];
+                    const int nd = om->op == QO_OP_SPHERE ? 2 : 3;
+                    for (int q = 0; q < nd; ++q, ++e) {
+                        double bx[2];
+                        qo_uniform_pair(seed, attempt, replica, (uint32_t)(64 + e / 2), bx);
+                        od[q] = bx[e & 1];
+                    }
+                    if (om->op == QO_OP_BALL) {
+                        double r = 0.0 + (om->step - 0.0) * od[0], phi = 0.0 + (TWO_PI - 0.0) * od[1], cc = -1.0 + (1.0 - -1.0) * od[2];
+                        double sq = sqrt(1 - cc * cc);
+                        t2[0] = r * sq * cos(phi); t2[1] = r * sq * sin(phi); t2[2] = r * cc;
+                    } else if (om->op == QO_OP_SPHERE) {
+                        double phi = 0.0 + (TWO_PI - 0.0) * od[0], cc = -1.0 + (1.0 - -1.0) * od[1];
+                        double sq = sqrt(1 - cc * cc);
+                        t2[0] = om->step * (sq * cos(phi)); t2[1] = om->step * (sq * sin(phi)); t2[2] = om->step * cc;
+                    } else if (om->op == QO_OP_BOX) {
+                        for (int x = 0; x < 3; ++x) t2[x] = -om->step + (om->step - -om->step) * od[x];
+                    } else { rc = -1; goto done; }
+                    for (int x = 0; x < 3; ++x) t[x] = t[x] + t2[x];
+                }
                 memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
                 if (mv->op == QO_OP_ROTATION) {
                     /* Rotation.calculate (operations/displacement.py:192-200): molecule.euler_rotate(phi, theta, psi, center="COM")

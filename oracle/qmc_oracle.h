@@ -45,7 +45,10 @@ typedef struct {
     int32_t axes;          /* CellMove: bit d set = axis d is deformed (diagonal of IsotropicDeformation.mask); 0 = all three */
     int32_t minimum_count; /* MoveStorage.minimum_count (mc/core.py:331-342) */
     int32_t max_cycles;    /* cycles per step (entry 0), needed if some minimum_count > 0 */
+    int32_t n_extra_ops;   /* CompositeOperation: 0..2 further displacement operations, translations added in list order */
+    int32_t extra_op[2];
     int32_t _pad;
+    double extra_step[2];
     int32_t *labels;       /* [n_max] this move's labels, updated in place on accepted exchanges */
 } qo_move_t;
 

@@ -54,7 +54,10 @@ class Move(C.Structure):
         ("axes", C.c_int32),
         ("minimum_count", C.c_int32),
         ("max_cycles", C.c_int32),
+        ("n_extra_ops", C.c_int32),
+        ("extra_op", C.c_int32 * 2),
         ("_pad", C.c_int32),
+        ("extra_step", C.c_double * 2),
         ("labels", C.c_void_p),
     ]
 

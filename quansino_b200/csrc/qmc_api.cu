@@ -298,6 +298,17 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         a.mv[m].repeat = mv.repeat > 0 ? mv.repeat : 1;
         a.mv[m].chain = mv.chain;
         a.mv[m].axes = (mv.axes & 7) ? (mv.axes & 7) : 7;
+        if (mv.n_extra_ops < 0 || mv.n_extra_ops > 2) return fail(QMC_ERR_UNSUPPORTED, "move %d: at most three operations per move on the GPU path", m);
+        if (mv.n_extra_ops > 0 && (mv.type != QMC_MOVE_DISPLACEMENT || mv.chain || mv.repeat > 1 || mv.op == QMC_OP_ROTATION))
+            return fail(QMC_ERR_UNSUPPORTED, "move %d: composite operations belong to plain single-atom displacement moves", m);
+        a.mv[m].n_extra_ops = mv.n_extra_ops;
+        for (int q = 0; q < mv.n_extra_ops; ++q) {
+            if (mv.extra_op[q] != QMC_OP_BALL && mv.extra_op[q] != QMC_OP_BOX && mv.extra_op[q] != QMC_OP_SPHERE)
+                return fail(QMC_ERR_UNSUPPORTED, "move %d: operation %d cannot be part of a composite operation on the GPU path", m, mv.extra_op[q]);
+            a.mv[m].extra_op[q] = mv.extra_op[q];
+            a.mv[m].extra_step[q] = mv.extra_step[q];
+        }
+        any_composite |= mv.n_extra_ops > 0;
         a.mv[m].labels = mv.labels;
     }
     if (!(tot > 0.0)) return fail(QMC_ERR_INVALID, "move probabilities sum to zero");

@@ -27,6 +27,8 @@ struct MoveDev {
     int default_label;
     int repeat, chain;  // composite displacement moves: this entry `repeat` times, then on to the next entry if `chain`
     int axes;           // cell moves: bit d set = axis d is deformed (never 0 here)
+    int n_extra_ops, extra_op[2];  // CompositeOperation: further displacement operations, translations added in list order
+    double extra_step[2];
     int *labels;  // device [R][n_max] or nullptr (= arange, no exchange)
 };
 
@@ -687,7 +689,12 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
             for (int mm = m;; ++mm) {
                 const MoveDev &sm = a.mv[mm];
                 if ((FEAT & F_CELL) && sm.type == QMC_MOVE_CELL) {  // closes a plain chain (validated by the library)
-                    const double u_cell = n_drawn == 0 ? D.o0 : D.u_swap;
+                    double u_cell = D.o0;  // no displacement drew: op draw 0; else the attempt's first extra draw (block 64)
+                    if (n_drawn > 0) {
+                        double d0, d1;
+                        uniform_pair(key, attempt, grep, 64u, d0, d1);
+                        u_cell = d0;
+                    }
                     const double s = exp(__dadd_rn(-sm.step, __dmul_rn(sm.step - -sm.step, u_cell)));
                     double scale[3];
 #pragma unroll
@@ -789,6 +796,22 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                 const int i = (FEAT & F_LABELS) ? select_bit(R.labbits(m), nullptr, LY::LABW, idx) : idx;
                 double t[3];
                 propose_translation(mv.op, mv.step, D.o0, D.o1, D.o2, t);
+                if ((FEAT & F_COMPOSITE) && mv.n_extra_ops > 0) {
+                    // CompositeOperation (operations/composite.py:58-73): np.sum of the operations' displacements; the further
+                    // operations draw the attempt's extra draws e = 0, 1, ... = block 64 + e / 2, half e & 1
+                    for (int xo = 0, e = 0; xo < mv.n_extra_ops; ++xo) {
+                        double d0, d1;
+                        uniform_pair(key, attempt, grep, 64u + (uint32_t)((e + lane) >> 1), d0, d1);
+                        const double mine = ((e + lane) & 1) ? d1 : d0;  // lane j holds extra draw e + j
+                        const double x0 = __shfl_sync(FULL, mine, 0), x1 = __shfl_sync(FULL, mine, 1), x2 = __shfl_sync(FULL, mine, 2);
+                        double t2[3];
+                        propose_translation(mv.extra_op[xo], mv.extra_step[xo], x0, x1, x2, t2);
+                        t[0] = __dadd_rn(t[0], t2[0]);
+                        t[1] = __dadd_rn(t[1], t2[1]);
+                        t[2] = __dadd_rn(t[2], t2[2]);
+                        e += mv.extra_op[xo] == QMC_OP_SPHERE ? 2 : 3;
+                    }
+                }
                 const double po[3] = {R.x(i), R.y(i), R.z(i)};
                 const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
                 const Trial T = local_delta_move<LY>(pot, R, C, lane, lt, R.n, i, po, pn, status);

@@ -191,7 +191,7 @@ class MonteCarlo:
                     st._label_tensor = torch.from_numpy(lab).to(self.batch.device)
                 grouped = bool(getattr(st.move, "_grouped", False) or getattr(getattr(st.move, "moves", [None])[0], "_grouped", False))
                 grouped = grouped or any(c.op == _lib.OP_ROTATION for c in chain)  # rotations live in the label-group path
-                if grouped and (any_exchange or len(chain) > 1 or chain[0].repeat > 1 or m.type != _lib.MOVE_DISPLACEMENT):
+                if grouped and (any_exchange or len(chain) > 1 or chain[0].repeat > 1 or m.type != _lib.MOVE_DISPLACEMENT or m.n_extra_ops):
                     raise NotImplementedError(
                         "label groups (several atoms per label, or labels not increasing with the atom index) cannot be combined "
                         "with exchange moves or composite moves on the GPU path (SURVEY.md section 8f)"

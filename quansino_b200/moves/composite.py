@@ -108,6 +108,8 @@ class CompositeMove:
             if mv is not first and not (np.array_equal(np.asarray(mv.labels), np.asarray(first.labels)) and mv.default_label == first.default_label):
                 raise NotImplementedError("the sub-moves of a composite move must share one label array on the GPU path")
             m = mv.lower()
+            if m.n_extra_ops:
+                raise NotImplementedError("composite operations inside composite moves are not available on the GPU path")
             key = (m.op, m.step)
             if keys and keys[-1] == key:
                 entries[-1].repeat += 1

@@ -88,6 +88,11 @@ class DisplacementMove(BaseMove):
         m = _lib.Move()
         m.type = self.move_type
         m.op, m.step = self.operation.lower()
+        if hasattr(self.operation, "lower_all"):  # CompositeOperation: the further parts ride along in the same entry
+            extra = self.operation.lower_all()[1:]
+            m.n_extra_ops = len(extra)
+            for q, (code, step) in enumerate(extra):
+                m.extra_op[q], m.extra_step[q] = code, step
         if m.op not in (_lib.OP_BALL, _lib.OP_BOX, _lib.OP_SPHERE, _lib.OP_ROTATION):
             raise NotImplementedError(f"{type(self.operation).__name__} is not a displacement operation of the GPU path")
         m.default_label = _lib.LABEL_NONE if self.default_label is None else int(self.default_label)

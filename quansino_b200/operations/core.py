@@ -36,4 +36,19 @@ class BaseOperation:
         return cls(**data.get("kwargs", {}))
 
     def __add__(self, other):
-        raise NotImplementedError("CompositeOperation is not available on the GPU path (SURVEY.md section 8f)")
+        """``operations/core.py:72-93``."""
+        from quansino_b200.operations.composite import CompositeOperation
+
+        if isinstance(other, CompositeOperation):
+            return CompositeOperation([self, *other.operations])
+        return CompositeOperation([self, other])
+
+    def __mul__(self, n: int):
+        """``operations/core.py:95-116``."""
+        from quansino_b200.operations.composite import CompositeOperation
+
+        if not isinstance(n, int) or isinstance(n, bool) or n < 1:
+            raise ValueError("The number of times the move is repeated must be a positive, non-zero integer.")
+        return CompositeOperation([self] * n)
+
+    __rmul__ = __mul__

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in sorted(declared):
         assert getattr(lib, name) is not None, name
-    assert lib.qmc_abi_version() == int(re.search(r"#define\s+QMC_ABI_VERSION\s+(\d+)", header).group(1)) == 5
+    assert lib.qmc_abi_version() == int(re.search(r"#define\s+QMC_ABI_VERSION\s+(\d+)", header).group(1)) == 6
 
 
 def test_struct_layouts_match_the_header():
@@ -231,7 +231,8 @@ def test_to_dict_from_dict_round_trips_through_the_registry():
     from quansino_b200.utils.moves import MoveStorage
 
     def pod(m):
-        return tuple(getattr(m, f) for f, _ in m._fields_ if f != "labels")
+        vals = (getattr(m, f) for f, _ in m._fields_ if f != "labels")
+        return tuple(tuple(v) if hasattr(v, "__len__") else v for v in vals)
 
     def through_json(d):
         return _decode(json.loads(json.dumps(d, cls=_Encoder)))
@@ -260,6 +261,18 @@ def test_to_dict_from_dict_round_trips_through_the_registry():
     assert get_typed_class("CanonicalCriteria", type(CanonicalCriteria()).__mro__[1]) is CanonicalCriteria
     with pytest.raises(KeyError):
         get_class("NoSuchMove")
+
+    ops = Ball(0.1) + Box(0.2) * 2  # operations/core.py:72-116, operations/composite.py
+    assert type(ops).__name__ == "CompositeOperation" and len(ops) == 3 and type(ops[1]) is Box and type(3 * Ball(0.1)).__name__ == "CompositeOperation"
+    mv = DisplacementMove(lab, ops)
+    low = mv.lower()
+    assert (low.op, low.step, low.n_extra_ops, list(low.extra_op), list(low.extra_step)) == (0, 0.1, 2, [1, 1], [0.2, 0.2])
+    again = get_class("DisplacementMove").from_dict(through_json(mv.to_dict()))
+    assert pod(again.lower())[:4] == pod(low)[:4] and list(again.lower().extra_step) == [0.2, 0.2]
+    with pytest.raises(NotImplementedError):
+        DisplacementMove(lab, Ball(0.1) * 4).lower()
+    with pytest.raises(NotImplementedError):
+        DisplacementMove(lab, Ball(0.1) + Rotation()).lower()
 
     class MyBall(Ball):
         pass
