@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define QMC_ABI_VERSION 6
+#define QMC_ABI_VERSION 7
 #define QMC_MAX_FORCED 16 /* sum of minimum_count over the move table */
 #define QMC_MAX_MOVES 4
 
@@ -166,6 +166,40 @@ int qmc_device_count(void);
 
 /* bytes of dynamic shared memory one replica (one warp) of the sweep kernel needs for `n_max` atoms */
 int64_t qmc_sweep_smem_per_replica(const qmc_potential_t *pot, int32_t n_max);
+
+/* ---- device-resident state owned by the library (for hosts without a device allocator of their own) -----------------
+ * What `Context` owns per simulation in the reference (src/quansino/mc/contexts.py:20-96: atoms, last_* snapshots,
+ * calculator caches) for ALL replicas of one GPU.  The handle owns the device arrays of `qmc_batch_t`; `qmc_batch_view`
+ * fills a `qmc_batch_t` with those pointers (the scalar members -- pbc, replica_offset, mass, pressure, ... -- are the
+ * caller's to set) for qmc_energy_full / qmc_sweep / qmc_hmc / ...; hosts that already hold device memory (the Python
+ * package uses torch tensors) skip the handle and fill `qmc_batch_t` themselves. */
+typedef struct qmc_batch_handle qmc_batch_handle_t;
+enum qmc_field {
+    QMC_FIELD_POS = 0,      /* f64 [R][3][n_max] */
+    QMC_FIELD_CELL,         /* f64 [R][9] */
+    QMC_FIELD_N_ATOMS,      /* i32 [R] */
+    QMC_FIELD_ENERGY,       /* f64 [R] */
+    QMC_FIELD_TEMPERATURE,  /* f64 [R] */
+    QMC_FIELD_SIGMA1,       /* f64 [R][n_max] */
+    QMC_FIELD_EATOM,        /* f64 [R][n_max] */
+    QMC_FIELD_MOMENTA,      /* f64 [R][3][n_max] (only with_momenta) */
+    QMC_FIELD_KINETIC,      /* f64 [R]           (only with_momenta) */
+    QMC_FIELD_N_EXCHANGE,   /* i32 [R] */
+    QMC_FIELD_COUNTERS,     /* i64 [R][QMC_MAX_MOVES][3] */
+    QMC_FIELD_STATUS,       /* i32 [R] */
+    QMC_FIELD_PAIR_EVALS,   /* i64 [R] */
+    QMC_FIELD_LABELS0       /* i32 [R][n_max]: label table t is field QMC_FIELD_LABELS0 + t, t < n_label_tables */
+};
+/* all arrays zero-initialised (energy NaN: "not primed") */
+int qmc_batch_create(int32_t n_replicas, int32_t n_max, int32_t with_momenta, int32_t n_label_tables, qmc_batch_handle_t **out);
+int qmc_batch_destroy(qmc_batch_handle_t *handle);
+/* whole-array host <-> device copies; `bytes` must equal the size of the field */
+int qmc_batch_upload(qmc_batch_handle_t *handle, int32_t field, const void *host, int64_t bytes);
+int qmc_batch_download(qmc_batch_handle_t *handle, int32_t field, void *host, int64_t bytes);
+/* n_replicas, n_max and every device pointer of *out; other members are left untouched */
+int qmc_batch_view(qmc_batch_handle_t *handle, qmc_batch_t *out);
+/* device pointer of label table `table` (for qmc_move_t.labels), NULL if out of range */
+int32_t *qmc_batch_labels(qmc_batch_handle_t *handle, int32_t table);
 
 /* validate_simulation (src/quansino/mc/canonical.py:114-122, mc/core.py:221-229): full energy of every
  * replica; fills energy[], sigma1[], eatom[].  `pair_count` (device [R] int64 or NULL) receives the number

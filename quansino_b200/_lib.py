@@ -17,6 +17,8 @@ LABEL_NONE = -(2**31)
 
 POT_EMT, POT_LJ = 0, 1
 MOVE_DISPLACEMENT, MOVE_CELL, MOVE_EXCHANGE, MOVE_HMC = 0, 1, 2, 3
+(FIELD_POS, FIELD_CELL, FIELD_N_ATOMS, FIELD_ENERGY, FIELD_TEMPERATURE, FIELD_SIGMA1, FIELD_EATOM, FIELD_MOMENTA, FIELD_KINETIC,
+ FIELD_N_EXCHANGE, FIELD_COUNTERS, FIELD_STATUS, FIELD_PAIR_EVALS, FIELD_LABELS0) = range(14)
 OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET, OP_ROTATION = 0, 1, 2, 3, 4, 5, 6
 
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
@@ -25,7 +27,8 @@ STATUS_EXP_OVERFLOW, STATUS_CAPACITY, STATUS_CELL_TOO_SMALL, STATUS_LIST_OVERFLO
 EXPORTS = (
     "qmc_abi_version", "qmc_last_error", "qmc_device_count", "qmc_sweep_smem_per_replica", "qmc_energy_full",
     "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_hmc_workspace_bytes", "qmc_pt_swap", "qmc_fp64_peak",
-    "qmc_sweep_host", "qmc_debug_math", "qmc_fbmc_step",
+    "qmc_sweep_host", "qmc_debug_math", "qmc_fbmc_step", "qmc_batch_create", "qmc_batch_destroy", "qmc_batch_upload",
+    "qmc_batch_download", "qmc_batch_view", "qmc_batch_labels",
 )  # fmt: skip
 
 
@@ -140,6 +143,15 @@ def load() -> C.CDLL:
     L.qmc_sweep_host.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), i32, u64, u64, i32, C.POINTER(Trace)]
     L.qmc_fbmc_step.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.c_double, u64, u64, vp, i32, vp, vp, vp, i64, vp]
     L.qmc_fbmc_step.restype = C.c_int
+    L.qmc_batch_create.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
+    L.qmc_batch_destroy.argtypes = [vp]
+    L.qmc_batch_upload.argtypes = [vp, i32, vp, i64]
+    L.qmc_batch_download.argtypes = [vp, i32, vp, i64]
+    L.qmc_batch_view.argtypes = [vp, C.POINTER(Batch)]
+    L.qmc_batch_labels.argtypes = [vp, i32]
+    L.qmc_batch_labels.restype = vp
+    for name in ("qmc_batch_create", "qmc_batch_destroy", "qmc_batch_upload", "qmc_batch_download", "qmc_batch_view"):
+        getattr(L, name).restype = C.c_int
     L.qmc_debug_math.argtypes = [i32, vp, vp, i32, vp]
     L.qmc_debug_math.restype = C.c_int
     for name in ("qmc_energy_full", "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_pt_swap", "qmc_fp64_peak", "qmc_sweep_host"):

@@ -495,6 +495,107 @@ int qmc_debug_math(int32_t which, const double *in, double *out, int32_t n, void
     return QMC_OK;
 }
 
+// ---- library-owned device state -------------------------------------------------------------------------------------
+struct qmc_batch_handle {
+    int32_t R, N, n_tables;
+    bool momenta;
+    std::vector<void *> ptr;       // one per field (QMC_FIELD_*), nullptr if absent
+    std::vector<size_t> bytes;
+};
+
+int qmc_batch_create(int32_t n_replicas, int32_t n_max, int32_t with_momenta, int32_t n_label_tables, qmc_batch_handle_t **out) {
+    if (!out) return fail(QMC_ERR_INVALID, "out is NULL");
+    if (n_replicas <= 0 || n_max <= 0 || n_label_tables < 0 || n_label_tables > QMC_MAX_MOVES)
+        return fail(QMC_ERR_INVALID, "bad batch dimensions");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(QMC_ERR_NO_DEVICE, "no CUDA device: there is no CPU fallback");
+    auto *h = new qmc_batch_handle{n_replicas, n_max, n_label_tables, with_momenta != 0, {}, {}};
+    const size_t R = (size_t)n_replicas, N = (size_t)n_max;
+    const size_t sizes[QMC_FIELD_LABELS0] = {R * 3 * N * 8, R * 9 * 8, R * 4, R * 8, R * 8, R * N * 8, R * N * 8,
+                                             with_momenta ? R * 3 * N * 8 : 0, with_momenta ? R * 8 : 0, R * 4,
+                                             R * QMC_MAX_MOVES * 3 * 8, R * 4, R * 8};
+    for (int f = 0; f < QMC_FIELD_LABELS0 + n_label_tables; ++f) {
+        const size_t b = f < QMC_FIELD_LABELS0 ? sizes[f] : R * N * 4;
+        void *p = nullptr;
+        if (b) {
+            cudaError_t e = cudaMalloc(&p, b);
+            if (e == cudaSuccess) e = cudaMemset(p, f >= QMC_FIELD_LABELS0 ? 0xFF : 0, b);  // label tables start as -1 (not movable)
+            if (e != cudaSuccess) {
+                for (void *q : h->ptr) cudaFree(q);
+                delete h;
+                return fail(QMC_ERR_CUDA, "device allocation of %zu bytes failed: %s", b, cudaGetErrorString(e));
+            }
+        }
+        h->ptr.push_back(p);
+        h->bytes.push_back(b);
+    }
+    {  // energies (and kinetic energies) start as NaN = "not primed", like last_potential_energy in the reference
+        std::vector<double> nan(R, std::nan(""));
+        cudaMemcpy(h->ptr[QMC_FIELD_ENERGY], nan.data(), R * 8, cudaMemcpyHostToDevice);
+        if (with_momenta) cudaMemcpy(h->ptr[QMC_FIELD_KINETIC], nan.data(), R * 8, cudaMemcpyHostToDevice);
+    }
+    *out = h;
+    return QMC_OK;
+}
+
+int qmc_batch_destroy(qmc_batch_handle_t *h) {
+    if (!h) return QMC_OK;
+    for (void *p : h->ptr) cudaFree(p);
+    delete h;
+    return QMC_OK;
+}
+
+static int batch_field(qmc_batch_handle_t *h, int32_t field, int64_t bytes, void **p) {
+    if (!h) return fail(QMC_ERR_INVALID, "handle is NULL");
+    if (field < 0 || field >= (int32_t)h->ptr.size() || !h->ptr[field]) return fail(QMC_ERR_INVALID, "field %d is not part of this batch", field);
+    if (bytes != (int64_t)h->bytes[field]) return fail(QMC_ERR_INVALID, "field %d holds %zu bytes, got %lld", field, h->bytes[field], (long long)bytes);
+    *p = h->ptr[field];
+    return QMC_OK;
+}
+
+int qmc_batch_upload(qmc_batch_handle_t *h, int32_t field, const void *host, int64_t bytes) {
+    void *p;
+    int rc;
+    if (!host) return fail(QMC_ERR_INVALID, "host pointer is NULL");
+    if ((rc = batch_field(h, field, bytes, &p))) return rc;
+    CUDA_TRY(cudaMemcpy(p, host, (size_t)bytes, cudaMemcpyHostToDevice));
+    return QMC_OK;
+}
+
+int qmc_batch_download(qmc_batch_handle_t *h, int32_t field, void *host, int64_t bytes) {
+    void *p;
+    int rc;
+    if (!host) return fail(QMC_ERR_INVALID, "host pointer is NULL");
+    if ((rc = batch_field(h, field, bytes, &p))) return rc;
+    CUDA_TRY(cudaMemcpy(host, p, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return QMC_OK;
+}
+
+int qmc_batch_view(qmc_batch_handle_t *h, qmc_batch_t *out) {
+    if (!h || !out) return fail(QMC_ERR_INVALID, "NULL argument");
+    out->n_replicas = h->R;
+    out->n_max = h->N;
+    out->pos = (double *)h->ptr[QMC_FIELD_POS];
+    out->cell = (double *)h->ptr[QMC_FIELD_CELL];
+    out->n_atoms = (int32_t *)h->ptr[QMC_FIELD_N_ATOMS];
+    out->energy = (double *)h->ptr[QMC_FIELD_ENERGY];
+    out->temperature = (double *)h->ptr[QMC_FIELD_TEMPERATURE];
+    out->sigma1 = (double *)h->ptr[QMC_FIELD_SIGMA1];
+    out->eatom = (double *)h->ptr[QMC_FIELD_EATOM];
+    out->momenta = (double *)h->ptr[QMC_FIELD_MOMENTA];
+    out->kinetic = (double *)h->ptr[QMC_FIELD_KINETIC];
+    out->n_exchange = (int32_t *)h->ptr[QMC_FIELD_N_EXCHANGE];
+    out->counters = (int64_t *)h->ptr[QMC_FIELD_COUNTERS];
+    out->status = (int32_t *)h->ptr[QMC_FIELD_STATUS];
+    out->pair_evals = (int64_t *)h->ptr[QMC_FIELD_PAIR_EVALS];
+    return QMC_OK;
+}
+
+int32_t *qmc_batch_labels(qmc_batch_handle_t *h, int32_t table) {
+    if (!h || table < 0 || table >= h->n_tables) return nullptr;
+    return (int32_t *)h->ptr[QMC_FIELD_LABELS0 + table];
+}
+
 int qmc_sweep_host(const qmc_potential_t *pot, const qmc_batch_t *h, const qmc_move_t *moves_host, int32_t n_moves, uint64_t seed,
                    uint64_t attempt_base, int32_t n_attempts, const qmc_trace_t *trace_host) {
     if (!pot || !h || !moves_host) return fail(QMC_ERR_INVALID, "NULL argument");

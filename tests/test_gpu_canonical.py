@@ -281,3 +281,53 @@ def test_overflow_is_reported_like_the_reference(cuda_lib):
                    default_displacement_move=DisplacementMove(np.arange(2), operations.Ball(0.3)))  # fmt: skip
     with pytest.raises(OverflowError):
         mc.run(1)
+
+
+def test_library_owned_batch_handle(cuda_lib):
+    """The handle API (qmc_batch_create / upload / view / download): a host without a device allocator of its own drives the
+    same kernels and gets the same bits as the torch-backed path."""
+    import ctypes as C
+
+    from quansino_b200 import EMT, _lib, operations
+
+    lib = cuda_lib
+    R, sweeps = 5, 2
+    pos, cell, n = cu_replicas(3, R, seed=71)
+    mc = _driver(pos, cell, n, operations.Ball(0.1), steps_per_launch=sweeps, resync_interval=0)
+    mc.run(sweeps)
+    want_pos, want_e, want_cnt = mc.download().positions, mc.batch.energy.cpu().numpy(), mc.counters()
+
+    h = C.c_void_p()
+    _lib.check(lib.qmc_batch_create(R, n, 0, 0, C.byref(h)))
+    try:
+        def up(field, arr):
+            arr = np.ascontiguousarray(arr)
+            _lib.check(lib.qmc_batch_upload(h, field, arr.ctypes.data, arr.nbytes))
+
+        def down(field, arr):
+            _lib.check(lib.qmc_batch_download(h, field, arr.ctypes.data, arr.nbytes))
+            return arr
+
+        up(_lib.FIELD_POS, pos.transpose(0, 2, 1))
+        up(_lib.FIELD_CELL, np.broadcast_to(cell.reshape(9), (R, 9)))
+        up(_lib.FIELD_N_ATOMS, np.full(R, n, dtype=np.int32))
+        up(_lib.FIELD_TEMPERATURE, np.full(R, 300.0))
+        b = _lib.Batch()
+        _lib.check(lib.qmc_batch_view(h, C.byref(b)))
+        b.pbc = (C.c_int32 * 3)(1, 1, 1)
+        b.mass = 63.546
+        pot = EMT().lower("Cu")
+        e0 = down(_lib.FIELD_ENERGY, np.zeros(R))
+        assert np.all(np.isnan(e0))  # not primed yet
+        _lib.check(lib.qmc_energy_full(C.byref(pot), C.byref(b), None, None))
+        move = mc._lower(["default_displacement_move"])[0]
+        _lib.check(lib.qmc_sweep(C.byref(pot), C.byref(b), move, 1, 1234, 0, sweeps * n, None, None))
+        got_pos = down(_lib.FIELD_POS, np.zeros((R, 3, n))).transpose(0, 2, 1)
+        assert np.array_equal(got_pos, want_pos)
+        assert np.array_equal(down(_lib.FIELD_ENERGY, np.zeros(R)), want_e)
+        assert np.array_equal(down(_lib.FIELD_COUNTERS, np.zeros((R, 4, 3), dtype=np.int64)), want_cnt)
+        assert lib.qmc_batch_upload(h, _lib.FIELD_POS, pos.ctypes.data, 8) == _lib.ERR_INVALID  # wrong size
+        assert lib.qmc_batch_upload(h, _lib.FIELD_MOMENTA, pos.ctypes.data, pos.nbytes) == _lib.ERR_INVALID  # created without momenta
+        assert lib.qmc_batch_labels(h, 0) is None
+    finally:
+        _lib.check(lib.qmc_batch_destroy(h))
