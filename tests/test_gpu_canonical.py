@@ -2,6 +2,8 @@
 
 Bar (north_star): energies within 1e-10 relative, identical accept / reject sequences, bit-exact integer state."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -324,7 +326,10 @@ def test_library_owned_batch_handle(cuda_lib):
         _lib.check(lib.qmc_sweep(C.byref(pot), C.byref(b), move, 1, 1234, 0, sweeps * n, None, None))
         got_pos = down(_lib.FIELD_POS, np.zeros((R, 3, n))).transpose(0, 2, 1)
         assert np.array_equal(got_pos, want_pos)
-        assert np.array_equal(down(_lib.FIELD_ENERGY, np.zeros(R)), want_e)
+        if os.environ.get("QMC_FORCE_KERNEL") == "cached":  # the torch-backed run used the pair-term cache: another summation order
+            np.testing.assert_allclose(down(_lib.FIELD_ENERGY, np.zeros(R)), want_e, rtol=1e-13)
+        else:
+            assert np.array_equal(down(_lib.FIELD_ENERGY, np.zeros(R)), want_e)
         assert np.array_equal(down(_lib.FIELD_COUNTERS, np.zeros((R, 4, 3), dtype=np.int64)), want_cnt)
         assert lib.qmc_batch_upload(h, _lib.FIELD_POS, pos.ctypes.data, 8) == _lib.ERR_INVALID  # wrong size
         assert lib.qmc_batch_upload(h, _lib.FIELD_MOMENTA, pos.ctypes.data, pos.nbytes) == _lib.ERR_INVALID  # created without momenta
