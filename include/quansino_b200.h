@@ -234,6 +234,12 @@ int64_t qmc_hmc_workspace_bytes(const qmc_potential_t *pot, const qmc_batch_t *b
 int qmc_fbmc_step(const qmc_potential_t *pot, const qmc_batch_t *batch, double delta, uint64_t seed, uint64_t step, double *forces,
                   int32_t forces_valid, double *gamma_max, int32_t *n_calls, void *workspace, int64_t workspace_bytes, void *stream);
 
+/* the same step with one delta per replica (device [R], overrides `delta` when not NULL): AdaptiveForceBias
+ * (src/quansino/mc/fbmc.py:285-488, update_delta :382-391) whose "energy" scheme gives every system its own delta. */
+int qmc_fbmc_step_v(const qmc_potential_t *pot, const qmc_batch_t *batch, double delta, const double *delta_per_replica, uint64_t seed,
+                    uint64_t step, double *forces, int32_t forces_valid, double *gamma_max, int32_t *n_calls, void *workspace,
+                    int64_t workspace_bytes, void *stream);
+
 /* parallel tempering between temperature-adjacent replicas (no counterpart in the reference):
  * `energies_all` / `temperatures_all` are device [R_global] arrays every rank holds after the all-gather;
  * the kernel evaluates the swap decisions of round `round` (even / odd pairs) from the shared stream and

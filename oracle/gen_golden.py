@@ -35,7 +35,7 @@ from ase.calculators.lj import LennardJones  # noqa: E402
 from quansino.integrators.displacement import Verlet  # noqa: E402
 from quansino.mc.canonical import Canonical, HamiltonianCanonical  # noqa: E402
 from quansino.mc.criteria import CanonicalCriteria, IsobaricCriteria  # noqa: E402
-from quansino.mc.fbmc import ForceBias  # noqa: E402
+from quansino.mc.fbmc import AdaptiveForceBias, ForceBias  # noqa: E402
 from quansino.moves.composite import CompositeMove  # noqa: E402
 from quansino.mc.gcmc import GrandCanonical  # noqa: E402
 from quansino.mc.isobaric import Isobaric  # noqa: E402
@@ -177,23 +177,34 @@ def case_rotation(seed, n_attempts):
     )  # fmt: skip
 
 
-def case_fbmc(seed, steps, delta, temperature):
+def case_fbmc(seed, steps, delta, temperature, adaptive=None):
     """ForceBias (mc/fbmc.py:202-241): every atom moves every step, zeta drawn by rejection against the force-biased trial
-    probability; no acceptance test."""
+    probability; no acceptance test.  ``adaptive = (min_delta, max_delta, scheme, update_function, reference_variance)`` runs
+    AdaptiveForceBias (mc/fbmc.py:285-488) instead: EMT has no committee, so every step warns and falls back to the reference
+    variance -- delta = min + (max - min) * update(reference_variance)."""
     import warnings
 
     atoms, pos0, cell = cu_atoms(3, 0.05, 1212)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")  # "No FixCom constraint found"
-        fb = ForceBias(atoms, delta=delta, temperature=temperature, seed=1)
+        if adaptive:
+            fb = AdaptiveForceBias(atoms, adaptive[0], adaptive[1], temperature=temperature, scheme=adaptive[2],
+                                   update_function=adaptive[3], reference_variance=adaptive[4], seed=1)  # fmt: skip
+        else:
+            fb = ForceBias(atoms, delta=delta, temperature=temperature, seed=1)
     fb._rng = InjectedStream(seed, 10, mode="fbmc")
-    traj, energies, gmax = [], [], []
+    traj, energies, gmax, deltas = [], [], [], []
     for _ in range(steps):
-        fb.step()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # "No committee forces available"
+            fb.step()
+        delta = float(np.max(fb.delta))
+        assert np.all(np.asarray(fb.delta) == delta)
+        deltas.append(delta)
         traj.append(atoms.positions.copy())
         energies.append(float(atoms.get_potential_energy()))
         gmax.append(float(np.max(np.abs(fb.gamma))))
-    return dict(kind="fbmc", seed=seed, replica=10, temperature=temperature, delta=delta, positions0=pos0, cell=cell,
+    return dict(kind="fbmc", seed=seed, replica=10, temperature=temperature, delta=delta, delta_steps=np.array(deltas), positions0=pos0, cell=cell,
                 trajectory=np.array(traj), energy=np.array(energies), gamma_max=np.array(gmax), positions=atoms.positions.copy(),
                 accepted=np.ones(steps, np.int8), move=np.zeros(steps, np.int8), n_atoms=np.full(steps, len(atoms), np.int32))  # fmt: skip
 
@@ -361,6 +372,8 @@ def main():
         "group_rotation": lambda: case_rotation(8001, 100),
         "force_bias": lambda: case_fbmc(9001, 4, 0.1, 600.0),
         "composite_operation": lambda: case_composite_operation(9501, 90),
+        "adaptive_force_bias": lambda: case_fbmc(9002, 3, None, 700.0, adaptive=(0.04, 0.13, "forces", "tanh", 0.1)),
+        "adaptive_force_bias_exp": lambda: case_fbmc(9003, 3, None, 500.0, adaptive=(0.02, 0.2, "energy", "exp", 0.3)),
     }
     only = set(sys.argv[1:])
     for name, fn in cases.items():

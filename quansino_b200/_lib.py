@@ -27,7 +27,7 @@ STATUS_EXP_OVERFLOW, STATUS_CAPACITY, STATUS_CELL_TOO_SMALL, STATUS_LIST_OVERFLO
 EXPORTS = (
     "qmc_abi_version", "qmc_last_error", "qmc_device_count", "qmc_sweep_smem_per_replica", "qmc_energy_full",
     "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_hmc_workspace_bytes", "qmc_pt_swap", "qmc_fp64_peak",
-    "qmc_sweep_host", "qmc_debug_math", "qmc_fbmc_step", "qmc_batch_create", "qmc_batch_destroy", "qmc_batch_upload",
+    "qmc_sweep_host", "qmc_debug_math", "qmc_fbmc_step", "qmc_fbmc_step_v", "qmc_batch_create", "qmc_batch_destroy", "qmc_batch_upload",
     "qmc_batch_download", "qmc_batch_view", "qmc_batch_labels",
 )  # fmt: skip
 
@@ -143,6 +143,8 @@ def load() -> C.CDLL:
     L.qmc_sweep_host.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), i32, u64, u64, i32, C.POINTER(Trace)]
     L.qmc_fbmc_step.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.c_double, u64, u64, vp, i32, vp, vp, vp, i64, vp]
     L.qmc_fbmc_step.restype = C.c_int
+    L.qmc_fbmc_step_v.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.c_double, vp, u64, u64, vp, i32, vp, vp, vp, i64, vp]
+    L.qmc_fbmc_step_v.restype = C.c_int
     L.qmc_batch_create.argtypes = [i32, i32, i32, i32, C.POINTER(vp)]
     L.qmc_batch_destroy.argtypes = [vp]
     L.qmc_batch_upload.argtypes = [vp, i32, vp, i64]

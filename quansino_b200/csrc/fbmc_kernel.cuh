@@ -19,6 +19,7 @@ struct FbmcArgs {
     qmc_batch_t b;
     const double *forces;  // [R][3][n_max] at the current positions
     double delta;
+    const double *delta_r;  // device [R] or nullptr: per-replica delta (AdaptiveForceBias, energy scheme)
     unsigned long long seed, step;
     double *gamma_max;  // [R] or null: max |gamma| of the step (the reference's "Gamma/GammaMax" logger field)
     int *n_calls;       // [R] or null: rejection rounds
@@ -56,6 +57,7 @@ __global__ void __launch_bounds__(FBMC_THREADS) fbmc_kernel(const __grid_constan
     unsigned char *conv = reinterpret_cast<unsigned char *>(zeta + 3 * nmax);
     const size_t base = (size_t)r * 3 * nmax;
     const double kT2 = 2 * a.b.temperature[r] * KB;  // (2 * T) * kB, mc/fbmc.py:104
+    const double delta = a.delta_r ? a.delta_r[r] : a.delta;
     const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
     const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
     // contiguous chunk of the flattened (N, 3) array per thread: element m = 3 i + c lives at forces[c][i]
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(FBMC_THREADS) fbmc_kernel(const __grid_constan
     double gm = 0.0;
     for (int m = m0; m < m1; ++m) {  // calculate_gamma (mc/fbmc.py:93-108)
         const double f = a.forces[base + (size_t)(m % 3) * nmax + m / 3];
-        double g = __ddiv_rn(__dmul_rn(f, a.delta), kT2);
+        double g = __ddiv_rn(__dmul_rn(f, delta), kT2);
         g = g < -FBMC_GAMMA_MAX ? -FBMC_GAMMA_MAX : (g > FBMC_GAMMA_MAX ? FBMC_GAMMA_MAX : g);
         gam[m] = g;
         den[m] = exp(g) - exp(-g);
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(FBMC_THREADS) fbmc_kernel(const __grid_constan
     // displacement = zeta * delta * (min(m) / m)^0.25 (single species: 1); momenta round trip m * d / m (mc/fbmc.py:243-251)
     const double mass = a.b.mass;
     for (int m = m0; m < m1; ++m) {
-        const double d = __dmul_rn(__dmul_rn(zeta[m], a.delta), 1.0);
+        const double d = __dmul_rn(__dmul_rn(zeta[m], delta), 1.0);
         double *x = a.b.pos + base + (size_t)(m % 3) * nmax + m / 3;
         *x = __dadd_rn(*x, __ddiv_rn(__dmul_rn(mass, d), mass));
     }

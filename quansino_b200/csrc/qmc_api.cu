@@ -425,10 +425,17 @@ int qmc_hmc(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move
 
 int qmc_fbmc_step(const qmc_potential_t *pot, const qmc_batch_t *batch, double delta, uint64_t seed, uint64_t step, double *forces,
                   int32_t forces_valid, double *gamma_max, int32_t *n_calls, void *workspace, int64_t workspace_bytes, void *stream) {
+    return qmc_fbmc_step_v(pot, batch, delta, nullptr, seed, step, forces, forces_valid, gamma_max, n_calls, workspace, workspace_bytes,
+                           stream);
+}
+
+int qmc_fbmc_step_v(const qmc_potential_t *pot, const qmc_batch_t *batch, double delta, const double *delta_per_replica, uint64_t seed,
+                    uint64_t step, double *forces, int32_t forces_valid, double *gamma_max, int32_t *n_calls, void *workspace,
+                    int64_t workspace_bytes, void *stream) {
     if (!pot || !forces) return fail(QMC_ERR_INVALID, "potential / forces is NULL");
     int rc;
     if ((rc = check_batch(batch, pot->kind))) return rc;
-    if (!(delta > 0.0)) return fail(QMC_ERR_INVALID, "delta must be positive");
+    if (!delta_per_replica && !(delta > 0.0)) return fail(QMC_ERR_INVALID, "delta must be positive");
     if (batch->n_replicas == 0) return QMC_OK;
     qmc::PotDev pd;
     if ((rc = make_potdev(pot, pd))) return rc;
@@ -440,6 +447,7 @@ int qmc_fbmc_step(const qmc_potential_t *pot, const qmc_batch_t *batch, double d
     a.b = *batch;
     a.forces = forces;
     a.delta = delta;
+    a.delta_r = delta_per_replica;
     a.seed = seed;
     a.step = step;
     a.gamma_max = gamma_max;

@@ -8,12 +8,12 @@ from quansino_b200.mc.core import MonteCarlo
 from quansino_b200.mc.criteria import (
     BaseCriteria, CanonicalCriteria, GrandCanonicalCriteria, HamiltonianCanonicalCriteria, IsobaricCriteria,
 )
-from quansino_b200.mc.fbmc import ForceBias
+from quansino_b200.mc.fbmc import AdaptiveForceBias, ForceBias
 from quansino_b200.mc.gcmc import GrandCanonical
 from quansino_b200.mc.isobaric import Isobaric
 
 __all__ = [
-    "BaseCriteria", "Canonical", "CanonicalCriteria", "Context", "DeformationContext", "DisplacementContext",
+    "AdaptiveForceBias", "BaseCriteria", "Canonical", "CanonicalCriteria", "Context", "DeformationContext", "DisplacementContext",
     "ExchangeContext", "ForceBias", "GrandCanonical", "GrandCanonicalCriteria", "HamiltonianCanonical",
     "HamiltonianCanonicalCriteria", "HamiltonianDisplacementContext", "Isobaric", "IsobaricCriteria", "MonteCarlo",
     "MultiContexts",

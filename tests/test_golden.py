@@ -39,15 +39,25 @@ def test_golden_cases_exercise_every_branch():
     assert ((g["move"] == 1) & (g["accepted"] == 1)).sum() > 0 and ((g["move"] == 1) & (g["accepted"] == 0)).sum() > 0
 
 
-def test_oracle_reproduces_genuine_force_bias():
-    """ForceBias.step (mc/fbmc.py:202-251) run by the genuine sources: same positions bit for bit, same energies."""
+@pytest.mark.parametrize("name", ["force_bias", "adaptive_force_bias", "adaptive_force_bias_exp"])
+def test_oracle_reproduces_genuine_force_bias(name):
+    """ForceBias.step (mc/fbmc.py:202-251) run by the genuine sources: same positions bit for bit, same energies.  The adaptive
+    cases (mc/fbmc.py:285-488) replay the deltas the genuine ``update_delta`` chose and check them against its formula."""
     from oracle import capi
-    from oracle.potentials import emt_params
+    from oracle.potentials import emt_energy_forces, emt_params
 
-    g = load("force_bias")
+    g = load(name)
+    if name == "adaptive_force_bias":  # forces scheme, tanh: no committee -> reference variance every step
+        assert np.all(g["delta_steps"] == 0.04 + (0.13 - 0.04) * (1 - np.tanh(0.1 / 0.1 * np.arctanh(0.5))))
+    if name == "adaptive_force_bias_exp":  # energy scheme, exp: first step falls back, then std(E_atom) / N of the last evaluation
+        assert g["delta_steps"][0] == 0.02 + (0.2 - 0.02) * np.exp(-0.3 / 0.3 * np.log(2))
+        for s in (1, 2):
+            e_atoms = emt_energy_forces(g["trajectory"][s - 1], g["cell"], (True,) * 3, emt_params("Cu"), want_forces=False)["energies"]
+            d = 0.02 + (0.2 - 0.02) * np.exp(-(np.std(e_atoms) / len(e_atoms)) / 0.3 * np.log(2))
+            assert abs(d - g["delta_steps"][s]) <= 1e-15
     pos = g["positions0"].copy()
     par = emt_params("Cu")
     for s in range(len(g["energy"])):
-        e, gmax, calls = capi.fbmc_step(par, pos, g["cell"], (1, 1, 1), 63.546, g["temperature"], g["delta"], int(g["seed"]), int(g["replica"]), s)
+        e, gmax, calls = capi.fbmc_step(par, pos, g["cell"], (1, 1, 1), 63.546, g["temperature"], float(g["delta_steps"][s]), int(g["seed"]), int(g["replica"]), s)
         assert np.array_equal(pos, g["trajectory"][s])
         assert abs(e - g["energy"][s]) <= 1e-11 * abs(g["energy"][s]) and abs(gmax - g["gamma_max"][s]) <= 1e-12 and calls >= 5

@@ -1,5 +1,7 @@
 """The CUDA path against the golden traces of the GENUINE quansino sources (tests/golden/, oracle/gen_golden.py)."""
 
+import contextlib
+
 import numpy as np
 import pytest
 
@@ -66,3 +68,30 @@ def test_cuda_reproduces_genuine_force_bias(cuda_lib):
     f = fb.forces  # the forces left by the last step are the forces at the final positions
     ref = capi.energy(par, out.positions[0], cell, (1, 1, 1), want_forces=True)
     np.testing.assert_allclose(f[0], ref["forces"], rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["adaptive_force_bias", "adaptive_force_bias_exp"])
+def test_cuda_reproduces_genuine_adaptive_force_bias(cuda_lib, name):
+    """AdaptiveForceBias (mc/fbmc.py:285-488) of the genuine sources over EMT: the "forces" scheme falls back to the reference
+    variance every step; the "energy" scheme falls back on the first step and then follows std(E_atom) / N."""
+    from quansino_b200 import EMT, BatchedAtoms
+    from quansino_b200.mc import AdaptiveForceBias
+
+    g = load(name)
+    steps, n = len(g["energy"]), len(g["positions0"])
+    scheme, fn, lo, hi, ref = (("forces", "tanh", 0.04, 0.13, 0.1) if name == "adaptive_force_bias" else ("energy", "exp", 0.02, 0.2, 0.3))
+    pos = np.repeat(g["positions0"][None], 2, axis=0)
+    pos[1] *= 0.999  # a second replica with other atomic energies: its delta must differ in the energy scheme
+    atoms = BatchedAtoms(pos, g["cell"], np.array([n, n], np.int32), "Cu", (True,) * 3, EMT())
+    fb = AdaptiveForceBias(atoms, lo, hi, temperature=g["temperature"], scheme=scheme, update_function=fn, reference_variance=ref,
+                           seed=int(g["seed"]), replica_offset=int(g["replica"]))  # fmt: skip
+    for s in range(steps):
+        with pytest.warns(UserWarning) if (scheme == "forces" or s == 0) else contextlib.nullcontext():
+            fb.run(1)
+        d = np.broadcast_to(np.asarray(fb.delta, float), (2,))
+        assert abs(d[0] - g["delta_steps"][s]) <= 1e-13 * g["delta_steps"][s]
+        assert (d[0] == d[1]) == (scheme == "forces" or s == 0)
+        np.testing.assert_allclose(fb.download().positions[0], g["trajectory"][s], rtol=0, atol=1e-12)
+        assert abs(fb.context.last_potential_energy[0] - g["energy"][s]) <= 1e-10 * abs(g["energy"][s])
+    d = fb.to_dict()
+    assert d["name"] == "AdaptiveForceBias" and d["kwargs"]["min_delta"] == lo and "delta" not in d["kwargs"]
