@@ -206,6 +206,11 @@ int32_t *qmc_batch_labels(qmc_batch_handle_t *handle, int32_t table);
  * of (atom, neighbour image) pairs evaluated. */
 int qmc_energy_full(const qmc_potential_t *pot, const qmc_batch_t *batch, int64_t *pair_count, void *stream);
 
+/* the same evaluation, also storing the per-atom energies -- `calc.results["energies"]` of ASE's EMT / LennardJones, which
+ * AdaptiveForceBias reads under its committee keyword (src/quansino/mc/fbmc.py:329, :431-433) -- into `atom_energies`
+ * (device [R][n_max]; NULL = qmc_energy_full).  Replicas of at most 1024 atoms. */
+int qmc_atom_energies(const qmc_potential_t *pot, const qmc_batch_t *batch, double *atom_energies, int64_t *pair_count, void *stream);
+
 /* full energy AND forces (device [R][3][n_max]) -- `atoms.get_forces()`; workspace as for qmc_hmc */
 int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double *forces, void *workspace,
                     int64_t workspace_bytes, void *stream);

@@ -25,7 +25,7 @@ ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
 STATUS_EXP_OVERFLOW, STATUS_CAPACITY, STATUS_CELL_TOO_SMALL, STATUS_LIST_OVERFLOW = 1, 2, 4, 8
 
 EXPORTS = (
-    "qmc_abi_version", "qmc_last_error", "qmc_device_count", "qmc_sweep_smem_per_replica", "qmc_energy_full",
+    "qmc_abi_version", "qmc_last_error", "qmc_device_count", "qmc_sweep_smem_per_replica", "qmc_energy_full", "qmc_atom_energies",
     "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_hmc_workspace_bytes", "qmc_pt_swap", "qmc_fp64_peak",
     "qmc_sweep_host", "qmc_debug_math", "qmc_fbmc_step", "qmc_fbmc_step_v", "qmc_batch_create", "qmc_batch_destroy", "qmc_batch_upload",
     "qmc_batch_download", "qmc_batch_view", "qmc_batch_labels",
@@ -133,6 +133,8 @@ def load() -> C.CDLL:
     L.qmc_sweep_smem_per_replica.argtypes = [C.POINTER(Potential), i32]
     L.qmc_sweep_smem_per_replica.restype = i64
     L.qmc_energy_full.argtypes = [C.POINTER(Potential), C.POINTER(Batch), vp, vp]
+    L.qmc_atom_energies.argtypes = [C.POINTER(Potential), C.POINTER(Batch), vp, vp, vp]
+    L.qmc_atom_energies.restype = C.c_int
     L.qmc_forces_full.argtypes = [C.POINTER(Potential), C.POINTER(Batch), vp, vp, i64, vp]
     L.qmc_sweep.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), i32, u64, u64, i32, C.POINTER(Trace), vp]
     L.qmc_hmc.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), u64, u64, i32, C.POINTER(Trace), vp, i64, vp]

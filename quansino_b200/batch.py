@@ -268,6 +268,16 @@ class ReplicaBatch:
         self.pair_cache_valid = self.pair_cache is not None and self.cells_uniform
         return self.energy
 
+    def atom_energies(self) -> torch.Tensor:
+        """Per-atom energies [R][n_max] (``calc.results["energies"]`` of ASE's EMT / LennardJones) at the current positions; the
+        energies and EMT caches are refreshed as by ``energy_full``."""
+        out = torch.zeros((self.R, self.n_max), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            b = self.struct()
+            _lib.check(self.lib.qmc_atom_energies(C.byref(self.potential), C.byref(b), out.data_ptr(), None, self.stream()))
+        self.pair_cache_valid = False
+        return out
+
     def forces_full(self) -> torch.Tensor:
         """Forces [R][3][n_max] (and energies) of every replica."""
         f = torch.zeros_like(self.pos)

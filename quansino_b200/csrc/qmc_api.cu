@@ -212,6 +212,10 @@ int64_t qmc_sweep_smem_per_replica(const qmc_potential_t *pot, int32_t n_max) {
 }
 
 int qmc_energy_full(const qmc_potential_t *pot, const qmc_batch_t *batch, int64_t *pair_count, void *stream) {
+    return qmc_atom_energies(pot, batch, nullptr, pair_count, stream);
+}
+
+int qmc_atom_energies(const qmc_potential_t *pot, const qmc_batch_t *batch, double *atom_energies, int64_t *pair_count, void *stream) {
     if (!pot) return fail(QMC_ERR_INVALID, "potential is NULL");
     int rc;
     if ((rc = check_batch(batch, pot->kind))) return rc;
@@ -220,8 +224,9 @@ int qmc_energy_full(const qmc_potential_t *pot, const qmc_batch_t *batch, int64_
     std::memset(&a, 0, sizeof(a));
     if ((rc = make_potdev(pot, a.pot))) return rc;
     a.b = *batch;
+    a.atom_energies = atom_energies;
     if ((rc = fill_cell_args(batch, a.pot, a))) return rc;
-    if (const CachedInst *c = find_cached(pot, batch))  // also fills the pair-term cache
+    if (const CachedInst *c = atom_energies ? nullptr : find_cached(pot, batch))  // also fills the pair-term cache
         return c->energy(a, (long long *)pair_count, (cudaStream_t)stream, g_err, sizeof(g_err));
     const Inst *inst = find_inst(pot->kind, batch->n_max);
     if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica kernels");

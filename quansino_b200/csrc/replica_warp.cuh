@@ -422,11 +422,12 @@ __device__ __forceinline__ void eval_list(const PotDev &pot, const RV &R, const 
     __syncwarp();
 }
 
-// Full evaluation of the replica in shared memory: fills sig / eat (EMT), returns the total energy on every lane.
+// Full evaluation of the replica in shared memory: fills sig / eat (EMT), returns the total energy on every lane;
+// `atom_e` (global, may be null) receives the per-atom energies.
 // `pairs` (per-lane partial) counts the evaluated (atom, image) pairs.
 template <class LY, class CELL>
 __device__ inline double replica_full_energy(const PotDev &pot, const Rep<LY> &R, const CELL &C, const int lane, long long &pairs,
-                                             int &status) {
+                                             int &status, double *atom_e = nullptr) {
     const unsigned lt = lanemask_lt();
     double epart = 0.0;  // lane partial of per-atom energies
     for (int a = 0; a < R.n; ++a) {
@@ -444,7 +445,10 @@ __device__ inline double replica_full_energy(const PotDev &pot, const Rep<LY> &R
                 R.eat(a) = vs;  // sigma_2 sum parked here until the embedding pass below
             }
         } else {
-            if (lane == (a & 31)) epart += 0.5 * vs;  // energies[ii] = 0.5 * pairwise_energies.sum()
+            if (lane == (a & 31)) {
+                epart += 0.5 * vs;  // energies[ii] = 0.5 * pairwise_energies.sum()
+                if (atom_e) atom_e[a] = 0.5 * vs;
+            }
         }
         __syncwarp();
     }
@@ -452,7 +456,9 @@ __device__ inline double replica_full_energy(const PotDev &pot, const Rep<LY> &R
         for (int a = lane; a < R.n; a += 32) {
             const double ea = emt_embed(pot, R.sig(a));
             // energies[a] = E_c + E_AS,2 - E0 + 0.5 * sum(es + eo), es = eo = neghalfv0overgamma2 * dsigma2
-            epart += ea + pot.neghalfv0overgamma2 * R.eat(a);
+            const double e_a = ea + pot.neghalfv0overgamma2 * R.eat(a);
+            epart += e_a;
+            if (atom_e) atom_e[a] = e_a;  // results["energies"] of ASE's calculator
             R.eat(a) = ea;
         }
         __syncwarp();

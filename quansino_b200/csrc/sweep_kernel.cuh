@@ -49,6 +49,7 @@ struct SweepArgs {
     // global counter; done[r] = number of finished chunks of replica r (a chunk waits for its predecessor)
     int chunk_len, n_chunks;
     int *work_counter, *done;
+    double *atom_energies;  // energy kernel only: device [R][n_max] per-atom energies, or nullptr
     qmc_trace_t tr;
 };
 
@@ -1042,7 +1043,8 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32) energy_kernel(con
     const bool ok = store_cell(R, cell, a.b.pbc, a.pot.cut_pre, lane);
     long long pairs = 0;
     int status = 0;
-    const double E = ok ? replica_full_energy<LY>(a.pot, R, C, lane, pairs, status) : __longlong_as_double(0x7ff8000000000000LL);
+    const double E = ok ? replica_full_energy<LY>(a.pot, R, C, lane, pairs, status, a.atom_energies ? a.atom_energies + (size_t)r * nmax : nullptr)
+                        : __longlong_as_double(0x7ff8000000000000LL);
     if (POT == QMC_POT_EMT) {
         for (int j = lane; j < R.n; j += 32) {
             a.b.sigma1[(size_t)r * nmax + j] = R.sig(j);

@@ -150,8 +150,8 @@ class AdaptiveForceBias(ForceBias):
         self._delta_dev: torch.Tensor | None = None
         self._results_available = False  # the reference's calculator has no results before the first evaluation
         super().__init__(atoms, (self.min_delta + self.max_delta) / 2, temperature, **mc_kwargs)
-        if self.scheme == "energy" and self.batch.potential.kind != _lib.POT_EMT:
-            raise NotImplementedError("AdaptiveForceBias(scheme='energy') needs per-atom energies: EMT batches only on the GPU path")
+        if self.scheme == "energy" and self.batch.n_max > 1024:
+            raise NotImplementedError("AdaptiveForceBias(scheme='energy'): per-atom energies are limited to 1024 atoms per replica")
         if self.default_logger:  # mc/fbmc.py:355-380
             lg = self.default_logger
             if self.scheme == "forces":
@@ -187,12 +187,11 @@ class AdaptiveForceBias(ForceBias):
             warn("No committee energies available, using default reference variance.", stacklevel=2)
             return self.reference_variance
         b = self.batch
-        b.energy_full()  # per-atom energies at the current positions (the force kernels do not store them)
+        e = b.atom_energies()  # at the current positions (the force kernels do not keep them)
         n = b.n_atoms.to(torch.float64)
         mask = torch.arange(b.n_max, device=b.device)[None, :] < b.n_atoms[:, None]
-        e = torch.where(mask, b.eatom, torch.zeros_like(b.eatom))
-        mean = e.sum(dim=1) / n
-        var = (torch.where(mask, (b.eatom - mean[:, None]) ** 2, torch.zeros_like(e))).sum(dim=1) / n
+        mean = torch.where(mask, e, torch.zeros_like(e)).sum(dim=1) / n
+        var = torch.where(mask, (e - mean[:, None]) ** 2, torch.zeros_like(e)).sum(dim=1) / n
         return var.sqrt() / n
 
     def tanh_update(self, variation_coefficient):

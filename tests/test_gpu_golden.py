@@ -95,3 +95,26 @@ def test_cuda_reproduces_genuine_adaptive_force_bias(cuda_lib, name):
         assert abs(fb.context.last_potential_energy[0] - g["energy"][s]) <= 1e-10 * abs(g["energy"][s])
     d = fb.to_dict()
     assert d["name"] == "AdaptiveForceBias" and d["kwargs"]["min_delta"] == lo and "delta" not in d["kwargs"]
+
+
+def test_atom_energies_match_the_numpy_restatement(cuda_lib):
+    """qmc_atom_energies = ``calc.results["energies"]``: EMT (periodic Cu) and Lennard-Jones (Pt cluster), sums = total energy."""
+    from oracle.potentials import LJParams, emt_energy_forces, emt_params, lj_energy_forces
+    from quansino_b200 import EMT, BatchedAtoms, LennardJones
+    from quansino_b200.batch import ReplicaBatch
+    from quansino_b200.systems import octahedron
+    from tests.helpers import cu_replicas
+
+    pos, cell, n = cu_replicas(3, 3, seed=5)
+    b = ReplicaBatch(BatchedAtoms(pos.copy(), cell, np.full(3, n, np.int32), "Cu", (True,) * 3, EMT()))
+    e = b.atom_energies().cpu().numpy()
+    for r in range(3):
+        ref = emt_energy_forces(pos[r], cell, (True,) * 3, emt_params("Cu"), want_forces=False)
+        np.testing.assert_allclose(e[r, :n], ref["energies"], rtol=1e-11, atol=1e-12)
+        assert abs(e[r, :n].sum() - float(b.energy[r])) <= 1e-11 * abs(ref["energy"])
+    p, c = octahedron("Pt", 4, 10.0)
+    padded = np.zeros((1, 64, 3))
+    padded[0, : len(p)] = p
+    b = ReplicaBatch(BatchedAtoms(padded, c, np.array([len(p)], np.int32), "Pt", (False,) * 3, LennardJones(sigma=2.5, epsilon=0.1)))
+    ref = lj_energy_forces(p, c, (False,) * 3, LJParams(sigma=2.5, epsilon=0.1), want_forces=False)
+    np.testing.assert_allclose(b.atom_energies().cpu().numpy()[0, : len(p)], ref["energies"], rtol=1e-11, atol=1e-12)
