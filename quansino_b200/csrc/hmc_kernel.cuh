@@ -29,7 +29,17 @@
 namespace qmc {
 
 constexpr int HMC_THREADS = 128;
-constexpr double HMC_SKIN = 1.0;  // Angstrom
+constexpr double HMC_SKIN_DEFAULT = 0.7;  // Angstrom; measured on C5 (64 x 2048 atoms): 0.3 .. 1.0 -> best 0.6 - 0.7 (profiles/r1_m_hmc.md)
+// Verlet-list skin: entries within cutoff + skin are listed, the list is rebuilt once an atom has moved skin / 2.  QMC_HMC_SKIN
+// (environment, read once) overrides the default for tuning.
+__host__ inline double hmc_skin() {
+    static const double skin = [] {
+        const char *e = std::getenv("QMC_HMC_SKIN");
+        const double v = e ? std::atof(e) : 0.0;
+        return v > 0.0 && v <= 4.0 ? v : HMC_SKIN_DEFAULT;
+    }();
+    return skin;
+}
 
 struct HmcWork {  // carved from the caller's workspace
     double *x[2];      // [R][3][N] double-buffered positions
@@ -56,6 +66,8 @@ struct HmcArgs {
     qmc_trace_t tr;
     double *forces_out;
     int lpa;   // lanes per atom (power of two <= 32)
+    double skin;  // Verlet-list skin (hmc_skin())
+    int build_lanes;  // lanes per atom of the list build (1: hmc_build_kernel)
     int cur;   // position buffer holding the current positions
     int mode;  // pass 2: 0 first evaluation, 1 middle, 2 last, 3 forces only, 4 single evaluation of a zero-step trajectory
 };
@@ -67,7 +79,7 @@ __host__ inline int hmc_max_neighbours(const PotDev &pot, const qmc_batch_t &b) 
     // vacuum in it (slabs, clusters, per-replica cells) cannot be: the atoms sit at condensed-phase density whatever the box
     // volume says, so those are sized for the densest packing the potential supports (0.10 atoms / A^3 covers the EMT metals,
     // 1.4 / sigma^3 a compressed Lennard-Jones solid).
-    const double rl = pot.cut + HMC_SKIN, sphere = 4.18879 * rl * rl * rl;
+    const double rl = pot.cut + hmc_skin(), sphere = 4.18879 * rl * rl * rl;
     const double dense = pot.kind == QMC_POT_EMT ? 0.10 : 1.4 / (pot.sigma2 * std::sqrt(pot.sigma2));
     double est = dense * sphere * 1.3 + 24.0;
     const bool periodic = b.pbc[0] && b.pbc[1] && b.pbc[2];
@@ -171,7 +183,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_build_kernel(const __grid_con
     const int r = blockIdx.y;
     if (a.w.flags[r] == 0) return;
     const int nmax = a.b.n_max, n = a.b.n_atoms[r];
-    const double rl = a.pot.cut + HMC_SKIN, rl2 = rl * rl;
+    const double rl = a.pot.cut + a.skin, rl2 = rl * rl;
     CellDev C;
     if (!hmc_cell(a, r, rl * (1.0 + 1e-9), C)) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
@@ -243,20 +255,144 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_build_kernel(const __grid_con
     }
 }
 
+// The same list built by G lanes per atom (G = a.build_lanes, a power of two <= 32): large replicas flag a rebuild one or a few
+// at a time, and one thread per atom then walks all N candidates alone (0.2 ms for 2048 atoms, whatever the number of flagged
+// replicas).  The G lanes of an atom take G consecutive candidates per round; hits are compacted in lane order with one ballot
+// per round (and per further periodic image), so the entries come out in ascending candidate order: a fixed order, hence
+// bit-reproducible sums downstream.
+__global__ void __launch_bounds__(HMC_THREADS) hmc_build_split_kernel(const __grid_constant__ HmcArgs a) {
+    __shared__ double sx[HMC_THREADS], sy[HMC_THREADS], sz[HMC_THREADS];
+    const int r = blockIdx.y;
+    if (a.w.flags[r] == 0) return;
+    const int nmax = a.b.n_max, n = a.b.n_atoms[r];
+    const double rl = a.pot.cut + a.skin, rl2 = rl * rl;
+    CellDev C;
+    if (!hmc_cell(a, r, rl * (1.0 + 1e-9), C)) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
+        return;
+    }
+    const int G = a.build_lanes, lane = threadIdx.x & 31, sub = lane & (G - 1);
+    const unsigned gmask = (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (lane - sub), below = gmask & ((1u << lane) - 1u);
+    const double *x = a.w.x[a.cur] + (size_t)r * 3 * nmax, *y = x + nmax, *z = y + nmax;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool own = i < n;
+    const double pi[3] = {own ? x[i] : 0.0, own ? y[i] : 0.0, own ? z[i] : 0.0};
+    unsigned *list = a.w.list + (size_t)r * a.w.max_nb * nmax;
+    int k = 0, overflow = 0;  // k: entries of the atom so far, the same on its G lanes
+    for (int j0 = 0; j0 < n; j0 += HMC_THREADS) {
+        __syncthreads();
+        const int jl = j0 + threadIdx.x;
+        if (jl < n) {
+            sx[threadIdx.x] = x[jl];
+            sy[threadIdx.x] = y[jl];
+            sz[threadIdx.x] = z[jl];
+        }
+        __syncthreads();
+        const int jn = min(HMC_THREADS, n - j0);
+        for (int t0 = 0; t0 < jn; t0 += G) {
+            const int t = t0 + sub, j = j0 + t;
+            bool active = own && t < jn && j != i;
+            double d0[3] = {0.0, 0.0, 0.0}, d1[3] = {0.0, 0.0, 0.0}, k0[3] = {0.0, 0.0, 0.0};
+            unsigned avail = 0, c = 0;
+            if (active) {
+                const double pj[3] = {sx[t], sy[t], sz[t]};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (C.per[q]) {
+                        const double f = (pi[q] - pj[q]) * C.invL[q];
+                        k0[q] = (f + RINT_MAGIC) - RINT_MAGIC;
+                        d0[q] = fma(k0[q], C.L[q], pj[q]) - pi[q];
+                        d1[q] = d0[q] - copysign(C.L[q], d0[q]);
+                        if (fabs(d0[q]) > C.thr[q]) avail |= 1u << q;
+                    } else {
+                        d0[q] = d1[q] = pj[q] - pi[q];
+                    }
+                }
+            }
+            while (__any_sync(FULL, active)) {  // nearest image first, then the further images a short cell edge allows
+                bool hit = false;
+                int sh[3] = {0, 0, 0};
+                if (active) {
+                    const double dx = (c & 1u) ? d1[0] : d0[0], dy = (c & 2u) ? d1[1] : d0[1], dz = (c & 4u) ? d1[2] : d0[2];
+                    hit = dx * dx + dy * dy + dz * dz < rl2;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) sh[q] = (int)k0[q] - (((c >> q) & 1u) ? (d0[q] > 0.0 ? 1 : -1) : 0);
+                    if (hit && (abs(sh[0]) > 15 || abs(sh[1]) > 15 || abs(sh[2]) > 15)) {
+                        overflow = 1;
+                        hit = false;
+                    }
+                }
+                const unsigned hits = __ballot_sync(FULL, hit) & gmask;
+                if (hit) {
+                    const int slot = k + __popc(hits & below);
+                    if (slot < a.w.max_nb)
+                        list[(size_t)slot * nmax + i] = (unsigned)j | ((unsigned)(sh[0] + 16) << 16) | ((unsigned)(sh[1] + 16) << 21) | ((unsigned)(sh[2] + 16) << 26);
+                    else
+                        overflow = 1;
+                }
+                k += __popc(hits);
+                if (active) {
+                    if (c == avail) active = false;
+                    else c = ((c | (~avail & 7u)) + 1u) & avail;
+                }
+            }
+        }
+    }
+    if (own && sub == 0) {
+        a.w.nnb[(size_t)r * nmax + i] = min(k, a.w.max_nb);
+        double *ref = a.w.ref + (size_t)r * 3 * nmax;
+        ref[i] = pi[0];
+        ref[nmax + i] = pi[1];
+        ref[2 * nmax + i] = pi[2];
+    }
+    if (overflow) atomicOr(a.b.status + r, (int)QMC_STATUS_LIST_OVERFLOW);
+}
+
 // the build kernels of all CTAs must have seen the flag before it is cleared: separate tiny kernel
 __global__ void hmc_clear_flags_kernel(int *flags, int n) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r < n) flags[r] = 0;
 }
 
-// image vector of list entry e for atom i
-__device__ __forceinline__ void entry_vector(unsigned e, const double *x, const double *y, const double *z, const CellDev &C, double xi,
-                                             double yi, double zi, int &j, double &dx, double &dy, double &dz) {
+// List entries are walked through a two-deep software pipeline: the entry word two iterations ahead and the neighbour's
+// coordinates one iteration ahead are in flight while the pair functions of the current entry are evaluated (ncu before: 6.8 of
+// 13 stall cycles per issue were long-scoreboard waits on the dependent pair list word -> gathered coordinates).
+struct NbPipe {
+    unsigned e0, e1;    // current entry, next entry
+    double gx, gy, gz;  // coordinates of the current entry's atom
+};
+
+__device__ __forceinline__ void nb_start(NbPipe &P, const unsigned *lp, int nmax, int k, int lpa, int nn, const double *x, const double *y,
+                                         const double *z) {
+    P.e0 = k < nn ? lp[(size_t)k * nmax] : 0u;
+    P.e1 = k + lpa < nn ? lp[(size_t)(k + lpa) * nmax] : 0u;
+    const int j = (int)(P.e0 & 0xFFFFu);
+    P.gx = x[j];
+    P.gy = y[j];
+    P.gz = z[j];
+}
+
+// image vector of the current entry for the atom at (xi, yi, zi); its atom index in j
+__device__ __forceinline__ void nb_vector(const NbPipe &P, const CellDev &C, double xi, double yi, double zi, int &j, double &dx, double &dy,
+                                          double &dz) {
+    const unsigned e = P.e0;
     j = (int)(e & 0xFFFFu);
     const int sx = (int)((e >> 16) & 31u) - 16, sy = (int)((e >> 21) & 31u) - 16, sz = (int)((e >> 26) & 31u) - 16;
-    dx = fma((double)sx, C.L[0], x[j]) - xi;
-    dy = fma((double)sy, C.L[1], y[j]) - yi;
-    dz = fma((double)sz, C.L[2], z[j]) - zi;
+    dx = fma((double)sx, C.L[0], P.gx) - xi;
+    dy = fma((double)sy, C.L[1], P.gy) - yi;
+    dz = fma((double)sz, C.L[2], P.gz) - zi;
+}
+
+// issue the loads of the following iterations (entry word k + 2 lpa, coordinates of entry k + lpa)
+__device__ __forceinline__ void nb_advance(NbPipe &P, const unsigned *lp, int nmax, int k, int lpa, int nn, const double *x, const double *y,
+                                           const double *z) {
+    const unsigned e2 = k + 2 * lpa < nn ? lp[(size_t)(k + 2 * lpa) * nmax] : 0u;
+    P.e0 = P.e1;
+    P.e1 = e2;
+    const int j = (int)(P.e0 & 0xFFFFu);  // entry 0 (atom 0) past the end: a harmless load
+    P.gx = x[j];
+    P.gy = y[j];
+    P.gz = z[j];
 }
 
 // ---- pass 1: sigma_1, energies, dE/dsigma_1 ----------------------------------------------------------------------
@@ -275,10 +411,13 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass1_kernel(const __grid_con
     if (own) {
         const double xi = x[i], yi = y[i], zi = z[i];
         const int nn = a.w.nnb[(size_t)r * nmax + i];
+        NbPipe P;
+        nb_start(P, list + i, nmax, sub, lpa, nn, x, y, z);
         for (int k = sub; k < nn; k += lpa) {
             int j;
             double dx, dy, dz;
-            entry_vector(list[(size_t)k * nmax + i], x, y, z, C, xi, yi, zi, j, dx, dy, dz);
+            nb_vector(P, C, xi, yi, zi, j, dx, dy, dz);
+            nb_advance(P, list + i, nmax, k, lpa, nn, x, y, z);
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
             if (r2 < a.pot.cut_pre2) {
                 if (POT == QMC_POT_EMT) {
@@ -330,10 +469,16 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass2_kernel(const __grid_con
         xi = x[i]; yi = y[i]; zi = z[i];
         const double da = POT == QMC_POT_EMT ? deds[i] : 0.0;
         const int nn = a.w.nnb[(size_t)r * nmax + i];
+        NbPipe P;
+        nb_start(P, list + i, nmax, sub, lpa, nn, x, y, z);
+        double dj_next = POT == QMC_POT_EMT ? deds[P.e0 & 0xFFFFu] : 0.0;
         for (int k = sub; k < nn; k += lpa) {
             int j;
             double dx, dy, dz;
-            entry_vector(list[(size_t)k * nmax + i], x, y, z, C, xi, yi, zi, j, dx, dy, dz);
+            nb_vector(P, C, xi, yi, zi, j, dx, dy, dz);
+            const double dj = dj_next;
+            nb_advance(P, list + i, nmax, k, lpa, nn, x, y, z);
+            if (POT == QMC_POT_EMT) dj_next = deds[P.e0 & 0xFFFFu];
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
             if (r2 < a.pot.cut_pre2) {
                 double g = 0.0;
@@ -347,7 +492,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass2_kernel(const __grid_con
                         const double es = a.pot.neghalfv0overgamma2 * ds2;
                         const double dedr_pair = es * (dwdroverw - a.pot.kappa_over_beta);
                         const double dds1dr = ds1 * (dwdroverw - a.pot.eta2);
-                        g = ((dedr_pair + dedr_pair) + (da * dds1dr + deds[j] * dds1dr)) * rcp_fast(rr);
+                        g = ((dedr_pair + dedr_pair) + (da * dds1dr + dj * dds1dr)) * rcp_fast(rr);
                     }
                 } else if (!(r2 > a.pot.lj_rc2)) {
                     const double q = a.pot.sigma2 * rcp_fast(r2);
@@ -393,7 +538,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass2_kernel(const __grid_con
                 }
                 a.w.p[base + (size_t)c * nmax + i] = p;
             }
-            if (dsq > 0.25 * HMC_SKIN * HMC_SKIN) a.w.flags[r] = 1;
+            if (dsq > 0.25 * a.skin * a.skin) a.w.flags[r] = 1;
         }
     }
     if (a.mode == 2 || a.mode == 4) {
@@ -476,6 +621,18 @@ inline int hmc_pick_lpa(const qmc_batch_t &b) {
     return lpa;
 }
 
+// Lanes per atom of the list build: replicas of a few hundred atoms come in large batches (one thread per atom fills the GPU);
+// large replicas rebuild one at a time, so the walk over the N candidates is split.
+inline int hmc_pick_build_lanes(const qmc_batch_t &b) {
+    if (const char *e = std::getenv("QMC_HMC_BUILD_LANES")) {
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) return v;
+    }
+    int g = 1;
+    while (g < 32 && b.n_max >= 128 * g) g <<= 1;  // 128 atoms: 2, 256: 4, ... 2048 and more: 32
+    return g;
+}
+
 inline int hmc_check(cudaError_t e, const char *what, char *err, size_t errn) {
     if (e == cudaSuccess) return QMC_OK;
     snprintf(err, errn, "%s failed: %s", what, cudaGetErrorString(e));
@@ -486,7 +643,12 @@ inline int hmc_check(cudaError_t e, const char *what, char *err, size_t errn) {
 inline void hmc_force_eval(HmcArgs &a, cudaStream_t s) {
     const int N = a.b.n_max, R = a.b.n_replicas;
     const dim3 g1((N + HMC_THREADS - 1) / HMC_THREADS, R), gl((N * a.lpa + HMC_THREADS - 1) / HMC_THREADS, R);
-    hmc_build_kernel<<<g1, HMC_THREADS, 0, s>>>(a);
+    if (a.build_lanes > 1) {
+        const dim3 gb((N * a.build_lanes + HMC_THREADS - 1) / HMC_THREADS, R);
+        hmc_build_split_kernel<<<gb, HMC_THREADS, 0, s>>>(a);
+    } else {
+        hmc_build_kernel<<<g1, HMC_THREADS, 0, s>>>(a);
+    }
     hmc_clear_flags_kernel<<<(R + 127) / 128, 128, 0, s>>>(a.w.flags, R);
     if (a.pot.kind == QMC_POT_EMT) {
         hmc_pass1_kernel<QMC_POT_EMT><<<gl, HMC_THREADS, 0, s>>>(a);
@@ -507,6 +669,8 @@ inline int hmc_forces(const PotDev &pot, const qmc_batch_t &b, double *forces, v
     hmc_carve(pot, b, workspace, &a.w);
     a.forces_out = forces;
     a.lpa = hmc_pick_lpa(b);
+    a.skin = hmc_skin();
+    a.build_lanes = hmc_pick_build_lanes(b);
     a.cur = 0;
     a.mode = 3;
     const int N = b.n_max, R = b.n_replicas;
@@ -533,6 +697,8 @@ inline int hmc_run(const PotDev &pot, const qmc_batch_t &b, double dt, int n_ste
     a.tr = tr;
     a.n_attempts = n_attempts;
     a.lpa = hmc_pick_lpa(b);
+    a.skin = hmc_skin();
+    a.build_lanes = hmc_pick_build_lanes(b);
     const int N = b.n_max, R = b.n_replicas;
     const int nb1 = (N + HMC_THREADS - 1) / HMC_THREADS, nb2 = (N * a.lpa + HMC_THREADS - 1) / HMC_THREADS;
     const dim3 g1(nb1, R);

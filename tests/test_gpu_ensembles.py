@@ -172,9 +172,13 @@ def test_grand_canonical_emt_matches_oracle(cuda_lib):
     assert changed > 5
 
 
-def test_forces_match_oracle(cuda_lib):
+@pytest.mark.parametrize("build_lanes", [1, 4, 32])
+def test_forces_match_oracle(cuda_lib, monkeypatch, build_lanes):
+    """``build_lanes``: lanes per atom of the neighbour-list build (hmc_build_kernel / hmc_build_split_kernel); the library
+    reads QMC_HMC_BUILD_LANES at every call."""
     from quansino_b200 import ReplicaBatch
 
+    monkeypatch.setenv("QMC_HMC_BUILD_LANES", str(build_lanes))
     R = 4
     pos, cell, n = cu_replicas(3, R, seed=21)
     batch = ReplicaBatch(_emt_atoms(pos, cell, n), temperature=300.0)
