@@ -52,6 +52,7 @@ struct HmcWork {  // carved from the caller's workspace
     unsigned *list;    // [R][max_nb][N]
     int *nnb;          // [R][N]
     int *flags;        // [R] rebuild requested
+    float *bbox;       // [R][ceil(N / 32)][6] centre and half-width of every 32-atom chunk (list build)
     int max_nb, nb_blocks;
 };
 
@@ -104,10 +105,10 @@ __host__ inline int64_t hmc_carve(const PotDev &pot, const qmc_batch_t &b, void 
     };
     void *x0 = take(R * 3 * N * 8), *x1 = take(R * 3 * N * 8), *p = take(R * 3 * N * 8), *deds = take(R * N * 8), *ref = take(R * 3 * N * 8);
     void *partial = take(R * nb_blocks * 2 * 8), *ke0 = take(R * nb_blocks * 8), *list = take(R * (int64_t)max_nb * N * 4);
-    void *nnb = take(R * N * 4), *flags = take(R * 4), *result = take(R * 2 * 8);
+    void *nnb = take(R * N * 4), *flags = take(R * 4), *result = take(R * 2 * 8), *bbox = take(R * ((N + 31) / 32) * 6 * 4);
     if (w) {
         w->x[0] = (double *)x0; w->x[1] = (double *)x1; w->p = (double *)p; w->deds = (double *)deds; w->ref = (double *)ref;
-        w->partial = (double *)partial; w->ke0 = (double *)ke0; w->list = (unsigned *)list; w->nnb = (int *)nnb; w->flags = (int *)flags; w->result = (double *)result;
+        w->partial = (double *)partial; w->ke0 = (double *)ke0; w->list = (unsigned *)list; w->nnb = (int *)nnb; w->flags = (int *)flags; w->result = (double *)result; w->bbox = (float *)bbox;
         w->max_nb = max_nb; w->nb_blocks = nb_blocks;
     }
     return off;
@@ -262,21 +263,26 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_build_kernel(const __grid_con
 // bit-reproducible sums downstream.
 __global__ void __launch_bounds__(HMC_THREADS) hmc_build_split_kernel(const __grid_constant__ HmcArgs a) {
     __shared__ double sx[HMC_THREADS], sy[HMC_THREADS], sz[HMC_THREADS];
-    const int r = blockIdx.y;
-    if (a.w.flags[r] == 0) return;
+    for (int r = blockIdx.y; r < a.b.n_replicas; r += gridDim.y) {  // few grid rows: a launch without requests costs little
+    if (a.w.flags[r] == 0) continue;
     const int nmax = a.b.n_max, n = a.b.n_atoms[r];
     const double rl = a.pot.cut + a.skin, rl2 = rl * rl;
     CellDev C;
     if (!hmc_cell(a, r, rl * (1.0 + 1e-9), C)) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
-        return;
+        continue;
     }
     const int G = a.build_lanes, lane = threadIdx.x & 31, sub = lane & (G - 1);
+    // single-precision copy of the atom and the cell for the chunk test below (margins cover the rounding)
+    const float rlf = (float)rl + 0.02f, rlf2 = rlf * rlf;
+    const float *bbox = a.w.bbox + (size_t)r * ((nmax + 31) / 32) * 6;
     const unsigned gmask = (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (lane - sub), below = gmask & ((1u << lane) - 1u);
     const double *x = a.w.x[a.cur] + (size_t)r * 3 * nmax, *y = x + nmax, *z = y + nmax;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / G;
     const bool own = i < n;
     const double pi[3] = {own ? x[i] : 0.0, own ? y[i] : 0.0, own ? z[i] : 0.0};
+    const float pif[3] = {(float)pi[0], (float)pi[1], (float)pi[2]}, Lf[3] = {(float)C.L[0], (float)C.L[1], (float)C.L[2]};
+    const float iLf[3] = {(float)C.invL[0], (float)C.invL[1], (float)C.invL[2]};
     unsigned *list = a.w.list + (size_t)r * a.w.max_nb * nmax;
     int k = 0, overflow = 0;  // k: entries of the atom so far, the same on its G lanes
     for (int j0 = 0; j0 < n; j0 += HMC_THREADS) {
@@ -291,7 +297,18 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_build_split_kernel(const __gr
         const int jn = min(HMC_THREADS, n - j0);
         for (int t0 = 0; t0 < jn; t0 += G) {
             const int t = t0 + sub, j = j0 + t;
-            bool active = own && t < jn && j != i;
+            // chunk test: the 32 atoms around candidate j lie in a box (centre, half-width); when the nearest image of that box
+            // is farther than the list radius no candidate of this round can be listed (second images are farther still)
+            const float *bb = bbox + (size_t)((j0 + t0) >> 5) * 6;
+            float gap2 = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                float d = pif[q] - bb[q];
+                if (C.per[q]) d -= Lf[q] * rintf(d * iLf[q]);
+                const float gap = fabsf(d) - bb[3 + q];
+                gap2 += gap > 0.0f ? gap * gap : 0.0f;
+            }
+            bool active = own && t < jn && j != i && !(gap2 > rlf2);
             double d0[3] = {0.0, 0.0, 0.0}, d1[3] = {0.0, 0.0, 0.0}, k0[3] = {0.0, 0.0, 0.0};
             unsigned avail = 0, c = 0;
             if (active) {
@@ -346,6 +363,33 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_build_split_kernel(const __gr
         ref[2 * nmax + i] = pi[2];
     }
     if (overflow) atomicOr(a.b.status + r, (int)QMC_STATUS_LIST_OVERFLOW);
+    }
+}
+
+// centre and half-width (single precision, rounded outwards) of every 32-atom chunk of the replicas that requested a rebuild
+__global__ void __launch_bounds__(HMC_THREADS) hmc_bbox_kernel(const __grid_constant__ HmcArgs a) {
+    const int nmax = a.b.n_max, lane = threadIdx.x & 31;
+    for (int r = blockIdx.y; r < a.b.n_replicas; r += gridDim.y) {
+        if (a.w.flags[r] == 0) continue;
+        const int n = a.b.n_atoms[r], j = blockIdx.x * blockDim.x + threadIdx.x;
+        if (j - lane >= nmax) continue;
+        const double *x = a.w.x[a.cur] + (size_t)r * 3 * nmax;
+        float *bb = a.w.bbox + ((size_t)r * ((nmax + 31) / 32) + (j >> 5)) * 6;
+        for (int q = 0; q < 3; ++q) {
+            double lo = j < n ? x[(size_t)q * nmax + j] : 1e300, hi = j < n ? lo : -1e300;
+            for (int o = 16; o > 0; o >>= 1) {
+                lo = fmin(lo, __shfl_xor_sync(FULL, lo, o));
+                hi = fmax(hi, __shfl_xor_sync(FULL, hi, o));
+            }
+            if (lane == 0) {
+                const bool any = hi >= lo;
+                const float c = any ? (float)(0.5 * (lo + hi)) : 0.0f;
+                // half-width measured from the rounded centre, plus a margin for the single-precision arithmetic of the test
+                bb[q] = c;
+                bb[3 + q] = any ? (float)fmax(hi - (double)c, (double)c - lo) * 1.0001f + 1e-3f : 0.0f;
+            }
+        }
+    }
 }
 
 // the build kernels of all CTAs must have seen the flag before it is cleared: separate tiny kernel
@@ -644,7 +688,9 @@ inline void hmc_force_eval(HmcArgs &a, cudaStream_t s) {
     const int N = a.b.n_max, R = a.b.n_replicas;
     const dim3 g1((N + HMC_THREADS - 1) / HMC_THREADS, R), gl((N * a.lpa + HMC_THREADS - 1) / HMC_THREADS, R);
     if (a.build_lanes > 1) {
-        const dim3 gb((N * a.build_lanes + HMC_THREADS - 1) / HMC_THREADS, R);
+        const int rows = R < 8 ? R : 8;
+        const dim3 gb((N * a.build_lanes + HMC_THREADS - 1) / HMC_THREADS, rows), gq((N + HMC_THREADS - 1) / HMC_THREADS, rows);
+        hmc_bbox_kernel<<<gq, HMC_THREADS, 0, s>>>(a);
         hmc_build_split_kernel<<<gb, HMC_THREADS, 0, s>>>(a);
     } else {
         hmc_build_kernel<<<g1, HMC_THREADS, 0, s>>>(a);
