@@ -659,6 +659,10 @@ __global__ void hmc_energy_publish_kernel(const __grid_constant__ HmcArgs a, int
 
 // ---- host side ---------------------------------------------------------------------------------------------------
 inline int hmc_pick_lpa(const qmc_batch_t &b) {
+    if (const char *e = std::getenv("QMC_HMC_LPA")) {
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 32 && (v & (v - 1)) == 0) return v;
+    }
     const long long atoms = (long long)b.n_replicas * b.n_max;
     int lpa = 1;
     while (lpa < 32 && atoms * lpa < 148LL * 1024) lpa <<= 1;
