@@ -262,6 +262,8 @@ def run_native(args):
     if world > 1:
         import torch.distributed as dist
 
+        # stdout carries ONE JSON line: whatever NCCL logs (a box with NCCL_DEBUG=VERSION prints "NCCL version ...") goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     R = args.replicas
