@@ -31,14 +31,11 @@ namespace qmc {
 constexpr int HMC_THREADS = 128;
 constexpr double HMC_SKIN_DEFAULT = 0.7;  // Angstrom; measured on C5 (64 x 2048 atoms): 0.3 .. 1.0 -> best 0.6 - 0.7 (profiles/r1_m_hmc.md)
 // Verlet-list skin: entries within cutoff + skin are listed, the list is rebuilt once an atom has moved skin / 2.  QMC_HMC_SKIN
-// (environment, read once) overrides the default for tuning.
+// (environment, read at every call) overrides the default for tuning and tests.
 __host__ inline double hmc_skin() {
-    static const double skin = [] {
-        const char *e = std::getenv("QMC_HMC_SKIN");
-        const double v = e ? std::atof(e) : 0.0;
-        return v > 0.0 && v <= 4.0 ? v : HMC_SKIN_DEFAULT;
-    }();
-    return skin;
+    const char *e = std::getenv("QMC_HMC_SKIN");
+    const double v = e ? std::atof(e) : 0.0;
+    return v > 0.0 && v <= 4.0 ? v : HMC_SKIN_DEFAULT;
 }
 
 struct HmcWork {  // carved from the caller's workspace

@@ -191,6 +191,27 @@ def test_forces_match_oracle(cuda_lib, monkeypatch, build_lanes):
         assert abs(e[r] - ref["energy"]) <= 1e-10 * abs(ref["energy"])
 
 
+def test_neighbour_list_build_variants_agree(cuda_lib, monkeypatch):
+    """500-atom cell (nearest images only): the list built by 1, 8 or 32 lanes per atom has the same entries in the same order, so
+    forces and energies are bit-identical; another skin lists other entries, the physics stays (1e-12)."""
+    from quansino_b200 import ReplicaBatch
+
+    pos, cell, n = cu_replicas(5, 2, seed=33)
+    out = {}
+    for lanes, skin in ((1, "0.7"), (8, "0.7"), (32, "0.7"), (32, "0.25"), (1, "1.3")):
+        monkeypatch.setenv("QMC_HMC_BUILD_LANES", str(lanes))
+        monkeypatch.setenv("QMC_HMC_SKIN", skin)
+        batch = ReplicaBatch(_emt_atoms(pos, cell, n), temperature=300.0)
+        out[lanes, skin] = (batch.forces_full().cpu().numpy(), batch.energy.cpu().numpy().copy())
+    f0, e0 = out[1, "0.7"]
+    assert np.abs(f0).max() > 0.01
+    for key in ((8, "0.7"), (32, "0.7")):
+        assert np.array_equal(out[key][0], f0) and np.array_equal(out[key][1], e0)
+    for key in ((32, "0.25"), (1, "1.3")):
+        np.testing.assert_allclose(out[key][0], f0, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(out[key][1], e0, rtol=1e-13)
+
+
 def test_hmc_matches_oracle(cuda_lib):
     from quansino_b200.integrators import Verlet
     from quansino_b200.mc import HamiltonianCanonical
