@@ -163,7 +163,7 @@ def run_reference_arm(args):
         "cpu_baseline": last,
         "e2e": {"value": v, "unit": "attempts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -262,8 +262,6 @@ def run_native(args):
     if world > 1:
         import torch.distributed as dist
 
-        # stdout carries ONE JSON line: whatever NCCL logs (a box with NCCL_DEBUG=VERSION prints "NCCL version ...") goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
 
     R = args.replicas
@@ -432,12 +430,35 @@ def run_native(args):
         "cpu_baseline": cpu,
         "wall_s_timed_region": wall,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout carries ONE JSON line.  Native libraries write there too (NCCL prints "NCCL version ..." on a box with
+    NCCL_DEBUG=VERSION), so file descriptor 1 is pointed at stderr for the whole run and the result line goes to a saved
+    duplicate of the original stdout."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)

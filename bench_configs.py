@@ -140,7 +140,6 @@ def c5pt(R_global=64, repeat=8, n_steps=100, rounds=4):
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=device)
     offset, count = shard(R_global, world, rank)
     pos0, cell = fcc_cubic("Cu", repeat)
