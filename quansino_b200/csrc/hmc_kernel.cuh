@@ -11,17 +11,20 @@
 // Organisation (config C5: 64 replicas x 2048 atoms, 8 per GPU on 8 GPUs): LPA lanes per atom (chosen so that the whole
 // GPU is busy whatever the replica count), a Verlet neighbour list with skin in global memory ([slot][atom]: coalesced
 // for LPA = 1, L2-resident), double-buffered positions, and four kernels per force evaluation:
-//   build   (only when an atom moved more than skin / 2 since the last build: the kernel exits at once otherwise)
+//   build   (only when an atom moved more than skin / 2 since the last build: the kernel exits at once otherwise); one thread
+//           per atom for batches of small replicas, up to 32 lanes per atom with ballot compaction and chunk bounding boxes for
+//           large ones (hmc_bbox_kernel + hmc_build_split_kernel)
 //   pass 1  sigma_1, pair energy, embedding energy and dE/dsigma_1 per atom          [emt.py _calc_e_c_a2]
-//   pass 2  forces (recomputing the pair functions rather than streaming 32 B per pair through HBM), fused with the
+//   pass 2  forces (recomputing the pair functions: streaming 16 B per list entry from pass 1 was measured and is no faster,
+//           profiles/r1_m_hmc.md), fused with the
 //           velocity-Verlet update of the atom and the displacement check            [emt.py _calc_fs_c_a2 / _calc_efs_a1]
 //   finish  deterministic reductions (fixed-order sums of per-CTA partials), acceptance test, commit
 // Forces are the analytic gradient of exactly the energy expression of the sweep kernel.
 #pragma once
 
 #include <cmath>
-
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "replica_warp.cuh"
