@@ -157,9 +157,13 @@ def test_cell_geometries(cuda_lib, case):
         np.testing.assert_allclose(e_u, e_w, rtol=1e-11)
 
 
+@pytest.mark.parametrize("build_lanes", [None, 32])
 @pytest.mark.parametrize("case", ["cell32", "cell864", "cell2048", "slab", "unwrapped", "lj_cluster"])
-def test_neighbour_list_forces_on_other_shapes(cuda_lib, case):
-    """The Hamiltonian kernels' forces and energies (Verlet-list build, image shifts, lanes per atom) against the oracle."""
+def test_neighbour_list_forces_on_other_shapes(cuda_lib, monkeypatch, case, build_lanes):
+    """The Hamiltonian kernels' forces and energies (Verlet-list build, image shifts, lanes per atom) against the oracle;
+    ``build_lanes`` 32 forces the split list build with its bounding-box test onto every shape (None: the automatic choice)."""
+    if build_lanes is not None:
+        monkeypatch.setenv("QMC_HMC_BUILD_LANES", str(build_lanes))
     from quansino_b200 import EMT, BatchedAtoms, LennardJones, ReplicaBatch
     from quansino_b200.systems import fcc_cubic, octahedron, rattle
     from oracle.potentials import LJParams, emt_params
