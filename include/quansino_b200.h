@@ -91,7 +91,9 @@ typedef struct qmc_potential {
  * order of the reference's sorted unique labels (-1 = not movable); every atom of the selected rank is displaced. */
 enum qmc_move_type { QMC_MOVE_DISPLACEMENT = 0, QMC_MOVE_CELL = 1, QMC_MOVE_EXCHANGE = 2, QMC_MOVE_HMC = 3 };
 enum qmc_op { QMC_OP_BALL = 0, QMC_OP_BOX = 1, QMC_OP_SPHERE = 2, QMC_OP_TRANSLATION = 3, QMC_OP_ISOTROPIC = 4, QMC_OP_VERLET = 5,
-              QMC_OP_ROTATION = 6 /* Rotation (operations/displacement.py:178-200): label groups only, rigid z-x-z Euler rotation about the centre */ };
+              QMC_OP_ROTATION = 6 /* Rotation (operations/displacement.py:178-200): label groups only, rigid z-x-z Euler rotation about the centre */,
+              QMC_OP_TRANSLATION_ROTATION = 7 /* TranslationRotation (:203-227): label groups only; QMC_OP_TRANSLATION (:156-175) also
+                                                 serves displacement moves of label groups: centroid to a uniform point of the cell */ };
 #define QMC_LABEL_NONE INT32_MIN
 typedef struct qmc_move {
     int32_t type;          /* qmc_move_type */

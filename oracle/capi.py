@@ -16,7 +16,7 @@ _LIB_PATH = _HERE / "_build" / "libqmc_oracle.so"
 
 POT_EMT, POT_LJ = 0, 1
 MOVE_DISPLACEMENT, MOVE_CELL, MOVE_EXCHANGE, MOVE_HMC = 0, 1, 2, 3
-OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET, OP_ROTATION = 0, 1, 2, 3, 4, 5, 6
+OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET, OP_ROTATION, OP_TRANSLATION_ROTATION = 0, 1, 2, 3, 4, 5, 6, 7
 LABEL_NONE = -(2**31)
 
 
@@ -295,6 +295,6 @@ def fbmc_step(par, positions, cell, pbc, mass, temperature, delta, seed, replica
 
 __all__ = [
     "LABEL_NONE", "MOVE_CELL", "MOVE_DISPLACEMENT", "MOVE_EXCHANGE", "MOVE_HMC", "OP_BALL", "OP_BOX", "OP_ISOTROPIC",
-    "OP_ROTATION", "OP_SPHERE", "OP_TRANSLATION", "OP_VERLET", "MoveSpec", "Replica", "build", "emt_params", "energy", "fbmc_step", "lib", "mc_run",
+    "OP_ROTATION", "OP_SPHERE", "OP_TRANSLATION", "OP_TRANSLATION_ROTATION", "OP_VERLET", "MoveSpec", "Replica", "build", "emt_params", "energy", "fbmc_step", "lib", "mc_run",
     "philox", "uniform_pair",
 ]  # fmt: skip

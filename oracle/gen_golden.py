@@ -43,7 +43,7 @@ from quansino.moves.cell import CellMove  # noqa: E402
 from quansino.moves.displacement import DisplacementMove, HamiltonianDisplacementMove  # noqa: E402
 from quansino.moves.exchange import ExchangeMove  # noqa: E402
 from quansino.operations.cell import IsotropicDeformation  # noqa: E402
-from quansino.operations.displacement import Ball, Box, Rotation, Sphere  # noqa: E402
+from quansino.operations.displacement import Ball, Box, Rotation, Sphere, Translation, TranslationRotation  # noqa: E402
 
 from oracle.philox import InjectedStream  # noqa: E402
 from oracle.units import bar  # noqa: E402
@@ -159,20 +159,22 @@ def case_groups(seed, n_attempts):
     )  # fmt: skip
 
 
-def case_rotation(seed, n_attempts):
+def case_rotation(seed, n_attempts, op_name="Rotation"):
     """Rotation (operations/displacement.py:178-200) of label groups -- trimers and one group of six -- next to rigid translations
-    of the same groups."""
+    of the same groups; ``op_name`` "Translation" / "TranslationRotation" (:156-175, :203-227) relocates (and turns) the group
+    instead: centroid to a uniform point of the cell."""
     atoms, pos0, cell = cu_atoms(3, 0.05, 9191)
     n = len(atoms)
     labels = np.full(n, -1)
     labels[0:36] = np.repeat(np.arange(12), 3) * 2 + 11  # trimers (0,1,2), (3,4,5), ...
     labels[[40, 51, 62, 73, 84, 95]] = 4
     mc = Canonical(atoms, temperature=4000.0, max_cycles=n_attempts, default_displacement_move=DisplacementMove(labels, Ball(0.05)))
-    mc.add_move(DisplacementMove(labels, Rotation()), name="rotation", probability=1.0)
+    op = {"Rotation": Rotation, "Translation": Translation, "TranslationRotation": TranslationRotation}[op_name]()
+    mc.add_move(DisplacementMove(labels, op), name="rotation", probability=1.0)
     inject(mc, seed, 9)
     tr = run_steps(mc, 1)
     return dict(
-        kind="rotation", seed=seed, replica=9, temperature=4000.0, step_size=0.05, positions0=pos0, cell=cell, labels=labels,
+        kind="rotation", op=op_name, seed=seed, replica=9, temperature=4000.0, step_size=0.05, positions0=pos0, cell=cell, labels=labels,
         positions=atoms.positions.copy(), **tr,
     )  # fmt: skip
 
@@ -370,6 +372,8 @@ def main():
         "label_groups": lambda: case_groups(6001, 100),
         "forced_moves": lambda: case_forced(7001, 3),
         "group_rotation": lambda: case_rotation(8001, 100),
+        "group_translation": lambda: case_rotation(8002, 60, "Translation"),
+        "group_translation_rotation": lambda: case_rotation(8003, 100, "TranslationRotation"),
         "force_bias": lambda: case_fbmc(9001, 4, 0.1, 600.0),
         "composite_operation": lambda: case_composite_operation(9501, 90),
         "adaptive_force_bias": lambda: case_fbmc(9002, 3, None, 700.0, adaptive=(0.04, 0.13, "forces", "tanh", 0.1)),

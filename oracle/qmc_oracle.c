@@ -671,6 +671,21 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                     for (int x = 0; x < 3; ++x) t[x] = -mv->step + (mv->step - -mv->step) * opd[x];
                 } else if (mv->op == QO_OP_ROTATION) {
                     t[0] = t[1] = t[2] = 0.0; /* per-atom displacements below */
+                } else if (mv->op == QO_OP_TRANSLATION || mv->op == QO_OP_TRANSLATION_ROTATION) {
+                    /* Translation.calculate (operations/displacement.py:170-175): uniform(0, 1, (1, 3)) @ cell -
+                     * positions[moving].mean(axis=0); the mean adds the rows in index order and divides by their number */
+                    double mean[3] = {0, 0, 0};
+                    int cntm = 0;
+                    for (int i = 0; i < n; ++i)
+                        if (mv->labels[i] == label) {
+                            for (int x = 0; x < 3; ++x) mean[x] += st->pos[3 * i + x];
+                            ++cntm;
+                        }
+                    for (int x = 0; x < 3; ++x) {
+                        double fc = 0.0;
+                        for (int q = 0; q < 3; ++q) fc += (0.0 + (1.0 - 0.0) * opd[q]) * st->cell[3 * q + x];
+                        t[x] = fc - mean[x] / (double)cntm;
+                    }
                 } else { rc = -1; goto done; }
                 /* CompositeOperation (operations/composite.py:58-73): np.sum of the operations' displacements, each drawing
                  * in turn.  Their draws are the attempt's extra draws e = 0, 1, ... (block 64 + e / 2, half e & 1). */
@@ -697,12 +712,21 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                     for (int x = 0; x < 3; ++x) t[x] = t[x] + t2[x];
                 }
                 memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
-                if (mv->op == QO_OP_ROTATION) {
+                const int rotates = mv->op == QO_OP_ROTATION || mv->op == QO_OP_TRANSLATION_ROTATION;
+                if (rotates) {
                     /* Rotation.calculate (operations/displacement.py:192-200): molecule.euler_rotate(phi, theta, psi, center="COM")
                      * with phi, theta, psi = uniform(0, 2 pi, 3); ASE reads the angles as DEGREES [ASE-recalled: ase/atoms.py
                      * euler_rotate, get_center_of_mass]; the move adds molecule.positions - positions[moving] */
                     double ang[3], com[3] = {0, 0, 0}, msum = 0.0;
-                    for (int q = 0; q < 3; ++q) ang[q] = (0.0 + (TWO_PI - 0.0) * opd[q]) * (3.141592653589793 / 180);
+                    double ua[3] = {opd[0], opd[1], opd[2]};
+                    if (mv->op == QO_OP_TRANSLATION_ROTATION) /* TranslationRotation (:220-227): the translation drew first; the
+                                                               * angles are the attempt's extra draws 0, 1, 2 */
+                        for (int e = 0; e < 3; ++e) {
+                            double bx[2];
+                            qo_uniform_pair(seed, attempt, replica, (uint32_t)(64 + e / 2), bx);
+                            ua[e] = bx[e & 1];
+                        }
+                    for (int q = 0; q < 3; ++q) ang[q] = (0.0 + (TWO_PI - 0.0) * ua[q]) * (3.141592653589793 / 180);
                     for (int i = 0; i < n; ++i)
                         if (mv->labels[i] == label) {
                             for (int x = 0; x < 3; ++x) com[x] += st->mass * st->pos[3 * i + x];
@@ -723,11 +747,14 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                             double rcv[3], xn[3];
                             for (int x = 0; x < 3; ++x) rcv[x] = st->pos[3 * i + x] - com[x];
                             for (int x = 0; x < 3; ++x) xn[x] = ((A[x][0] * rcv[0] + A[x][1] * rcv[1]) + A[x][2] * rcv[2]) + com[x];
-                            for (int x = 0; x < 3; ++x) trial[3 * i + x] = st->pos[3 * i + x] + (xn[x] - st->pos[3 * i + x]);
+                            /* translation (1, 3) + rotation (k, 3), then positions[moving] += displacement */
+                            for (int x = 0; x < 3; ++x)
+                                trial[3 * i + x] = mv->op == QO_OP_ROTATION ? st->pos[3 * i + x] + (xn[x] - st->pos[3 * i + x])
+                                                                            : st->pos[3 * i + x] + (t[x] + (xn[x] - st->pos[3 * i + x]));
                         }
                 }
                 for (int i = 0; i < n; ++i)
-                    if (mv->op != QO_OP_ROTATION && mv->labels[i] == label)
+                    if (!rotates && mv->labels[i] == label)
                         for (int x = 0; x < 3; ++x) trial[3 * i + x] = st->pos[3 * i + x] + t[x];
                 moved = a; /* first member of the group */
                 double e_new;

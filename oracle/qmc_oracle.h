@@ -17,7 +17,8 @@ extern "C" {
 
 enum { QO_POT_EMT = 0, QO_POT_LJ = 1 };
 enum { QO_MOVE_DISPLACEMENT = 0, QO_MOVE_CELL = 1, QO_MOVE_EXCHANGE = 2, QO_MOVE_HMC = 3 };
-enum { QO_OP_BALL = 0, QO_OP_BOX = 1, QO_OP_SPHERE = 2, QO_OP_TRANSLATION = 3, QO_OP_ISOTROPIC = 4, QO_OP_VERLET = 5, QO_OP_ROTATION = 6 };
+enum { QO_OP_BALL = 0, QO_OP_BOX = 1, QO_OP_SPHERE = 2, QO_OP_TRANSLATION = 3, QO_OP_ISOTROPIC = 4, QO_OP_VERLET = 5, QO_OP_ROTATION = 6,
+       QO_OP_TRANSLATION_ROTATION = 7 };
 
 /* ase/calculators/emt.py (single species) and ase/calculators/lj.py constants, eV / Angstrom */
 typedef struct {

@@ -19,7 +19,7 @@ POT_EMT, POT_LJ = 0, 1
 MOVE_DISPLACEMENT, MOVE_CELL, MOVE_EXCHANGE, MOVE_HMC = 0, 1, 2, 3
 (FIELD_POS, FIELD_CELL, FIELD_N_ATOMS, FIELD_ENERGY, FIELD_TEMPERATURE, FIELD_SIGMA1, FIELD_EATOM, FIELD_MOMENTA, FIELD_KINETIC,
  FIELD_N_EXCHANGE, FIELD_COUNTERS, FIELD_STATUS, FIELD_PAIR_EVALS, FIELD_LABELS0) = range(14)
-OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET, OP_ROTATION = 0, 1, 2, 3, 4, 5, 6
+OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET, OP_ROTATION, OP_TRANSLATION_ROTATION = 0, 1, 2, 3, 4, 5, 6, 7
 
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
 STATUS_EXP_OVERFLOW, STATUS_CAPACITY, STATUS_CELL_TOO_SMALL, STATUS_LIST_OVERFLOW = 1, 2, 4, 8

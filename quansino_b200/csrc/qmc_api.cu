@@ -274,9 +274,10 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
             }
         switch (mv.type) {
             case QMC_MOVE_DISPLACEMENT:
-                if (mv.op == QMC_OP_ROTATION && !(mv.chain & 4))
-                    return fail(QMC_ERR_UNSUPPORTED, "move %d: Rotation needs label groups (chain bit 2 and a label array)", m);
-                if (mv.op != QMC_OP_BALL && mv.op != QMC_OP_BOX && mv.op != QMC_OP_SPHERE && mv.op != QMC_OP_ROTATION)
+                if ((mv.op == QMC_OP_ROTATION || mv.op == QMC_OP_TRANSLATION || mv.op == QMC_OP_TRANSLATION_ROTATION) && !(mv.chain & 4))
+                    return fail(QMC_ERR_UNSUPPORTED, "move %d: Rotation / Translation / TranslationRotation need label groups (chain bit 2 and a label array)", m);
+                if (mv.op != QMC_OP_BALL && mv.op != QMC_OP_BOX && mv.op != QMC_OP_SPHERE && mv.op != QMC_OP_ROTATION &&
+                    mv.op != QMC_OP_TRANSLATION && mv.op != QMC_OP_TRANSLATION_ROTATION)
                     return fail(QMC_ERR_UNSUPPORTED, "move %d: displacement operation %d is not available on the GPU path", m, mv.op);
                 break;
             case QMC_MOVE_CELL:

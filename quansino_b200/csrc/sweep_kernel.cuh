@@ -212,11 +212,13 @@ __device__ __forceinline__ double gathered_dsigma(const RV &R, int j) {
 template <class LY, class CELL>
 __device__ __forceinline__ Trial local_delta(const PotDev &pot, const Rep<LY> &R, const CELL &C, const int lane, const unsigned lt,
                                              int n_scan, int i, bool has_old, bool has_new, const double po[3], const double pn[3],
-                                             int &status) {
+                                             int &status, int skip_when_adding = -1) {
+    // `skip_when_adding`: an insertion normally scans every stored atom (the new one is not stored yet); a relocated atom is
+    // still stored at its old place and must not see itself
     Trial T;
     DeltaAcc acc = {0.0, 0.0, 0};
     int xstart;
-    const int cnt = scan_neighbours<Rep<LY>, 0>(pot, R, C, lane, lt, n_scan, has_old ? i : -1, has_old, has_new, po, pn, T.n2, xstart, status);
+    const int cnt = scan_neighbours<Rep<LY>, 0>(pot, R, C, lane, lt, n_scan, has_old ? i : skip_when_adding, has_old, has_new, po, pn, T.n2, xstart, status);
     eval_list<Rep<LY>, 0>(pot, R, lane, cnt, xstart, acc);
     const double vs = warp_sum(acc.v);
     T.pairs = acc.pairs;
@@ -556,10 +558,39 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
             const int ng = lab ? max_label(lab, R.n) + 1 : 0;
             if (ng > 0) {
                 const int g = (int)(D.u_label * (double)ng);
-                const bool rot = mv.op == QMC_OP_ROTATION;
-                double t[3] = {0.0, 0.0, 0.0}, A[9], com[3] = {0.0, 0.0, 0.0};
+                const bool rot = mv.op == QMC_OP_ROTATION || mv.op == QMC_OP_TRANSLATION_ROTATION;
+                const bool relocate = mv.op == QMC_OP_TRANSLATION || mv.op == QMC_OP_TRANSLATION_ROTATION;
+                double t[3] = {0.0, 0.0, 0.0}, tt[3] = {0.0, 0.0, 0.0}, A[9], com[3] = {0.0, 0.0, 0.0};
+                if (relocate) {
+                    // Translation.calculate (operations/displacement.py:170-175): uniform(0, 1, (1, 3)) @ cell -
+                    // positions[moving].mean(axis=0); the mean adds the rows in index order and divides by their number
+                    double sum[3] = {0.0, 0.0, 0.0};
+                    int members_n = 0;
+                    for (int base = 0; base < R.n; base += 32) {
+                        const int j = base + lane;
+                        unsigned members = __ballot_sync(FULL, j < R.n && __ldcg(lab + min(j, R.n - 1)) == g);
+                        while (members) {
+                            const int i = base + __ffs(members) - 1;
+                            members &= members - 1;
+                            sum[0] = __dadd_rn(sum[0], R.x(i));
+                            sum[1] = __dadd_rn(sum[1], R.y(i));
+                            sum[2] = __dadd_rn(sum[2], R.z(i));
+                            ++members_n;
+                        }
+                    }
+                    const double f[3] = {D.o0, D.o1, D.o2};
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+                        tt[q] = __dsub_rn(__dmul_rn(f[q], UNIFORM ? a.cell.L[q] : cell[q]), __ddiv_rn(sum[q], (double)max(members_n, 1)));
+                }
                 if (!rot) {
-                    propose_translation(mv.op, mv.step, D.o0, D.o1, D.o2, t);
+                    if (relocate) {
+                        t[0] = tt[0];
+                        t[1] = tt[1];
+                        t[2] = tt[2];
+                    } else {
+                        propose_translation(mv.op, mv.step, D.o0, D.o1, D.o2, t);
+                    }
                 } else {
                     // Rotation.calculate (operations/displacement.py:192-200): euler_rotate(phi, theta, psi, center="COM") with
                     // phi, theta, psi = uniform(0, 2 pi, 3) -- ASE reads them as DEGREES -- z-x-z, A = B (C D); products and sums in
@@ -578,7 +609,15 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                         }
                     }
                     double sn[3], cs[3];
-                    const double u3[3] = {D.o0, D.o1, D.o2};
+                    double u3[3] = {D.o0, D.o1, D.o2};
+                    if (relocate) {  // TranslationRotation (:220-227): the translation drew first; the angles are extra draws 0, 1, 2
+                        double d0, d1, d2, d3;
+                        uniform_pair(key, attempt, grep, 64u, d0, d1);
+                        uniform_pair(key, attempt, grep, 65u, d2, d3);
+                        u3[0] = d0;
+                        u3[1] = d1;
+                        u3[2] = d2;
+                    }
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         com[q] = __ddiv_rn(com[q], ms);
@@ -624,13 +663,26 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                             for (int q = 0; q < 3; ++q) {
                                 const double ar = __dadd_rn(__dadd_rn(__dmul_rn(A[3 * q], rc[0]), __dmul_rn(A[3 * q + 1], rc[1])), __dmul_rn(A[3 * q + 2], rc[2]));
                                 t[q] = __dsub_rn(__dadd_rn(ar, com[q]), po[q]);
+                                if (relocate) t[q] = __dadd_rn(tt[q], t[q]);  // translation (1, 3) + rotation (k, 3)
                             }
                         }
                         const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
-                        const Trial T = local_delta_move<LY>(pot, R, C, lane, lt, R.n, i, po, pn, status);
-                        n_pairs += T.pairs;
-                        de_total += T.dE;
-                        commit_move<LY>(R, lane, T);
+                        Trial T;
+                        if (relocate) {
+                            // old and new surroundings are unrelated (twice the entries of a local move, beyond the paired list):
+                            // take the atom out, then put it in -- the two one-sided deltas of an exchange move
+                            const Trial T1 = local_delta<LY>(pot, R, C, lane, lt, R.n, i, true, false, po, pn, status);
+                            commit_trial<LY>(R, lane, T1);
+                            T = local_delta<LY>(pot, R, C, lane, lt, R.n, i, false, true, po, pn, status, i);
+                            commit_trial<LY>(R, lane, T);
+                            n_pairs += T1.pairs + T.pairs;
+                            de_total += T1.dE + T.dE;
+                        } else {
+                            T = local_delta_move<LY>(pot, R, C, lane, lt, R.n, i, po, pn, status);
+                            n_pairs += T.pairs;
+                            de_total += T.dE;
+                            commit_move<LY>(R, lane, T);
+                        }
                         if (lane == 0) {
                             R.x(i) = pn[0];
                             R.y(i) = pn[1];

@@ -13,6 +13,9 @@ from quansino_b200.operations.displacement import Ball
 from quansino_b200.utils.dynamics import maxwell_boltzmann_distribution
 
 
+_GROUP_OPS = (_lib.OP_ROTATION, _lib.OP_TRANSLATION, _lib.OP_TRANSLATION_ROTATION)  # operations of the label-group kernel path
+
+
 class DisplacementMove(BaseMove):
     """``DisplacementMove(labels, operation=None, apply_constraints=True)`` (``moves/displacement.py:28-273``).
 
@@ -55,7 +58,7 @@ class DisplacementMove(BaseMove):
             raise ValueError("labels must have shape (n_atoms,) or (n_replicas, n_max)")
         out = np.full((n_replicas, n_max), -1, dtype=np.int32)
         out[:, : lab.shape[1]] = lab
-        self._grouped = getattr(self.operation, "op_code", -1) == _lib.OP_ROTATION  # rotations always take the group path
+        self._grouped = getattr(self.operation, "op_code", -1) in _GROUP_OPS  # rotations / relocations always take the group path
         for r in range(n_replicas):
             if lab.shape[1] < n_atoms[r]:
                 raise ValueError("Labels must have the same length as the number of atoms.")
@@ -77,7 +80,7 @@ class DisplacementMove(BaseMove):
 
     def is_identity(self, n_atoms: np.ndarray) -> bool:
         lab = np.asarray(self.labels)
-        if lab.ndim != 1 or self.default_label or getattr(self.operation, "op_code", -1) == _lib.OP_ROTATION:
+        if lab.ndim != 1 or self.default_label or getattr(self.operation, "op_code", -1) in _GROUP_OPS:
             return False  # (rotations run through the label-group path, which needs the label table)
         return bool(np.all(n_atoms == len(lab)) and np.array_equal(lab, np.arange(len(lab))))
 
@@ -93,7 +96,9 @@ class DisplacementMove(BaseMove):
             m.n_extra_ops = len(extra)
             for q, (code, step) in enumerate(extra):
                 m.extra_op[q], m.extra_step[q] = code, step
-        if m.op not in (_lib.OP_BALL, _lib.OP_BOX, _lib.OP_SPHERE, _lib.OP_ROTATION):
+        if m.op in _GROUP_OPS and m.n_extra_ops:
+            raise NotImplementedError("Rotation / Translation / TranslationRotation inside a CompositeOperation are not lowered")
+        if m.op not in (_lib.OP_BALL, _lib.OP_BOX, _lib.OP_SPHERE) + _GROUP_OPS:
             raise NotImplementedError(f"{type(self.operation).__name__} is not a displacement operation of the GPU path")
         m.default_label = _lib.LABEL_NONE if self.default_label is None else int(self.default_label)
         return m

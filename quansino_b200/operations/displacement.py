@@ -40,7 +40,8 @@ class Ball(DisplacementOperation):
 
 
 class Translation(BaseOperation):
-    """Move the selected atoms to a uniform point of the cell (used by exchange insertions)."""
+    """Move the selected atoms to a uniform point of the cell (``operations/displacement.py:156-175``): exchange insertions, and
+    displacement moves of label groups (the centroid lands on the point)."""
 
     op_code = _lib.OP_TRANSLATION
 
@@ -54,4 +55,8 @@ class Rotation(BaseOperation):
 
 
 class TranslationRotation(BaseOperation):
-    """Molecular translation + rotation is not available on the GPU path."""
+    """``Translation`` + ``Rotation`` of the selected label group (``operations/displacement.py:203-227``): the centroid goes to a
+    uniform point of the cell, the group turns about its centre of mass; the translation draws first.  Displacement moves of label
+    groups only (molecular insertion is not lowered yet)."""
+
+    op_code = _lib.OP_TRANSLATION_ROTATION

@@ -113,8 +113,12 @@ def test_moves_lower_like_the_reference_defaults():
     assert HamiltonianDisplacementMove().max_attempts == 10 and DisplacementMove(np.arange(2)).max_attempts == 10000
     # refused, never ignored
     assert DisplacementMove(np.arange(4), Rotation()).lower().op == _lib.OP_ROTATION  # label groups rotate rigidly
+    from quansino_b200.operations import TranslationRotation
+
+    assert DisplacementMove(np.arange(4), Translation()).lower().op == _lib.OP_TRANSLATION  # the group's centroid is relocated
+    assert DisplacementMove(np.arange(4), TranslationRotation()).lower().op == _lib.OP_TRANSLATION_ROTATION
     with pytest.raises(NotImplementedError):
-        DisplacementMove(np.arange(4), Translation()).lower()
+        DisplacementMove(np.arange(4), Rotation() + Ball(0.1)).lower()
     with pytest.raises(NotImplementedError):
         CellMove(scale_atoms=False).lower()
     assert CellMove().lower().axes == 7
