@@ -190,7 +190,8 @@ class MonteCarlo:
                     lab = st.move.validated_labels(self.batch.R, self.batch.n_max, n_atoms)
                     st._label_tensor = torch.from_numpy(lab).to(self.batch.device)
                 grouped = bool(getattr(st.move, "_grouped", False) or getattr(getattr(st.move, "moves", [None])[0], "_grouped", False))
-                grouped = grouped or any(c.op == _lib.OP_ROTATION for c in chain)  # rotations live in the label-group path
+                # rotations and relocations of displacement moves live in the label-group path
+                grouped = grouped or any(c.type == _lib.MOVE_DISPLACEMENT and c.op in (_lib.OP_ROTATION, _lib.OP_TRANSLATION, _lib.OP_TRANSLATION_ROTATION) for c in chain)
                 if grouped and (any_exchange or len(chain) > 1 or chain[0].repeat > 1 or m.type != _lib.MOVE_DISPLACEMENT or m.n_extra_ops):
                     raise NotImplementedError(
                         "label groups (several atoms per label, or labels not increasing with the atom index) cannot be combined "

@@ -58,7 +58,8 @@ class DisplacementMove(BaseMove):
             raise ValueError("labels must have shape (n_atoms,) or (n_replicas, n_max)")
         out = np.full((n_replicas, n_max), -1, dtype=np.int32)
         out[:, : lab.shape[1]] = lab
-        self._grouped = getattr(self.operation, "op_code", -1) in _GROUP_OPS  # rotations / relocations always take the group path
+        # rotations / relocations of a displacement move always take the group path (an ExchangeMove places its atom itself)
+        self._grouped = self.move_type == _lib.MOVE_DISPLACEMENT and getattr(self.operation, "op_code", -1) in _GROUP_OPS
         for r in range(n_replicas):
             if lab.shape[1] < n_atoms[r]:
                 raise ValueError("Labels must have the same length as the number of atoms.")
@@ -80,7 +81,7 @@ class DisplacementMove(BaseMove):
 
     def is_identity(self, n_atoms: np.ndarray) -> bool:
         lab = np.asarray(self.labels)
-        if lab.ndim != 1 or self.default_label or getattr(self.operation, "op_code", -1) in _GROUP_OPS:
+        if lab.ndim != 1 or self.default_label or (self.move_type == _lib.MOVE_DISPLACEMENT and getattr(self.operation, "op_code", -1) in _GROUP_OPS):
             return False  # (rotations run through the label-group path, which needs the label table)
         return bool(np.all(n_atoms == len(lab)) and np.array_equal(lab, np.arange(len(lab))))
 
