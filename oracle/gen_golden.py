@@ -318,6 +318,35 @@ def case_gc_lj(seed, n_attempts, mu):
     )  # fmt: skip
 
 
+def case_gc_molecule(seed, n_attempts, mu):
+    """Grand-canonical insertion / deletion of a DIMER (two atoms sharing one label) placed by TranslationRotation, next to
+    displacement moves whose inserted molecules become label groups (moves/exchange.py:88-176, moves/displacement.py:226-253,
+    operations/displacement.py:203-227).  NOT lowered to the device yet: the trace is the fixture the next
+    step starts from; tests/test_golden.py checks its bookkeeping invariants."""
+    pos0, cell = octahedron("Pt", 4, 10.0)
+    pos0 = rattle(pos0, 0.02, 98)
+    n = len(pos0)
+    atoms = Atoms(f"Pt{n}", positions=pos0, cell=cell, pbc=False, calculator=LennardJones(sigma=2.5, epsilon=0.1))
+    disp = DisplacementMove(np.arange(n))
+    exch = ExchangeMove(np.full(n, -1), TranslationRotation())
+    dimer = Atoms("Pt2", positions=[[0.0, 0.0, 0.0], [0.0, 0.0, 2.8]])
+    mc = GrandCanonical(
+        atoms, exchange_atoms=dimer, temperature=300.0, chemical_potential=mu, number_of_exchange_particles=0,
+        max_cycles=n_attempts, default_displacement_move=disp, default_exchange_move=exch,
+    )  # fmt: skip
+    mc.moves["default_displacement_move"].probability = 0.5
+    mc.moves["default_exchange_move"].probability = 0.5
+    inject(mc, seed, 3)
+    tr = run_steps(mc, 1)
+    return dict(
+        kind="gc_molecule", seed=seed, replica=3, temperature=300.0, chemical_potential=mu, sigma=2.5, epsilon=0.1, step_size=0.1,
+        accessible_volume=float(mc.accessible_volume), exchange_mass=float(mc.exchange_atoms.get_masses().sum()),
+        exchange_positions=dimer.positions.copy(), positions0=pos0, cell=cell, positions=atoms.positions.copy(),
+        labels_displacement=np.asarray(disp.labels), labels_exchange=np.asarray(exch.labels),
+        n_exchange=int(mc.number_of_exchange_particles), **tr,
+    )  # fmt: skip
+
+
 def case_gc_emt(seed, n_attempts, mu, temperature):
     atoms, pos0, cell = cu_atoms(3, 0.05, 31337)
     n = len(atoms)
@@ -364,6 +393,7 @@ def main():
         "isobaric_masked": lambda: case_isobaric(2003, 1, 0.25, mask=np.diag([True, False, True])),
         "gc_lj": lambda: case_gc_lj(3001, 700, -0.5),
         "gc_emt": lambda: case_gc_emt(3002, 150, -3.4, 3000.0),
+        "gc_molecule": lambda: case_gc_molecule(3003, 600, -0.6),
         "hmc": lambda: case_hmc(4001, 3, 2.0, 12, 800.0),
         "composite_mul": lambda: case_composite("mul", 5001, 120),
         "composite_add": lambda: case_composite("add", 5002, 80),

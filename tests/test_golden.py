@@ -61,3 +61,28 @@ def test_oracle_reproduces_genuine_force_bias(name):
         e, gmax, calls = capi.fbmc_step(par, pos, g["cell"], (1, 1, 1), 63.546, g["temperature"], float(g["delta_steps"][s]), int(g["seed"]), int(g["replica"]), s)
         assert np.array_equal(pos, g["trajectory"][s])
         assert abs(e - g["energy"][s]) <= 1e-11 * abs(g["energy"][s]) and abs(gmax - g["gamma_max"][s]) <= 1e-12 and calls >= 5
+
+
+def test_molecular_exchange_fixture_bookkeeping():
+    """``gc_molecule``: dimers inserted / deleted by the genuine sources (ExchangeMove + TranslationRotation).  The device path does
+    not lower molecular exchange yet (DESIGN.md section 8 has the plan); this pins what the plan relies on: a molecule carries ONE
+    label in every move, counts change by whole molecules, and labels stay non-decreasing with the atom index, so that a label
+    group is a contiguous run even after deletions have left gaps in the label values."""
+    g = load("gc_molecule")
+    n_atoms = np.concatenate([[len(g["positions0"])], g["n_atoms"]])
+    steps = np.diff(n_atoms)
+    assert set(np.unique(steps)) <= {-2, 0, 2} and (steps > 0).sum() > 20 and (steps < 0).sum() > 20
+    moved = g["accepted"] == 1
+    assert np.all(steps[~moved] == 0) and np.all(steps[(g["move"] == 0)] == 0)
+    n0, n = len(g["positions0"]), int(n_atoms[-1])
+    assert n == len(g["positions"]) and g["n_exchange"] == (n - n0) // 2
+    for key, first in (("labels_exchange", -1), ("labels_displacement", None)):
+        lab = g[key]
+        assert len(lab) == n
+        if first is not None:
+            assert np.all(lab[:n0] == first)
+        tail = lab[n0:]
+        assert np.all(tail[0::2] == tail[1::2]) and np.all(np.diff(tail[0::2]) > 0)  # pairs share a label; labels increase
+        assert np.any(np.diff(tail[0::2]) > 1)  # deletions left gaps: the labels are no longer dense
+    d = np.linalg.norm(g["positions"][n0::2] - g["positions"][n0 + 1 :: 2], axis=1)
+    np.testing.assert_allclose(d, 2.8, rtol=0, atol=1e-12)  # rigid bodies: placed by a rotation, moved as a label group
