@@ -72,6 +72,9 @@ class State(C.Structure):
         ("_pad", C.c_int32),
         ("last_energy", C.c_double),
         ("last_kinetic", C.c_double),
+        ("n_exchange_atoms", C.c_int32),
+        ("_pad2", C.c_int32),
+        ("exchange_mol", C.c_double * 24),
     ]
 
 
@@ -202,6 +205,7 @@ class Replica:
     accessible_volume: float | None = None
     exchange_mass: float = 0.0
     exchange_pos: tuple = (0.0, 0.0, 0.0)
+    exchange_mol: np.ndarray | None = None  # (k, 3) positions of a molecular exchange species (k <= 8); None: the single atom
     n_exchange: int = 0
     last_energy: float = float("nan")
     last_kinetic: float = float("nan")
@@ -232,6 +236,13 @@ def mc_run(par, rep: Replica, moves: list[MoveSpec], seed: int, replica_id: int,
     st.chemical_potential, st.accessible_volume = rep.chemical_potential, rep.accessible_volume
     st.exchange_mass = rep.exchange_mass
     st.exchange_pos = (C.c_double * 3)(*rep.exchange_pos)
+    if rep.exchange_mol is not None:
+        mol = np.asarray(rep.exchange_mol, dtype=np.float64).reshape(-1, 3)
+        if len(mol) > 8:
+            raise ValueError("the oracle holds exchange molecules of at most 8 atoms")
+        st.n_exchange_atoms = len(mol)
+        for q, v in enumerate(mol.reshape(-1)):
+            st.exchange_mol[q] = float(v)
     st.n_exchange = rep.n_exchange
     st.last_energy, st.last_kinetic = rep.last_energy, rep.last_kinetic
 

@@ -382,6 +382,20 @@ static void labels_on_atoms_changed(qo_move_t *mv, int n_before, int added, int 
     }
 }
 
+/* the same for a molecule (moves/displacement.py:244-253): ONE new label for all `n_added` atoms appended at the end, or the
+ * atoms flagged in `gone` deleted with np.delete (order preserved) */
+static void labels_on_molecule_changed(qo_move_t *mv, int n_before, int n_added, const unsigned char *gone, int *scratch) {
+    if (n_added > 0) {
+        int k = unique_labels(mv->labels, n_before, scratch);
+        int label = (mv->default_label != INT32_MIN && mv->default_label != 0) ? mv->default_label : (k ? scratch[k - 1] + 1 : 0);
+        for (int q = 0; q < n_added; ++q) mv->labels[n_before + q] = label;
+    } else if (gone) {
+        int o = 0;
+        for (int i = 0; i < n_before; ++i)
+            if (!gone[i]) mv->labels[o++] = mv->labels[i];
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------
  * One attempt of each move type.  All work on a TRIAL copy; commit on accept => revert is bit-exact.
  * ---------------------------------------------------------------------------------------------- */
@@ -477,6 +491,7 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
     double *frc = (double *)malloc(sizeof(double) * 3 * (size_t)nmax);
     int *uniq = (int *)malloc(sizeof(int) * (size_t)(nmax + 1));
     char *seen = (char *)malloc((size_t)(nmax + 1));
+    unsigned char *gone = (unsigned char *)calloc((size_t)(nmax + 1), 1); /* atoms of the molecule being deleted */
     double cdf[16];
     int64_t cnt[4] = {0, 0, 0, 0};
     if (!trial || !mom || !frc || !uniq || !seen || n_moves > 16 || n_moves < 1) { rc = -1; goto done; }
@@ -803,31 +818,88 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
             /* moves/exchange.py:134-176 */
             int is_addition = u_coin < mv->bias_insert;
             int n_new = n, particle_delta = 0, removed = -1;
+            const int n_mol = st->n_exchange_atoms > 1 ? st->n_exchange_atoms : 1;
+            const int molecular = n_mol > 1 || mv->op == QO_OP_TRANSLATION_ROTATION;
+            int n_gone = 0;
             if (is_addition) {
-                if (n + 1 > nmax) { rc = -3; goto done; }
+                if (n + n_mol > nmax) { rc = -3; goto done; }
                 memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
-                /* Translation (operations/displacement.py:173-175): uniform(0,1,(1,3)) @ cell - mean(pos[moving]) */
+                const double *tmpl = st->n_exchange_atoms >= 1 ? st->exchange_mol : st->exchange_pos;
+                /* atoms.extend(exchange_atoms), then attempt_displacement on the new indices (moves/exchange.py:103-112).
+                 * Translation (operations/displacement.py:173-175): uniform(0,1,(1,3)) @ cell - mean(pos[moving]) */
+                double mean[3] = {0, 0, 0}, t[3];
+                for (int q = 0; q < n_mol; ++q)
+                    for (int x = 0; x < 3; ++x) mean[x] += tmpl[3 * q + x];
                 for (int x = 0; x < 3; ++x) {
                     double fc = (opd[0] * st->cell[x] + opd[1] * st->cell[3 + x]) + opd[2] * st->cell[6 + x];
-                    trial[3 * n + x] = st->exchange_pos[x] + (fc - st->exchange_pos[x]);
+                    t[x] = fc - mean[x] / (double)n_mol;
                 }
-                n_new = n + 1; particle_delta = 1; moved = n;
+                if (mv->op == QO_OP_TRANSLATION_ROTATION) {
+                    /* + Rotation.calculate (:192-200) of the still untranslated molecule; its angles are extra draws 0, 1, 2 */
+                    double ua[3], ang[3], com[3] = {0, 0, 0}, msum = 0.0;
+                    const double m1 = st->exchange_mass / (double)n_mol; /* single species */
+                    for (int e = 0; e < 3; ++e) {
+                        double bx[2];
+                        qo_uniform_pair(seed, attempt, replica, (uint32_t)(64 + e / 2), bx);
+                        ua[e] = bx[e & 1];
+                    }
+                    for (int q = 0; q < 3; ++q) ang[q] = (0.0 + (TWO_PI - 0.0) * ua[q]) * (3.141592653589793 / 180);
+                    for (int q = 0; q < n_mol; ++q) {
+                        for (int x = 0; x < 3; ++x) com[x] += m1 * tmpl[3 * q + x];
+                        msum += m1;
+                    }
+                    for (int x = 0; x < 3; ++x) com[x] /= msum;
+                    const double cphi = cos(ang[0]), sphi = sin(ang[0]), cth = cos(ang[1]), sth = sin(ang[1]), cpsi = cos(ang[2]), spsi = sin(ang[2]);
+                    const double D[3][3] = {{cphi, sphi, 0.0}, {-sphi, cphi, 0.0}, {0.0, 0.0, 1.0}};
+                    const double Cm[3][3] = {{1.0, 0.0, 0.0}, {0.0, cth, sth}, {0.0, -sth, cth}};
+                    const double B[3][3] = {{cpsi, spsi, 0.0}, {-spsi, cpsi, 0.0}, {0.0, 0.0, 1.0}};
+                    double CD[3][3], A[3][3];
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) CD[i][j] = (Cm[i][0] * D[0][j] + Cm[i][1] * D[1][j]) + Cm[i][2] * D[2][j];
+                    for (int i = 0; i < 3; ++i)
+                        for (int j = 0; j < 3; ++j) A[i][j] = (B[i][0] * CD[0][j] + B[i][1] * CD[1][j]) + B[i][2] * CD[2][j];
+                    for (int q = 0; q < n_mol; ++q) {
+                        double rcv[3], xn[3];
+                        for (int x = 0; x < 3; ++x) rcv[x] = tmpl[3 * q + x] - com[x];
+                        for (int x = 0; x < 3; ++x) xn[x] = ((A[x][0] * rcv[0] + A[x][1] * rcv[1]) + A[x][2] * rcv[2]) + com[x];
+                        for (int x = 0; x < 3; ++x) trial[3 * (n + q) + x] = tmpl[3 * q + x] + (t[x] + (xn[x] - tmpl[3 * q + x]));
+                    }
+                } else {
+                    for (int q = 0; q < n_mol; ++q)
+                        for (int x = 0; x < 3; ++x) trial[3 * (n + q) + x] = tmpl[3 * q + x] + t[x];
+                }
+                n_new = n + n_mol; particle_delta = 1; moved = n;
                 memset(seen, 0, (size_t)n_new);
-                seen[n] = 1;
-                cnt[1] += count_neighbours(pot, n_new, trial, st->cell, st->pbc, n, seen);
+                for (int q = 0; q < n_mol; ++q) {
+                    seen[n + q] = 1;
+                    cnt[1] += count_neighbours(pot, n_new, trial, st->cell, st->pbc, n + q, seen);
+                }
                 for (int i = 0; i < n_new; ++i) cnt[2] += seen[i];
             } else {
                 int nu = unique_labels(mv->labels, n, uniq);
                 if (nu > 0) {
                     int label = uniq[(int)(u_label * (double)nu)];
-                    int a = atom_of_label(mv->labels, n, label);
+                    int a = -1;
+                    if (molecular) {
+                        for (int i = 0; i < n && a < 0; ++i)
+                            if (mv->labels[i] == label) a = i;
+                    } else {
+                        a = atom_of_label(mv->labels, n, label);
+                    }
                     if (a < 0) { rc = -2; goto done; }
                     memset(seen, 0, (size_t)n);
-                    cnt[1] += count_neighbours(pot, n, st->pos, st->cell, st->pbc, a, seen);
+                    /* indices = where(labels == label) (moves/exchange.py:129): the whole molecule goes */
+                    memset(gone, 0, (size_t)n);
+                    for (int i = 0; i < n; ++i)
+                        if (molecular ? mv->labels[i] == label : i == a) {
+                            gone[i] = 1;
+                            ++n_gone;
+                            cnt[1] += count_neighbours(pot, n, st->pos, st->cell, st->pbc, i, seen);
+                        }
                     for (int i = 0; i < n; ++i) cnt[2] += seen[i];
                     for (int i = 0, o = 0; i < n; ++i)
-                        if (i != a) { memcpy(trial + 3 * o, st->pos + 3 * i, sizeof(double) * 3); ++o; }
-                    n_new = n - 1; particle_delta = -1; removed = a; moved = a;
+                        if (!gone[i]) { memcpy(trial + 3 * o, st->pos + 3 * i, sizeof(double) * 3); ++o; }
+                    n_new = n - n_gone; particle_delta = -1; removed = a; moved = a;
                 }
             }
             if (particle_delta != 0) {
@@ -843,11 +915,16 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                 if (accepted) {
                     /* GrandCanonical.save_state (mc/gcmc.py:207-214): every move re-labels, then N_ex += delta */
                     for (int q = 0; q < n_moves; ++q)
-                        if (moves[q].labels) labels_on_atoms_changed(&moves[q], n, particle_delta > 0, removed, uniq);
+                        if (moves[q].labels) {
+                            if (molecular) labels_on_molecule_changed(&moves[q], n, particle_delta > 0 ? n_mol : 0, particle_delta < 0 ? gone : NULL, uniq);
+                            else labels_on_atoms_changed(&moves[q], n, particle_delta > 0, removed, uniq);
+                        }
                     memcpy(st->pos, trial, sizeof(double) * 3 * (size_t)n_new);
                     if (st->momenta) {
-                        if (particle_delta > 0) memset(st->momenta + 3 * n, 0, sizeof(double) * 3);
-                        else memmove(st->momenta + 3 * removed, st->momenta + 3 * (removed + 1), sizeof(double) * 3 * (size_t)(n - removed - 1));
+                        if (particle_delta > 0) memset(st->momenta + 3 * n, 0, sizeof(double) * 3 * (size_t)n_mol);
+                        else
+                            for (int i = 0, o = 0; i < n; ++i)
+                                if (!gone[i]) { memmove(st->momenta + 3 * o, st->momenta + 3 * i, sizeof(double) * 3); ++o; }
                     }
                     st->n_atoms = n_new;
                     st->n_exchange += particle_delta;
@@ -903,6 +980,6 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
     }
 done:
     if (counters) for (int i = 0; i < 4; ++i) counters[i] += cnt[i];
-    free(trial); free(mom); free(frc); free(uniq); free(seen);
+    free(trial); free(mom); free(frc); free(uniq); free(seen); free(gone);
     return rc;
 }

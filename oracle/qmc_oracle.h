@@ -72,6 +72,9 @@ typedef struct {
     int32_t _pad;
     double last_energy;          /* last_potential_energy; NaN => primed by the first call */
     double last_kinetic;         /* last_kinetic_energy */
+    int32_t n_exchange_atoms;    /* atoms of the exchange molecule; 0 / 1: the single atom at exchange_pos */
+    int32_t _pad2;
+    double exchange_mol[24];     /* [n_exchange_atoms][3] exchange_atoms.positions (at most 8 atoms) */
 } qo_state_t;
 
 /* Per-attempt trace (all optional, may be NULL). */
