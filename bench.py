@@ -269,6 +269,7 @@ def run_native(args):
     atoms = BatchedAtoms(pos.copy(), cell, np.full(R, N_ATOMS, dtype=np.int32), "Cu", (True, True, True), EMT())
     mc = Canonical(
         atoms, temperature=TEMPERATURE, seed=SEED, device=device, replica_offset=rank * R, resync_interval=0,
+        neighbour_rows={"on": True, "off": False, "auto": None}[args.rows],
         default_displacement_move=DisplacementMove(np.arange(N_ATOMS), Ball(STEP_SIZE)),
     )  # fmt: skip
     lib = mc.batch.lib
@@ -341,6 +342,7 @@ def run_native(args):
     def e2e_step():
         src, dst = host_bufs[turn[0]], host_bufs[1 - turn[0]]
         mc.batch.pos.copy_(src, non_blocking=True)
+        mc.batch.drop_rows()  # new positions: neighbour rows (if any) are rebuilt by the next launch
         mc.batch.energy_full()
         for _ in mc.step():
             pass
@@ -466,6 +468,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--replicas", type=int, default=4096, help="replicas per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rows", default="on", choices=["on", "off", "auto"], help="neighbour rows (csrc/sweep_rows.cuh) in the sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -33,9 +33,11 @@
 extern "C" {
 #endif
 
-#define QMC_ABI_VERSION 7
+#define QMC_ABI_VERSION 8
 #define QMC_MAX_FORCED 16 /* sum of minimum_count over the move table */
 #define QMC_MAX_MOVES 4
+#define QMC_NBR_SKIN_DEFAULT 0.7 /* Angstrom: Cu EMT rows stay within three 32-entry passes (profiles/r2_a_rows.md) */
+#define QMC_MAX_SUBMOVES 16 /* displacements one composite move may perform per attempt (random-stream layout) */
 
 enum qmc_error {
     QMC_OK = 0,
@@ -50,7 +52,8 @@ enum qmc_status {
     QMC_STATUS_EXP_OVERFLOW = 1, /* criteria exponent > 709.78: the reference raises OverflowError (mc/criteria.py:108) */
     QMC_STATUS_CAPACITY = 2,     /* insertion beyond n_max */
     QMC_STATUS_CELL_TOO_SMALL = 4, /* a periodic edge shrank below the neighbour cutoff */
-    QMC_STATUS_LIST_OVERFLOW = 8
+    QMC_STATUS_LIST_OVERFLOW = 8,
+    QMC_STATUS_ROW_SHIFT = 16    /* neighbour rows: interacting atoms whose unwrapped coordinates are more than 63 cells apart */
 };
 
 /* replaces ase.calculators.emt.EMT / ase.calculators.lj.LennardJones behind
@@ -125,8 +128,7 @@ typedef struct qmc_batch {
     int32_t replica_offset; /* global id of local replica 0 */
     int32_t pbc[3];
     int32_t cells_uniform;  /* != 0: every replica has the fixed cell diag(cell_diag) (fast path); cell moves clear it */
-    int32_t pair_cache_valid; /* != 0: pair_cache holds the terms of the CURRENT positions (filled by qmc_energy_full, kept by
-                                  displacement-only qmc_sweep calls); anything else that moves atoms must clear it */
+    int32_t nbr_row_cap;    /* entries per neighbour row (multiple of 32); 0 = no neighbour rows (brute-force scan kernels) */
     double cell_diag[3];
     double *pos;            /* [R][3][n_max]  x-row, y-row, z-row per replica */
     double *cell;           /* [R][9] row-major, diagonal */
@@ -141,9 +143,15 @@ typedef struct qmc_batch {
     int64_t *counters;      /* [R][QMC_MAX_MOVES][3] attempted, accepted, failed -- accumulated */
     int32_t *status;        /* [R] qmc_status bits, OR-ed */
     int64_t *pair_evals;    /* [R] pair evaluations performed by the sweeps, accumulated, or NULL */
-    double *pair_cache;     /* [R][n_max][n_max][2] image-summed (sigma_1, sigma_2) terms of every pair, or NULL: the canonical
-                               EMT fast path reads the old-position terms from here instead of recomputing them */
-    double *pair_pending;   /* [R][n_max][2] scratch row of the attempt in flight (with pair_cache) */
+    /* Neighbour rows of the row-based sweep kernel (csrc/sweep_rows.cuh; the ASE side is NeighborList behind
+     * mc/criteria.py:104-106): one row per atom listing every periodic image of another atom within cutoff + skin as
+     * (atom index, integer image shift per axis), padded with 0xFFFFFFFF.  The kernel (re)builds the rows of replica r when
+     * nbr_state[r] == 0 and whenever a committed atom has moved further than the skin allows; whoever moves atoms by other
+     * means (uploads, qmc_hmc, qmc_fbmc_step, the scan-based sweep kernels) must zero nbr_state.  All NULL / 0: not used. */
+    uint32_t *nbr_rows;     /* [R][n_max][nbr_row_cap] */
+    double *nbr_ref;        /* [R][3][n_max] positions at the time the rows were built (in units of the cell at that time) */
+    int32_t *nbr_state;     /* [R] 0 = rows invalid; otherwise number of builds so far */
+    double nbr_skin;        /* Angstrom; 0 = library default */
     double mass;            /* amu, single species */
     double pressure;        /* eV / A^3 */
     double chemical_potential;
@@ -198,10 +206,17 @@ int qmc_batch_destroy(qmc_batch_handle_t *handle);
 /* whole-array host <-> device copies; `bytes` must equal the size of the field */
 int qmc_batch_upload(qmc_batch_handle_t *handle, int32_t field, const void *host, int64_t bytes);
 int qmc_batch_download(qmc_batch_handle_t *handle, int32_t field, void *host, int64_t bytes);
-/* n_replicas, n_max and every device pointer of *out; other members are left untouched */
+/* n_replicas, n_max, nbr_row_cap and every device pointer of *out; other members are left untouched */
 int qmc_batch_view(qmc_batch_handle_t *handle, qmc_batch_t *out);
+/* allocates the neighbour rows of the row-based sweep kernel (nbr_rows / nbr_ref / nbr_state, zeroed state = "build at the next
+ * launch"); qmc_batch_view then fills the nbr_* members and uploads of positions / cells / atom counts invalidate the rows */
+int qmc_batch_enable_rows(qmc_batch_handle_t *handle, const qmc_potential_t *pot);
 /* device pointer of label table `table` (for qmc_move_t.labels), NULL if out of range */
 int32_t *qmc_batch_labels(qmc_batch_handle_t *handle, int32_t table);
+
+/* words (u32) per neighbour row the row-based sweep kernel expects for this potential and capacity (qmc_batch_t.nbr_row_cap;
+ * nbr_rows holds n_replicas * n_max rows), or a negative QMC_ERR_* code */
+int32_t qmc_nbr_row_words(const qmc_potential_t *pot, int32_t n_max);
 
 /* validate_simulation (src/quansino/mc/canonical.py:114-122, mc/core.py:221-229): full energy of every
  * replica; fills energy[], sigma1[], eatom[].  `pair_count` (device [R] int64 or NULL) receives the number

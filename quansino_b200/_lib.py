@@ -21,14 +21,15 @@ MOVE_DISPLACEMENT, MOVE_CELL, MOVE_EXCHANGE, MOVE_HMC = 0, 1, 2, 3
  FIELD_N_EXCHANGE, FIELD_COUNTERS, FIELD_STATUS, FIELD_PAIR_EVALS, FIELD_LABELS0) = range(14)
 OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET, OP_ROTATION, OP_TRANSLATION_ROTATION = 0, 1, 2, 3, 4, 5, 6, 7
 
+NBR_SKIN_DEFAULT = 0.7  # include/quansino_b200.h: QMC_NBR_SKIN_DEFAULT
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
-STATUS_EXP_OVERFLOW, STATUS_CAPACITY, STATUS_CELL_TOO_SMALL, STATUS_LIST_OVERFLOW = 1, 2, 4, 8
+STATUS_EXP_OVERFLOW, STATUS_CAPACITY, STATUS_CELL_TOO_SMALL, STATUS_LIST_OVERFLOW, STATUS_ROW_SHIFT = 1, 2, 4, 8, 16
 
 EXPORTS = (
     "qmc_abi_version", "qmc_last_error", "qmc_device_count", "qmc_sweep_smem_per_replica", "qmc_energy_full", "qmc_atom_energies",
     "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_hmc_workspace_bytes", "qmc_pt_swap", "qmc_fp64_peak",
     "qmc_sweep_host", "qmc_debug_math", "qmc_fbmc_step", "qmc_fbmc_step_v", "qmc_batch_create", "qmc_batch_destroy", "qmc_batch_upload",
-    "qmc_batch_download", "qmc_batch_view", "qmc_batch_labels",
+    "qmc_batch_download", "qmc_batch_view", "qmc_batch_labels", "qmc_nbr_row_words", "qmc_batch_enable_rows",
 )  # fmt: skip
 
 
@@ -72,7 +73,7 @@ class Batch(C.Structure):
         ("replica_offset", C.c_int32),
         ("pbc", C.c_int32 * 3),
         ("cells_uniform", C.c_int32),
-        ("pair_cache_valid", C.c_int32),
+        ("nbr_row_cap", C.c_int32),
         ("cell_diag", C.c_double * 3),
         ("pos", C.c_void_p),
         ("cell", C.c_void_p),
@@ -87,8 +88,10 @@ class Batch(C.Structure):
         ("counters", C.c_void_p),
         ("status", C.c_void_p),
         ("pair_evals", C.c_void_p),
-        ("pair_cache", C.c_void_p),
-        ("pair_pending", C.c_void_p),
+        ("nbr_rows", C.c_void_p),
+        ("nbr_ref", C.c_void_p),
+        ("nbr_state", C.c_void_p),
+        ("nbr_skin", C.c_double),
         ("mass", C.c_double),
         ("pressure", C.c_double),
         ("chemical_potential", C.c_double),
@@ -152,10 +155,14 @@ def load() -> C.CDLL:
     L.qmc_batch_upload.argtypes = [vp, i32, vp, i64]
     L.qmc_batch_download.argtypes = [vp, i32, vp, i64]
     L.qmc_batch_view.argtypes = [vp, C.POINTER(Batch)]
+    L.qmc_batch_enable_rows.argtypes = [vp, C.POINTER(Potential)]
+    L.qmc_batch_enable_rows.restype = C.c_int
     L.qmc_batch_labels.argtypes = [vp, i32]
     L.qmc_batch_labels.restype = vp
     for name in ("qmc_batch_create", "qmc_batch_destroy", "qmc_batch_upload", "qmc_batch_download", "qmc_batch_view"):
         getattr(L, name).restype = C.c_int
+    L.qmc_nbr_row_words.argtypes = [C.POINTER(Potential), i32]
+    L.qmc_nbr_row_words.restype = i32
     L.qmc_debug_math.argtypes = [i32, vp, vp, i32, vp]
     L.qmc_debug_math.restype = C.c_int
     for name in ("qmc_energy_full", "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_pt_swap", "qmc_fp64_peak", "qmc_sweep_host"):

@@ -127,7 +127,7 @@ class ReplicaBatch:
         device: str | torch.device = "cuda",
         replica_offset: int = 0,
         with_momenta: bool = False,
-        pair_cache: bool | None = None,
+        neighbour_rows: bool | None = None,
     ):
         self.lib = _lib.load()
         self.calc = calc if calc is not None else atoms.calc
@@ -168,14 +168,12 @@ class ReplicaBatch:
         self.exchange_pos = (0.0, 0.0, 0.0)
         self.cells_uniform = False
         self.cell_diag = (0.0, 0.0, 0.0)
-        # optional pair-term cache of the canonical EMT path (csrc/sweep_cached.cuh): 16 B per ordered pair of atoms.  Off by
-        # default: measured SLOWER than recomputing (2.45e8 vs 3.10e8 attempts/s, profiles/r1_f_pair_cache.md)
-        want_cache = bool(pair_cache)
-        self.pair_cache = self.pair_pending = None
-        self.pair_cache_valid = False
-        if want_cache and self.potential.kind == _lib.POT_EMT and N <= 128 and R > 0:
-            self.pair_cache = torch.zeros((R, N, N, 2), dtype=f64, device=dev)
-            self.pair_pending = torch.zeros((R, N, 2), dtype=f64, device=dev)
+        # neighbour rows of the row-based sweep kernel (csrc/sweep_rows.cuh), allocated on first use (`ensure_rows`)
+        self.want_rows = neighbour_rows
+        self.nbr_rows = self.nbr_ref = self.nbr_state = None
+        self.nbr_row_cap = 0
+        self.nbr_skin = 0.0
+        self.rows_valid = False  # host-side: False = the device flags nbr_state must be zeroed before the next row-based launch
         self.set_temperature(temperature)
         self.upload(atoms)
 
@@ -189,7 +187,9 @@ class ReplicaBatch:
         self.cell.copy_(cell, non_blocking=non_blocking)
         self.n_atoms.copy_(n, non_blocking=non_blocking)
         nbytes = pos.numel() * 8 + cell.numel() * 8 + n.numel() * 4
-        self.pair_cache_valid = False
+        self.rows_valid = False
+        diag = atoms.cell[:, [0, 1, 2], [0, 1, 2]] if self.R else np.zeros((1, 3))
+        self._min_edge = tuple(float(diag[:, k].min()) for k in range(3))
         # one fixed cell shared by every replica: the kernels read it from their arguments (fast path)
         self.cells_uniform = bool(self.R > 0 and np.all(atoms.cell == atoms.cell[0]))
         self.cell_diag = tuple(float(atoms.cell[0, k, k]) for k in range(3)) if self.R else (0.0, 0.0, 0.0)
@@ -224,14 +224,18 @@ class ReplicaBatch:
         self.temperature.copy_(torch.from_numpy(np.array(t, order="C", copy=True)))
 
     # -- C struct ----------------------------------------------------------------------------------
-    def struct(self) -> _lib.Batch:
+    def struct(self, with_rows: bool = False) -> _lib.Batch:
+        """``qmc_batch_t`` of the current state; the neighbour rows ride along only for launches that may use them."""
         b = _lib.Batch()
         b.n_replicas, b.n_max, b.replica_offset = self.R, self.n_max, self.replica_offset
         b.pbc = (C.c_int32 * 3)(*[int(x) for x in self.pbc])
         b.cells_uniform = int(self.cells_uniform)
-        b.pair_cache_valid = int(self.pair_cache_valid and self.pair_cache is not None)
-        b.pair_cache = self.pair_cache.data_ptr() if self.pair_cache is not None else None
-        b.pair_pending = self.pair_pending.data_ptr() if self.pair_pending is not None else None
+        rows = with_rows and self.nbr_rows is not None
+        b.nbr_row_cap = int(self.nbr_row_cap) if rows else 0
+        b.nbr_rows = self.nbr_rows.data_ptr() if rows else None
+        b.nbr_ref = self.nbr_ref.data_ptr() if rows else None
+        b.nbr_state = self.nbr_state.data_ptr() if rows else None
+        b.nbr_skin = float(self.nbr_skin)
         b.cell_diag = (C.c_double * 3)(*self.cell_diag)
         b.pos, b.cell, b.n_atoms = self.pos.data_ptr(), self.cell.data_ptr(), self.n_atoms.data_ptr()
         b.energy, b.temperature = self.energy.data_ptr(), self.temperature.data_ptr()
@@ -247,6 +251,35 @@ class ReplicaBatch:
 
     def stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
+
+    # -- neighbour rows of the row-based sweep kernel ------------------------------------------------
+    def rows_possible(self, skin: float | None = None) -> bool:
+        """Whether this batch can carry neighbour rows: at most 1024 atoms per replica and every periodic edge at least
+        cutoff + skin (checked against the cells known to the host; the kernel re-checks per replica)."""
+        if self.n_max > 1024 or self.R == 0:
+            return False
+        skin = float(skin if skin is not None else (self.nbr_skin or _lib.NBR_SKIN_DEFAULT))
+        need = self.calc.cutoff * (1.0 + 1e-9) + skin
+        return all((not self.pbc[k]) or self._min_edge[k] >= need for k in range(3))
+
+    def ensure_rows(self) -> None:
+        """Allocate the neighbour rows (``qmc_batch_t.nbr_*``) on first use; the kernel builds them when ``nbr_state`` is 0."""
+        if self.nbr_rows is None:
+            words = int(self.lib.qmc_nbr_row_words(C.byref(self.potential), self.n_max))
+            if words < 0:
+                _lib.check(words)
+            self.nbr_row_cap = words
+            self.nbr_rows = torch.zeros((self.R, self.n_max, words), dtype=torch.int32, device=self.device)
+            self.nbr_ref = torch.zeros((self.R, 8), dtype=torch.float64, device=self.device)
+            self.nbr_state = torch.zeros(self.R, dtype=torch.int32, device=self.device)
+            self.rows_valid = True  # (the zeroed state says "build")
+        elif not self.rows_valid:
+            self.nbr_state.zero_()
+            self.rows_valid = True
+
+    def drop_rows(self) -> None:
+        """Positions were changed behind the rows' back (upload, direct writes to ``pos``): rebuild at the next launch."""
+        self.rows_valid = False
 
     # -- kernels -----------------------------------------------------------------------------------
     def energy_full(self, pair_count: torch.Tensor | None = None) -> torch.Tensor:
@@ -264,8 +297,6 @@ class ReplicaBatch:
                     C.byref(self.potential), C.byref(b), pair_count.data_ptr() if pair_count is not None else None, self.stream()
                 )
             )
-        # qmc_energy_full fills the pair-term cache whenever the cached path can serve the batch (EMT, one fixed cell)
-        self.pair_cache_valid = self.pair_cache is not None and self.cells_uniform
         return self.energy
 
     def atom_energies(self) -> torch.Tensor:
@@ -275,7 +306,6 @@ class ReplicaBatch:
         with torch.cuda.device(self.device):
             b = self.struct()
             _lib.check(self.lib.qmc_atom_energies(C.byref(self.potential), C.byref(b), out.data_ptr(), None, self.stream()))
-        self.pair_cache_valid = False
         return out
 
     def forces_full(self) -> torch.Tensor:
@@ -310,6 +340,9 @@ class ReplicaBatch:
         if bits & _lib.STATUS_CAPACITY:
             raise ValueError("an insertion exceeded the atom capacity n_max of the batch")
         if bits & _lib.STATUS_CELL_TOO_SMALL:
-            raise NotImplementedError("a periodic cell edge became shorter than the neighbour cutoff")
+            raise NotImplementedError("a periodic cell edge became shorter than the neighbour cutoff (plus the skin of the neighbour rows, if used)")
         if bits & _lib.STATUS_LIST_OVERFLOW:
             raise RuntimeError("neighbour list overflow")
+        if bits & _lib.STATUS_ROW_SHIFT:
+            raise RuntimeError("neighbour rows: interacting atoms whose unwrapped coordinates are more than 63 cells apart; "
+                               "run with neighbour_rows=False")

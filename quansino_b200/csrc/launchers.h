@@ -6,11 +6,12 @@
 #include <cuda_runtime.h>
 
 #include "sweep_block.cuh"
-#include "sweep_cached.cuh"
+#include "sweep_rows.cuh"
 
 namespace qmc {
 
 typedef int (*sweep_launch_fn)(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn);
+typedef int (*rows_launch_fn)(int feat, const SweepArgs &a, const RowArgs &ra, cudaStream_t s, char *err, size_t errn);
 typedef int (*energy_launch_fn)(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn);
 
 #define QMC_FOR_EACH_NS(X, POT) X(POT, 32) X(POT, 64) X(POT, 108) X(POT, 128) X(POT, 256) X(POT, 512) X(POT, 1024)
@@ -18,14 +19,8 @@ typedef int (*energy_launch_fn)(const SweepArgs &a, long long *pair_count, cudaS
 #define QMC_DECLARE_INST(POT, NS)                                                                           \
     int sweep_launch_##POT##_##NS(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn);     \
     int energy_launch_##POT##_##NS(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn); \
-    int sweep_block_launch_##POT##_##NS(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn);
-
-// cached canonical fast path: EMT, capacity classes served by the warp kernel
-#define QMC_FOR_EACH_CACHED_NS(X) X(32) X(64) X(108) X(128)
-#define QMC_DECLARE_CACHED(NS)                                                                        \
-    int sweep_cached_launch_##NS(const SweepArgs &a, cudaStream_t s, char *err, size_t errn);         \
-    int energy_cached_launch_##NS(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn);
-QMC_FOR_EACH_CACHED_NS(QMC_DECLARE_CACHED)
+    int sweep_block_launch_##POT##_##NS(int feat, const SweepArgs &a, cudaStream_t s, char *err, size_t errn); \
+    int sweep_rows_launch_##POT##_##NS(int feat, const SweepArgs &a, const RowArgs &ra, cudaStream_t s, char *err, size_t errn);
 
 QMC_FOR_EACH_NS(QMC_DECLARE_INST, 0)
 QMC_FOR_EACH_NS(QMC_DECLARE_INST, 1)

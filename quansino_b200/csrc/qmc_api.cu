@@ -95,52 +95,14 @@ struct Inst {
     qmc::energy_launch_fn energy;
     qmc::sweep_launch_fn sweep_block;
     int block_minb;  // CTAs (= replicas) of the block kernel one SM holds
+    qmc::rows_launch_fn sweep_rows;
+    int row_words;   // u32 words per neighbour row
 };
 
 #define QMC_TABLE_ROW(POT, NS) \
-    {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS, qmc::sweep_block_launch_##POT##_##NS, qmc::LayoutB<POT, NS>::REPS},
+    {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS, qmc::sweep_block_launch_##POT##_##NS, qmc::LayoutB<POT, NS>::REPS, \
+     qmc::sweep_rows_launch_##POT##_##NS, qmc::LayoutR<POT, NS>::ROWW},
 const Inst g_inst[2][7] = {{QMC_FOR_EACH_NS(QMC_TABLE_ROW, 0)}, {QMC_FOR_EACH_NS(QMC_TABLE_ROW, 1)}};
-
-// per-(device, stream) scratch of the dynamic work distribution: one work counter + one progress counter per replica
-struct Scratch {
-    int *buf = nullptr;
-    size_t ints = 0;
-};
-std::mutex g_scratch_mu;
-std::map<std::pair<int, cudaStream_t>, Scratch> g_scratch;
-
-int get_scratch(cudaStream_t s, size_t ints, int **out) {
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(g_scratch_mu);
-    Scratch &sc = g_scratch[{dev, s}];
-    if (sc.ints < ints) {
-        if (sc.buf) CUDA_TRY(cudaFree(sc.buf));
-        sc.buf = nullptr;
-        sc.ints = 0;
-        CUDA_TRY(cudaMalloc(&sc.buf, ints * sizeof(int)));
-        sc.ints = ints;
-    }
-    *out = sc.buf;
-    return QMC_OK;
-}
-
-struct CachedInst {
-    int ns;
-    int (*sweep)(const qmc::SweepArgs &, cudaStream_t, char *, size_t);
-    int (*energy)(const qmc::SweepArgs &, long long *, cudaStream_t, char *, size_t);
-};
-#define QMC_CACHED_ROW(NS) {NS, qmc::sweep_cached_launch_##NS, qmc::energy_cached_launch_##NS},
-const CachedInst g_cached[] = {QMC_FOR_EACH_CACHED_NS(QMC_CACHED_ROW)};
-
-// the pair-term cache serves EMT batches with one fixed cell whose capacity class runs one warp per replica
-const CachedInst *find_cached(const qmc_potential_t *pot, const qmc_batch_t *b) {
-    if (pot->kind != QMC_POT_EMT || !b->pair_cache || !b->pair_pending || !b->cells_uniform) return nullptr;
-    const int ns = qmc::capacity_class(b->n_max);
-    for (const CachedInst &c : g_cached)
-        if (c.ns == ns) return &c;
-    return nullptr;
-}
 
 const Inst *find_inst(int kind, int n_max) {
     const int ns = qmc::capacity_class(n_max);
@@ -211,6 +173,13 @@ int64_t qmc_sweep_smem_per_replica(const qmc_potential_t *pot, int32_t n_max) {
     }
 }
 
+int32_t qmc_nbr_row_words(const qmc_potential_t *pot, int32_t n_max) {
+    if (!pot || n_max <= 0) return fail(QMC_ERR_INVALID, "bad arguments");
+    const Inst *inst = find_inst(pot->kind, n_max);
+    if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica sweep kernels");
+    return inst->row_words;
+}
+
 int qmc_energy_full(const qmc_potential_t *pot, const qmc_batch_t *batch, int64_t *pair_count, void *stream) {
     return qmc_atom_energies(pot, batch, nullptr, pair_count, stream);
 }
@@ -226,8 +195,6 @@ int qmc_atom_energies(const qmc_potential_t *pot, const qmc_batch_t *batch, doub
     a.b = *batch;
     a.atom_energies = atom_energies;
     if ((rc = fill_cell_args(batch, a.pot, a))) return rc;
-    if (const CachedInst *c = atom_energies ? nullptr : find_cached(pot, batch))  // also fills the pair-term cache
-        return c->energy(a, (long long *)pair_count, (cudaStream_t)stream, g_err, sizeof(g_err));
     const Inst *inst = find_inst(pot->kind, batch->n_max);
     if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica kernels");
     return inst->energy(a, (long long *)pair_count, (cudaStream_t)stream, g_err, sizeof(g_err));
@@ -318,6 +285,17 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         a.mv[m].labels = mv.labels;
     }
     if (!(tot > 0.0)) return fail(QMC_ERR_INVALID, "move probabilities sum to zero");
+    // Random stream layout: drawing sub-move c >= 1 of a composite uses Philox blocks 32 + 2 (c - 1) and 33 + 2 (c - 1); the extra
+    // draws (closing CellMove, CompositeOperation, TranslationRotation angles) start at block 64.  A composite with more than
+    // 16 drawing sub-moves would read the same numbers twice (and tie the volume change to the atom chosen): refuse it.
+    for (int m = 0, drawn = 0; m < n_moves; ++m) {
+        const bool head = m == 0 || !(moves[m - 1].chain & 1);
+        if (head) drawn = 0;
+        if (moves[m].type == QMC_MOVE_DISPLACEMENT) drawn += moves[m].repeat > 0 ? moves[m].repeat : 1;
+        if (drawn > QMC_MAX_SUBMOVES)
+            return fail(QMC_ERR_UNSUPPORTED, "move %d: a composite move may displace at most %d times per attempt on the GPU path "
+                        "(Philox blocks 32..63 hold the sub-move draws)", m, QMC_MAX_SUBMOVES);
+    }
     if (a.n_forced > 0) {  // mc/core.py:161-165: the forced moves must fit into a step; steps are counted from attempt 0
         a.max_cycles = moves[0].max_cycles;
         if (a.max_cycles < a.n_forced) return fail(QMC_ERR_INVALID, "The number of forced moves exceeds the number of cycles.");
@@ -355,37 +333,54 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         if (moves[m].type == QMC_MOVE_EXCHANGE) feat |= qmc::F_EXCHANGE;
     }
     if (any_composite) feat |= qmc::F_COMPOSITE;
+    // label tables, composite and forced moves run in instantiations that also contain the exchange code, which reads and writes
+    // n_exchange unconditionally
+    if ((feat & (qmc::F_LABELS | qmc::F_EXCHANGE | qmc::F_COMPOSITE)) && !batch->n_exchange)
+        return fail(QMC_ERR_INVALID, "batch.n_exchange is required with label tables, composite, forced or exchange moves");
     if ((rc = fill_cell_args(batch, a.pot, a))) return rc;
     const Inst *inst = find_inst(pot->kind, batch->n_max);
     if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica sweep kernel");
     // one warp per replica fills the GPU only with thousands of replicas; smaller batches run CTA-per-replica
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    int sms = 148, dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     // (measured on B200: at 108 atoms a warp owns a single 32-atom tile and the block kernel loses, 1.5e8 vs 1.7e8 attempts/s at
     // 1024 replicas; at 500 atoms it wins 1.9x -- profiles/r1_e_kernel_choice.md)
     bool block = inst->ns >= 256 && batch->n_replicas <= 2 * sms * inst->block_minb;
     const char *force = std::getenv("QMC_FORCE_KERNEL");
-    if (force) block = std::strcmp(force, "block") == 0;
-    if (any_composite) block = false;  // composite moves exist in the warp-per-replica kernel only
-    // canonical fast path: old-position pair terms come from the HBM cache instead of being recomputed
-    if (feat == 0 && batch->pair_cache_valid && !block && !(force && std::strcmp(force, "cached") != 0))
-        if (const CachedInst *c = find_cached(pot, batch)) return c->sweep(a, (cudaStream_t)stream, g_err, sizeof(g_err));
-    if (!block) {
-        // dynamic (chunk, replica) work items: warps the scheduler favours take over from the ones it starves
-        // (measured neutral at best when every replica already owns a warp -- a replica is a sequential chain, so nobody can
-        // help a starved one; it pays only through multi-wave batches.  Off unless QMC_CHUNK is set.)
-        int chunk = 0;
-        if (const char *c = std::getenv("QMC_CHUNK")) chunk = std::atoi(c);
-        if (chunk > 0 && n_attempts > chunk && !any_composite) {
-            int *buf = nullptr;
-            if ((rc = get_scratch((cudaStream_t)stream, (size_t)batch->n_replicas + 1, &buf))) return rc;
-            CUDA_TRY(cudaMemsetAsync(buf, 0, ((size_t)batch->n_replicas + 1) * sizeof(int), (cudaStream_t)stream));
-            a.chunk_len = chunk;
-            a.n_chunks = (n_attempts + chunk - 1) / chunk;
-            a.work_counter = buf;
-            a.done = buf + 1;
+    // Row-based kernel (csrc/sweep_rows.cuh): single-atom displacement moves and cell moves of a batch that carries neighbour
+    // rows.  It needs cutoff + skin <= every periodic edge (no self-images) and step <= skin / 2 (a trial position must stay
+    // inside the reach of the moved atom's row right after a rebuild).
+    if (batch->nbr_rows && !(force && std::strcmp(force, "rows") != 0)) {
+        bool ok = !any_exchange && !any_composite && (feat & qmc::F_EXCHANGE) == 0 && batch->nbr_ref && batch->nbr_state;
+        double tmax = 0.0;
+        for (int m = 0; m < n_moves && ok; ++m) {
+            if (moves[m].type == QMC_MOVE_DISPLACEMENT) {
+                ok = moves[m].op == QMC_OP_BALL || moves[m].op == QMC_OP_BOX || moves[m].op == QMC_OP_SPHERE;
+                tmax = std::max(tmax, std::fabs(moves[m].step) * (moves[m].op == QMC_OP_BOX ? std::sqrt(3.0) : 1.0));
+            } else if (moves[m].type != QMC_MOVE_CELL) {
+                ok = false;
+            }
+        }
+        qmc::RowArgs ra;
+        ra.skin = batch->nbr_skin > 0.0 ? batch->nbr_skin : QMC_NBR_SKIN_DEFAULT;
+        ra.cutb = a.pot.cut_pre + ra.skin;
+        ra.bound2 = 0.25 * ra.skin * ra.skin;
+        if (ok && !(tmax * (1.0 + 1e-9) <= 0.5 * ra.skin)) ok = false;
+        if (ok && batch->cells_uniform)
+            for (int k = 0; k < 3; ++k)
+                if (batch->pbc[k] && !(batch->cell_diag[k] >= ra.cutb)) ok = false;
+        if (ok) {
+            if (batch->nbr_row_cap != inst->row_words)
+                return fail(QMC_ERR_INVALID, "batch.nbr_row_cap is %d, the row-based kernel of this capacity class uses %d words (qmc_nbr_row_words)",
+                            batch->nbr_row_cap, inst->row_words);
+            return inst->sweep_rows(feat, a, ra, (cudaStream_t)stream, g_err, sizeof(g_err));
         }
     }
+    // every other kernel moves atoms without looking at the rows: they are stale from here on
+    if (batch->nbr_state) CUDA_TRY(cudaMemsetAsync(batch->nbr_state, 0, (size_t)batch->n_replicas * sizeof(int32_t), (cudaStream_t)stream));
+    if (force) block = std::strcmp(force, "block") == 0;
+    if (any_composite) block = false;  // composite moves exist in the warp-per-replica kernel only
     return (block ? inst->sweep_block : inst->sweep)(feat, a, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 
@@ -425,6 +420,7 @@ int qmc_hmc(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move
     qmc_trace_t tr;
     std::memset(&tr, 0, sizeof(tr));
     if (trace) tr = *trace;
+    if (batch->nbr_state) CUDA_TRY(cudaMemsetAsync(batch->nbr_state, 0, (size_t)batch->n_replicas * sizeof(int32_t), (cudaStream_t)stream));
     return qmc::hmc_run(pd, *batch, move->dt, move->n_steps, seed, attempt_base, n_attempts, tr, workspace, (cudaStream_t)stream,
                         g_err, sizeof(g_err));
 }
@@ -447,6 +443,7 @@ int qmc_fbmc_step_v(const qmc_potential_t *pot, const qmc_batch_t *batch, double
     if ((rc = make_potdev(pot, pd))) return rc;
     if (!workspace || workspace_bytes < qmc::hmc_workspace_bytes(pd, *batch)) return fail(QMC_ERR_INVALID, "workspace too small");
     cudaStream_t s = (cudaStream_t)stream;
+    if (batch->nbr_state) CUDA_TRY(cudaMemsetAsync(batch->nbr_state, 0, (size_t)batch->n_replicas * sizeof(int32_t), s));
     if (!forces_valid && (rc = qmc::hmc_forces(pd, *batch, forces, workspace, s, g_err, sizeof(g_err)))) return rc;
     qmc::FbmcArgs a;
     std::memset(&a, 0, sizeof(a));
@@ -515,6 +512,8 @@ struct qmc_batch_handle {
     bool momenta;
     std::vector<void *> ptr;       // one per field (QMC_FIELD_*), nullptr if absent
     std::vector<size_t> bytes;
+    void *rows = nullptr, *rows_ref = nullptr, *rows_state = nullptr;  // neighbour rows (qmc_batch_enable_rows)
+    int32_t row_words = 0;
 };
 
 int qmc_batch_create(int32_t n_replicas, int32_t n_max, int32_t with_momenta, int32_t n_label_tables, qmc_batch_handle_t **out) {
@@ -523,7 +522,11 @@ int qmc_batch_create(int32_t n_replicas, int32_t n_max, int32_t with_momenta, in
         return fail(QMC_ERR_INVALID, "bad batch dimensions");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(QMC_ERR_NO_DEVICE, "no CUDA device: there is no CPU fallback");
-    auto *h = new qmc_batch_handle{n_replicas, n_max, n_label_tables, with_momenta != 0, {}, {}};
+    auto *h = new qmc_batch_handle;
+    h->R = n_replicas;
+    h->N = n_max;
+    h->n_tables = n_label_tables;
+    h->momenta = with_momenta != 0;
     const size_t R = (size_t)n_replicas, N = (size_t)n_max;
     const size_t sizes[QMC_FIELD_LABELS0] = {R * 3 * N * 8, R * 9 * 8, R * 4, R * 8, R * 8, R * N * 8, R * N * 8,
                                              with_momenta ? R * 3 * N * 8 : 0, with_momenta ? R * 8 : 0, R * 4,
@@ -555,6 +558,9 @@ int qmc_batch_create(int32_t n_replicas, int32_t n_max, int32_t with_momenta, in
 int qmc_batch_destroy(qmc_batch_handle_t *h) {
     if (!h) return QMC_OK;
     for (void *p : h->ptr) cudaFree(p);
+    cudaFree(h->rows);
+    cudaFree(h->rows_ref);
+    cudaFree(h->rows_state);
     delete h;
     return QMC_OK;
 }
@@ -573,6 +579,8 @@ int qmc_batch_upload(qmc_batch_handle_t *h, int32_t field, const void *host, int
     if (!host) return fail(QMC_ERR_INVALID, "host pointer is NULL");
     if ((rc = batch_field(h, field, bytes, &p))) return rc;
     CUDA_TRY(cudaMemcpy(p, host, (size_t)bytes, cudaMemcpyHostToDevice));
+    if (h->rows_state && (field == QMC_FIELD_POS || field == QMC_FIELD_CELL || field == QMC_FIELD_N_ATOMS))
+        CUDA_TRY(cudaMemset(h->rows_state, 0, (size_t)h->R * 4));  // the rows no longer describe these positions
     return QMC_OK;
 }
 
@@ -602,6 +610,34 @@ int qmc_batch_view(qmc_batch_handle_t *h, qmc_batch_t *out) {
     out->counters = (int64_t *)h->ptr[QMC_FIELD_COUNTERS];
     out->status = (int32_t *)h->ptr[QMC_FIELD_STATUS];
     out->pair_evals = (int64_t *)h->ptr[QMC_FIELD_PAIR_EVALS];
+    out->nbr_rows = (uint32_t *)h->rows;
+    out->nbr_ref = (double *)h->rows_ref;
+    out->nbr_state = (int32_t *)h->rows_state;
+    out->nbr_row_cap = h->row_words;
+    return QMC_OK;
+}
+
+int qmc_batch_enable_rows(qmc_batch_handle_t *h, const qmc_potential_t *pot) {
+    if (!h || !pot) return fail(QMC_ERR_INVALID, "NULL argument");
+    if (h->rows) return QMC_OK;
+    const int32_t words = qmc_nbr_row_words(pot, h->N);
+    if (words < 0) return words;
+    const size_t R = (size_t)h->R, N = (size_t)h->N;
+    void *rows = nullptr, *ref = nullptr, *state = nullptr;
+    cudaError_t e = cudaMalloc(&rows, R * N * words * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&ref, R * 8 * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&state, R * 4);
+    if (e == cudaSuccess) e = cudaMemset(state, 0, R * 4);
+    if (e != cudaSuccess) {
+        cudaFree(rows);
+        cudaFree(ref);
+        cudaFree(state);
+        return fail(QMC_ERR_CUDA, "device allocation of the neighbour rows failed: %s", cudaGetErrorString(e));
+    }
+    h->rows = rows;
+    h->rows_ref = ref;
+    h->rows_state = state;
+    h->row_words = words;
     return QMC_OK;
 }
 
@@ -629,9 +665,10 @@ int qmc_sweep_host(const qmc_potential_t *pot, const qmc_batch_t *h, const qmc_m
     auto cleanup = [&]() { for (void *p : owned) cudaFree(p); };
     qmc_batch_t d = *h;
     d.cells_uniform = 0;
-    d.pair_cache = nullptr;
-    d.pair_pending = nullptr;
-    d.pair_cache_valid = 0;
+    d.nbr_rows = nullptr;
+    d.nbr_ref = nullptr;
+    d.nbr_state = nullptr;
+    d.nbr_row_cap = 0;
     int rc = QMC_OK;
 #define UP(field, bytes, src) if (rc == QMC_OK) rc = dev_alloc(bytes, src, (void **)&d.field)
     UP(pos, R * 3 * N * 8, h->pos);
@@ -643,14 +680,25 @@ int qmc_sweep_host(const qmc_potential_t *pot, const qmc_batch_t *h, const qmc_m
     UP(eatom, R * N * 8, nullptr);
     UP(counters, R * QMC_MAX_MOVES * 3 * 8, h->counters);
     UP(status, R * 4, nullptr);
-    if (h->n_exchange) UP(n_exchange, R * 4, h->n_exchange);
+    UP(n_exchange, R * 4, h->n_exchange);  // (zeros if the caller has none: the general kernels read and write it)
     d.momenta = nullptr;
     d.kinetic = nullptr;
     d.pair_evals = nullptr;
     if (h->pair_evals) UP(pair_evals, R * 8, h->pair_evals);
     std::vector<qmc_move_t> mv(moves_host, moves_host + n_moves);
-    for (int m = 0; m < n_moves && rc == QMC_OK; ++m)
-        if (moves_host[m].labels) rc = dev_alloc(R * N * 4, moves_host[m].labels, (void **)&mv[m].labels);
+    // one device table per DISTINCT host label array: the sub-moves of a composite must share theirs (qmc_sweep checks the
+    // pointers), and moves that share a host array must not overwrite each other on the way back
+    std::map<const int32_t *, int32_t *> tables;
+    for (int m = 0; m < n_moves && rc == QMC_OK; ++m) {
+        if (!moves_host[m].labels) continue;
+        auto it = tables.find(moves_host[m].labels);
+        if (it == tables.end()) {
+            int32_t *p = nullptr;
+            rc = dev_alloc(R * N * 4, moves_host[m].labels, (void **)&p);
+            it = tables.emplace(moves_host[m].labels, p).first;
+        }
+        mv[m].labels = it->second;
+    }
     qmc_trace_t tr;
     std::memset(&tr, 0, sizeof(tr));
     const size_t T = R * (size_t)n_attempts;
@@ -680,8 +728,7 @@ int qmc_sweep_host(const qmc_potential_t *pot, const qmc_batch_t *h, const qmc_m
     down(h->eatom, d.eatom, R * N * 8);
     if (h->n_exchange) down(h->n_exchange, d.n_exchange, R * 4);
     if (h->pair_evals) down(h->pair_evals, d.pair_evals, R * 8);
-    for (int m = 0; m < n_moves; ++m)
-        if (moves_host[m].labels) down(moves_host[m].labels, mv[m].labels, R * N * 4);
+    for (const auto &t : tables) down(const_cast<int32_t *>(t.first), t.second, R * N * 4);
     if (trace_host) {
         down(trace_host->move, tr.move, T);
         down(trace_host->accepted, tr.accepted, T);

@@ -60,6 +60,26 @@ int CAT(sweep_block_launch_, INST_POT, _, INST_NS)(int feat, const SweepArgs &a,
     return launch_block_feat<F_CELLVAR | F_CELL | F_LABELS | F_EXCHANGE>(a, s, err, errn);
 }
 
+template <int FEAT>
+static inline int launch_rows_feat(const SweepArgs &a, const RowArgs &ra, cudaStream_t s, char *err, size_t errn) {
+    using LY = LayoutR<INST_POT, INST_NS>;
+    static_assert(LY::FITS, "replica does not fit in shared memory");
+    constexpr size_t smem = (size_t)LY::WARPS * LY::BYTES;
+    auto kernel = sweep_rows_kernel<INST_POT, INST_NS, FEAT>;
+    int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
+    if (rc) return rc;
+    kernel<<<(a.b.n_replicas + LY::WARPS - 1) / LY::WARPS, LY::WARPS * 32, smem, s>>>(a, ra);
+    return report(cudaGetLastError(), "row-based sweep kernel launch", err, errn);
+}
+
+// row-based variant (csrc/sweep_rows.cuh); instantiated feature sets: canonical, per-replica cells, + cell moves, + label tables
+int CAT(sweep_rows_launch_, INST_POT, _, INST_NS)(int feat, const SweepArgs &a, const RowArgs &ra, cudaStream_t s, char *err, size_t errn) {
+    if (feat == 0) return launch_rows_feat<0>(a, ra, s, err, errn);
+    if ((feat & ~F_CELLVAR) == 0) return launch_rows_feat<F_CELLVAR>(a, ra, s, err, errn);
+    if ((feat & ~(F_CELLVAR | F_CELL)) == 0) return launch_rows_feat<F_CELLVAR | F_CELL>(a, ra, s, err, errn);
+    return launch_rows_feat<F_CELLVAR | F_CELL | F_LABELS>(a, ra, s, err, errn);
+}
+
 int CAT(energy_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn) {
     using LY = Layout<INST_POT, INST_NS>;
     constexpr size_t smem = (size_t)LY::WARPS * LY::BYTES;
@@ -70,32 +90,5 @@ int CAT(energy_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, long long *pai
     kernel<<<grid, LY::WARPS * 32, smem, s>>>(a, pair_count);
     return report(cudaGetLastError(), "energy kernel launch", err, errn);
 }
-
-#if INST_POT == 0 && INST_NS <= 128
-#define CATC_(a, b) a##b
-#define CATC(a, b) CATC_(a, b)
-int CATC(sweep_cached_launch_, INST_NS)(const SweepArgs &a, cudaStream_t s, char *err, size_t errn) {
-    using LY = LayoutC<INST_NS>;
-    static_assert(LY::FITS, "replica does not fit in shared memory");
-    constexpr size_t smem = (size_t)LY::WARPS * LY::BYTES;
-    auto kernel = sweep_cached_kernel<INST_NS>;
-    int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
-    if (rc) return rc;
-    const int grid = (a.b.n_replicas + LY::WARPS - 1) / LY::WARPS;
-    kernel<<<grid, LY::WARPS * 32, smem, s>>>(a);
-    return report(cudaGetLastError(), "cached sweep kernel launch", err, errn);
-}
-
-int CATC(energy_cached_launch_, INST_NS)(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn) {
-    using LY = LayoutC<INST_NS>;
-    constexpr size_t smem = (size_t)LY::WARPS * LY::BYTES;
-    auto kernel = energy_cached_kernel<INST_NS>;
-    int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
-    if (rc) return rc;
-    const int grid = (a.b.n_replicas + LY::WARPS - 1) / LY::WARPS;
-    kernel<<<grid, LY::WARPS * 32, smem, s>>>(a, pair_count);
-    return report(cudaGetLastError(), "cached energy kernel launch", err, errn);
-}
-#endif
 
 }  // namespace qmc

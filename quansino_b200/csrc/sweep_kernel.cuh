@@ -45,10 +45,6 @@ struct SweepArgs {
     unsigned long long seed, attempt_base;
     int n_attempts;
     int has_trace;
-    // dynamic work distribution of the warp-per-replica kernel: items = (chunk of attempts, replica), taken in order from a
-    // global counter; done[r] = number of finished chunks of replica r (a chunk waits for its predecessor)
-    int chunk_len, n_chunks;
-    int *work_counter, *done;
     double *atom_energies;  // energy kernel only: device [R][n_max] per-atom energies, or nullptr
     qmc_trace_t tr;
 };
@@ -412,8 +408,8 @@ __device__ __forceinline__ Draws read_draws(const RV &R, int a, bool need_coin) 
 }
 
 // per-replica cell constants in shared memory (F_CELLVAR); returns false if an edge is below the cutoff
-template <class LY>
-__device__ __forceinline__ bool store_cell(const Rep<LY> &R, const double diag[3], const int pbc[3], double cut_pre, int lane) {
+template <class RV>
+__device__ __forceinline__ bool store_cell(const RV &R, const double diag[3], const int pbc[3], double cut_pre, int lane) {
     CellArgs c;
     const bool ok = cell_constants(diag, pbc, cut_pre, c);
     if (lane == 0) {
@@ -446,29 +442,10 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
         R.b = reinterpret_cast<double *>(__cvta_shared_to_generic((size_t)sb));
     }
     const CellView<LY, UNIFORM> C{&a.cell, R.b + LY::CELLC};
-    const bool dynamic = a.n_chunks > 1;
-    // Work items.  Static: warp w of the grid owns replica w for the whole launch.  Dynamic: (chunk, replica) items are taken
-    // in order from a global counter, so that warps the hardware scheduler favours take over work from the ones it starves
-    // (measured: per-replica time 0.77 .. 1.39 ms inside one launch, profiles/r1_g_dynamic_chunks.md).
-    for (int item = blockIdx.x * WARPS + warp;; ) {
-        if (dynamic) {
-            if (lane == 0) item = atomicAdd(a.work_counter, 1);
-            item = __shfl_sync(FULL, item, 0);
-            if (item >= a.n_chunks * a.b.n_replicas) break;
-        } else if (item >= a.b.n_replicas) {
-            break;
-        }
-        const int r = dynamic ? item % a.b.n_replicas : item;
-        const int chunk = dynamic ? item / a.b.n_replicas : 0;
-        if (dynamic && chunk > 0) {  // the previous chunk of this replica was taken earlier by a running warp: wait for it
-            if (lane == 0)
-                while (*reinterpret_cast<volatile int *>(a.done + r) < chunk) __nanosleep(100);
-            __syncwarp();
-            __threadfence();
-        }
-        const int k_begin = dynamic ? chunk * a.chunk_len : 0;
-        const int k_end = dynamic ? min(k_begin + a.chunk_len, a.n_attempts) : a.n_attempts;
-    // ---- load the replica (L1 bypassed: another SM may have written the state in an earlier chunk) ----
+    const int r = blockIdx.x * WARPS + warp;  // warp w of the grid owns replica w for the whole launch
+    if (r >= a.b.n_replicas) return;
+    const int k_begin = 0, k_end = a.n_attempts;
+    // ---- load the replica ----
     R.n = __ldcg(a.b.n_atoms + r);
     double *gx = a.b.pos + (size_t)r * 3 * nmax, *gy = gx + nmax, *gz = gy + nmax;
     double *gs = POT == QMC_POT_EMT ? a.b.sigma1 + (size_t)r * nmax : nullptr;
@@ -1063,11 +1040,6 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
     if (a.b.pair_evals) {
         for (int o = 16; o > 0; o >>= 1) n_pairs += __shfl_xor_sync(FULL, n_pairs, o);
         if (lane == 0) a.b.pair_evals[r] += n_pairs;
-    }
-        if (!dynamic) break;
-        __threadfence();  // the stored state is visible before the chunk is published
-        __syncwarp();
-        if (lane == 0) atomicExch(a.done + r, chunk + 1);
     }
 }
 

@@ -76,13 +76,13 @@ class MonteCarlo:
         restart_file=None,
         logging_interval: int = 1,
         logging_mode: str = "a",
-        pair_cache: bool | None = None,
+        neighbour_rows: bool | None = None,
     ) -> None:
         self.moves: dict[str, MoveStorage] = {}
         self.max_cycles = max_cycles
         self.acceptance_rate: np.ndarray | float = 0.0
         self.move_history: list[tuple[str, Any]] = []
-        self._seed = int(seed) if seed else int.from_bytes(os.urandom(8), "little")
+        self._seed = int(seed) if seed is not None else int.from_bytes(os.urandom(8), "little")  # 0 is a valid seed (mc/driver.py:77-78)
         self.logging_interval = logging_interval
         self.logging_mode = logging_mode
         self.step_count = 0
@@ -98,7 +98,7 @@ class MonteCarlo:
             atoms = BatchedAtoms.from_ase(atoms, replicas=replicas if not isinstance(atoms, (list, tuple)) else None, calc=calc)
         self.atoms = atoms
         self.batch = ReplicaBatch(
-            atoms, calc=calc, device=device, replica_offset=replica_offset, with_momenta=self.needs_momenta, pair_cache=pair_cache
+            atoms, calc=calc, device=device, replica_offset=replica_offset, with_momenta=self.needs_momenta, neighbour_rows=neighbour_rows
         )
         self.context = self.default_context(atoms, self.batch, self._seed)
         # default observers (mc/driver.py:42-63, 196-262): created from a path / stream, or attached as given
@@ -155,14 +155,10 @@ class MonteCarlo:
     def _lower(self, names: list[str]):
         """POD move table for the given (available) move names; label tables are created once per move.  A composite
         move occupies a chain of consecutive entries; ``self._slots[name]`` is the entry of its head (counters, trace)."""
-        key = tuple(names)
-        if self._lowered is not None and self._lowered[0] == key:
-            for n in names:  # probabilities and forced counts may be changed between steps (mc/core.py:331-347)
-                self._lowered[1][self._slots[n]].probability = float(self.moves[n].probability)
-                self._lowered[1][self._slots[n]].minimum_count = int(self.moves[n].minimum_count)
-            self._lowered[1][0].max_cycles = int(self.max_cycles)
-            return self._lowered[1], self._lowered[2]
-        n_atoms = self.batch.n_atoms.cpu().numpy()
+        # The table is lowered afresh at EVERY launch: the reference re-reads step sizes, operations, probabilities, Verlet
+        # parameters and labels on every call, so changes made between runs must reach the kernel (a few small structs).
+        # Only the device label tables persist (they are the labels' state once exchange moves re-label them).
+        n_atoms = None  # fetched (one device sync) only when a label table has to be created
         any_exchange = any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE for n in names)
         entries, keep, slots = [], [], {}
         for n in names:
@@ -180,6 +176,12 @@ class MonteCarlo:
             if m.minimum_count and m.type == _lib.MOVE_HMC:
                 raise NotImplementedError("forced Hamiltonian moves are not available on the GPU path")
             if m.type in (_lib.MOVE_DISPLACEMENT, _lib.MOVE_EXCHANGE):
+                version = self._labels_version(st.move)
+                if hasattr(st, "_label_tensor") and getattr(st, "_label_version", version) != version:
+                    del st._label_tensor  # set_labels() was called since the table was uploaded
+                st._label_version = version
+                if n_atoms is None and (not hasattr(st, "_label_tensor") or (st._label_tensor is None and any_exchange)):
+                    n_atoms = self.batch.n_atoms.cpu().numpy()
                 if not hasattr(st, "_label_tensor"):
                     if any_exchange or not st.move.is_identity(n_atoms):
                         lab = st.move.validated_labels(self.batch.R, self.batch.n_max, n_atoms)
@@ -212,8 +214,13 @@ class MonteCarlo:
             arr[i] = m
         arr[0].max_cycles = int(self.max_cycles)
         self._slots = slots
-        self._lowered = (key, arr, keep)
+        self._lowered = (tuple(names), arr, keep)  # keeps the ctypes array and the label tensors alive during the launch
         return arr, keep
+
+    @staticmethod
+    def _labels_version(move) -> tuple:
+        subs = getattr(move, "moves", None) or [move]
+        return tuple(getattr(m, "_labels_version", 0) for m in subs)
 
     def labels(self, name: str) -> np.ndarray | None:
         """Current label table [R][n_max] of a displacement / exchange move (None = arange)."""
@@ -337,17 +344,13 @@ class MonteCarlo:
                 "moved": torch.zeros((R, n_attempts), dtype=torch.int32, device=b.device),
             }
             tr = _lib.Trace(*[bufs[k].data_ptr() for k in ("move", "accepted", "energy", "delta", "moved")])
-        # the pair-term cache follows displacement-only sweeps of a fixed cell; everything else leaves it stale
-        keeps_cache = (
-            b.pair_cache is not None and b.cells_uniform and os.environ.get("QMC_FORCE_KERNEL") in (None, "cached")
-            and all(m.type == _lib.MOVE_DISPLACEMENT and not m.labels and not m.chain and m.repeat <= 1 for m in moves)
-        )  # fmt: skip
-        if keeps_cache and not b.pair_cache_valid:
-            b.energy_full()
-        if not keeps_cache:
-            b.pair_cache_valid = False
+        use_rows = self._use_rows(moves, n_attempts)
+        if use_rows:
+            b.ensure_rows()
+        else:
+            b.rows_valid = False  # whatever runs now moves atoms without looking at the rows
         with torch.cuda.device(b.device):
-            bs = b.struct()
+            bs = b.struct(with_rows=use_rows)
             if moves[0].type == _lib.MOVE_HMC:
                 if len(names) != 1:
                     raise NotImplementedError("Hamiltonian moves cannot be mixed with other moves in one step on the GPU path")
@@ -366,6 +369,33 @@ class MonteCarlo:
             b.cells_uniform = False  # accepted cell moves make the cells replica-specific
         if bufs is not None:
             self.last_trace = {k: v.cpu().numpy() for k, v in bufs.items()}
+
+    rows_min_sweeps: ClassVar[float] = 2.0  # auto mode: build rows only for launches of at least this many attempts per atom
+
+    def _use_rows(self, moves, n_attempts: int) -> bool:
+        """Whether this launch runs the row-based sweep kernel (``csrc/sweep_rows.cuh``): tables of single-atom displacement
+        moves (Ball / Box / Sphere, steps within half the skin) and cell moves, on batches whose cells leave room for cutoff +
+        skin.  ``neighbour_rows=True`` / ``False`` (or ``QMC_FORCE_KERNEL``) decide; by default the rows are used when they are
+        already built or when the launch is long enough to pay for building them."""
+        b = self.batch
+        force = os.environ.get("QMC_FORCE_KERNEL")
+        want = b.want_rows if force is None else (True if force == "rows" else False)
+        if want is False or not b.rows_possible():
+            return False
+        skin = b.nbr_skin or _lib.NBR_SKIN_DEFAULT
+        for m in moves:
+            if m.type == _lib.MOVE_CELL:
+                continue
+            if m.type != _lib.MOVE_DISPLACEMENT or m.op not in (_lib.OP_BALL, _lib.OP_BOX, _lib.OP_SPHERE):
+                return False
+            if m.chain or m.repeat > 1 or m.n_extra_ops or m.minimum_count:
+                return False
+            if abs(m.step) * (3.0**0.5 if m.op == _lib.OP_BOX else 1.0) * (1.0 + 1e-9) > 0.5 * skin:
+                return False
+        if want:
+            return True
+        built = b.nbr_rows is not None and b.rows_valid
+        return built or n_attempts >= self.rows_min_sweeps * b.n_max
 
     # -- results ------------------------------------------------------------------------------------
     def counters(self) -> np.ndarray:

@@ -92,7 +92,7 @@ class ForceBias(MonteCarlo):
             )  # fmt: skip
         _lib.check(rc)
         self._forces_valid = True
-        b.pair_cache_valid = False
+        b.rows_valid = False
         b.raise_on_status()
         return
         yield  # pragma: no cover

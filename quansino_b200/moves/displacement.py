@@ -38,6 +38,8 @@ class DisplacementMove(BaseMove):
     def set_labels(self, new_labels) -> None:
         self.labels = np.asarray(new_labels)
         self.unique_labels = np.unique(self.labels[self.labels >= 0])
+        # the driver uploads the label table again when this changes (moves/displacement.py:173-184 takes effect at once)
+        self._labels_version = getattr(self, "_labels_version", 0) + 1
 
     @property
     def default_operation(self):

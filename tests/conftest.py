@@ -27,11 +27,11 @@ def cuda_lib():
     return _lib.load()
 
 
-@pytest.fixture(params=["warp", "block", "cached"])
+@pytest.fixture(params=["warp", "block", "rows"])
 def kernel_variant(request, monkeypatch):
-    """Run a sweep test through both organisations of the sweep kernel: one warp per replica (csrc/sweep_kernel.cuh)
-    one CTA per replica (csrc/sweep_block.cuh), and the canonical fast path with the HBM pair-term cache
-    (csrc/sweep_cached.cuh; it only engages for displacement-only EMT sweeps, other tables run as "auto").  Without the
-    variable the library picks by batch size."""
+    """Run a sweep test through the organisations of the sweep kernel: one warp per replica with a brute-force scan
+    (csrc/sweep_kernel.cuh), one CTA per replica (csrc/sweep_block.cuh), and one warp per replica reading per-atom neighbour
+    rows (csrc/sweep_rows.cuh; it only engages for single-atom displacement / cell-move tables, other tables run as "auto").
+    Without the variable the library picks by table and batch size."""
     monkeypatch.setenv("QMC_FORCE_KERNEL", request.param)
     return request.param

@@ -23,7 +23,7 @@ def _driver(pos, cell, n, op, temperature=300.0, seed=1234, trace=True, **kw):
     atoms = BatchedAtoms(pos.copy(), cell, np.full(len(pos), n, dtype=np.int32), "Cu", (True, True, True), EMT())
     import os
 
-    kw.setdefault("pair_cache", os.environ.get("QMC_FORCE_KERNEL") == "cached")
+    kw.setdefault("neighbour_rows", os.environ.get("QMC_FORCE_KERNEL") == "rows")
     mc = Canonical(atoms, temperature=temperature, seed=seed, trace=trace, default_displacement_move=DisplacementMove(np.arange(n), op), **kw)
     return mc
 
@@ -326,7 +326,7 @@ def test_library_owned_batch_handle(cuda_lib):
         _lib.check(lib.qmc_sweep(C.byref(pot), C.byref(b), move, 1, 1234, 0, sweeps * n, None, None))
         got_pos = down(_lib.FIELD_POS, np.zeros((R, 3, n))).transpose(0, 2, 1)
         assert np.array_equal(got_pos, want_pos)
-        if os.environ.get("QMC_FORCE_KERNEL") == "cached":  # the torch-backed run used the pair-term cache: another summation order
+        if os.environ.get("QMC_FORCE_KERNEL") == "rows":  # the torch-backed run read neighbour rows: image vectors round differently (<= 1 ulp)
             np.testing.assert_allclose(down(_lib.FIELD_ENERGY, np.zeros(R)), want_e, rtol=1e-13)
         else:
             assert np.array_equal(down(_lib.FIELD_ENERGY, np.zeros(R)), want_e)

@@ -22,13 +22,13 @@ def test_canonical_capacity_classes(cuda_lib, repeat, n_attempts):
     from quansino_b200.moves import DisplacementMove
     import os
 
-    if repeat == 2 and os.environ.get("QMC_FORCE_KERNEL") in ("block", "cached"):
-        pytest.skip("the CTA-per-replica and pair-cache kernels are sized for cells of >= 64 atoms (never selected below 256 / on request only)")
+    if repeat == 2 and os.environ.get("QMC_FORCE_KERNEL") == "block":
+        pytest.skip("the CTA-per-replica kernel is sized for cells of >= 64 atoms (never selected below 256 / on request only)")
     R = 3
     pos, cell, n = cu_replicas(repeat, R, seed=40 + repeat)
     atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
     mc = Canonical(atoms, temperature=400.0, seed=700 + repeat, trace=True, max_cycles=n_attempts, resync_interval=0,
-                   pair_cache=os.environ.get("QMC_FORCE_KERNEL") == "cached",
+                   neighbour_rows=os.environ.get("QMC_FORCE_KERNEL") == "rows",
                    default_displacement_move=DisplacementMove(np.arange(n), operations.Ball(0.12)))  # fmt: skip
     e0 = mc.batch.energy_full().cpu().numpy().copy()
     mc.run(1)
@@ -84,8 +84,6 @@ def test_several_waves_of_replicas(cuda_lib):
     from quansino_b200.moves import DisplacementMove
     import os
 
-    if os.environ.get("QMC_FORCE_KERNEL") == "cached":
-        pytest.skip("the pair-term cache of 10 000 replicas is a 3.7 GB allocation; covered at smaller sizes")
     R = 10000
     pos, cell, n = cu_replicas(3, R, seed=3)
     atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
@@ -135,7 +133,7 @@ def test_cell_geometries(cuda_lib, case):
         pos += rng.integers(-3, 4, size=(R, n, 3)) * L  # every atom somewhere within +-3 cells
     atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", pbc, EMT())
     mc = Canonical(atoms, temperature=500.0, seed=99, trace=True, max_cycles=n_attempts, resync_interval=0,
-                   pair_cache=os.environ.get("QMC_FORCE_KERNEL") == "cached",
+                   neighbour_rows=os.environ.get("QMC_FORCE_KERNEL") == "rows",
                    default_displacement_move=DisplacementMove(np.arange(n), operations.Sphere(0.1)))  # fmt: skip
     mc.run(1)
     tr, out = mc.last_trace, mc.download()

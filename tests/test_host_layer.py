@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in sorted(declared):
         assert getattr(lib, name) is not None, name
-    assert lib.qmc_abi_version() == int(re.search(r"#define\s+QMC_ABI_VERSION\s+(\d+)", header).group(1)) == 7
+    assert lib.qmc_abi_version() == int(re.search(r"#define\s+QMC_ABI_VERSION\s+(\d+)", header).group(1)) == 8
 
 
 def test_struct_layouts_match_the_header():
