@@ -269,7 +269,7 @@ def run_native(args):
     atoms = BatchedAtoms(pos.copy(), cell, np.full(R, N_ATOMS, dtype=np.int32), "Cu", (True, True, True), EMT())
     mc = Canonical(
         atoms, temperature=TEMPERATURE, seed=SEED, device=device, replica_offset=rank * R, resync_interval=0,
-        neighbour_rows={"on": True, "off": False, "auto": None}[args.rows],
+        neighbour_rows={"on": True, "off": False, "auto": None}[args.rows], steps_per_launch=args.sweeps,
         default_displacement_move=DisplacementMove(np.arange(N_ATOMS), Ball(STEP_SIZE)),
     )  # fmt: skip
     lib = mc.batch.lib
@@ -289,9 +289,9 @@ def run_native(args):
     mc.validate_simulation()
     mc.max_steps = 10**12
     for _ in range(args.warmup):
-        for _ in mc.step():
+        for _ in mc.step(args.sweeps):
             pass
-        mc.step_count += 1
+        mc.step_count += args.sweeps
     pair0 = int(mc.batch.pair_evals.sum().item())
     acc0 = mc.batch.counters[:, 0, 1].sum().item()
     launches = 0
@@ -303,10 +303,10 @@ def run_native(args):
         for i in range(args.steps):
             flush.fill_(i & 0xFF)  # evict the replica state from L2 (untimed)
             starts[i].record()
-            for _ in mc.step():
+            for _ in mc.step(args.sweeps):
                 pass
             ends[i].record()
-            mc.step_count += 1
+            mc.step_count += args.sweeps
             launches += 1
         if dist is not None:  # observable reduction: sum of accepted moves and energies
             obs = torch.stack([mc.batch.counters[:, 0, 1].sum().double(), mc.batch.energy.sum()])
@@ -320,7 +320,7 @@ def run_native(args):
     ms_total = float(t.item())
     mc.batch.raise_on_status()
 
-    attempts_rank = R * N_ATOMS * args.steps
+    attempts_rank = R * N_ATOMS * args.steps * args.sweeps
     pairs_rank = int(mc.batch.pair_evals.sum().item()) - pair0
     accepted_rank = mc.batch.counters[:, 0, 1].sum().item() - acc0
     agg = torch.tensor([attempts_rank, pairs_rank, accepted_rank], dtype=torch.float64, device=device)
@@ -374,7 +374,7 @@ def run_native(args):
     m_per_attempt = cpu["embed_evals_per_attempt_local"] if cpu else 67.0
     flop_per_attempt = A_PAIR * p_per_attempt + A_EMBED * m_per_attempt
     launch_s = ms_total * 1e-3 / args.steps
-    achieved_tflops = flop_per_attempt * R * N_ATOMS / launch_s / 1e12  # per GPU, per launch
+    achieved_tflops = flop_per_attempt * R * N_ATOMS * args.sweeps / launch_s / 1e12  # per GPU, per launch
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -468,6 +468,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--replicas", type=int, default=4096, help="replicas per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sweeps", type=int, default=1, help="MonteCarlo steps (sweeps of 108 attempts per replica) fused into one launch = one bench step")
     ap.add_argument("--rows", default="on", choices=["on", "off", "auto"], help="neighbour rows (csrc/sweep_rows.cuh) in the sweep")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -97,11 +97,12 @@ struct Inst {
     int block_minb;  // CTAs (= replicas) of the block kernel one SM holds
     qmc::rows_launch_fn sweep_rows;
     int row_words;   // u32 words per neighbour row
+    int rows_wide_reps;  // replicas one SM holds with four warps per replica (0: not instantiated)
 };
 
 #define QMC_TABLE_ROW(POT, NS) \
     {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS, qmc::sweep_block_launch_##POT##_##NS, qmc::LayoutB<POT, NS>::REPS, \
-     qmc::sweep_rows_launch_##POT##_##NS, qmc::LayoutR<POT, NS>::ROWW},
+     qmc::sweep_rows_launch_##POT##_##NS, qmc::LayoutR<POT, NS, 1>::ROWW, NS >= 256 ? qmc::LayoutR<POT, NS, 4>::REPS : 0},
 const Inst g_inst[2][7] = {{QMC_FOR_EACH_NS(QMC_TABLE_ROW, 0)}, {QMC_FOR_EACH_NS(QMC_TABLE_ROW, 1)}};
 
 const Inst *find_inst(int kind, int n_max) {
@@ -374,7 +375,11 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
             if (batch->nbr_row_cap != inst->row_words)
                 return fail(QMC_ERR_INVALID, "batch.nbr_row_cap is %d, the row-based kernel of this capacity class uses %d words (qmc_nbr_row_words)",
                             batch->nbr_row_cap, inst->row_words);
-            return inst->sweep_rows(feat, a, ra, (cudaStream_t)stream, g_err, sizeof(g_err));
+            // four warps per replica when one warp per replica would leave most warp slots of the GPU empty (C3: 1024 replicas of
+            // 500 atoms = 7 per SM)
+            int wide = inst->rows_wide_reps > 0 && batch->n_replicas <= 2 * sms * inst->rows_wide_reps;
+            if (const char *w = std::getenv("QMC_ROWS_WIDE")) wide = inst->rows_wide_reps > 0 && std::atoi(w) != 0;
+            return inst->sweep_rows(feat, wide, a, ra, (cudaStream_t)stream, g_err, sizeof(g_err));
         }
     }
     // every other kernel moves atoms without looking at the rows: they are stale from here on

@@ -60,24 +60,31 @@ int CAT(sweep_block_launch_, INST_POT, _, INST_NS)(int feat, const SweepArgs &a,
     return launch_block_feat<F_CELLVAR | F_CELL | F_LABELS | F_EXCHANGE>(a, s, err, errn);
 }
 
-template <int FEAT>
+template <int FEAT, int NW>
 static inline int launch_rows_feat(const SweepArgs &a, const RowArgs &ra, cudaStream_t s, char *err, size_t errn) {
-    using LY = LayoutR<INST_POT, INST_NS>;
+    using LY = LayoutR<INST_POT, INST_NS, NW>;
     static_assert(LY::FITS, "replica does not fit in shared memory");
-    constexpr size_t smem = (size_t)LY::WARPS * LY::BYTES;
-    auto kernel = sweep_rows_kernel<INST_POT, INST_NS, FEAT>;
+    constexpr size_t smem = (size_t)LY::REPS * LY::BYTES;
+    auto kernel = sweep_rows_kernel<INST_POT, INST_NS, FEAT, NW>;
     int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
     if (rc) return rc;
-    kernel<<<(a.b.n_replicas + LY::WARPS - 1) / LY::WARPS, LY::WARPS * 32, smem, s>>>(a, ra);
+    kernel<<<(a.b.n_replicas + LY::REPS - 1) / LY::REPS, LY::THREADS, smem, s>>>(a, ra);
     return report(cudaGetLastError(), "row-based sweep kernel launch", err, errn);
 }
 
-// row-based variant (csrc/sweep_rows.cuh); instantiated feature sets: canonical, per-replica cells, + cell moves, + label tables
-int CAT(sweep_rows_launch_, INST_POT, _, INST_NS)(int feat, const SweepArgs &a, const RowArgs &ra, cudaStream_t s, char *err, size_t errn) {
-    if (feat == 0) return launch_rows_feat<0>(a, ra, s, err, errn);
-    if ((feat & ~F_CELLVAR) == 0) return launch_rows_feat<F_CELLVAR>(a, ra, s, err, errn);
-    if ((feat & ~(F_CELLVAR | F_CELL)) == 0) return launch_rows_feat<F_CELLVAR | F_CELL>(a, ra, s, err, errn);
-    return launch_rows_feat<F_CELLVAR | F_CELL | F_LABELS>(a, ra, s, err, errn);
+// row-based variant (csrc/sweep_rows.cuh), `wide` = four warps per replica; instantiated feature sets: canonical, per-replica
+// cells, + cell moves, + label tables
+int CAT(sweep_rows_launch_, INST_POT, _, INST_NS)(int feat, int wide, const SweepArgs &a, const RowArgs &ra, cudaStream_t s, char *err, size_t errn) {
+#if INST_NS >= 256
+    if (wide) {
+        if ((feat & ~(F_CELLVAR | F_CELL)) == 0) return launch_rows_feat<F_CELLVAR | F_CELL, 4>(a, ra, s, err, errn);
+        return launch_rows_feat<F_CELLVAR | F_CELL | F_LABELS, 4>(a, ra, s, err, errn);
+    }
+#endif
+    if (feat == 0) return launch_rows_feat<0, 1>(a, ra, s, err, errn);
+    if ((feat & ~F_CELLVAR) == 0) return launch_rows_feat<F_CELLVAR, 1>(a, ra, s, err, errn);
+    if ((feat & ~(F_CELLVAR | F_CELL)) == 0) return launch_rows_feat<F_CELLVAR | F_CELL, 1>(a, ra, s, err, errn);
+    return launch_rows_feat<F_CELLVAR | F_CELL | F_LABELS, 1>(a, ra, s, err, errn);
 }
 
 int CAT(energy_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn) {

@@ -370,7 +370,7 @@ class MonteCarlo:
         if bufs is not None:
             self.last_trace = {k: v.cpu().numpy() for k, v in bufs.items()}
 
-    rows_min_sweeps: ClassVar[float] = 2.0  # auto mode: build rows only for launches of at least this many attempts per atom
+    rows_min_atoms: ClassVar[int] = 256  # auto mode: neighbour rows from this capacity on (profiles/r2_a_rows.md)
 
     def _use_rows(self, moves, n_attempts: int) -> bool:
         """Whether this launch runs the row-based sweep kernel (``csrc/sweep_rows.cuh``): tables of single-atom displacement
@@ -394,8 +394,7 @@ class MonteCarlo:
                 return False
         if want:
             return True
-        built = b.nbr_rows is not None and b.rows_valid
-        return built or n_attempts >= self.rows_min_sweeps * b.n_max
+        return b.n_max >= self.rows_min_atoms
 
     # -- results ------------------------------------------------------------------------------------
     def counters(self) -> np.ndarray:
