@@ -4,12 +4,17 @@
 Contract (see the task prompt): ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line.
 
 * workload: BASELINE.json configs[1] -- 4096 replicas per GPU of fcc Cu 3x3x3 (108 atoms), ASE-EMT semantics,
-  300 K, ``DisplacementMove(arange(108), Ball(0.1))``, ``max_cycles = 108``.  One "step" = one ``MonteCarlo.step``
-  for every replica = 108 attempts per replica = one launch of the sweep kernel.
+  300 K, ``DisplacementMove(arange(108), Ball(0.1))``, ``max_cycles = 108``.  One "step" = ``--sweeps`` (default 10)
+  ``MonteCarlo.step`` s for every replica fused into ONE launch of the sweep kernel (what ``run()`` does between two
+  observer calls, ``steps_per_launch``) = 1080 attempts per replica.
 * ``value``: move attempts / s summed over all replicas and GPUs, state resident in HBM (CUDA events around each
   step on the launching stream, L2 flushed between steps, max over ranks).
 * ``e2e``: the same metric through the public driver with HOST buffers: every step uploads the positions from
-  pinned host memory, primes the caches, runs the step and reads positions + energies back.
+  pinned host memory, primes the caches, runs the step and reads positions + energies back; the batch is driven
+  as four replica chunks on four streams so that the copies of one chunk overlap the kernels of the others.
+* ``pt``: a short leg of BASELINE.json configs[4] -- 64-temperature parallel tempering of 2048-atom Cu under HMC
+  (Verlet 100 x 1 fs), replicas sharded over the ranks, one NCCL all-gather + swap kernel per round: the only real
+  collective of the path, under the same clock as the headline.
 * ``roofline``: the sweep kernel against the FP64 pipe (this path is transcendental-heavy FP64 with the replica
   state resident in shared memory; HBM traffic is ~80 B per attempt).  ``peak`` is a register-resident DFMA loop
   measured in the same process; the HBM figure is reported beside it in ``roofline_hbm``.
@@ -36,6 +41,7 @@ if str(ROOT) not in sys.path:
     sys.path.insert(0, str(ROOT))
 
 N_ATOMS = 108
+E2E_CHUNKS = 4
 TEMPERATURE = 300.0
 STEP_SIZE = 0.1
 SEED = 20261019
@@ -239,6 +245,86 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------------
+def pt_leg(device, dist, rank, world, n_temperatures=64, repeat=8, n_steps=100, rounds=20, warmup=2):
+    """BASELINE.json configs[4] under the bench clock: 64-temperature parallel tempering of 2048-atom Cu (EMT) under HMC, the
+    replicas sharded over the ranks in contiguous blocks with the ladder spread so that every rank holds temperatures from the
+    whole range.  One round = one trajectory (Verlet 100 x 1 fs) per replica + `ReplicaExchange.exchange` (NCCL all-gather of the
+    energies and temperatures, swap kernel on every rank; configurations never move).  CUDA events around the timed rounds, max
+    over ranks; the checksums must not depend on the number of ranks."""
+    import torch
+
+    from quansino_b200 import EMT, BatchedAtoms
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.mc import HamiltonianCanonical
+    from quansino_b200.mc.tempering import ReplicaExchange, gather_replicas, shard, spread_ladder
+    from quansino_b200.moves import HamiltonianDisplacementMove
+    from quansino_b200.systems import fcc_cubic
+
+    offset, count = shard(n_temperatures, world, rank)
+    pos0, cell = fcc_cubic("Cu", repeat)
+    n = len(pos0)
+    rng = np.random.default_rng(5)
+    pos_all = pos0[None] + rng.normal(scale=0.03, size=(n_temperatures, n, 3))
+    ladder = 300.0 * 4.0 ** (np.arange(n_temperatures) / max(n_temperatures - 1, 1))  # geometric, 300 -> 1200 K
+    temps_all = spread_ladder(ladder)
+    atoms = BatchedAtoms(pos_all[offset : offset + count], cell, np.full(count, n, np.int32), "Cu", (True,) * 3, EMT())
+    mc = HamiltonianCanonical(
+        atoms, temperature=temps_all[offset : offset + count], max_cycles=1, seed=5, resync_interval=0, device=device, replica_offset=offset,
+        default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=1.0, max_steps=n_steps)),
+    )  # fmt: skip
+    pt = ReplicaExchange.for_driver(mc, n_global=n_temperatures)
+    mc.validate_simulation()
+    mc.max_steps = 10**12
+    ex_events = []
+
+    def one_round(timed):
+        for _ in mc.step():
+            pass
+        mc.step_count += 1
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        pt.exchange()
+        e1.record()
+        if timed:
+            ex_events.append((e0, e1))
+
+    for _ in range(warmup):  # neighbour lists, trajectory graph, NCCL channels
+        one_round(False)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(rounds):
+        one_round(True)
+    t1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(device)
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    mc.batch.raise_on_status()
+    e_all = gather_replicas(mc.batch.energy, pt.counts).cpu().numpy()
+    t_all = gather_replicas(mc.batch.temperature, pt.counts).cpu().numpy()
+    acc = gather_replicas(mc.batch.counters[:, 0, 1].double(), pt.counts).cpu().numpy()
+    w = np.arange(1, n_temperatures + 1)
+    return {
+        "workload": f"{n_temperatures} temperatures (300-1200 K, geometric) x {n}-atom Cu EMT, HMC Verlet {n_steps} x 1 fs, swap after every trajectory",
+        "trajectories_per_s": n_temperatures * rounds / (float(ms.item()) * 1e-3),
+        "ms_per_round": float(ms.item()) / rounds,
+        "exchange_ms_per_round": float(np.mean([a.elapsed_time(b) for a, b in ex_events])),
+        "rounds": rounds,
+        "ranks": world,
+        "swap_acceptance": pt.n_accepted / max(pt.n_pairs, 1),
+        "hmc_acceptance": float(acc.sum() / (n_temperatures * (rounds + warmup))),
+        "ladder_is_permutation": bool(np.array_equal(np.sort(t_all), np.sort(temps_all))),
+        "ladder_checksum": float(np.sum(t_all * w)),
+        "energy_checksum": float(np.sum(e_all * w)),
+        "collective": "all_gather of 2 x 64 doubles per round (NCCL)" if world > 1 else "none (one rank)",
+    }
+
+
 # measured once per round under ncu for the default workload (4096 replicas, 1 GPU); see profiles/
 NCU_DRAM_BYTES_PER_LAUNCH = 18.1e6
 
@@ -330,26 +416,47 @@ def run_native(args):
     value = attempts / (ms_total * 1e-3)
 
     # ---- e2e: host buffers in / out every step through the public driver ----
-    # two pinned buffers used in turn: the output of one step is the input of the next, on the host, without a host copy
-    host_bufs = [torch.from_numpy(np.ascontiguousarray(pos.transpose(0, 2, 1))).pin_memory(), None]
-    host_bufs[1] = torch.empty_like(host_bufs[0]).pin_memory()
-    host_e = torch.empty(R, dtype=torch.float64).pin_memory()
+    # The batch is driven as E2E_CHUNKS independent drivers (replica chunks) on separate streams: upload -> prime -> step ->
+    # download of one chunk overlap the kernels of the others (1024 replicas = 37 wide CTAs, four chunks fill the 148 SMs).
+    # Two pinned buffers per chunk used in turn: the output of one step is the input of the next, without a host copy.
+    del mc, flush
+    torch.cuda.empty_cache()
+    n_chunks = E2E_CHUNKS if R % E2E_CHUNKS == 0 else 1
+    Rc = R // n_chunks
+    chunks = []
+    for c in range(n_chunks):
+        sl = slice(c * Rc, (c + 1) * Rc)
+        at = BatchedAtoms(pos[sl].copy(), cell, np.full(Rc, N_ATOMS, dtype=np.int32), "Cu", (True, True, True), EMT())
+        st = torch.cuda.Stream(device)
+        with torch.cuda.stream(st):
+            drv = Canonical(
+                at, temperature=TEMPERATURE, seed=SEED, device=device, replica_offset=rank * R + c * Rc, resync_interval=0,
+                neighbour_rows={"on": True, "off": False, "auto": None}[args.rows], steps_per_launch=args.sweeps,
+                default_displacement_move=DisplacementMove(np.arange(N_ATOMS), Ball(STEP_SIZE)),
+            )  # fmt: skip
+            drv.max_steps = 10**12
+        bufs = [torch.from_numpy(np.ascontiguousarray(pos[sl].transpose(0, 2, 1))).pin_memory(), None]
+        bufs[1] = torch.empty_like(bufs[0]).pin_memory()
+        chunks.append({"mc": drv, "stream": st, "bufs": bufs, "e": torch.empty(Rc, dtype=torch.float64).pin_memory()})
     e2e_steps = max(3, min(args.steps, 20))
-    h2d = host_bufs[0].numel() * 8
-    d2h = host_bufs[1].numel() * 8 + host_e.numel() * 8
+    h2d = sum(ch["bufs"][0].numel() * 8 for ch in chunks)
+    d2h = sum(ch["bufs"][1].numel() * 8 + ch["e"].numel() * 8 for ch in chunks)
     turn = [0]
 
     def e2e_step():
-        src, dst = host_bufs[turn[0]], host_bufs[1 - turn[0]]
-        mc.batch.pos.copy_(src, non_blocking=True)
-        mc.batch.drop_rows()  # new positions: neighbour rows (if any) are rebuilt by the next launch
-        mc.batch.energy_full()
-        for _ in mc.step():
-            pass
-        mc.step_count += 1
-        dst.copy_(mc.batch.pos, non_blocking=True)
-        host_e.copy_(mc.batch.energy, non_blocking=True)
-        torch.cuda.current_stream(device).synchronize()
+        for ch in chunks:
+            src, dst, drv = ch["bufs"][turn[0]], ch["bufs"][1 - turn[0]], ch["mc"]
+            with torch.cuda.stream(ch["stream"]):
+                drv.batch.pos.copy_(src, non_blocking=True)
+                drv.batch.drop_rows()  # new positions: neighbour rows (if any) are rebuilt by the next launch
+                drv.batch.energy_full()
+                for _ in drv.step(args.sweeps):
+                    pass
+                drv.step_count += args.sweeps
+                dst.copy_(drv.batch.pos, non_blocking=True)
+                ch["e"].copy_(drv.batch.energy, non_blocking=True)
+        for ch in chunks:
+            ch["stream"].synchronize()
         turn[0] = 1 - turn[0]  # the next step reads what this step wrote
 
     for _ in range(2):
@@ -362,7 +469,13 @@ def run_native(args):
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if dist is not None:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * R * N_ATOMS * e2e_steps / float(dt.item())
+    e2e_value = world * R * N_ATOMS * args.sweeps * e2e_steps / float(dt.item())
+    for ch in chunks:
+        ch["mc"].batch.raise_on_status()
+    del chunks
+    torch.cuda.empty_cache()
+
+    pt = None if args.no_pt else pt_leg(device, dist, rank, world)
 
     if rank != 0:
         if dist is not None:
@@ -371,7 +484,10 @@ def run_native(args):
 
     cpu = cpu_reference(seconds_target=12.0) if world == 1 and not args.no_cpu else None
     p_per_attempt = pairs / attempts
+    # M (embedding evaluations per attempt) is counted by the oracle on a sample of this very workload in this run (cpu_baseline
+    # leg); without that leg the figure of profiles/r1_l_summary.md is used and labelled as such
     m_per_attempt = cpu["embed_evals_per_attempt_local"] if cpu else 67.0
+    m_source = "oracle sample in this run (cpu_baseline leg)" if cpu else "constant from profiles/r1_l_summary.md (no cpu leg in this run)"
     flop_per_attempt = A_PAIR * p_per_attempt + A_EMBED * m_per_attempt
     launch_s = ms_total * 1e-3 / args.steps
     achieved_tflops = flop_per_attempt * R * N_ATOMS * args.sweeps / launch_s / 1e12  # per GPU, per launch
@@ -398,7 +514,9 @@ def run_native(args):
         "config": {
             "workload": WORKLOAD,
             "replicas_per_gpu": R,
-            "attempts_per_step": R * N_ATOMS * world,
+            "attempts_per_step": R * N_ATOMS * world * args.sweeps,
+            "sweeps_per_step": args.sweeps,
+            "kernel": "sweep_rows_kernel (neighbour rows)" if args.rows == "on" else "sweep_kernel (scan)",
             "l2": "flushed between timed steps (256 MiB fill, untimed)",
             "parallelism": f"replicas sharded over {world} GPU(s), no data-path collective",
         },
@@ -406,7 +524,8 @@ def run_native(args):
         "acceptance": accepted / attempts,
         "gpu_launches": launches,
         "clocks": clocks.summary(),
-        "e2e": {"value": e2e_value, "unit": "attempts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+        "e2e": {"value": e2e_value, "unit": "attempts/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "chunks": n_chunks, "note": "per step: pinned host -> device positions, cache priming, one launch of `sweeps_per_step` sweeps, device -> pinned host positions + energies; four replica chunks on four streams"},
         "roofline": {
             "bound": "fp64",
             "achieved": achieved_tflops,
@@ -419,6 +538,7 @@ def run_native(args):
             "flop_per_attempt": flop_per_attempt,
             "pair_evals_per_attempt": p_per_attempt,
             "embed_evals_per_attempt": m_per_attempt,
+            "embed_evals_source": m_source,
             "kernel": "sweep_kernel<EMT>",
         },
         "roofline_hbm": {
@@ -430,6 +550,7 @@ def run_native(args):
             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
         },
         "cpu_baseline": cpu,
+        "pt": pt,
         "wall_s_timed_region": wall,
     }
     _emit(line)
@@ -463,13 +584,14 @@ def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--replicas", type=int, default=4096, help="replicas per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--sweeps", type=int, default=1, help="MonteCarlo steps (sweeps of 108 attempts per replica) fused into one launch = one bench step")
-    ap.add_argument("--rows", default="on", choices=["on", "off", "auto"], help="neighbour rows (csrc/sweep_rows.cuh) in the sweep")
+    ap.add_argument("--no-pt", action="store_true", help="skip the parallel-tempering leg (BASELINE.json configs[4])")
+    ap.add_argument("--sweeps", type=int, default=10, help="MonteCarlo steps (sweeps of 108 attempts per replica) fused into one launch = one bench step")
+    ap.add_argument("--rows", default="off", choices=["on", "off", "auto"], help="neighbour rows (csrc/sweep_rows.cuh) in the sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -12,7 +12,13 @@ Runs the unmodified reference (``/root/reference/src/quansino``, v0.1.3) in this
 Everything else -- move selection, proposals, criteria, save / revert, label bookkeeping, Verlet -- is quansino's own
 code.  The traces pin the C oracle (tests/test_golden.py) and the CUDA path (tests/test_gpu_golden.py).
 
-Usage (in the build container only; the GPU box has no /root/reference):  python oracle/gen_golden.py
+Usage (in the build container only; the GPU box has no /root/reference):  python oracle/gen_golden.py [case ...]
+
+``--real-ase`` (wherever the genuine ``ase`` is importable): the same runs over REAL ASE instead of ``oracle/ase_shim``; nothing
+is written -- every trace is compared with the committed golden file (integer traces identical, floats to 1e-10 relative /
+1e-12 A) and the script exits non-zero on any difference.  ``tests/test_ase_parity.py`` runs it when ``ase`` is present.  This
+is the check that pins the ASE-owned arithmetic (EMT, Lennard-Jones, image enumeration, ``euler_rotate``) that the shim and
+``oracle/potentials.py`` restate.
 """
 
 from __future__ import annotations
@@ -24,7 +30,12 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
-sys.path[:0] = [str(ROOT), str(ROOT / "oracle" / "ase_shim"), "/root/reference/src"]
+REAL_ASE = "--real-ase" in sys.argv
+if REAL_ASE:
+    sys.argv.remove("--real-ase")
+    sys.path[:0] = [str(ROOT), "/root/reference/src"]  # the genuine ase from site-packages
+else:
+    sys.path[:0] = [str(ROOT), str(ROOT / "oracle" / "ase_shim"), "/root/reference/src"]
 
 _orig_version = _md.version
 _md.version = lambda name: "0.1.3" if name == "quansino" else _orig_version(name)
@@ -105,7 +116,7 @@ def case_canonical(opname, op, seed, steps):
     tr = run_steps(mc, steps)
     return dict(
         kind="canonical", op=opname, step_size=0.1, seed=seed, replica=3, temperature=300.0, positions0=pos0, cell=cell,
-        positions=atoms.positions.copy(), n_calculations=atoms.calc.n_calculations, **tr,
+        positions=atoms.positions.copy(), n_calculations=getattr(atoms.calc, "n_calculations", -1), **tr,
     )  # fmt: skip
 
 
@@ -410,14 +421,37 @@ def main():
         "adaptive_force_bias_exp": lambda: case_fbmc(9003, 3, None, 500.0, adaptive=(0.02, 0.2, "energy", "exp", 0.3)),
     }
     only = set(sys.argv[1:])
+    failures = []
     for name, fn in cases.items():
         if only and name not in only:
             continue
         data = fn()
+        if REAL_ASE:  # compare, never write
+            want = np.load(GOLDEN / f"{name}.npz", allow_pickle=True)
+            identical = True
+            for key in want.files:
+                if key == "n_calculations" or key not in data:
+                    continue
+                a, b = np.asarray(data[key]), np.asarray(want[key])
+                if a.shape != b.shape:
+                    failures.append(f"{name}.{key}: shape {a.shape} != {b.shape}")
+                elif a.dtype.kind in "iub" or b.dtype.kind in "iubSU":
+                    if not np.array_equal(a, b):
+                        failures.append(f"{name}.{key}: integer / string trace differs")
+                elif not np.allclose(a, b, rtol=1e-10, atol=1e-12, equal_nan=True):
+                    failures.append(f"{name}.{key}: max |diff| {np.nanmax(np.abs(a - b)):.3e}")
+                else:
+                    identical &= bool(np.array_equal(a, b, equal_nan=True))
+            print(f"{name}: real ASE {'byte-identical' if identical else 'equal to 1e-10'} to the committed golden trace"
+                  if not any(f.startswith(name + ".") for f in failures) else f"{name}: DIFFERS")
+            continue
         np.savez_compressed(GOLDEN / f"{name}.npz", **data)
         acc = data["accepted"]
         print(f"{name}: {len(acc)} attempts, accepted {int((acc == 1).sum())}, rejected {int((acc == 0).sum())}, failed {int((acc == -1).sum())}, "
               f"E_last = {data['energy'][-1]:.12f}")  # fmt: skip
+    if failures:
+        print("\n".join(failures))
+        raise SystemExit(1)
 
 
 if __name__ == "__main__":

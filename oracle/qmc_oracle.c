@@ -154,6 +154,80 @@ static inline void image_vector(const images_t *im, const double *pos, const dou
     }
 }
 
+/* Candidate list for large orthorhombic cells (test-size speed-up only: C5's 2048 atoms): per atom the (j, q) pairs that
+ * can be inside the cutoff, in EXACTLY the order of the brute-force loops (j ascending, q ascending), found from a cheap
+ * per-axis bound.  The evaluation loops apply the very same arithmetic and the very same `r < rc_list` test to them, so the
+ * results are bit-identical to the brute-force enumeration (tests/test_oracle.py checks this).  NULL start = not built. */
+typedef struct {
+    int64_t *start; /* [n + 1] */
+    int32_t *j, *q;
+} pairlist_t;
+
+static void pairlist_free(pairlist_t *pl) {
+    free(pl->start); free(pl->j); free(pl->q);
+    memset(pl, 0, sizeof(*pl));
+}
+
+static int pairlist_build(pairlist_t *pl, const images_t *im, int n, const double *pos, const double cell[9], double cutoff) {
+    memset(pl, 0, sizeof(*pl));
+    if (n < 256 || getenv("QO_NO_PAIRLIST")) return 0;
+    for (int x = 0; x < 9; ++x)
+        if (x % 4 != 0 && cell[x] != 0.0) return 0; /* diagonal cells only */
+    const double rc = cutoff * (1.0 + 1e-9) + 1e-12, rc2 = rc * rc;
+    const int w0 = 2 * im->nmax[0] + 1, w1 = 2 * im->nmax[1] + 1, w2 = 2 * im->nmax[2] + 1;
+    (void)w0;
+    size_t cap = (size_t)n * 128, cnt = 0;
+    pl->start = (int64_t *)malloc(sizeof(int64_t) * ((size_t)n + 1));
+    pl->j = (int32_t *)malloc(sizeof(int32_t) * cap);
+    pl->q = (int32_t *)malloc(sizeof(int32_t) * cap);
+    if (!pl->start || !pl->j || !pl->q) { pairlist_free(pl); return -1; }
+    for (int i = 0; i < n; ++i) {
+        pl->start[i] = (int64_t)cnt;
+        for (int j = 0; j < n; ++j) {
+            int lo[3], hi[3];
+            double u[3][8]; /* candidate components per axis (at most 2 nmax + 1 <= 7) */
+            int ok = 1;
+            for (int k = 0; k < 3 && ok; ++k) {
+                const double L = cell[4 * k];
+                const double base = (pos[3 * j + k] - pos[3 * i + k]) + (double)(im->wrap[3 * i + k] - im->wrap[3 * j + k]) * L;
+                lo[k] = 1; hi[k] = 0;
+                if (im->nmax[k] > 3) { ok = 0; break; }
+                for (int a = -im->nmax[k]; a <= im->nmax[k]; ++a) {
+                    const double v = base + (double)a * L;
+                    u[k][a + im->nmax[k]] = v;
+                    if (fabs(v) < rc) {
+                        if (lo[k] > hi[k]) lo[k] = a;
+                        hi[k] = a;
+                    }
+                }
+                if (lo[k] > hi[k]) ok = 0;
+            }
+            if (!ok) {
+                if (im->nmax[0] > 3 || im->nmax[1] > 3 || im->nmax[2] > 3) { pairlist_free(pl); return 0; }
+                continue;
+            }
+            for (int a = lo[0]; a <= hi[0]; ++a)
+                for (int b = lo[1]; b <= hi[1]; ++b)
+                    for (int c = lo[2]; c <= hi[2]; ++c) {
+                        const double x = u[0][a + im->nmax[0]], y = u[1][b + im->nmax[1]], z = u[2][c + im->nmax[2]];
+                        if (!(x * x + y * y + z * z < rc2)) continue;
+                        if (j == i && a == 0 && b == 0 && c == 0) continue;
+                        if (cnt == cap) {
+                            cap *= 2;
+                            int32_t *nj = (int32_t *)realloc(pl->j, sizeof(int32_t) * cap), *nq = (int32_t *)realloc(pl->q, sizeof(int32_t) * cap);
+                            if (!nj || !nq) { if (nj) pl->j = nj; if (nq) pl->q = nq; pairlist_free(pl); return -1; }
+                            pl->j = nj; pl->q = nq;
+                        }
+                        pl->j[cnt] = j;
+                        pl->q[cnt] = ((a + im->nmax[0]) * w1 + (b + im->nmax[1])) * w2 + (c + im->nmax[2]);
+                        ++cnt;
+                    }
+        }
+    }
+    pl->start[n] = (int64_t)cnt;
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * ASE EMT, single species  (ase/calculators/emt.py: calculate, _get_neighbors, _calc_theta, _calc_dsigma1,
  * _calc_dsigma2, _calc_e_c_a2, _calc_efs_a1, _calc_fs_c_a2; energies -= E0 at the end)
@@ -162,6 +236,8 @@ static int64_t emt_eval(const qo_potential_t *p, int n, const double *pos, const
                         double *energy, double *forces, double *sigma1_out) {
     images_t im;
     if (images_build(&im, n, pos, cell, pbc, p->rc_list) != 0) { images_free(&im); return -1; }
+    pairlist_t pl;
+    if (pairlist_build(&pl, &im, n, pos, cell, p->rc_list) != 0) { images_free(&im); return -1; }
     double *sig = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
     double *deds = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
     double *en = (double *)calloc((size_t)(n > 0 ? n : 1), sizeof(double));
@@ -173,8 +249,10 @@ static int64_t emt_eval(const qo_potential_t *p, int n, const double *pos, const
     for (int i = 0; i < n; ++i) {
         double s1 = 0.0, s2 = 0.0;
         int cnt = 0;
-        for (int j = 0; j < n; ++j)
-            for (int q = 0; q < im.n_off; ++q) {
+        /* all (j, q) in ascending order -- or, for large orthorhombic cells, the candidates among them in the same order */
+        const int64_t c_end = pl.start ? pl.start[i + 1] : (int64_t)n * im.n_off;
+        for (int64_t c = pl.start ? pl.start[i] : 0; c < c_end; ++c) {
+                const int j = pl.start ? pl.j[c] : (int)(c / im.n_off), q = pl.start ? pl.q[c] : (int)(c % im.n_off);
                 if (j == i && im.off[3 * q] == 0 && im.off[3 * q + 1] == 0 && im.off[3 * q + 2] == 0) continue;
                 double d[3];
                 image_vector(&im, pos, cell, i, j, q, d);
@@ -213,8 +291,9 @@ static int64_t emt_eval(const qo_potential_t *p, int n, const double *pos, const
     if (forces) {
         for (int i = 0; i < n; ++i) {
             double f[3] = {0, 0, 0};
-            for (int j = 0; j < n; ++j)
-                for (int q = 0; q < im.n_off; ++q) {
+            const int64_t c_end = pl.start ? pl.start[i + 1] : (int64_t)n * im.n_off;
+            for (int64_t c = pl.start ? pl.start[i] : 0; c < c_end; ++c) {
+                    const int j = pl.start ? pl.j[c] : (int)(c / im.n_off), q = pl.start ? pl.q[c] : (int)(c % im.n_off);
                     if (j == i && im.off[3 * q] == 0 && im.off[3 * q + 1] == 0 && im.off[3 * q + 2] == 0) continue;
                     double d[3];
                     image_vector(&im, pos, cell, i, j, q, d);
@@ -235,6 +314,7 @@ static int64_t emt_eval(const qo_potential_t *p, int n, const double *pos, const
         }
     }
     free(sig); free(deds); free(en);
+    pairlist_free(&pl);
     images_free(&im);
     return npairs;
 }

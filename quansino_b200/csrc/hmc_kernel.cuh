@@ -27,6 +27,10 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "replica_warp.cuh"
 
 namespace qmc {
@@ -53,6 +57,8 @@ struct HmcWork {  // carved from the caller's workspace
     int *nnb;          // [R][N]
     int *flags;        // [R] rebuild requested
     float *bbox;       // [R][ceil(N / 32)][6] centre and half-width of every 32-atom chunk (list build)
+    unsigned long long *ctr;  // [2] attempt index, trace column of the trajectory in flight (advanced on the device: one CUDA graph
+                              // serves every trajectory)
     int max_nb, nb_blocks;
 };
 
@@ -62,8 +68,8 @@ struct HmcArgs {
     HmcWork w;
     double dt;
     int n_steps;
-    unsigned long long seed, attempt;
-    int trace_index, n_attempts;
+    unsigned long long seed;
+    int n_attempts;
     qmc_trace_t tr;
     double *forces_out;
     int lpa;   // lanes per atom (power of two <= 32)
@@ -106,9 +112,10 @@ __host__ inline int64_t hmc_carve(const PotDev &pot, const qmc_batch_t &b, void 
     void *x0 = take(R * 3 * N * 8), *x1 = take(R * 3 * N * 8), *p = take(R * 3 * N * 8), *deds = take(R * N * 8), *ref = take(R * 3 * N * 8);
     void *partial = take(R * nb_blocks * 2 * 8), *ke0 = take(R * nb_blocks * 8), *list = take(R * (int64_t)max_nb * N * 4);
     void *nnb = take(R * N * 4), *flags = take(R * 4), *result = take(R * 2 * 8), *bbox = take(R * ((N + 31) / 32) * 6 * 4);
+    void *ctr = take(16);
     if (w) {
         w->x[0] = (double *)x0; w->x[1] = (double *)x1; w->p = (double *)p; w->deds = (double *)deds; w->ref = (double *)ref;
-        w->partial = (double *)partial; w->ke0 = (double *)ke0; w->list = (unsigned *)list; w->nnb = (int *)nnb; w->flags = (int *)flags; w->result = (double *)result; w->bbox = (float *)bbox;
+        w->partial = (double *)partial; w->ke0 = (double *)ke0; w->list = (unsigned *)list; w->nnb = (int *)nnb; w->flags = (int *)flags; w->result = (double *)result; w->bbox = (float *)bbox; w->ctr = (unsigned long long *)ctr;
         w->max_nb = max_nb; w->nb_blocks = nb_blocks;
     }
     return off;
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_init_kernel(const __grid_cons
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             a.w.x[0][base + (size_t)c * nmax + i] = a.b.pos[base + (size_t)c * nmax + i];
-            const double p = hmc_normal(key, a.attempt, grep, 3u * i + c) * pscale;
+            const double p = hmc_normal(key, a.w.ctr[0], grep, 3u * i + c) * pscale;
             a.w.p[base + (size_t)c * nmax + i] = p;
             ke += p * (p / mass);
         }
@@ -392,10 +399,15 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_bbox_kernel(const __grid_cons
     }
 }
 
-// the build kernels of all CTAs must have seen the flag before it is cleared: separate tiny kernel
-__global__ void hmc_clear_flags_kernel(int *flags, int n) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < n) flags[r] = 0;
+// (the rebuild flag of a replica is cleared by pass 1, which runs after every CTA of the build kernels has seen it)
+__global__ void hmc_set_ctr_kernel(unsigned long long *ctr, unsigned long long attempt, unsigned long long column) {
+    ctr[0] = attempt;
+    ctr[1] = column;
+}
+
+__global__ void hmc_bump_ctr_kernel(unsigned long long *ctr) {
+    ctr[0] += 1ull;
+    ctr[1] += 1ull;
 }
 
 // List entries are walked through a two-deep software pipeline: the entry word two iterations ahead and the neighbour's
@@ -452,6 +464,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass1_kernel(const __grid_con
     const double *x = a.w.x[a.cur] + (size_t)r * 3 * nmax, *y = x + nmax, *z = y + nmax;
     const unsigned *list = a.w.list + (size_t)r * a.w.max_nb * nmax;
     double s1 = 0.0, s2 = 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.w.flags[r] = 0;  // the list build (previous kernels) has consumed the request
     if (own) {
         const double xi = x[i], yi = y[i], zi = z[i];
         const int nn = a.w.nnb[(size_t)r * nmax + i];
@@ -608,7 +621,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_finish_kernel(const __grid_co
     const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
     const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
     double o2, u_accept;
-    uniform_pair(key, a.attempt, grep, 2, o2, u_accept);
+    uniform_pair(key, a.w.ctr[0], grep, 2, o2, u_accept);
     int status = 0;
     const bool acc = metropolis(u_accept, -delta / kT, status);
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -632,7 +645,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_finish_kernel(const __grid_co
         cnt[0] += 1;
         if (acc) cnt[1] += 1;
         if (status) atomicOr(a.b.status + r, status);
-        const size_t ti = (size_t)r * a.n_attempts + a.trace_index;
+        const size_t ti = (size_t)r * a.n_attempts + (size_t)a.w.ctr[1];
         if (a.tr.move) a.tr.move[ti] = 0;
         if (a.tr.accepted) a.tr.accepted[ti] = acc ? 1 : 0;
         if (a.tr.energy) a.tr.energy[ti] = acc ? e_pot : last_pot;
@@ -699,7 +712,6 @@ inline void hmc_force_eval(HmcArgs &a, cudaStream_t s) {
     } else {
         hmc_build_kernel<<<g1, HMC_THREADS, 0, s>>>(a);
     }
-    hmc_clear_flags_kernel<<<(R + 127) / 128, 128, 0, s>>>(a.w.flags, R);
     if (a.pot.kind == QMC_POT_EMT) {
         hmc_pass1_kernel<QMC_POT_EMT><<<gl, HMC_THREADS, 0, s>>>(a);
         hmc_pass2_kernel<QMC_POT_EMT><<<gl, HMC_THREADS, 0, s>>>(a);
@@ -733,6 +745,83 @@ inline int hmc_forces(const PotDev &pot, const qmc_batch_t &b, double *forces, v
     return hmc_check(cudaGetLastError(), "force kernels", err, errn);
 }
 
+// One trajectory = init + (n_steps + 1) force evaluations (4 launches each) + finish + publish + counter bump: ~410 launches for
+// Verlet 100.  The sequence never depends on the data (list rebuilds are decided on the device), so it is captured ONCE into a
+// CUDA graph -- on a private capture stream, the caller's stream may be the legacy default stream -- and launched once per
+// attempt; the attempt index lives in device memory (w.ctr) and is advanced by the graph itself.  Executables are cached by the
+// exact kernel arguments (the parallel-tempering loop calls with one trajectory per round).  QMC_HMC_GRAPH=0 launches directly.
+inline void hmc_trajectory_launches(HmcArgs a, int n_steps, int nb1, int nb2, cudaStream_t s) {
+    const int R = a.b.n_replicas;
+    const dim3 g1(nb1, R);
+    a.cur = 0;
+    hmc_init_kernel<<<g1, HMC_THREADS, 0, s>>>(a);
+    for (int step = 0; step <= n_steps; ++step) {
+        a.mode = n_steps == 0 ? 4 : (step == 0 ? 0 : (step == n_steps ? 2 : 1));
+        hmc_force_eval(a, s);
+        if (a.mode == 0 || a.mode == 1) a.cur ^= 1;
+    }
+    hmc_finish_kernel<<<g1, HMC_THREADS, 0, s>>>(a, nb1, nb2);
+    hmc_publish_kernel<<<(R + 127) / 128, 128, 0, s>>>(a);
+    hmc_bump_ctr_kernel<<<1, 1, 0, s>>>(a.w.ctr);
+}
+
+struct HmcGraphCache {
+    struct Entry {
+        std::string key;
+        cudaGraphExec_t exec;
+        int device;
+    };
+    std::mutex mu;
+    std::vector<Entry> entries;  // most recently used last
+    cudaStream_t capture_stream[16] = {};
+};
+
+inline HmcGraphCache &hmc_graph_cache() {
+    static HmcGraphCache c;
+    return c;
+}
+
+inline cudaGraphExec_t hmc_trajectory_graph(const HmcArgs &a, int n_steps, int nb1, int nb2) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    std::string key(reinterpret_cast<const char *>(&a), sizeof(a));
+    key.append(reinterpret_cast<const char *>(&n_steps), sizeof(n_steps));
+    key.append(reinterpret_cast<const char *>(&dev), sizeof(dev));
+    HmcGraphCache &c = hmc_graph_cache();
+    std::lock_guard<std::mutex> lock(c.mu);
+    for (size_t k = 0; k < c.entries.size(); ++k)
+        if (c.entries[k].key == key) {
+            HmcGraphCache::Entry e = c.entries[k];
+            c.entries.erase(c.entries.begin() + k);
+            c.entries.push_back(e);
+            return e.exec;
+        }
+    if (!c.capture_stream[dev] && cudaStreamCreateWithFlags(&c.capture_stream[dev], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    cudaStream_t cs = c.capture_stream[dev];
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    hmc_trajectory_launches(a, n_steps, nb1, nb2, cs);
+    if (cudaStreamEndCapture(cs, &graph) != cudaSuccess || !graph || cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        return nullptr;
+    }
+    cudaGraphDestroy(graph);
+    if (c.entries.size() >= 8) {
+        cudaGraphExecDestroy(c.entries.front().exec);
+        c.entries.erase(c.entries.begin());
+    }
+    c.entries.push_back({key, exec, dev});
+    return exec;
+}
+
 inline int hmc_run(const PotDev &pot, const qmc_batch_t &b, double dt, int n_steps, unsigned long long seed,
                    unsigned long long attempt_base, int n_attempts, const qmc_trace_t &tr, void *workspace, cudaStream_t s, char *err,
                    size_t errn) {
@@ -749,21 +838,18 @@ inline int hmc_run(const PotDev &pot, const qmc_batch_t &b, double dt, int n_ste
     a.lpa = hmc_pick_lpa(b);
     a.skin = hmc_skin();
     a.build_lanes = hmc_pick_build_lanes(b);
-    const int N = b.n_max, R = b.n_replicas;
+    const int N = b.n_max;
     const int nb1 = (N + HMC_THREADS - 1) / HMC_THREADS, nb2 = (N * a.lpa + HMC_THREADS - 1) / HMC_THREADS;
-    const dim3 g1(nb1, R);
+    hmc_set_ctr_kernel<<<1, 1, 0, s>>>(a.w.ctr, attempt_base, 0ull);
+    const char *env = std::getenv("QMC_HMC_GRAPH");
+    cudaGraphExec_t exec = (env && std::atoi(env) == 0) ? nullptr : hmc_trajectory_graph(a, n_steps, nb1, nb2);
     for (int k = 0; k < n_attempts; ++k) {
-        a.attempt = attempt_base + (unsigned long long)k;
-        a.trace_index = k;
-        a.cur = 0;
-        hmc_init_kernel<<<g1, HMC_THREADS, 0, s>>>(a);
-        for (int step = 0; step <= n_steps; ++step) {
-            a.mode = n_steps == 0 ? 4 : (step == 0 ? 0 : (step == n_steps ? 2 : 1));
-            hmc_force_eval(a, s);
-            if (a.mode == 0 || a.mode == 1) a.cur ^= 1;
+        if (exec) {
+            int rc = hmc_check(cudaGraphLaunch(exec, s), "trajectory graph launch", err, errn);
+            if (rc) return rc;
+        } else {
+            hmc_trajectory_launches(a, n_steps, nb1, nb2, s);
         }
-        hmc_finish_kernel<<<g1, HMC_THREADS, 0, s>>>(a, nb1, nb2);
-        hmc_publish_kernel<<<(R + 127) / 128, 128, 0, s>>>(a);
         int rc = hmc_check(cudaGetLastError(), "trajectory kernels", err, errn);
         if (rc) return rc;
     }

@@ -32,6 +32,21 @@ def shard(n_global: int, world_size: int, rank: int) -> tuple[int, int]:
     return offset, count
 
 
+def spread_ladder(temperatures, groups: int = 8) -> np.ndarray:
+    """Assignment of a temperature ladder to contiguously sharded replicas such that every shard holds temperatures from the
+    whole range: replica g gets ladder[(g % groups) * (R // groups) + g // groups].  A geometric ladder handed out in order puts
+    the hottest replicas -- whose neighbour lists are rebuilt most often and whose trajectories cost most -- on the last rank,
+    and the whole job then waits for that rank (profiles/r1_k_scaling.md).  The assignment does not depend on the number of
+    ranks (1, 2, 4 or 8 of a node), so results stay independent of the sharding; swaps act on temperature-adjacent pairs
+    wherever they live.  Ladders whose length is not a multiple of ``groups`` are returned unchanged."""
+    t = np.asarray(temperatures, dtype=np.float64)
+    R = len(t)
+    if groups <= 1 or R % groups != 0:
+        return t.copy()
+    g = np.arange(R)
+    return t[(g % groups) * (R // groups) + g // groups]
+
+
 def _dist():
     import torch.distributed as dist
 
@@ -79,7 +94,7 @@ class ReplicaExchange:
         self.counts, self.rank, self.seed, self.swap = list(counts), int(rank), int(seed), swap
         self.offset = sum(self.counts[: self.rank])
         self.round = 0
-        self.n_accepted = 0
+        self._accepted = torch.zeros((), dtype=torch.int64, device=energies.device)  # summed on the device: no host sync per round
         self.n_pairs = 0
 
     @classmethod
@@ -101,9 +116,14 @@ class ReplicaExchange:
         self.temperatures.copy_(t_all[self.offset : self.offset + self.counts[self.rank]])
         n = t_all.numel()
         self.n_pairs += len(range(self.round & 1, n - 1, 2))
-        self.n_accepted += int(accepted.sum().item())
+        self._accepted += accepted.sum()
         self.round += 1
         return accepted
+
+    @property
+    def n_accepted(self) -> int:
+        """Accepted swaps so far (reads the device counter: synchronises)."""
+        return int(self._accepted.item())
 
 
 def reduce_observables(values: torch.Tensor) -> torch.Tensor:
@@ -130,4 +150,4 @@ def observables(mc) -> dict[str, float]:
     }  # fmt: skip
 
 
-__all__ = ["ReplicaExchange", "device_swap", "gather_replicas", "observables", "reduce_observables", "shard"]
+__all__ = ["ReplicaExchange", "device_swap", "gather_replicas", "observables", "reduce_observables", "shard", "spread_ladder"]

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import capi
+from oracle.potentials import emt_params
 from tests.helpers import cu_replicas, oracle_par, oracle_run
 
 pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("kernel_variant")]
@@ -336,3 +337,32 @@ def test_library_owned_batch_handle(cuda_lib):
         assert lib.qmc_batch_labels(h, 0) is None
     finally:
         _lib.check(lib.qmc_batch_destroy(h))
+
+
+def test_seed_zero_is_a_seed_and_tables_are_relowered(cuda_lib):
+    """(1) `seed=0` keys the stream like any other seed (the reference: `Generator(PCG64(0))`, mc/driver.py:77-78) instead of being
+    replaced by a random one.  (2) Changes made to a move BETWEEN runs -- step size, operation -- reach the kernel: the reference
+    re-reads them on every call (moves/displacement.py:109-141)."""
+    from quansino_b200 import operations
+
+    R = 3
+    pos, cell, n = cu_replicas(3, R, seed=12)
+    runs = []
+    for _ in range(2):
+        mc = _driver(pos, cell, n, operations.Ball(0.1), seed=0, trace=True, resync_interval=0)
+        assert mc._seed == 0
+        mc.run(1)
+        mc.moves["default_displacement_move"].move.operation.step_size = 0.04
+        mc.run(1)
+        mc.moves["default_displacement_move"].move.operation = operations.Box(0.05)
+        mc.run(1)
+        runs.append((mc.download().positions.copy(), mc.last_trace["accepted"].copy()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    par = emt_params("Cu")
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, temperature=300.0)
+        lab = np.arange(n, dtype=np.int32)
+        for k, (op, step) in enumerate(((capi.OP_BALL, 0.1), (capi.OP_BALL, 0.04), (capi.OP_BOX, 0.05))):
+            tr = capi.mc_run(par, rep, [capi.MoveSpec(capi.MOVE_DISPLACEMENT, op, step=step, labels=lab)], 0, r, k * n, n)
+        assert np.array_equal(runs[0][1][r], tr["accepted"])
+        np.testing.assert_allclose(runs[0][0][r], rep.positions, rtol=0, atol=1e-12)

@@ -235,12 +235,93 @@ def test_hmc_matches_oracle(cuda_lib):
         specs = [capi.MoveSpec(capi.MOVE_HMC, capi.OP_VERLET, dt=2.0 * fs, n_steps=n_steps)]
         ref = capi.mc_run(par, rep, specs, 99, r, 0, n_attempts)
         assert np.array_equal(tr["accepted"][r], ref["accepted"])
-        np.testing.assert_allclose(tr["delta"][r], ref["delta"], rtol=1e-7, atol=1e-9)  # sums of O(100 eV) terms
+        np.testing.assert_allclose(tr["delta"][r], ref["delta"], rtol=1e-9, atol=1e-10)  # differences of sums of O(100 eV) terms
         np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10)
         np.testing.assert_allclose(out.positions[r], rep.positions, rtol=0, atol=1e-10)
         np.testing.assert_allclose(out.momenta[r], rep.momenta, rtol=0, atol=1e-10)
         assert abs(mc.batch.kinetic.cpu().numpy()[r] - rep.last_kinetic) <= 1e-9 * abs(rep.last_kinetic)
     assert tr["accepted"].sum() > 0
+
+
+def test_hmc_c5_shape_matches_oracle(cuda_lib, kernel_variant):
+    """BASELINE.json configuration C5 at its real shape: ONE replica of 2048-atom Cu (8 x 8 x 8), Verlet 100 x 1 fs, two
+    trajectories -- accept sequence identical, energies / positions / momenta to 1e-10 against the C oracle
+    (integrators/displacement.py:52-81, mc/criteria.py:117-140).  The oracle needs ~1 min for its 202 force evaluations."""
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.integrators.displacement import fs
+    from quansino_b200.mc import HamiltonianCanonical
+    from quansino_b200.moves import HamiltonianDisplacementMove
+
+    if kernel_variant != "warp":
+        pytest.skip("the Hamiltonian kernels do not depend on the sweep-kernel variant; run once")
+    n_attempts, n_steps = 2, 100
+    pos, cell, n = cu_replicas(8, 1, seed=51, stdev=0.03)
+    assert n == 2048
+    mc = HamiltonianCanonical(
+        _emt_atoms(pos, cell, n), temperature=600.0, max_cycles=1, seed=2024, trace=True, resync_interval=0, steps_per_launch=n_attempts,
+        default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=1.0, max_steps=n_steps)),
+    )  # fmt: skip
+    mc.run(n_attempts)
+    tr, out = mc.last_trace, mc.download()
+    rep = capi.Replica(positions=pos[0].copy(), cell=cell, temperature=600.0, mass=63.546, momenta=np.zeros((n, 3)))
+    specs = [capi.MoveSpec(capi.MOVE_HMC, capi.OP_VERLET, dt=1.0 * fs, n_steps=n_steps)]
+    ref = capi.mc_run(emt_params("Cu"), rep, specs, 2024, 0, 0, n_attempts)
+    assert np.array_equal(tr["accepted"][0], ref["accepted"])
+    np.testing.assert_allclose(tr["delta"][0], ref["delta"], rtol=1e-9, atol=1e-9)  # H = O(1e3) eV: 1e-9 absolute is 1e-12 of H
+    np.testing.assert_allclose(tr["energy"][0], ref["energy"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(out.positions[0], rep.positions, rtol=0, atol=1e-10)
+    np.testing.assert_allclose(out.momenta[0], rep.momenta, rtol=0, atol=1e-10)
+    assert abs(mc.batch.kinetic.cpu().numpy()[0] - rep.last_kinetic) <= 1e-10 * abs(rep.last_kinetic)
+    assert int(mc.batch.status.max().item()) == 0
+
+
+def test_parallel_tempering_round_matches_oracle_replay(cuda_lib, kernel_variant):
+    """The whole parallel-tempering round of C5 on one device -- HMC trajectory of every replica at its CURRENT temperature, then
+    `ReplicaExchange.exchange` (all-gather is the identity here) -- for 8 temperatures and 5 rounds against a replay with the
+    C oracle: trajectories by `qo_mc_run`, swap decisions by `qo_pt_swap_accept` from the shared stream."""
+    from oracle import capi as oc
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.integrators.displacement import fs
+    from quansino_b200.mc import HamiltonianCanonical
+    from quansino_b200.mc.tempering import ReplicaExchange
+    from quansino_b200.moves import HamiltonianDisplacementMove
+
+    if kernel_variant != "warp":
+        pytest.skip("the Hamiltonian kernels do not depend on the sweep-kernel variant; run once")
+    R, rounds, n_steps, seed = 8, 5, 12, 77
+    pos, cell, n = cu_replicas(3, R, seed=61, stdev=0.03)
+    temps0 = 300.0 * (400.0 / 300.0) ** (np.arange(R) / (R - 1))
+    mc = HamiltonianCanonical(
+        _emt_atoms(pos, cell, n), temperature=temps0, max_cycles=1, seed=seed, resync_interval=0,
+        default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=2.0, max_steps=n_steps)),
+    )  # fmt: skip
+    pt = ReplicaExchange.for_driver(mc)
+    par = emt_params("Cu")
+    reps = [capi.Replica(positions=pos[r].copy(), cell=cell, temperature=float(temps0[r]), mass=63.546, momenta=np.zeros((n, 3))) for r in range(R)]
+    specs = [capi.MoveSpec(capi.MOVE_HMC, capi.OP_VERLET, dt=2.0 * fs, n_steps=n_steps)]
+    expect = temps0.copy()
+    n_swaps = 0
+    for rnd in range(rounds):
+        mc.run(1)
+        pt.exchange()
+        for r in range(R):  # the replay: same trajectory, same temperature, same draws
+            reps[r].temperature = float(expect[r])
+            capi.mc_run(par, reps[r], specs, seed, r, rnd, 1)
+        energies = np.array([rep.last_energy for rep in reps])
+        np.testing.assert_allclose(mc.batch.energy.cpu().numpy(), energies, rtol=1e-10, atol=1e-10)
+        order = np.argsort(expect, kind="stable")
+        for k in range(rnd & 1, R - 1, 2):
+            ra, rb = order[k], order[k + 1]
+            u = oc.uniform_pair(seed, rnd, k, 3)[1]
+            if oc.lib().qo_pt_swap_accept(energies[ra], energies[rb], expect[ra], expect[rb], u):
+                expect[ra], expect[rb] = expect[rb], expect[ra]
+                n_swaps += 1
+        assert np.array_equal(mc.batch.temperature.cpu().numpy(), expect), f"ladder after round {rnd}"
+    out = mc.download()
+    for r in range(R):
+        np.testing.assert_allclose(out.positions[r], reps[r].positions, rtol=0, atol=1e-10)
+    assert n_swaps >= 3 and pt.n_accepted == n_swaps
+    assert np.array_equal(np.sort(expect), np.sort(temps0))
 
 
 def test_parallel_tempering_swap_matches_oracle(cuda_lib):

@@ -283,3 +283,52 @@ def test_to_dict_from_dict_round_trips_through_the_registry():
 
     register_class(MyBall)
     assert get_class("MyBall") is MyBall
+
+
+def _dummy_batch(lib_mod, with_n_exchange: bool):
+    """A batch whose pointers are non-NULL but never dereferenced: qmc_sweep validates the table before it touches the device."""
+    b = lib_mod.Batch()
+    b.n_replicas, b.n_max = 2, 108
+    for name in ("pos", "cell", "n_atoms", "energy", "temperature", "sigma1", "eatom", "counters", "status"):
+        setattr(b, name, 4096)
+    if with_n_exchange:
+        b.n_exchange = 4096
+    b.pbc = (1, 1, 1)
+    return b
+
+
+def test_sweep_refuses_tables_the_kernels_would_mishandle():
+    """Advisor findings of round 1, as C-ABI behaviour: (1) label tables / composites without batch.n_exchange (the instantiation
+    that serves them reads and writes it) are an invalid argument, not an illegal address; (2) a composite with more than 16
+    displacements per attempt would reuse Philox blocks (the extra draws start at block 64) and is refused."""
+    import ctypes as C
+
+    from quansino_b200 import EMT, _lib
+
+    lib = _lib.load()
+    pot = EMT().lower("Cu")
+    mv = (_lib.Move * 2)()
+    mv[0].type, mv[0].op, mv[0].step, mv[0].probability = _lib.MOVE_DISPLACEMENT, _lib.OP_BALL, 0.1, 1.0
+    mv[0].labels = 4096  # a label table
+    rc = lib.qmc_sweep(C.byref(pot), C.byref(_dummy_batch(_lib, False)), mv, 1, 1, 0, 10, None, None)
+    assert rc == _lib.ERR_INVALID and b"n_exchange" in lib.qmc_last_error()
+    mv[0].labels = None
+    mv[0].repeat = 17  # DisplacementMove * 17
+    rc = lib.qmc_sweep(C.byref(pot), C.byref(_dummy_batch(_lib, True)), mv, 1, 1, 0, 10, None, None)
+    assert rc == _lib.ERR_UNSUPPORTED and b"Philox" in lib.qmc_last_error()
+    mv[0].repeat, mv[0].chain = 9, 3  # plain CompositeMove: 9 + 8 displacements, then a closing cell move would read block 64
+    mv[1].type, mv[1].op, mv[1].step, mv[1].repeat, mv[1].chain = _lib.MOVE_DISPLACEMENT, _lib.OP_BALL, 0.1, 8, 2
+    rc = lib.qmc_sweep(C.byref(pot), C.byref(_dummy_batch(_lib, True)), mv, 2, 1, 0, 10, None, None)
+    assert rc == _lib.ERR_UNSUPPORTED and b"Philox" in lib.qmc_last_error()
+
+
+def test_neighbour_row_geometry_is_exported():
+    import ctypes as C
+
+    from quansino_b200 import EMT, LennardJones, _lib
+
+    lib = _lib.load()
+    emt, lj = EMT().lower("Cu"), LennardJones(sigma=2.5, epsilon=0.1).lower("Pt")
+    assert lib.qmc_nbr_row_words(C.byref(emt), 108) == 112 and lib.qmc_nbr_row_words(C.byref(emt), 500) == 160
+    assert lib.qmc_nbr_row_words(C.byref(lj), 44) == 208
+    assert lib.qmc_nbr_row_words(C.byref(emt), 2048) == _lib.ERR_UNSUPPORTED

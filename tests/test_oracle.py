@@ -184,3 +184,25 @@ def test_pt_swap_rule():
     assert lib.qo_pt_swap_accept(1.0, 2.0, 300.0, 600.0, math.exp(x) * 0.99) == 1
     assert lib.qo_pt_swap_accept(1.0, 2.0, 300.0, 600.0, min(0.999999, math.exp(x) * 1.01)) == (1 if math.exp(x) * 1.01 > 0.999999 else 0)
     assert lib.qo_pt_swap_accept(2.0, 1.0, 300.0, 600.0, 0.999999) == 1  # hot replica found the lower energy: always swap
+
+
+def test_candidate_list_is_bit_identical_to_brute_force(monkeypatch):
+    """Large orthorhombic cells (C5: 2048 atoms) visit a candidate list instead of every (atom, image) pair -- same order, same
+    arithmetic, same cutoff test: energies, forces and sigma_1 must agree to the last bit with the brute-force loops."""
+    import os
+
+    from tests.helpers import cu_replicas
+
+    pos, cell, n = cu_replicas(5, 1, seed=77, stdev=0.08)
+    pos[0] += np.random.default_rng(5).integers(-2, 3, size=(n, 3)) * cell[0, 0]  # unwrapped coordinates
+    par = emt_params("Cu")
+    fast = capi.energy(par, pos[0], cell, (1, 1, 1), want_forces=True, want_sigma=True)
+    monkeypatch.setenv("QO_NO_PAIRLIST", "1")
+    brute = capi.energy(par, pos[0], cell, (1, 1, 1), want_forces=True, want_sigma=True)
+    assert "QO_NO_PAIRLIST" in os.environ
+    assert fast["n_pairs"] == brute["n_pairs"] and fast["energy"] == brute["energy"]
+    assert np.array_equal(fast["forces"], brute["forces"]) and np.array_equal(fast["sigma1"], brute["sigma1"])
+    slab = capi.energy(par, pos[0], cell, (1, 1, 0), want_forces=True)
+    monkeypatch.delenv("QO_NO_PAIRLIST")
+    slab_fast = capi.energy(par, pos[0], cell, (1, 1, 0), want_forces=True)
+    assert slab["energy"] == slab_fast["energy"] and np.array_equal(slab["forces"], slab_fast["forces"])
