@@ -91,7 +91,14 @@ typedef struct qmc_potential {
  *
  * Label groups (moves/displacement.py:164-167: `where(labels == label)` may select several atoms, which then move by ONE
  * translation): `chain` bit 2 on a single displacement entry says that `labels` holds dense group ranks 0..G-1 in the
- * order of the reference's sorted unique labels (-1 = not movable); every atom of the selected rank is displaced. */
+ * order of the reference's sorted unique labels (-1 = not movable); every atom of the selected rank is displaced.
+ *
+ * Run-coded groups (`chain` bit 3; tables with a molecular ExchangeMove): an inserted molecule receives ONE new label
+ * max + 1 in every registered move (moves/displacement.py:244-250) and deletions preserve the order, so the non-negative labels
+ * of a table stay non-decreasing with the atom index and a group is a contiguous RUN of equal labels: the k-th unique label is
+ * the k-th run.  `labels` then holds the reference's own label values (the caller checks that they start non-decreasing);
+ * a displacement entry moves the whole run rigidly, an exchange entry deletes the whole run or appends n_exchange_atoms
+ * atoms with one new label (placed by Translation or TranslationRotation), ONE criteria evaluation either way. */
 enum qmc_move_type { QMC_MOVE_DISPLACEMENT = 0, QMC_MOVE_CELL = 1, QMC_MOVE_EXCHANGE = 2, QMC_MOVE_HMC = 3 };
 enum qmc_op { QMC_OP_BALL = 0, QMC_OP_BOX = 1, QMC_OP_SPHERE = 2, QMC_OP_TRANSLATION = 3, QMC_OP_ISOTROPIC = 4, QMC_OP_VERLET = 5,
               QMC_OP_ROTATION = 6 /* Rotation (operations/displacement.py:178-200): label groups only, rigid z-x-z Euler rotation about the centre */,
@@ -109,7 +116,7 @@ typedef struct qmc_move {
     int32_t default_label; /* DisplacementMove.default_label; QMC_LABEL_NONE = None */
     int32_t repeat;        /* displacement moves: how many times this entry is performed per attempt (>= 1; 0 reads as 1) */
     int32_t chain;         /* bit 0: the next table entry belongs to the same composite move; bit 1: plain CompositeMove;
-                              bit 2: label groups (labels = dense group ranks) */
+                              bit 2: label groups (labels = dense group ranks); bit 3: label groups coded as RUNS (see below) */
     int32_t axes;          /* cell moves: bit d set = axis d is deformed (the diagonal of IsotropicDeformation.mask,
                               operations/cell.py:167-169); 0 reads as all three axes */
     int32_t minimum_count; /* MoveStorage.minimum_count: forced occurrences of this move per step (mc/core.py:331-342) */
@@ -158,6 +165,12 @@ typedef struct qmc_batch {
     double accessible_volume;
     double exchange_mass;   /* amu */
     double exchange_pos[3];
+    /* Molecular exchange (moves/exchange.py:88-132 with an `exchange_atoms` of several atoms; the docstring at :194-203 places
+     * it with TranslationRotation): atoms per inserted / deleted molecule (0 or 1 = the single atom at exchange_pos) and the
+     * molecule's positions [n_exchange_atoms][3]; exchange_mass is the mass of the WHOLE molecule (mc/criteria.py:262). */
+    int32_t n_exchange_atoms;
+    int32_t _pad2;
+    double exchange_mol[24];
 } qmc_batch_t;
 
 /* optional per-attempt trace, device [R][n_attempts] each, any pointer may be NULL */

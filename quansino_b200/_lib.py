@@ -98,6 +98,9 @@ class Batch(C.Structure):
         ("accessible_volume", C.c_double),
         ("exchange_mass", C.c_double),
         ("exchange_pos", C.c_double * 3),
+        ("n_exchange_atoms", C.c_int32),
+        ("_pad2", C.c_int32),
+        ("exchange_mol", C.c_double * 24),
     ]
 
 

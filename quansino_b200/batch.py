@@ -166,6 +166,7 @@ class ReplicaBatch:
         self.accessible_volume = float(abs(np.linalg.det(atoms.cell[0]))) if R else 0.0
         self.exchange_mass = 0.0
         self.exchange_pos = (0.0, 0.0, 0.0)
+        self.exchange_mol = np.zeros((1, 3))  # positions of the exchange molecule (one row: the single exchange atom)
         self.cells_uniform = False
         self.cell_diag = (0.0, 0.0, 0.0)
         # neighbour rows of the row-based sweep kernel (csrc/sweep_rows.cuh), allocated on first use (`ensure_rows`)
@@ -247,6 +248,9 @@ class ReplicaBatch:
         b.mass, b.pressure, b.chemical_potential = self.mass, self.pressure, self.chemical_potential
         b.accessible_volume, b.exchange_mass = self.accessible_volume, self.exchange_mass
         b.exchange_pos = (C.c_double * 3)(*self.exchange_pos)
+        mol = np.asarray(self.exchange_mol, dtype=np.float64).reshape(-1, 3)
+        b.n_exchange_atoms = len(mol)
+        b.exchange_mol = (C.c_double * 24)(*mol.reshape(-1), *([0.0] * (24 - mol.size)))
         return b
 
     def stream(self) -> int:

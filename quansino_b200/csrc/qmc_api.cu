@@ -213,7 +213,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     std::memset(&a, 0, sizeof(a));
     if ((rc = make_potdev(pot, a.pot))) return rc;
     a.b = *batch;
-    bool any_exchange = false, any_composite = false;
+    bool any_exchange = false, any_composite = false, any_runs = false;
     double tot = 0.0;
     for (int m = 0; m < n_moves; ++m) {
         const qmc_move_t &mv = moves[m];
@@ -221,7 +221,10 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         if (head && !(mv.probability >= 0.0)) return fail(QMC_ERR_INVALID, "move %d: negative probability", m);
         if (head) tot += mv.probability;
         if (mv.repeat < 0) return fail(QMC_ERR_INVALID, "move %d: negative repeat", m);
-        if (mv.chain < 0 || mv.chain > 4) return fail(QMC_ERR_INVALID, "move %d: chain must be bits 0 / 1 (composite) or bit 2 alone (label groups)", m);
+        if (mv.chain < 0 || (mv.chain > 4 && mv.chain != 8))
+            return fail(QMC_ERR_INVALID, "move %d: chain must be bits 0 / 1 (composite), bit 2 alone (label groups) or bit 3 alone (run-coded groups)", m);
+        if ((mv.chain & 8) && ((mv.type != QMC_MOVE_DISPLACEMENT && mv.type != QMC_MOVE_EXCHANGE) || !mv.labels || !head || mv.repeat > 1 || mv.n_extra_ops))
+            return fail(QMC_ERR_UNSUPPORTED, "move %d: run-coded label groups need a single displacement or exchange move with a label array", m);
         if ((mv.chain & 4) && (mv.type != QMC_MOVE_DISPLACEMENT || !mv.labels || !head || mv.repeat > 1))
             return fail(QMC_ERR_UNSUPPORTED, "move %d: label groups need a single displacement move with a label array", m);
         if ((mv.chain & 1) && m + 1 == n_moves) return fail(QMC_ERR_INVALID, "move %d: chain bit 0 set on the last table entry", m);
@@ -229,11 +232,12 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
             return fail(QMC_ERR_INVALID, "move %d: chain bit 1 (plain CompositeMove) must be the same on every entry of a chain", m);
         // a CellMove may close a plain CompositeMove chain (the hybrid NPT move); everything else in a chain is a displacement
         const bool closing_cell = !head && mv.type == QMC_MOVE_CELL && (mv.chain & 2) && !(mv.chain & 1) && mv.repeat <= 1;
-        if ((mv.chain || !head || mv.repeat > 1) && mv.type != QMC_MOVE_DISPLACEMENT && !closing_cell)
+        if (((mv.chain & 7) || !head || mv.repeat > 1) && mv.type != QMC_MOVE_DISPLACEMENT && !closing_cell)
             return fail(QMC_ERR_UNSUPPORTED, "move %d: a composite move is a chain of displacement moves, optionally closed by a cell move", m);
         if (!head && mv.type == QMC_MOVE_DISPLACEMENT && mv.labels != moves[m - 1].labels)
             return fail(QMC_ERR_UNSUPPORTED, "move %d: the sub-moves of a composite move must share one label array", m);
-        any_composite |= mv.chain || mv.repeat > 1;
+        any_composite |= mv.chain || mv.repeat > 1;  // (label groups, too, live in the general instantiation)
+        any_runs |= (mv.chain & 8) != 0;
         if (mv.minimum_count < 0) return fail(QMC_ERR_INVALID, "move %d: negative minimum_count", m);
         if (head)
             for (int q = 0; q < mv.minimum_count; ++q) {
@@ -242,7 +246,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
             }
         switch (mv.type) {
             case QMC_MOVE_DISPLACEMENT:
-                if ((mv.op == QMC_OP_ROTATION || mv.op == QMC_OP_TRANSLATION || mv.op == QMC_OP_TRANSLATION_ROTATION) && !(mv.chain & 4))
+                if ((mv.op == QMC_OP_ROTATION || mv.op == QMC_OP_TRANSLATION || mv.op == QMC_OP_TRANSLATION_ROTATION) && !(mv.chain & 12))
                     return fail(QMC_ERR_UNSUPPORTED, "move %d: Rotation / Translation / TranslationRotation need label groups (chain bit 2 and a label array)", m);
                 if (mv.op != QMC_OP_BALL && mv.op != QMC_OP_BOX && mv.op != QMC_OP_SPHERE && mv.op != QMC_OP_ROTATION &&
                     mv.op != QMC_OP_TRANSLATION && mv.op != QMC_OP_TRANSLATION_ROTATION)
@@ -254,8 +258,12 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
                     return fail(QMC_ERR_UNSUPPORTED, "move %d: only IsotropicDeformation is available on the GPU path", m);
                 break;
             case QMC_MOVE_EXCHANGE:
-                if (mv.op != QMC_OP_TRANSLATION)
-                    return fail(QMC_ERR_UNSUPPORTED, "move %d: only Translation is available for exchange moves", m);
+                if (mv.op != QMC_OP_TRANSLATION && !(mv.op == QMC_OP_TRANSLATION_ROTATION && (mv.chain & 8)))
+                    return fail(QMC_ERR_UNSUPPORTED, "move %d: exchange moves place with Translation (TranslationRotation with run-coded groups)", m);
+                if (batch->n_exchange_atoms < 0 || batch->n_exchange_atoms > 8)
+                    return fail(QMC_ERR_INVALID, "batch.n_exchange_atoms must be in [0, 8]");
+                if (batch->n_exchange_atoms > 1 && !(mv.chain & 8))
+                    return fail(QMC_ERR_UNSUPPORTED, "move %d: a molecular exchange species needs run-coded label groups (chain bit 3) on every move", m);
                 if (!batch->n_exchange) return fail(QMC_ERR_INVALID, "exchange move needs batch.n_exchange");
                 any_exchange = true;
                 break;
@@ -306,7 +314,11 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     }
     if (any_exchange)
         for (int m = 0; m < n_moves; ++m)
-            if (moves[m].chain & 4) return fail(QMC_ERR_UNSUPPORTED, "label groups cannot be combined with exchange moves on the GPU path");
+            if (moves[m].chain & 4) return fail(QMC_ERR_UNSUPPORTED, "rank-coded label groups cannot be combined with exchange moves: use run-coded groups (chain bit 3)");
+    if (any_runs)
+        for (int m = 0; m < n_moves; ++m)
+            if (moves[m].type != QMC_MOVE_CELL && !(moves[m].chain & 8))
+                return fail(QMC_ERR_INVALID, "run-coded label groups (chain bit 3) must be set on every displacement / exchange move of the table");
     if (any_exchange)
         for (int m = 0; m < n_moves; ++m)
             if (moves[m].type != QMC_MOVE_CELL && !moves[m].labels)

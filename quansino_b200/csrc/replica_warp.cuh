@@ -281,10 +281,19 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
     const bool p0 = C.per(0), p1 = C.per(1), p2 = C.per(2);
     const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);
     int cnt = 0, nq = 0;
-    for (int base = tile_first * 32; base < n_scan; base += 32 * tile_step) {
-        const int j = base + lane;
-        const bool valid = j < n_scan && j != i_excl;
-        const int jc = valid ? j : 0;
+    // one tile: 32 candidate atoms.  The distance arithmetic of a tile is a chain of dependent instructions (load -> nearest image
+    // -> r^2 -> compare -> ballot -> slot); a warp is latency-bound (7 warps per scheduler each progress as if alone), so TWO
+    // tiles are in flight per iteration: their chains are independent and interleave (profiles/r2_b_ilp.md).
+    struct Tile {
+        int j;
+        bool valid, any, ex_o, ex_n;
+        double neg_r2o, r2n;
+    };
+    auto measure = [&](const int base) {
+        Tile t;
+        t.j = base + lane;
+        t.valid = t.j < n_scan && t.j != i_excl;
+        const int jc = t.valid ? t.j : 0;
         const double xj = R.x(jc), yj = R.y(jc), zj = R.z(jc);
         bool fo = false, fn = false;
         const double dxo = axis_nearest_any(po[0], xj, A0, fo);
@@ -294,26 +303,38 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
         const double dyn = axis_nearest_any(pn[1], yj, A1, fn);
         const double dzn = axis_nearest_any(pn[2], zj, A2, fn);
         const double r2o = fma(dzo, dzo, fma(dyo, dyo, dxo * dxo));
-        const double r2n = fma(dzn, dzn, fma(dyn, dyn, dxn * dxn));
-        const bool in_o = valid && r2o < pot.cut_pre2, in_n = valid && r2n < pot.cut_pre2;
-        const bool any = in_o || in_n;
-        const unsigned b = __ballot_sync(FULL, any);
+        t.r2n = fma(dzn, dzn, fma(dyn, dyn, dxn * dxn));
+        const bool in_o = t.valid && r2o < pot.cut_pre2, in_n = t.valid && t.r2n < pot.cut_pre2;
+        t.any = in_o || in_n;
+        t.neg_r2o = __hiloint2double(__double2hiint(r2o) ^ (int)0x80000000, __double2loint(r2o));  // sign flip, integer pipe
+        // second images: only if the nearest image is inside (it is the closest of all images)
+        t.ex_o = in_o && fo;
+        t.ex_n = in_n && fn;
+        return t;
+    };
+    auto file = [&](const Tile &t) {
+        const unsigned b = __ballot_sync(FULL, t.any);
         const int pos = min(cnt + 2 * __popc(b & lt), RV::CAPE - 2);
-        if (any) {
-            const double neg_r2o = __hiloint2double(__double2hiint(r2o) ^ (int)0x80000000, __double2loint(r2o));  // sign flip, integer pipe
-            *reinterpret_cast<double2 *>(&R.lr(pos)) = make_double2(neg_r2o, r2n);
-            if (TRACK) R.l2(pos >> 1) = (uint16_t)j;
+        if (t.any) {
+            *reinterpret_cast<double2 *>(&R.lr(pos)) = make_double2(t.neg_r2o, t.r2n);
+            if (TRACK) R.l2(pos >> 1) = (uint16_t)t.j;
         }
-        if (TRACK && valid) R.pp(j) = any ? ((unsigned)pos | ((unsigned)(pos + 1) << 16)) : (NOPOS | (NOPOS << 16));
+        if (TRACK && t.valid) R.pp(t.j) = t.any ? ((unsigned)pos | ((unsigned)(pos + 1) << 16)) : (NOPOS | (NOPOS << 16));
         cnt += 2 * __popc(b);
-        // second images: only if the nearest image is inside (it is the closest of all images).  A flagged lane pushes two
-        // queue words (old side, new side; NOITEM for a side that is not flagged): at most 2 (n - 1) < QCAP words in total.
-        const bool exo = in_o && fo, exn = in_n && fn;
-        const unsigned bq = __ballot_sync(FULL, exo || exn);
-        if (exo || exn)
-            *reinterpret_cast<uint2 *>(queue + nq + 2 * __popc(bq & lt)) = make_uint2(exo ? (unsigned)j : NOITEM, exn ? ((unsigned)j | 0x8000u) : NOITEM);
+        // A flagged lane pushes two queue words (old side, new side; NOITEM for a side that is not flagged): at most
+        // 2 (n - 1) < QCAP words in total.
+        const unsigned bq = __ballot_sync(FULL, t.ex_o || t.ex_n);
+        if (t.ex_o || t.ex_n)
+            *reinterpret_cast<uint2 *>(queue + nq + 2 * __popc(bq & lt)) = make_uint2(t.ex_o ? (unsigned)t.j : NOITEM, t.ex_n ? ((unsigned)t.j | 0x8000u) : NOITEM);
         nq += 2 * __popc(bq);
+    };
+    int base = tile_first * 32;
+    for (; base + 32 * tile_step < n_scan; base += 64 * tile_step) {
+        const Tile ta = measure(base), tb = measure(base + 32 * tile_step);
+        file(ta);
+        file(tb);
     }
+    if (base < n_scan) file(measure(base));
     if (cnt > RV::CAPE) {
         status |= QMC_STATUS_LIST_OVERFLOW;
         cnt = RV::CAPE;

@@ -185,6 +185,86 @@ __device__ inline void shift_down(double *arr, int removed, int n) {
     }
 }
 
+
+// --- run-coded label groups (qmc_move_t.chain bit 3): non-negative labels never decrease with the atom index, a group is a
+// contiguous run of equal labels, the k-th unique label (np.unique sorts) is the k-th run ---------------------------------
+__device__ inline bool run_head(const int *lab, int n, int j) {
+    if (j >= n) return false;
+    const int v = __ldcg(lab + j);
+    return v >= 0 && (j == 0 || __ldcg(lab + j - 1) != v);
+}
+
+__device__ inline int run_count(const int *lab, int n) {
+    int c = 0;
+    for (int base = 0; base < n; base += 32) c += __popc(__ballot_sync(FULL, run_head(lab, n, base + lane_id())));
+    return c;
+}
+
+// first atom and length of the idx-th run (idx < run_count)
+__device__ inline void run_select(const int *lab, int n, int idx, int &first, int &len) {
+    int seen = 0;
+    first = -1;
+    for (int base = 0; base < n; base += 32) {
+        const unsigned b = __ballot_sync(FULL, run_head(lab, n, base + lane_id()));
+        const int c = __popc(b);
+        if (first < 0 && idx < seen + c) first = base + (int)__fns(b, 0, idx - seen + 1);
+        seen += c;
+    }
+    len = 0;
+    if (first < 0) return;
+    const int v = __ldcg(lab + first);
+    for (int base = first; base < n; base += 32) {  // equal labels directly behind the head
+        const int j = base + lane_id();
+        const unsigned same = __ballot_sync(FULL, j < n && __ldcg(lab + min(j, n - 1)) == v);
+        const int run = same == FULL ? 32 : __ffs(~same) - 1;
+        len += run;
+        if (run < 32) break;
+    }
+}
+
+// on_atoms_changed for a molecule (moves/displacement.py:226-253): `added` atoms get ONE new label behind the last atom, or the
+// `removed` atoms starting at `first` disappear (order preserved)
+__device__ inline void labels_molecule_changed(int *lab, int n, int added, int first, int removed, int default_label) {
+    const int lane = lane_id();
+    if (added > 0) {
+        const int mx = max_label(lab, n);
+        const int label = (default_label != QMC_LABEL_NONE && default_label != 0) ? default_label : (mx >= 0 ? mx + 1 : 0);
+        if (lane < added) lab[n + lane] = label;
+        __syncwarp();
+    } else if (removed > 0) {
+        for (int base = first; base < n - removed; base += 32) {
+            const int j = base + lane;
+            int t = 0;
+            if (j < n - removed) t = __ldcg(lab + j + removed);
+            __syncwarp();
+            if (j < n - removed) lab[j] = t;
+            __syncwarp();
+        }
+    }
+}
+
+// z-x-z Euler matrix A = B (C D) of ASE's euler_rotate for the angles 2 pi u[q] read as DEGREES (operations/displacement.py:192-200);
+// products and sums in numpy's order, without contraction
+__device__ inline void euler_matrix(const double u3[3], double A[9]) {
+    double sn[3], cs[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) sincos_2pi(__dmul_rn(__dmul_rn(TWO_PI, u3[q]), 3.141592653589793 / 180), sn[q], cs[q]);
+    const double Dm[9] = {cs[0], sn[0], 0.0, -sn[0], cs[0], 0.0, 0.0, 0.0, 1.0};
+    const double Cm[9] = {1.0, 0.0, 0.0, 0.0, cs[1], sn[1], 0.0, -sn[1], cs[1]};
+    const double Bm[9] = {cs[2], sn[2], 0.0, -sn[2], cs[2], 0.0, 0.0, 0.0, 1.0};
+    double CD[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const int i3 = q / 3 * 3, j3 = q % 3;
+        CD[q] = __dadd_rn(__dadd_rn(__dmul_rn(Cm[i3], Dm[j3]), __dmul_rn(Cm[i3 + 1], Dm[3 + j3])), __dmul_rn(Cm[i3 + 2], Dm[6 + j3]));
+    }
+#pragma unroll
+    for (int q = 0; q < 9; ++q) {
+        const int i3 = q / 3 * 3, j3 = q % 3;
+        A[q] = __dadd_rn(__dadd_rn(__dmul_rn(Bm[i3], CD[j3]), __dmul_rn(Bm[i3 + 1], CD[3 + j3])), __dmul_rn(Bm[i3 + 2], CD[6 + j3]));
+    }
+}
+
 // --- local energy delta -----------------------------------------------------------------------------------------
 struct Trial {
     double dE;     // energy difference of the whole system
@@ -279,15 +359,41 @@ __device__ __forceinline__ Trial local_delta_move(const PotDev &pot, const Rep<L
     T.sig_i = warp_sum(acc.snew);
     double part = 0.0, e_i_lane = 0.0;
     double2 *slots = reinterpret_cast<double2 *>(&R.lr(0));
-    for (int e = lane; e <= T.n2; e += 32) {
+    // one item = one touched atom (or, item n2, the moved atom): log + 2 exp, a long chain of dependent instructions.  While a
+    // second block of 32 items exists, TWO items per lane are in flight (independent chains interleave: the warp is latency-bound)
+    auto item = [&](const int e, double &en_out, double2 &slot_out) {
         const bool nb = e < T.n2;
         const int j = nb ? R.l2(e) : i;
         const double2 t = nb ? slots[e] : make_double2(0.0, 0.0);
         const double sn = nb ? R.sig(j) + (t.y - t.x) : T.sig_i;
-        const double en = emt_embed(pot, sn);
-        part += en - R.eat(j);
-        if (nb) slots[e] = make_double2(sn, en);
-        else e_i_lane = en;
+        en_out = emt_embed(pot, sn);
+        slot_out = make_double2(sn, en_out);
+        return en_out - R.eat(j);
+    };
+    int e0 = 0;
+    for (; e0 + 32 <= T.n2; e0 += 64) {  // (items e0 .. e0 + 63; the second block holds at least one item)
+        const int ea = e0 + lane, eb = e0 + 32 + lane;
+        const bool has_b = eb <= T.n2;
+        double en_a, en_b;
+        double2 sa, sb;
+        const double da = item(ea, en_a, sa), db = item(has_b ? eb : ea, en_b, sb);
+        part += da;
+        slots[ea] = sa;  // (ea < n2 here)
+        if (has_b) {
+            part += db;
+            if (eb < T.n2) slots[eb] = sb;
+            else e_i_lane = en_b;
+        }
+    }
+    if (e0 <= T.n2) {  // a last, single block
+        const int e = e0 + lane;
+        if (e <= T.n2) {
+            double en;
+            double2 sv;
+            part += item(e, en, sv);
+            if (e < T.n2) slots[e] = sv;
+            else e_i_lane = en;
+        }
     }
     T.eat_i = __shfl_sync(FULL, e_i_lane, T.n2 & 31);
     // pair part: rows (i, j) and (j, i) change together: 2 * 0.5 * (es + eo) = 2 * neghalfv0overgamma2 * dsigma2
@@ -527,14 +633,22 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
         int accepted = -1, moved = -1;
         double delta = __longlong_as_double(0x7ff8000000000000LL);  // NaN
 
-        if ((FEAT & F_COMPOSITE) && mv.type == QMC_MOVE_DISPLACEMENT && (mv.chain & 4)) {
+        if ((FEAT & F_COMPOSITE) && mv.type == QMC_MOVE_DISPLACEMENT && (mv.chain & 12)) {
             // Label groups (moves/displacement.py:164-167, 126-127): every atom whose label equals the selected one moves by the
             // SAME translation; one criteria evaluation.  `lab` holds dense group ranks (the library's caller normalises them in the
             // order of the sorted unique labels), so unique_labels[idx] is rank idx.  Same snapshot / commit / restore scheme as the
             // composite moves below.
-            const int ng = lab ? max_label(lab, R.n) + 1 : 0;
+            // (chain bit 3: the groups are runs of equal labels -- tables with a molecular exchange move -- and the members of the
+            // selected group are the atoms [g_first, g_first + g_len); bit 2: `lab` holds dense ranks, members have lab == g)
+            const bool runs = (mv.chain & 8) != 0;
+            const int ng = !lab ? 0 : runs ? run_count(lab, R.n) : max_label(lab, R.n) + 1;
             if (ng > 0) {
                 const int g = (int)(D.u_label * (double)ng);
+                int g_first = 0, g_len = 0;
+                if (runs) run_select(lab, R.n, g, g_first, g_len);
+                auto member = [&](const int j) {
+                    return runs ? (j >= g_first && j < g_first + g_len) : (j < R.n && __ldcg(lab + min(j, R.n - 1)) == g);
+                };
                 const bool rot = mv.op == QMC_OP_ROTATION || mv.op == QMC_OP_TRANSLATION_ROTATION;
                 const bool relocate = mv.op == QMC_OP_TRANSLATION || mv.op == QMC_OP_TRANSLATION_ROTATION;
                 double t[3] = {0.0, 0.0, 0.0}, tt[3] = {0.0, 0.0, 0.0}, A[9], com[3] = {0.0, 0.0, 0.0};
@@ -545,7 +659,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     int members_n = 0;
                     for (int base = 0; base < R.n; base += 32) {
                         const int j = base + lane;
-                        unsigned members = __ballot_sync(FULL, j < R.n && __ldcg(lab + min(j, R.n - 1)) == g);
+                        unsigned members = __ballot_sync(FULL, member(j));
                         while (members) {
                             const int i = base + __ffs(members) - 1;
                             members &= members - 1;
@@ -575,7 +689,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     double ms = 0.0;
                     for (int base = 0; base < R.n; base += 32) {
                         const int j = base + lane;
-                        unsigned members = __ballot_sync(FULL, j < R.n && __ldcg(lab + min(j, R.n - 1)) == g);
+                        unsigned members = __ballot_sync(FULL, member(j));
                         while (members) {
                             const int i = base + __ffs(members) - 1;
                             members &= members - 1;
@@ -629,7 +743,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                 int n_moved = 0;
                 for (int base = 0; base < R.n; base += 32) {
                     const int j = base + lane;
-                    unsigned members = __ballot_sync(FULL, j < R.n && __ldcg(lab + min(j, R.n - 1)) == g);
+                    unsigned members = __ballot_sync(FULL, member(j));
                     while (members) {
                         const int i = base + __ffs(members) - 1;
                         members &= members - 1;
@@ -917,6 +1031,149 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
             }
             __syncwarp();
             accepted = acc ? 1 : 0;
+        } else if ((FEAT & F_EXCHANGE) && (FEAT & F_COMPOSITE) && mv.type == QMC_MOVE_EXCHANGE && (mv.chain & 8)) {
+            // Molecular exchange (moves/exchange.py:88-176 with an `exchange_atoms` of several atoms, or any exchange placed by
+            // TranslationRotation): insertion = the molecule's atoms appended one after the other, each with the local delta of a
+            // single-atom insertion and committed at once (the next one sees it); deletion = the atoms of the selected label (a
+            // run of equal labels) taken out from the top down.  ONE criteria evaluation on the summed energy change, one
+            // particle; the snapshot in global memory is restored on reject.
+            const bool is_add = D.u_coin < mv.bias;
+            const int k_mol = a.b.n_exchange_atoms > 1 ? a.b.n_exchange_atoms : 1;
+            const double *tmpl = a.b.n_exchange_atoms >= 1 ? a.b.exchange_mol : a.b.exchange_pos;
+            const int n_before = R.n;
+            int pd = 0, first = -1, len = 0;
+            if (is_add) {
+                if (R.n + k_mol > nmax) status |= QMC_STATUS_CAPACITY;
+                else pd = 1;
+            } else {
+                const int nu = lab ? run_count(lab, R.n) : 0;
+                if (nu > 0) {
+                    run_select(lab, R.n, (int)(D.u_label * (double)nu), first, len);
+                    pd = -1;
+                }
+            }
+            if (pd != 0) {
+                for (int j = lane; j < n_before; j += 32) {  // snapshot of the last accepted state
+                    gx[j] = R.x(j);
+                    gy[j] = R.y(j);
+                    gz[j] = R.z(j);
+                    if (POT == QMC_POT_EMT) {
+                        gs[j] = R.sig(j);
+                        ge[j] = R.eat(j);
+                    }
+                }
+                __syncwarp();
+                double de_total = 0.0;
+                const double po0[3] = {0.0, 0.0, 0.0};
+                if (pd > 0) {
+                    // Translation.calculate (operations/displacement.py:170-175): uniform(0,1,(1,3)) @ cell - mean(molecule)
+                    double mean[3] = {0.0, 0.0, 0.0}, t[3], A[9], com[3] = {0.0, 0.0, 0.0};
+                    for (int q = 0; q < k_mol; ++q)
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) mean[d] = __dadd_rn(mean[d], tmpl[3 * q + d]);
+                    const double f[3] = {D.o0, D.o1, D.o2};
+#pragma unroll
+                    for (int d = 0; d < 3; ++d)
+                        t[d] = __dsub_rn(__dmul_rn(f[d], UNIFORM ? a.cell.L[d] : cell[d]), __ddiv_rn(mean[d], (double)k_mol));
+                    const bool rot = mv.op == QMC_OP_TRANSLATION_ROTATION;
+                    if (rot) {  // + Rotation.calculate (:192-200) of the still untranslated molecule; angles = extra draws 0, 1, 2
+                        double u3[3], d3;
+                        uniform_pair(key, attempt, grep, 64u, u3[0], u3[1]);
+                        uniform_pair(key, attempt, grep, 65u, u3[2], d3);
+                        euler_matrix(u3, A);
+                        const double m1 = __ddiv_rn(a.b.exchange_mass, (double)k_mol);  // single species
+                        double ms = 0.0;
+                        for (int q = 0; q < k_mol; ++q) {
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) com[d] = __dadd_rn(com[d], __dmul_rn(m1, tmpl[3 * q + d]));
+                            ms = __dadd_rn(ms, m1);
+                        }
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) com[d] = __ddiv_rn(com[d], ms);
+                    }
+                    for (int q = 0; q < k_mol; ++q) {
+                        const double tq[3] = {tmpl[3 * q], tmpl[3 * q + 1], tmpl[3 * q + 2]};
+                        double pn[3];
+                        if (rot) {
+                            const double rc[3] = {__dsub_rn(tq[0], com[0]), __dsub_rn(tq[1], com[1]), __dsub_rn(tq[2], com[2])};
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) {
+                                const double xn = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(A[3 * d], rc[0]), __dmul_rn(A[3 * d + 1], rc[1])), __dmul_rn(A[3 * d + 2], rc[2])), com[d]);
+                                pn[d] = __dadd_rn(tq[d], __dadd_rn(t[d], __dsub_rn(xn, tq[d])));
+                            }
+                        } else {
+#pragma unroll
+                            for (int d = 0; d < 3; ++d) pn[d] = __dadd_rn(tq[d], t[d]);
+                        }
+                        const int i = R.n;
+                        const Trial T = local_delta<LY>(pot, R, C, lane, lt, R.n, i, false, true, po0, pn, status);
+                        commit_trial<LY>(R, lane, T);
+                        if (lane == 0) {
+                            R.x(i) = pn[0];
+                            R.y(i) = pn[1];
+                            R.z(i) = pn[2];
+                            if (POT == QMC_POT_EMT) {
+                                R.sig(i) = T.sig_i;
+                                R.eat(i) = T.eat_i;
+                            }
+                        }
+                        R.n += 1;
+                        n_pairs += T.pairs;
+                        de_total += T.dE;
+                        __syncwarp();
+                    }
+                    moved = n_before;
+                } else {
+                    for (int q = len - 1; q >= 0; --q) {  // top down: the indices below stay valid
+                        const int i = first + q;
+                        const double po[3] = {R.x(i), R.y(i), R.z(i)};
+                        const Trial T = local_delta<LY>(pot, R, C, lane, lt, R.n, i, true, false, po, po0, status);
+                        commit_trial<LY>(R, lane, T);
+                        shift_down(&R.x(0), i, R.n);
+                        shift_down(&R.y(0), i, R.n);
+                        shift_down(&R.z(0), i, R.n);
+                        if (POT == QMC_POT_EMT) {
+                            shift_down(&R.sig(0), i, R.n);
+                            shift_down(&R.eat(0), i, R.n);
+                        }
+                        R.n -= 1;
+                        n_pairs += T.pairs;
+                        de_total += T.dE;
+                        __syncwarp();
+                    }
+                    moved = first;
+                }
+                delta = de_total;
+                bool ov;
+                const double prob = gc_probability(delta, pd, n_ex, a.b.accessible_volume, a.b.exchange_mass, temperature,
+                                                   a.b.chemical_potential, ov);
+                if (ov) status |= QMC_STATUS_EXP_OVERFLOW;
+                const bool acc = D.u_accept < prob;
+                if (acc) {
+                    // GrandCanonical.save_state (mc/gcmc.py:207-214): every registered move re-labels
+                    for (int q = 0; q < a.n_moves; ++q)
+                        if (a.mv[q].labels)
+                            labels_molecule_changed(a.mv[q].labels + (size_t)r * nmax, n_before, pd > 0 ? k_mol : 0, first, pd < 0 ? len : 0,
+                                                    a.mv[q].default_label);
+                    n_ex += pd;
+                    E += delta;
+                    __syncwarp();
+                    if (FEAT & F_LABELS) rebuild_movable(R, a.mv, a.n_moves, r, nmax, LY::LABW);
+                } else {
+                    R.n = n_before;
+                    for (int j = lane; j < n_before; j += 32) {
+                        R.x(j) = gx[j];
+                        R.y(j) = gy[j];
+                        R.z(j) = gz[j];
+                        if (POT == QMC_POT_EMT) {
+                            R.sig(j) = gs[j];
+                            R.eat(j) = ge[j];
+                        }
+                    }
+                }
+                __syncwarp();
+                accepted = acc ? 1 : 0;
+            }
         } else if ((FEAT & F_EXCHANGE) && mv.type == QMC_MOVE_EXCHANGE) {
             const bool is_add = D.u_coin < mv.bias;
             int pd = 0, i = -1;

@@ -125,25 +125,30 @@ class ExchangeContext(DisplacementContext):
 
     @exchange_atoms.setter
     def exchange_atoms(self, value) -> None:
-        """One exchange atom: an ASE-like ``Atoms`` of length 1, or ``(symbol, position)``."""
+        """The exchange species: an ASE-like ``Atoms`` (one atom, or a molecule of up to 8 atoms of the batch's species), or
+        ``(symbol, position)`` / ``(symbol, positions (k, 3))``."""
         from quansino_b200.calculators import ATOMIC_MASSES
 
         if value is None:
             self._exchange_atoms = None
             return
         if isinstance(value, (tuple, list)) and isinstance(value[0], str):
-            symbol, pos = value[0], np.asarray(value[1] if len(value) > 1 else (0.0, 0.0, 0.0), dtype=float)
-            mass = ATOMIC_MASSES[symbol]
+            symbol = value[0]
+            pos = np.atleast_2d(np.asarray(value[1] if len(value) > 1 else (0.0, 0.0, 0.0), dtype=float))
+            mass = ATOMIC_MASSES[symbol] * len(pos)
         else:
             symbols = list(value.get_chemical_symbols())
-            if len(symbols) != 1:
-                raise NotImplementedError("molecular exchange (more than one atom per insertion) is SURVEY.md section 8f")
-            symbol, pos, mass = symbols[0], np.asarray(value.positions[0], dtype=float), float(np.sum(value.get_masses()))
+            if len(set(symbols)) != 1:
+                raise NotImplementedError("single-species systems only on the GPU path: the exchange molecule must be of one species")
+            symbol, pos, mass = symbols[0], np.atleast_2d(np.asarray(value.positions, dtype=float)), float(np.sum(value.get_masses()))
         if symbol != self.batch.symbol:
             raise NotImplementedError("single-species systems only on the GPU path: the exchange atom must match the batch species")
+        if not 1 <= len(pos) <= 8:
+            raise NotImplementedError("exchange molecules of 1 to 8 atoms on the GPU path")
         self._exchange_atoms = value
-        self.batch.exchange_mass = float(mass)
-        self.batch.exchange_pos = tuple(float(x) for x in pos)
+        self.batch.exchange_mass = float(mass)  # of the whole molecule (mc/criteria.py:262: exchange_atoms.get_masses().sum())
+        self.batch.exchange_pos = tuple(float(x) for x in pos[0])
+        self.batch.exchange_mol = pos.copy()
 
     def to_dict(self) -> dict[str, Any]:
         return {

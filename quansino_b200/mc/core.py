@@ -160,6 +160,12 @@ class MonteCarlo:
         # Only the device label tables persist (they are the labels' state once exchange moves re-label them).
         n_atoms = None  # fetched (one device sync) only when a label table has to be created
         any_exchange = any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE for n in names)
+        # molecular exchange (several atoms per insertion, or TranslationRotation placement): every move of the table selects
+        # label GROUPS, coded as runs of equal labels (include/quansino_b200.h: chain bit 3)
+        molecular = any_exchange and (
+            len(np.atleast_2d(self.batch.exchange_mol)) > 1
+            or any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE and getattr(self.moves[n].move.operation, "op_code", -1) == _lib.OP_TRANSLATION_ROTATION for n in names)
+        )  # fmt: skip
         entries, keep, slots = [], [], {}
         for n in names:
             st = self.moves[n]
@@ -182,18 +188,24 @@ class MonteCarlo:
                 st._label_version = version
                 if n_atoms is None and (not hasattr(st, "_label_tensor") or (st._label_tensor is None and any_exchange)):
                     n_atoms = self.batch.n_atoms.cpu().numpy()
+                make_table = st.move.run_labels if molecular else st.move.validated_labels
                 if not hasattr(st, "_label_tensor"):
                     if any_exchange or not st.move.is_identity(n_atoms):
-                        lab = st.move.validated_labels(self.batch.R, self.batch.n_max, n_atoms)
+                        lab = make_table(self.batch.R, self.batch.n_max, n_atoms)
                         st._label_tensor = torch.from_numpy(lab).to(self.batch.device)
                     else:
                         st._label_tensor = None
                 elif st._label_tensor is None and any_exchange:
-                    lab = st.move.validated_labels(self.batch.R, self.batch.n_max, n_atoms)
+                    lab = make_table(self.batch.R, self.batch.n_max, n_atoms)
                     st._label_tensor = torch.from_numpy(lab).to(self.batch.device)
                 grouped = bool(getattr(st.move, "_grouped", False) or getattr(getattr(st.move, "moves", [None])[0], "_grouped", False))
                 # rotations and relocations of displacement moves live in the label-group path
                 grouped = grouped or any(c.type == _lib.MOVE_DISPLACEMENT and c.op in (_lib.OP_ROTATION, _lib.OP_TRANSLATION, _lib.OP_TRANSLATION_ROTATION) for c in chain)
+                if molecular:
+                    if len(chain) > 1 or chain[0].repeat > 1 or m.n_extra_ops:
+                        raise NotImplementedError("composite moves next to a molecular exchange move are not available on the GPU path")
+                    m.chain = 8  # run-coded label groups
+                    grouped = False
                 if grouped and (any_exchange or len(chain) > 1 or chain[0].repeat > 1 or m.type != _lib.MOVE_DISPLACEMENT or m.n_extra_ops):
                     raise NotImplementedError(
                         "label groups (several atoms per label, or labels not increasing with the atom index) cannot be combined "

@@ -81,6 +81,30 @@ class DisplacementMove(BaseMove):
                     v[movable] = np.unique(v[movable], return_inverse=True)[1].astype(np.int32)
         return out
 
+    def run_labels(self, n_replicas: int, n_max: int, n_atoms: np.ndarray) -> np.ndarray:
+        """int32 [R][n_max] label table for tables with a molecular exchange move (``qmc_move_t.chain`` bit 3): the label VALUES
+        as given, padding -1; the non-negative labels must not decrease with the atom index, so that every label is one
+        contiguous run and the k-th unique label is the k-th run (what ``arange`` and the reference's ``max + 1`` appending
+        produce and order-preserving deletions keep)."""
+        lab = np.asarray(self.labels)
+        if lab.ndim == 1:
+            lab = np.broadcast_to(lab, (n_replicas, lab.shape[0]))
+        if lab.shape[0] != n_replicas or lab.shape[1] > n_max:
+            raise ValueError("labels must have shape (n_atoms,) or (n_replicas, n_max)")
+        out = np.full((n_replicas, n_max), -1, dtype=np.int32)
+        out[:, : lab.shape[1]] = lab
+        for r in range(n_replicas):
+            if lab.shape[1] < n_atoms[r]:
+                raise ValueError("Labels must have the same length as the number of atoms.")
+            out[r, n_atoms[r] :] = -1
+            v = out[r, : n_atoms[r]]
+            v = v[v >= 0]
+            if len(v) and np.any(np.diff(v) < 0):
+                raise NotImplementedError(
+                    "with a molecular exchange move the labels of every move must not decrease with the atom index on the GPU path"
+                )
+        return out
+
     def is_identity(self, n_atoms: np.ndarray) -> bool:
         lab = np.asarray(self.labels)
         if lab.ndim != 1 or self.default_label or (self.move_type == _lib.MOVE_DISPLACEMENT and getattr(self.operation, "op_code", -1) in _GROUP_OPS):

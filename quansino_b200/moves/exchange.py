@@ -8,8 +8,9 @@ from quansino_b200.operations.displacement import Translation
 
 
 class ExchangeMove(DisplacementMove):
-    """``ExchangeMove(labels, operation=None, bias_towards_insert=0.5, apply_constraints=True)``: insert one exchange
-    atom at a uniform point of the cell, or delete the atom of a random non-negative label."""
+    """``ExchangeMove(labels, operation=None, bias_towards_insert=0.5, apply_constraints=True)``: insert the exchange species
+    (one atom, or a molecule placed by ``Translation`` / ``TranslationRotation``) at a uniform point of the cell, or delete the
+    atoms of a random non-negative label."""
 
     move_type = _lib.MOVE_EXCHANGE
 
@@ -32,7 +33,7 @@ class ExchangeMove(DisplacementMove):
         m = _lib.Move()
         m.type = self.move_type
         m.op, m.step = self.operation.lower()
-        if m.op != _lib.OP_TRANSLATION:
+        if m.op not in (_lib.OP_TRANSLATION, _lib.OP_TRANSLATION_ROTATION):  # (the latter is what the reference prescribes for molecules)
             raise NotImplementedError(f"{type(self.operation).__name__} is not an exchange operation of the GPU path")
         m.bias_insert = float(self.bias_towards_insert)
         m.default_label = _lib.LABEL_NONE if self.default_label is None else int(self.default_label)

@@ -10,7 +10,7 @@ import pytest
 from tests.golden_cases import CASES, load, oracle_replay
 
 
-@pytest.mark.parametrize("name", [*CASES, "gc_molecule"])  # gc_molecule: oracle only, the device path does not lower it yet
+@pytest.mark.parametrize("name", CASES)
 def test_oracle_reproduces_genuine_quansino(name):
     g = load(name)
     rep, tr, labels = oracle_replay(g)
