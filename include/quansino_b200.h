@@ -282,6 +282,19 @@ int qmc_fbmc_step_v(const qmc_potential_t *pot, const qmc_batch_t *batch, double
 int qmc_pt_swap(double *temperatures_all, const double *energies_all, int32_t n_global, uint64_t seed,
                 uint64_t round, int8_t *accepted, void *stream);
 
+/* The multi-GPU part of the path for hosts without torch.distributed (the reference has none: `MultiDriver` is an
+ * empty stub, src/quansino/mc/driver.py:349-371).  `nccl_comm` is an `ncclComm_t` of the caller (one rank per GPU, replicas sharded
+ * in equal contiguous blocks, rank-major), passed as `void *`; NULL = a single rank.  NCCL is resolved at run time from the
+ * host process (or libnccl.so.2), the library does not link against it.
+ *
+ * qmc_pt_exchange: one parallel-tempering round -- all-gather of the n_local temperatures and energies of every rank into
+ * `scratch` (device, 2 * n_local * ranks doubles), `qmc_pt_swap` on every rank (identical decisions from the shared stream), the
+ * rank's slice of the permuted temperatures written back to `temperature_local`.  Configurations never move.
+ * qmc_reduce_observables: in-place sum of `n` doubles (device) over the ranks (acceptance counts, energy sums, ...). */
+int qmc_pt_exchange(void *nccl_comm, double *temperature_local, const double *energy_local, int32_t n_local, uint64_t seed,
+                    uint64_t round, double *scratch, int8_t *accepted, void *stream);
+int qmc_reduce_observables(void *nccl_comm, double *values, int32_t n, void *stream);
+
 /* measured-FP64-peak microbenchmark used by bench.py for the roofline denominator: runs a register-resident
  * DFMA loop and returns achieved FLOP/s in *flops (2 flop per DFMA). */
 int qmc_fp64_peak(double *flops, void *stream);

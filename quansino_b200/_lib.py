@@ -29,7 +29,7 @@ EXPORTS = (
     "qmc_abi_version", "qmc_last_error", "qmc_device_count", "qmc_sweep_smem_per_replica", "qmc_energy_full", "qmc_atom_energies",
     "qmc_forces_full", "qmc_sweep", "qmc_hmc", "qmc_hmc_workspace_bytes", "qmc_pt_swap", "qmc_fp64_peak",
     "qmc_sweep_host", "qmc_debug_math", "qmc_fbmc_step", "qmc_fbmc_step_v", "qmc_batch_create", "qmc_batch_destroy", "qmc_batch_upload",
-    "qmc_batch_download", "qmc_batch_view", "qmc_batch_labels", "qmc_nbr_row_words", "qmc_batch_enable_rows",
+    "qmc_batch_download", "qmc_batch_view", "qmc_batch_labels", "qmc_nbr_row_words", "qmc_batch_enable_rows", "qmc_pt_exchange", "qmc_reduce_observables",
 )  # fmt: skip
 
 
@@ -147,6 +147,10 @@ def load() -> C.CDLL:
     L.qmc_hmc_workspace_bytes.argtypes = [C.POINTER(Potential), C.POINTER(Batch)]
     L.qmc_hmc_workspace_bytes.restype = i64
     L.qmc_pt_swap.argtypes = [vp, vp, i32, u64, u64, vp, vp]
+    L.qmc_pt_exchange.argtypes = [vp, vp, vp, i32, u64, u64, vp, vp, vp]
+    L.qmc_pt_exchange.restype = C.c_int
+    L.qmc_reduce_observables.argtypes = [vp, vp, i32, vp]
+    L.qmc_reduce_observables.restype = C.c_int
     L.qmc_fp64_peak.argtypes = [C.POINTER(C.c_double), vp]
     L.qmc_sweep_host.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.POINTER(Move), i32, u64, u64, i32, C.POINTER(Trace)]
     L.qmc_fbmc_step.argtypes = [C.POINTER(Potential), C.POINTER(Batch), C.c_double, u64, u64, vp, i32, vp, vp, vp, i64, vp]

@@ -62,7 +62,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             sys.stderr.write(f"--- {obj.name}\n{log}")
     if any(rc != 0 for _, rc, _ in results):
         raise RuntimeError("nvcc failed building libquansino_b200.so")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *[str(o) for o, _, _ in results]]
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *[str(o) for o, _, _ in results], "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

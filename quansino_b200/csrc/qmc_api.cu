@@ -1,6 +1,7 @@
 // C ABI of quansino_b200 (include/quansino_b200.h): argument checking, launch geometry, kernel launches.
 // No CPU fallback anywhere: without a CUDA device every compute entry point returns QMC_ERR_NO_DEVICE.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -481,6 +482,77 @@ int qmc_pt_swap(double *temperatures_all, const double *energies_all, int32_t n_
     if (!temperatures_all || !energies_all || n_global < 0) return fail(QMC_ERR_INVALID, "bad arguments");
     if (n_global < 2) return QMC_OK;
     return qmc::pt_swap(temperatures_all, energies_all, n_global, seed, round, accepted, (cudaStream_t)stream, g_err, sizeof(g_err));
+}
+
+// ---- multi-GPU part of the path behind the C ABI: NCCL is resolved at run time -- first among the symbols the host
+// process has already loaded (the communicator must come from the same NCCL the calls go to), then from libnccl.so.2 -- so the
+// library itself has no link-time dependency on it.
+namespace {
+struct Nccl {
+    int (*all_gather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    int (*all_reduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*comm_count)(void *, int *) = nullptr;
+    int (*comm_rank)(void *, int *) = nullptr;
+    const char *(*error_string)(int) = nullptr;
+    bool ok = false;
+};
+const Nccl &nccl() {
+    static Nccl n = [] {
+        Nccl x;
+        void *h = RTLD_DEFAULT;  // (a null handle: "not found" must be told apart by the lookup, not by the handle)
+        if (!dlsym(h, "ncclAllGather")) {
+            h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+            if (!h) return x;
+        }
+        x.all_gather = (decltype(x.all_gather))dlsym(h, "ncclAllGather");
+        x.all_reduce = (decltype(x.all_reduce))dlsym(h, "ncclAllReduce");
+        x.comm_count = (decltype(x.comm_count))dlsym(h, "ncclCommCount");
+        x.comm_rank = (decltype(x.comm_rank))dlsym(h, "ncclCommUserRank");
+        x.error_string = (decltype(x.error_string))dlsym(h, "ncclGetErrorString");
+        x.ok = x.all_gather && x.all_reduce && x.comm_count && x.comm_rank;
+        return x;
+    }();
+    return n;
+}
+constexpr int NCCL_FLOAT64 = 8, NCCL_SUM = 0;  // ncclDataType_t / ncclRedOp_t values of nccl.h
+int nccl_fail(int rc, const char *what) {
+    return fail(QMC_ERR_CUDA, "%s failed: %s", what, nccl().error_string ? nccl().error_string(rc) : "NCCL error");
+}
+}  // namespace
+
+int qmc_pt_exchange(void *nccl_comm, double *temperature_local, const double *energy_local, int32_t n_local, uint64_t seed, uint64_t round,
+                    double *scratch, int8_t *accepted, void *stream) {
+    if (!temperature_local || !energy_local || !scratch || n_local < 0) return fail(QMC_ERR_INVALID, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    int world = 1, rank = 0;
+    if (nccl_comm) {
+        if (!nccl().ok) return fail(QMC_ERR_UNSUPPORTED, "NCCL is not available in this process (libnccl.so.2 not found)");
+        int rc;
+        if ((rc = nccl().comm_count(nccl_comm, &world))) return nccl_fail(rc, "ncclCommCount");
+        if ((rc = nccl().comm_rank(nccl_comm, &rank))) return nccl_fail(rc, "ncclCommUserRank");
+    }
+    const int n_global = n_local * world;
+    double *t_all = scratch, *e_all = scratch + n_global;
+    if (world > 1) {  // the only collective of the path: 2 x n_global doubles, latency bound
+        int rc;
+        if ((rc = nccl().all_gather(temperature_local, t_all, (size_t)n_local, NCCL_FLOAT64, nccl_comm, s))) return nccl_fail(rc, "ncclAllGather");
+        if ((rc = nccl().all_gather(energy_local, e_all, (size_t)n_local, NCCL_FLOAT64, nccl_comm, s))) return nccl_fail(rc, "ncclAllGather");
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(t_all, temperature_local, (size_t)n_local * 8, cudaMemcpyDeviceToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(e_all, energy_local, (size_t)n_local * 8, cudaMemcpyDeviceToDevice, s));
+    }
+    int rc = qmc_pt_swap(t_all, e_all, n_global, seed, round, accepted, stream);  // the same decisions on every rank
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(temperature_local, t_all + (size_t)rank * n_local, (size_t)n_local * 8, cudaMemcpyDeviceToDevice, s));
+    return QMC_OK;
+}
+
+int qmc_reduce_observables(void *nccl_comm, double *values, int32_t n, void *stream) {
+    if (!values || n < 0) return fail(QMC_ERR_INVALID, "bad arguments");
+    if (!nccl_comm || n == 0) return QMC_OK;
+    if (!nccl().ok) return fail(QMC_ERR_UNSUPPORTED, "NCCL is not available in this process (libnccl.so.2 not found)");
+    const int rc = nccl().all_reduce(values, values, (size_t)n, NCCL_FLOAT64, NCCL_SUM, nccl_comm, (cudaStream_t)stream);
+    return rc ? nccl_fail(rc, "ncclAllReduce") : QMC_OK;
 }
 
 int qmc_fp64_peak(double *flops, void *stream) {

@@ -536,3 +536,29 @@ def test_forced_moves_match_oracle(cuda_lib):
         assert np.all((per_step == 1).sum(axis=1) == 4)  # probability 0: exactly the forced ones
         assert np.all((per_step == 2).sum(axis=1) >= 1)
     assert len({tuple(np.where(move[r].reshape(steps, M)[0] == 1)[0]) for r in range(R)}) > 1  # placements differ between replicas
+
+
+def test_c_abi_exchange_and_reduction_single_rank(cuda_lib):
+    """`qmc_pt_exchange` / `qmc_reduce_observables` without a communicator (one rank): the exchange equals `qmc_pt_swap` on the
+    local arrays, the reduction is the identity.  (Two ranks over NCCL: tests/nccl_c_abi.py, run under torchrun.)"""
+    import torch
+
+    from quansino_b200 import _lib
+
+    lib = cuda_lib
+    n = 16
+    rng = np.random.default_rng(8)
+    temps = 300.0 * 2.0 ** (rng.permutation(n) / (n - 1))
+    energies = 1.0 + 0.01 * temps + rng.normal(scale=0.2, size=n)
+    t_a, t_b = torch.from_numpy(temps.copy()).cuda(), torch.from_numpy(temps.copy()).cuda()
+    e = torch.from_numpy(energies).cuda()
+    scratch = torch.zeros(2 * n, dtype=torch.float64, device="cuda")
+    acc_a, acc_b = torch.zeros(n, dtype=torch.int8, device="cuda"), torch.zeros(n, dtype=torch.int8, device="cuda")
+    for rnd in range(4):
+        _lib.check(lib.qmc_pt_exchange(None, t_a.data_ptr(), e.data_ptr(), n, 99, rnd, scratch.data_ptr(), acc_a.data_ptr(), None))
+        _lib.check(lib.qmc_pt_swap(t_b.data_ptr(), e.data_ptr(), n, 99, rnd, acc_b.data_ptr(), None))
+        assert torch.equal(t_a, t_b) and torch.equal(acc_a, acc_b)
+    assert not np.array_equal(t_a.cpu().numpy(), temps)
+    v = torch.arange(5, dtype=torch.float64, device="cuda")
+    _lib.check(lib.qmc_reduce_observables(None, v.data_ptr(), 5, None))
+    assert torch.equal(v.cpu(), torch.arange(5, dtype=torch.float64))
