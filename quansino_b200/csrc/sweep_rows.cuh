@@ -58,7 +58,9 @@ struct LayoutR {
                                             // squared displacement, E, 1 / kT
     static constexpr int RED = PS + 14;     // NW x 4 doubles: per-warp partial sums
     static constexpr int MVT = RED + NW * 4;  // move table: cdf[QMC_MAX_MOVES], step[QMC_MAX_MOVES], then (type, op, axes, -) ints per move
-    static constexpr int DRAW_B = (MVT + 4 * QMC_MAX_MOVES) * 8;      // 2 groups x DRAW_AHEAD attempts x 4 blocks x double2
+    static constexpr int PROP = MVT + 4 * QMC_MAX_MOVES;  // NW > 1: three proposals, 8 doubles each (translation[3], u_accept, o0, then 4 ints + pad)
+    static constexpr int SROW = PROP + (NW > 1 ? 24 : 0);  // NW > 1: three row buffers shared by the warps of the replica
+    static constexpr int DRAW_B = (SROW + (NW > 1 ? 3 * ROWW / 2 : 0)) * 8;  // 2 groups x DRAW_AHEAD attempts x 4 blocks x double2
     static constexpr int CNT_B = DRAW_B + 2 * DRAW_AHEAD * 64;        // counters + status, pair evaluations, next move, next atom
     static constexpr int LABW = round_up(NS, 32) / 32;
     static constexpr int LABBIT_B = CNT_B + (QMC_MAX_MOVES * 3 + 4) * 4;
@@ -66,7 +68,9 @@ struct LayoutR {
     // ---- one region per warp: slot pairs (double2), atom index per pair (+ sentinel), two row buffers ----
     static constexpr int L2_OFF = CAPW * 16;
     static constexpr int ROW_OFF = round_up(L2_OFF + (CAPW + 2) * 2, 16);
-    static constexpr int REG_B = ROW_OFF + 2 * ROWW * 4;
+    static constexpr int NROWBUF = NW == 1 ? 2 : 1;  // (NW > 1: displacement rows come through the shared buffers; the full
+                                                      // evaluation refills its single buffer right after the row pass)
+    static constexpr int REG_B = ROW_OFF + NROWBUF * ROWW * 4;
     static constexpr int BYTES = round_up(REG0_B + NW * REG_B, 16);
     // launch geometry: one wide CTA per SM, as many replicas as shared memory and the 72-register budget (28 warps) allow
     static constexpr int fit = (SMEM_PER_SM - 1024) / BYTES;
@@ -94,6 +98,8 @@ struct RepR {
     __device__ __forceinline__ double &mv_cdf(int m) const { return b[LY::MVT + m]; }
     __device__ __forceinline__ double &mv_step(int m) const { return b[LY::MVT + QMC_MAX_MOVES + m]; }
     __device__ __forceinline__ int4 &mv_info(int m) const { return reinterpret_cast<int4 *>(b + LY::MVT + 2 * QMC_MAX_MOVES)[m]; }
+    __device__ __forceinline__ double *prop(int which) const { return b + LY::PROP + 8 * which; }
+    __device__ __forceinline__ uint32_t *srow(int which) const { return reinterpret_cast<uint32_t *>(b + LY::SROW) + which * LY::ROWW; }
     __device__ __forceinline__ double2 *draws() const { return reinterpret_cast<double2 *>(reinterpret_cast<char *>(b) + LY::DRAW_B); }
     __device__ __forceinline__ uint32_t *counts() const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(b) + LY::CNT_B); }
     __device__ __forceinline__ uint32_t *labbits(int m) const { return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(b) + LY::LABBIT_B) + m * LY::LABW; }
@@ -305,6 +311,29 @@ __device__ __forceinline__ Trial local_delta_rows(const PotDev &pot, const RepR<
         return T;
     }
     double s1 = warp_sum(acc.snew);
+    double2 *const sl2 = slots;
+    // embedding of the touched atoms this warp owns: the first entry of an atom sums the terms of its further images
+    auto embed_items = [&](const int total, double &part, double &e_i_lane) {
+        for (int e = lane; e < total; e += 32) {
+            const bool nb = e < cnt;
+            const int j = nb ? (int)R.l2(e) : i;
+            const bool head = !nb || e == 0 || (int)R.l2(e - 1) != j;
+            if (head) {
+                double2 t = nb ? sl2[e] : make_double2(0.0, 0.0);
+                if (nb)
+                    for (int q = e + 1; (int)R.l2(q) == j; ++q) {  // further images of the same atom
+                        const double2 u = sl2[q];
+                        t.x += u.x;
+                        t.y += u.y;
+                    }
+                const double sn = nb ? R.sig(j) + (t.y - t.x) : T.sig_i;
+                const double en = emt_embed(pot, sn);
+                part += en - R.eat(j);
+                if (nb) sl2[e] = make_double2(sn, en);
+                else e_i_lane = en;
+            }
+        }
+    };
     if (NW > 1) {  // both sums behind one barrier
         if (lane == 0) {
             R.red(warp * 4 + 0) = vs;
@@ -320,29 +349,12 @@ __device__ __forceinline__ Trial local_delta_rows(const PotDev &pot, const RepR<
     }
     T.sig_i = s1;
     double part = 0.0, e_i_lane = 0.0;
-    const int total = cnt + (warp == 0 ? 1 : 0);  // the moved atom is one more item of warp 0
-    for (int e = lane; e < total; e += 32) {
-        const bool nb = e < cnt;
-        const int j = nb ? (int)R.l2(e) : i;
-        const bool head = !nb || e == 0 || (int)R.l2(e - 1) != j;
-        if (head) {
-            double2 t = nb ? slots[e] : make_double2(0.0, 0.0);
-            if (nb)
-                for (int q = e + 1; (int)R.l2(q) == j; ++q) {  // further images of the same atom
-                    const double2 u = slots[q];
-                    t.x += u.x;
-                    t.y += u.y;
-                }
-            const double sn = nb ? R.sig(j) + (t.y - t.x) : T.sig_i;
-            const double en = emt_embed(pot, sn);
-            part += en - R.eat(j);
-            if (nb) slots[e] = make_double2(sn, en);
-            else e_i_lane = en;
-        }
-    }
+    embed_items(cnt + (warp == 0 ? 1 : 0), part, e_i_lane);  // the moved atom is one more item of warp 0
     if (warp == 0) T.eat_i = __shfl_sync(FULL, e_i_lane, cnt & 31);
     const double psum = rep_sum<NW>(R, warp, lane, 2, warp_sum(part));  // B2
     T.dE = psum + 2.0 * pot.neghalfv0overgamma2 * vs;
+    // (measured and rejected for NW = 4: evaluating the neighbours' embeddings before the exchange of the sums and the moved atom's
+    // embedding on every warp saves one barrier but costs 5 % -- 1.42e8 instead of 1.49e8 attempts/s on C3)
     __syncwarp();
     return T;
 }
@@ -376,11 +388,12 @@ __device__ __noinline__ FullEnergy full_energy_rows(const PotDev &pot, const Rep
     unsigned pairs = 0;
     const double Lx = C.axis(0).L, Ly = C.axis(1).L, Lz = C.axis(2).L;
     double epart = 0.0;
+    constexpr bool TWO = LY::NROWBUF == 2;
     if (warp < R.n) row_prefetch<LY::ROWW>(R.rowbuf(0), grows + (size_t)warp * LY::ROWW, lane);
     int which = 0;
-    for (int a = warp; a < R.n; a += NW, which ^= 1) {
+    for (int a = warp; a < R.n; a += NW, which ^= (TWO ? 1 : 0)) {
         row_wait();
-        if (a + NW < R.n) row_prefetch<LY::ROWW>(R.rowbuf(which ^ 1), grows + (size_t)(a + NW) * LY::ROWW, lane);
+        if (TWO && a + NW < R.n) row_prefetch<LY::ROWW>(R.rowbuf(which ^ 1), grows + (size_t)(a + NW) * LY::ROWW, lane);
         const uint32_t *row = R.rowbuf(which);
         const double xa = R.x(a), ya = R.y(a), za = R.z(a);
         const int len = (int)row[0];
@@ -399,6 +412,8 @@ __device__ __noinline__ FullEnergy full_energy_rows(const PotDev &pot, const Rep
             if (in) R.sl(cnt + __popc(b & lt)) = r2;  // <= len <= CAPS <= 2 CAPW doubles
             cnt += __popc(b);
         }
+        __syncwarp();
+        if (!TWO && a + NW < R.n) row_prefetch<LY::ROWW>(R.rowbuf(0), grows + (size_t)(a + NW) * LY::ROWW, lane);  // the buffer is free again
         __syncwarp();
         DeltaAcc acc = {0.0, 0.0, 0};
         eval_slots<RepR<LY>, false>(pot, R, lane, cnt, acc);
@@ -630,75 +645,273 @@ __global__ void __launch_bounds__(LayoutR<POT, NS, NW>::THREADS, 1) sweep_rows_k
         const int idx = (int)(u_label * (double)nu);
         return (FEAT & F_LABELS) ? select_bit(R.labbits(m), nullptr, LY::LABW, idx) : idx;
     };
-    const int k_end = a.n_attempts;
-    draw_group(R, key, a.attempt_base, (uint32_t)(a.b.replica_offset + r), lane, 0);
-    rep_sync_r<NW>();
-    int m_cur, i_cur;
-    {
-        const double2 d0 = R.draws()[0];
-        m_cur = select_move(d0.x);
-        i_cur = select_atom(m_cur, d0.y);
-    }
-    if (i_cur >= 0) row_prefetch<LY::ROWW>(R.rowbuf(0), row_of(i_cur), lane);
-
-    for (int k = 0; k < k_end; ++k) {
-        const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
-        const int dslot = k & (DRAW_AHEAD - 1), grp = (k / DRAW_AHEAD) & 1;
-        if (dslot == 0 && k + DRAW_AHEAD < k_end) {  // the group after this one (the launch's first group exists already)
-            draw_group(R, key, attempt + DRAW_AHEAD, (uint32_t)(a.b.replica_offset + opaque(r)), lane, grp ^ 1);
-            rep_sync_r<NW>();
+    if constexpr (NW == 1) {
+        const int k_end = a.n_attempts;
+        draw_group(R, key, a.attempt_base, (uint32_t)(a.b.replica_offset + r), lane, 0);
+        rep_sync_r<NW>();
+        int m_cur, i_cur;
+        {
+            const double2 d0 = R.draws()[0];
+            m_cur = select_move(d0.x);
+            i_cur = select_atom(m_cur, d0.y);
         }
-        const double2 *dk = R.draws() + (grp * DRAW_AHEAD + dslot) * 4;
-        // (u_accept is read where it is needed: nothing but the launch's persistent state should live across the list passes)
-        const double o0 = dk[1].x, o1 = dk[1].y, o2 = dk[2].x;
-        const int m = m_cur, i = i_cur;
-        const int4 mvi = R.mv_info(m);
-        const int mv_type = mvi.x, mv_op = mvi.y;
-        const double mv_step = R.mv_step(m);
-        // next attempt: selection now, prefetch below (after this attempt's row is safe)
-        int m_next = 0, i_next = -1;
-        if (k + 1 < k_end) {
-            const int k1 = k + 1;
-            const double2 dn = R.draws()[(((k1 / DRAW_AHEAD) & 1) * DRAW_AHEAD + (k1 & (DRAW_AHEAD - 1))) * 4];
-            m_next = select_move(dn.x);
-            i_next = select_atom(m_next, dn.y);
-        }
-        if (tid == 0) {  // parked for the next iteration (read back after the barrier that ends this attempt)
-            R.counts()[NSTAT + 2] = (uint32_t)m_next;
-            R.counts()[NSTAT + 3] = (uint32_t)i_next;
-        }
+        if (i_cur >= 0) row_prefetch<LY::ROWW>(R.rowbuf(0), row_of(i_cur), lane);
 
-        int accepted = -1, moved = -1;
-        double delta = __longlong_as_double(0x7ff8000000000000LL);  // NaN
+        for (int k = 0; k < k_end; ++k) {
+            const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
+            const int dslot = k & (DRAW_AHEAD - 1), grp = (k / DRAW_AHEAD) & 1;
+            if (dslot == 0 && k + DRAW_AHEAD < k_end) {  // the group after this one (the launch's first group exists already)
+                draw_group(R, key, attempt + DRAW_AHEAD, (uint32_t)(a.b.replica_offset + opaque(r)), lane, grp ^ 1);
+                rep_sync_r<NW>();
+            }
+            const double2 *dk = R.draws() + (grp * DRAW_AHEAD + dslot) * 4;
+            // (u_accept is read where it is needed: nothing but the launch's persistent state should live across the list passes)
+            const double o0 = dk[1].x, o1 = dk[1].y, o2 = dk[2].x;
+            const int m = m_cur, i = i_cur;
+            const int4 mvi = R.mv_info(m);
+            const int mv_type = mvi.x, mv_op = mvi.y;
+            const double mv_step = R.mv_step(m);
+            // next attempt: selection now, prefetch below (after this attempt's row is safe)
+            int m_next = 0, i_next = -1;
+            if (k + 1 < k_end) {
+                const int k1 = k + 1;
+                const double2 dn = R.draws()[(((k1 / DRAW_AHEAD) & 1) * DRAW_AHEAD + (k1 & (DRAW_AHEAD - 1))) * 4];
+                m_next = select_move(dn.x);
+                i_next = select_atom(m_next, dn.y);
+            }
+            if (tid == 0) {  // parked for the next iteration (read back after the barrier that ends this attempt)
+                R.counts()[NSTAT + 2] = (uint32_t)m_next;
+                R.counts()[NSTAT + 3] = (uint32_t)i_next;
+            }
 
-        if (mv_type == QMC_MOVE_DISPLACEMENT) {
-            if (i >= 0) {
-                row_wait();
-                const uint32_t *row = R.rowbuf(k & 1);
-                double po[3], pn[3], d2;
-                // The trial position must stay within the bound of the atom's build position (build metric).  If it does not, the
-                // rows are rebuilt (then the build position IS the old position) and the proposal is simply evaluated again, so that
-                // nothing but the launch's persistent state is alive across the (rare) rebuild.
+            int accepted = -1, moved = -1;
+            double delta = __longlong_as_double(0x7ff8000000000000LL);  // NaN
+
+            if (mv_type == QMC_MOVE_DISPLACEMENT) {
+                if (i >= 0) {
+                    row_wait();
+                    const uint32_t *row = R.rowbuf(k & 1);
+                    double po[3], pn[3], d2;
+                    // The trial position must stay within the bound of the atom's build position (build metric).  If it does not, the
+                    // rows are rebuilt (then the build position IS the old position) and the proposal is simply evaluated again, so that
+                    // nothing but the launch's persistent state is alive across the (rare) rebuild.
+                    for (int tries = 0;; ++tries) {
+                        double t[3];
+                        propose_translation(mv_op, mv_step, o0, o1, o2, t);
+                        po[0] = R.x(i), po[1] = R.y(i), po[2] = R.z(i);
+                        pn[0] = po[0] + t[0], pn[1] = po[1] + t[1], pn[2] = po[2] + t[2];
+                        const double *ref = reinterpret_cast<const double *>(row + 2);
+                        const double ux = CELLMOVES ? fma(pn[0], R.ps(0), -ref[0]) : pn[0] - ref[0];
+                        const double uy = CELLMOVES ? fma(pn[1], R.ps(1), -ref[1]) : pn[1] - ref[1];
+                        const double uz = CELLMOVES ? fma(pn[2], R.ps(2), -ref[2]) : pn[2] - ref[2];
+                        d2 = fma(uz, uz, fma(uy, uy, ux * ux));
+                        if (d2 <= bound2()) break;
+                        if (tries) {  // step > skin / 2: refused by the library beforehand
+                            flag(QMC_STATUS_LIST_OVERFLOW);
+                            break;
+                        }
+                        rebuild(cell);
+                        row_prefetch<LY::ROWW>(R.rowbuf(k & 1), row_of(i), lane);
+                        row_wait();
+                    }
+                    if (i_next >= 0) row_prefetch<LY::ROWW>(R.rowbuf((k + 1) & 1), row_of(i_next), lane);
+                    if (tid == 0) {  // parked until the commit
+                        R.ps(8) = pn[0];
+                        R.ps(9) = pn[1];
+                        R.ps(10) = pn[2];
+                        if (CELLMOVES) R.ps(11) = d2;
+                    }
+                    const Trial T = local_delta_rows<LY, NW>(pot, R, C, warp, lane, lt, row, i, po, pn);
+                    const unsigned np = __reduce_add_sync(FULL, (unsigned)T.pairs);
+                    if (lane == 0) atomicAdd(R.counts() + NSTAT + 1, np);
+                    delta = T.dE;
+                    int st = 0;
+                    const bool acc = metropolis(dk[2].y, -delta * R.ps(13), st);
+                    flag(st);
+                    if (acc) {
+                        commit_rows<LY>(R, lane, T);
+                        if (tid == 0) {
+                            R.x(i) = R.ps(8);
+                            R.y(i) = R.ps(9);
+                            R.z(i) = R.ps(10);
+                            if (POT == QMC_POT_EMT) {
+                                R.sig(i) = T.sig_i;
+                                R.eat(i) = T.eat_i;
+                            }
+                            if (CELLMOVES) R.ps(4) = fmax(R.ps(4), R.ps(11));
+                            R.ps(12) += delta;
+                        }
+                    }
+                    accepted = acc ? 1 : 0;
+                    moved = i;
+                } else if (i_next >= 0) {
+                    row_prefetch<LY::ROWW>(R.rowbuf((k + 1) & 1), row_of(i_next), lane);
+                }
+            } else if (CELLMOVES && mv_type == QMC_MOVE_CELL) {
+                // snapshot the last accepted state in global memory, deform in place, recompute everything through the rows
+                replica_to_global<POT, NW>(a.b, R, opaque(r), tid);
+                const double s = exp(__dadd_rn(-mv_step, __dmul_rn(mv_step - -mv_step, o0)));
+                const int mv_axes = mvi.z;
+                double ncell[3], scale[3];
+    #pragma unroll
+                for (int d = 0; d < 3; ++d) {
+                    ncell[d] = (((mv_axes >> d) & 1) ? s : 1.0) * cell[d];
+                    scale[d] = ncell[d] / cell[d];
+                }
+                // the rows must reach every pair of the TRIAL geometry: if the slack left by the committed displacements does not cover
+                // the compression, rebuild at the CURRENT geometry first (normal density; still valid if the trial is rejected)
+                set_metric(ncell);
+                if (!in_reach()) {
+                    rebuild(cell);
+                    set_metric(ncell);
+                }
+                for (int j = tid; j < R.n; j += 32 * NW) {
+                    R.x(j) = R.x(j) * scale[0];
+                    R.y(j) = R.y(j) * scale[1];
+                    R.z(j) = R.z(j) * scale[2];
+                }
+                if (!in_reach()) {  // a single deformation beyond skin / cutoff (12 % for Cu): rows of the trial geometry itself
+                    store_cell_r<NW>(R, ncell, a.b.pbc, pot.cut_pre, tid);
+                    rebuild(ncell);
+                }
+                const bool cell_ok = store_cell_r<NW>(R, ncell, a.b.pbc, pot.cut_pre, tid);
+                if (!cell_ok) flag(QMC_STATUS_CELL_TOO_SMALL);
+                const double E_old = R.ps(12);
+                double e_new = E_old;
+                if (cell_ok) {
+                    const FullEnergy fe = full_energy_rows<LY, NW>(pot, R, C, warp, lane, lt, row_of(0));
+                    e_new = fe.e;
+                    const unsigned np = __reduce_add_sync(FULL, fe.pairs);
+                    if (lane == 0) atomicAdd(R.counts() + NSTAT + 1, np);
+                }
+                delta = e_new - E_old;
+                const double v_new = fabs((ncell[0] * ncell[1]) * ncell[2]), v_old = fabs((cell[0] * cell[1]) * cell[2]);
+                const double kT = a.b.temperature[r] * KB;
+                const double x = -(delta + a.b.pressure * (v_new - v_old)) / kT + (double)(R.n + 1) * log(v_new / v_old);
+                int st = 0;
+                const bool acc = cell_ok && metropolis(dk[2].y, x, st);
+                flag(st);
+                rep_sync_r<NW>();  // everybody has read E_old
+                if (acc) {
+                    if (tid == 0) R.ps(12) = e_new;
+                    cell[0] = ncell[0];
+                    cell[1] = ncell[1];
+                    cell[2] = ncell[2];
+                } else {
+                    replica_from_global<POT, NW>(a.b, R, opaque(r), tid);
+                    store_cell_r<NW>(R, cell, a.b.pbc, pot.cut_pre, tid);
+                }
+                set_metric(cell);
+                if (!in_reach()) rebuild(cell);
+                if (i_next >= 0) row_prefetch<LY::ROWW>(R.rowbuf((k + 1) & 1), row_of(i_next), lane);
+                accepted = acc ? 1 : 0;
+            }
+
+            if (tid == 0) {
+                uint32_t *cnt = R.counts() + m * 3;
+                cnt[0] += 1u;
+                if (accepted == 1) cnt[1] += 1u;
+                if (accepted < 0) cnt[2] += 1u;
+            }
+            rep_sync_r<NW>();  // B3: the committed state (and the parked selection) is visible to every warp
+            if (tid == 0 && a.has_trace) {
+                const size_t ti = (size_t)r * a.n_attempts + k;
+                if (a.tr.move) a.tr.move[ti] = (int8_t)m;
+                if (a.tr.accepted) a.tr.accepted[ti] = (int8_t)accepted;
+                if (a.tr.energy) a.tr.energy[ti] = R.ps(12);
+                if (a.tr.delta) a.tr.delta[ti] = delta;
+                if (a.tr.moved) a.tr.moved[ti] = moved;
+            }
+            m_cur = (int)R.counts()[NSTAT + 2];
+            i_cur = (int)R.counts()[NSTAT + 3];
+            if (NW > 1) rep_sync_r<NW>();  // ... and read before the next attempt parks its own
+        }
+    } else {
+        // ---- NW warps per replica: the SCOUT.  The scalar part of an attempt (draws, move selection, atom, translation) depends on
+        // nothing but the random stream and the static tables, so the last warp -- which owns the fourth block of a row and is idle
+        // whenever a row has at most 96 entries -- works it out TWO ATTEMPTS AHEAD and publishes it in shared memory (prop[k % 3]),
+        // together with the row of the atom (cp.async into srow[k % 3]: a whole attempt passes before the row is needed, the rows of
+        // C3 live in HBM).  The other warps read the proposal, form the trial position and go straight to their block of the row:
+        // the scalar work leaves the critical path, and is done once instead of NW times (profiles/r2_a_rows.md: ~500 of a warp's
+        // ~1 080 instructions).  One cp.async group per published attempt, in order: "all but the newest group" = the next row.
+        constexpr int SCOUT = NW - 1;
+        const int k_end = a.n_attempts;
+        auto fetch = [&](const int k1, const int i) {  // SCOUT only: one group per attempt (empty if the attempt needs no row)
+            if (i >= 0) row_prefetch<LY::ROWW>(R.srow(k1 % 3), row_of(i), lane);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        auto publish = [&](const int k1) {  // SCOUT only: proposal of attempt k1 -> prop[k1 % 3], its row -> srow[k1 % 3] (in flight)
+            const unsigned long long att = a.attempt_base + (unsigned long long)k1;
+            if ((k1 & (DRAW_AHEAD - 1)) == 0) draw_group(R, key, att, (uint32_t)(a.b.replica_offset + opaque(r)), lane, 0);
+            const double2 *dk = R.draws() + (k1 & (DRAW_AHEAD - 1)) * 4;
+            const int m = select_move(dk[0].x);
+            const int i = select_atom(m, dk[0].y);
+            const int4 mvi = R.mv_info(m);
+            double t[3] = {0.0, 0.0, 0.0};
+            const bool disp = mvi.x == QMC_MOVE_DISPLACEMENT && i >= 0;
+            fetch(k1, disp ? i : -1);
+            if (disp) propose_translation(mvi.y, R.mv_step(m), dk[1].x, dk[1].y, dk[2].x, t);
+            if (lane == 0) {
+                double *P = R.prop(k1 % 3);
+                P[0] = t[0], P[1] = t[1], P[2] = t[2];
+                P[3] = dk[2].y;  // u_accept
+                P[4] = dk[1].x;  // o0: the cell move's draw
+                *reinterpret_cast<int4 *>(P + 6) = make_int4(m, i, mvi.x, mvi.z);
+            }
+        };
+        auto refetch = [&](const int k1) {  // SCOUT only: the rows were rebuilt after the row of attempt k1 had been fetched
+            if (k1 >= k_end) return;
+            const int4 q = *reinterpret_cast<const int4 *>(R.prop(k1 % 3) + 6);
+            fetch(k1, q.z == QMC_MOVE_DISPLACEMENT ? q.y : -1);
+        };
+        if (warp == SCOUT) {
+            publish(0);
+            if (k_end > 1) publish(1);
+            row_wait();
+        }
+        rep_sync_r<NW>();
+        for (int k = 0; k < k_end; ++k) {
+            const double *P = R.prop(k % 3);
+            const int4 pi = *reinterpret_cast<const int4 *>(P + 6);
+            const int m = pi.x, i = pi.y, mv_type = pi.z;
+            int accepted = -1, moved = -1;
+            double delta = __longlong_as_double(0x7ff8000000000000LL);  // NaN
+            const bool displace = mv_type == QMC_MOVE_DISPLACEMENT && i >= 0;
+            const uint32_t *row = R.srow(k % 3);
+            double po[3] = {0.0, 0.0, 0.0}, pn[3] = {0.0, 0.0, 0.0}, d2 = 0.0;
+            bool rebuilt = false;
+            if (displace) {
+                // trial position and its distance from the atom's build position (see the one-warp loop above); every warp decides alike
                 for (int tries = 0;; ++tries) {
-                    double t[3];
-                    propose_translation(mv_op, mv_step, o0, o1, o2, t);
                     po[0] = R.x(i), po[1] = R.y(i), po[2] = R.z(i);
-                    pn[0] = po[0] + t[0], pn[1] = po[1] + t[1], pn[2] = po[2] + t[2];
+                    pn[0] = po[0] + P[0], pn[1] = po[1] + P[1], pn[2] = po[2] + P[2];
                     const double *ref = reinterpret_cast<const double *>(row + 2);
                     const double ux = CELLMOVES ? fma(pn[0], R.ps(0), -ref[0]) : pn[0] - ref[0];
                     const double uy = CELLMOVES ? fma(pn[1], R.ps(1), -ref[1]) : pn[1] - ref[1];
                     const double uz = CELLMOVES ? fma(pn[2], R.ps(2), -ref[2]) : pn[2] - ref[2];
                     d2 = fma(uz, uz, fma(uy, uy, ux * ux));
                     if (d2 <= bound2()) break;
-                    if (tries) {  // step > skin / 2: refused by the library beforehand
+                    if (tries) {
                         flag(QMC_STATUS_LIST_OVERFLOW);
                         break;
                     }
                     rebuild(cell);
-                    row_prefetch<LY::ROWW>(R.rowbuf(k & 1), row_of(i), lane);
-                    row_wait();
+                    rebuilt = true;
+                    if (warp == SCOUT) {  // this attempt's row again, and (below) the next one's
+                        row_wait();
+                        row_prefetch<LY::ROWW>(R.srow(k % 3), row_of(i), lane);
+                        row_wait();
+                    }
+                    rep_sync_r<NW>();
                 }
-                if (i_next >= 0) row_prefetch<LY::ROWW>(R.rowbuf((k + 1) & 1), row_of(i_next), lane);
+            }
+            // the attempt after next (after a possible rebuild, so that its row is read from the rows that are valid now)
+            if (warp == SCOUT) {
+                if (rebuilt) refetch(k + 1);
+                if (k + 2 < k_end) publish(k + 2);
+                else asm volatile("cp.async.commit_group;" ::: "memory");  // keeps "all but the newest group" = the next row
+            }
+            if (displace) {
                 if (tid == 0) {  // parked until the commit
                     R.ps(8) = pn[0];
                     R.ps(9) = pn[1];
@@ -707,10 +920,10 @@ __global__ void __launch_bounds__(LayoutR<POT, NS, NW>::THREADS, 1) sweep_rows_k
                 }
                 const Trial T = local_delta_rows<LY, NW>(pot, R, C, warp, lane, lt, row, i, po, pn);
                 const unsigned np = __reduce_add_sync(FULL, (unsigned)T.pairs);
-                if (lane == 0) atomicAdd(R.counts() + NSTAT + 1, np);
+                if (lane == 0 && np) atomicAdd(R.counts() + NSTAT + 1, np);
                 delta = T.dE;
                 int st = 0;
-                const bool acc = metropolis(dk[2].y, -delta * R.ps(13), st);
+                const bool acc = metropolis(P[3], -delta * R.ps(13), st);
                 flag(st);
                 if (acc) {
                     commit_rows<LY>(R, lane, T);
@@ -728,87 +941,88 @@ __global__ void __launch_bounds__(LayoutR<POT, NS, NW>::THREADS, 1) sweep_rows_k
                 }
                 accepted = acc ? 1 : 0;
                 moved = i;
-            } else if (i_next >= 0) {
-                row_prefetch<LY::ROWW>(R.rowbuf((k + 1) & 1), row_of(i_next), lane);
-            }
-        } else if (CELLMOVES && mv_type == QMC_MOVE_CELL) {
-            // snapshot the last accepted state in global memory, deform in place, recompute everything through the rows
-            replica_to_global<POT, NW>(a.b, R, opaque(r), tid);
-            const double s = exp(__dadd_rn(-mv_step, __dmul_rn(mv_step - -mv_step, o0)));
-            const int mv_axes = mvi.z;
-            double ncell[3], scale[3];
+            } else if (CELLMOVES && mv_type == QMC_MOVE_CELL) {
+                replica_to_global<POT, NW>(a.b, R, opaque(r), tid);
+                const double mv_step = R.mv_step(m);
+                const double s = exp(__dadd_rn(-mv_step, __dmul_rn(mv_step - -mv_step, P[4])));
+                double ncell[3], scale[3];
 #pragma unroll
-            for (int d = 0; d < 3; ++d) {
-                ncell[d] = (((mv_axes >> d) & 1) ? s : 1.0) * cell[d];
-                scale[d] = ncell[d] / cell[d];
-            }
-            // the rows must reach every pair of the TRIAL geometry: if the slack left by the committed displacements does not cover
-            // the compression, rebuild at the CURRENT geometry first (normal density; still valid if the trial is rejected)
-            set_metric(ncell);
-            if (!in_reach()) {
-                rebuild(cell);
+                for (int d = 0; d < 3; ++d) {
+                    ncell[d] = (((pi.w >> d) & 1) ? s : 1.0) * cell[d];
+                    scale[d] = ncell[d] / cell[d];
+                }
                 set_metric(ncell);
+                if (!in_reach()) {
+                    rebuild(cell);
+                    set_metric(ncell);
+                }
+                for (int j = tid; j < R.n; j += 32 * NW) {
+                    R.x(j) = R.x(j) * scale[0];
+                    R.y(j) = R.y(j) * scale[1];
+                    R.z(j) = R.z(j) * scale[2];
+                }
+                if (!in_reach()) {
+                    store_cell_r<NW>(R, ncell, a.b.pbc, pot.cut_pre, tid);
+                    rebuild(ncell);
+                }
+                const bool cell_ok = store_cell_r<NW>(R, ncell, a.b.pbc, pot.cut_pre, tid);
+                if (!cell_ok) flag(QMC_STATUS_CELL_TOO_SMALL);
+                const double E_old = R.ps(12);
+                double e_new = E_old;
+                if (cell_ok) {
+                    const FullEnergy fe = full_energy_rows<LY, NW>(pot, R, C, warp, lane, lt, row_of(0));
+                    e_new = fe.e;
+                    const unsigned np = __reduce_add_sync(FULL, fe.pairs);
+                    if (lane == 0) atomicAdd(R.counts() + NSTAT + 1, np);
+                }
+                delta = e_new - E_old;
+                const double v_new = fabs((ncell[0] * ncell[1]) * ncell[2]), v_old = fabs((cell[0] * cell[1]) * cell[2]);
+                const double kT = a.b.temperature[r] * KB;
+                const double x = -(delta + a.b.pressure * (v_new - v_old)) / kT + (double)(R.n + 1) * log(v_new / v_old);
+                int st = 0;
+                const bool acc = cell_ok && metropolis(P[3], x, st);
+                flag(st);
+                rep_sync_r<NW>();  // everybody has read E_old
+                if (acc) {
+                    if (tid == 0) R.ps(12) = e_new;
+                    cell[0] = ncell[0];
+                    cell[1] = ncell[1];
+                    cell[2] = ncell[2];
+                } else {
+                    replica_from_global<POT, NW>(a.b, R, opaque(r), tid);
+                    store_cell_r<NW>(R, cell, a.b.pbc, pot.cut_pre, tid);
+                }
+                set_metric(cell);
+                if (!in_reach()) rebuild(cell);
+                // the rows may have been rebuilt since the scout fetched the rows of the next two attempts: fetch them again
+                if (warp == SCOUT) {
+                    row_wait();
+                    refetch(k + 1);
+                    refetch(k + 2);
+                    if (k + 2 >= k_end) asm volatile("cp.async.commit_group;" ::: "memory");
+                }
+                accepted = acc ? 1 : 0;
             }
-            for (int j = tid; j < R.n; j += 32 * NW) {
-                R.x(j) = R.x(j) * scale[0];
-                R.y(j) = R.y(j) * scale[1];
-                R.z(j) = R.z(j) * scale[2];
+            if (tid == 0) {
+                uint32_t *cnt = R.counts() + m * 3;
+                cnt[0] += 1u;
+                if (accepted == 1) cnt[1] += 1u;
+                if (accepted < 0) cnt[2] += 1u;
             }
-            if (!in_reach()) {  // a single deformation beyond skin / cutoff (12 % for Cu): rows of the trial geometry itself
-                store_cell_r<NW>(R, ncell, a.b.pbc, pot.cut_pre, tid);
-                rebuild(ncell);
+            if (warp == SCOUT) {  // the next attempt's row has landed before the barrier publishes it (the one after may be in flight)
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+                __syncwarp();
             }
-            const bool cell_ok = store_cell_r<NW>(R, ncell, a.b.pbc, pot.cut_pre, tid);
-            if (!cell_ok) flag(QMC_STATUS_CELL_TOO_SMALL);
-            const double E_old = R.ps(12);
-            double e_new = E_old;
-            if (cell_ok) {
-                const FullEnergy fe = full_energy_rows<LY, NW>(pot, R, C, warp, lane, lt, row_of(0));
-                e_new = fe.e;
-                const unsigned np = __reduce_add_sync(FULL, fe.pairs);
-                if (lane == 0) atomicAdd(R.counts() + NSTAT + 1, np);
+            rep_sync_r<NW>();               // B3: committed state, next proposal and its row are visible to every warp
+            if (tid == 0 && a.has_trace) {
+                const size_t ti = (size_t)r * a.n_attempts + k;
+                if (a.tr.move) a.tr.move[ti] = (int8_t)m;
+                if (a.tr.accepted) a.tr.accepted[ti] = (int8_t)accepted;
+                if (a.tr.energy) a.tr.energy[ti] = R.ps(12);
+                if (a.tr.delta) a.tr.delta[ti] = delta;
+                if (a.tr.moved) a.tr.moved[ti] = moved;
             }
-            delta = e_new - E_old;
-            const double v_new = fabs((ncell[0] * ncell[1]) * ncell[2]), v_old = fabs((cell[0] * cell[1]) * cell[2]);
-            const double kT = a.b.temperature[r] * KB;
-            const double x = -(delta + a.b.pressure * (v_new - v_old)) / kT + (double)(R.n + 1) * log(v_new / v_old);
-            int st = 0;
-            const bool acc = cell_ok && metropolis(dk[2].y, x, st);
-            flag(st);
-            rep_sync_r<NW>();  // everybody has read E_old
-            if (acc) {
-                if (tid == 0) R.ps(12) = e_new;
-                cell[0] = ncell[0];
-                cell[1] = ncell[1];
-                cell[2] = ncell[2];
-            } else {
-                replica_from_global<POT, NW>(a.b, R, opaque(r), tid);
-                store_cell_r<NW>(R, cell, a.b.pbc, pot.cut_pre, tid);
-            }
-            set_metric(cell);
-            if (!in_reach()) rebuild(cell);
-            if (i_next >= 0) row_prefetch<LY::ROWW>(R.rowbuf((k + 1) & 1), row_of(i_next), lane);
-            accepted = acc ? 1 : 0;
         }
-
-        if (tid == 0) {
-            uint32_t *cnt = R.counts() + m * 3;
-            cnt[0] += 1u;
-            if (accepted == 1) cnt[1] += 1u;
-            if (accepted < 0) cnt[2] += 1u;
-        }
-        rep_sync_r<NW>();  // B3: the committed state (and the parked selection) is visible to every warp
-        if (tid == 0 && a.has_trace) {
-            const size_t ti = (size_t)r * a.n_attempts + k;
-            if (a.tr.move) a.tr.move[ti] = (int8_t)m;
-            if (a.tr.accepted) a.tr.accepted[ti] = (int8_t)accepted;
-            if (a.tr.energy) a.tr.energy[ti] = R.ps(12);
-            if (a.tr.delta) a.tr.delta[ti] = delta;
-            if (a.tr.moved) a.tr.moved[ti] = moved;
-        }
-        m_cur = (int)R.counts()[NSTAT + 2];
-        i_cur = (int)R.counts()[NSTAT + 3];
-        if (NW > 1) rep_sync_r<NW>();  // ... and read before the next attempt parks its own
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
 
