@@ -118,6 +118,7 @@ def c5(R=64, repeat=8, n_steps=100, attempts=1):
     mc = HamiltonianCanonical(atoms, temperature=temps, max_cycles=1, seed=5, resync_interval=0,
                               default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=1.0, max_steps=n_steps)))  # fmt: skip
     t0 = time.perf_counter()
+    timed(mc, 1, 0)  # neighbour lists, trajectory graph
     t, _ = timed(mc, attempts, 0)
     force_evals = R * attempts * (n_steps + 1)
     return {"config": f"C5 HMC Cu {n}-atom EMT, {R} temperatures, Verlet {n_steps} x 1 fs", "trajectories_per_s": R * attempts / t,
@@ -235,6 +236,8 @@ if __name__ == "__main__":
     for w in which:
         if w == "c5small":
             print(json.dumps(c5(R=64, repeat=4, n_steps=20)), flush=True)
+        elif w.startswith("c5r"):  # c5r8: the share of one GPU when C5's 64 temperatures are spread over 8 GPUs
+            print(json.dumps(c5(R=int(w[3:]), attempts=4)), flush=True)
         else:
             res = {"c3": c3, "c4": c4, "c5": c5, "c5pt": c5pt, "composite": composite, "fbmc": fbmc}[w]()
             if res is not None:
