@@ -485,9 +485,9 @@ def run_native(args):
     cpu = cpu_reference(seconds_target=12.0) if world == 1 and not args.no_cpu else None
     p_per_attempt = pairs / attempts
     # M (embedding evaluations per attempt) is counted by the oracle on a sample of this very workload in this run (cpu_baseline
-    # leg); without that leg the figure of profiles/r1_l_summary.md is used and labelled as such
+    # leg); without that leg the round-1 oracle figure (profiles/r1_l_summary.md) is used and labelled as such
     m_per_attempt = cpu["embed_evals_per_attempt_local"] if cpu else 67.0
-    m_source = "oracle sample in this run (cpu_baseline leg)" if cpu else "constant from profiles/r1_l_summary.md (no cpu leg in this run)"
+    m_source = "oracle sample in this run (cpu_baseline leg)" if cpu else "constant measured with the oracle in round 1 (profiles/r1_l_summary.md; no cpu leg in this run)"
     flop_per_attempt = A_PAIR * p_per_attempt + A_EMBED * m_per_attempt
     launch_s = ms_total * 1e-3 / args.steps
     achieved_tflops = flop_per_attempt * R * N_ATOMS * args.sweeps / launch_s / 1e12  # per GPU, per launch
@@ -533,7 +533,7 @@ def run_native(args):
             "unit": "TFLOP/s",
             "frac": achieved_tflops / (fp64_peak / 1e12),
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH if R == 4096 and world == 1 else None,
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch, ncu --set full (profiles/r1_l_summary.md); bytes, algorithmic 35.7e6",
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch, ncu --set full of the same command (profiles/r2_v_sweep_kernel_ncu_raw.csv: 18.12 MB read, 0 written back before the kernel ends -- the 126 MB L2 holds the write-back); bytes per launch, algorithmic 35.7e6 (replica state read once and written once per launch, whatever the number of sweeps)",
             "peak_source": "register-resident DFMA loop measured in this process (qmc_fp64_peak); nominal 37.2",
             "flop_per_attempt": flop_per_attempt,
             "pair_evals_per_attempt": p_per_attempt,

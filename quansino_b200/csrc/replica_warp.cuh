@@ -283,7 +283,7 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
     int cnt = 0, nq = 0;
     // one tile: 32 candidate atoms.  The distance arithmetic of a tile is a chain of dependent instructions (load -> nearest image
     // -> r^2 -> compare -> ballot -> slot); a warp is latency-bound (7 warps per scheduler each progress as if alone), so TWO
-    // tiles are in flight per iteration: their chains are independent and interleave (profiles/r2_b_ilp.md).
+    // tiles are in flight per iteration: their chains are independent and interleave (profiles/r2_a_rows.md, last section).
     struct Tile {
         int j;
         bool valid, any, ex_o, ex_n;

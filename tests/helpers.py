@@ -28,9 +28,22 @@ def oracle_par(calc, symbol="Cu"):
     return LJParams(sigma=calc.sigma, epsilon=calc.epsilon, rc=calc.rc)
 
 
-def oracle_run(par, positions, n_atoms, cell, pbc, moves, seed, n_attempts, replica_ids, attempt_base=0, **state):
-    """Run the C oracle replica by replica.  ``moves`` is a list of dicts (MoveSpec kwargs); labels default to arange.
-    Returns (list of Replica, list of traces)."""
+def oracle_run(par, positions, n_atoms, cell, pbc, moves, seed, n_attempts, replica_ids, attempt_base=0, threads=1, **state):
+    """Run the C oracle replica by replica (``threads`` > 1: replicas in parallel, the C call releases the GIL).  ``moves`` is a
+    list of dicts (MoveSpec kwargs); labels default to arange.  Returns (list of Replica, list of traces)."""
+    replica_ids = list(replica_ids)
+    if threads > 1 and len(replica_ids) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        def one(k):
+            sub = {key: (val[k : k + 1] if isinstance(val, np.ndarray) and val.ndim >= 1 and key in ("temperature", "n_exchange") else val) for key, val in state.items()}
+            r, t = oracle_run(par, positions[k : k + 1], n_atoms[k : k + 1], cell[k : k + 1] if np.ndim(cell) == 3 else cell, pbc, moves, seed,
+                              n_attempts, [replica_ids[k]], attempt_base, **sub)  # fmt: skip
+            return r[0], t[0]
+
+        with ThreadPoolExecutor(threads) as ex:
+            out = list(ex.map(one, range(len(replica_ids))))
+        return [o[0] for o in out], [o[1] for o in out]
     reps, traces = [], []
     for k, rid in enumerate(replica_ids):
         n_max = positions.shape[1]

@@ -77,6 +77,47 @@ def test_isobaric_500_atoms(cuda_lib):
     assert n_cell >= 6
 
 
+def test_isobaric_c3_full_step_32_replicas(cuda_lib):
+    """BASELINE.json configuration C3 as the bench runs it, at a size the oracle finishes in seconds: 32 replicas of the 500-atom
+    cell, ONE full step of the default move table (max_cycles = 500 attempts, cell move with the default probability 1 / (N + 1),
+    IsotropicDeformation 0.05), every attempt of every replica against the C oracle (`mc/isobaric.py:117-147`,
+    `mc/criteria.py:146-172`)."""
+    import os
+
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import Isobaric
+    from quansino_b200.moves import CellMove, DisplacementMove
+
+    R = 32
+    pos, cell, n = cu_replicas(5, R, seed=56)
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    mc = Isobaric(atoms, temperature=300.0, pressure=1.0 * BAR, seed=909, trace=True, resync_interval=0,
+                  default_displacement_move=DisplacementMove(np.arange(n), operations.Ball(0.1)),
+                  default_cell_move=CellMove(operations.IsotropicDeformation(0.05)))  # fmt: skip
+    n_attempts = mc.max_cycles
+    assert n_attempts == n  # `mc/canonical.py:70-72`: max_cycles defaults to the number of atoms; the cell move shares them
+    p_disp, p_cell = mc.moves["default_displacement_move"].probability, mc.moves["default_cell_move"].probability
+    mc.run(1)
+    tr, out = mc.last_trace, mc.download()
+    par = oracle_par(mc.batch.calc)
+    moves = [dict(type=capi.MOVE_DISPLACEMENT, op=capi.OP_BALL, step=0.1, probability=p_disp),
+             dict(type=capi.MOVE_CELL, op=capi.OP_ISOTROPIC, step=0.05, probability=p_cell)]  # fmt: skip
+    reps, otr = oracle_run(par, pos, np.full(R, n), cell, (1, 1, 1), moves, 909, n_attempts, range(R), threads=min(16, os.cpu_count() or 1),
+                           temperature=300.0, pressure=1.0 * BAR)  # fmt: skip
+    n_cell = n_cell_acc = 0
+    for r in range(R):
+        assert np.array_equal(tr["move"][r], otr[r]["move"])
+        assert np.array_equal(tr["accepted"][r], otr[r]["accepted"]), f"accept/reject sequence differs for replica {r}"
+        np.testing.assert_allclose(tr["energy"][r], otr[r]["energy"], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(out.positions[r], reps[r].positions, rtol=0, atol=1e-10)
+        np.testing.assert_allclose(out.cell[r], reps[r].cell, rtol=1e-13)
+        cells = otr[r]["move"] == 1
+        n_cell += int(cells.sum())
+        n_cell_acc += int((otr[r]["accepted"][cells] == 1).sum())
+    assert n_cell >= 15, n_cell
+    assert int(mc.batch.status.max().item()) == 0
+
+
 def test_several_waves_of_replicas(cuda_lib):
     """10 000 replicas = 2.4 waves of CTAs: every replica is written exactly once, sampled replicas match the oracle."""
     from quansino_b200 import EMT, BatchedAtoms, operations
