@@ -114,7 +114,12 @@ typedef struct qmc_move {
     double dt;             /* Verlet dt in ASE time units */
     int32_t n_steps;       /* Verlet max_steps */
     int32_t default_label; /* DisplacementMove.default_label; QMC_LABEL_NONE = None */
-    int32_t repeat;        /* displacement moves: how many times this entry is performed per attempt (>= 1; 0 reads as 1) */
+    int32_t repeat;        /* displacement moves: how many times this entry is performed per attempt (>= 1; 0 reads as 1).
+                              exchange moves: repeat = k > 1 is a CompositeExchangeMove of k single-atom exchange moves holding equal
+                              labels (moves/exchange.py:237-316): one coin (`bias_insert` = the composite's), k insertions with their own
+                              Translation draws (sub-move c >= 1: extra draws 3 (c - 1) + {0, 1, 2}, blocks 64 + e / 2) or k label deletions
+                              without replacement (drawing sub-move c >= 1: block 32 + 2 (c - 1), first double), ONE criteria evaluation
+                              with particle_delta = +-(sub-moves that acted); needs chain bit 3 on every move of the table */
     int32_t chain;         /* bit 0: the next table entry belongs to the same composite move; bit 1: plain CompositeMove;
                               bit 2: label groups (labels = dense group ranks); bit 3: label groups coded as RUNS (see below) */
     int32_t axes;          /* cell moves: bit d set = axis d is deformed (the diagonal of IsotropicDeformation.mask,

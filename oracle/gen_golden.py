@@ -45,14 +45,14 @@ from ase.calculators.emt import EMT  # noqa: E402
 from ase.calculators.lj import LennardJones  # noqa: E402
 from quansino.integrators.displacement import Verlet  # noqa: E402
 from quansino.mc.canonical import Canonical, HamiltonianCanonical  # noqa: E402
-from quansino.mc.criteria import CanonicalCriteria, IsobaricCriteria  # noqa: E402
+from quansino.mc.criteria import CanonicalCriteria, GrandCanonicalCriteria, IsobaricCriteria  # noqa: E402
 from quansino.mc.fbmc import AdaptiveForceBias, ForceBias  # noqa: E402
 from quansino.moves.composite import CompositeMove  # noqa: E402
 from quansino.mc.gcmc import GrandCanonical  # noqa: E402
 from quansino.mc.isobaric import Isobaric  # noqa: E402
 from quansino.moves.cell import CellMove  # noqa: E402
 from quansino.moves.displacement import DisplacementMove, HamiltonianDisplacementMove  # noqa: E402
-from quansino.moves.exchange import ExchangeMove  # noqa: E402
+from quansino.moves.exchange import CompositeExchangeMove, ExchangeMove  # noqa: E402
 from quansino.operations.cell import IsotropicDeformation  # noqa: E402
 from quansino.operations.displacement import Ball, Box, Rotation, Sphere, Translation, TranslationRotation  # noqa: E402
 
@@ -358,6 +358,41 @@ def case_gc_molecule(seed, n_attempts, mu):
     )  # fmt: skip
 
 
+def case_gc_composite(seed, n_attempts, mu, temperature, k=2):
+    """``CompositeExchangeMove`` of k single-atom ``ExchangeMove`` objects with equal labels (moves/exchange.py:237-316): one coin,
+    k insertions with their own Translation draws or k label deletions without replacement, ONE GrandCanonicalCriteria evaluation
+    with particle_delta = +-k (mc/criteria.py:225-277); after an accepted insertion every move gives the k new atoms one label
+    (moves/displacement.py:244-249), so that they are displaced and deleted together from then on."""
+    pos0, cell = octahedron("Pt", 4, 10.0)
+    pos0 = rattle(pos0, 0.02, 97)
+    n = len(pos0)
+    atoms = Atoms(f"Pt{n}", positions=pos0, cell=cell, pbc=False, calculator=LennardJones(sigma=2.5, epsilon=0.1))
+    disp = DisplacementMove(np.arange(n))
+    subs = [ExchangeMove(np.full(n, -1)) for _ in range(k)]
+    exch = subs[0]
+    for sub in subs[1:]:
+        exch = exch + sub
+    assert isinstance(exch, CompositeExchangeMove) and len(exch) == k
+    mc = GrandCanonical(
+        atoms, exchange_atoms=Atoms("Pt"), temperature=temperature, chemical_potential=mu, number_of_exchange_particles=0,
+        max_cycles=n_attempts, default_displacement_move=disp,
+    )  # fmt: skip
+    mc.add_move(exch, criteria=GrandCanonicalCriteria(), name="default_exchange_move")
+    mc.moves["default_displacement_move"].probability = 0.5
+    mc.moves["default_exchange_move"].probability = 0.5
+    inject(mc, seed, 4)
+    tr = run_steps(mc, 1)
+    for sub in subs[1:]:
+        assert np.array_equal(sub.labels, subs[0].labels)
+    return dict(
+        kind="gc_composite", seed=seed, replica=4, temperature=temperature, chemical_potential=mu, sigma=2.5, epsilon=0.1, step_size=0.1,
+        k=k, bias=float(exch.bias_towards_insert), accessible_volume=float(mc.accessible_volume),
+        exchange_mass=float(mc.exchange_atoms.get_masses().sum()), positions0=pos0, cell=cell, positions=atoms.positions.copy(),
+        labels_displacement=np.asarray(disp.labels), labels_exchange=np.asarray(subs[0].labels),
+        n_exchange=int(mc.number_of_exchange_particles), **tr,
+    )  # fmt: skip
+
+
 def case_gc_emt(seed, n_attempts, mu, temperature):
     atoms, pos0, cell = cu_atoms(3, 0.05, 31337)
     n = len(atoms)
@@ -405,6 +440,7 @@ def main():
         "gc_lj": lambda: case_gc_lj(3001, 700, -0.5),
         "gc_emt": lambda: case_gc_emt(3002, 150, -3.4, 3000.0),
         "gc_molecule": lambda: case_gc_molecule(3003, 600, -0.6),
+        "gc_composite": lambda: case_gc_composite(3004, 600, -3.3, 2000.0),
         "hmc": lambda: case_hmc(4001, 3, 2.0, 12, 800.0),
         "composite_mul": lambda: case_composite("mul", 5001, 120),
         "composite_add": lambda: case_composite("add", 5002, 80),

@@ -899,9 +899,83 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
             int is_addition = u_coin < mv->bias_insert;
             int n_new = n, particle_delta = 0, removed = -1;
             const int n_mol = st->n_exchange_atoms > 1 ? st->n_exchange_atoms : 1;
-            const int molecular = n_mol > 1 || mv->op == QO_OP_TRANSLATION_ROTATION;
+            /* repeat = k > 1: CompositeExchangeMove of k single-atom ExchangeMoves holding equal labels (moves/exchange.py:237-316):
+             * ONE coin for all of them (the composite's own bias_towards_insert); insertion = every sub-move places one atom with
+             * its own Translation draws (sub-move 0: the standard operation slots, sub-move c >= 1: "extra" draws 3 (c - 1) + {0,
+             * 1, 2} = block 64 + e / 2, half e & 1); deletion = every sub-move draws a label among those nobody deleted yet in this
+             * composite (sub-move 0: u_label, drawing sub-move c >= 1: block 32 + 2 (c - 1), first double) and ALL atoms carrying
+             * it go; particle_delta = +-(number of sub-moves that acted); GrandCanonical.save_state then gives the k added atoms
+             * ONE new label (moves/displacement.py:244-249), so that later deletions take them out together. */
+            const int k_sub = mv->repeat > 1 ? mv->repeat : 1;
+            const int composite = k_sub > 1;
+            const int molecular = composite || n_mol > 1 || mv->op == QO_OP_TRANSLATION_ROTATION;
             int n_gone = 0;
-            if (is_addition) {
+            if (composite && (n_mol > 1 || mv->op != QO_OP_TRANSLATION || !mv->labels)) { rc = -1; goto done; }
+            if (composite && is_addition) {
+                if (n + k_sub > nmax) { rc = -3; goto done; }
+                memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
+                const double *tmpl = st->n_exchange_atoms >= 1 ? st->exchange_mol : st->exchange_pos;
+                for (int c = 0; c < k_sub; ++c) {
+                    double f[3];
+                    for (int j = 0; j < 3; ++j) {
+                        if (c == 0) f[j] = opd[j];
+                        else {
+                            const int e = 3 * (c - 1) + j;
+                            double bx[2];
+                            qo_uniform_pair(seed, attempt, replica, (uint32_t)(64 + e / 2), bx);
+                            f[j] = bx[e & 1];
+                        }
+                    }
+                    for (int x = 0; x < 3; ++x) {
+                        double fc = (f[0] * st->cell[x] + f[1] * st->cell[3 + x]) + f[2] * st->cell[6 + x];
+                        trial[3 * (n + c) + x] = tmpl[x] + (fc - tmpl[x] / 1.0);
+                    }
+                }
+                n_new = n + k_sub; particle_delta = k_sub; moved = n;
+                memset(seen, 0, (size_t)n_new);
+                for (int q = 0; q < k_sub; ++q) {
+                    seen[n + q] = 1;
+                    cnt[1] += count_neighbours(pot, n_new, trial, st->cell, st->pbc, n + q, seen);
+                }
+                for (int i = 0; i < n_new; ++i) cnt[2] += seen[i];
+            } else if (composite) {
+                int n_del = 0, c = 0;
+                int deleted[16];
+                memset(gone, 0, (size_t)n);
+                memset(seen, 0, (size_t)n);
+                for (int sub = 0; sub < k_sub; ++sub) {
+                    int nu = unique_labels(mv->labels, n, uniq), na = 0;
+                    for (int q = 0; q < nu; ++q) { /* setdiff1d(unique_labels, deleted_labels) */
+                        int taken = 0;
+                        for (int d = 0; d < n_del; ++d) taken |= deleted[d] == uniq[q];
+                        if (!taken) uniq[na++] = uniq[q];
+                    }
+                    if (na == 0) continue;
+                    double ul = u_label;
+                    if (c > 0) {
+                        double e0[2];
+                        qo_uniform_pair(seed, attempt, replica, (uint32_t)(32 + 2 * (c - 1)), e0);
+                        ul = e0[0];
+                    }
+                    ++c;
+                    const int label = uniq[(int)(ul * (double)na)];
+                    if (n_del >= 16) { rc = -1; goto done; }
+                    deleted[n_del++] = label;
+                    for (int i = 0; i < n; ++i)
+                        if (mv->labels[i] == label) {
+                            if (removed < 0) removed = i;
+                            gone[i] = 1;
+                            ++n_gone;
+                            cnt[1] += count_neighbours(pot, n, st->pos, st->cell, st->pbc, i, seen);
+                        }
+                }
+                if (n_del > 0) {
+                    for (int i = 0; i < n; ++i) cnt[2] += seen[i];
+                    for (int i = 0, o = 0; i < n; ++i)
+                        if (!gone[i]) { memcpy(trial + 3 * o, st->pos + 3 * i, sizeof(double) * 3); ++o; }
+                    n_new = n - n_gone; particle_delta = -n_del; moved = removed;
+                }
+            } else if (is_addition) {
                 if (n + n_mol > nmax) { rc = -3; goto done; }
                 memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
                 const double *tmpl = st->n_exchange_atoms >= 1 ? st->exchange_mol : st->exchange_pos;
@@ -996,12 +1070,12 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                     /* GrandCanonical.save_state (mc/gcmc.py:207-214): every move re-labels, then N_ex += delta */
                     for (int q = 0; q < n_moves; ++q)
                         if (moves[q].labels) {
-                            if (molecular) labels_on_molecule_changed(&moves[q], n, particle_delta > 0 ? n_mol : 0, particle_delta < 0 ? gone : NULL, uniq);
+                            if (molecular) labels_on_molecule_changed(&moves[q], n, particle_delta > 0 ? (composite ? k_sub : n_mol) : 0, particle_delta < 0 ? gone : NULL, uniq);
                             else labels_on_atoms_changed(&moves[q], n, particle_delta > 0, removed, uniq);
                         }
                     memcpy(st->pos, trial, sizeof(double) * 3 * (size_t)n_new);
                     if (st->momenta) {
-                        if (particle_delta > 0) memset(st->momenta + 3 * n, 0, sizeof(double) * 3 * (size_t)n_mol);
+                        if (particle_delta > 0) memset(st->momenta + 3 * n, 0, sizeof(double) * 3 * (size_t)(n_new - n));
                         else
                             for (int i = 0, o = 0; i < n; ++i)
                                 if (!gone[i]) { memmove(st->momenta + 3 * o, st->momenta + 3 * i, sizeof(double) * 3); ++o; }

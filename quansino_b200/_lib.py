@@ -13,6 +13,7 @@ _PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(__import__("os").environ.get("QUANSINO_B200_LIB", _PKG / "libquansino_b200.so"))
 
 QMC_MAX_MOVES = 4
+QMC_MAX_SUBMOVES = 16
 LABEL_NONE = -(2**31)
 
 POT_EMT, POT_LJ = 0, 1

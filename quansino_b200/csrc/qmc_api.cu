@@ -224,8 +224,14 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         if (mv.repeat < 0) return fail(QMC_ERR_INVALID, "move %d: negative repeat", m);
         if (mv.chain < 0 || (mv.chain > 4 && mv.chain != 8))
             return fail(QMC_ERR_INVALID, "move %d: chain must be bits 0 / 1 (composite), bit 2 alone (label groups) or bit 3 alone (run-coded groups)", m);
-        if ((mv.chain & 8) && ((mv.type != QMC_MOVE_DISPLACEMENT && mv.type != QMC_MOVE_EXCHANGE) || !mv.labels || !head || mv.repeat > 1 || mv.n_extra_ops))
+        // an exchange entry with repeat = k > 1 is a CompositeExchangeMove of k single-atom exchange moves (run-coded groups only)
+        const bool composite_exchange = mv.type == QMC_MOVE_EXCHANGE && mv.repeat > 1;
+        if ((mv.chain & 8) && ((mv.type != QMC_MOVE_DISPLACEMENT && mv.type != QMC_MOVE_EXCHANGE) || !mv.labels || !head ||
+                               (mv.repeat > 1 && !composite_exchange) || mv.n_extra_ops))
             return fail(QMC_ERR_UNSUPPORTED, "move %d: run-coded label groups need a single displacement or exchange move with a label array", m);
+        if (composite_exchange && (!(mv.chain & 8) || mv.op != QMC_OP_TRANSLATION || batch->n_exchange_atoms > 1 || mv.repeat > QMC_MAX_SUBMOVES))
+            return fail(QMC_ERR_UNSUPPORTED, "move %d: a composite exchange move (repeat > 1) needs run-coded label groups (chain bit 3), Translation "
+                        "placement, a single-atom exchange species and at most %d sub-moves", m, QMC_MAX_SUBMOVES);
         if ((mv.chain & 4) && (mv.type != QMC_MOVE_DISPLACEMENT || !mv.labels || !head || mv.repeat > 1))
             return fail(QMC_ERR_UNSUPPORTED, "move %d: label groups need a single displacement move with a label array", m);
         if ((mv.chain & 1) && m + 1 == n_moves) return fail(QMC_ERR_INVALID, "move %d: chain bit 0 set on the last table entry", m);
@@ -233,7 +239,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
             return fail(QMC_ERR_INVALID, "move %d: chain bit 1 (plain CompositeMove) must be the same on every entry of a chain", m);
         // a CellMove may close a plain CompositeMove chain (the hybrid NPT move); everything else in a chain is a displacement
         const bool closing_cell = !head && mv.type == QMC_MOVE_CELL && (mv.chain & 2) && !(mv.chain & 1) && mv.repeat <= 1;
-        if (((mv.chain & 7) || !head || mv.repeat > 1) && mv.type != QMC_MOVE_DISPLACEMENT && !closing_cell)
+        if (((mv.chain & 7) || !head || (mv.repeat > 1 && !composite_exchange)) && mv.type != QMC_MOVE_DISPLACEMENT && !closing_cell)
             return fail(QMC_ERR_UNSUPPORTED, "move %d: a composite move is a chain of displacement moves, optionally closed by a cell move", m);
         if (!head && mv.type == QMC_MOVE_DISPLACEMENT && mv.labels != moves[m - 1].labels)
             return fail(QMC_ERR_UNSUPPORTED, "move %d: the sub-moves of a composite move must share one label array", m);

@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(LayoutB<POT, NS>::REPS * BW * 32, 1) sweep_blo
                         rep_sync();
                         if (warp == 0) {
                             for (int q = 0; q < a.n_moves; ++q)
-                                if (a.mv[q].labels)
+                                if (a.mv[q].labels && table_first_use(a.mv, q))
                                     labels_changed(a.mv[q].labels + (size_t)r * nmax, R.n, pd > 0, pd < 0 ? i : -1, a.mv[q].default_label);
                             if (pd < 0) {
                                 shift_down(&R.x(0), i, R.n);

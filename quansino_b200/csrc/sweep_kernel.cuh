@@ -150,6 +150,15 @@ __device__ inline int max_label(const int *lab, int n) {
     return m;
 }
 
+// a label table shared by several entries of the move table (qmc_sweep_host uploads equal host arrays once; the sub-moves of a
+// composite share theirs) is re-labelled ONCE per accepted exchange
+template <class MV>
+__device__ inline bool table_first_use(const MV *mv, int q) {
+    for (int p = 0; p < q; ++p)
+        if (mv[p].labels == mv[q].labels) return false;
+    return true;
+}
+
 // on_atoms_changed for one move: append one label and / or remove index `removed`
 __device__ inline void labels_changed(int *lab, int n, bool added, int removed, int default_label) {
     const int lane = lane_id();
@@ -419,8 +428,17 @@ __device__ __forceinline__ void commit_move(const Rep<LY> &R, const int lane, co
 // GrandCanonicalCriteria.evaluate (mc/criteria.py:243-278): criteria * prefactor
 __device__ inline double gc_probability(double dE, int delta, int n_ex, double acc_volume, double mass, double temperature,
                                         double mu, bool &overflow) {
-    const double vol = delta > 0 ? acc_volume : 1.0 / acc_volume;
-    const double factorial_term = delta > 0 ? 1.0 / (double)(n_ex + 1) : (double)n_ex;
+    // particle_delta = +-1 for plain exchange moves; a CompositeExchangeMove changes several particles at once (mc/criteria.py:246-262)
+    double vol = delta > 0 ? acc_volume : 1.0 / acc_volume;
+    double factorial_term = delta > 0 ? 1.0 / (double)(n_ex + 1) : (double)n_ex;
+    if (delta > 1 || delta < -1) {
+        vol = pow(acc_volume, (double)delta);
+        factorial_term = 1.0;
+        if (delta > 0)
+            for (int i = n_ex + 1; i < n_ex + delta + 1; ++i) factorial_term /= (double)i;
+        else
+            for (int i = n_ex + delta + 1; i < n_ex + 1; ++i) factorial_term *= (double)i;
+    }
     const double denom = 2 * 3.141592653589793 * mass * KB * temperature / 6.022140857e23 * 1e-3 * 1.6021766208e-19;
     const double lam = sqrt(6.626070040e-34 * 6.626070040e-34 / denom) * 1e10;
     const double debroglie = pow(lam, (double)(-3 * delta));
@@ -1037,14 +1055,45 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
             // single-atom insertion and committed at once (the next one sees it); deletion = the atoms of the selected label (a
             // run of equal labels) taken out from the top down.  ONE criteria evaluation on the summed energy change, one
             // particle; the snapshot in global memory is restored on reject.
+            //
+            // repeat = k > 1: CompositeExchangeMove of k single-atom ExchangeMoves holding equal labels (moves/exchange.py:237-316).
+            // One coin; insertion = k atoms, each placed with its own Translation draws (sub-move 0: the standard operation slots,
+            // sub-move c >= 1: extra draws 3 (c - 1) + {0, 1, 2}); deletion = every sub-move draws a label among those nobody
+            // deleted yet in this composite (sub-move 0: u_label, drawing sub-move c >= 1: block 32 + 2 (c - 1), first double) and
+            // its whole run goes; particle_delta = +-(sub-moves that acted); an accepted insertion gives the k atoms ONE label.
             const bool is_add = D.u_coin < mv.bias;
             const int k_mol = a.b.n_exchange_atoms > 1 ? a.b.n_exchange_atoms : 1;
+            const int k_sub = mv.repeat > 1 ? min(mv.repeat, QMC_MAX_SUBMOVES) : 1;
+            const bool comp = k_sub > 1;
+            const int k_ins = comp ? k_sub : k_mol;  // atoms appended by an insertion
             const double *tmpl = a.b.n_exchange_atoms >= 1 ? a.b.exchange_mol : a.b.exchange_pos;
             const int n_before = R.n;
             int pd = 0, first = -1, len = 0;
+            int n_del = 0, del_ord[QMC_MAX_SUBMOVES];  // composite deletion: ordinals of the chosen runs, ascending
             if (is_add) {
-                if (R.n + k_mol > nmax) status |= QMC_STATUS_CAPACITY;
-                else pd = 1;
+                if (R.n + k_ins > nmax) status |= QMC_STATUS_CAPACITY;
+                else pd = comp ? k_sub : 1;
+            } else if (comp) {
+                const int nu = lab ? run_count(lab, R.n) : 0;
+                int c = 0;
+                for (int sub = 0; sub < k_sub; ++sub) {
+                    const int na = nu - n_del;  // setdiff1d(unique_labels, deleted_labels)
+                    if (na <= 0) break;
+                    double ul = D.u_label, unused;
+                    if (c > 0) uniform_pair(key, attempt, grep, 32u + 2u * (unsigned)(c - 1), ul, unused);
+                    ++c;
+                    int ord = (int)(ul * (double)na);
+                    int at = 0;  // the ord-th run that is still available; keep del_ord sorted
+                    while (at < n_del && del_ord[at] <= ord) {
+                        ++ord;
+                        ++at;
+                    }
+                    for (int q = n_del; q > at; --q) del_ord[q] = del_ord[q - 1];
+                    del_ord[at] = ord;
+                    ++n_del;
+                    if (sub == 0) run_select(lab, R.n, ord, first, len);  // `moved` of the trace: first atom of the first label drawn
+                }
+                pd = -n_del;
             } else {
                 const int nu = lab ? run_count(lab, R.n) : 0;
                 if (nu > 0) {
@@ -1052,6 +1101,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     pd = -1;
                 }
             }
+            const int moved_first = first;
             if (pd != 0) {
                 for (int j = lane; j < n_before; j += 32) {  // snapshot of the last accepted state
                     gx[j] = R.x(j);
@@ -1091,10 +1141,25 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
 #pragma unroll
                         for (int d = 0; d < 3; ++d) com[d] = __ddiv_rn(com[d], ms);
                     }
-                    for (int q = 0; q < k_mol; ++q) {
-                        const double tq[3] = {tmpl[3 * q], tmpl[3 * q + 1], tmpl[3 * q + 2]};
+                    for (int q = 0; q < k_ins; ++q) {
+                        const int qt = comp ? 0 : q;
+                        const double tq[3] = {tmpl[3 * qt], tmpl[3 * qt + 1], tmpl[3 * qt + 2]};
                         double pn[3];
-                        if (rot) {
+                        if (comp) {  // sub-move q of a composite: its own fractional coordinates
+                            double fq[3] = {D.o0, D.o1, D.o2};
+                            if (q > 0) {
+                                const unsigned e0 = 3u * (unsigned)(q - 1);
+                                double lo, hi;
+#pragma unroll
+                                for (int d = 0; d < 3; ++d) {
+                                    uniform_pair(key, attempt, grep, 64u + (e0 + d) / 2u, lo, hi);
+                                    fq[d] = ((e0 + d) & 1u) ? hi : lo;
+                                }
+                            }
+#pragma unroll
+                            for (int d = 0; d < 3; ++d)
+                                pn[d] = __dadd_rn(tq[d], __dsub_rn(__dmul_rn(fq[d], UNIFORM ? a.cell.L[d] : cell[d]), __ddiv_rn(tq[d], 1.0)));
+                        } else if (rot) {
                             const double rc[3] = {__dsub_rn(tq[0], com[0]), __dsub_rn(tq[1], com[1]), __dsub_rn(tq[2], com[2])};
 #pragma unroll
                             for (int d = 0; d < 3; ++d) {
@@ -1124,6 +1189,8 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     }
                     moved = n_before;
                 } else {
+                  for (int run = comp ? n_del - 1 : 0; run >= 0; --run) {  // composite: the chosen runs, highest first
+                    if (comp) run_select(lab, n_before, del_ord[run], first, len);
                     for (int q = len - 1; q >= 0; --q) {  // top down: the indices below stay valid
                         const int i = first + q;
                         const double po[3] = {R.x(i), R.y(i), R.z(i)};
@@ -1141,7 +1208,8 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                         de_total += T.dE;
                         __syncwarp();
                     }
-                    moved = first;
+                  }
+                    moved = moved_first;
                 }
                 delta = de_total;
                 bool ov;
@@ -1151,9 +1219,29 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                 const bool acc = D.u_accept < prob;
                 if (acc) {
                     // GrandCanonical.save_state (mc/gcmc.py:207-214): every registered move re-labels
+                    auto first_use = [&](int q) { return table_first_use(a.mv, q); };
+                    int *labw = mv.labels + (size_t)r * nmax;
+                    if (comp && pd < 0) {
+                        // the runs were located in the exchange move's labels; every table holds the same runs (run-coded tables are
+                        // re-labelled together from the start), so the positions are valid for all of them
+                        int n_cur = n_before;
+                        for (int run = n_del - 1; run >= 0; --run) {
+                            run_select(lab, n_before, del_ord[run], first, len);  // `lab` itself is edited last (below)
+                            for (int q = 0; q < a.n_moves; ++q)
+                                if (a.mv[q].labels && a.mv[q].labels != mv.labels && first_use(q))
+                                    labels_molecule_changed(a.mv[q].labels + (size_t)r * nmax, n_cur, 0, first, len, a.mv[q].default_label);
+                            n_cur -= len;
+                        }
+                        n_cur = n_before;
+                        for (int run = n_del - 1; run >= 0; --run) {
+                            run_select(lab, n_cur, del_ord[run], first, len);  // lower ordinals are untouched by the deletions above them
+                            labels_molecule_changed(labw, n_cur, 0, first, len, mv.default_label);
+                            n_cur -= len;
+                        }
+                    } else
                     for (int q = 0; q < a.n_moves; ++q)
-                        if (a.mv[q].labels)
-                            labels_molecule_changed(a.mv[q].labels + (size_t)r * nmax, n_before, pd > 0 ? k_mol : 0, first, pd < 0 ? len : 0,
+                        if (a.mv[q].labels && first_use(q))
+                            labels_molecule_changed(a.mv[q].labels + (size_t)r * nmax, n_before, pd > 0 ? k_ins : 0, first, pd < 0 ? len : 0,
                                                     a.mv[q].default_label);
                     n_ex += pd;
                     E += delta;
@@ -1218,7 +1306,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     commit_trial<LY>(R, lane, T);
                     // GrandCanonical.save_state (mc/gcmc.py:207-214): every registered move re-labels
                     for (int q = 0; q < a.n_moves; ++q)
-                        if (a.mv[q].labels)
+                        if (a.mv[q].labels && table_first_use(a.mv, q))
                             labels_changed(a.mv[q].labels + (size_t)r * nmax, R.n, pd > 0, pd < 0 ? i : -1, a.mv[q].default_label);
                     if (pd > 0) {
                         if (lane == 0) {

@@ -126,12 +126,14 @@ class ExchangeContext(DisplacementContext):
     @exchange_atoms.setter
     def exchange_atoms(self, value) -> None:
         """The exchange species: an ASE-like ``Atoms`` (one atom, or a molecule of up to 8 atoms of the batch's species), or
-        ``(symbol, position)`` / ``(symbol, positions (k, 3))``."""
+        ``symbol`` / ``(symbol, position)`` / ``(symbol, positions (k, 3))``."""
         from quansino_b200.calculators import ATOMIC_MASSES
 
         if value is None:
             self._exchange_atoms = None
             return
+        if isinstance(value, str):  # a chemical symbol alone: one atom at the origin (like ``Atoms("Cu")``)
+            value = (value,)
         if isinstance(value, (tuple, list)) and isinstance(value[0], str):
             symbol = value[0]
             pos = np.atleast_2d(np.asarray(value[1] if len(value) > 1 else (0.0, 0.0, 0.0), dtype=float))

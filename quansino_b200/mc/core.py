@@ -165,7 +165,8 @@ class MonteCarlo:
         molecular = any_exchange and (
             len(np.atleast_2d(self.batch.exchange_mol)) > 1
             or any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE and getattr(self.moves[n].move.operation, "op_code", -1) == _lib.OP_TRANSLATION_ROTATION for n in names)
-        )  # fmt: skip
+            or any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE and len(getattr(self.moves[n].move, "moves", ())) > 1 for n in names)
+        )  # fmt: skip  (a CompositeExchangeMove gives the atoms of one insertion ONE label: groups, too)
         entries, keep, slots = [], [], {}
         for n in names:
             st = self.moves[n]
@@ -202,7 +203,7 @@ class MonteCarlo:
                 # rotations and relocations of displacement moves live in the label-group path
                 grouped = grouped or any(c.type == _lib.MOVE_DISPLACEMENT and c.op in (_lib.OP_ROTATION, _lib.OP_TRANSLATION, _lib.OP_TRANSLATION_ROTATION) for c in chain)
                 if molecular:
-                    if len(chain) > 1 or chain[0].repeat > 1 or m.n_extra_ops:
+                    if len(chain) > 1 or (chain[0].repeat > 1 and m.type != _lib.MOVE_EXCHANGE) or m.n_extra_ops:
                         raise NotImplementedError("composite moves next to a molecular exchange move are not available on the GPU path")
                     m.chain = 8  # run-coded label groups
                     grouped = False

@@ -22,7 +22,7 @@ def test_oracle_reproduces_genuine_quansino(name):
     np.testing.assert_allclose(rep.positions[:n], g["positions"], rtol=0, atol=1e-11)
     if g["kind"] in ("isobaric", "hybrid", "forced"):
         np.testing.assert_allclose(rep.cell, g["cell"], rtol=1e-14)
-    if g["kind"] in ("gc_lj", "gc_emt", "gc_molecule"):
+    if g["kind"] in ("gc_lj", "gc_emt", "gc_molecule", "gc_composite"):
         assert rep.n_exchange == g["n_exchange"]
         assert np.array_equal(labels["displacement"][:n], g["labels_displacement"])
         assert np.array_equal(labels["exchange"][:n], g["labels_exchange"])

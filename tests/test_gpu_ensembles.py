@@ -234,6 +234,69 @@ def test_molecular_exchange_matches_oracle(cuda_lib):
     assert int(mc.batch.status.max().item()) == 0
 
 
+def test_composite_exchange_matches_oracle(cuda_lib):
+    """`CompositeExchangeMove` on the device (moves/exchange.py:237-316; reference test tests/moves/test_composite_moves.py:264-296):
+    three single-atom exchange moves under one coin and ONE criteria evaluation with particle_delta = +-(sub-moves that acted),
+    Cu cluster in a periodic box with the many-body potential.  An accepted insertion gives its three atoms ONE label, so later
+    deletions take out three atoms per label (one, two or three labels at a time) and displacement moves translate them together --
+    traces, atom counts, particle counts and both label tables bit-exact against the C oracle."""
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.mc import GrandCanonical
+    from quansino_b200.mc.criteria import GrandCanonicalCriteria
+    from quansino_b200.moves import CompositeExchangeMove, DisplacementMove, ExchangeMove
+    from quansino_b200.systems import fcc_cubic, rattle
+
+    R, n_max, n_attempts, mu, L, k = 4, 96, 300, -0.5, 16.0, 3
+    pos0, cell0 = fcc_cubic("Cu", 2)
+    n = len(pos0)
+    cell = np.eye(3) * L
+    pos0 = pos0 + (L - cell0[0, 0]) / 2
+    pos = np.zeros((R, n_max, 3))
+    for r in range(R):
+        pos[r, :n] = rattle(pos0, 0.03, 800 + r)
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    exch = ExchangeMove(np.full(n, -1)) + ExchangeMove(np.full(n, -1)) + ExchangeMove(np.full(n, -1))
+    assert isinstance(exch, CompositeExchangeMove) and len(exch) == k
+    mc = GrandCanonical(
+        atoms, exchange_atoms="Cu", temperature=2500.0, chemical_potential=mu, number_of_exchange_particles=0,
+        max_cycles=n_attempts, seed=22, trace=True, resync_interval=0,
+        default_displacement_move=DisplacementMove(np.arange(n), operations.Ball(0.15)),
+    )  # fmt: skip
+    mc.add_move(exch, criteria=GrandCanonicalCriteria(), name="default_exchange_move")
+    mc.accessible_volume = L**3
+    mc.moves["default_displacement_move"].probability = 0.4
+    mc.moves["default_exchange_move"].probability = 0.6
+    mc.run(1)
+    tr, out = mc.last_trace, mc.download()
+    n_ex = mc.number_of_exchange_particles
+    labels_d, labels_x = mc.labels("default_displacement_move"), mc.labels("default_exchange_move")
+    par = emt_params("Cu")
+    changes: dict[int, int] = {}
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, pbc=(1, 1, 1), n_atoms=n, temperature=2500.0, mass=63.546, chemical_potential=mu,
+                           exchange_mass=63.546, n_exchange=0, accessible_volume=L**3)  # fmt: skip
+        ld = np.full(n_max, -1, np.int32)
+        ld[:n] = np.arange(n)
+        lx = np.full(n_max, -1, np.int32)
+        specs = [
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.15, probability=0.4, labels=ld),
+            capi.MoveSpec(capi.MOVE_EXCHANGE, capi.OP_TRANSLATION, probability=0.6, labels=lx, repeat=k, bias_insert=0.5),
+        ]
+        ref = capi.mc_run(par, rep, specs, 22, r, 0, n_attempts)
+        assert np.array_equal(tr["move"][r], ref["move"])
+        assert np.array_equal(tr["accepted"][r], ref["accepted"]), f"accept/reject sequence differs for replica {r}"
+        assert np.array_equal(tr["moved"][r], ref["moved"])
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10)
+        assert out.n_atoms[r] == rep.n_atoms and n_ex[r] == rep.n_exchange
+        assert np.array_equal(labels_d[r, : rep.n_atoms], ld[: rep.n_atoms])
+        assert np.array_equal(labels_x[r, : rep.n_atoms], lx[: rep.n_atoms])
+        np.testing.assert_allclose(out.positions[r, : rep.n_atoms], rep.positions[: rep.n_atoms], rtol=0, atol=1e-10)
+        d_n = np.diff(np.concatenate([[n], ref["n_atoms"]]))
+        for v, c in zip(*np.unique(d_n, return_counts=True)):
+            changes[int(v)] = changes.get(int(v), 0) + int(c)
+    assert changes.get(3, 0) > 20 and changes.get(-3, 0) > 10 and changes.get(-6, 0) > 0, changes
+    assert int(mc.batch.status.max().item()) == 0
+
 @pytest.mark.parametrize("build_lanes", [1, 4, 32])
 def test_forces_match_oracle(cuda_lib, monkeypatch, build_lanes):
     """``build_lanes``: lanes per atom of the neighbour-list build (hmc_build_kernel / hmc_build_split_kernel); the library

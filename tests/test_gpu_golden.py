@@ -24,7 +24,7 @@ def test_cuda_reproduces_genuine_quansino(cuda_lib, name):
     np.testing.assert_allclose(out.positions[0, :n], g["positions"], rtol=0, atol=1e-10)
     if g["kind"] in ("isobaric", "hybrid", "forced"):
         np.testing.assert_allclose(out.cell[0], g["cell"], rtol=1e-13)
-    if g["kind"] in ("gc_lj", "gc_emt", "gc_molecule"):
+    if g["kind"] in ("gc_lj", "gc_emt", "gc_molecule", "gc_composite"):
         assert mc.number_of_exchange_particles[0] == g["n_exchange"]
         assert np.array_equal(mc.labels("default_displacement_move")[0, :n], g["labels_displacement"])
         assert np.array_equal(mc.labels("default_exchange_move")[0, :n], g["labels_exchange"])

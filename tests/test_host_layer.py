@@ -332,3 +332,31 @@ def test_neighbour_row_geometry_is_exported():
     assert lib.qmc_nbr_row_words(C.byref(emt), 108) == 112 and lib.qmc_nbr_row_words(C.byref(emt), 500) == 160
     assert lib.qmc_nbr_row_words(C.byref(lj), 44) == 208
     assert lib.qmc_nbr_row_words(C.byref(emt), 2048) == _lib.ERR_UNSUPPORTED
+
+
+def test_composite_exchange_move_algebra_and_lowering():
+    """``ExchangeMove + ExchangeMove`` / ``* k`` build a ``CompositeExchangeMove`` (``moves/exchange.py:86,237-252``,
+    ``tests/moves/test_composite_moves.py:264-296``); it lowers to ONE exchange entry with ``repeat`` = number of sub-moves."""
+    from quansino_b200 import _lib, operations
+    from quansino_b200.moves import CompositeExchangeMove, CompositeMove, DisplacementMove, ExchangeMove
+
+    a, b = ExchangeMove(np.full(4, -1)), ExchangeMove(np.full(4, -1))
+    comp = a + b
+    assert isinstance(comp, CompositeExchangeMove) and len(comp) == 2 and comp.bias_towards_insert == 0.5
+    four = comp * 2
+    assert isinstance(four, CompositeExchangeMove) and len(four) == 4 and all(isinstance(m, ExchangeMove) for m in four)
+    assert isinstance(a * 3, CompositeExchangeMove)
+    assert type(a + DisplacementMove(np.arange(4))) is CompositeMove  # mixed kinds fall back to the plain composite
+    with pytest.raises(ValueError):
+        comp * 0
+    with pytest.raises(TypeError):
+        comp * 1.5
+    four.bias_towards_insert = 0.25
+    (entry,) = four.lower_chain()
+    assert entry.type == _lib.MOVE_EXCHANGE and entry.op == _lib.OP_TRANSLATION and entry.repeat == 4 and entry.bias_insert == 0.25
+    with pytest.raises(NotImplementedError, match="equal label arrays"):
+        (a + ExchangeMove(np.array([-1, -1, 0, 1]))).lower_chain()
+    with pytest.raises(NotImplementedError, match="Translation"):
+        (a + ExchangeMove(np.full(4, -1), operations.TranslationRotation())).lower_chain()
+    with pytest.raises(NotImplementedError, match="at most"):
+        (a * (_lib.QMC_MAX_SUBMOVES + 1)).lower_chain()
