@@ -18,7 +18,8 @@
  *  - units are ASE's: eV, Angstrom, amu, Kelvin; time in ASE units (fs * 0.0982269...).
  *  - replicas are independent; replica r of this batch is GLOBAL replica `replica_offset + r` for the
  *    random stream, so results do not depend on how replicas are sharded over GPUs.
- *  - cells must be orthorhombic (diagonal); each periodic edge must be >= the neighbour cutoff.
+ *  - cells are orthorhombic (diagonal), each periodic edge >= the neighbour cutoff; general (triclinic) cells run through the
+ *    general-cell kernels (qmc_batch_t.triclinic) with displacement and cell moves only.
  *
  * Random stream (shared with the oracle, DESIGN.md "Random stream"): Philox4x32-10,
  * key = seed, counter = (attempt_lo, attempt_hi, global_replica, block); block 0 = (u_select, u_label),
@@ -33,7 +34,7 @@
 extern "C" {
 #endif
 
-#define QMC_ABI_VERSION 8
+#define QMC_ABI_VERSION 9
 #define QMC_MAX_FORCED 16 /* sum of minimum_count over the move table */
 #define QMC_MAX_MOVES 4
 #define QMC_NBR_SKIN_DEFAULT 0.7 /* Angstrom: Cu EMT rows stay within three 32-entry passes (profiles/r2_a_rows.md) */
@@ -103,7 +104,10 @@ enum qmc_move_type { QMC_MOVE_DISPLACEMENT = 0, QMC_MOVE_CELL = 1, QMC_MOVE_EXCH
 enum qmc_op { QMC_OP_BALL = 0, QMC_OP_BOX = 1, QMC_OP_SPHERE = 2, QMC_OP_TRANSLATION = 3, QMC_OP_ISOTROPIC = 4, QMC_OP_VERLET = 5,
               QMC_OP_ROTATION = 6 /* Rotation (operations/displacement.py:178-200): label groups only, rigid z-x-z Euler rotation about the centre */,
               QMC_OP_TRANSLATION_ROTATION = 7 /* TranslationRotation (:203-227): label groups only; QMC_OP_TRANSLATION (:156-175) also
-                                                 serves displacement moves of label groups: centroid to a uniform point of the cell */ };
+                                                 serves displacement moves of label groups: centroid to a uniform point of the cell */,
+              QMC_OP_ANISOTROPIC = 8 /* AnisotropicDeformation (operations/cell.py:56-96): expm of a symmetric matrix of six U(-max, max)
+                                        components (draw order: xx, yy, zz = operation draws 0..2; xy, xz, yz = extra draws 0..2) */,
+              QMC_OP_SHAPE = 9 /* ShapeDeformation (:99-141): the same with the mean of the diagonal removed (volume preserving) */ };
 #define QMC_LABEL_NONE INT32_MIN
 typedef struct qmc_move {
     int32_t type;          /* qmc_move_type */
@@ -122,8 +126,9 @@ typedef struct qmc_move {
                               with particle_delta = +-(sub-moves that acted); needs chain bit 3 on every move of the table */
     int32_t chain;         /* bit 0: the next table entry belongs to the same composite move; bit 1: plain CompositeMove;
                               bit 2: label groups (labels = dense group ranks); bit 3: label groups coded as RUNS (see below) */
-    int32_t axes;          /* cell moves: bit d set = axis d is deformed (the diagonal of IsotropicDeformation.mask,
-                              operations/cell.py:167-169); 0 reads as all three axes */
+    int32_t axes;          /* cell moves: QMC_OP_ISOTROPIC: bit d set = axis d is deformed (the diagonal of IsotropicDeformation.mask,
+                              operations/cell.py:167-169); 0 reads as all three axes.  QMC_OP_ANISOTROPIC / QMC_OP_SHAPE: the 3 x 3 mask,
+                              bit 3 i + j = mask[i][j] (F = expm(T) * mask + eye * ~mask); 0 reads as all nine */
     int32_t minimum_count; /* MoveStorage.minimum_count: forced occurrences of this move per step (mc/core.py:331-342) */
     int32_t max_cycles;    /* cycles per step; read from entry 0, needed only if some minimum_count > 0 */
     int32_t n_extra_ops;   /* CompositeOperation (operations/composite.py:22-109): 0..2 further displacement operations whose */
@@ -143,7 +148,7 @@ typedef struct qmc_batch {
     int32_t nbr_row_cap;    /* entries per neighbour row (multiple of 32); 0 = no neighbour rows (brute-force scan kernels) */
     double cell_diag[3];
     double *pos;            /* [R][3][n_max]  x-row, y-row, z-row per replica */
-    double *cell;           /* [R][9] row-major, diagonal */
+    double *cell;           /* [R][9] row-major; diagonal unless `triclinic` is set */
     int32_t *n_atoms;       /* [R] */
     double *energy;         /* [R] last_potential_energy */
     double *temperature;    /* [R] Kelvin (per replica so that parallel tempering only permutes this array) */
@@ -176,6 +181,15 @@ typedef struct qmc_batch {
     int32_t n_exchange_atoms;
     int32_t _pad2;
     double exchange_mol[24];
+    /* General (triclinic) cells.  triclinic != 0: `cell` holds full 3 x 3 matrices (rows = cell vectors) and qmc_sweep /
+     * qmc_energy_full / qmc_atom_energies run the general-cell kernels (csrc/sweep_tri.cuh): single-atom displacement moves and
+     * cell moves (all three deformation operations); every periodic HEIGHT of the cell must be >= the neighbour cutoff.
+     * isotension != 0: cell moves are judged by IsotensionCriteria (mc/criteria.py:175-219) with `external_stress` (eV / A^3,
+     * row-major 3 x 3) and `pressure`; otherwise by IsobaricCriteria.  Batches with QMC_OP_ANISOTROPIC / QMC_OP_SHAPE moves must
+     * set triclinic (an accepted move leaves a general cell behind). */
+    int32_t triclinic;
+    int32_t isotension;
+    double external_stress[9];
 } qmc_batch_t;
 
 /* optional per-attempt trace, device [R][n_attempts] each, any pointer may be NULL */

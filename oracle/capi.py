@@ -17,6 +17,7 @@ _LIB_PATH = _HERE / "_build" / "libqmc_oracle.so"
 POT_EMT, POT_LJ = 0, 1
 MOVE_DISPLACEMENT, MOVE_CELL, MOVE_EXCHANGE, MOVE_HMC = 0, 1, 2, 3
 OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET, OP_ROTATION, OP_TRANSLATION_ROTATION = 0, 1, 2, 3, 4, 5, 6, 7
+OP_ANISOTROPIC, OP_SHAPE = 8, 9
 LABEL_NONE = -(2**31)
 
 
@@ -75,6 +76,9 @@ class State(C.Structure):
         ("n_exchange_atoms", C.c_int32),
         ("_pad2", C.c_int32),
         ("exchange_mol", C.c_double * 24),
+        ("isotension", C.c_int32),
+        ("_pad3", C.c_int32),
+        ("external_stress", C.c_double * 9),
     ]
 
 
@@ -119,6 +123,8 @@ def lib() -> C.CDLL:
         L.qo_debroglie_wavelength.restype = C.c_double
         L.qo_gc_acceptance.argtypes = [C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double]
         L.qo_gc_acceptance.restype = C.c_double
+        L.qo_expm_sym3.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.qo_expm_sym3.restype = None
         L.qo_pt_swap_accept.argtypes = [C.c_double] * 5
         L.qo_pt_swap_accept.restype = C.c_int
         _lib = L
@@ -207,6 +213,7 @@ class Replica:
     exchange_pos: tuple = (0.0, 0.0, 0.0)
     exchange_mol: np.ndarray | None = None  # (k, 3) positions of a molecular exchange species (k <= 8); None: the single atom
     n_exchange: int = 0
+    external_stress: np.ndarray | None = None  # (3, 3) eV / A^3: cell moves are judged by IsotensionCriteria; None: IsobaricCriteria
     last_energy: float = float("nan")
     last_kinetic: float = float("nan")
     momenta: np.ndarray | None = None
@@ -219,6 +226,14 @@ class Replica:
             self.n_atoms = len(self.positions)
         if self.accessible_volume is None:
             self.accessible_volume = abs(float(np.linalg.det(self.cell)))
+
+
+def expm_sym3(a: np.ndarray) -> np.ndarray:
+    """exp of a symmetric 3 x 3 matrix by the oracle's Jacobi rotations."""
+    a = np.ascontiguousarray(a, dtype=np.float64).reshape(9)
+    out = np.zeros(9)
+    lib().qo_expm_sym3(a.ctypes.data_as(C.POINTER(C.c_double)), out.ctypes.data_as(C.POINTER(C.c_double)))
+    return out.reshape(3, 3)
 
 
 def mc_run(par, rep: Replica, moves: list[MoveSpec], seed: int, replica_id: int, attempt_base: int, n_attempts: int):
@@ -244,6 +259,9 @@ def mc_run(par, rep: Replica, moves: list[MoveSpec], seed: int, replica_id: int,
         for q, v in enumerate(mol.reshape(-1)):
             st.exchange_mol[q] = float(v)
     st.n_exchange = rep.n_exchange
+    if rep.external_stress is not None:
+        st.isotension = 1
+        st.external_stress = (C.c_double * 9)(*np.asarray(rep.external_stress, dtype=np.float64).reshape(9))
     st.last_energy, st.last_kinetic = rep.last_energy, rep.last_kinetic
 
     mv = (Move * len(moves))()
@@ -306,6 +324,6 @@ def fbmc_step(par, positions, cell, pbc, mass, temperature, delta, seed, replica
 
 __all__ = [
     "LABEL_NONE", "MOVE_CELL", "MOVE_DISPLACEMENT", "MOVE_EXCHANGE", "MOVE_HMC", "OP_BALL", "OP_BOX", "OP_ISOTROPIC",
-    "OP_ROTATION", "OP_SPHERE", "OP_TRANSLATION", "OP_TRANSLATION_ROTATION", "OP_VERLET", "MoveSpec", "Replica", "build", "emt_params", "energy", "fbmc_step", "lib", "mc_run",
+    "OP_ANISOTROPIC", "OP_ROTATION", "OP_SHAPE", "OP_SPHERE", "OP_TRANSLATION", "OP_TRANSLATION_ROTATION", "OP_VERLET", "MoveSpec", "Replica", "build", "emt_params", "energy", "expm_sym3", "fbmc_step", "lib", "mc_run",
     "philox", "uniform_pair",
 ]  # fmt: skip

@@ -45,15 +45,16 @@ from ase.calculators.emt import EMT  # noqa: E402
 from ase.calculators.lj import LennardJones  # noqa: E402
 from quansino.integrators.displacement import Verlet  # noqa: E402
 from quansino.mc.canonical import Canonical, HamiltonianCanonical  # noqa: E402
-from quansino.mc.criteria import CanonicalCriteria, GrandCanonicalCriteria, IsobaricCriteria  # noqa: E402
+from quansino.mc.criteria import CanonicalCriteria, GrandCanonicalCriteria, IsobaricCriteria, IsotensionCriteria  # noqa: E402
 from quansino.mc.fbmc import AdaptiveForceBias, ForceBias  # noqa: E402
 from quansino.moves.composite import CompositeMove  # noqa: E402
 from quansino.mc.gcmc import GrandCanonical  # noqa: E402
 from quansino.mc.isobaric import Isobaric  # noqa: E402
+from quansino.mc.isotension import Isotension  # noqa: E402
 from quansino.moves.cell import CellMove  # noqa: E402
 from quansino.moves.displacement import DisplacementMove, HamiltonianDisplacementMove  # noqa: E402
 from quansino.moves.exchange import CompositeExchangeMove, ExchangeMove  # noqa: E402
-from quansino.operations.cell import IsotropicDeformation  # noqa: E402
+from quansino.operations.cell import AnisotropicDeformation, IsotropicDeformation, ShapeDeformation  # noqa: E402
 from quansino.operations.displacement import Ball, Box, Rotation, Sphere, Translation, TranslationRotation  # noqa: E402
 
 from oracle.philox import InjectedStream  # noqa: E402
@@ -306,6 +307,34 @@ def case_isobaric(seed, steps, p_cell, mask=None):
     )  # fmt: skip
 
 
+def case_general_cell(seed, n_attempts, op_name, max_value, p_cell, stress=None, shear=None, mask=None):
+    """Cell moves that leave GENERAL (triclinic) cells behind (operations/cell.py:56-141: AnisotropicDeformation, ShapeDeformation;
+    IsotropicDeformation of an already sheared cell), judged by IsobaricCriteria (mc/criteria.py:143-172) or, with `stress`, by
+    IsotensionCriteria through the Isotension driver (mc/criteria.py:175-219, mc/isotension.py:27-121); displacement moves in
+    between see the deformed cell."""
+    atoms, pos0, cell = cu_atoms(3, 0.05, 24680 + seed)
+    if shear is not None:  # start from a sheared cell: cell' = S @ cell, atoms carried along
+        atoms.set_cell(np.asarray(shear) @ cell, scale_atoms=True)
+        pos0, cell = atoms.positions.copy(), atoms.cell.array.copy()
+    n = len(atoms)
+    pressure = 1000.0 * bar
+    op = {"Anisotropic": AnisotropicDeformation, "Shape": ShapeDeformation, "Isotropic": IsotropicDeformation}[op_name](max_value, mask=mask)
+    common = dict(temperature=600.0, pressure=pressure, max_cycles=n_attempts,
+                  default_displacement_move=DisplacementMove(np.arange(n), Ball(0.1)), default_cell_move=CellMove(op))  # fmt: skip
+    mc = Isobaric(atoms, **common) if stress is None else Isotension(atoms, external_stress=np.asarray(stress, dtype=float), **common)
+    assert isinstance(mc.moves["default_cell_move"].criteria, IsobaricCriteria if stress is None else IsotensionCriteria)
+    mc.moves["default_cell_move"].probability = p_cell
+    mc.moves["default_displacement_move"].probability = 1 - p_cell
+    inject(mc, seed, 5)
+    tr = run_steps(mc, 1)
+    m9 = np.ones((3, 3), dtype=bool) if mask is None else np.asarray(mask, dtype=bool)
+    return dict(
+        kind="general_cell", seed=seed, replica=5, temperature=600.0, pressure=pressure, step_size=0.1, max_value=max_value, op=op_name,
+        p_cell=p_cell, isotension=int(stress is not None), external_stress=np.zeros((3, 3)) if stress is None else np.asarray(stress, dtype=float),
+        mask=m9, positions0=pos0, cell0=cell, positions=atoms.positions.copy(), cell=atoms.cell.array.copy(), **tr,
+    )  # fmt: skip
+
+
 def case_gc_lj(seed, n_attempts, mu):
     pos0, cell = octahedron("Pt", 4, 10.0)
     pos0 = rattle(pos0, 0.02, 99)
@@ -437,6 +466,12 @@ def main():
         "isobaric_default": lambda: case_isobaric(2001, 1, None),
         "isobaric_pcell": lambda: case_isobaric(2002, 1, 0.2),
         "isobaric_masked": lambda: case_isobaric(2003, 1, 0.25, mask=np.diag([True, False, True])),
+        "npt_anisotropic": lambda: case_general_cell(2101, 160, "Anisotropic", 0.008, 0.25),
+        "nst_shape": lambda: case_general_cell(2102, 160, "Shape", 0.012, 0.25, stress=np.array([[2e-3, 1e-3, 0.0], [1e-3, -1e-3, 5e-4], [0.0, 5e-4, 1e-3]])),
+        "nst_anisotropic_masked": lambda: case_general_cell(
+            2103, 160, "Anisotropic", 0.008, 0.25, stress=np.diag([1e-3, 2e-3, -1e-3]),
+            mask=np.array([[True, True, False], [True, True, False], [False, False, True]])),
+        "npt_isotropic_sheared": lambda: case_general_cell(2104, 120, "Isotropic", 0.02, 0.2, shear=[[1.0, 0.0, 0.0], [0.12, 1.0, 0.0], [-0.08, 0.1, 1.0]]),
         "gc_lj": lambda: case_gc_lj(3001, 700, -0.5),
         "gc_emt": lambda: case_gc_emt(3002, 150, -3.4, 3000.0),
         "gc_molecule": lambda: case_gc_molecule(3003, 600, -0.6),

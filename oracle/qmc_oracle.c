@@ -508,6 +508,84 @@ static void scale_positions(int n, double *pos, const double old_cell[9], const 
     }
 }
 
+/* exp of a SYMMETRIC 3 x 3 matrix (the reference: scipy.linalg.expm, operations/cell.py:96,141) by cyclic Jacobi rotations:
+ * A = V diag(w) V^T  =>  exp(A) = V diag(exp(w)) V^T.  Deliberately a different method from the device's scaling-and-squaring
+ * Taylor polynomial; tests/test_oracle.py pins it against scipy to 1e-15. */
+static void expm_sym3(const double A[9], double E[9]) {
+    double a[3][3], v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) a[i][j] = A[3 * i + j];
+    for (int sweep = 0; sweep < 64; ++sweep) {
+        double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (fabs(a[p][q]) < 1e-300) continue;
+                double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < 3; ++k) { /* A <- A J */
+                    double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - sn * akq; a[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < 3; ++k) { /* A <- J^T A */
+                    double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - sn * aqk; a[q][k] = sn * apk + c * aqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = c * vkp - sn * vkq; v[k][q] = sn * vkp + c * vkq;
+                }
+            }
+    }
+    double w[3] = {exp(a[0][0]), exp(a[1][1]), exp(a[2][2])};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) E[3 * i + j] = (v[i][0] * w[0] * v[j][0] + v[i][1] * w[1] * v[j][1]) + v[i][2] * w[2] * v[j][2];
+}
+
+void qo_expm_sym3(const double A[9], double E[9]) { expm_sym3(A, E); }
+
+static void mat3_mul(const double a[9], const double b[9], double c[9]) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) c[3 * i + j] = (a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j]) + a[3 * i + 2] * b[6 + j];
+}
+
+/* deformation gradient of a CellMove (operations/cell.py:67-169) from the six uniform draws u[0..5] of the attempt */
+static void deformation_gradient(const qo_move_t *mv, const double u[6], double F[9]) {
+    if (mv->op == QO_OP_ISOTROPIC) {
+        double s = exp(-mv->step + (mv->step - -mv->step) * u[0]);
+        for (int q = 0; q < 9; ++q) F[q] = (q % 4 == 0) ? ((mv->axes == 0 || ((mv->axes >> (q / 4)) & 1)) ? s : 1.0) : 0.0;
+        return;
+    }
+    double c[6], T[9], E[9];
+    for (int q = 0; q < 6; ++q) c[q] = -mv->step + (mv->step - -mv->step) * u[q];
+    double mean = mv->op == QO_OP_SHAPE ? (c[0] + c[1] + c[2]) / 3.0 : 0.0;
+    T[0] = c[0] - mean; T[4] = c[1] - mean; T[8] = c[2] - mean;
+    T[1] = T[3] = c[3]; T[2] = T[6] = c[4]; T[5] = T[7] = c[5];
+    expm_sym3(T, E);
+    const int mask = mv->axes == 0 ? 0x1FF : mv->axes; /* bit 3 i + j = mask[i][j] */
+    for (int q = 0; q < 9; ++q) F[q] = ((mask >> q) & 1) ? E[q] : ((q % 4 == 0) ? 1.0 : 0.0);
+}
+
+/* the work term of the cell criteria: IsobaricCriteria p dV (mc/criteria.py:168-170), or IsotensionCriteria's elastic energy
+ * (:196-208), literally: strain = 0.5 (inv(old^T) @ new^T @ old @ inv(old) - 1); p dV + V_old trace((stress - p) @ strain) with
+ * the scalar p subtracted from EVERY component of the stress matrix (numpy broadcasting) */
+static double cell_work(const qo_state_t *st, const double new_cell[9]) {
+    double v_new = volume(new_cell), v_old = volume(st->cell);
+    double work = st->pressure * (v_new - v_old);
+    if (st->isotension) {
+        double oT[9], nT[9], ioT[9], io[9], P[9], Q[9], S[9];
+        for (int q = 0; q < 9; ++q) { oT[q] = st->cell[3 * (q % 3) + q / 3]; nT[q] = new_cell[3 * (q % 3) + q / 3]; }
+        inv3(oT, ioT); inv3(st->cell, io);
+        mat3_mul(ioT, nT, P); mat3_mul(P, st->cell, Q); mat3_mul(Q, io, S);
+        double tr = 0.0;
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) tr += (st->external_stress[3 * i + j] - st->pressure) * (0.5 * (S[3 * j + i] - (i == j ? 1.0 : 0.0)));
+        work += v_old * tr;
+    }
+    return work;
+}
+
 int qo_fbmc_step(const qo_potential_t *pot, int32_t n, double *pos, const double *cell, const int32_t *pbc, double mass,
                  double temperature, double delta, uint64_t seed, uint32_t replica, uint64_t step, double *energy,
                  double *gamma_max, int32_t *n_iter) {
@@ -873,12 +951,22 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                 }
             }
         } else if (mv->type == QO_MOVE_CELL) {
-            /* operations/cell.py:167-169, moves/cell.py:73-84, mc/criteria.py:160-172 */
-            double s = exp(-mv->step + (mv->step - -mv->step) * opd[0]);
-            double new_cell[9];
-            for (int r = 0; r < 3; ++r) /* F = eye * s * mask + eye * ~mask (operations/cell.py:167-169); F @ cell */
-                for (int c = 0; c < 3; ++c)
-                    new_cell[3 * r + c] = ((mv->axes == 0 || ((mv->axes >> r) & 1)) ? s : 1.0) * st->cell[3 * r + c];
+            /* operations/cell.py:67-169, moves/cell.py:73-84, mc/criteria.py:160-219.  Draws of Anisotropic / ShapeDeformation
+             * (uniform(-max, max, size=6)): components 0..2 are the operation draws, 3..5 the attempt's extra draws 0..2 */
+            double u6[6] = {opd[0], opd[1], opd[2], 0, 0, 0}, F[9], new_cell[9];
+            if (mv->op != QO_OP_ISOTROPIC) {
+                double e0[2], e1[2];
+                qo_uniform_pair(seed, attempt, replica, 64, e0);
+                qo_uniform_pair(seed, attempt, replica, 65, e1);
+                u6[3] = e0[0]; u6[4] = e0[1]; u6[5] = e1[0];
+            }
+            deformation_gradient(mv, u6, F);
+            if (mv->op == QO_OP_ISOTROPIC) { /* F is diagonal: row r scaled by F[r][r], exactly */
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) new_cell[3 * r + c] = F[4 * r] * st->cell[3 * r + c];
+            } else {
+                mat3_mul(F, st->cell, new_cell);
+            }
             memcpy(trial, st->pos, sizeof(double) * 3 * (size_t)n);
             scale_positions(n, trial, st->cell, new_cell);
             double e_new;
@@ -886,7 +974,7 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
             cnt[0] += np_; cnt[3] += 1; cnt[1] += np_; cnt[2] += n;
             delta = e_new - st->last_energy;
             double v_new = volume(new_cell), v_old = volume(st->cell);
-            double x = -(delta + st->pressure * (v_new - v_old)) / kT + (double)(n + 1) * log(v_new / v_old);
+            double x = -(delta + cell_work(st, new_cell)) / kT + (double)(n + 1) * log(v_new / v_old);
             if (x > 709.782712893384) { rc = -4; goto done; }
             accepted = u_accept < exp(x);
             if (accepted) {

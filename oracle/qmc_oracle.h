@@ -18,7 +18,9 @@ extern "C" {
 enum { QO_POT_EMT = 0, QO_POT_LJ = 1 };
 enum { QO_MOVE_DISPLACEMENT = 0, QO_MOVE_CELL = 1, QO_MOVE_EXCHANGE = 2, QO_MOVE_HMC = 3 };
 enum { QO_OP_BALL = 0, QO_OP_BOX = 1, QO_OP_SPHERE = 2, QO_OP_TRANSLATION = 3, QO_OP_ISOTROPIC = 4, QO_OP_VERLET = 5, QO_OP_ROTATION = 6,
-       QO_OP_TRANSLATION_ROTATION = 7 };
+       QO_OP_TRANSLATION_ROTATION = 7,
+       QO_OP_ANISOTROPIC = 8, /* AnisotropicDeformation (operations/cell.py:56-96) */
+       QO_OP_SHAPE = 9        /* ShapeDeformation (operations/cell.py:99-141) */ };
 
 /* ase/calculators/emt.py (single species) and ase/calculators/lj.py constants, eV / Angstrom */
 typedef struct {
@@ -75,6 +77,9 @@ typedef struct {
     int32_t n_exchange_atoms;    /* atoms of the exchange molecule; 0 / 1: the single atom at exchange_pos */
     int32_t _pad2;
     double exchange_mol[24];     /* [n_exchange_atoms][3] exchange_atoms.positions (at most 8 atoms) */
+    int32_t isotension;          /* cell moves judged by IsotensionCriteria (mc/criteria.py:175-219) instead of IsobaricCriteria */
+    int32_t _pad3;
+    double external_stress[9];   /* eV / A^3, row-major (DeformationContext.external_stress) */
 } qo_state_t;
 
 /* Per-attempt trace (all optional, may be NULL). */
@@ -115,6 +120,9 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
 
 /* GrandCanonicalCriteria prefactor pieces (mc/criteria.py:243-271), exposed for the known-answer tests. */
 double qo_debroglie_wavelength(double mass_amu, double temperature);
+/* exp of a symmetric 3 x 3 matrix (row-major), as used by the Anisotropic / Shape deformations */
+void qo_expm_sym3(const double A[9], double E[9]);
+
 double qo_gc_acceptance(double delta_e, int32_t particle_delta, int32_t n_exchange, double accessible_volume,
                         double mass_amu, double temperature, double mu);
 

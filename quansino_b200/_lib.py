@@ -21,6 +21,7 @@ MOVE_DISPLACEMENT, MOVE_CELL, MOVE_EXCHANGE, MOVE_HMC = 0, 1, 2, 3
 (FIELD_POS, FIELD_CELL, FIELD_N_ATOMS, FIELD_ENERGY, FIELD_TEMPERATURE, FIELD_SIGMA1, FIELD_EATOM, FIELD_MOMENTA, FIELD_KINETIC,
  FIELD_N_EXCHANGE, FIELD_COUNTERS, FIELD_STATUS, FIELD_PAIR_EVALS, FIELD_LABELS0) = range(14)
 OP_BALL, OP_BOX, OP_SPHERE, OP_TRANSLATION, OP_ISOTROPIC, OP_VERLET, OP_ROTATION, OP_TRANSLATION_ROTATION = 0, 1, 2, 3, 4, 5, 6, 7
+OP_ANISOTROPIC, OP_SHAPE = 8, 9
 
 NBR_SKIN_DEFAULT = 0.7  # include/quansino_b200.h: QMC_NBR_SKIN_DEFAULT
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = -1, -2, -3, -4
@@ -102,6 +103,9 @@ class Batch(C.Structure):
         ("n_exchange_atoms", C.c_int32),
         ("_pad2", C.c_int32),
         ("exchange_mol", C.c_double * 24),
+        ("triclinic", C.c_int32),
+        ("isotension", C.c_int32),
+        ("external_stress", C.c_double * 9),
     ]
 
 

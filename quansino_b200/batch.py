@@ -102,18 +102,38 @@ class BatchedAtoms:
         return self.positions[r, : self.n_atoms[r]]
 
 
-def _check_cell(cell: np.ndarray, pbc, cutoff: float) -> None:
-    off = cell.copy()
-    off[:, [0, 1, 2], [0, 1, 2]] = 0.0
-    if np.any(off != 0.0):
-        raise NotImplementedError("the GPU path needs orthorhombic cells with axes along x, y, z (diagonal cell matrix)")
-    diag = cell[:, [0, 1, 2], [0, 1, 2]]
+def cell_heights(cell: np.ndarray) -> np.ndarray:
+    """Perpendicular widths of (R, 3, 3) cells: w_k = |det| / |a_(k+1) x a_(k+2)| (what bounds the image search,
+    ``ase/neighborlist.py``)."""
+    cell = np.asarray(cell, dtype=np.float64).reshape(-1, 3, 3)
+    vol = np.abs(np.linalg.det(cell))
+    out = np.empty((len(cell), 3))
     for k in range(3):
-        if pbc[k] and np.any(diag[:, k] < cutoff * (1.0 + 1e-9)):
+        out[:, k] = vol / np.linalg.norm(np.cross(cell[:, (k + 1) % 3], cell[:, (k + 2) % 3]), axis=1)
+    return out
+
+
+def _is_diagonal(cell: np.ndarray) -> bool:
+    off = np.array(cell, dtype=np.float64, copy=True).reshape(-1, 3, 3)
+    off[:, [0, 1, 2], [0, 1, 2]] = 0.0
+    return not np.any(off != 0.0)
+
+
+def _check_cell(cell: np.ndarray, pbc, cutoff: float) -> bool:
+    """Checks the cells against the image search of the kernels (two images per axis: every periodic height >= the cutoff);
+    returns True if some cell is not diagonal (-> the general-cell kernels, ``csrc/sweep_tri.cuh``)."""
+    if len(cell) == 0:
+        return False
+    if np.any(np.abs(np.linalg.det(cell)) <= 0.0):
+        raise ValueError("singular cell")
+    h = cell_heights(cell)
+    for k in range(3):
+        if pbc[k] and np.any(h[:, k] < cutoff * (1.0 + 1e-9)):
             raise NotImplementedError(
-                f"periodic cell edge {diag[:, k].min():.3f} A along axis {k} is shorter than the neighbour cutoff "
+                f"periodic cell height {h[:, k].min():.3f} A along axis {k} is shorter than the neighbour cutoff "
                 f"{cutoff:.3f} A: more than two images per axis are not available on the GPU path"
             )
+    return not _is_diagonal(cell)
 
 
 class ReplicaBatch:
@@ -144,7 +164,11 @@ class ReplicaBatch:
         self.potential = self.calc.lower(atoms.symbol)
         self.R, self.n_max = atoms.n_replicas, atoms.n_max
         self.replica_offset = int(replica_offset)
-        _check_cell(atoms.cell, self.pbc, self.calc.cutoff)
+        # general (triclinic) cells run through their own kernels; drivers also switch this on for moves that leave general
+        # cells behind (AnisotropicDeformation, ShapeDeformation) or need the IsotensionCriteria
+        self.triclinic = _check_cell(atoms.cell, self.pbc, self.calc.cutoff)
+        self.isotension = False
+        self.external_stress = np.zeros((3, 3))
         dev, f64 = self.device, torch.float64
         R, N = self.R, self.n_max
         self.pos = torch.zeros((R, 3, N), dtype=f64, device=dev)
@@ -189,7 +213,9 @@ class ReplicaBatch:
         self.n_atoms.copy_(n, non_blocking=non_blocking)
         nbytes = pos.numel() * 8 + cell.numel() * 8 + n.numel() * 4
         self.rows_valid = False
-        diag = atoms.cell[:, [0, 1, 2], [0, 1, 2]] if self.R else np.zeros((1, 3))
+        if self.R and not _is_diagonal(atoms.cell):
+            self.triclinic = True
+        diag = cell_heights(atoms.cell) if self.R else np.zeros((1, 3))  # (= the edges of diagonal cells)
         self._min_edge = tuple(float(diag[:, k].min()) for k in range(3))
         # one fixed cell shared by every replica: the kernels read it from their arguments (fast path)
         self.cells_uniform = bool(self.R > 0 and np.all(atoms.cell == atoms.cell[0]))
@@ -251,6 +277,8 @@ class ReplicaBatch:
         mol = np.asarray(self.exchange_mol, dtype=np.float64).reshape(-1, 3)
         b.n_exchange_atoms = len(mol)
         b.exchange_mol = (C.c_double * 24)(*mol.reshape(-1), *([0.0] * (24 - mol.size)))
+        b.triclinic, b.isotension = int(self.triclinic), int(self.isotension)
+        b.external_stress = (C.c_double * 9)(*np.asarray(self.external_stress, dtype=np.float64).reshape(9))
         return b
 
     def stream(self) -> int:
@@ -260,7 +288,7 @@ class ReplicaBatch:
     def rows_possible(self, skin: float | None = None) -> bool:
         """Whether this batch can carry neighbour rows: at most 1024 atoms per replica and every periodic edge at least
         cutoff + skin (checked against the cells known to the host; the kernel re-checks per replica)."""
-        if self.n_max > 1024 or self.R == 0:
+        if self.n_max > 1024 or self.R == 0 or self.triclinic:
             return False
         skin = float(skin if skin is not None else (self.nbr_skin or _lib.NBR_SKIN_DEFAULT))
         need = self.calc.cutoff * (1.0 + 1e-9) + skin

@@ -99,11 +99,14 @@ struct Inst {
     qmc::rows_launch_fn sweep_rows;
     int row_words;   // u32 words per neighbour row
     int rows_wide_reps;  // replicas one SM holds with four warps per replica (0: not instantiated)
+    qmc::tri_launch_fn sweep_tri;      // general (triclinic) cells
+    qmc::energy_launch_fn energy_tri;
 };
 
 #define QMC_TABLE_ROW(POT, NS) \
     {NS, qmc::sweep_launch_##POT##_##NS, qmc::energy_launch_##POT##_##NS, qmc::sweep_block_launch_##POT##_##NS, qmc::LayoutB<POT, NS>::REPS, \
-     qmc::sweep_rows_launch_##POT##_##NS, qmc::LayoutR<POT, NS, 1>::ROWW, NS >= 256 ? qmc::LayoutR<POT, NS, 4>::REPS : 0},
+     qmc::sweep_rows_launch_##POT##_##NS, qmc::LayoutR<POT, NS, 1>::ROWW, NS >= 256 ? qmc::LayoutR<POT, NS, 4>::REPS : 0, \
+     qmc::sweep_tri_launch_##POT##_##NS, qmc::energy_tri_launch_##POT##_##NS},
 const Inst g_inst[2][7] = {{QMC_FOR_EACH_NS(QMC_TABLE_ROW, 0)}, {QMC_FOR_EACH_NS(QMC_TABLE_ROW, 1)}};
 
 const Inst *find_inst(int kind, int n_max) {
@@ -118,8 +121,8 @@ const Inst *find_inst(int kind, int n_max) {
 int fill_cell_args(const qmc_batch_t *b, const qmc::PotDev &pd, qmc::SweepArgs &a) {
     const double diag[3] = {b->cell_diag[0], b->cell_diag[1], b->cell_diag[2]};
     const double one[3] = {1.0, 1.0, 1.0};
-    const bool ok = qmc::cell_constants(b->cells_uniform ? diag : one, b->pbc, pd.cut_pre, a.cell);
-    if (b->cells_uniform && !ok)
+    const bool ok = qmc::cell_constants(b->cells_uniform && !b->triclinic ? diag : one, b->pbc, pd.cut_pre, a.cell);
+    if (b->cells_uniform && !b->triclinic && !ok)
         return fail(QMC_ERR_UNSUPPORTED, "a periodic cell edge is shorter than the neighbour cutoff %.3f A", pd.cut);
     return QMC_OK;
 }
@@ -199,7 +202,7 @@ int qmc_atom_energies(const qmc_potential_t *pot, const qmc_batch_t *batch, doub
     if ((rc = fill_cell_args(batch, a.pot, a))) return rc;
     const Inst *inst = find_inst(pot->kind, batch->n_max);
     if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica kernels");
-    return inst->energy(a, (long long *)pair_count, (cudaStream_t)stream, g_err, sizeof(g_err));
+    return (batch->triclinic ? inst->energy_tri : inst->energy)(a, (long long *)pair_count, (cudaStream_t)stream, g_err, sizeof(g_err));
 }
 
 int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move_t *moves, int32_t n_moves, uint64_t seed,
@@ -260,9 +263,16 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
                     return fail(QMC_ERR_UNSUPPORTED, "move %d: displacement operation %d is not available on the GPU path", m, mv.op);
                 break;
             case QMC_MOVE_CELL:
-                if (mv.axes < 0 || mv.axes > 7) return fail(QMC_ERR_INVALID, "move %d: axes must be a mask of bits 0..2", m);
-                if (mv.op != QMC_OP_ISOTROPIC)
-                    return fail(QMC_ERR_UNSUPPORTED, "move %d: only IsotropicDeformation is available on the GPU path", m);
+                if (mv.axes < 0) return fail(QMC_ERR_INVALID, "move %d: negative axes mask", m);
+                if (mv.op == QMC_OP_ANISOTROPIC || mv.op == QMC_OP_SHAPE) {
+                    if (!batch->triclinic)
+                        return fail(QMC_ERR_INVALID, "move %d: AnisotropicDeformation / ShapeDeformation leave general cells behind: set batch.triclinic", m);
+                    if (mv.axes > 0x1FF) return fail(QMC_ERR_INVALID, "move %d: axes must be a mask of bits 0..8 (the 3 x 3 deformation mask)", m);
+                } else if (mv.op != QMC_OP_ISOTROPIC) {
+                    return fail(QMC_ERR_UNSUPPORTED, "move %d: cell operation %d is not available on the GPU path", m, mv.op);
+                } else if (mv.axes > 7) {
+                    return fail(QMC_ERR_INVALID, "move %d: axes must be a mask of bits 0..2", m);
+                }
                 break;
             case QMC_MOVE_EXCHANGE:
                 if (mv.op != QMC_OP_TRANSLATION && !(mv.op == QMC_OP_TRANSLATION_ROTATION && (mv.chain & 8)))
@@ -286,7 +296,7 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         a.mv[m].default_label = mv.default_label;
         a.mv[m].repeat = mv.repeat > 0 ? mv.repeat : 1;
         a.mv[m].chain = mv.chain;
-        a.mv[m].axes = (mv.axes & 7) ? (mv.axes & 7) : 7;
+        a.mv[m].axes = (mv.op == QMC_OP_ANISOTROPIC || mv.op == QMC_OP_SHAPE) ? ((mv.axes & 0x1FF) ? (mv.axes & 0x1FF) : 0x1FF) : ((mv.axes & 7) ? (mv.axes & 7) : 7);
         if (mv.n_extra_ops < 0 || mv.n_extra_ops > 2) return fail(QMC_ERR_UNSUPPORTED, "move %d: at most three operations per move on the GPU path", m);
         if (mv.n_extra_ops > 0 && (mv.type != QMC_MOVE_DISPLACEMENT || mv.chain || mv.repeat > 1 || mv.op == QMC_OP_ROTATION))
             return fail(QMC_ERR_UNSUPPORTED, "move %d: composite operations belong to plain single-atom displacement moves", m);
@@ -360,6 +370,16 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     if ((rc = fill_cell_args(batch, a.pot, a))) return rc;
     const Inst *inst = find_inst(pot->kind, batch->n_max);
     if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica sweep kernel");
+    if (batch->triclinic) {
+        // general cells (csrc/sweep_tri.cuh): plain single-atom displacement moves and cell moves
+        if (any_exchange || any_composite || a.n_forced > 0)
+            return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: exchange, composite and forced moves are not available on the GPU path");
+        for (int m = 0; m < n_moves; ++m)
+            if (moves[m].type == QMC_MOVE_DISPLACEMENT && moves[m].op != QMC_OP_BALL && moves[m].op != QMC_OP_BOX && moves[m].op != QMC_OP_SPHERE)
+                return fail(QMC_ERR_UNSUPPORTED, "move %d: general (triclinic) cells take Ball / Box / Sphere displacements of single atoms", m);
+        if (batch->nbr_state) CUDA_TRY(cudaMemsetAsync(batch->nbr_state, 0, (size_t)batch->n_replicas * sizeof(int32_t), (cudaStream_t)stream));
+        return inst->sweep_tri(a, (cudaStream_t)stream, g_err, sizeof(g_err));
+    }
     // one warp per replica fills the GPU only with thousands of replicas; smaller batches run CTA-per-replica
     int sms = 148, dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
@@ -413,6 +433,7 @@ int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double
     if (!pot || !forces) return fail(QMC_ERR_INVALID, "potential / forces is NULL");
     int rc;
     if ((rc = check_batch(batch, pot->kind))) return rc;
+    if (batch->triclinic) return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: the force kernels (Hamiltonian and ForceBias moves) take diagonal cells only");
     if (batch->n_replicas == 0) return QMC_OK;
     qmc::PotDev pd;
     if ((rc = make_potdev(pot, pd))) return rc;
@@ -433,6 +454,7 @@ int qmc_hmc(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move
     if (!pot || !move) return fail(QMC_ERR_INVALID, "potential / move is NULL");
     int rc;
     if ((rc = check_batch(batch, pot->kind))) return rc;
+    if (batch->triclinic) return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: the force kernels (Hamiltonian and ForceBias moves) take diagonal cells only");
     if (move->type != QMC_MOVE_HMC || move->op != QMC_OP_VERLET)
         return fail(QMC_ERR_UNSUPPORTED, "qmc_hmc runs HamiltonianDisplacementMove + Verlet only");
     if (!batch->momenta || !batch->kinetic) return fail(QMC_ERR_INVALID, "Hamiltonian moves need batch.momenta and batch.kinetic");
@@ -461,6 +483,7 @@ int qmc_fbmc_step_v(const qmc_potential_t *pot, const qmc_batch_t *batch, double
     if (!pot || !forces) return fail(QMC_ERR_INVALID, "potential / forces is NULL");
     int rc;
     if ((rc = check_batch(batch, pot->kind))) return rc;
+    if (batch->triclinic) return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: the force kernels (Hamiltonian and ForceBias moves) take diagonal cells only");
     if (!delta_per_replica && !(delta > 0.0)) return fail(QMC_ERR_INVALID, "delta must be positive");
     if (batch->n_replicas == 0) return QMC_OK;
     qmc::PotDev pd;

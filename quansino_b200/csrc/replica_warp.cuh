@@ -138,6 +138,7 @@ __host__ __device__ inline bool cell_constants(const double diag[3], const int p
 
 template <class LY, bool UNIFORM>
 struct CellView {
+    static constexpr bool TRI = false;
     const CellArgs *u;  // kernel-argument cell (uniform) -- also carries the pbc flags
     double *s;          // shared-memory cell constants of this replica (per-replica cells)
     __device__ __forceinline__ Axis axis(int k) const {
@@ -145,6 +146,64 @@ struct CellView {
         return Axis{s[k], s[3 + k], s[6 + k]};
     }
     __device__ __forceinline__ bool per(int k) const { return u->per[k] != 0; }
+};
+
+// General (triclinic) cell of one replica, constants in shared memory (csrc/sweep_tri.cuh: store_cell_tri):
+//   s[0..8]   H, row k = cell vector a_k (positions = fractional @ H)
+//   s[9..17]  H^-1 (fractional_k = sum_x d_x * s[9 + 3 x + k]); the column of a non-periodic axis is zero
+//   s[18..20] thr_k = 1 - cutoff' / w_k (w_k = height of the cell along axis k), 1e300 for a non-periodic axis
+// Image rule: with every periodic height w_k >= cutoff', an image of j inside the cutoff has fractional components |f_k| <=
+// cutoff' / w_k <= 1 (f_k = r . b_k, |b_k| = 1 / w_k), so with fr = f - rint(f) the candidates are fr_k and, where |fr_k| > thr_k,
+// fr_k - sign(fr_k): at most 2 x 2 x 2 images, the same subset enumeration as for diagonal cells -- but the image found by rounding
+// is NOT always the closest one, so the second images are looked at whether or not the first one is inside the cutoff.
+struct TriView {
+    static constexpr bool TRI = true;
+    const double *s;
+    __device__ __forceinline__ bool per(int k) const { return s[18 + k] < 1e299; }
+    // image of d = xj - xi found by rounding the fractional coordinates; sg[k] = sign of the reduced fractional coordinate;
+    // returns bit k set if the image shifted by -sg[k] a_k can be inside the cutoff as well
+    __device__ __forceinline__ unsigned reduce(double dx, double dy, double dz, double d0[3], double sg[3]) const {
+        const double f0 = fma(dz, s[15], fma(dy, s[12], dx * s[9]));
+        const double f1 = fma(dz, s[16], fma(dy, s[13], dx * s[10]));
+        const double f2 = fma(dz, s[17], fma(dy, s[14], dx * s[11]));
+        const double k0 = (f0 + RINT_MAGIC) - RINT_MAGIC, k1 = (f1 + RINT_MAGIC) - RINT_MAGIC, k2 = (f2 + RINT_MAGIC) - RINT_MAGIC;
+        d0[0] = fma(-k2, s[6], fma(-k1, s[3], fma(-k0, s[0], dx)));
+        d0[1] = fma(-k2, s[7], fma(-k1, s[4], fma(-k0, s[1], dy)));
+        d0[2] = fma(-k2, s[8], fma(-k1, s[5], fma(-k0, s[2], dz)));
+        const double r0 = f0 - k0, r1 = f1 - k1, r2 = f2 - k2;
+        sg[0] = copysign(1.0, r0);
+        sg[1] = copysign(1.0, r1);
+        sg[2] = copysign(1.0, r2);
+        return (fabs(r0) > s[18] ? 1u : 0u) | (fabs(r1) > s[19] ? 2u : 0u) | (fabs(r2) > s[20] ? 4u : 0u);
+    }
+    // r^2 of the CLOSEST image among the candidates (subset `best` of the flagged axes `fl`): flagged lanes walk their <= 8 subsets
+    __device__ __forceinline__ double nearest(double dx, double dy, double dz, double d0[3], double sg[3], unsigned &fl, unsigned &best) const {
+        fl = reduce(dx, dy, dz, d0, sg);
+        double rb = fma(d0[2], d0[2], fma(d0[1], d0[1], d0[0] * d0[0]));
+        best = 0u;
+        if (fl != 0u) {
+            unsigned c = fl & (0u - fl);
+            while (true) {
+                double d[3];
+                shifted(d0, sg, c, d);
+                const double r2 = fma(d[2], d[2], fma(d[1], d[1], d[0] * d[0]));
+                if (r2 < rb) {
+                    rb = r2;
+                    best = c;
+                }
+                if (c == fl) break;
+                c = ((c | (~fl & 7u)) + 1u) & fl;
+            }
+        }
+        return rb;
+    }
+    // the image of subset c (bit k: shifted by -sg[k] a_k)
+    __device__ __forceinline__ void shifted(const double d0[3], const double sg[3], unsigned c, double d[3]) const {
+        const double m0 = (c & 1u) ? sg[0] : 0.0, m1 = (c & 2u) ? sg[1] : 0.0, m2 = (c & 4u) ? sg[2] : 0.0;
+        d[0] = fma(-m2, s[6], fma(-m1, s[3], fma(-m0, s[0], d0[0])));
+        d[1] = fma(-m2, s[7], fma(-m1, s[4], fma(-m0, s[1], d0[1])));
+        d[2] = fma(-m2, s[8], fma(-m1, s[5], fma(-m0, s[2], d0[2])));
+    }
 };
 
 // nearest image d0 of (xj - xi) along one axis (4 FP64 operations, branch-free); sets `bit` in `extra` if the second image
@@ -167,11 +226,85 @@ __device__ __forceinline__ double axis_nearest_any(double xi, double xj, const A
     return d0;
 }
 
+template <class CELL>
+__device__ __forceinline__ Axis axis_of(const CELL &C, int k) {
+    if constexpr (CELL::TRI) return Axis{0.0, 0.0, 0.0};
+    else return C.axis(k);
+}
+
 struct DeltaAcc {
     double v;     // per-lane partial of the signed sigma_2 terms (EMT) or signed pair energies (LJ)
     double snew;  // per-lane partial of the sigma_1 terms of the NEW position (= sigma_1 of the moved atom)
     int pairs;    // per-lane count of evaluated list entries
 };
+
+// One-sided scan in a general cell (full-energy rows): every image of every other atom inside the cutoff, signed r^2 into the list.
+template <class RV, class CELL>
+__device__ __forceinline__ int scan_neighbours_tri(const PotDev &pot, const RV &R, const CELL &C, const int lane, const unsigned lt, int n_scan,
+                                                   int i_excl, bool side, const double p[3], int &n2, int &xstart, int &status,
+                                                   int tile_first, int tile_step) {
+    uint32_t *queue = R.queue();
+    int cnt = 0, nq = 0;
+    for (int base = tile_first * 32; base < n_scan; base += 32 * tile_step) {
+        const int j = base + lane;
+        const bool valid = j < n_scan && j != i_excl;
+        const int jc = valid ? j : 0;
+        double d0[3], sg[3];
+        const unsigned fl = C.reduce(R.x(jc) - p[0], R.y(jc) - p[1], R.z(jc) - p[2], d0, sg);
+        const double r2 = fma(d0[2], d0[2], fma(d0[1], d0[1], d0[0] * d0[0]));
+        const bool in = valid && r2 < pot.cut_pre2;
+        const unsigned b = __ballot_sync(FULL, in);
+        const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
+        if (in) R.lr(pos) = side ? r2 : -r2;
+        cnt += __popc(b);
+        const bool ex = valid && fl != 0u;  // further images are looked at whether or not this one is inside
+        const unsigned bq = __ballot_sync(FULL, ex);
+        if (ex) queue[min(nq + __popc(bq & lt), RV::QCAP - 1)] = (unsigned)j;
+        nq += __popc(bq);
+    }
+    if (cnt > RV::CAPE) {
+        status |= QMC_STATUS_LIST_OVERFLOW;
+        cnt = RV::CAPE;
+    }
+    n2 = cnt;
+    xstart = cnt;
+    if (nq > RV::QCAP) {
+        status |= QMC_STATUS_LIST_OVERFLOW;
+        nq = RV::QCAP;
+    }
+    if (nq > 0) {
+        __syncwarp();
+        for (int q0 = 0; q0 < nq; q0 += 32) {
+            const int q = q0 + lane;
+            const bool has = q < nq;
+            const int j = has ? (int)queue[q] : 0;
+            double d0[3], sg[3];
+            const unsigned fl = C.reduce(R.x(j) - p[0], R.y(j) - p[1], R.z(j) - p[2], d0, sg);
+            unsigned c = fl & (0u - fl);  // first non-empty subset of fl
+            bool more = has && fl != 0u;
+            while (__any_sync(FULL, more)) {
+                double d[3];
+                C.shifted(d0, sg, c, d);
+                const double r2 = fma(d[2], d[2], fma(d[1], d[1], d[0] * d[0]));
+                const bool in = more && r2 < pot.cut_pre2;
+                const unsigned b = __ballot_sync(FULL, in);
+                const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
+                if (in) R.lr(pos) = side ? r2 : -r2;
+                cnt += __popc(b);
+                if (more) {
+                    if (c == fl) more = false;
+                    else c = ((c | (~fl & 7u)) + 1u) & fl;
+                }
+            }
+        }
+    }
+    if (cnt > RV::CAPE) {
+        status |= QMC_STATUS_LIST_OVERFLOW;
+        cnt = RV::CAPE;
+    }
+    __syncwarp();
+    return cnt;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // One-sided scan (an inserted atom or a row of a full evaluation: new side; a deleted atom: old side): fills the list with the
@@ -187,6 +320,10 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const RV &R, c
                                                int tile_step = 1) {
     constexpr bool TRACK = (MODE == 0 && RV::EMT);
     uint32_t *queue = R.queue();  // one word per flagged neighbour: at most n - 1 <= QCAP
+    if constexpr (CELL::TRI) {
+        static_assert(!TRACK, "general cells: full-energy rows only (the slot bookkeeping of the local delta lives in scan_both)");
+        return scan_neighbours_tri<RV>(pot, R, C, lane, lt, n_scan, i_excl, has_new, has_new ? pn : po, n2, xstart, status, tile_first, tile_step);
+    } else {
     const bool p0 = C.per(0), p1 = C.per(1), p2 = C.per(2);
     const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);
     const bool side = has_new;  // true: new position (positive r^2), false: old position (negative)
@@ -264,6 +401,7 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const RV &R, c
     }
     __syncwarp();
     return cnt;
+    }
 }
 
 // Two-sided scan for a single-atom displacement (old and new position of atom i_excl): every neighbour that is inside the cutoff on
@@ -279,7 +417,8 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
     static_assert(RV::CAPE % 2 == 0, "paired list slots need an even capacity");
     uint32_t *queue = R.queue();
     const bool p0 = C.per(0), p1 = C.per(1), p2 = C.per(2);
-    const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);
+    const auto A0 = axis_of(C, 0), A1 = axis_of(C, 1), A2 = axis_of(C, 2);  // (unused for general cells)
+    (void)p0; (void)p1; (void)p2; (void)A0; (void)A1; (void)A2;
     int cnt = 0, nq = 0;
     // one tile: 32 candidate atoms.  The distance arithmetic of a tile is a chain of dependent instructions (load -> nearest image
     // -> r^2 -> compare -> ballot -> slot); a warp is latency-bound (7 warps per scheduler each progress as if alone), so TWO
@@ -295,6 +434,20 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
         t.valid = t.j < n_scan && t.j != i_excl;
         const int jc = t.valid ? t.j : 0;
         const double xj = R.x(jc), yj = R.y(jc), zj = R.z(jc);
+        if constexpr (CELL::TRI) {
+            // general cells: the slot pair holds the CLOSEST image of each side (found among the <= 8 candidates), so that -- as for
+            // diagonal cells -- further images need looking at only if that one is inside, and their sigma_1 terms have a slot
+            double d0[3], sg[3];
+            unsigned flo, fln, best;
+            const double r2o = C.nearest(xj - po[0], yj - po[1], zj - po[2], d0, sg, flo, best);
+            t.r2n = C.nearest(xj - pn[0], yj - pn[1], zj - pn[2], d0, sg, fln, best);
+            const bool in_o = t.valid && r2o < pot.cut_pre2, in_n = t.valid && t.r2n < pot.cut_pre2;
+            t.any = in_o || in_n;
+            t.neg_r2o = __hiloint2double(__double2hiint(r2o) ^ (int)0x80000000, __double2loint(r2o));
+            t.ex_o = in_o && flo != 0u;
+            t.ex_n = in_n && fln != 0u;
+            return t;
+        } else {
         bool fo = false, fn = false;
         const double dxo = axis_nearest_any(po[0], xj, A0, fo);
         const double dyo = axis_nearest_any(po[1], yj, A1, fo);
@@ -311,6 +464,7 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
         t.ex_o = in_o && fo;
         t.ex_n = in_n && fn;
         return t;
+        }
     };
     auto file = [&](const Tile &t) {
         const unsigned b = __ballot_sync(FULL, t.any);
@@ -349,6 +503,31 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
             const bool has = item != NOITEM;
             const int j = has ? (int)(item & 0x7FFFu) : 0;
             const bool side = (item & 0x8000u) != 0u;  // false: old position, true: new position
+            if constexpr (CELL::TRI) {
+                double d0[3], sg[3];
+                unsigned fl, best;
+                C.nearest(R.x(j) - (side ? pn[0] : po[0]), R.y(j) - (side ? pn[1] : po[1]), R.z(j) - (side ? pn[2] : po[2]), d0, sg, fl, best);
+                unsigned c = 0u;  // every subset of the flagged axes (the empty one included) except the closest image, which has its slot
+                bool more = has && fl != 0u;
+                while (__any_sync(FULL, more)) {
+                    double d[3];
+                    C.shifted(d0, sg, c, d);
+                    const double r2 = fma(d[2], d[2], fma(d[1], d[1], d[0] * d[0]));
+                    const bool in = more && c != best && r2 < pot.cut_pre2;
+                    const unsigned b = __ballot_sync(FULL, in);
+                    const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
+                    if (in) {
+                        R.lr(pos) = side ? r2 : -r2;
+                        if (TRACK) R.xj(min(pos - xstart, RV::XCAPN - 1)) = (uint16_t)j;
+                    }
+                    cnt += __popc(b);
+                    if (more) {
+                        if (c == fl) more = false;
+                        else c = ((c | (~fl & 7u)) + 1u) & fl;
+                    }
+                }
+                continue;
+            } else {
             unsigned fl = 0;
             const double dx0 = axis_nearest(side ? pn[0] : po[0], R.x(j), A0, p0, fl, 1u);
             const double dy0 = axis_nearest(side ? pn[1] : po[1], R.y(j), A1, p1, fl, 2u);
@@ -371,6 +550,7 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
                     if (c == fl) more = false;
                     else c = ((c | (~fl & 7u)) + 1u) & fl;
                 }
+            }
             }
         }
     }

@@ -98,4 +98,30 @@ int CAT(energy_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, long long *pai
     return report(cudaGetLastError(), "energy kernel launch", err, errn);
 }
 
+// general (triclinic) cells (csrc/sweep_tri.cuh): the replica layout of the scan kernel plus the cell constants of every warp
+int CAT(sweep_tri_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, cudaStream_t s, char *err, size_t errn) {
+    using LY = Layout<INST_POT, INST_NS>;
+    constexpr int W = tri_warps<LY>();
+    constexpr size_t smem = (size_t)W * (LY::BYTES + TRI_CELL_DOUBLES * 8);
+    static_assert(smem <= SMEM_PER_CTA_MAX, "replicas and cell constants do not fit in shared memory");
+    auto kernel = sweep_tri_kernel<INST_POT, INST_NS>;
+    int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
+    if (rc) return rc;
+    const int grid = (a.b.n_replicas + W - 1) / W;
+    kernel<<<grid, W * 32, smem, s>>>(a);
+    return report(cudaGetLastError(), "general-cell sweep kernel launch", err, errn);
+}
+
+int CAT(energy_tri_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn) {
+    using LY = Layout<INST_POT, INST_NS>;
+    constexpr int W = tri_warps<LY>();
+    constexpr size_t smem = (size_t)W * (LY::BYTES + TRI_CELL_DOUBLES * 8);
+    auto kernel = energy_tri_kernel<INST_POT, INST_NS>;
+    int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
+    if (rc) return rc;
+    const int grid = (a.b.n_replicas + W - 1) / W;
+    kernel<<<grid, W * 32, smem, s>>>(a, pair_count);
+    return report(cudaGetLastError(), "general-cell energy kernel launch", err, errn);
+}
+
 }  // namespace qmc

@@ -80,6 +80,18 @@ class DeformationContext(DisplacementContext):
         self.batch.pressure = float(value)
 
     @property
+    def external_stress(self) -> np.ndarray:
+        """(3, 3) eV / A^3 (``mc/contexts.py`` DeformationContext.external_stress); read by the IsotensionCriteria."""
+        return self.batch.external_stress
+
+    @external_stress.setter
+    def external_stress(self, value) -> None:
+        v = np.asarray(value, dtype=np.float64)
+        if v.shape != (3, 3):
+            raise ValueError("external_stress must be a 3x3 array")
+        self.batch.external_stress = v.copy()
+
+    @property
     def last_cell(self) -> np.ndarray:
         return self.batch.cell.cpu().numpy().reshape(-1, 3, 3)
 

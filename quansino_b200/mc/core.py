@@ -147,7 +147,7 @@ class MonteCarlo:
     # -- lowering -----------------------------------------------------------------------------------
     _criteria_for: ClassVar[dict[int, tuple[str, ...]]] = {
         _lib.MOVE_DISPLACEMENT: ("CanonicalCriteria",),
-        _lib.MOVE_CELL: ("IsobaricCriteria",),
+        _lib.MOVE_CELL: ("IsobaricCriteria", "IsotensionCriteria"),
         _lib.MOVE_EXCHANGE: ("GrandCanonicalCriteria",),
         _lib.MOVE_HMC: ("HamiltonianCanonicalCriteria",),
     }
@@ -168,6 +168,18 @@ class MonteCarlo:
             or any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE and len(getattr(self.moves[n].move, "moves", ())) > 1 for n in names)
         )  # fmt: skip  (a CompositeExchangeMove gives the atoms of one insertion ONE label: groups, too)
         entries, keep, slots = [], [], {}
+        cell_criteria = {type(self.moves[n].criteria).__name__ for n in names if self.moves[n].move.move_type == _lib.MOVE_CELL}
+        if len(cell_criteria) > 1:
+            raise NotImplementedError("cell moves judged by different criteria in one step are not available on the GPU path")
+        # IsotensionCriteria lives in the general-cell kernels (csrc/sweep_tri.cuh), and so do the deformations that leave
+        # general cells behind; a batch that was switched to them stays there (its cells may be triclinic by now)
+        self.batch.isotension = cell_criteria == {"IsotensionCriteria"}
+        if self.batch.isotension or any(
+            getattr(getattr(self.moves[n].move, "operation", None), "op_code", -1) in (_lib.OP_ANISOTROPIC, _lib.OP_SHAPE) for n in names
+        ):
+            if not self.batch.triclinic:
+                self.batch.triclinic = True
+                self.batch.drop_rows()
         for n in names:
             st = self.moves[n]
             st.criteria._check_supported()

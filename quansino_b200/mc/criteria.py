@@ -6,6 +6,7 @@ reference's expressions:
 * ``CanonicalCriteria``            u < exp(-dE / (T kB))                                              (``:104-110``)
 * ``HamiltonianCanonicalCriteria`` u < exp(-((E_pot + E_kin) - last_pot - last_kin) / (T kB))         (``:131-140``)
 * ``IsobaricCriteria``             u < exp(-(dE + P (V' - V)) / (T kB) + (N + 1) ln(V' / V))          (``:160-172``)
+* ``IsotensionCriteria``           the same with P (V' - V) + V trace((stress - P) @ strain) as the work term           (``:196-213``)
 * ``GrandCanonicalCriteria``       u < exp((delta mu - dE) / (T kB)) V^delta F(N_ex, delta) Lambda^(-3 delta)  (``:240-278``)
 
 The classes below are the tags the drivers use to pick the kernel branch; user-defined criteria are Python
@@ -45,6 +46,10 @@ class HamiltonianCanonicalCriteria(BaseCriteria):
 
 class IsobaricCriteria(BaseCriteria):
     """NPT test."""
+
+
+class IsotensionCriteria(BaseCriteria):
+    """NST test (``mc/criteria.py:175-219``): strain = 0.5 (inv(old^T) @ new^T @ old @ inv(old) - 1) as the reference writes it."""
 
 
 class GrandCanonicalCriteria(BaseCriteria):

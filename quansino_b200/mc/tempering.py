@@ -54,16 +54,23 @@ def _dist():
 
 
 def gather_replicas(local: torch.Tensor, counts: list[int]) -> torch.Tensor:
-    """All-gather of per-replica values with (possibly) uneven shard sizes; every rank gets the global vector."""
+    """All-gather of per-replica values (``[count]`` or ``[count, k]``) with possibly uneven shard sizes; every rank gets the
+    global array.  ONE collective call on one flat buffer."""
     dist = _dist()
     if dist is None or dist.get_world_size() == 1:
         return local.clone()
     width = max(counts)  # collectives want equal sizes: pad every shard to the widest one
-    padded = torch.zeros(width, dtype=local.dtype, device=local.device)
-    padded[: local.numel()] = local
-    parts = [torch.empty(width, dtype=local.dtype, device=local.device) for _ in counts]
-    dist.all_gather(parts, padded)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+    tail = tuple(local.shape[1:])
+    if local.shape[0] == width:
+        padded = local.contiguous()
+    else:
+        padded = torch.zeros((width, *tail), dtype=local.dtype, device=local.device)
+        padded[: local.shape[0]] = local
+    out = torch.empty((len(counts) * width, *tail), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded)
+    if all(c == width for c in counts):
+        return out
+    return torch.cat([out[i * width : i * width + c] for i, c in enumerate(counts)])
 
 
 def device_swap(temperatures_all: torch.Tensor, energies_all: torch.Tensor, seed: int, round_index: int) -> torch.Tensor:
@@ -110,8 +117,9 @@ class ReplicaExchange:
 
     def exchange(self) -> torch.Tensor:
         """One swap round (even pairs on even rounds, odd pairs on odd rounds); returns the accepted flags (global)."""
-        e_all = gather_replicas(self.energies, self.counts)
-        t_all = gather_replicas(self.temperatures, self.counts)
+        # energies and temperatures travel together: one latency-bound collective per round instead of two
+        both = gather_replicas(torch.stack((self.energies, self.temperatures), dim=1), self.counts)
+        e_all, t_all = both[:, 0].contiguous(), both[:, 1].contiguous()
         accepted = self.swap(t_all, e_all, self.seed, self.round)
         self.temperatures.copy_(t_all[self.offset : self.offset + self.counts[self.rank]])
         n = t_all.numel()

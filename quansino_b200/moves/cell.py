@@ -27,10 +27,10 @@ class CellMove(BaseMove):
         m = _lib.Move()
         m.type = self.move_type
         m.op, m.step = self.operation.lower()
-        if m.op != _lib.OP_ISOTROPIC:
+        if m.op not in (_lib.OP_ISOTROPIC, _lib.OP_ANISOTROPIC, _lib.OP_SHAPE):
             raise NotImplementedError(f"{type(self.operation).__name__} is not a cell operation of the GPU path")
         m.default_label = _lib.LABEL_NONE
-        m.axes = self.operation.axes  # the diagonal of IsotropicDeformation.mask
+        m.axes = self.operation.axes  # IsotropicDeformation: the diagonal of the mask; Anisotropic / Shape: all nine bits
         return m
 
     def to_dict(self):

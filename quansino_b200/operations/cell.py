@@ -38,9 +38,31 @@ class IsotropicDeformation(DeformationOperation):
         return super().lower()
 
 
-class AnisotropicDeformation(DeformationOperation):
-    """Not available on the GPU path (needs expm and triclinic cells)."""
+class _ExpmDeformation(DeformationOperation):
+    """F = expm(T) * mask + eye * ~mask with a symmetric T of six U(-max_value, max_value) components."""
+
+    @property
+    def axes(self) -> int:
+        """The 3 x 3 mask as bits 3 i + j (``qmc_move_t.axes`` for these operations)."""
+        m = np.asarray(self.mask, dtype=bool)
+        return int(sum(int(m[i, j]) << (3 * i + j) for i in range(3) for j in range(3)))
+
+    def lower(self):
+        if np.asarray(self.mask).shape != (3, 3):
+            raise ValueError("mask must be a 3x3 boolean array")
+        if self.axes == 0:
+            raise NotImplementedError("a mask without any deformed component describes no move")
+        return super().lower()
 
 
-class ShapeDeformation(DeformationOperation):
-    """Not available on the GPU path."""
+class AnisotropicDeformation(_ExpmDeformation):
+    """``operations/cell.py:56-96``: T = [[c0, c3, c4], [c3, c1, c5], [c4, c5, c2]], c = U(-max_value, max_value, 6); the cell
+    becomes triclinic (general-cell kernels, ``csrc/sweep_tri.cuh``)."""
+
+    op_code = _lib.OP_ANISOTROPIC
+
+
+class ShapeDeformation(_ExpmDeformation):
+    """``operations/cell.py:99-141``: the same with the mean of the diagonal removed (trace 0: volume preserving)."""
+
+    op_code = _lib.OP_SHAPE

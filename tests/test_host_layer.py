@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in sorted(declared):
         assert getattr(lib, name) is not None, name
-    assert lib.qmc_abi_version() == int(re.search(r"#define\s+QMC_ABI_VERSION\s+(\d+)", header).group(1)) == 8
+    assert lib.qmc_abi_version() == int(re.search(r"#define\s+QMC_ABI_VERSION\s+(\d+)", header).group(1)) == 9
 
 
 def test_struct_layouts_match_the_header():
@@ -202,13 +202,19 @@ def test_label_validation():
 def test_cell_checks():
     from quansino_b200.batch import _check_cell
 
-    _check_cell(np.diag([10.83, 10.83, 10.83])[None], (True,) * 3, 5.8768)
+    assert _check_cell(np.diag([10.83, 10.83, 10.83])[None], (True,) * 3, 5.8768) is False
     with pytest.raises(NotImplementedError):
         _check_cell(np.diag([3.61, 3.61, 3.61])[None], (True,) * 3, 5.8768)  # the reference's 4-atom fixture
-    _check_cell(np.diag([3.61, 3.61, 3.61])[None], (False,) * 3, 5.8768)
+    assert _check_cell(np.diag([3.61, 3.61, 3.61])[None], (False,) * 3, 5.8768) is False
+    # general cells: allowed (-> the general-cell kernels) as long as every periodic HEIGHT clears the cutoff
     tri = np.array([[10.0, 0, 0], [1.0, 10.0, 0], [0, 0, 10.0]])[None]
-    with pytest.raises(NotImplementedError):
-        _check_cell(tri, (True,) * 3, 5.0)
+    assert _check_cell(tri, (True,) * 3, 5.0) is True
+    flat = np.array([[10.0, 0, 0], [9.0, 5.2, 0], [0, 0, 10.0]])[None]  # edges of 10 A, but a height of 5.2 * 10 / |(9, 5.2)| = 5.0 A
+    with pytest.raises(NotImplementedError, match="height"):
+        _check_cell(flat, (True,) * 3, 5.1)
+    assert _check_cell(flat, (False, False, True), 5.1) is True
+    with pytest.raises(ValueError):
+        _check_cell(np.zeros((1, 3, 3)), (True,) * 3, 5.0)
 
 
 def test_shard_is_a_partition():

@@ -206,3 +206,19 @@ def test_candidate_list_is_bit_identical_to_brute_force(monkeypatch):
     monkeypatch.delenv("QO_NO_PAIRLIST")
     slab_fast = capi.energy(par, pos[0], cell, (1, 1, 0), want_forces=True)
     assert slab["energy"] == slab_fast["energy"] and np.array_equal(slab["forces"], slab_fast["forces"])
+
+
+def test_expm_of_symmetric_matrices_matches_scipy():
+    """The deformation gradient of Anisotropic / ShapeDeformation is ``scipy.linalg.expm`` of a symmetric matrix
+    (``operations/cell.py:96,141``); the oracle diagonalises by Jacobi rotations instead of scipy's Pade approximants."""
+    from scipy.linalg import expm
+
+    rng = np.random.default_rng(17)
+    for scale in (1e-4, 0.01, 0.1, 1.0):
+        for _ in range(20):
+            c = rng.uniform(-scale, scale, 6)
+            t = np.array([[c[0], c[3], c[4]], [c[3], c[1], c[5]], [c[4], c[5], c[2]]])
+            np.testing.assert_allclose(capi.expm_sym3(t), expm(t), rtol=0, atol=2e-15 * max(1.0, float(np.exp(3 * scale))))
+    np.testing.assert_array_equal(capi.expm_sym3(np.zeros((3, 3))), np.eye(3))
+    d = np.diag([0.3, -0.2, 0.1])
+    np.testing.assert_allclose(capi.expm_sym3(d), np.diag(np.exp([0.3, -0.2, 0.1])), rtol=0, atol=1e-16)
