@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Secondary measurements: the other configurations of BASELINE.json (C3 isobaric, C4 grand-canonical LJ, C5 HMC) on one
-GPU.  Not part of the bench.py contract; results are recorded under profiles/.  Usage: python bench_configs.py [c3|c4|c5|c5pt|composite|fbmc] ... (c5pt also under torchrun)"""
+GPU.  Not part of the bench.py contract; results are recorded under profiles/.  Usage: python bench_configs.py [c3|c4|c5|c5pt|composite|fbmc|tri] ... (c5pt also under torchrun)"""
 
 from __future__ import annotations
 
@@ -231,6 +231,34 @@ def composite(R=4096, k=4, steps=20):
             "ms_per_step": 1e3 * t / steps, "acceptance": float(c[:, 0, 1].sum() / c[:, 0, 0].sum())}  # fmt: skip
 
 
+def tri(R=4096, steps=5):
+    """General (triclinic) cells (csrc/sweep_tri.cuh): the C2 workload in a sheared cell (canonical displacement sweeps), the same
+    batch in the diagonal cell for comparison, and NST sweeps with AnisotropicDeformation under IsotensionCriteria."""
+    from quansino_b200.mc import Canonical, Isotension
+    from quansino_b200.operations import AnisotropicDeformation
+
+    pos0, cell0 = fcc_cubic("Cu", 3)
+    n = len(pos0)
+    rng = np.random.default_rng(11)
+    shear = np.array([[1.0, 0.0, 0.0], [0.08, 1.0, 0.0], [-0.05, 0.06, 1.0]])
+    frac = np.linalg.solve(cell0.T, (pos0[None] + rng.normal(scale=0.05, size=(R, n, 3))).reshape(-1, 3).T).T.reshape(R, n, 3)
+    out = {"config": f"general-cell kernels, {R} replicas x {n}-atom Cu EMT, 300 K"}
+    for name, cell in (("diagonal_cell_scan_kernel", cell0), ("sheared_cell", shear @ cell0)):
+        atoms = BatchedAtoms(frac @ cell, cell, np.full(R, n, np.int32), "Cu", (True,) * 3, EMT())
+        mc = Canonical(atoms, temperature=300.0, seed=12, resync_interval=0, default_displacement_move=DisplacementMove(np.arange(n), Ball(0.1)))
+        t, pairs = timed(mc, steps, 2)
+        out[name] = {"attempts_per_s": R * n * steps / t, "pair_evals_per_s": pairs / t, "ms_per_sweep": 1e3 * t / steps,
+                     "acceptance": float(mc.counters()[:, 0, 1].sum() / mc.counters()[:, 0, 0].sum())}  # fmt: skip
+    atoms = BatchedAtoms(frac @ cell0, cell0, np.full(R, n, np.int32), "Cu", (True,) * 3, EMT())
+    mc = Isotension(atoms, temperature=300.0, pressure=1.0 * BAR, external_stress=np.diag([1e-3, -1e-3, 0.0]), seed=13, resync_interval=0,
+                    default_displacement_move=DisplacementMove(np.arange(n), Ball(0.1)), default_cell_move=CellMove(AnisotropicDeformation(0.005)))  # fmt: skip
+    t, pairs = timed(mc, steps, 2)
+    c = mc.counters()
+    out["nst_anisotropic"] = {"attempts_per_s": R * n * steps / t, "pair_evals_per_s": pairs / t, "ms_per_step": 1e3 * t / steps,
+                              "cell_moves": int(c[:, 1, 0].sum()), "cell_accepted": int(c[:, 1, 1].sum())}  # fmt: skip
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c3", "c4", "c5"]
     for w in which:
@@ -239,6 +267,6 @@ if __name__ == "__main__":
         elif w.startswith("c5r"):  # c5r8: the share of one GPU when C5's 64 temperatures are spread over 8 GPUs
             print(json.dumps(c5(R=int(w[3:]), attempts=4)), flush=True)
         else:
-            res = {"c3": c3, "c4": c4, "c5": c5, "c5pt": c5pt, "composite": composite, "fbmc": fbmc}[w]()
+            res = {"c3": c3, "c4": c4, "c5": c5, "c5pt": c5pt, "composite": composite, "fbmc": fbmc, "tri": tri}[w]()
             if res is not None:
                 print(json.dumps(res), flush=True)
