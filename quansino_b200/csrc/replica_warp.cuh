@@ -149,32 +149,33 @@ struct CellView {
 };
 
 // General (triclinic) cell of one replica, constants in shared memory (csrc/sweep_tri.cuh: store_cell_tri):
-//   s[0..8]   H, row k = cell vector a_k (positions = fractional @ H)
-//   s[9..17]  H^-1 (fractional_k = sum_x d_x * s[9 + 3 x + k]); the column of a non-periodic axis is zero
-//   s[18..20] thr_k = 1 - cutoff' / w_k (w_k = height of the cell along axis k), 1e300 for a non-periodic axis
+//   h[0..8]   H, row k = cell vector a_k (positions = fractional @ H)
+//   t[0..8]   H^-1 (fractional_k = sum_x d_x * t[3 x + k]); the column of a non-periodic axis is zero
+//   t[9..11]  thr_k = 1 - cutoff' / w_k (w_k = height of the cell along axis k), 1e300 for a non-periodic axis
 // Image rule: with every periodic height w_k >= cutoff', an image of j inside the cutoff has fractional components |f_k| <=
 // cutoff' / w_k <= 1 (f_k = r . b_k, |b_k| = 1 / w_k), so with fr = f - rint(f) the candidates are fr_k and, where |fr_k| > thr_k,
 // fr_k - sign(fr_k): at most 2 x 2 x 2 images, the same subset enumeration as for diagonal cells -- but the image found by rounding
 // is NOT always the closest one, so the second images are looked at whether or not the first one is inside the cutoff.
 struct TriView {
     static constexpr bool TRI = true;
-    const double *s;
-    __device__ __forceinline__ bool per(int k) const { return s[18 + k] < 1e299; }
+    const double *h;  // H[9]
+    const double *t;  // H^-1[9], thr[3]
+    __device__ __forceinline__ bool per(int k) const { return t[9 + k] < 1e299; }
     // image of d = xj - xi found by rounding the fractional coordinates; sg[k] = sign of the reduced fractional coordinate;
     // returns bit k set if the image shifted by -sg[k] a_k can be inside the cutoff as well
     __device__ __forceinline__ unsigned reduce(double dx, double dy, double dz, double d0[3], double sg[3]) const {
-        const double f0 = fma(dz, s[15], fma(dy, s[12], dx * s[9]));
-        const double f1 = fma(dz, s[16], fma(dy, s[13], dx * s[10]));
-        const double f2 = fma(dz, s[17], fma(dy, s[14], dx * s[11]));
+        const double f0 = fma(dz, t[6], fma(dy, t[3], dx * t[0]));
+        const double f1 = fma(dz, t[7], fma(dy, t[4], dx * t[1]));
+        const double f2 = fma(dz, t[8], fma(dy, t[5], dx * t[2]));
         const double k0 = (f0 + RINT_MAGIC) - RINT_MAGIC, k1 = (f1 + RINT_MAGIC) - RINT_MAGIC, k2 = (f2 + RINT_MAGIC) - RINT_MAGIC;
-        d0[0] = fma(-k2, s[6], fma(-k1, s[3], fma(-k0, s[0], dx)));
-        d0[1] = fma(-k2, s[7], fma(-k1, s[4], fma(-k0, s[1], dy)));
-        d0[2] = fma(-k2, s[8], fma(-k1, s[5], fma(-k0, s[2], dz)));
+        d0[0] = fma(-k2, h[6], fma(-k1, h[3], fma(-k0, h[0], dx)));
+        d0[1] = fma(-k2, h[7], fma(-k1, h[4], fma(-k0, h[1], dy)));
+        d0[2] = fma(-k2, h[8], fma(-k1, h[5], fma(-k0, h[2], dz)));
         const double r0 = f0 - k0, r1 = f1 - k1, r2 = f2 - k2;
         sg[0] = copysign(1.0, r0);
         sg[1] = copysign(1.0, r1);
         sg[2] = copysign(1.0, r2);
-        return (fabs(r0) > s[18] ? 1u : 0u) | (fabs(r1) > s[19] ? 2u : 0u) | (fabs(r2) > s[20] ? 4u : 0u);
+        return (fabs(r0) > t[9] ? 1u : 0u) | (fabs(r1) > t[10] ? 2u : 0u) | (fabs(r2) > t[11] ? 4u : 0u);
     }
     // r^2 of the CLOSEST image among the candidates (subset `best` of the flagged axes `fl`): flagged lanes walk their <= 8 subsets
     __device__ __forceinline__ double nearest(double dx, double dy, double dz, double d0[3], double sg[3], unsigned &fl, unsigned &best) const {
@@ -200,9 +201,9 @@ struct TriView {
     // the image of subset c (bit k: shifted by -sg[k] a_k)
     __device__ __forceinline__ void shifted(const double d0[3], const double sg[3], unsigned c, double d[3]) const {
         const double m0 = (c & 1u) ? sg[0] : 0.0, m1 = (c & 2u) ? sg[1] : 0.0, m2 = (c & 4u) ? sg[2] : 0.0;
-        d[0] = fma(-m2, s[6], fma(-m1, s[3], fma(-m0, s[0], d0[0])));
-        d[1] = fma(-m2, s[7], fma(-m1, s[4], fma(-m0, s[1], d0[1])));
-        d[2] = fma(-m2, s[8], fma(-m1, s[5], fma(-m0, s[2], d0[2])));
+        d[0] = fma(-m2, h[6], fma(-m1, h[3], fma(-m0, h[0], d0[0])));
+        d[1] = fma(-m2, h[7], fma(-m1, h[4], fma(-m0, h[1], d0[1])));
+        d[2] = fma(-m2, h[8], fma(-m1, h[5], fma(-m0, h[2], d0[2])));
     }
 };
 

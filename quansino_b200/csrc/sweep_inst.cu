@@ -102,7 +102,7 @@ int CAT(energy_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, long long *pai
 int CAT(sweep_tri_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, cudaStream_t s, char *err, size_t errn) {
     using LY = Layout<INST_POT, INST_NS>;
     constexpr int W = tri_warps<LY>();
-    constexpr size_t smem = (size_t)W * (LY::BYTES + TRI_CELL_DOUBLES * 8);
+    constexpr size_t smem = tri_smem<LY>();
     static_assert(smem <= SMEM_PER_CTA_MAX, "replicas and cell constants do not fit in shared memory");
     auto kernel = sweep_tri_kernel<INST_POT, INST_NS>;
     int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
@@ -115,7 +115,7 @@ int CAT(sweep_tri_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, cudaStream_
 int CAT(energy_tri_launch_, INST_POT, _, INST_NS)(const SweepArgs &a, long long *pair_count, cudaStream_t s, char *err, size_t errn) {
     using LY = Layout<INST_POT, INST_NS>;
     constexpr int W = tri_warps<LY>();
-    constexpr size_t smem = (size_t)W * (LY::BYTES + TRI_CELL_DOUBLES * 8);
+    constexpr size_t smem = tri_smem<LY>();
     auto kernel = energy_tri_kernel<INST_POT, INST_NS>;
     int rc = report(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute", err, errn);
     if (rc) return rc;

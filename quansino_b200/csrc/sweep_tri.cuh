@@ -14,14 +14,35 @@
 
 namespace qmc {
 
-constexpr int TRI_CELL_DOUBLES = 24;  // H[9], H^-1[9], thr[3], padding
+constexpr int TRI_T_DOUBLES = 12;  // H^-1[9], thr[3]; H[9] sits where the diagonal kernels keep their cell constants (LY::CELLC)
 
-// warps (= replicas) per CTA: the scan kernel's layouts fill the SM exactly, the cell constants of every warp need 192 bytes more
+// The general-cell kernels run no composite, forced or label-bitmap code: those regions of the replica layout (from DISP_B to the
+// end) hold H^-1 and the thresholds, so that the kernels keep the scan kernel's geometry (28 replicas per SM for 108 atoms --
+// with 27, 4096 replicas need a second wave of 4 CTAs that doubles the launch time).  Layouts without room put them behind the
+// replicas and give up warps.
+template <class LY>
+__host__ __device__ constexpr bool tri_inplace() {
+    return LY::BYTES - LY::DISP_B >= TRI_T_DOUBLES * 8 && LY::DISP_B % 8 == 0;
+}
+
 template <class LY>
 __host__ __device__ constexpr int tri_warps() {
     int w = LY::WARPS;
-    while (w > 1 && w * (LY::BYTES + TRI_CELL_DOUBLES * 8) > SMEM_PER_CTA_MAX) --w;
+    if constexpr (!tri_inplace<LY>())
+        while (w > 1 && w * (LY::BYTES + TRI_T_DOUBLES * 8) > SMEM_PER_CTA_MAX) --w;
     return w;
+}
+
+template <class LY>
+__host__ __device__ constexpr size_t tri_smem() {
+    return (size_t)tri_warps<LY>() * (LY::BYTES + (tri_inplace<LY>() ? 0 : TRI_T_DOUBLES * 8));
+}
+
+// shared-memory homes of the cell constants of warp `warp`
+template <class LY>
+__device__ __forceinline__ double *tri_t_ptr(double *smem_d, double *rb, int warp) {
+    if (tri_inplace<LY>()) return reinterpret_cast<double *>(reinterpret_cast<char *>(rb) + LY::DISP_B);
+    return smem_d + tri_warps<LY>() * (LY::BYTES / 8) + warp * TRI_T_DOUBLES;
 }
 
 __host__ __device__ inline double det3(const double h[9]) {
@@ -85,7 +106,8 @@ __host__ __device__ inline void expm3(const double A[9], double E[9]) {
 }
 
 // cell constants of one replica into shared memory (TriView); false if a periodic height is below the cutoff
-__device__ inline bool store_cell_tri(double *s, const double H[9], const int pbc[3], double cut_pre, int lane) {
+__device__ inline bool store_cell_tri(const TriView &V, const double H[9], const int pbc[3], double cut_pre, int lane) {
+    double *h = const_cast<double *>(V.h), *t = const_cast<double *>(V.t);
     double inv[9], w[3];
     inv3(H, inv);
     cell_heights(H, w);
@@ -96,13 +118,13 @@ __device__ inline bool store_cell_tri(double *s, const double H[9], const int pb
     __syncwarp();
     if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < 9; ++q) s[q] = H[q];
+        for (int q = 0; q < 9; ++q) h[q] = H[q];
 #pragma unroll
         for (int x = 0; x < 3; ++x)
 #pragma unroll
-            for (int k = 0; k < 3; ++k) s[9 + 3 * x + k] = pbc[k] ? inv[3 * x + k] : 0.0;
+            for (int k = 0; k < 3; ++k) t[3 * x + k] = pbc[k] ? inv[3 * x + k] : 0.0;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) s[18 + k] = pbc[k] ? 1.0 - cut_pre / w[k] - 1e-9 : 1e300;  // (the margin only adds candidates)
+        for (int k = 0; k < 3; ++k) t[9 + k] = pbc[k] ? 1.0 - cut_pre / w[k] - 1e-9 : 1e300;  // (the margin only adds candidates)
     }
     __syncwarp();
     return ok;
@@ -131,6 +153,110 @@ __device__ inline void deformation_gradient(int op, double step, int mask, const
     for (int q = 0; q < 9; ++q) F[q] = ((mask >> q) & 1) ? E[q] : ((q % 4 == 0) ? 1.0 : 0.0);  // expm(T) * mask + eye * ~mask
 }
 
+// One cell move of one replica (moves/cell.py:77-91, operations/cell.py:67-169, mc/criteria.py:160-219).  Kept out of line: its
+// 3 x 3 temporaries would otherwise weigh on the registers of the displacement path.  The last accepted cell is read from the
+// replica's constants in shared memory; an accepted cell is written through to global memory at once.
+template <int POT, int NS>
+__device__ __noinline__ bool cell_move_tri(const SweepArgs &a, const Rep<Layout<POT, NS>> &R, const TriView &C, const MoveDev &mv, const Draws &D,
+                                           unsigned long long attempt, int r, int lane, double &E, double &delta, long long &n_pairs,
+                                           int &status) {
+    using LY = Layout<POT, NS>;
+    const PotDev &pot = a.pot;
+    const int nmax = a.b.n_max;
+    const double kT = a.b.temperature[r] * KB;
+    const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
+    const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
+    double *gx = a.b.pos + (size_t)r * 3 * nmax, *gy = gx + nmax, *gz = gy + nmax;
+    double *gs = POT == QMC_POT_EMT ? a.b.sigma1 + (size_t)r * nmax : nullptr;
+    double *ge = POT == QMC_POT_EMT ? a.b.eatom + (size_t)r * nmax : nullptr;
+    double H[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) H[q] = C.h[q];
+    __syncwarp();
+    // moves/cell.py:77-91: cell' = F @ cell, positions' = positions @ solve(cell, cell') (Atoms.set_cell(scale_atoms=True));
+    // snapshot the last accepted state in global memory, deform in place, recompute everything
+    for (int j = lane; j < R.n; j += 32) {
+        gx[j] = R.x(j);
+        gy[j] = R.y(j);
+        gz[j] = R.z(j);
+        if (POT == QMC_POT_EMT) {
+            gs[j] = R.sig(j);
+            ge[j] = R.eat(j);
+        }
+    }
+    double u[6] = {D.o0, D.o1, D.o2, 0.0, 0.0, 0.0};
+    if (mv.op != QMC_OP_ISOTROPIC) {  // components 3..5: the attempt's extra draws 0..2
+        double e2, e3;
+        uniform_pair(key, attempt, grep, 64u, u[3], u[4]);
+        uniform_pair(key, attempt, grep, 65u, e2, e3);
+        u[5] = e2;
+    }
+    double F[9], N[9], inv[9], M[9];
+    deformation_gradient(mv.op, mv.step, mv.axes, u, F);
+    matmul3(F, H, N);
+    inv3(H, inv);
+    matmul3(inv, N, M);
+    for (int j = lane; j < R.n; j += 32) {
+        const double x = R.x(j), y = R.y(j), z = R.z(j);
+        R.x(j) = (x * M[0] + y * M[3]) + z * M[6];
+        R.y(j) = (x * M[1] + y * M[4]) + z * M[7];
+        R.z(j) = (x * M[2] + y * M[5]) + z * M[8];
+    }
+    __syncwarp();
+    const bool cell_ok = store_cell_tri(C, N, a.b.pbc, pot.cut_pre, lane);
+    if (!cell_ok) status |= QMC_STATUS_CELL_TOO_SMALL;
+    long long fp = 0;
+    const double e_new = cell_ok ? replica_full_energy<LY>(pot, R, C, lane, fp, status) : E;
+    n_pairs += fp;
+    delta = e_new - E;
+    const double v_new = fabs(det3(N)), v_old = fabs(det3(H));
+    double work = a.b.pressure * (v_new - v_old);
+    if (a.b.isotension) {
+        // IsotensionCriteria (mc/criteria.py:196-213), literally: strain = 0.5 (inv(old^T) @ new^T @ old @ inv(old) - 1),
+        // elastic = p dV + V_old trace((stress - p) @ strain) with the SCALAR p subtracted from every component
+        double HT[9], NT[9], iHT[9], P[9], Q[9], S[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            HT[q] = H[3 * (q % 3) + q / 3];
+            NT[q] = N[3 * (q % 3) + q / 3];
+        }
+        inv3(HT, iHT);
+        matmul3(iHT, NT, P);
+        matmul3(P, H, Q);
+        matmul3(Q, inv, S);
+        double tr = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const double strain_ji = 0.5 * (S[3 * j + i] - (i == j ? 1.0 : 0.0));
+                tr += (a.b.external_stress[3 * i + j] - a.b.pressure) * strain_ji;
+            }
+        work += v_old * tr;
+    }
+    const double x = -(delta + work) / kT + (double)(R.n + 1) * log(v_new / v_old);
+    const bool acc = cell_ok && metropolis(D.u_accept, x, status);
+    if (acc) {
+        E = e_new;
+        if (lane == 0)
+#pragma unroll
+            for (int q = 0; q < 9; ++q) a.b.cell[(size_t)r * 9 + q] = N[q];
+    } else {
+        for (int j = lane; j < R.n; j += 32) {
+            R.x(j) = gx[j];
+            R.y(j) = gy[j];
+            R.z(j) = gz[j];
+            if (POT == QMC_POT_EMT) {
+                R.sig(j) = gs[j];
+                R.eat(j) = ge[j];
+            }
+        }
+        store_cell_tri(C, H, a.b.pbc, pot.cut_pre, lane);
+    }
+    __syncwarp();
+    return acc;
+}
+
 template <int POT, int NS>
 __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_kernel(const __grid_constant__ SweepArgs a) {
     using LY = Layout<POT, NS>;
@@ -142,8 +268,7 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_k
     const int nmax = a.b.n_max;
     Rep<LY> R;
     R.b = smem_d + warp * (LY::BYTES / 8);
-    double *cs = smem_d + WARPS * (LY::BYTES / 8) + warp * TRI_CELL_DOUBLES;
-    const TriView C{cs};
+    const TriView C{R.b + LY::CELLC, tri_t_ptr<LY>(smem_d, R.b, warp)};
     const int r = blockIdx.x * WARPS + warp;
     if (r >= a.b.n_replicas) return;
     R.n = __ldcg(a.b.n_atoms + r);
@@ -161,10 +286,12 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_k
         }
     }
     int status = 0;
-    double H[9];
+    {
+        double H[9];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) H[q] = __ldcg(a.b.cell + (size_t)r * 9 + q);
-    if (!store_cell_tri(cs, H, a.b.pbc, pot.cut_pre, lane)) status |= QMC_STATUS_CELL_TOO_SMALL;
+        for (int q = 0; q < 9; ++q) H[q] = __ldcg(a.b.cell + (size_t)r * 9 + q);
+        if (!store_cell_tri(C, H, a.b.pbc, pot.cut_pre, lane)) status |= QMC_STATUS_CELL_TOO_SMALL;
+    }
     double E = __ldcg(a.b.energy + r);
     const double kT = a.b.temperature[r] * KB;
     const double inv_kT = 1.0 / kT;
@@ -172,7 +299,6 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_k
     const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
     const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
     long long n_pairs = 0;
-    bool cell_changed = false;
     __syncwarp();
 
     for (int k = 0; k < a.n_attempts; ++k) {
@@ -218,88 +344,7 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_k
                 moved = i;
             }
         } else if (mv.type == QMC_MOVE_CELL) {
-            // moves/cell.py:77-91: cell' = F @ cell, positions' = positions @ solve(cell, cell') (Atoms.set_cell(scale_atoms=True));
-            // snapshot the last accepted state in global memory, deform in place, recompute everything
-            for (int j = lane; j < R.n; j += 32) {
-                gx[j] = R.x(j);
-                gy[j] = R.y(j);
-                gz[j] = R.z(j);
-                if (POT == QMC_POT_EMT) {
-                    gs[j] = R.sig(j);
-                    ge[j] = R.eat(j);
-                }
-            }
-            double u[6] = {D.o0, D.o1, D.o2, 0.0, 0.0, 0.0};
-            if (mv.op != QMC_OP_ISOTROPIC) {  // components 3..5: the attempt's extra draws 0..2
-                double e2, e3;
-                uniform_pair(key, attempt, grep, 64u, u[3], u[4]);
-                uniform_pair(key, attempt, grep, 65u, e2, e3);
-                u[5] = e2;
-            }
-            double F[9], N[9], inv[9], M[9];
-            deformation_gradient(mv.op, mv.step, mv.axes, u, F);
-            matmul3(F, H, N);
-            inv3(H, inv);
-            matmul3(inv, N, M);
-            for (int j = lane; j < R.n; j += 32) {
-                const double x = R.x(j), y = R.y(j), z = R.z(j);
-                R.x(j) = (x * M[0] + y * M[3]) + z * M[6];
-                R.y(j) = (x * M[1] + y * M[4]) + z * M[7];
-                R.z(j) = (x * M[2] + y * M[5]) + z * M[8];
-            }
-            __syncwarp();
-            const bool cell_ok = store_cell_tri(cs, N, a.b.pbc, pot.cut_pre, lane);
-            if (!cell_ok) status |= QMC_STATUS_CELL_TOO_SMALL;
-            long long fp = 0;
-            const double e_new = cell_ok ? replica_full_energy<LY>(pot, R, C, lane, fp, status) : E;
-            n_pairs += fp;
-            delta = e_new - E;
-            const double v_new = fabs(det3(N)), v_old = fabs(det3(H));
-            double work = a.b.pressure * (v_new - v_old);
-            if (a.b.isotension) {
-                // IsotensionCriteria (mc/criteria.py:196-213), literally: strain = 0.5 (inv(old^T) @ new^T @ old @ inv(old) - 1),
-                // elastic = p dV + V_old trace((stress - p) @ strain) with the SCALAR p subtracted from every component
-                double HT[9], NT[9], iHT[9], P[9], Q[9], S[9];
-#pragma unroll
-                for (int q = 0; q < 9; ++q) {
-                    HT[q] = H[3 * (q % 3) + q / 3];
-                    NT[q] = N[3 * (q % 3) + q / 3];
-                }
-                inv3(HT, iHT);
-                matmul3(iHT, NT, P);
-                matmul3(P, H, Q);
-                matmul3(Q, inv, S);
-                double tr = 0.0;
-#pragma unroll
-                for (int i = 0; i < 3; ++i)
-#pragma unroll
-                    for (int j = 0; j < 3; ++j) {
-                        const double strain_ji = 0.5 * (S[3 * j + i] - (i == j ? 1.0 : 0.0));
-                        tr += (a.b.external_stress[3 * i + j] - a.b.pressure) * strain_ji;
-                    }
-                work += v_old * tr;
-            }
-            const double x = -(delta + work) / kT + (double)(R.n + 1) * log(v_new / v_old);
-            const bool acc = cell_ok && metropolis(D.u_accept, x, status);
-            if (acc) {
-                E = e_new;
-#pragma unroll
-                for (int q = 0; q < 9; ++q) H[q] = N[q];
-                cell_changed = true;
-            } else {
-                for (int j = lane; j < R.n; j += 32) {
-                    R.x(j) = gx[j];
-                    R.y(j) = gy[j];
-                    R.z(j) = gz[j];
-                    if (POT == QMC_POT_EMT) {
-                        R.sig(j) = gs[j];
-                        R.eat(j) = ge[j];
-                    }
-                }
-                store_cell_tri(cs, H, a.b.pbc, pot.cut_pre, lane);
-            }
-            __syncwarp();
-            accepted = acc ? 1 : 0;
+            accepted = cell_move_tri<POT, NS>(a, R, C, mv, D, attempt, r, lane, E, delta, n_pairs, status) ? 1 : 0;
         }  // (the host admits no other move types for general cells)
 
         if (lane == 0) {
@@ -334,8 +379,6 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_k
     }
     if (lane == 0) {
         a.b.energy[r] = E;
-        if (cell_changed)
-            for (int q = 0; q < 9; ++q) a.b.cell[(size_t)r * 9 + q] = H[q];
         if (status) atomicOr(a.b.status + r, status);
     }
     if (a.b.pair_evals) {
@@ -356,8 +399,7 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) energy_tri_
     const int nmax = a.b.n_max;
     Rep<LY> R;
     R.b = smem_d + warp * (LY::BYTES / 8);
-    double *cs = smem_d + WARPS * (LY::BYTES / 8) + warp * TRI_CELL_DOUBLES;
-    const TriView C{cs};
+    const TriView C{R.b + LY::CELLC, tri_t_ptr<LY>(smem_d, R.b, warp)};
     R.n = a.b.n_atoms[r];
     const double *gx = a.b.pos + (size_t)r * 3 * nmax, *gy = gx + nmax, *gz = gy + nmax;
     for (int j = lane; j < nmax; j += 32) {
@@ -369,7 +411,7 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) energy_tri_
     double H[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) H[q] = a.b.cell[(size_t)r * 9 + q];
-    const bool ok = store_cell_tri(cs, H, a.b.pbc, a.pot.cut_pre, lane);
+    const bool ok = store_cell_tri(C, H, a.b.pbc, a.pot.cut_pre, lane);
     long long pairs = 0;
     int status = 0;
     const double E = ok ? replica_full_energy<LY>(a.pot, R, C, lane, pairs, status, a.atom_energies ? a.atom_energies + (size_t)r * nmax : nullptr)
