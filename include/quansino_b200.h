@@ -19,7 +19,7 @@
  *  - replicas are independent; replica r of this batch is GLOBAL replica `replica_offset + r` for the
  *    random stream, so results do not depend on how replicas are sharded over GPUs.
  *  - cells are orthorhombic (diagonal), each periodic edge >= the neighbour cutoff; general (triclinic) cells run through the
- *    general-cell kernels (qmc_batch_t.triclinic) with displacement and cell moves only.
+ *    general-cell kernels (qmc_batch_t.triclinic) with displacement, plain exchange and cell moves only.
  *
  * Random stream (shared with the oracle, DESIGN.md "Random stream"): Philox4x32-10,
  * key = seed, counter = (attempt_lo, attempt_hi, global_replica, block); block 0 = (u_select, u_label),
@@ -182,8 +182,9 @@ typedef struct qmc_batch {
     int32_t _pad2;
     double exchange_mol[24];
     /* General (triclinic) cells.  triclinic != 0: `cell` holds full 3 x 3 matrices (rows = cell vectors) and qmc_sweep /
-     * qmc_energy_full / qmc_atom_energies run the general-cell kernels (csrc/sweep_tri.cuh): single-atom displacement moves and
-     * cell moves (all three deformation operations); every periodic HEIGHT of the cell must be >= the neighbour cutoff.
+     * qmc_energy_full / qmc_atom_energies run the general-cell kernels (csrc/sweep_tri.cuh): single-atom displacement moves,
+     * single-atom exchange moves placed by Translation, and cell moves (all three deformation operations); every periodic HEIGHT
+     * of the cell must be >= the neighbour cutoff.
      * isotension != 0: cell moves are judged by IsotensionCriteria (mc/criteria.py:175-219) with `external_stress` (eV / A^3,
      * row-major 3 x 3) and `pressure`; otherwise by IsobaricCriteria.  Batches with QMC_OP_ANISOTROPIC / QMC_OP_SHAPE moves must
      * set triclinic (an accepted move leaves a general cell behind). */

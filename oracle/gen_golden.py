@@ -422,8 +422,11 @@ def case_gc_composite(seed, n_attempts, mu, temperature, k=2):
     )  # fmt: skip
 
 
-def case_gc_emt(seed, n_attempts, mu, temperature):
+def case_gc_emt(seed, n_attempts, mu, temperature, shear=None):
     atoms, pos0, cell = cu_atoms(3, 0.05, 31337)
+    if shear is not None:  # a general (triclinic) cell: cell' = S @ cell, atoms carried along
+        atoms.set_cell(np.asarray(shear) @ cell, scale_atoms=True)
+        pos0, cell = atoms.positions.copy(), atoms.cell.array.copy()
     n = len(atoms)
     disp = DisplacementMove(np.arange(n))
     exch = ExchangeMove(np.arange(n))
@@ -475,6 +478,7 @@ def main():
         "gc_lj": lambda: case_gc_lj(3001, 700, -0.5),
         "gc_emt": lambda: case_gc_emt(3002, 150, -3.4, 3000.0),
         "gc_molecule": lambda: case_gc_molecule(3003, 600, -0.6),
+        "gc_emt_sheared": lambda: case_gc_emt(3005, 200, -3.8, 3000.0, shear=[[1.0, 0.02, 0.0], [0.05, 1.0, -0.02], [-0.03, 0.04, 1.0]]),
         "gc_composite": lambda: case_gc_composite(3004, 600, -3.3, 2000.0),
         "hmc": lambda: case_hmc(4001, 3, 2.0, 12, 800.0),
         "composite_mul": lambda: case_composite("mul", 5001, 120),

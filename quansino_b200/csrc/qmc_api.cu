@@ -372,11 +372,14 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica sweep kernel");
     if (batch->triclinic) {
         // general cells (csrc/sweep_tri.cuh): plain single-atom displacement moves and cell moves
-        if (any_exchange || any_composite || a.n_forced > 0)
-            return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: exchange, composite and forced moves are not available on the GPU path");
-        for (int m = 0; m < n_moves; ++m)
+        if (any_composite || a.n_forced > 0)
+            return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: composite moves, label groups and forced moves are not available on the GPU path");
+        for (int m = 0; m < n_moves; ++m) {
             if (moves[m].type == QMC_MOVE_DISPLACEMENT && moves[m].op != QMC_OP_BALL && moves[m].op != QMC_OP_BOX && moves[m].op != QMC_OP_SPHERE)
                 return fail(QMC_ERR_UNSUPPORTED, "move %d: general (triclinic) cells take Ball / Box / Sphere displacements of single atoms", m);
+            if (moves[m].type == QMC_MOVE_EXCHANGE && (moves[m].op != QMC_OP_TRANSLATION || batch->n_exchange_atoms > 1))
+                return fail(QMC_ERR_UNSUPPORTED, "move %d: general (triclinic) cells take single-atom exchange moves placed by Translation", m);
+        }
         if (batch->nbr_state) CUDA_TRY(cudaMemsetAsync(batch->nbr_state, 0, (size_t)batch->n_replicas * sizeof(int32_t), (cudaStream_t)stream));
         return inst->sweep_tri(a, (cudaStream_t)stream, g_err, sizeof(g_err));
     }

@@ -155,7 +155,8 @@ struct CellView {
 // Image rule: with every periodic height w_k >= cutoff', an image of j inside the cutoff has fractional components |f_k| <=
 // cutoff' / w_k <= 1 (f_k = r . b_k, |b_k| = 1 / w_k), so with fr = f - rint(f) the candidates are fr_k and, where |fr_k| > thr_k,
 // fr_k - sign(fr_k): at most 2 x 2 x 2 images, the same subset enumeration as for diagonal cells -- but the image found by rounding
-// is NOT always the closest one, so the second images are looked at whether or not the first one is inside the cutoff.
+// is NOT always the closest one, so a flagged lane first finds the closest of its candidates (`nearest`); that image plays the
+// part the nearest image plays in a diagonal cell (it owns the slot, the others are looked at only if it is inside the cutoff).
 struct TriView {
     static constexpr bool TRI = true;
     const double *h;  // H[9]
@@ -239,8 +240,10 @@ struct DeltaAcc {
     int pairs;    // per-lane count of evaluated list entries
 };
 
-// One-sided scan in a general cell (full-energy rows): every image of every other atom inside the cutoff, signed r^2 into the list.
-template <class RV, class CELL>
+// One-sided scan in a general cell (full-energy rows, and the local delta of an inserted / deleted atom): every image of every other
+// atom inside the cutoff, signed r^2 into the list.  The CLOSEST image of an atom comes first (for the local delta it owns the
+// atom's slot, pp / l2); the further images are looked at only if that one is inside, and follow behind all closest images.
+template <class RV, bool TRACK, class CELL>
 __device__ __forceinline__ int scan_neighbours_tri(const PotDev &pot, const RV &R, const CELL &C, const int lane, const unsigned lt, int n_scan,
                                                    int i_excl, bool side, const double p[3], int &n2, int &xstart, int &status,
                                                    int tile_first, int tile_step) {
@@ -251,14 +254,18 @@ __device__ __forceinline__ int scan_neighbours_tri(const PotDev &pot, const RV &
         const bool valid = j < n_scan && j != i_excl;
         const int jc = valid ? j : 0;
         double d0[3], sg[3];
-        const unsigned fl = C.reduce(R.x(jc) - p[0], R.y(jc) - p[1], R.z(jc) - p[2], d0, sg);
-        const double r2 = fma(d0[2], d0[2], fma(d0[1], d0[1], d0[0] * d0[0]));
+        unsigned fl, best;
+        const double r2 = C.nearest(R.x(jc) - p[0], R.y(jc) - p[1], R.z(jc) - p[2], d0, sg, fl, best);
         const bool in = valid && r2 < pot.cut_pre2;
         const unsigned b = __ballot_sync(FULL, in);
         const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
-        if (in) R.lr(pos) = side ? r2 : -r2;
+        if (in) {
+            R.lr(pos) = side ? r2 : -r2;
+            if (TRACK) R.l2(pos) = (uint16_t)j;
+        }
+        if (TRACK && valid) R.pp(j) = !in ? (NOPOS | (NOPOS << 16)) : side ? (NOPOS | ((unsigned)pos << 16)) : ((NOPOS << 16) | (unsigned)pos);
         cnt += __popc(b);
-        const bool ex = valid && fl != 0u;  // further images are looked at whether or not this one is inside
+        const bool ex = in && fl != 0u;
         const unsigned bq = __ballot_sync(FULL, ex);
         if (ex) queue[min(nq + __popc(bq & lt), RV::QCAP - 1)] = (unsigned)j;
         nq += __popc(bq);
@@ -280,17 +287,21 @@ __device__ __forceinline__ int scan_neighbours_tri(const PotDev &pot, const RV &
             const bool has = q < nq;
             const int j = has ? (int)queue[q] : 0;
             double d0[3], sg[3];
-            const unsigned fl = C.reduce(R.x(j) - p[0], R.y(j) - p[1], R.z(j) - p[2], d0, sg);
-            unsigned c = fl & (0u - fl);  // first non-empty subset of fl
+            unsigned fl, best;
+            C.nearest(R.x(j) - p[0], R.y(j) - p[1], R.z(j) - p[2], d0, sg, fl, best);
+            unsigned c = 0u;  // every subset of the flagged axes except the closest image
             bool more = has && fl != 0u;
             while (__any_sync(FULL, more)) {
                 double d[3];
                 C.shifted(d0, sg, c, d);
                 const double r2 = fma(d[2], d[2], fma(d[1], d[1], d[0] * d[0]));
-                const bool in = more && r2 < pot.cut_pre2;
+                const bool in = more && c != best && r2 < pot.cut_pre2;
                 const unsigned b = __ballot_sync(FULL, in);
                 const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
-                if (in) R.lr(pos) = side ? r2 : -r2;
+                if (in) {
+                    R.lr(pos) = side ? r2 : -r2;
+                    if (TRACK) R.xj(min(pos - xstart, RV::XCAPN - 1)) = (uint16_t)j;
+                }
                 cnt += __popc(b);
                 if (more) {
                     if (c == fl) more = false;
@@ -299,9 +310,10 @@ __device__ __forceinline__ int scan_neighbours_tri(const PotDev &pot, const RV &
             }
         }
     }
-    if (cnt > RV::CAPE) {
+    if (cnt > RV::CAPE || (TRACK && cnt - xstart > RV::XCAPN)) {
         status |= QMC_STATUS_LIST_OVERFLOW;
-        cnt = RV::CAPE;
+        cnt = min(cnt, RV::CAPE);
+        if (TRACK && cnt - xstart > RV::XCAPN) cnt = xstart + RV::XCAPN;
     }
     __syncwarp();
     return cnt;
@@ -322,8 +334,7 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const RV &R, c
     constexpr bool TRACK = (MODE == 0 && RV::EMT);
     uint32_t *queue = R.queue();  // one word per flagged neighbour: at most n - 1 <= QCAP
     if constexpr (CELL::TRI) {
-        static_assert(!TRACK, "general cells: full-energy rows only (the slot bookkeeping of the local delta lives in scan_both)");
-        return scan_neighbours_tri<RV>(pot, R, C, lane, lt, n_scan, i_excl, has_new, has_new ? pn : po, n2, xstart, status, tile_first, tile_step);
+        return scan_neighbours_tri<RV, TRACK>(pot, R, C, lane, lt, n_scan, i_excl, has_new, has_new ? pn : po, n2, xstart, status, tile_first, tile_step);
     } else {
     const bool p0 = C.per(0), p1 = C.per(1), p2 = C.per(2);
     const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);

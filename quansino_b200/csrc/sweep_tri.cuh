@@ -6,8 +6,10 @@
 // full-energy building blocks (csrc/replica_warp.cuh) -- only the image arithmetic differs: fractional coordinates through H^-1,
 // rounding, and up to 2 x 2 x 2 images per pair (TriView).  A cell move recomputes everything (the reference does, too).
 //
-// Not in this kernel (the host refuses them for triclinic batches): exchange moves, composite moves, label groups, forced moves,
-// neighbour rows, the Hamiltonian / ForceBias force kernels.
+// Plain single-atom exchange moves (moves/exchange.py:88-176 with Translation placement) run here as well.
+//
+// Not in this kernel (the host refuses them for triclinic batches): molecular and composite exchange, composite moves, label
+// groups, forced moves, neighbour rows, the Hamiltonian / ForceBias force kernels.
 #pragma once
 
 #include "sweep_kernel.cuh"
@@ -257,6 +259,93 @@ __device__ __noinline__ bool cell_move_tri(const SweepArgs &a, const Rep<Layout<
     return acc;
 }
 
+// One plain exchange move of one replica in a general cell (moves/exchange.py:134-176, mc/criteria.py:225-277): the branch of
+// csrc/sweep_kernel.cuh with `uniform(0, 1, (1, 3)) @ cell` for a full cell matrix.  Out of line like the cell move.
+template <int POT, int NS>
+__device__ __noinline__ int exchange_move_tri(const SweepArgs &a, const Rep<Layout<POT, NS>> &Rc, const TriView &C, const MoveDev &mv, const Draws &D,
+                                              int r, int lane, double &E, double &delta, long long &n_pairs, int &n_ex, int &n_now,
+                                              int &moved, int &status) {
+    using LY = Layout<POT, NS>;
+    Rep<LY> R = Rc;
+    R.n = n_now;
+    const PotDev &pot = a.pot;
+    const unsigned lt = lanemask_lt();
+    const int nmax = a.b.n_max;
+    const int *lab = mv.labels ? mv.labels + (size_t)r * nmax : nullptr;
+    const bool is_add = D.u_coin < mv.bias;
+    int pd = 0, i = -1;
+    Trial T;
+    double pn[3] = {0, 0, 0}, po[3] = {0, 0, 0};
+    if (is_add) {
+        if (R.n + 1 > nmax) {
+            status |= QMC_STATUS_CAPACITY;
+        } else {
+            // Translation (operations/displacement.py:173-175): uniform(0,1,(1,3)) @ cell - mean(positions[moving])
+            const double f[3] = {D.o0, D.o1, D.o2};
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                const double fc = __dadd_rn(__dadd_rn(__dmul_rn(f[0], C.h[d]), __dmul_rn(f[1], C.h[3 + d])), __dmul_rn(f[2], C.h[6 + d]));
+                pn[d] = __dadd_rn(a.b.exchange_pos[d], __dsub_rn(fc, a.b.exchange_pos[d]));
+            }
+            i = R.n;
+            T = local_delta<LY>(pot, R, C, lane, lt, R.n, i, false, true, po, pn, status);
+            pd = 1;
+        }
+    } else {
+        const int nu = lab ? count_labelled(lab, R.n) : R.n;
+        if (nu > 0) {
+            const int idx = (int)(D.u_label * (double)nu);
+            i = lab ? select_labelled(lab, R.n, idx) : idx;
+            po[0] = R.x(i);
+            po[1] = R.y(i);
+            po[2] = R.z(i);
+            T = local_delta<LY>(pot, R, C, lane, lt, R.n, i, true, false, po, pn, status);
+            pd = -1;
+        }
+    }
+    if (pd == 0) return -1;
+    n_pairs += T.pairs;
+    delta = T.dE;
+    bool ov;
+    const double prob = gc_probability(delta, pd, n_ex, a.b.accessible_volume, a.b.exchange_mass, a.b.temperature[r], a.b.chemical_potential, ov);
+    if (ov) status |= QMC_STATUS_EXP_OVERFLOW;
+    const bool acc = D.u_accept < prob;
+    if (acc) {
+        commit_trial<LY>(R, lane, T);
+        // GrandCanonical.save_state (mc/gcmc.py:207-214): every registered move re-labels
+        for (int q = 0; q < a.n_moves; ++q)
+            if (a.mv[q].labels && table_first_use(a.mv, q))
+                labels_changed(a.mv[q].labels + (size_t)r * nmax, R.n, pd > 0, pd < 0 ? i : -1, a.mv[q].default_label);
+        if (pd > 0) {
+            if (lane == 0) {
+                R.x(i) = pn[0];
+                R.y(i) = pn[1];
+                R.z(i) = pn[2];
+                if (POT == QMC_POT_EMT) {
+                    R.sig(i) = T.sig_i;
+                    R.eat(i) = T.eat_i;
+                }
+            }
+            R.n += 1;
+        } else {
+            shift_down(&R.x(0), i, R.n);
+            shift_down(&R.y(0), i, R.n);
+            shift_down(&R.z(0), i, R.n);
+            if (POT == QMC_POT_EMT) {
+                shift_down(&R.sig(0), i, R.n);
+                shift_down(&R.eat(0), i, R.n);
+            }
+            R.n -= 1;
+        }
+        n_ex += pd;
+        E += delta;
+    }
+    __syncwarp();
+    n_now = R.n;
+    moved = i;
+    return acc ? 1 : 0;
+}
+
 template <int POT, int NS>
 __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_kernel(const __grid_constant__ SweepArgs a) {
     using LY = Layout<POT, NS>;
@@ -299,13 +388,14 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_k
     const uint32_t grep = (uint32_t)(a.b.replica_offset + r);
     const PhiloxKey key = {(uint32_t)a.seed, (uint32_t)(a.seed >> 32)};
     long long n_pairs = 0;
+    int n_ex = a.need_coin ? __ldcg(a.b.n_exchange + r) : 0;
     __syncwarp();
 
     for (int k = 0; k < a.n_attempts; ++k) {
         const unsigned long long attempt = a.attempt_base + (unsigned long long)k;
         const int ahead = k & (DRAW_AHEAD - 1);
         if (ahead == 0) draw_ahead(R, key, attempt, grep, lane);
-        const Draws D = read_draws(R, ahead, false);
+        const Draws D = read_draws(R, ahead, a.need_coin != 0);
         int m = 0;
         while (m < a.n_moves - 1 && a.cdf[m] <= D.u_select) ++m;
         const MoveDev &mv = a.mv[m];
@@ -345,6 +435,8 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_k
             }
         } else if (mv.type == QMC_MOVE_CELL) {
             accepted = cell_move_tri<POT, NS>(a, R, C, mv, D, attempt, r, lane, E, delta, n_pairs, status) ? 1 : 0;
+        } else if (mv.type == QMC_MOVE_EXCHANGE) {
+            accepted = exchange_move_tri<POT, NS>(a, R, C, mv, D, r, lane, E, delta, n_pairs, n_ex, R.n, moved, status);
         }  // (the host admits no other move types for general cells)
 
         if (lane == 0) {
@@ -379,6 +471,8 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_k
     }
     if (lane == 0) {
         a.b.energy[r] = E;
+        a.b.n_atoms[r] = R.n;
+        if (a.need_coin) a.b.n_exchange[r] = n_ex;
         if (status) atomicOr(a.b.status + r, status);
     }
     if (a.b.pair_evals) {

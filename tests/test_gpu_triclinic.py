@@ -176,6 +176,67 @@ def test_shape_deformation_preserves_the_volume(cuda_lib):
     np.testing.assert_allclose(np.abs(np.linalg.det(out.cell)), abs(np.linalg.det(cell0)), rtol=1e-12)
 
 
+def test_grand_canonical_in_general_cells_matches_oracle(cuda_lib):
+    """Plain exchange moves (moves/exchange.py:88-176, Translation placement `uniform(0, 1, (1, 3)) @ cell`) in sheared periodic
+    cells, one shear per replica: a Lennard-Jones fluid that gains and loses atoms, every attempt against the oracle, label tables
+    bit-exact."""
+    from quansino_b200 import BatchedAtoms, LennardJones
+    from quansino_b200.mc import GrandCanonical
+    from quansino_b200.moves import DisplacementMove, ExchangeMove
+
+    R, n0, n_max, n_attempts, mu, T = 4, 20, 64, 500, -0.5, 400.0
+    rng = np.random.default_rng(3)
+    cells = np.zeros((R, 3, 3))
+    pos = np.zeros((R, n_max, 3))
+    for r in range(R):
+        cells[r] = (np.eye(3) + rng.uniform(-0.2, 0.2, (3, 3)) * (1 - np.eye(3))) @ (np.eye(3) * 12.0)
+        grid = np.array([[i, j, k] for i in range(3) for j in range(3) for k in range(3)], dtype=float)[:n0]
+        pos[r, :n0] = ((grid + 0.5) / 3.0 + rng.normal(scale=0.02, size=(n0, 3))) @ cells[r]
+    calc = LennardJones(sigma=2.5, epsilon=0.05, rc=6.0)
+    par = LJParams(sigma=2.5, epsilon=0.05, rc=6.0)
+    atoms = BatchedAtoms(pos.copy(), cells, np.full(R, n0, dtype=np.int32), "Pt", (True, True, True), calc)
+    lab = np.arange(n0)
+    mc = GrandCanonical(
+        atoms, exchange_atoms=("Pt", (0.0, 0.0, 0.0)), temperature=T, chemical_potential=mu, number_of_exchange_particles=n0,
+        max_cycles=n_attempts, seed=31, trace=True, resync_interval=0,
+        default_displacement_move=DisplacementMove(lab), default_exchange_move=ExchangeMove(lab),
+    )  # fmt: skip
+    mc.moves["default_displacement_move"].probability = 0.4
+    mc.moves["default_exchange_move"].probability = 0.6
+    vol = np.abs(np.linalg.det(cells))
+    assert mc.batch.triclinic
+    mc.accessible_volume = float(vol[0])
+    mc.run(1)
+    tr, out = mc.last_trace, mc.download()
+    n_ex = mc.number_of_exchange_particles
+    labels_d, labels_x = mc.labels("default_displacement_move"), mc.labels("default_exchange_move")
+    ins = dele = 0
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cells[r], pbc=(1, 1, 1), n_atoms=n0, temperature=T, mass=195.084, chemical_potential=mu,
+                           exchange_mass=195.084, n_exchange=n0, accessible_volume=float(vol[0]))  # fmt: skip
+        ld = np.full(n_max, -1, np.int32)
+        ld[:n0] = lab
+        lx = ld.copy()
+        specs = [
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.1, probability=0.4, labels=ld),
+            capi.MoveSpec(capi.MOVE_EXCHANGE, capi.OP_TRANSLATION, probability=0.6, labels=lx),
+        ]
+        ref = capi.mc_run(par, rep, specs, 31, r, 0, n_attempts)
+        assert np.array_equal(tr["move"][r], ref["move"])
+        assert np.array_equal(tr["accepted"][r], ref["accepted"]), f"accept/reject sequence differs for replica {r}"
+        assert np.array_equal(tr["moved"][r], ref["moved"])
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10)
+        assert out.n_atoms[r] == rep.n_atoms and n_ex[r] == rep.n_exchange
+        assert np.array_equal(labels_d[r, : rep.n_atoms], ld[: rep.n_atoms])
+        assert np.array_equal(labels_x[r, : rep.n_atoms], lx[: rep.n_atoms])
+        np.testing.assert_allclose(out.positions[r, : rep.n_atoms], rep.positions[: rep.n_atoms], rtol=0, atol=1e-10)
+        d_n = np.diff(np.concatenate([[n0], ref["n_atoms"]]))
+        ins += int((d_n == 1).sum())
+        dele += int((d_n == -1).sum())
+    assert ins > 20 and dele > 20, (ins, dele)
+    assert int(mc.batch.status.max().item()) == 0
+
+
 def test_general_cells_refuse_what_their_kernels_do_not_hold(cuda_lib):
     from quansino_b200 import EMT, BatchedAtoms, ReplicaBatch
     from quansino_b200.mc import GrandCanonical, HamiltonianCanonical
@@ -185,8 +246,9 @@ def test_general_cells_refuse_what_their_kernels_do_not_hold(cuda_lib):
     pos_pad = np.zeros((2, 128, 3))
     pos_pad[:, :n] = pos
     atoms = BatchedAtoms(pos_pad, cells, np.full(2, n, dtype=np.int32), "Cu", (True, True, True), EMT())
-    gc = GrandCanonical(atoms, exchange_atoms="Cu", temperature=1000.0, chemical_potential=-3.0, number_of_exchange_particles=n, max_cycles=10,
-                        seed=1, default_displacement_move=DisplacementMove(np.arange(n)), default_exchange_move=ExchangeMove(np.arange(n)))  # fmt: skip
+    dimer = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 2.5]])  # a molecular species: run-coded label groups, not in the general-cell kernels
+    gc = GrandCanonical(atoms, exchange_atoms=("Cu", dimer), temperature=1000.0, chemical_potential=-3.0, number_of_exchange_particles=0, max_cycles=10,
+                        seed=1, default_displacement_move=DisplacementMove(np.arange(n)), default_exchange_move=ExchangeMove(np.full(n, -1)))  # fmt: skip
     with pytest.raises(NotImplementedError, match="triclinic"):
         gc.run(1)
     atoms = BatchedAtoms(pos.copy(), cells, np.full(2, n, dtype=np.int32), "Cu", (True, True, True), EMT())
