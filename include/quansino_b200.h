@@ -184,7 +184,8 @@ typedef struct qmc_batch {
     /* General (triclinic) cells.  triclinic != 0: `cell` holds full 3 x 3 matrices (rows = cell vectors) and qmc_sweep /
      * qmc_energy_full / qmc_atom_energies run the general-cell kernels (csrc/sweep_tri.cuh): single-atom displacement moves,
      * single-atom exchange moves placed by Translation, and cell moves (all three deformation operations); every periodic HEIGHT
-     * of the cell must be >= the neighbour cutoff.
+     * of the cell must be >= the neighbour cutoff.  qmc_forces_full / qmc_hmc / qmc_fbmc_step take general cells, too (the
+     * Verlet-list shifts then count cell vectors).
      * isotension != 0: cell moves are judged by IsotensionCriteria (mc/criteria.py:175-219) with `external_stress` (eV / A^3,
      * row-major 3 x 3) and `pressure`; otherwise by IsobaricCriteria.  Batches with QMC_OP_ANISOTROPIC / QMC_OP_SHAPE moves must
      * set triclinic (an accepted move leaves a general cell behind). */

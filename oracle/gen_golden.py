@@ -446,8 +446,11 @@ def case_gc_emt(seed, n_attempts, mu, temperature, shear=None):
     )  # fmt: skip
 
 
-def case_hmc(seed, n_attempts, dt_fs, n_steps, temperature):
+def case_hmc(seed, n_attempts, dt_fs, n_steps, temperature, shear=None):
     atoms, pos0, cell = cu_atoms(3, 0.03, 2718)
+    if shear is not None:  # a general (triclinic) cell
+        atoms.set_cell(np.asarray(shear) @ cell, scale_atoms=True)
+        pos0, cell = atoms.positions.copy(), atoms.cell.array.copy()
     mc = HamiltonianCanonical(
         atoms, temperature=temperature, max_cycles=1,
         default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=dt_fs, max_steps=n_steps)),
@@ -481,6 +484,7 @@ def main():
         "gc_emt_sheared": lambda: case_gc_emt(3005, 200, -3.8, 3000.0, shear=[[1.0, 0.02, 0.0], [0.05, 1.0, -0.02], [-0.03, 0.04, 1.0]]),
         "gc_composite": lambda: case_gc_composite(3004, 600, -3.3, 2000.0),
         "hmc": lambda: case_hmc(4001, 3, 2.0, 12, 800.0),
+        "hmc_sheared": lambda: case_hmc(4002, 3, 2.0, 12, 800.0, shear=[[1.0, 0.02, 0.0], [0.05, 1.0, -0.02], [-0.03, 0.04, 1.0]]),
         "composite_mul": lambda: case_composite("mul", 5001, 120),
         "composite_add": lambda: case_composite("add", 5002, 80),
         "composite_exhaust": lambda: case_composite("exhaust", 5003, 40),

@@ -90,7 +90,7 @@ __host__ inline int hmc_max_neighbours(const PotDev &pot, const qmc_batch_t &b) 
     const double dense = pot.kind == QMC_POT_EMT ? 0.10 : 1.4 / (pot.sigma2 * std::sqrt(pot.sigma2));
     double est = dense * sphere * 1.3 + 24.0;
     const bool periodic = b.pbc[0] && b.pbc[1] && b.pbc[2];
-    if (periodic && b.cells_uniform && b.cell_diag[0] > 0 && b.cell_diag[1] > 0 && b.cell_diag[2] > 0) {
+    if (periodic && b.cells_uniform && !b.triclinic && b.cell_diag[0] > 0 && b.cell_diag[1] > 0 && b.cell_diag[2] > 0) {
         const double density = (double)b.n_max / (b.cell_diag[0] * b.cell_diag[1] * b.cell_diag[2]);
         est = density * sphere * 1.5 + 24.0;
     }
@@ -135,10 +135,36 @@ __device__ inline double block_sum(double v, double *red) {
 struct CellDev {
     double L[3], invL[3], thr[3];
     bool per[3];
+    // general (triclinic) cells, qmc_batch_t.triclinic: rows of H are the cell vectors, Hi = H^-1 (the column of a non-periodic axis
+    // zeroed), thr = fractional threshold 1 - cut / height (csrc/replica_warp.cuh: TriView has the image rule)
+    bool tri;
+    double H[9], Hi[9];
 };
 
 __device__ inline bool hmc_cell(const HmcArgs &a, int r, double cut, CellDev &C) {
     bool ok = true;
+    C.tri = a.b.triclinic != 0;
+    if (C.tri) {
+        double h[9];
+        for (int q = 0; q < 9; ++q) h[q] = C.H[q] = a.b.cell[(size_t)r * 9 + q];
+        const double det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) + h[2] * (h[3] * h[7] - h[4] * h[6]);
+        const double d = 1.0 / det;
+        const double inv[9] = {(h[4] * h[8] - h[5] * h[7]) * d, (h[2] * h[7] - h[1] * h[8]) * d, (h[1] * h[5] - h[2] * h[4]) * d,
+                               (h[5] * h[6] - h[3] * h[8]) * d, (h[0] * h[8] - h[2] * h[6]) * d, (h[2] * h[3] - h[0] * h[5]) * d,
+                               (h[3] * h[7] - h[4] * h[6]) * d, (h[1] * h[6] - h[0] * h[7]) * d, (h[0] * h[4] - h[1] * h[3]) * d};
+        for (int k = 0; k < 3; ++k) {
+            const double *p = h + 3 * ((k + 1) % 3), *q = h + 3 * ((k + 2) % 3);
+            const double cx = p[1] * q[2] - p[2] * q[1], cy = p[2] * q[0] - p[0] * q[2], cz = p[0] * q[1] - p[1] * q[0];
+            const double w = fabs(det) / sqrt(cx * cx + cy * cy + cz * cz);  // height of the cell along axis k
+            C.per[k] = a.b.pbc[k] != 0;
+            C.L[k] = w;
+            C.invL[k] = 0.0;
+            C.thr[k] = C.per[k] ? 1.0 - cut / w - 1e-9 : 1e300;
+            for (int x = 0; x < 3; ++x) C.Hi[3 * x + k] = C.per[k] ? inv[3 * x + k] : 0.0;
+            if (C.per[k] && !(w >= cut)) ok = false;
+        }
+        return ok;
+    }
     for (int k = 0; k < 3; ++k) {
         const double L = a.b.cell[(size_t)r * 9 + 4 * k];
         C.L[k] = L;
@@ -148,6 +174,53 @@ __device__ inline bool hmc_cell(const HmcArgs &a, int r, double cut, CellDev &C)
         if (C.per[k] && !(L >= cut)) ok = false;
     }
     return ok;
+}
+
+// Candidate images of atom j seen from atom i for the list build: the image found by rounding (vector d0, integer shift k0) and,
+// per flagged axis q (bit q of `avail`), the one shifted by -sgn[q] cell vectors.  Image c (a subset of `avail`) is
+// d0 - sum_{q in c} sgn[q] a_q with the integer shift k0[q] - sgn[q].
+__device__ inline void hmc_images(const CellDev &C, const double pi[3], const double pj[3], double d0[3], double k0[3], double sgn[3],
+                                  unsigned &avail) {
+    avail = 0;
+    if (C.tri) {
+        const double ex = pi[0] - pj[0], ey = pi[1] - pj[1], ez = pi[2] - pj[2];
+        double fr[3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const double f = fma(ez, C.Hi[6 + q], fma(ey, C.Hi[3 + q], ex * C.Hi[q]));
+            k0[q] = (f + RINT_MAGIC) - RINT_MAGIC;
+            fr[q] = f - k0[q];
+            sgn[q] = fr[q] > 0.0 ? -1.0 : 1.0;  // the fractional coordinate of d0 along q is -fr[q]
+            if (fabs(fr[q]) > C.thr[q]) avail |= 1u << q;
+        }
+#pragma unroll
+        for (int x = 0; x < 3; ++x) d0[x] = fma(k0[2], C.H[6 + x], fma(k0[1], C.H[3 + x], fma(k0[0], C.H[x], pj[x]))) - pi[x];
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        if (C.per[q]) {
+            const double f = (pi[q] - pj[q]) * C.invL[q];
+            k0[q] = (f + RINT_MAGIC) - RINT_MAGIC;
+            d0[q] = fma(k0[q], C.L[q], pj[q]) - pi[q];
+            if (fabs(d0[q]) > C.thr[q]) avail |= 1u << q;
+        } else {
+            k0[q] = 0.0;
+            d0[q] = pj[q] - pi[q];
+        }
+        sgn[q] = d0[q] > 0.0 ? 1.0 : -1.0;
+    }
+}
+
+__device__ inline void hmc_image_vector(const CellDev &C, const double d0[3], const double sgn[3], unsigned c, double d[3]) {
+    if (C.tri) {
+        const double m0 = (c & 1u) ? sgn[0] : 0.0, m1 = (c & 2u) ? sgn[1] : 0.0, m2 = (c & 4u) ? sgn[2] : 0.0;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) d[x] = fma(-m2, C.H[6 + x], fma(-m1, C.H[3 + x], fma(-m0, C.H[x], d0[x])));
+        return;
+    }
+#pragma unroll
+    for (int q = 0; q < 3; ++q) d[q] = ((c >> q) & 1u) ? d0[q] - copysign(C.L[q], d0[q]) : d0[q];
 }
 
 __device__ inline double hmc_normal(PhiloxKey key, unsigned long long attempt, uint32_t replica, uint32_t m) {
@@ -217,30 +290,19 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_build_kernel(const __grid_con
         for (int t = 0; t < jn; ++t) {
             const int j = j0 + t;
             if (j == i) continue;
-            double d0[3], d1[3], k0[3];
+            double d0[3], k0[3], sgn[3];
             unsigned avail = 0;
             const double pj[3] = {sx[t], sy[t], sz[t]}, pi[3] = {xi, yi, zi};
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                if (C.per[c]) {
-                    const double q = (pi[c] - pj[c]) * C.invL[c];
-                    k0[c] = (q + RINT_MAGIC) - RINT_MAGIC;
-                    d0[c] = fma(k0[c], C.L[c], pj[c]) - pi[c];
-                    d1[c] = d0[c] - copysign(C.L[c], d0[c]);
-                    if (fabs(d0[c]) > C.thr[c]) avail |= 1u << c;
-                } else {
-                    k0[c] = 0.0;
-                    d0[c] = d1[c] = pj[c] - pi[c];
-                }
-            }
+            hmc_images(C, pi, pj, d0, k0, sgn, avail);
             unsigned c = 0;
             while (true) {
-                const double dx = (c & 1u) ? d1[0] : d0[0], dy = (c & 2u) ? d1[1] : d0[1], dz = (c & 4u) ? d1[2] : d0[2];
-                if (dx * dx + dy * dy + dz * dz < rl2) {
-                    // integer image shift per axis: nearest image k0, second image k0 -+ 1
+                double d[3];
+                hmc_image_vector(C, d0, sgn, c, d);
+                if (d[0] * d[0] + d[1] * d[1] + d[2] * d[2] < rl2) {
+                    // integer image shift per axis: the image found by rounding k0, the further image k0 - sgn
                     int sh[3];
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) sh[q] = (int)k0[q] - (((c >> q) & 1u) ? (d0[q] > 0.0 ? 1 : -1) : 0);
+                    for (int q = 0; q < 3; ++q) sh[q] = (int)k0[q] - (((c >> q) & 1u) ? (int)sgn[q] : 0);
                     if (abs(sh[0]) > 15 || abs(sh[1]) > 15 || abs(sh[2]) > 15 || k >= a.w.max_nb) {
                         overflow = 1;
                     } else {
@@ -315,32 +377,23 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_build_split_kernel(const __gr
                 const float gap = fabsf(d) - bb[3 + q];
                 gap2 += gap > 0.0f ? gap * gap : 0.0f;
             }
+            if (C.tri) gap2 = 0.0f;  // general cells: the per-axis wrap of the chunk test does not apply, every round is looked at
             bool active = own && t < jn && j != i && !(gap2 > rlf2);
-            double d0[3] = {0.0, 0.0, 0.0}, d1[3] = {0.0, 0.0, 0.0}, k0[3] = {0.0, 0.0, 0.0};
+            double d0[3] = {0.0, 0.0, 0.0}, sgn[3] = {1.0, 1.0, 1.0}, k0[3] = {0.0, 0.0, 0.0};
             unsigned avail = 0, c = 0;
             if (active) {
                 const double pj[3] = {sx[t], sy[t], sz[t]};
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    if (C.per[q]) {
-                        const double f = (pi[q] - pj[q]) * C.invL[q];
-                        k0[q] = (f + RINT_MAGIC) - RINT_MAGIC;
-                        d0[q] = fma(k0[q], C.L[q], pj[q]) - pi[q];
-                        d1[q] = d0[q] - copysign(C.L[q], d0[q]);
-                        if (fabs(d0[q]) > C.thr[q]) avail |= 1u << q;
-                    } else {
-                        d0[q] = d1[q] = pj[q] - pi[q];
-                    }
-                }
+                hmc_images(C, pi, pj, d0, k0, sgn, avail);
             }
-            while (__any_sync(FULL, active)) {  // nearest image first, then the further images a short cell edge allows
+            while (__any_sync(FULL, active)) {  // the image found by rounding first, then the further images a short cell allows
                 bool hit = false;
                 int sh[3] = {0, 0, 0};
                 if (active) {
-                    const double dx = (c & 1u) ? d1[0] : d0[0], dy = (c & 2u) ? d1[1] : d0[1], dz = (c & 4u) ? d1[2] : d0[2];
-                    hit = dx * dx + dy * dy + dz * dz < rl2;
+                    double d[3];
+                    hmc_image_vector(C, d0, sgn, c, d);
+                    hit = d[0] * d[0] + d[1] * d[1] + d[2] * d[2] < rl2;
 #pragma unroll
-                    for (int q = 0; q < 3; ++q) sh[q] = (int)k0[q] - (((c >> q) & 1u) ? (d0[q] > 0.0 ? 1 : -1) : 0);
+                    for (int q = 0; q < 3; ++q) sh[q] = (int)k0[q] - (((c >> q) & 1u) ? (int)sgn[q] : 0);
                     if (hit && (abs(sh[0]) > 15 || abs(sh[1]) > 15 || abs(sh[2]) > 15)) {
                         overflow = 1;
                         hit = false;
@@ -429,11 +482,18 @@ __device__ __forceinline__ void nb_start(NbPipe &P, const unsigned *lp, int nmax
 }
 
 // image vector of the current entry for the atom at (xi, yi, zi); its atom index in j
+template <bool TRI>
 __device__ __forceinline__ void nb_vector(const NbPipe &P, const CellDev &C, double xi, double yi, double zi, int &j, double &dx, double &dy,
                                           double &dz) {
     const unsigned e = P.e0;
     j = (int)(e & 0xFFFFu);
     const int sx = (int)((e >> 16) & 31u) - 16, sy = (int)((e >> 21) & 31u) - 16, sz = (int)((e >> 26) & 31u) - 16;
+    if (TRI) {  // general cell: the integer shift counts cell VECTORS
+        dx = fma((double)sz, C.H[6], fma((double)sy, C.H[3], fma((double)sx, C.H[0], P.gx))) - xi;
+        dy = fma((double)sz, C.H[7], fma((double)sy, C.H[4], fma((double)sx, C.H[1], P.gy))) - yi;
+        dz = fma((double)sz, C.H[8], fma((double)sy, C.H[5], fma((double)sx, C.H[2], P.gz))) - zi;
+        return;
+    }
     dx = fma((double)sx, C.L[0], P.gx) - xi;
     dy = fma((double)sy, C.L[1], P.gy) - yi;
     dz = fma((double)sz, C.L[2], P.gz) - zi;
@@ -452,7 +512,7 @@ __device__ __forceinline__ void nb_advance(NbPipe &P, const unsigned *lp, int nm
 }
 
 // ---- pass 1: sigma_1, energies, dE/dsigma_1 ----------------------------------------------------------------------
-template <int POT>
+template <int POT, bool TRI>
 __global__ void __launch_bounds__(HMC_THREADS) hmc_pass1_kernel(const __grid_constant__ HmcArgs a) {
     __shared__ double red[32];
     const int r = blockIdx.y, nmax = a.b.n_max, n = a.b.n_atoms[r];
@@ -473,7 +533,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass1_kernel(const __grid_con
         for (int k = sub; k < nn; k += lpa) {
             int j;
             double dx, dy, dz;
-            nb_vector(P, C, xi, yi, zi, j, dx, dy, dz);
+            nb_vector<TRI>(P, C, xi, yi, zi, j, dx, dy, dz);
             nb_advance(P, list + i, nmax, k, lpa, nn, x, y, z);
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
             if (r2 < a.pot.cut_pre2) {
@@ -508,7 +568,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass1_kernel(const __grid_con
 }
 
 // ---- pass 2: forces + velocity-Verlet update --------------------------------------------------------------------
-template <int POT>
+template <int POT, bool TRI>
 __global__ void __launch_bounds__(HMC_THREADS) hmc_pass2_kernel(const __grid_constant__ HmcArgs a) {
     __shared__ double red[32];
     const int r = blockIdx.y, nmax = a.b.n_max, n = a.b.n_atoms[r];
@@ -532,7 +592,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass2_kernel(const __grid_con
         for (int k = sub; k < nn; k += lpa) {
             int j;
             double dx, dy, dz;
-            nb_vector(P, C, xi, yi, zi, j, dx, dy, dz);
+            nb_vector<TRI>(P, C, xi, yi, zi, j, dx, dy, dz);
             const double dj = dj_next;
             nb_advance(P, list + i, nmax, k, lpa, nn, x, y, z);
             if (POT == QMC_POT_EMT) dj_next = deds[P.e0 & 0xFFFFu];
@@ -712,12 +772,20 @@ inline void hmc_force_eval(HmcArgs &a, cudaStream_t s) {
     } else {
         hmc_build_kernel<<<g1, HMC_THREADS, 0, s>>>(a);
     }
-    if (a.pot.kind == QMC_POT_EMT) {
-        hmc_pass1_kernel<QMC_POT_EMT><<<gl, HMC_THREADS, 0, s>>>(a);
-        hmc_pass2_kernel<QMC_POT_EMT><<<gl, HMC_THREADS, 0, s>>>(a);
+    if (a.b.triclinic) {  // general cells: the list shifts count cell vectors
+        if (a.pot.kind == QMC_POT_EMT) {
+            hmc_pass1_kernel<QMC_POT_EMT, true><<<gl, HMC_THREADS, 0, s>>>(a);
+            hmc_pass2_kernel<QMC_POT_EMT, true><<<gl, HMC_THREADS, 0, s>>>(a);
+        } else {
+            hmc_pass1_kernel<QMC_POT_LJ, true><<<gl, HMC_THREADS, 0, s>>>(a);
+            hmc_pass2_kernel<QMC_POT_LJ, true><<<gl, HMC_THREADS, 0, s>>>(a);
+        }
+    } else if (a.pot.kind == QMC_POT_EMT) {
+        hmc_pass1_kernel<QMC_POT_EMT, false><<<gl, HMC_THREADS, 0, s>>>(a);
+        hmc_pass2_kernel<QMC_POT_EMT, false><<<gl, HMC_THREADS, 0, s>>>(a);
     } else {
-        hmc_pass1_kernel<QMC_POT_LJ><<<gl, HMC_THREADS, 0, s>>>(a);
-        hmc_pass2_kernel<QMC_POT_LJ><<<gl, HMC_THREADS, 0, s>>>(a);
+        hmc_pass1_kernel<QMC_POT_LJ, false><<<gl, HMC_THREADS, 0, s>>>(a);
+        hmc_pass2_kernel<QMC_POT_LJ, false><<<gl, HMC_THREADS, 0, s>>>(a);
     }
 }
 

@@ -436,7 +436,6 @@ int qmc_forces_full(const qmc_potential_t *pot, const qmc_batch_t *batch, double
     if (!pot || !forces) return fail(QMC_ERR_INVALID, "potential / forces is NULL");
     int rc;
     if ((rc = check_batch(batch, pot->kind))) return rc;
-    if (batch->triclinic) return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: the force kernels (Hamiltonian and ForceBias moves) take diagonal cells only");
     if (batch->n_replicas == 0) return QMC_OK;
     qmc::PotDev pd;
     if ((rc = make_potdev(pot, pd))) return rc;
@@ -457,7 +456,6 @@ int qmc_hmc(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_move
     if (!pot || !move) return fail(QMC_ERR_INVALID, "potential / move is NULL");
     int rc;
     if ((rc = check_batch(batch, pot->kind))) return rc;
-    if (batch->triclinic) return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: the force kernels (Hamiltonian and ForceBias moves) take diagonal cells only");
     if (move->type != QMC_MOVE_HMC || move->op != QMC_OP_VERLET)
         return fail(QMC_ERR_UNSUPPORTED, "qmc_hmc runs HamiltonianDisplacementMove + Verlet only");
     if (!batch->momenta || !batch->kinetic) return fail(QMC_ERR_INVALID, "Hamiltonian moves need batch.momenta and batch.kinetic");
@@ -486,7 +484,6 @@ int qmc_fbmc_step_v(const qmc_potential_t *pot, const qmc_batch_t *batch, double
     if (!pot || !forces) return fail(QMC_ERR_INVALID, "potential / forces is NULL");
     int rc;
     if ((rc = check_batch(batch, pot->kind))) return rc;
-    if (batch->triclinic) return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: the force kernels (Hamiltonian and ForceBias moves) take diagonal cells only");
     if (!delta_per_replica && !(delta > 0.0)) return fail(QMC_ERR_INVALID, "delta must be positive");
     if (batch->n_replicas == 0) return QMC_OK;
     qmc::PotDev pd;

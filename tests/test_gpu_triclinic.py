@@ -237,10 +237,71 @@ def test_grand_canonical_in_general_cells_matches_oracle(cuda_lib):
     assert int(mc.batch.status.max().item()) == 0
 
 
+@pytest.mark.parametrize("build_lanes", [1, 4, 32])
+@pytest.mark.parametrize("repeat", [3, 4])
+def test_forces_in_general_cells_match_oracle(cuda_lib, monkeypatch, build_lanes, repeat):
+    """The Verlet-list force kernels (csrc/hmc_kernel.cuh) in sheared cells: list shifts count cell vectors, the build rounds in
+    fractional coordinates; 108 atoms (several images per pair) and 256 atoms, atoms that wandered by whole cell vectors."""
+    from quansino_b200 import EMT, BatchedAtoms, ReplicaBatch
+
+    monkeypatch.setenv("QMC_HMC_BUILD_LANES", str(build_lanes))
+    R = 3
+    pos, cells, n = _sheared(repeat, R, seed=70 + repeat, strength=0.1, wander=0.1)
+    batch = ReplicaBatch(BatchedAtoms(pos.copy(), cells, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT()), EMT())
+    f = batch.forces_full().cpu().numpy().transpose(0, 2, 1)
+    e = batch.energy.cpu().numpy()
+    for r in range(R):
+        ref = capi.energy(emt_params("Cu"), pos[r], cells[r], (1, 1, 1), want_forces=True)
+        np.testing.assert_allclose(f[r], ref["forces"], rtol=1e-9, atol=1e-10)
+        assert abs(e[r] - ref["energy"]) <= 1e-10 * abs(ref["energy"])
+    assert int(batch.status.max().item()) == 0
+
+
+def test_hmc_and_force_bias_in_general_cells_match_oracle(cuda_lib):
+    """Hamiltonian moves (integrators/displacement.py:52-81, mc/criteria.py:117-140) and ForceBias steps (mc/fbmc.py:202-251) in
+    sheared cells, one shear per replica, against the oracle."""
+    from quansino_b200 import EMT, BatchedAtoms
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.integrators.displacement import fs
+    from quansino_b200.mc import ForceBias, HamiltonianCanonical
+    from quansino_b200.moves import HamiltonianDisplacementMove
+
+    R, n_attempts, n_steps = 4, 3, 12
+    pos, cells, n = _sheared(3, R, seed=81, strength=0.08, stdev=0.03)
+    temps = np.array([300.0, 500.0, 800.0, 1200.0])
+    atoms = BatchedAtoms(pos.copy(), cells, np.full(R, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+    mc = HamiltonianCanonical(
+        atoms, temperature=temps, max_cycles=1, seed=98, trace=True, resync_interval=0, steps_per_launch=n_attempts,
+        default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=2.0, max_steps=n_steps)),
+    )  # fmt: skip
+    mc.run(n_attempts)
+    tr, out, par = mc.last_trace, mc.download(), emt_params("Cu")
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cells[r], temperature=float(temps[r]), mass=63.546, momenta=np.zeros((n, 3)))
+        specs = [capi.MoveSpec(capi.MOVE_HMC, capi.OP_VERLET, dt=2.0 * fs, n_steps=n_steps)]
+        ref = capi.mc_run(par, rep, specs, 98, r, 0, n_attempts)
+        assert np.array_equal(tr["accepted"][r], ref["accepted"])
+        np.testing.assert_allclose(tr["delta"][r], ref["delta"], rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(out.positions[r], rep.positions, rtol=0, atol=1e-10)
+        np.testing.assert_allclose(out.momenta[r], rep.momenta, rtol=0, atol=1e-10)
+    assert tr["accepted"].sum() > 0
+    steps = 3
+    fb = ForceBias(BatchedAtoms(pos.copy(), cells, np.full(R, n, np.int32), "Cu", (True,) * 3, EMT()), delta=0.08, temperature=temps, seed=76)
+    fb.run(steps)
+    out, e_gpu = fb.download(), fb.context.last_potential_energy
+    for r in range(R):
+        p = pos[r].copy()
+        for s in range(steps):
+            e, _, _ = capi.fbmc_step(par, p, cells[r], (1, 1, 1), 63.546, float(temps[r]), 0.08, 76, r, s)
+        np.testing.assert_allclose(out.positions[r], p, rtol=0, atol=1e-11)
+        assert abs(e_gpu[r] - e) <= 1e-10 * abs(e)
+
+
 def test_general_cells_refuse_what_their_kernels_do_not_hold(cuda_lib):
     from quansino_b200 import EMT, BatchedAtoms, ReplicaBatch
-    from quansino_b200.mc import GrandCanonical, HamiltonianCanonical
-    from quansino_b200.moves import DisplacementMove, ExchangeMove, HamiltonianDisplacementMove
+    from quansino_b200.mc import GrandCanonical
+    from quansino_b200.moves import DisplacementMove, ExchangeMove
 
     pos, cells, n = _sheared(3, 2, seed=5)
     pos_pad = np.zeros((2, 128, 3))
@@ -251,10 +312,6 @@ def test_general_cells_refuse_what_their_kernels_do_not_hold(cuda_lib):
                         seed=1, default_displacement_move=DisplacementMove(np.arange(n)), default_exchange_move=ExchangeMove(np.full(n, -1)))  # fmt: skip
     with pytest.raises(NotImplementedError, match="triclinic"):
         gc.run(1)
-    atoms = BatchedAtoms(pos.copy(), cells, np.full(2, n, dtype=np.int32), "Cu", (True, True, True), EMT())
-    hmc = HamiltonianCanonical(atoms, temperature=300.0, seed=2, max_cycles=1, default_displacement_move=HamiltonianDisplacementMove())
-    with pytest.raises(NotImplementedError, match="triclinic"):
-        hmc.run(1)
     small = cells.copy()
     small[:, 0] *= 0.5  # a height below the cutoff
     with pytest.raises(NotImplementedError, match="height"):
