@@ -60,6 +60,52 @@ def test_energies_in_general_cells_match_oracle(cuda_lib, repeat, pot):
     assert int(batch.status.max().item()) == 0
 
 
+def test_ragged_batch_in_general_cells(cuda_lib):
+    """Replicas of different sizes in one padded batch (n_atoms 20 ... 108 of n_max 128, one of them EMPTY), each in its own sheared
+    cell: energies, then displacement + anisotropic cell moves, against the oracle replica by replica."""
+    from quansino_b200 import EMT, BatchedAtoms, ReplicaBatch, operations
+    from quansino_b200.mc import Isobaric
+    from quansino_b200.moves import CellMove, DisplacementMove
+
+    pos108, cells, n = _sheared(3, 5, seed=15, strength=0.08)
+    counts = np.array([108, 61, 20, 0, 97], dtype=np.int32)
+    n_max = 128
+    pos = np.zeros((5, n_max, 3))
+    for r in range(5):
+        pos[r, : counts[r]] = pos108[r, : counts[r]]
+    atoms = BatchedAtoms(pos.copy(), cells, counts, "Cu", (True, True, True), EMT())
+    batch = ReplicaBatch(atoms, EMT())
+    e = batch.energy_full().cpu().numpy()
+    par = emt_params("Cu")
+    for r in range(5):
+        ref = capi.energy(par, pos[r, : counts[r]], cells[r], (1, 1, 1))["energy"] if counts[r] else 0.0
+        assert abs(e[r] - ref) <= 1e-10 * max(1.0, abs(ref)), (r, e[r], ref)
+    n_attempts, p_cell = 80, 0.25
+    mc = Isobaric(atoms, temperature=700.0, pressure=200.0 * BAR, seed=444, trace=True, resync_interval=0, max_cycles=n_attempts,
+                  default_displacement_move=DisplacementMove(np.arange(n_max)), default_cell_move=CellMove(operations.AnisotropicDeformation(0.006)))  # fmt: skip
+    mc.moves["default_cell_move"].probability = p_cell
+    mc.moves["default_displacement_move"].probability = 1 - p_cell
+    mc.run(1)
+    tr, out = mc.last_trace, mc.download()
+    for r in range(5):
+        if counts[r] == 0:
+            assert np.all(tr["accepted"][r][tr["move"][r] == 0] == -1)  # nothing to displace: the move fails, like the reference's None
+            continue
+        rep = capi.Replica(positions=pos[r].copy(), cell=cells[r], n_atoms=int(counts[r]), temperature=700.0, pressure=200.0 * BAR)
+        lab = np.arange(n_max, dtype=np.int32)
+        lab[counts[r] :] = -1
+        specs = [
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.1, probability=1 - p_cell, labels=lab),
+            capi.MoveSpec(capi.MOVE_CELL, capi.OP_ANISOTROPIC, step=0.006, probability=p_cell),
+        ]
+        ref = capi.mc_run(par, rep, specs, 444, r, 0, n_attempts)
+        assert np.array_equal(tr["accepted"][r], ref["accepted"]), f"accept/reject sequence differs for replica {r}"
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10)
+        np.testing.assert_allclose(out.positions[r, : counts[r]], rep.positions[: counts[r]], rtol=0, atol=1e-10)
+        np.testing.assert_allclose(out.cell[r], rep.cell, rtol=0, atol=1e-12)
+    assert int(mc.batch.status.max().item()) == 0
+
+
 def test_partially_periodic_general_cell(cuda_lib):
     """A sheared slab: periodic along the two in-plane vectors only."""
     from quansino_b200 import EMT, BatchedAtoms, ReplicaBatch
