@@ -141,10 +141,11 @@ struct CellDev {
     double H[9], Hi[9];
 };
 
+template <bool TRI>
 __device__ inline bool hmc_cell(const HmcArgs &a, int r, double cut, CellDev &C) {
     bool ok = true;
-    C.tri = a.b.triclinic != 0;
-    if (C.tri) {
+    C.tri = TRI;
+    if (TRI) {
         double h[9];
         for (int q = 0; q < 9; ++q) h[q] = C.H[q] = a.b.cell[(size_t)r * 9 + q];
         const double det = h[0] * (h[4] * h[8] - h[5] * h[7]) - h[1] * (h[3] * h[8] - h[5] * h[6]) + h[2] * (h[3] * h[7] - h[4] * h[6]);
@@ -259,14 +260,93 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_init_kernel(const __grid_cons
 }
 
 // ---- neighbour list (brute force over tiles staged in shared memory; only when requested) ----------------------
-__global__ void __launch_bounds__(HMC_THREADS) hmc_build_kernel(const __grid_constant__ HmcArgs a) {
+// (diagonal cells: the round-1 code, untouched)
+__global__ void __launch_bounds__(HMC_THREADS) hmc_build_kernel_diag(const __grid_constant__ HmcArgs a) {
     __shared__ double sx[HMC_THREADS], sy[HMC_THREADS], sz[HMC_THREADS];
     const int r = blockIdx.y;
     if (a.w.flags[r] == 0) return;
     const int nmax = a.b.n_max, n = a.b.n_atoms[r];
     const double rl = a.pot.cut + a.skin, rl2 = rl * rl;
     CellDev C;
-    if (!hmc_cell(a, r, rl * (1.0 + 1e-9), C)) {
+    if (!hmc_cell<false>(a, r, rl * (1.0 + 1e-9), C)) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
+        return;
+    }
+    const double *x = a.w.x[a.cur] + (size_t)r * 3 * nmax, *y = x + nmax, *z = y + nmax;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool own = i < n;
+    const double xi = own ? x[i] : 0.0, yi = own ? y[i] : 0.0, zi = own ? z[i] : 0.0;
+    unsigned *list = a.w.list + (size_t)r * a.w.max_nb * nmax;
+    int k = 0, overflow = 0;
+    for (int j0 = 0; j0 < n; j0 += HMC_THREADS) {
+        __syncthreads();
+        const int jl = j0 + threadIdx.x;
+        if (jl < n) {
+            sx[threadIdx.x] = x[jl];
+            sy[threadIdx.x] = y[jl];
+            sz[threadIdx.x] = z[jl];
+        }
+        __syncthreads();
+        if (!own) continue;
+        const int jn = min(HMC_THREADS, n - j0);
+        for (int t = 0; t < jn; ++t) {
+            const int j = j0 + t;
+            if (j == i) continue;
+            double d0[3], d1[3], k0[3];
+            unsigned avail = 0;
+            const double pj[3] = {sx[t], sy[t], sz[t]}, pi[3] = {xi, yi, zi};
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                if (C.per[c]) {
+                    const double q = (pi[c] - pj[c]) * C.invL[c];
+                    k0[c] = (q + RINT_MAGIC) - RINT_MAGIC;
+                    d0[c] = fma(k0[c], C.L[c], pj[c]) - pi[c];
+                    d1[c] = d0[c] - copysign(C.L[c], d0[c]);
+                    if (fabs(d0[c]) > C.thr[c]) avail |= 1u << c;
+                } else {
+                    k0[c] = 0.0;
+                    d0[c] = d1[c] = pj[c] - pi[c];
+                }
+            }
+            unsigned c = 0;
+            while (true) {
+                const double dx = (c & 1u) ? d1[0] : d0[0], dy = (c & 2u) ? d1[1] : d0[1], dz = (c & 4u) ? d1[2] : d0[2];
+                if (dx * dx + dy * dy + dz * dz < rl2) {
+                    // integer image shift per axis: nearest image k0, second image k0 -+ 1
+                    int sh[3];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) sh[q] = (int)k0[q] - (((c >> q) & 1u) ? (d0[q] > 0.0 ? 1 : -1) : 0);
+                    if (abs(sh[0]) > 15 || abs(sh[1]) > 15 || abs(sh[2]) > 15 || k >= a.w.max_nb) {
+                        overflow = 1;
+                    } else {
+                        list[(size_t)k * nmax + i] = (unsigned)j | ((unsigned)(sh[0] + 16) << 16) | ((unsigned)(sh[1] + 16) << 21) | ((unsigned)(sh[2] + 16) << 26);
+                        ++k;
+                    }
+                }
+                if (c == avail) break;
+                c = ((c | (~avail & 7u)) + 1u) & avail;
+            }
+        }
+    }
+    if (own) {
+        a.w.nnb[(size_t)r * nmax + i] = k;
+        double *ref = a.w.ref + (size_t)r * 3 * nmax;
+        ref[i] = xi;
+        ref[nmax + i] = yi;
+        ref[2 * nmax + i] = zi;
+        if (overflow) atomicOr(a.b.status + r, (int)QMC_STATUS_LIST_OVERFLOW);
+    }
+}
+
+// (general cells: images through hmc_images / hmc_image_vector)
+__global__ void __launch_bounds__(HMC_THREADS) hmc_build_kernel_tri(const __grid_constant__ HmcArgs a) {
+    __shared__ double sx[HMC_THREADS], sy[HMC_THREADS], sz[HMC_THREADS];
+    const int r = blockIdx.y;
+    if (a.w.flags[r] == 0) return;
+    const int nmax = a.b.n_max, n = a.b.n_atoms[r];
+    const double rl = a.pot.cut + a.skin, rl2 = rl * rl;
+    CellDev C;
+    if (!hmc_cell<true>(a, r, rl * (1.0 + 1e-9), C)) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
         return;
     }
@@ -330,14 +410,121 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_build_kernel(const __grid_con
 // replicas).  The G lanes of an atom take G consecutive candidates per round; hits are compacted in lane order with one ballot
 // per round (and per further periodic image), so the entries come out in ascending candidate order: a fixed order, hence
 // bit-reproducible sums downstream.
-__global__ void __launch_bounds__(HMC_THREADS) hmc_build_split_kernel(const __grid_constant__ HmcArgs a) {
+// (diagonal cells: the round-1 code, untouched)
+__global__ void __launch_bounds__(HMC_THREADS) hmc_build_split_kernel_diag(const __grid_constant__ HmcArgs a) {
     __shared__ double sx[HMC_THREADS], sy[HMC_THREADS], sz[HMC_THREADS];
     for (int r = blockIdx.y; r < a.b.n_replicas; r += gridDim.y) {  // few grid rows: a launch without requests costs little
     if (a.w.flags[r] == 0) continue;
     const int nmax = a.b.n_max, n = a.b.n_atoms[r];
     const double rl = a.pot.cut + a.skin, rl2 = rl * rl;
     CellDev C;
-    if (!hmc_cell(a, r, rl * (1.0 + 1e-9), C)) {
+    if (!hmc_cell<false>(a, r, rl * (1.0 + 1e-9), C)) {
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
+        continue;
+    }
+    const int G = a.build_lanes, lane = threadIdx.x & 31, sub = lane & (G - 1);
+    // single-precision copy of the atom and the cell for the chunk test below (margins cover the rounding)
+    const float rlf = (float)rl + 0.02f, rlf2 = rlf * rlf;
+    const float *bbox = a.w.bbox + (size_t)r * ((nmax + 31) / 32) * 6;
+    const unsigned gmask = (G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u)) << (lane - sub), below = gmask & ((1u << lane) - 1u);
+    const double *x = a.w.x[a.cur] + (size_t)r * 3 * nmax, *y = x + nmax, *z = y + nmax;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+    const bool own = i < n;
+    const double pi[3] = {own ? x[i] : 0.0, own ? y[i] : 0.0, own ? z[i] : 0.0};
+    const float pif[3] = {(float)pi[0], (float)pi[1], (float)pi[2]}, Lf[3] = {(float)C.L[0], (float)C.L[1], (float)C.L[2]};
+    const float iLf[3] = {(float)C.invL[0], (float)C.invL[1], (float)C.invL[2]};
+    unsigned *list = a.w.list + (size_t)r * a.w.max_nb * nmax;
+    int k = 0, overflow = 0;  // k: entries of the atom so far, the same on its G lanes
+    for (int j0 = 0; j0 < n; j0 += HMC_THREADS) {
+        __syncthreads();
+        const int jl = j0 + threadIdx.x;
+        if (jl < n) {
+            sx[threadIdx.x] = x[jl];
+            sy[threadIdx.x] = y[jl];
+            sz[threadIdx.x] = z[jl];
+        }
+        __syncthreads();
+        const int jn = min(HMC_THREADS, n - j0);
+        for (int t0 = 0; t0 < jn; t0 += G) {
+            const int t = t0 + sub, j = j0 + t;
+            // chunk test: the 32 atoms around candidate j lie in a box (centre, half-width); when the nearest image of that box
+            // is farther than the list radius no candidate of this round can be listed (second images are farther still)
+            const float *bb = bbox + (size_t)((j0 + t0) >> 5) * 6;
+            float gap2 = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                float d = pif[q] - bb[q];
+                if (C.per[q]) d -= Lf[q] * rintf(d * iLf[q]);
+                const float gap = fabsf(d) - bb[3 + q];
+                gap2 += gap > 0.0f ? gap * gap : 0.0f;
+            }
+            bool active = own && t < jn && j != i && !(gap2 > rlf2);
+            double d0[3] = {0.0, 0.0, 0.0}, d1[3] = {0.0, 0.0, 0.0}, k0[3] = {0.0, 0.0, 0.0};
+            unsigned avail = 0, c = 0;
+            if (active) {
+                const double pj[3] = {sx[t], sy[t], sz[t]};
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    if (C.per[q]) {
+                        const double f = (pi[q] - pj[q]) * C.invL[q];
+                        k0[q] = (f + RINT_MAGIC) - RINT_MAGIC;
+                        d0[q] = fma(k0[q], C.L[q], pj[q]) - pi[q];
+                        d1[q] = d0[q] - copysign(C.L[q], d0[q]);
+                        if (fabs(d0[q]) > C.thr[q]) avail |= 1u << q;
+                    } else {
+                        d0[q] = d1[q] = pj[q] - pi[q];
+                    }
+                }
+            }
+            while (__any_sync(FULL, active)) {  // nearest image first, then the further images a short cell edge allows
+                bool hit = false;
+                int sh[3] = {0, 0, 0};
+                if (active) {
+                    const double dx = (c & 1u) ? d1[0] : d0[0], dy = (c & 2u) ? d1[1] : d0[1], dz = (c & 4u) ? d1[2] : d0[2];
+                    hit = dx * dx + dy * dy + dz * dz < rl2;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) sh[q] = (int)k0[q] - (((c >> q) & 1u) ? (d0[q] > 0.0 ? 1 : -1) : 0);
+                    if (hit && (abs(sh[0]) > 15 || abs(sh[1]) > 15 || abs(sh[2]) > 15)) {
+                        overflow = 1;
+                        hit = false;
+                    }
+                }
+                const unsigned hits = __ballot_sync(FULL, hit) & gmask;
+                if (hit) {
+                    const int slot = k + __popc(hits & below);
+                    if (slot < a.w.max_nb)
+                        list[(size_t)slot * nmax + i] = (unsigned)j | ((unsigned)(sh[0] + 16) << 16) | ((unsigned)(sh[1] + 16) << 21) | ((unsigned)(sh[2] + 16) << 26);
+                    else
+                        overflow = 1;
+                }
+                k += __popc(hits);
+                if (active) {
+                    if (c == avail) active = false;
+                    else c = ((c | (~avail & 7u)) + 1u) & avail;
+                }
+            }
+        }
+    }
+    if (own && sub == 0) {
+        a.w.nnb[(size_t)r * nmax + i] = min(k, a.w.max_nb);
+        double *ref = a.w.ref + (size_t)r * 3 * nmax;
+        ref[i] = pi[0];
+        ref[nmax + i] = pi[1];
+        ref[2 * nmax + i] = pi[2];
+    }
+    if (overflow) atomicOr(a.b.status + r, (int)QMC_STATUS_LIST_OVERFLOW);
+    }
+}
+
+// (general cells: images through hmc_images / hmc_image_vector)
+__global__ void __launch_bounds__(HMC_THREADS) hmc_build_split_kernel_tri(const __grid_constant__ HmcArgs a) {
+    __shared__ double sx[HMC_THREADS], sy[HMC_THREADS], sz[HMC_THREADS];
+    for (int r = blockIdx.y; r < a.b.n_replicas; r += gridDim.y) {  // few grid rows: a launch without requests costs little
+    if (a.w.flags[r] == 0) continue;
+    const int nmax = a.b.n_max, n = a.b.n_atoms[r];
+    const double rl = a.pot.cut + a.skin, rl2 = rl * rl;
+    CellDev C;
+    if (!hmc_cell<true>(a, r, rl * (1.0 + 1e-9), C)) {
         if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(a.b.status + r, (int)QMC_STATUS_CELL_TOO_SMALL);
         continue;
     }
@@ -520,7 +707,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass1_kernel(const __grid_con
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / lpa;
     const bool own = i < n;
     CellDev C;
-    hmc_cell(a, r, a.pot.cut_pre, C);
+    hmc_cell<TRI>(a, r, a.pot.cut_pre, C);
     const double *x = a.w.x[a.cur] + (size_t)r * 3 * nmax, *y = x + nmax, *z = y + nmax;
     const unsigned *list = a.w.list + (size_t)r * a.w.max_nb * nmax;
     double s1 = 0.0, s2 = 0.0;
@@ -576,7 +763,7 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass2_kernel(const __grid_con
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) / lpa;
     const bool own = i < n;
     CellDev C;
-    hmc_cell(a, r, a.pot.cut_pre, C);
+    hmc_cell<TRI>(a, r, a.pot.cut_pre, C);
     const size_t base = (size_t)r * 3 * nmax;
     const double *x = a.w.x[a.cur] + base, *y = x + nmax, *z = y + nmax;
     const unsigned *list = a.w.list + (size_t)r * a.w.max_nb * nmax;
@@ -768,9 +955,11 @@ inline void hmc_force_eval(HmcArgs &a, cudaStream_t s) {
         const int rows = R < 8 ? R : 8;
         const dim3 gb((N * a.build_lanes + HMC_THREADS - 1) / HMC_THREADS, rows), gq((N + HMC_THREADS - 1) / HMC_THREADS, rows);
         hmc_bbox_kernel<<<gq, HMC_THREADS, 0, s>>>(a);
-        hmc_build_split_kernel<<<gb, HMC_THREADS, 0, s>>>(a);
+        if (a.b.triclinic) hmc_build_split_kernel_tri<<<gb, HMC_THREADS, 0, s>>>(a);
+        else hmc_build_split_kernel_diag<<<gb, HMC_THREADS, 0, s>>>(a);
     } else {
-        hmc_build_kernel<<<g1, HMC_THREADS, 0, s>>>(a);
+        if (a.b.triclinic) hmc_build_kernel_tri<<<g1, HMC_THREADS, 0, s>>>(a);
+        else hmc_build_kernel_diag<<<g1, HMC_THREADS, 0, s>>>(a);
     }
     if (a.b.triclinic) {  // general cells: the list shifts count cell vectors
         if (a.pot.kind == QMC_POT_EMT) {
