@@ -103,6 +103,8 @@ def restore_simulation(data: dict[str, Any] | IO | str | Path, calc, device="cud
         kw["temperature"] = np.array(st["temperature"])
     if "Isobaric" in names:
         kw["pressure"] = float(ctx["pressure"])
+    if "Isotension" in names and "external_stress" in ctx:
+        kw["external_stress"] = np.array(ctx["external_stress"], dtype=float).reshape(3, 3)
     if "GrandCanonical" in names:
         kw["chemical_potential"] = float(ctx["chemical_potential"])
         kw["number_of_exchange_particles"] = np.array(st["n_exchange"])
@@ -113,7 +115,9 @@ def restore_simulation(data: dict[str, Any] | IO | str | Path, calc, device="cud
     sim = cls(atoms, **kw)
     if "GrandCanonical" in names and "accessible_volume" in ctx:
         sim.accessible_volume = float(ctx["accessible_volume"])
-    for name, stored in data.get("moves", {}).items():
+    stored_moves = data.get("moves", {})
+    for name in data.get("move_order", list(stored_moves)):  # (JSON objects come back key-sorted: the list keeps the table order)
+        stored = stored_moves[name]
         ms = MoveStorage.from_dict(stored)
         sim.add_move(ms.move, criteria=ms.criteria, name=name, interval=ms.interval, probability=ms.probability, minimum_count=ms.minimum_count)
     sim.load_state(data)

@@ -96,7 +96,8 @@ class DeformationContext(DisplacementContext):
         return self.batch.cell.cpu().numpy().reshape(-1, 3, 3)
 
     def to_dict(self) -> dict[str, Any]:
-        return {**super().to_dict(), "pressure": self.pressure, "last_cell": self.last_cell}
+        # (external_stress is not in the reference's dictionary, `mc/contexts.py:260-272`; without it an Isotension run cannot restart)
+        return {**super().to_dict(), "pressure": self.pressure, "last_cell": self.last_cell, "external_stress": np.asarray(self.external_stress)}
 
 
 class ExchangeContext(DisplacementContext):

@@ -464,6 +464,7 @@ class MonteCarlo:
             "attributes": {"step_count": self.step_count, "attempt_counter": self.attempt_counter, "primed": self._primed},
             "context": self.context.to_dict(),
             "moves": {name: st.to_dict() for name, st in self.moves.items()},
+            "move_order": list(self.moves),  # the files are written with sorted keys; the ORDER of the moves is part of the state
             "state": state,
             "labels": labels,
         }  # fmt: skip
@@ -473,7 +474,7 @@ class MonteCarlo:
         like the one that wrote the restart (same class, moves in the same order, same batch shape)."""
         if data.get("name") != self.__class__.__name__:
             raise ValueError(f"restart data of a {data.get('name')} cannot be loaded into a {self.__class__.__name__}")
-        if list(data.get("moves", {})) != list(self.moves):
+        if list(data.get("move_order", data.get("moves", {}))) != list(self.moves):
             raise ValueError("the restart data was written with a different set of moves")
         st, b = data["state"], self.batch
         pos = np.asarray(st["positions"], dtype=np.float64)

@@ -108,6 +108,11 @@ class CompositeExchangeMove(CompositeMove):
     def is_identity(self, n_atoms) -> bool:
         return False
 
+    def to_dict(self):
+        d = super().to_dict()
+        d["attributes"] = {"bias_towards_insert": self.bias_towards_insert}  # read back by CompositeMove.from_dict
+        return d
+
     def lower_chain(self) -> list:
         """ONE ``qmc_move_t``: an exchange entry with ``repeat`` = number of sub-moves (include/quansino_b200.h)."""
         self._check()

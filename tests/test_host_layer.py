@@ -366,3 +366,10 @@ def test_composite_exchange_move_algebra_and_lowering():
         (a + ExchangeMove(np.full(4, -1), operations.TranslationRotation())).lower_chain()
     with pytest.raises(NotImplementedError, match="at most"):
         (a * (_lib.QMC_MAX_SUBMOVES + 1)).lower_chain()
+    # serialisation through the registry keeps the composite's own bias
+    from quansino_b200.registry import get_class
+
+    d = four.to_dict()
+    back = get_class(d["name"]).from_dict(d)
+    assert isinstance(back, CompositeExchangeMove) and len(back) == 4 and back.bias_towards_insert == 0.25
+    assert back.lower_chain()[0].repeat == 4

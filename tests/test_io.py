@@ -214,3 +214,42 @@ def test_grand_canonical_restart_keeps_integer_state(cuda_lib, tmp_path):
     assert np.array_equal(straight.counters(), second.counters())
     assert np.array_equal(straight.batch.energy.cpu().numpy(), second.batch.energy.cpu().numpy())
     assert (a.n_atoms != n).any()  # the run did insert / delete atoms
+
+
+@pytest.mark.gpu
+def test_isotension_restart_in_a_general_cell(cuda_lib, tmp_path):
+    """An NST run with ShapeDeformation (general cells, IsotensionCriteria): 4 steps straight == 2 steps, restart file, restored
+    through the registry (driver class, moves, criteria, external stress, the triclinic cells), 2 more steps -- same bits."""
+    from quansino_b200 import EMT, BatchedAtoms, operations
+    from quansino_b200.io import restore_simulation
+    from quansino_b200.mc import Isotension
+    from quansino_b200.moves import CellMove, DisplacementMove
+    from quansino_b200.systems import fcc_cubic, rattle
+
+    pos0, cell = fcc_cubic("Cu", 3)
+    n = len(pos0)
+    pos = np.stack([rattle(pos0, 0.05, 40 + r) for r in range(3)])
+    stress = np.array([[2e-3, 5e-4, 0.0], [5e-4, -1e-3, 0.0], [0.0, 0.0, 1e-3]])
+
+    def make(**kw):
+        atoms = BatchedAtoms(pos.copy(), cell, np.full(3, n, dtype=np.int32), "Cu", (True, True, True), EMT())
+        mc = Isotension(atoms, temperature=600.0, pressure=1e-4, external_stress=stress, seed=17, max_cycles=40, resync_interval=0,
+                        default_displacement_move=DisplacementMove(np.arange(n)), default_cell_move=CellMove(operations.ShapeDeformation(0.01)), **kw)  # fmt: skip
+        mc.moves["default_cell_move"].probability = 0.3
+        mc.moves["default_displacement_move"].probability = 0.7
+        return mc
+
+    straight = make()
+    straight.run(4)
+    ref = straight.download()
+    assert straight.batch.triclinic and np.abs(ref.cell[:, 0, 1]).max() > 1e-4  # the cells did leave the diagonal form
+    first = make(restart_file=tmp_path / "nst.json", logging_interval=2, logging_mode="w")
+    first.run(2)
+    first.close()
+    again = restore_simulation(tmp_path / "nst.json", EMT(), resync_interval=0)
+    assert type(again).__name__ == "Isotension" and np.array_equal(again.external_stress, stress) and again.step_count == 2
+    assert type(again.moves["default_cell_move"].criteria).__name__ == "IsotensionCriteria"
+    again.run(2)
+    out = again.download()
+    assert np.array_equal(out.positions, ref.positions) and np.array_equal(out.cell, ref.cell)
+    assert np.array_equal(again.batch.energy.cpu().numpy(), straight.batch.energy.cpu().numpy())
