@@ -372,9 +372,11 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
     if (!inst) return fail(QMC_ERR_UNSUPPORTED, "more than 1024 atoms per replica do not fit the warp-per-replica sweep kernel");
     if (batch->triclinic) {
         // general cells (csrc/sweep_tri.cuh): plain single-atom displacement moves and cell moves
-        if (any_composite || a.n_forced > 0)
-            return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: composite moves, label groups and forced moves are not available on the GPU path");
+        if (a.n_forced > 0)
+            return fail(QMC_ERR_UNSUPPORTED, "general (triclinic) cells: forced moves are not available on the GPU path");
         for (int m = 0; m < n_moves; ++m) {
+            if (moves[m].chain || moves[m].repeat > 1)  // (composite OPERATIONS, n_extra_ops, are fine: they only add translations)
+                return fail(QMC_ERR_UNSUPPORTED, "move %d: general (triclinic) cells: composite moves and label groups are not available on the GPU path", m);
             if (moves[m].type == QMC_MOVE_DISPLACEMENT && moves[m].op != QMC_OP_BALL && moves[m].op != QMC_OP_BOX && moves[m].op != QMC_OP_SPHERE)
                 return fail(QMC_ERR_UNSUPPORTED, "move %d: general (triclinic) cells take Ball / Box / Sphere displacements of single atoms", m);
             if (moves[m].type == QMC_MOVE_EXCHANGE && (moves[m].op != QMC_OP_TRANSLATION || batch->n_exchange_atoms > 1))

@@ -410,6 +410,20 @@ __global__ void __launch_bounds__(tri_warps<Layout<POT, NS>>() * 32) sweep_tri_k
                 const int i = lab ? select_labelled(lab, R.n, idx) : idx;
                 double t[3];
                 propose_translation(mv.op, mv.step, D.o0, D.o1, D.o2, t);
+                // CompositeOperation (operations/composite.py:58-73), as in csrc/sweep_kernel.cuh: the further operations draw the
+                // attempt's extra draws e = 0, 1, ... = block 64 + e / 2, half e & 1; translations added in list order
+                for (int xo = 0, e = 0; xo < mv.n_extra_ops; ++xo) {
+                    double d0, d1;
+                    uniform_pair(key, attempt, grep, 64u + (uint32_t)((e + lane) >> 1), d0, d1);
+                    const double mine = ((e + lane) & 1) ? d1 : d0;  // lane j holds extra draw e + j
+                    const double x0 = __shfl_sync(FULL, mine, 0), x1 = __shfl_sync(FULL, mine, 1), x2 = __shfl_sync(FULL, mine, 2);
+                    double t2[3];
+                    propose_translation(mv.extra_op[xo], mv.extra_step[xo], x0, x1, x2, t2);
+                    t[0] = __dadd_rn(t[0], t2[0]);
+                    t[1] = __dadd_rn(t[1], t2[1]);
+                    t[2] = __dadd_rn(t[2], t2[2]);
+                    e += mv.extra_op[xo] == QMC_OP_SPHERE ? 2 : 3;
+                }
                 const double po[3] = {R.x(i), R.y(i), R.z(i)};
                 const double pn[3] = {po[0] + t[0], po[1] + t[1], po[2] + t[2]};
                 const Trial T = local_delta_move<LY>(pot, R, C, lane, lt, R.n, i, po, pn, status);
