@@ -996,7 +996,9 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
              * ONE new label (moves/displacement.py:244-249), so that later deletions take them out together. */
             const int k_sub = mv->repeat > 1 ? mv->repeat : 1;
             const int composite = k_sub > 1;
-            const int molecular = composite || n_mol > 1 || mv->op == QO_OP_TRANSLATION_ROTATION;
+            /* (chain bit 3: the caller's labels hold GROUPS -- `where(labels == label)`, moves/exchange.py:127, takes out every atom of
+             * the drawn label whatever the size of exchange_atoms) */
+            const int molecular = composite || n_mol > 1 || mv->op == QO_OP_TRANSLATION_ROTATION || (mv->chain & 8);
             int n_gone = 0;
             if (composite && (n_mol > 1 || mv->op != QO_OP_TRANSLATION || !mv->labels)) { rc = -1; goto done; }
             if (composite && is_addition) {

@@ -174,3 +174,207 @@ def test_random_case_matches_oracle(cuda_lib, seed):
             assert np.array_equal(mc.labels("default_exchange_move")[r, :m], lx[:m])
             assert np.array_equal(mc.labels("default_displacement_move")[r, :m], ld[:m])
     assert int(mc.batch.status.max().item()) == 0, c
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# second family: grand-canonical tables with molecules, composite exchange moves and the label groups they leave behind
+# ---------------------------------------------------------------------------------------------------------------------------
+def _gc_case(seed):
+    rng = np.random.default_rng(30_000 + seed)
+    c = {"seed": seed, "R": 3, "n0": int(rng.integers(10, 26)), "L": float(rng.uniform(11.0, 14.0)), "n_max": 96}
+    c["pbc"] = bool(rng.random() < 0.6)
+    c["eps"], c["sigma"] = float(rng.uniform(0.03, 0.08)), float(rng.uniform(2.3, 2.7))
+    c["temperature"] = float(rng.uniform(300.0, 600.0))
+    c["mu"] = float(rng.uniform(-0.6, -0.4))
+    c["kind"] = str(rng.choice(["single", "molecule", "molecule", "composite", "composite"]))
+    c["k"] = int(rng.integers(2, 4))  # atoms per molecule / sub-moves per composite
+    c["rotate"] = bool(c["kind"] == "molecule" and rng.random() < 0.7)
+    mol = np.zeros((c["k"], 3))
+    for q in range(1, c["k"]):
+        v = rng.normal(size=3)
+        mol[q] = mol[q - 1] + v / np.linalg.norm(v) * rng.uniform(2.6, 3.0)
+    c["mol"] = mol.tolist()
+    c["deletable"] = bool(rng.random() < 0.5)  # the initial atoms carry exchange labels of their own
+    c["bias"] = float(rng.choice([0.5, 0.5, 0.35, 0.65])) if c["kind"] != "composite" else 0.5
+    c["p_disp"] = float(rng.uniform(0.3, 0.6))
+    c["disp_step"] = float(rng.uniform(0.05, 0.25))
+    c["n_attempts"] = 160
+    return c
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_grand_canonical_case_matches_oracle(cuda_lib, seed):
+    from quansino_b200 import BatchedAtoms, LennardJones, operations
+    from quansino_b200.mc import GrandCanonical
+    from quansino_b200.mc.criteria import GrandCanonicalCriteria
+    from quansino_b200.moves import DisplacementMove, ExchangeMove
+
+    c = _gc_case(seed)
+    rng = np.random.default_rng(40_000 + seed)
+    R, n0, n_max, L = c["R"], c["n0"], c["n_max"], c["L"]
+    cell = np.eye(3) * L
+    pbc = (c["pbc"],) * 3
+    pos = np.zeros((R, n_max, 3))
+    grid = np.array([[i, j, k] for i in range(3) for j in range(3) for k in range(3)], dtype=float)
+    for r in range(R):
+        pos[r, :n0] = ((grid[rng.permutation(27)[:n0]] + 0.5) / 3.0 + rng.normal(scale=0.02, size=(n0, 3))) * L
+    calc = LennardJones(sigma=c["sigma"], epsilon=c["eps"], rc=6.0)
+    par = LJParams(sigma=c["sigma"], epsilon=c["eps"], rc=6.0)
+    mass1 = 195.084
+    molecular = c["kind"] == "molecule"
+    mol = np.array(c["mol"]) if molecular else np.zeros((1, 3))
+    lab_x = np.arange(n0) if c["deletable"] else np.full(n0, -1)
+    atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n0, dtype=np.int32), "Pt", pbc, calc)
+    op = operations.TranslationRotation() if c["rotate"] else operations.Translation()
+    mc = GrandCanonical(
+        atoms, exchange_atoms=("Pt", mol), temperature=c["temperature"], chemical_potential=c["mu"],
+        number_of_exchange_particles=n0 if c["deletable"] else 0, max_cycles=c["n_attempts"], seed=777 + seed, trace=True, resync_interval=0,
+        default_displacement_move=DisplacementMove(np.arange(n0), operations.Ball(c["disp_step"])),
+    )  # fmt: skip
+    if c["kind"] == "composite":
+        exch = ExchangeMove(lab_x.copy())
+        for _ in range(c["k"] - 1):
+            exch = exch + ExchangeMove(lab_x.copy())
+    else:
+        exch = ExchangeMove(lab_x.copy(), op, bias_towards_insert=c["bias"])
+    mc.add_move(exch, criteria=GrandCanonicalCriteria(), name="default_exchange_move")
+    mc.accessible_volume = L**3
+    mc.moves["default_displacement_move"].probability = c["p_disp"]
+    mc.moves["default_exchange_move"].probability = 1 - c["p_disp"]
+    mc.run(1)
+    tr1 = {k: v.copy() for k, v in mc.last_trace.items()}
+    mc.run(1)
+    tr = {k: np.concatenate([tr1[k], mc.last_trace[k]], axis=1) for k in ("move", "accepted", "energy", "moved")}
+    out, n_ex = mc.download(), mc.number_of_exchange_particles
+    labels_d, labels_x = mc.labels("default_displacement_move"), mc.labels("default_exchange_move")
+    changes: dict[int, int] = {}
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, pbc=tuple(int(b) for b in pbc), n_atoms=n0, temperature=c["temperature"],
+                           mass=mass1, chemical_potential=c["mu"], exchange_mass=mass1 * len(mol), n_exchange=n0 if c["deletable"] else 0,
+                           accessible_volume=L**3, exchange_mol=mol if molecular else None)  # fmt: skip
+        ld = np.full(n_max, -1, np.int32)
+        ld[:n0] = np.arange(n0)
+        lx = np.full(n_max, -1, np.int32)
+        lx[:n0] = lab_x
+        specs = [
+            capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=c["disp_step"], probability=c["p_disp"], labels=ld),
+            capi.MoveSpec(capi.MOVE_EXCHANGE, capi.OP_TRANSLATION_ROTATION if c["rotate"] else capi.OP_TRANSLATION, probability=1 - c["p_disp"],
+                          labels=lx, repeat=c["k"] if c["kind"] == "composite" else 1, bias_insert=c["bias"]),
+        ]  # fmt: skip
+        ref = capi.mc_run(par, rep, specs, 777 + seed, r, 0, 2 * c["n_attempts"])
+        assert np.array_equal(tr["move"][r], ref["move"]), c
+        assert np.array_equal(tr["accepted"][r], ref["accepted"]), f"accept/reject sequence differs, replica {r}, case {c}"
+        assert np.array_equal(tr["moved"][r], ref["moved"]), c
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10, err_msg=str(c))
+        m = rep.n_atoms
+        assert out.n_atoms[r] == m and n_ex[r] == rep.n_exchange, c
+        assert np.array_equal(labels_d[r, :m], ld[:m]) and np.array_equal(labels_x[r, :m], lx[:m]), c
+        np.testing.assert_allclose(out.positions[r, :m], rep.positions[:m], rtol=0, atol=1e-10, err_msg=str(c))
+        d_n = np.diff(np.concatenate([[n0], ref["n_atoms"]]))
+        for v, cnt in zip(*np.unique(d_n, return_counts=True)):
+            changes[int(v)] = changes.get(int(v), 0) + int(cnt)
+    assert int(mc.batch.status.max().item()) == 0, c
+    assert sum(v for k, v in changes.items() if k != 0) > 0, (c, changes)  # something was inserted or deleted
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# third family: label groups in arbitrary order with the rigid-body operations, hybrid NPT composites, Hamiltonian moves
+# ---------------------------------------------------------------------------------------------------------------------------
+def _misc_case(seed):
+    rng = np.random.default_rng(50_000 + seed)
+    c = {"seed": seed, "R": 3, "kind": str(rng.choice(["groups", "groups", "hybrid", "hmc", "hmc"]))}
+    c["pot"] = str(rng.choice(["emt", "emt", "lj"]))
+    c["repeat"] = int(rng.choice([3, 3, 4]))
+    c["slab"] = bool(c["kind"] != "hybrid" and rng.random() < 0.3)
+    c["sheared"] = bool(c["kind"] == "hmc" and not c["slab"] and rng.random() < 0.5)
+    c["temperature"] = float(rng.choice([300.0, 800.0, 1500.0]))
+    c["step"] = float(rng.uniform(0.04, 0.15))
+    c["group_op"] = str(rng.choice(["Rotation", "Translation", "TranslationRotation"]))
+    c["k"] = int(rng.integers(2, 5))
+    c["cell_max"] = float(rng.uniform(0.003, 0.01))
+    c["p"] = float(rng.uniform(0.3, 0.7))
+    c["dt_fs"] = float(rng.uniform(0.5, 3.0))
+    c["n_steps"] = int(rng.integers(3, 16))
+    c["n_attempts"] = 3 if c["kind"] == "hmc" else 70
+    return c
+
+
+@pytest.mark.parametrize("seed", range(18))
+def test_random_groups_hybrid_hmc_case_matches_oracle(cuda_lib, seed):
+    from quansino_b200 import EMT, BatchedAtoms, LennardJones, operations
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.integrators.displacement import fs
+    from quansino_b200.mc import Canonical, HamiltonianCanonical, Isobaric
+    from quansino_b200.mc.criteria import IsobaricCriteria
+    from quansino_b200.moves import CellMove, DisplacementMove, HamiltonianDisplacementMove
+
+    c = _misc_case(seed)
+    rng = np.random.default_rng(60_000 + seed)
+    pos0, cell0 = fcc_cubic("Cu", c["repeat"])
+    n, R = len(pos0), c["R"]
+    cells = np.repeat(cell0[None], R, axis=0)
+    pbc = (True, True, not c["slab"])
+    pos = np.zeros((R, n, 3))
+    for r in range(R):
+        p = rattle(pos0, 0.04, 7000 + 10 * seed + r)
+        if c["sheared"]:
+            S = np.eye(3) + rng.uniform(-0.07, 0.07, (3, 3)) * (1 - np.eye(3))
+            cells[r] = S @ cell0
+            p = np.linalg.solve(cell0.T, p.T).T @ cells[r]
+        if c["slab"]:
+            cells[r, 2, 2] = cell0[2, 2] * 1.7
+        pos[r] = p
+    lj = c["pot"] == "lj"
+    calc = LennardJones(sigma=2.3, epsilon=0.2, rc=6.0) if lj else EMT()
+    par = LJParams(sigma=2.3, epsilon=0.2, rc=6.0) if lj else emt_params("Cu")
+    atoms = BatchedAtoms(pos.copy(), cells, np.full(R, n, dtype=np.int32), "Cu", pbc, calc)
+    common = dict(temperature=c["temperature"], seed=999 + seed, trace=True, resync_interval=0)
+    if c["kind"] == "groups":
+        # groups of 1 .. 4 atoms scattered over the index range, label VALUES in arbitrary order, some atoms immovable (-1)
+        ids = rng.permutation(np.repeat(np.arange(n // 2), 2))[:n]
+        values = rng.permutation(3 * n)[: n // 2]
+        lab = np.where(rng.random(n) < 0.1, -1, values[ids]).astype(np.int32)
+        mc = Canonical(atoms, max_cycles=c["n_attempts"], default_displacement_move=DisplacementMove(lab, operations.Ball(c["step"])), **common)
+        mc.add_move(DisplacementMove(lab, getattr(operations, c["group_op"])()), name="rigid", probability=1.0)
+        mc.moves["default_displacement_move"].probability = c["p"]
+        mc.moves["rigid"].probability = 1 - c["p"]
+        op2 = {"Rotation": capi.OP_ROTATION, "Translation": capi.OP_TRANSLATION, "TranslationRotation": capi.OP_TRANSLATION_ROTATION}[c["group_op"]]
+        specs = lambda: [capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=c["step"], probability=c["p"], labels=lab.copy()),
+                         capi.MoveSpec(capi.MOVE_DISPLACEMENT, op2, probability=1 - c["p"], labels=lab.copy())]  # noqa: E731  # fmt: skip
+        state = {}
+    elif c["kind"] == "hybrid":
+        lab = np.arange(n)
+        mc = Isobaric(atoms, pressure=300.0 * BAR, max_cycles=c["n_attempts"], default_displacement_move=DisplacementMove(lab, operations.Ball(c["step"])), **common)
+        hybrid = DisplacementMove(lab, operations.Ball(0.5 * c["step"])) * c["k"] + CellMove(operations.IsotropicDeformation(c["cell_max"]))
+        mc.add_move(hybrid, criteria=IsobaricCriteria(), name="hybrid", probability=1.0)
+        mc.moves["default_displacement_move"].probability = c["p"]
+        mc.moves["hybrid"].probability = 1 - c["p"]
+        labs = np.arange(n, dtype=np.int32)
+        specs = lambda: [capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=c["step"], probability=c["p"], labels=labs.copy()),
+                         capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.5 * c["step"], probability=1 - c["p"], labels=labs.copy(), repeat=c["k"], chain=3),
+                         capi.MoveSpec(capi.MOVE_CELL, capi.OP_ISOTROPIC, step=c["cell_max"], probability=1 - c["p"], chain=2)]  # noqa: E731  # fmt: skip
+        state = {"pressure": 300.0 * BAR}
+    else:
+        mc = HamiltonianCanonical(atoms, max_cycles=1, steps_per_launch=1,
+                                  default_displacement_move=HamiltonianDisplacementMove(operation=Verlet(dt=c["dt_fs"], max_steps=c["n_steps"])), **common)  # fmt: skip
+        specs = lambda: [capi.MoveSpec(capi.MOVE_HMC, capi.OP_VERLET, dt=c["dt_fs"] * fs, n_steps=c["n_steps"])]  # noqa: E731
+        state = {"mass": 63.546}
+    traces = []
+    launches = c["n_attempts"] if c["kind"] == "hmc" else 2
+    for _ in range(launches):
+        mc.run(1)
+        traces.append({k: v.copy() for k, v in mc.last_trace.items()})
+    tr = {k: np.concatenate([t[k] for t in traces], axis=1) for k in ("accepted", "energy")}
+    out = mc.download()
+    total = launches * (1 if c["kind"] == "hmc" else c["n_attempts"])
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cells[r], pbc=tuple(int(b) for b in pbc), temperature=c["temperature"],
+                           momenta=np.zeros((n, 3)) if c["kind"] == "hmc" else None, **state)  # fmt: skip
+        ref = capi.mc_run(par, rep, specs(), 999 + seed, r, 0, total)
+        assert np.array_equal(tr["accepted"][r], ref["accepted"]), f"accept/reject sequence differs, replica {r}, case {c}"
+        np.testing.assert_allclose(tr["energy"][r], ref["energy"], rtol=1e-10, atol=1e-10, err_msg=str(c))
+        np.testing.assert_allclose(out.positions[r], rep.positions, rtol=0, atol=1e-9 if c["kind"] == "hmc" else 1e-10, err_msg=str(c))
+        np.testing.assert_allclose(out.cell[r], rep.cell, rtol=1e-13, atol=0, err_msg=str(c))
+        if c["kind"] == "hmc":
+            np.testing.assert_allclose(out.momenta[r], rep.momenta, rtol=0, atol=1e-9, err_msg=str(c))
+    assert int(mc.batch.status.max().item()) == 0, c
