@@ -166,7 +166,9 @@ class MonteCarlo:
             len(np.atleast_2d(self.batch.exchange_mol)) > 1
             or any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE and getattr(self.moves[n].move.operation, "op_code", -1) == _lib.OP_TRANSLATION_ROTATION for n in names)
             or any(self.moves[n].move.move_type == _lib.MOVE_EXCHANGE and len(getattr(self.moves[n].move, "moves", ())) > 1 for n in names)
-        )  # fmt: skip  (a CompositeExchangeMove gives the atoms of one insertion ONE label: groups, too)
+            or any(self._has_label_groups(self.moves[n].move) for n in names)
+        )  # fmt: skip  (a CompositeExchangeMove gives the atoms of one insertion ONE label: groups, too; and so are label groups
+        # the caller defines himself -- `where(labels == label)` displaces / deletes all their atoms, moves/exchange.py:127)
         entries, keep, slots = [], [], {}
         cell_criteria = {type(self.moves[n].criteria).__name__ for n in names if self.moves[n].move.move_type == _lib.MOVE_CELL}
         if len(cell_criteria) > 1:
@@ -216,7 +218,7 @@ class MonteCarlo:
                 grouped = grouped or any(c.type == _lib.MOVE_DISPLACEMENT and c.op in (_lib.OP_ROTATION, _lib.OP_TRANSLATION, _lib.OP_TRANSLATION_ROTATION) for c in chain)
                 if molecular:
                     if len(chain) > 1 or (chain[0].repeat > 1 and m.type != _lib.MOVE_EXCHANGE) or m.n_extra_ops:
-                        raise NotImplementedError("composite moves next to a molecular exchange move are not available on the GPU path")
+                        raise NotImplementedError("composite moves next to a molecular exchange move or label groups are not available on the GPU path")
                     m.chain = 8  # run-coded label groups
                     grouped = False
                 if grouped and (any_exchange or len(chain) > 1 or chain[0].repeat > 1 or m.type != _lib.MOVE_DISPLACEMENT or m.n_extra_ops):
@@ -241,6 +243,22 @@ class MonteCarlo:
         self._slots = slots
         self._lowered = (tuple(names), arr, keep)  # keeps the ctypes array and the label tensors alive during the launch
         return arr, keep
+
+    @staticmethod
+    def _has_label_groups(move) -> bool:
+        """Whether a displacement / exchange move selects GROUPS: a non-negative label carried by several atoms, or a rigid-body
+        operation (Rotation / Translation / TranslationRotation of a displacement move)."""
+        for m in getattr(move, "moves", [move]):
+            if getattr(m, "move_type", None) not in (_lib.MOVE_DISPLACEMENT, _lib.MOVE_EXCHANGE) or not hasattr(m, "labels"):
+                continue
+            if m.move_type == _lib.MOVE_DISPLACEMENT and getattr(m.operation, "op_code", -1) in (_lib.OP_ROTATION, _lib.OP_TRANSLATION, _lib.OP_TRANSLATION_ROTATION):
+                return True
+            lab = np.atleast_2d(np.asarray(m.labels))
+            for row in lab:
+                v = row[row >= 0]
+                if len(np.unique(v)) < len(v):
+                    return True
+        return False
 
     @staticmethod
     def _labels_version(move) -> tuple:

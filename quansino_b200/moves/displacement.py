@@ -101,7 +101,8 @@ class DisplacementMove(BaseMove):
             v = v[v >= 0]
             if len(v) and np.any(np.diff(v) < 0):
                 raise NotImplementedError(
-                    "with a molecular exchange move the labels of every move must not decrease with the atom index on the GPU path"
+                    "next to exchange moves, label groups are coded as runs of equal labels: the labels of every move must not decrease "
+                    "with the atom index on the GPU path (contiguous groups in index order)"
                 )
         return out
 

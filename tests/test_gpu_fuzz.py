@@ -199,10 +199,13 @@ def _gc_case(seed):
     c["p_disp"] = float(rng.uniform(0.3, 0.6))
     c["disp_step"] = float(rng.uniform(0.05, 0.25))
     c["n_attempts"] = 160
+    # label groups of the caller's own (pairs of neighbouring atoms share a label in BOTH moves): a displacement translates the
+    # pair, a deletion takes both atoms out -- also next to single-atom insertions (moves/exchange.py:127, moves/displacement.py:164)
+    c["pairs"] = bool(seed >= 16)
     return c
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(24))
 def test_random_grand_canonical_case_matches_oracle(cuda_lib, seed):
     from quansino_b200 import BatchedAtoms, LennardJones, operations
     from quansino_b200.mc import GrandCanonical
@@ -224,12 +227,17 @@ def test_random_grand_canonical_case_matches_oracle(cuda_lib, seed):
     molecular = c["kind"] == "molecule"
     mol = np.array(c["mol"]) if molecular else np.zeros((1, 3))
     lab_x = np.arange(n0) if c["deletable"] else np.full(n0, -1)
+    lab_d = np.arange(n0)
+    if c["pairs"]:
+        lab_d = lab_x = np.arange(n0) // 2
+        c["deletable"] = True
+    n_ex0 = int(lab_x.max() + 1) if c["deletable"] else 0
     atoms = BatchedAtoms(pos.copy(), cell, np.full(R, n0, dtype=np.int32), "Pt", pbc, calc)
     op = operations.TranslationRotation() if c["rotate"] else operations.Translation()
     mc = GrandCanonical(
         atoms, exchange_atoms=("Pt", mol), temperature=c["temperature"], chemical_potential=c["mu"],
-        number_of_exchange_particles=n0 if c["deletable"] else 0, max_cycles=c["n_attempts"], seed=777 + seed, trace=True, resync_interval=0,
-        default_displacement_move=DisplacementMove(np.arange(n0), operations.Ball(c["disp_step"])),
+        number_of_exchange_particles=n_ex0, max_cycles=c["n_attempts"], seed=777 + seed, trace=True, resync_interval=0,
+        default_displacement_move=DisplacementMove(lab_d.copy(), operations.Ball(c["disp_step"])),
     )  # fmt: skip
     if c["kind"] == "composite":
         exch = ExchangeMove(lab_x.copy())
@@ -250,16 +258,16 @@ def test_random_grand_canonical_case_matches_oracle(cuda_lib, seed):
     changes: dict[int, int] = {}
     for r in range(R):
         rep = capi.Replica(positions=pos[r].copy(), cell=cell, pbc=tuple(int(b) for b in pbc), n_atoms=n0, temperature=c["temperature"],
-                           mass=mass1, chemical_potential=c["mu"], exchange_mass=mass1 * len(mol), n_exchange=n0 if c["deletable"] else 0,
+                           mass=mass1, chemical_potential=c["mu"], exchange_mass=mass1 * len(mol), n_exchange=n_ex0,
                            accessible_volume=L**3, exchange_mol=mol if molecular else None)  # fmt: skip
         ld = np.full(n_max, -1, np.int32)
-        ld[:n0] = np.arange(n0)
+        ld[:n0] = lab_d
         lx = np.full(n_max, -1, np.int32)
         lx[:n0] = lab_x
         specs = [
             capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=c["disp_step"], probability=c["p_disp"], labels=ld),
             capi.MoveSpec(capi.MOVE_EXCHANGE, capi.OP_TRANSLATION_ROTATION if c["rotate"] else capi.OP_TRANSLATION, probability=1 - c["p_disp"],
-                          labels=lx, repeat=c["k"] if c["kind"] == "composite" else 1, bias_insert=c["bias"]),
+                          labels=lx, repeat=c["k"] if c["kind"] == "composite" else 1, bias_insert=c["bias"], chain=8 if c["pairs"] else 0),
         ]  # fmt: skip
         ref = capi.mc_run(par, rep, specs, 777 + seed, r, 0, 2 * c["n_attempts"])
         assert np.array_equal(tr["move"][r], ref["move"]), c
