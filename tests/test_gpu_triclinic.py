@@ -303,6 +303,23 @@ def test_forces_in_general_cells_match_oracle(cuda_lib, monkeypatch, build_lanes
     assert int(batch.status.max().item()) == 0
 
 
+def test_large_replica_in_a_general_cell(cuda_lib):
+    """2048 atoms (beyond the shared-memory kernels: energies come from the Verlet-list kernels) in a sheared cell: energy and forces
+    against the oracle's brute-force image enumeration."""
+    from quansino_b200 import EMT, BatchedAtoms, ReplicaBatch
+
+    pos, cells, n = _sheared(8, 1, seed=88, strength=0.05, stdev=0.03)
+    assert n == 2048
+    batch = ReplicaBatch(BatchedAtoms(pos.copy(), cells, np.full(1, n, dtype=np.int32), "Cu", (True, True, True), EMT()), EMT())
+    assert batch.triclinic
+    e = batch.energy_full().cpu().numpy()
+    f = batch.forces_full().cpu().numpy().transpose(0, 2, 1)
+    ref = capi.energy(emt_params("Cu"), pos[0], cells[0], (1, 1, 1), want_forces=True)
+    assert abs(e[0] - ref["energy"]) <= 1e-10 * abs(ref["energy"])
+    np.testing.assert_allclose(f[0], ref["forces"], rtol=1e-9, atol=1e-10)
+    assert int(batch.status.max().item()) == 0
+
+
 def test_hmc_and_force_bias_in_general_cells_match_oracle(cuda_lib):
     """Hamiltonian moves (integrators/displacement.py:52-81, mc/criteria.py:117-140) and ForceBias steps (mc/fbmc.py:202-251) in
     sheared cells, one shear per replica, against the oracle."""
