@@ -321,7 +321,7 @@ def pt_leg(device, dist, rank, world, n_temperatures=64, repeat=8, n_steps=100, 
         "ladder_is_permutation": bool(np.array_equal(np.sort(t_all), np.sort(temps_all))),
         "ladder_checksum": float(np.sum(t_all * w)),
         "energy_checksum": float(np.sum(e_all * w)),
-        "collective": "all_gather of 2 x 64 doubles per round (NCCL)" if world > 1 else "none (one rank)",
+        "collective": "one all_gather of the 64 (energy, temperature) pairs per round (NCCL)" if world > 1 else "none (one rank)",
     }
 
 
