@@ -432,9 +432,7 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
     const auto A0 = axis_of(C, 0), A1 = axis_of(C, 1), A2 = axis_of(C, 2);  // (unused for general cells)
     (void)p0; (void)p1; (void)p2; (void)A0; (void)A1; (void)A2;
     int cnt = 0, nq = 0;
-    // one tile: 32 candidate atoms.  The distance arithmetic of a tile is a chain of dependent instructions (load -> nearest image
-    // -> r^2 -> compare -> ballot -> slot); a warp is latency-bound (7 warps per scheduler each progress as if alone), so TWO
-    // tiles are in flight per iteration: their chains are independent and interleave (profiles/r2_a_rows.md, last section).
+    // one tile: 32 candidate atoms, measured (load -> nearest image -> r^2 -> compare) and filed (ballot -> slot)
     struct Tile {
         int j;
         bool valid, any, ex_o, ex_n;
@@ -494,13 +492,8 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
             *reinterpret_cast<uint2 *>(queue + nq + 2 * __popc(bq & lt)) = make_uint2(t.ex_o ? (unsigned)t.j : NOITEM, t.ex_n ? ((unsigned)t.j | 0x8000u) : NOITEM);
         nq += 2 * __popc(bq);
     };
-    int base = tile_first * 32;
-    for (; base + 32 * tile_step < n_scan; base += 64 * tile_step) {
-        const Tile ta = measure(base), tb = measure(base + 32 * tile_step);
-        file(ta);
-        file(tb);
-    }
-    if (base < n_scan) file(measure(base));
+    // (two tiles in flight per iteration were measured: -2.4 % on the same box, profiles/r2_a_rows.md; one tile at a time)
+    for (int base = tile_first * 32; base < n_scan; base += 32 * tile_step) file(measure(base));
     if (cnt > RV::CAPE) {
         status |= QMC_STATUS_LIST_OVERFLOW;
         cnt = RV::CAPE;

@@ -368,8 +368,7 @@ __device__ __forceinline__ Trial local_delta_move(const PotDev &pot, const Rep<L
     T.sig_i = warp_sum(acc.snew);
     double part = 0.0, e_i_lane = 0.0;
     double2 *slots = reinterpret_cast<double2 *>(&R.lr(0));
-    // one item = one touched atom (or, item n2, the moved atom): log + 2 exp, a long chain of dependent instructions.  While a
-    // second block of 32 items exists, TWO items per lane are in flight (independent chains interleave: the warp is latency-bound)
+    // one item = one touched atom (or, item n2, the moved atom): log + 2 exp
     auto item = [&](const int e, double &en_out, double2 &slot_out) {
         const bool nb = e < T.n2;
         const int j = nb ? R.l2(e) : i;
@@ -380,19 +379,12 @@ __device__ __forceinline__ Trial local_delta_move(const PotDev &pot, const Rep<L
         return en_out - R.eat(j);
     };
     int e0 = 0;
-    for (; e0 + 32 <= T.n2; e0 += 64) {  // (items e0 .. e0 + 63; the second block holds at least one item)
-        const int ea = e0 + lane, eb = e0 + 32 + lane;
-        const bool has_b = eb <= T.n2;
-        double en_a, en_b;
-        double2 sa, sb;
-        const double da = item(ea, en_a, sa), db = item(has_b ? eb : ea, en_b, sb);
-        part += da;
-        slots[ea] = sa;  // (ea < n2 here)
-        if (has_b) {
-            part += db;
-            if (eb < T.n2) slots[eb] = sb;
-            else e_i_lane = en_b;
-        }
+    for (; e0 + 32 <= T.n2; e0 += 32) {  // (two items in flight per lane were measured: slower, profiles/r2_a_rows.md)
+        const int e = e0 + lane;
+        double en;
+        double2 sv;
+        part += item(e, en, sv);
+        slots[e] = sv;
     }
     if (e0 <= T.n2) {  // a last, single block
         const int e = e0 + lane;
