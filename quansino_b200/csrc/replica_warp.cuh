@@ -421,10 +421,11 @@ __device__ __forceinline__ int scan_neighbours(const PotDev &pot, const RV &R, c
 // r2 >= cut_pre2 and evaluates to zero), so that one ballot / popc compaction serves both sides, the list of touched atoms
 // is simply l2[pos / 2] = j and the gather reads both terms with one 16-byte load.  The queue of second-image candidates
 // holds j only; the image flags are recomputed when the queue is expanded.
+// the two-sided scan in a general cell (see scan_both below for the slot layout)
 template <class RV, class CELL>
-__device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const CELL &C, const int lane, const unsigned lt, int n_scan,
+__device__ __forceinline__ int scan_both_tri(const PotDev &pot, const RV &R, const CELL &C, const int lane, const unsigned lt, int n_scan,
                                          int i_excl, const double po[3], const double pn[3], int &n2, int &xstart, int &status,
-                                         int tile_first = 0, int tile_step = 1) {
+                                         int tile_first, int tile_step) {
     constexpr bool TRACK = RV::EMT;
     static_assert(RV::CAPE % 2 == 0, "paired list slots need an even capacity");
     uint32_t *queue = R.queue();
@@ -566,6 +567,102 @@ __device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const C
     }
     __syncwarp();
     return cnt;
+}
+
+template <class RV, class CELL>
+__device__ __forceinline__ int scan_both(const PotDev &pot, const RV &R, const CELL &C, const int lane, const unsigned lt, int n_scan,
+                                         int i_excl, const double po[3], const double pn[3], int &n2, int &xstart, int &status,
+                                         int tile_first = 0, int tile_step = 1) {
+    if constexpr (CELL::TRI) {  // general cells: csrc/replica_warp.cuh scan_both_tri (the closest of <= 8 images owns the slot pair)
+        return scan_both_tri(pot, R, C, lane, lt, n_scan, i_excl, po, pn, n2, xstart, status, tile_first, tile_step);
+    } else {
+    // (diagonal cells: the code below is kept instruction for instruction -- it is the inner loop of the headline kernel)
+    constexpr bool TRACK = RV::EMT;
+    static_assert(RV::CAPE % 2 == 0, "paired list slots need an even capacity");
+    uint32_t *queue = R.queue();
+    const bool p0 = C.per(0), p1 = C.per(1), p2 = C.per(2);
+    const Axis A0 = C.axis(0), A1 = C.axis(1), A2 = C.axis(2);
+    int cnt = 0, nq = 0;
+    for (int base = tile_first * 32; base < n_scan; base += 32 * tile_step) {
+        const int j = base + lane;
+        const bool valid = j < n_scan && j != i_excl;
+        const int jc = valid ? j : 0;
+        const double xj = R.x(jc), yj = R.y(jc), zj = R.z(jc);
+        bool fo = false, fn = false;
+        const double dxo = axis_nearest_any(po[0], xj, A0, fo);
+        const double dyo = axis_nearest_any(po[1], yj, A1, fo);
+        const double dzo = axis_nearest_any(po[2], zj, A2, fo);
+        const double dxn = axis_nearest_any(pn[0], xj, A0, fn);
+        const double dyn = axis_nearest_any(pn[1], yj, A1, fn);
+        const double dzn = axis_nearest_any(pn[2], zj, A2, fn);
+        const double r2o = fma(dzo, dzo, fma(dyo, dyo, dxo * dxo));
+        const double r2n = fma(dzn, dzn, fma(dyn, dyn, dxn * dxn));
+        const bool in_o = valid && r2o < pot.cut_pre2, in_n = valid && r2n < pot.cut_pre2;
+        const bool any = in_o || in_n;
+        const unsigned b = __ballot_sync(FULL, any);
+        const int pos = min(cnt + 2 * __popc(b & lt), RV::CAPE - 2);
+        if (any) {
+            const double neg_r2o = __hiloint2double(__double2hiint(r2o) ^ (int)0x80000000, __double2loint(r2o));  // sign flip, integer pipe
+            *reinterpret_cast<double2 *>(&R.lr(pos)) = make_double2(neg_r2o, r2n);
+            if (TRACK) R.l2(pos >> 1) = (uint16_t)j;
+        }
+        if (TRACK && valid) R.pp(j) = any ? ((unsigned)pos | ((unsigned)(pos + 1) << 16)) : (NOPOS | (NOPOS << 16));
+        cnt += 2 * __popc(b);
+        // second images: only if the nearest image is inside (it is the closest of all images).  A flagged lane pushes two
+        // queue words (old side, new side; NOITEM for a side that is not flagged): at most 2 (n - 1) < QCAP words in total.
+        const bool exo = in_o && fo, exn = in_n && fn;
+        const unsigned bq = __ballot_sync(FULL, exo || exn);
+        if (exo || exn)
+            *reinterpret_cast<uint2 *>(queue + nq + 2 * __popc(bq & lt)) = make_uint2(exo ? (unsigned)j : NOITEM, exn ? ((unsigned)j | 0x8000u) : NOITEM);
+        nq += 2 * __popc(bq);
+    }
+    if (cnt > RV::CAPE) {
+        status |= QMC_STATUS_LIST_OVERFLOW;
+        cnt = RV::CAPE;
+    }
+    n2 = cnt >> 1;
+    xstart = cnt;
+    if (nq > 0) {
+        __syncwarp();
+        for (int q0 = 0; q0 < nq; q0 += 32) {
+            const int q = q0 + lane;
+            const unsigned item = q < nq ? queue[q] : NOITEM;
+            const bool has = item != NOITEM;
+            const int j = has ? (int)(item & 0x7FFFu) : 0;
+            const bool side = (item & 0x8000u) != 0u;  // false: old position, true: new position
+            unsigned fl = 0;
+            const double dx0 = axis_nearest(side ? pn[0] : po[0], R.x(j), A0, p0, fl, 1u);
+            const double dy0 = axis_nearest(side ? pn[1] : po[1], R.y(j), A1, p1, fl, 2u);
+            const double dz0 = axis_nearest(side ? pn[2] : po[2], R.z(j), A2, p2, fl, 4u);
+            const double dx1 = dx0 - copysign(A0.L, dx0), dy1 = dy0 - copysign(A1.L, dy0), dz1 = dz0 - copysign(A2.L, dz0);
+            unsigned c = fl & (0u - fl);  // first non-empty subset of fl
+            bool more = has && fl != 0u;
+            while (__any_sync(FULL, more)) {
+                const double dx = (c & 1u) ? dx1 : dx0, dy = (c & 2u) ? dy1 : dy0, dz = (c & 4u) ? dz1 : dz0;
+                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                const bool in = more && r2 < pot.cut_pre2;
+                const unsigned b = __ballot_sync(FULL, in);
+                const int pos = min(cnt + __popc(b & lt), RV::CAPE - 1);
+                if (in) {
+                    R.lr(pos) = side ? r2 : -r2;
+                    if (TRACK) R.xj(min(pos - xstart, RV::XCAPN - 1)) = (uint16_t)j;
+                }
+                cnt += __popc(b);
+                if (more) {
+                    if (c == fl) more = false;
+                    else c = ((c | (~fl & 7u)) + 1u) & fl;
+                }
+            }
+        }
+    }
+    if (cnt > RV::CAPE || (TRACK && cnt - xstart > RV::XCAPN)) {
+        status |= QMC_STATUS_LIST_OVERFLOW;
+        cnt = min(cnt, RV::CAPE);
+        if (TRACK && cnt - xstart > RV::XCAPN) cnt = xstart + RV::XCAPN;
+    }
+    __syncwarp();
+    return cnt;
+    }
 }
 
 // pairs: evaluate the list.  MODE 0 leaves the sigma_1 term of every nearest-image entry in lr[e], with the terms of

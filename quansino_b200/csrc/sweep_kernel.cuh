@@ -368,33 +368,17 @@ __device__ __forceinline__ Trial local_delta_move(const PotDev &pot, const Rep<L
     T.sig_i = warp_sum(acc.snew);
     double part = 0.0, e_i_lane = 0.0;
     double2 *slots = reinterpret_cast<double2 *>(&R.lr(0));
-    // one item = one touched atom (or, item n2, the moved atom): log + 2 exp
-    auto item = [&](const int e, double &en_out, double2 &slot_out) {
+    // one item = one touched atom (or, item n2, the moved atom): log + 2 exp (two items in flight per lane were measured: slower,
+    // profiles/r2_a_rows.md)
+    for (int e = lane; e <= T.n2; e += 32) {
         const bool nb = e < T.n2;
         const int j = nb ? R.l2(e) : i;
         const double2 t = nb ? slots[e] : make_double2(0.0, 0.0);
         const double sn = nb ? R.sig(j) + (t.y - t.x) : T.sig_i;
-        en_out = emt_embed(pot, sn);
-        slot_out = make_double2(sn, en_out);
-        return en_out - R.eat(j);
-    };
-    int e0 = 0;
-    for (; e0 + 32 <= T.n2; e0 += 32) {  // (two items in flight per lane were measured: slower, profiles/r2_a_rows.md)
-        const int e = e0 + lane;
-        double en;
-        double2 sv;
-        part += item(e, en, sv);
-        slots[e] = sv;
-    }
-    if (e0 <= T.n2) {  // a last, single block
-        const int e = e0 + lane;
-        if (e <= T.n2) {
-            double en;
-            double2 sv;
-            part += item(e, en, sv);
-            if (e < T.n2) slots[e] = sv;
-            else e_i_lane = en;
-        }
+        const double en = emt_embed(pot, sn);
+        part += en - R.eat(j);
+        if (nb) slots[e] = make_double2(sn, en);
+        else e_i_lane = en;
     }
     T.eat_i = __shfl_sync(FULL, e_i_lane, T.n2 & 31);
     // pair part: rows (i, j) and (j, i) change together: 2 * 0.5 * (es + eo) = 2 * neghalfv0overgamma2 * dsigma2
