@@ -55,6 +55,12 @@ class MonteCarlo:
         Keep the per-attempt trace of the last launch in ``last_trace`` (parity tests).
     """
 
+    def __class_getitem__(cls, item):
+        """``Isobaric[Move, Criteria](...)``, ``CellMove[OperationType, ContextType]``: the reference's classes are ``Generic``; the
+        parameters carry no run-time meaning here either."""
+        return cls
+
+
     default_criteria: ClassVar[dict[type, type]] = {BaseMove: BaseCriteria}
     default_context: ClassVar[type] = Context
     needs_momenta: ClassVar[bool] = False

@@ -19,6 +19,12 @@ from quansino_b200 import _lib
 class CompositeMove:
     """Mirror of ``quansino.moves.composite.CompositeMove``: a list of moves executed inside ONE attempt."""
 
+    def __class_getitem__(cls, item):
+        """``Isobaric[Move, Criteria](...)``, ``CellMove[OperationType, ContextType]``: the reference's classes are ``Generic``; the
+        parameters carry no run-time meaning here either."""
+        return cls
+
+
     move_type: int = -1
 
     def __init__(self, moves: list) -> None:

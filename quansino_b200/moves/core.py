@@ -14,6 +14,12 @@ from quansino_b200 import _lib
 class BaseMove:
     """Mirror of ``quansino.moves.core.BaseMove``."""
 
+    def __class_getitem__(cls, item):
+        """``Isobaric[Move, Criteria](...)``, ``CellMove[OperationType, ContextType]``: the reference's classes are ``Generic``; the
+        parameters carry no run-time meaning here either."""
+        return cls
+
+
     move_type: int = -1
 
     def __init__(self, operation=None, apply_constraints: bool = True) -> None:

@@ -10,6 +10,12 @@ from typing import Any
 class MoveStorage:
     """A move, its criteria and its scheduling parameters."""
 
+    def __class_getitem__(cls, item):
+        """``Isobaric[Move, Criteria](...)``, ``CellMove[OperationType, ContextType]``: the reference's classes are ``Generic``; the
+        parameters carry no run-time meaning here either."""
+        return cls
+
+
     move: Any
     criteria: Any
     interval: int

@@ -373,3 +373,21 @@ def test_composite_exchange_move_algebra_and_lowering():
     back = get_class(d["name"]).from_dict(d)
     assert isinstance(back, CompositeExchangeMove) and len(back) == 4 and back.bias_towards_insert == 0.25
     assert back.lower_chain()[0].repeat == 4
+
+
+def test_generic_subscripts_and_protocols_like_the_reference():
+    """The reference's drivers and moves are ``Generic`` (``Isobaric[Move, Criteria](...)`` in its examples,
+    ``examples/orb-v3_isobaric_bulk_cu.py:23``) and ``quansino.protocols`` holds the structural types (``protocols.py:24-190``)."""
+    from quansino_b200.integrators import Verlet
+    from quansino_b200.mc import Canonical, ForceBias, GrandCanonical, HamiltonianCanonical, Isobaric, Isotension
+    from quansino_b200.mc.criteria import IsobaricCriteria
+    from quansino_b200.moves import CellMove, CompositeMove, DisplacementMove
+    from quansino_b200.operations import Ball
+    from quansino_b200.protocols import Criteria, Integrator, Move, Operation, Serializable
+    from quansino_b200.utils.moves import MoveStorage
+
+    for cls in (Canonical, ForceBias, GrandCanonical, HamiltonianCanonical, Isobaric, Isotension, CellMove, CompositeMove, MoveStorage):
+        assert cls[Move, Criteria] is cls
+    assert isinstance(DisplacementMove(np.arange(3)), Move) and isinstance(IsobaricCriteria(), Criteria)
+    assert isinstance(Ball(0.1), Operation) and isinstance(Verlet(), Integrator) and isinstance(Ball(0.1), Serializable)
+    assert not isinstance(object(), Move)

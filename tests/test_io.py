@@ -5,6 +5,7 @@ bit-identically (the counterpart of the reference's tests/mc/test_canonical.py:2
 
 import io
 import json
+from pathlib import Path
 
 import numpy as np
 import pytest
@@ -253,3 +254,18 @@ def test_isotension_restart_in_a_general_cell(cuda_lib, tmp_path):
     out = again.download()
     assert np.array_equal(out.positions, ref.positions) and np.array_equal(out.cell, ref.cell)
     assert np.array_equal(again.batch.energy.cpu().numpy(), straight.batch.energy.cpu().numpy())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script", ["canonical_bulk_cu.py", "isobaric_bulk_cu.py", "grand_canonical_pt_np.py", "hmc_parallel_tempering.py"])
+def test_examples_run(cuda_lib, tmp_path, script):
+    """The ports of the reference's examples (examples/, the same driver / move / observer calls) run on the device."""
+    import os
+    import subprocess
+    import sys
+
+    root = Path(__file__).resolve().parents[1]
+    env = dict(os.environ, QUANSINO_EXAMPLE_STEPS="3", PYTHONPATH=str(root))
+    res = subprocess.run([sys.executable, str(root / "examples" / script)], cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.strip(), "the example printed nothing"
