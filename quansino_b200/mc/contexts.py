@@ -175,6 +175,18 @@ class ExchangeContext(DisplacementContext):
         }
 
 
+class HamiltonianContext(Context):
+    """Marker base of the contexts that carry momenta (``mc/contexts.py:175-213``)."""
+
+
+class HamiltonianDeformationContext(HamiltonianDisplacementContext, DeformationContext):
+    """``mc/contexts.py:276-278``."""
+
+
+class HamiltonianExchangeContext(HamiltonianDisplacementContext, ExchangeContext):
+    """``mc/contexts.py:388-390``."""
+
+
 class MultiContexts:
     """``mc/contexts.py:393-436`` keeps a list of contexts; the batched contexts above already hold every replica."""
 

@@ -167,3 +167,13 @@ class HamiltonianDisplacementMove(BaseMove):
         m.op, m.dt, m.n_steps = self.operation.lower()
         m.default_label = _lib.LABEL_NONE
         return m
+
+
+def __getattr__(name: str):
+    """``quansino.moves.displacement.CompositeDisplacementMove`` (``moves/displacement.py:363-455``) lives in
+    :mod:`quansino_b200.moves.composite` here; importing it from this module works as in the reference."""
+    if name == "CompositeDisplacementMove":
+        from quansino_b200.moves.composite import CompositeDisplacementMove
+
+        return CompositeDisplacementMove
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -35,6 +35,15 @@ def get_typed_class(class_name: str, expected_base: type | None = None) -> type:
     return cls
 
 
+def get_class_name(cls: type) -> str | None:
+    """The registered name of a class, or None (``registry.py:105-124``)."""
+    _ensure_builtin()
+    for name, registered in _class_registry.items():
+        if registered is cls:
+            return name
+    return None
+
+
 def get_class_registry() -> dict[str, type]:
     _ensure_builtin()
     return dict(_class_registry)

@@ -391,3 +391,36 @@ def test_generic_subscripts_and_protocols_like_the_reference():
     assert isinstance(DisplacementMove(np.arange(3)), Move) and isinstance(IsobaricCriteria(), Criteria)
     assert isinstance(Ball(0.1), Operation) and isinstance(Verlet(), Integrator) and isinstance(Ball(0.1), Serializable)
     assert not isinstance(object(), Move)
+
+
+def test_search_molecules_and_import_paths_of_the_reference():
+    """``utils/atoms.py:40-90`` (reference test ``tests/utils/test_atoms_utils.py``): bonded clusters share a label, sizes filter; and the
+    module paths a script written for quansino imports exist here too."""
+    import importlib
+    from types import SimpleNamespace
+
+    from quansino_b200.utils.atoms import search_molecules
+
+    # three water-like trimers and two lone atoms in a periodic box; one trimer straddles the cell boundary
+    mol = np.array([[0.0, 0.0, 0.0], [0.96, 0.0, 0.0], [-0.24, 0.93, 0.0]])
+    pos = np.vstack([mol + [2.0, 2.0, 2.0], mol + [6.0, 6.0, 2.0], mol + [9.8, 1.0, 5.0], [[5.0, 1.0, 8.0]], [[1.0, 7.0, 7.0]]]) % 10.0  # wrapped
+    atoms = SimpleNamespace(positions=pos, cell=np.eye(3) * 10.0, pbc=(True, True, True))
+    lab = search_molecules(atoms, 1.2)
+    assert list(lab) == [0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 4]
+    assert list(search_molecules(atoms, 1.2, required_size=3)) == [0, 0, 0, 1, 1, 1, 2, 2, 2, -1, -1]
+    assert list(search_molecules(atoms, 1.2, required_size=(1, 1))) == [-1] * 9 + [3, 4]
+    open_box = SimpleNamespace(positions=pos, cell=np.eye(3) * 10.0, pbc=(False, False, False))
+    assert len(set(search_molecules(open_box, 1.2))) == 6  # without periodicity the straddling trimer falls apart
+    assert list(search_molecules(atoms, [0.6] * 11)) == [0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 4]  # per-atom radii
+    for path, names in {
+        "quansino_b200.protocols": ["Move", "Criteria", "Operation", "Integrator"], "quansino_b200.type_hints": ["IntegerArray", "Stress", "Deformation"],
+        "quansino_b200.mc.driver": ["Driver", "SingleDriver", "MultiDriver"], "quansino_b200.io.file": ["ObserverManager"],
+        "quansino_b200.integrators.core": ["BaseIntegrator"], "quansino_b200.utils.strings": ["get_auto_header_format"],
+        "quansino_b200.moves.displacement": ["CompositeDisplacementMove", "DisplacementMove", "HamiltonianDisplacementMove"],
+        "quansino_b200.moves.exchange": ["CompositeExchangeMove", "ExchangeMove"], "quansino_b200.mc.isotension": ["Isotension"],
+        "quansino_b200.mc.contexts": ["HamiltonianContext", "HamiltonianDeformationContext", "HamiltonianExchangeContext", "MultiContexts"],
+        "quansino_b200.registry": ["get_class_name", "get_class", "register_class"],
+    }.items():  # fmt: skip
+        module = importlib.import_module(path)
+        for name in names:
+            assert getattr(module, name) is not None, (path, name)
