@@ -42,8 +42,8 @@ for step in mc.irun(steps):
 del mc.moves["default_displacement_move"]
 del mc.moves["default_cell_move"]
 
-hybrid_move = DisplacementMove(labels=np.arange(n)) * 8 + CellMove()  # (at most 16 displacements per composite attempt on the device)
-mc.max_cycles = n // 8
+hybrid_move = DisplacementMove(labels=np.arange(n)) * n + CellMove()  # every atom once, then the cell: one criteria evaluation
+mc.max_cycles = 1
 mc.add_move(hybrid_move, name="hybrid_move", criteria=IsobaricCriteria())
 for _ in mc.srun(steps):
     pass

@@ -38,7 +38,9 @@ extern "C" {
 #define QMC_MAX_FORCED 16 /* sum of minimum_count over the move table */
 #define QMC_MAX_MOVES 4
 #define QMC_NBR_SKIN_DEFAULT 0.7 /* Angstrom: Cu EMT rows stay within three 32-entry passes (profiles/r2_a_rows.md) */
-#define QMC_MAX_SUBMOVES 16 /* displacements one composite move may perform per attempt (random-stream layout) */
+#define QMC_MAX_SUBMOVES 16 /* sub-moves of one composite EXCHANGE move */
+#define QMC_MAX_COMPOSITE_DISPLACEMENTS 1024 /* displacements one composite move may perform per attempt (sub-move c >= 1 draws from
+                                                Philox blocks 32 + 2 (c - 1), 33 + 2 (c - 1) for c <= 16 and 0x8000 + 2 (c - 17), + 1 beyond) */
 
 enum qmc_error {
     QMC_OK = 0,

@@ -135,6 +135,10 @@ def case_composite(variant, seed, n_attempts):
         mc.add_move(DisplacementMove(labels, Ball(0.08)) + DisplacementMove(labels, Box(0.04)) + DisplacementMove(labels, Sphere(0.05)),
                     criteria=CanonicalCriteria(), name="mixed")  # fmt: skip
         spec = [[("Ball", 0.08, 1), ("Box", 0.04, 1), ("Sphere", 0.05, 1)]]
+    elif variant == "mul24":  # more sub-moves than the first block range holds (sub-moves 17 and up draw from blocks 0x8000 ...)
+        mc = Canonical(atoms, temperature=300.0, max_cycles=n_attempts, default_displacement_move=DisplacementMove(labels, Ball(0.1)))
+        mc.add_move(DisplacementMove(labels, Ball(0.03)) * 24, criteria=CanonicalCriteria(), name="many", probability=1.0)
+        spec = [[("Ball", 0.1, 1)], [("Ball", 0.03, 24)]]
     elif variant == "exhaust":  # only two movable atoms: the third and fourth sub-moves find no candidate
         labels = np.full(n, -1)
         labels[7] = 0
@@ -488,6 +492,7 @@ def main():
         "composite_mul": lambda: case_composite("mul", 5001, 120),
         "composite_add": lambda: case_composite("add", 5002, 80),
         "composite_exhaust": lambda: case_composite("exhaust", 5003, 40),
+        "composite_mul24": lambda: case_composite("mul24", 5005, 60),
         "composite_hybrid": lambda: case_hybrid(5004, 90, 3),
         "label_groups": lambda: case_groups(6001, 100),
         "forced_moves": lambda: case_forced(7001, 3),

@@ -22,7 +22,8 @@ Layout (DESIGN.md section "Random stream"):
     block 3: d0 = u_coin  (insert / delete, ``moves/exchange.py:148``)   d1 = u_swap (parallel tempering)
     block 4 + j / 2 (of the FIRST attempt of a step): forced-move placement draw j (``mc/core.py:335-337``)
     block 32 + 2 (c - 1), 33 + 2 (c - 1): sub-move c >= 1 of a CompositeDisplacementMove (``moves/displacement.py:392-431``;
-             c counts the sub-moves that draw, the first one uses the standard slots above):
+             c counts the sub-moves that draw, the first one uses the standard slots above; from c = 17 on the pair of blocks is
+             0x8000 + 2 (c - 17), + 1 -- ``submove_block``):
              (u_label, operation draw 0) and (operation draw 1, operation draw 2); operation draws beyond the third of a
              (sub-)move -- the further operations of a ``CompositeOperation`` (``Ball(0.1) + Box(0.05)``), the CellMove
              closing a hybrid ``CompositeMove`` after displacements drew -- are numbered e = 0, 1, ... through the attempt
@@ -49,6 +50,13 @@ BLOCK_FORCED = 4
 BLOCK_NORMALS = 16
 BLOCK_COMPOSITE = 32
 BLOCK_EXTRA = 64
+BLOCK_COMPOSITE_FAR = 0x8000  # sub-moves 17 and up (blocks 32 .. 63 are full, the extra draws start at 64)
+
+
+def submove_block(c: int) -> int:
+    """Block of (u_label, op draw 0) of drawing sub-move c >= 1 of a composite move; (op draw 1, op draw 2): the next block."""
+    return BLOCK_COMPOSITE + 2 * (c - 1) if c <= 16 else BLOCK_COMPOSITE_FAR + 2 * (c - 17)
+
 
 _MASK = 0xFFFFFFFF
 
@@ -151,9 +159,9 @@ class InjectedStream:
         if self._labels > 1:  # sub-move c = _labels - 1 >= 1 of a composite displacement move
             c = self._labels - 1
             if k == 0:
-                return self._pair(BLOCK_COMPOSITE + 2 * (c - 1))[1]
+                return self._pair(submove_block(c))[1]
             if k in (1, 2):
-                return self._pair(BLOCK_COMPOSITE + 2 * (c - 1) + 1)[k - 1]
+                return self._pair(submove_block(c) + 1)[k - 1]
             raise RuntimeError("more than three operation draws in one sub-move: not a supported operation")
         if k == 0:
             return self._pair(BLOCK_OP01)[0]
@@ -189,7 +197,7 @@ class InjectedStream:
         self._labels += 1
         self._op_draws = 0
         c = self._labels - 1
-        u = self._pair(BLOCK_SELECT_LABEL)[1] if c == 0 else self._pair(BLOCK_COMPOSITE + 2 * (c - 1))[0]
+        u = self._pair(BLOCK_SELECT_LABEL)[1] if c == 0 else self._pair(submove_block(c))[0]
         self.log.append(("label", u))
         return a[int(u * len(a))]
 

@@ -640,6 +640,10 @@ out:
     return rc;
 }
 
+/* Philox block of (u_label, op draw 0) of drawing sub-move c >= 1 of a composite move; (op draw 1, op draw 2) sit in the next block.
+ * Blocks 32 .. 63 serve sub-moves 1 .. 16; the attempt's extra draws start at block 64, so later sub-moves continue at 0x8000. */
+static uint32_t submove_block(int c) { return c <= 16 ? (uint32_t)(32 + 2 * (c - 1)) : 0x8000u + (uint32_t)(2 * (c - 17)); }
+
 int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32_t n_moves, uint64_t seed, uint32_t replica,
               uint64_t attempt_base, int32_t n_attempts, qo_trace_t *trace, int64_t counters[4]) {
     const int nmax = st->n_max;
@@ -768,8 +772,8 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                     if (c == 0) { ul = u_label; od[0] = opd[0]; od[1] = opd[1]; od[2] = opd[2]; }
                     else {
                         double e0[2], e1[2];
-                        qo_uniform_pair(seed, attempt, replica, (uint32_t)(32 + 2 * (c - 1)), e0);
-                        qo_uniform_pair(seed, attempt, replica, (uint32_t)(33 + 2 * (c - 1)), e1);
+                        qo_uniform_pair(seed, attempt, replica, submove_block(c), e0);
+                        qo_uniform_pair(seed, attempt, replica, submove_block(c) + 1u, e1);
                         ul = e0[0]; od[0] = e0[1]; od[1] = e1[0]; od[2] = e1[1];
                     }
                     ++c;
@@ -1044,7 +1048,7 @@ int qo_mc_run(const qo_potential_t *pot, qo_state_t *st, qo_move_t *moves, int32
                     double ul = u_label;
                     if (c > 0) {
                         double e0[2];
-                        qo_uniform_pair(seed, attempt, replica, (uint32_t)(32 + 2 * (c - 1)), e0);
+                        qo_uniform_pair(seed, attempt, replica, submove_block(c), e0);
                         ul = e0[0];
                     }
                     ++c;

@@ -14,6 +14,7 @@ LIB_PATH = Path(__import__("os").environ.get("QUANSINO_B200_LIB", _PKG / "libqua
 
 QMC_MAX_MOVES = 4
 QMC_MAX_SUBMOVES = 16
+QMC_MAX_COMPOSITE_DISPLACEMENTS = 1024
 LABEL_NONE = -(2**31)
 
 POT_EMT, POT_LJ = 0, 1

@@ -311,16 +311,16 @@ int qmc_sweep(const qmc_potential_t *pot, const qmc_batch_t *batch, const qmc_mo
         a.mv[m].labels = mv.labels;
     }
     if (!(tot > 0.0)) return fail(QMC_ERR_INVALID, "move probabilities sum to zero");
-    // Random stream layout: drawing sub-move c >= 1 of a composite uses Philox blocks 32 + 2 (c - 1) and 33 + 2 (c - 1); the extra
-    // draws (closing CellMove, CompositeOperation, TranslationRotation angles) start at block 64.  A composite with more than
-    // 16 drawing sub-moves would read the same numbers twice (and tie the volume change to the atom chosen): refuse it.
+    // Random stream layout: drawing sub-move c >= 1 of a composite uses Philox blocks 32 + 2 (c - 1), 33 + 2 (c - 1) up to c = 16 and
+    // 0x8000 + 2 (c - 17), + 1 beyond (csrc/sweep_kernel.cuh: submove_block); the extra draws (closing CellMove, CompositeOperation,
+    // TranslationRotation angles) start at block 64.
     for (int m = 0, drawn = 0; m < n_moves; ++m) {
         const bool head = m == 0 || !(moves[m - 1].chain & 1);
         if (head) drawn = 0;
         if (moves[m].type == QMC_MOVE_DISPLACEMENT) drawn += moves[m].repeat > 0 ? moves[m].repeat : 1;
-        if (drawn > QMC_MAX_SUBMOVES)
-            return fail(QMC_ERR_UNSUPPORTED, "move %d: a composite move may displace at most %d times per attempt on the GPU path "
-                        "(Philox blocks 32..63 hold the sub-move draws)", m, QMC_MAX_SUBMOVES);
+        if (drawn > QMC_MAX_COMPOSITE_DISPLACEMENTS)
+            return fail(QMC_ERR_UNSUPPORTED, "move %d: a composite move may displace at most %d times per attempt on the GPU path", m,
+                        QMC_MAX_COMPOSITE_DISPLACEMENTS);
     }
     if (a.n_forced > 0) {  // mc/core.py:161-165: the forced moves must fit into a step; steps are counted from attempt 0
         a.max_cycles = moves[0].max_cycles;

@@ -432,6 +432,13 @@ constexpr int F_EXCHANGE = 4;  // exchange moves
 constexpr int F_CELLVAR = 8;   // per-replica cells (kept in shared memory); otherwise one constant cell for all
 constexpr int F_COMPOSITE = 16;  // composite displacement moves (chains of move-table entries)
 
+// Philox block of the (u_label, op draw 0) pair of drawing sub-move c >= 1 of a composite move; (op draw 1, op draw 2) sit in the
+// next block.  Sub-moves 1 .. 16 use blocks 32 .. 63 (the layout of the golden traces); the extra draws start at block 64, so
+// sub-moves 17 and up continue at 0x8000 (`DisplacementMove * N + CellMove` with N = len(atoms) is the reference's own example).
+__host__ __device__ __forceinline__ uint32_t submove_block(int c) {
+    return c <= 16 ? (uint32_t)(32 + 2 * (c - 1)) : 0x8000u + (uint32_t)(2 * (c - 17));
+}
+
 // translation of one displacement sub-move from its three operation draws (operations/displacement.py:67-153)
 __device__ __forceinline__ void propose_translation(int op, double step, double o0, double o1, double o2, double t[3]) {
     if (op == QMC_OP_BALL) {
@@ -860,9 +867,9 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     const int na = (FEAT & F_LABELS) ? count_bits(R.labbits(mm), disp, LY::LABW) : count_available(slab, R.n, disp);  // `disp` stays empty for a plain CompositeMove
                     if (na == 0) continue;  // register_failure: nothing drawn
                     double ul = D.u_label, o0 = D.o0, o1 = D.o1, o2 = D.o2;
-                    if (n_drawn > 0) {  // drawing sub-move c >= 1: blocks 32 + 2 (c - 1) and 33 + 2 (c - 1)
+                    if (n_drawn > 0) {  // drawing sub-move c >= 1: blocks submove_block(c) and submove_block(c) + 1
                         double d0, d1;
-                        uniform_pair(key, attempt, grep, (uint32_t)(32 + 2 * (n_drawn - 1) + (lane & 1)), d0, d1);
+                        uniform_pair(key, attempt, grep, submove_block(n_drawn) + (uint32_t)(lane & 1), d0, d1);
                         ul = __shfl_sync(FULL, d0, 0);
                         o0 = __shfl_sync(FULL, d1, 0);
                         o1 = __shfl_sync(FULL, d0, 1);
@@ -1056,7 +1063,7 @@ __global__ void __launch_bounds__(Layout<POT, NS>::WARPS * 32, Layout<POT, NS>::
                     const int na = nu - n_del;  // setdiff1d(unique_labels, deleted_labels)
                     if (na <= 0) break;
                     double ul = D.u_label, unused;
-                    if (c > 0) uniform_pair(key, attempt, grep, 32u + 2u * (unsigned)(c - 1), ul, unused);
+                    if (c > 0) uniform_pair(key, attempt, grep, submove_block(c), ul, unused);
                     ++c;
                     int ord = (int)(ul * (double)na);
                     int at = 0;  // the ord-th run that is still available; keep del_ord sorted

@@ -305,8 +305,8 @@ def _dummy_batch(lib_mod, with_n_exchange: bool):
 
 def test_sweep_refuses_tables_the_kernels_would_mishandle():
     """Advisor findings of round 1, as C-ABI behaviour: (1) label tables / composites without batch.n_exchange (the instantiation
-    that serves them reads and writes it) are an invalid argument, not an illegal address; (2) a composite with more than 16
-    displacements per attempt would reuse Philox blocks (the extra draws start at block 64) and is refused."""
+    that serves them reads and writes it) are an invalid argument, not an illegal address; (2) the number of displacements of one
+    composite attempt is bounded by the random-stream layout (round 1: 16, where the sub-move blocks ran into the extra draws)."""
     import ctypes as C
 
     from quansino_b200 import EMT, _lib
@@ -319,13 +319,15 @@ def test_sweep_refuses_tables_the_kernels_would_mishandle():
     rc = lib.qmc_sweep(C.byref(pot), C.byref(_dummy_batch(_lib, False)), mv, 1, 1, 0, 10, None, None)
     assert rc == _lib.ERR_INVALID and b"n_exchange" in lib.qmc_last_error()
     mv[0].labels = None
-    mv[0].repeat = 17  # DisplacementMove * 17
+    # (2) sub-moves beyond the 16th have Philox blocks of their own (0x8000 ...) since the hybrid example of the reference needs
+    # len(atoms) of them; the limit is the one the header states
+    mv[0].repeat = _lib.QMC_MAX_COMPOSITE_DISPLACEMENTS + 1
     rc = lib.qmc_sweep(C.byref(pot), C.byref(_dummy_batch(_lib, True)), mv, 1, 1, 0, 10, None, None)
-    assert rc == _lib.ERR_UNSUPPORTED and b"Philox" in lib.qmc_last_error()
-    mv[0].repeat, mv[0].chain = 9, 3  # plain CompositeMove: 9 + 8 displacements, then a closing cell move would read block 64
-    mv[1].type, mv[1].op, mv[1].step, mv[1].repeat, mv[1].chain = _lib.MOVE_DISPLACEMENT, _lib.OP_BALL, 0.1, 8, 2
+    assert rc == _lib.ERR_UNSUPPORTED and b"displace at most" in lib.qmc_last_error()
+    mv[0].repeat, mv[0].chain = 1000, 3  # a chain counts as a whole
+    mv[1].type, mv[1].op, mv[1].step, mv[1].repeat, mv[1].chain = _lib.MOVE_DISPLACEMENT, _lib.OP_BALL, 0.1, 25, 2
     rc = lib.qmc_sweep(C.byref(pot), C.byref(_dummy_batch(_lib, True)), mv, 2, 1, 0, 10, None, None)
-    assert rc == _lib.ERR_UNSUPPORTED and b"Philox" in lib.qmc_last_error()
+    assert rc == _lib.ERR_UNSUPPORTED and b"displace at most" in lib.qmc_last_error()
 
 
 def test_neighbour_row_geometry_is_exported():
