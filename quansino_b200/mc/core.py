@@ -147,6 +147,13 @@ class MonteCarlo:
                     break
         if criteria is None:
             raise ValueError(f"No criteria provided, and no default criteria found for move type {type(move)}.")
+        # limits of the device path are reported where the move is registered, not at the first launch: the sweep kernels keep a
+        # replica in shared memory (<= 1024 atoms); only Hamiltonian moves and ForceBias run on larger replicas
+        if getattr(move, "move_type", None) in (_lib.MOVE_DISPLACEMENT, _lib.MOVE_CELL, _lib.MOVE_EXCHANGE) and self.batch.n_max > 1024:
+            raise NotImplementedError(
+                f"{type(move).__name__}: the sweep kernels hold a replica in shared memory, at most 1024 atoms per replica "
+                f"(this batch has n_max = {self.batch.n_max}); Hamiltonian moves and ForceBias have no such limit"
+            )
         self.moves[name] = MoveStorage(move=move, criteria=criteria, interval=interval, probability=probability, minimum_count=minimum_count)
         self._lowered = None
 

@@ -99,6 +99,8 @@ class ReplicaExchange:
                  swap: Callable[[torch.Tensor, torch.Tensor, int, int], torch.Tensor] = device_swap):  # fmt: skip
         self.energies, self.temperatures = energies, temperatures
         self.counts, self.rank, self.seed, self.swap = list(counts), int(rank), int(seed), swap
+        if sum(self.counts) > 1024 and swap is device_swap:  # (one CTA ranks the ladder: csrc/hmc_kernel.cuh pt_swap_kernel)
+            raise NotImplementedError("parallel tempering over more than 1024 replicas is not available on the GPU path")
         self.offset = sum(self.counts[: self.rank])
         self.round = 0
         self._accepted = torch.zeros((), dtype=torch.int64, device=energies.device)  # summed on the device: no host sync per round
