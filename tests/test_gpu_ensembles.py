@@ -625,3 +625,70 @@ def test_c_abi_exchange_and_reduction_single_rank(cuda_lib):
     v = torch.arange(5, dtype=torch.float64, device="cuda")
     _lib.check(lib.qmc_reduce_observables(None, v.data_ptr(), 5, None))
     assert torch.equal(v.cpu(), torch.arange(5, dtype=torch.float64))
+
+
+def test_host_entry_point_with_a_shared_label_array(cuda_lib):
+    """qmc_sweep_host with exchange moves: a displacement and an exchange move that share ONE host label array (uploaded once,
+    re-labelled once per accepted exchange) give exactly what two equal arrays give, and what the oracle gives."""
+    import ctypes as C
+
+    from quansino_b200 import LennardJones, _lib
+    from quansino_b200.systems import octahedron, rattle
+
+    R, n_max, n_attempts, mu = 3, 64, 600, -0.5
+    pos0, cell = octahedron("Pt", 4, 10.0)
+    n = len(pos0)
+    pos = np.zeros((R, n_max, 3))
+    for r in range(R):
+        pos[r, :n] = rattle(pos0, 0.02, 600 + r)
+    pot = LennardJones(sigma=2.5, epsilon=0.1).lower("Pt")
+    volume = float(np.prod(np.diag(cell)))
+
+    def run(shared: bool):
+        hp = np.ascontiguousarray(pos.transpose(0, 2, 1))
+        hc = np.ascontiguousarray(np.broadcast_to(cell.reshape(9), (R, 9)))
+        n_atoms, n_ex = np.full(R, n, np.int32), np.full(R, n, np.int32)
+        energy, temp = np.zeros(R), np.full(R, 300.0)
+        counters, status = np.zeros((R, 4, 3), np.int64), np.zeros(R, np.int32)
+        lab_a = np.full((R, n_max), -1, np.int32)
+        lab_a[:, :n] = np.arange(n)
+        lab_b = lab_a if shared else lab_a.copy()
+        acc, nat = np.zeros((R, n_attempts), np.int8), None
+        b = _lib.Batch()
+        b.n_replicas, b.n_max, b.replica_offset = R, n_max, 0
+        b.pbc = (C.c_int32 * 3)(0, 0, 0)
+        b.pos, b.cell, b.n_atoms, b.energy, b.temperature = (a.ctypes.data for a in (hp, hc, n_atoms, energy, temp))
+        b.counters, b.status, b.n_exchange = counters.ctypes.data, status.ctypes.data, n_ex.ctypes.data
+        b.mass = b.exchange_mass = 195.084
+        b.chemical_potential, b.accessible_volume = mu, volume
+        mv = (_lib.Move * 2)()
+        mv[0].type, mv[0].op, mv[0].step, mv[0].probability, mv[0].default_label = _lib.MOVE_DISPLACEMENT, _lib.OP_BALL, 0.1, 0.5, _lib.LABEL_NONE
+        mv[1].type, mv[1].op, mv[1].probability, mv[1].bias_insert, mv[1].default_label = _lib.MOVE_EXCHANGE, _lib.OP_TRANSLATION, 0.5, 0.5, _lib.LABEL_NONE
+        mv[0].labels, mv[1].labels = lab_a.ctypes.data, lab_b.ctypes.data
+        tr = _lib.Trace()
+        tr.accepted = acc.ctypes.data
+        _lib.check(cuda_lib.qmc_sweep_host(C.byref(pot), C.byref(b), mv, 2, 41, 0, n_attempts, C.byref(tr)))
+        assert not status.any()
+        return hp, n_atoms, n_ex, lab_a, lab_b, acc, energy
+
+    a, s = run(False), run(True)
+    for x, y in zip(a, s):
+        assert np.array_equal(x, y)
+    par = LJParams(sigma=2.5, epsilon=0.1)
+    hp, n_atoms, n_ex, lab_a, lab_b, acc, energy = s
+    changed = 0
+    for r in range(R):
+        rep = capi.Replica(positions=pos[r].copy(), cell=cell, pbc=(0, 0, 0), n_atoms=n, temperature=300.0, mass=195.084, chemical_potential=mu,
+                           exchange_mass=195.084, n_exchange=n, accessible_volume=volume)  # fmt: skip
+        ld = np.full(n_max, -1, np.int32)
+        ld[:n] = np.arange(n)
+        lx = ld.copy()
+        specs = [capi.MoveSpec(capi.MOVE_DISPLACEMENT, capi.OP_BALL, step=0.1, probability=0.5, labels=ld),
+                 capi.MoveSpec(capi.MOVE_EXCHANGE, capi.OP_TRANSLATION, probability=0.5, labels=lx)]  # fmt: skip
+        ref = capi.mc_run(par, rep, specs, 41, r, 0, n_attempts)
+        assert np.array_equal(acc[r], ref["accepted"])
+        assert n_atoms[r] == rep.n_atoms and n_ex[r] == rep.n_exchange
+        assert np.array_equal(lab_a[r, : rep.n_atoms], ld[: rep.n_atoms]) and np.array_equal(lab_b[r, : rep.n_atoms], lx[: rep.n_atoms])
+        assert abs(energy[r] - rep.last_energy) <= 1e-10 * max(1.0, abs(rep.last_energy))
+        changed += int((np.diff(np.concatenate([[n], ref["n_atoms"]])) != 0).sum())
+    assert changed > 5  # insertions and deletions did happen (and every deletion re-labels the shared table once)
