@@ -567,7 +567,7 @@ def run_native(args):
             "unit": "TFLOP/s",
             "frac": achieved_tflops / (fp64_peak / 1e12),
             "traffic": NCU_DRAM_BYTES_PER_LAUNCH if R == 4096 and world == 1 else None,
-            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch, ncu --set full of the same command (profiles/r2_v_sweep_kernel_ncu_raw.csv: 18.12 MB read, 0 written back before the kernel ends -- the 126 MB L2 holds the write-back); bytes per launch, algorithmic 35.7e6 (replica state read once and written once per launch, whatever the number of sweeps)",
+            "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one sweep_kernel launch, ncu --set full of the same command (profiles/r2_aq_sweep_kernel_ncu_raw.csv: 18.11 MB read, 0 written back before the kernel ends -- the 126 MB L2 holds the write-back); bytes per launch, algorithmic 35.7e6 (replica state read once and written once per launch, whatever the number of sweeps)",
             "peak_source": "register-resident DFMA loop measured in this process (qmc_fp64_peak); nominal 37.2",
             "flop_per_attempt": flop_per_attempt,
             "pair_evals_per_attempt": p_per_attempt,
