@@ -73,6 +73,7 @@ struct HmcArgs {
     qmc_trace_t tr;
     double *forces_out;
     int lpa;   // lanes per atom (power of two <= 32)
+    int one_wave;  // the batch fits the GPU as one wave of 1024 threads per SM: pass 2 runs in its 64-register instantiation
     double skin;  // Verlet-list skin (hmc_skin())
     int build_lanes;  // lanes per atom of the list build (1: hmc_build_kernel)
     int cur;   // position buffer holding the current positions
@@ -755,8 +756,10 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass1_kernel(const __grid_con
 }
 
 // ---- pass 2: forces + velocity-Verlet update --------------------------------------------------------------------
-template <int POT, bool TRI>
-__global__ void __launch_bounds__(HMC_THREADS) hmc_pass2_kernel(const __grid_constant__ HmcArgs a) {
+// MINB = 8 bounds the kernel to 64 registers: 1024 resident threads per SM instead of 768, which lets a small batch (8 x 2048
+// atoms x 8 lanes) run as ONE wave instead of one and a tail (profiles/r2_aj_hmc_small_batch.md)
+template <int POT, bool TRI, int MINB = 1>
+__global__ void __launch_bounds__(HMC_THREADS, MINB) hmc_pass2_kernel(const __grid_constant__ HmcArgs a) {
     __shared__ double red[32];
     const int r = blockIdx.y, nmax = a.b.n_max, n = a.b.n_atoms[r];
     const int lpa = a.lpa, sub = threadIdx.x & (lpa - 1);
@@ -926,7 +929,15 @@ inline int hmc_pick_lpa(const qmc_batch_t &b) {
     const long long atoms = (long long)b.n_replicas * b.n_max;
     int lpa = 1;
     while (lpa < 32 && atoms * lpa < 148LL * 1024) lpa <<= 1;
+    // small batches: with half as many lanes the whole batch is resident at once (1024 threads per SM at 64 registers) -- one wave
+    // beats 1.7 waves of pass 1 and 2.3 of pass 2
+    if (lpa >= 8 && atoms * (lpa / 2) <= 148LL * 1024 && !(std::getenv("QMC_HMC_ONE_WAVE") && std::atoi(std::getenv("QMC_HMC_ONE_WAVE")) == 0)) lpa /= 2;
     return lpa;
+}
+
+inline int hmc_one_wave(const qmc_batch_t &b, int lpa) {
+    if (const char *e = std::getenv("QMC_HMC_ONE_WAVE")) return std::atoi(e) != 0;
+    return lpa >= 4 && (long long)b.n_replicas * b.n_max * lpa <= 148LL * 1024;
 }
 
 // Lanes per atom of the list build: replicas of a few hundred atoms come in large batches (one thread per atom fills the GPU);
@@ -971,7 +982,8 @@ inline void hmc_force_eval(HmcArgs &a, cudaStream_t s) {
         }
     } else if (a.pot.kind == QMC_POT_EMT) {
         hmc_pass1_kernel<QMC_POT_EMT, false><<<gl, HMC_THREADS, 0, s>>>(a);
-        hmc_pass2_kernel<QMC_POT_EMT, false><<<gl, HMC_THREADS, 0, s>>>(a);
+        if (a.one_wave) hmc_pass2_kernel<QMC_POT_EMT, false, 8><<<gl, HMC_THREADS, 0, s>>>(a);
+        else hmc_pass2_kernel<QMC_POT_EMT, false><<<gl, HMC_THREADS, 0, s>>>(a);
     } else {
         hmc_pass1_kernel<QMC_POT_LJ, false><<<gl, HMC_THREADS, 0, s>>>(a);
         hmc_pass2_kernel<QMC_POT_LJ, false><<<gl, HMC_THREADS, 0, s>>>(a);
@@ -988,6 +1000,7 @@ inline int hmc_forces(const PotDev &pot, const qmc_batch_t &b, double *forces, v
     hmc_carve(pot, b, workspace, &a.w);
     a.forces_out = forces;
     a.lpa = hmc_pick_lpa(b);
+    a.one_wave = hmc_one_wave(b, a.lpa);
     a.skin = hmc_skin();
     a.build_lanes = hmc_pick_build_lanes(b);
     a.cur = 0;
@@ -1093,6 +1106,7 @@ inline int hmc_run(const PotDev &pot, const qmc_batch_t &b, double dt, int n_ste
     a.tr = tr;
     a.n_attempts = n_attempts;
     a.lpa = hmc_pick_lpa(b);
+    a.one_wave = hmc_one_wave(b, a.lpa);
     a.skin = hmc_skin();
     a.build_lanes = hmc_pick_build_lanes(b);
     const int N = b.n_max;
