@@ -366,3 +366,19 @@ def test_seed_zero_is_a_seed_and_tables_are_relowered(cuda_lib):
             tr = capi.mc_run(par, rep, [capi.MoveSpec(capi.MOVE_DISPLACEMENT, op, step=step, labels=lab)], 0, r, k * n, n)
         assert np.array_equal(runs[0][1][r], tr["accepted"])
         np.testing.assert_allclose(runs[0][0][r], rep.positions, rtol=0, atol=1e-12)
+
+
+def test_device_emt_reproduces_ases_atomization_tutorial(cuda_lib):
+    """ASE's documentation prints 5.10 / 0.44 / 9.76 eV for the N atom, the N2 molecule (d = 1.1 A) and the atomization energy with
+    `EMT()`: the device kernels (sweep-path energy kernel and the Verlet-list force kernels) give the same digits."""
+    from quansino_b200 import EMT, BatchedAtoms, ReplicaBatch
+
+    pos = np.zeros((2, 2, 3))
+    pos[0, 1, 2] = 1.1  # replica 0: the molecule; replica 1: one atom
+    atoms = BatchedAtoms(pos, np.eye(3) * 10.0, np.array([2, 1], dtype=np.int32), "N", (False, False, False), EMT())
+    batch = ReplicaBatch(atoms, EMT())
+    e = batch.energy_full().cpu().numpy()
+    assert f"{e[1]:.2f}" == "5.10" and f"{e[0]:.2f}" == "0.44" and f"{2 * e[1] - e[0]:.2f}" == "9.76"
+    assert abs(e[0] - 0.440343573035614) <= 1e-12
+    f = batch.forces_full().cpu().numpy()
+    assert abs(batch.energy.cpu().numpy()[0] - e[0]) <= 1e-12 and abs(f[0, 2, 0] + f[0, 2, 1]) <= 1e-12 and abs(f[0, 2, 1] + 3.25179997) < 1e-6

@@ -222,3 +222,22 @@ def test_expm_of_symmetric_matrices_matches_scipy():
     np.testing.assert_array_equal(capi.expm_sym3(np.zeros((3, 3))), np.eye(3))
     d = np.diag([0.3, -0.2, 0.1])
     np.testing.assert_allclose(capi.expm_sym3(d), np.diag(np.exp([0.3, -0.2, 0.1])), rtol=0, atol=1e-16)
+
+
+def test_emt_reproduces_the_numbers_of_ases_atomization_tutorial():
+    """A second outside anchor for the ASE-owned arithmetic ("parity unpinned"): ASE's own documentation
+    (tutorial "Atomization energy", `N2` with `EMT()`: d = 1.1 A) prints `Nitrogen atom energy: 5.10 eV`, `Nitrogen molecule energy:
+    0.44 eV`, `Atomization energy: 9.76 eV`.  The restatements give 5.1 (an atom without neighbours: -E0), 0.440344 and 9.759656 --
+    the printed digits -- with the cutoff built from the largest s0 of the WHOLE table, the gamma normalisations and the theta
+    weight all taking part in the molecule's energy."""
+    from oracle.potentials import emt_energy_forces, emt_params
+
+    par = emt_params("N")
+    box = np.eye(3) * 10.0
+    atom = emt_energy_forces(np.zeros((1, 3)), box, (False,) * 3, par)["energy"]
+    pos = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 1.1]])
+    molecule = emt_energy_forces(pos, box, (False,) * 3, par)["energy"]
+    assert f"{atom:.2f}" == "5.10" and f"{molecule:.2f}" == "0.44" and f"{2 * atom - molecule:.2f}" == "9.76"
+    c = capi.energy(par, pos, box, (0, 0, 0), want_forces=True)
+    assert abs(c["energy"] - molecule) <= 1e-13 and abs(c["forces"][0, 2] + c["forces"][1, 2]) <= 1e-13
+    assert abs(molecule - 0.440343573035614) <= 1e-12  # (the value both restatements agree on, for regression)
