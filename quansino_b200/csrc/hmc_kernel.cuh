@@ -756,8 +756,9 @@ __global__ void __launch_bounds__(HMC_THREADS) hmc_pass1_kernel(const __grid_con
 }
 
 // ---- pass 2: forces + velocity-Verlet update --------------------------------------------------------------------
-// MINB = 8 bounds the kernel to 64 registers: 1024 resident threads per SM instead of 768, which lets a small batch (8 x 2048
-// atoms x 8 lanes) run as ONE wave instead of one and a tail (profiles/r2_aj_hmc_small_batch.md)
+// MINB = 8 bounds the kernel to 64 registers: 1024 resident threads per SM instead of 512, which lets a small batch (8 x 2048
+// atoms x 4 lanes) run as ONE wave instead of one and a tail (profiles/r2_aj_hmc_small_batch.md); MINB = 5 (96 registers, 640
+// threads) is the general choice for EMT in diagonal cells
 template <int POT, bool TRI, int MINB = 1>
 __global__ void __launch_bounds__(HMC_THREADS, MINB) hmc_pass2_kernel(const __grid_constant__ HmcArgs a) {
     __shared__ double red[32];
@@ -982,8 +983,10 @@ inline void hmc_force_eval(HmcArgs &a, cudaStream_t s) {
         }
     } else if (a.pot.kind == QMC_POT_EMT) {
         hmc_pass1_kernel<QMC_POT_EMT, false><<<gl, HMC_THREADS, 0, s>>>(a);
+        // five CTAs per SM (96 registers instead of the unbounded 106, no spills): +1.6 % on C5 and its tempering loop, +1 % on
+        // ForceBias against 4 / 6 / 7 / 8 CTAs in one call on one box (profiles/r2_av_hmc_pass_ncu.md)
         if (a.one_wave) hmc_pass2_kernel<QMC_POT_EMT, false, 8><<<gl, HMC_THREADS, 0, s>>>(a);
-        else hmc_pass2_kernel<QMC_POT_EMT, false><<<gl, HMC_THREADS, 0, s>>>(a);
+        else hmc_pass2_kernel<QMC_POT_EMT, false, 5><<<gl, HMC_THREADS, 0, s>>>(a);
     } else {
         hmc_pass1_kernel<QMC_POT_LJ, false><<<gl, HMC_THREADS, 0, s>>>(a);
         hmc_pass2_kernel<QMC_POT_LJ, false><<<gl, HMC_THREADS, 0, s>>>(a);
