@@ -19,6 +19,7 @@ pytestmark = pytest.mark.gpu
 
 # QMC_FUZZ_SCALE=4 runs four times as many seeds per family (a one-off hunt; the default keeps the suite short)
 SCALE = max(1, int(os.environ.get("QMC_FUZZ_SCALE", "1")))
+OFFSET = int(os.environ.get("QMC_FUZZ_OFFSET", "0"))  # first seed of a hunt (0: the committed seeds)
 BAR = 6.241509125883258e-07
 OPS = {"Ball": capi.OP_BALL, "Box": capi.OP_BOX, "Sphere": capi.OP_SPHERE}
 CELL_OPS = {"Isotropic": capi.OP_ISOTROPIC, "Anisotropic": capi.OP_ANISOTROPIC, "Shape": capi.OP_SHAPE}
@@ -158,7 +159,7 @@ def _run_oracle(c, pos, cells, counts, pbc, n, n_max, kinds_in_order, r):
     return rep, tr, ld, lx
 
 
-@pytest.mark.parametrize("seed", range(28 * SCALE))
+@pytest.mark.parametrize("seed", range(OFFSET, OFFSET + 28 * SCALE))
 def test_random_case_matches_oracle(cuda_lib, seed):
     c = _case(seed)
     pos, cells, counts, pbc, n, n_max = _system(c)
@@ -209,7 +210,7 @@ def _gc_case(seed):
     return c
 
 
-@pytest.mark.parametrize("seed", range(24 * SCALE))
+@pytest.mark.parametrize("seed", range(OFFSET, OFFSET + 24 * SCALE))
 def test_random_grand_canonical_case_matches_oracle(cuda_lib, seed):
     from quansino_b200 import BatchedAtoms, LennardJones, operations
     from quansino_b200.mc import GrandCanonical
@@ -312,7 +313,7 @@ def _misc_case(seed):
     return c
 
 
-@pytest.mark.parametrize("seed", range(18 * SCALE))
+@pytest.mark.parametrize("seed", range(OFFSET, OFFSET + 18 * SCALE))
 def test_random_groups_hybrid_hmc_case_matches_oracle(cuda_lib, seed):
     from quansino_b200 import EMT, BatchedAtoms, LennardJones, operations
     from quansino_b200.integrators import Verlet
